@@ -1,0 +1,90 @@
+"""ctypes binding of libsnb200.so (the C ABI declared in include/snb200.h).
+
+The product path has no CPU fallback: if the shared library is missing or a kernel reports an
+error, a RuntimeError is raised.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_int, c_int32, c_int64, c_longlong, c_size_t, c_void_p, POINTER, Structure
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libsnb200.so")
+
+
+class SnSssStage(Structure):
+    _fields_ = [(n, c_int32) for n in ("in_off", "in_dim", "out_off", "out_dim", "d_in", "d_out",
+                                      "off_ys", "off_yu", "off_ss", "off_su", "pack_off", "k")] + [("reserved", c_int32 * 4)]
+
+
+class SnSssChunk(Structure):
+    _fields_ = [(n, c_int32) for n in ("kk_begin", "kk_end", "col0", "ncols", "row0", "nrows", "second_visit", "reserved")]
+
+
+class SnSssPlan(Structure):
+    _fields_ = [(n, c_int32) for n in ("nb_states", "input_dim", "output_dim", "rows_pad", "k_pad", "d_pad", "nchunks",
+                                      "chunk_in_max", "chunk_out_max", "chunk_len_max", "nparams", "reserved")] + \
+               [("stages", c_void_p), ("chunks", c_void_p)]
+
+
+_lib = None
+
+
+def _declare(lib):
+    lib.sn_version.restype = c_int
+    lib.sn_last_error_string.restype = c_char_p
+    lib.sn_launch_count.restype = c_longlong
+    lib.sn_reset_launch_count.restype = None
+    P = POINTER(SnSssPlan)
+    lib.sn_sss_packed_floats.restype = c_size_t
+    lib.sn_sss_packed_floats.argtypes = [P]
+    lib.sn_sss_ckpt_floats.restype = c_size_t
+    lib.sn_sss_ckpt_floats.argtypes = [P, c_int64]
+    lib.sn_sss_pack.restype = c_int
+    lib.sn_sss_pack.argtypes = [P, c_void_p, c_void_p, c_void_p]
+    lib.sn_sss_forward.restype = c_int
+    lib.sn_sss_forward.argtypes = [P, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p]
+    lib.sn_sss_backward.restype = c_int
+    lib.sn_sss_backward.argtypes = [P, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_int64, c_int64, c_void_p]
+    for name, fn in _EXTRA_DECLS:
+        fn(lib)
+
+
+_EXTRA_DECLS = []  # filled by the other layer modules' declarations below
+
+
+def lib():
+    """The loaded library; raises if it has not been built (python -m structurednets_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libsnb200.so is missing (%s): build it with `python -m structurednets_b200.build`; "
+                "structurednets_b200 has no CPU or PyTorch fallback" % LIB_PATH)
+        _lib = ctypes.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().sn_last_error_string()
+        raise RuntimeError("libsnb200 %s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def launch_count() -> int:
+    return int(lib().sn_launch_count())
+
+
+def reset_launch_count():
+    lib().sn_reset_launch_count()

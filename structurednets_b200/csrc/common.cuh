@@ -1,0 +1,49 @@
+// Shared helpers for libsnb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "snb200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libsnb200 is written for sm_100a (B200) only"
+#endif
+
+namespace snb {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+inline cudaStream_t as_stream(sn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define SN_CHECK_ARG(cond, ...)                 \
+    do {                                        \
+        if (!(cond)) {                          \
+            snb::set_error(__VA_ARGS__);        \
+            return 1;                           \
+        }                                       \
+    } while (0)
+
+#define SN_CHECK_CUDA(expr)                                                                    \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            snb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return 2;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+#define SN_CHECK_LAUNCH(name)                                                                  \
+    do {                                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess) {                                                               \
+            snb::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));           \
+            return 3;                                                                          \
+        }                                                                                      \
+        snb::count_launch();                                                                   \
+    } while (0)
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+}  // namespace snb

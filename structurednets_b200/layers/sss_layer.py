@@ -1,0 +1,317 @@
+"""SSS (sequentially semiseparable / time-varying state-space) layer on B200.
+
+Drop-in for ``structurednets.layers.sss_layer.SSSLayer`` (reference layers/sss_layer.py:35-137): same
+constructor, same ``ParameterList`` names ``A..G`` and shapes (so the same ``state_dict`` keys
+``bias, A.0 .. G.{n-1}``), same ``statespace_dim`` budget rule and the same module-level helpers
+(``get_nb_parameters``, ``get_max_statespace_dim``, ``standard_dims_in_dims_out_computation``).
+``forward`` + autograd backward run in the hand-written kernels of ``csrc/sss.cu`` through the C ABI
+(``sn_sss_pack / sn_sss_forward / sn_sss_backward``, include/snb200.h); there is no CPU path.
+"""
+import ctypes
+import pickle
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from structurednets_b200 import _lib
+from structurednets_b200.layers.flat_params import FlatParamsMixin
+from structurednets_b200.layers.layer_helpers import get_random_glorot_uniform_matrix
+from structurednets_b200.layers.structured_layer import StructuredLayer
+
+SSS_CHUNK_LEN = 8  # stages between two state checkpoints (forward saves them, backward recomputes inside)
+
+
+def get_nb_parameters(optim_mat_shape: tuple, statespace_dim: int, nb_states: int) -> int:
+    """Upper-bound parameter count, reference layers/sss_layer.py:15-24."""
+    dims_in, dims_out = standard_dims_in_dims_out_computation(input_size=optim_mat_shape[1], output_size=optim_mat_shape[0], nb_states=nb_states)
+    nb_params = 0
+    for state_i, (inp_dim, out_dim) in enumerate(zip(dims_in, dims_out)):
+        if state_i > 0 and state_i < len(dims_in) - 1:
+            nb_params += 2 * statespace_dim * statespace_dim
+        nb_params += 2 * inp_dim * statespace_dim
+        nb_params += 2 * statespace_dim * out_dim
+        nb_params += inp_dim * out_dim
+    return int(nb_params)
+
+
+def has_less_parameters_than_allowed(optim_mat: np.ndarray, nb_params_share: float, nb_states: int, state_space_dim: int) -> bool:
+    return get_nb_parameters(optim_mat_shape=optim_mat.shape, statespace_dim=state_space_dim, nb_states=nb_states) < int(nb_params_share * optim_mat.size)
+
+
+def get_max_statespace_dim(optim_mat: np.ndarray, nb_params_share: float, nb_states: int) -> int:
+    """Largest statespace_dim whose upper-bound count fits the budget, reference layers/sss_layer.py:26-33."""
+    state_space_dim = 0
+    while has_less_parameters_than_allowed(optim_mat=optim_mat, nb_params_share=nb_params_share, nb_states=nb_states, state_space_dim=state_space_dim + 1):
+        state_space_dim += 1
+    return state_space_dim
+
+
+def standard_dims_in_dims_out_computation(input_size: int, output_size: int, nb_states: int):
+    """reference layers/sss_layer.py:139-146"""
+    dims_in = int(input_size / nb_states) * np.ones((nb_states,), dtype='int32')
+    dims_in[:(input_size - np.sum(dims_in))] += 1
+    assert np.sum(dims_in) == input_size, "Sum over input dimensions does not match the input size"
+    dims_out = int(output_size / nb_states) * np.ones((nb_states,), dtype='int32')
+    dims_out[:(output_size - np.sum(dims_out))] += 1
+    assert np.sum(dims_out) == output_size, "Sum over output dimensions does not match the output size"
+    return dims_in, dims_out
+
+
+def _identify_system(T_full: np.ndarray, dims_in, dims_out, statespace_dim: int):
+    """tvsclib path of the reference constructor (layers/sss_layer.py:66-68); tvsclib is a git-only,
+    unpinned dependency (reference setup.py:33)."""
+    try:
+        from tvsclib.mixed_system import MixedSystem
+        from tvsclib.toeplitz_operator import ToeplitzOperator
+        from tvsclib.system_identification_svd import SystemIdentificationSVD
+    except ImportError as e:
+        raise ImportError(
+            "SSSLayer: building the state-space realisation from a dense matrix needs tvsclib "
+            "(git+https://github.com/MatthiasKi/tvsclib), which is not installed; pass "
+            "initial_system_approx=<mixed system> instead") from e
+    T_operator = ToeplitzOperator(T_full, dims_in, dims_out)
+    S = SystemIdentificationSVD(toeplitz=T_operator, max_states_local=statespace_dim)
+    return MixedSystem(S)
+
+
+class _SSSFunction(torch.autograd.Function):
+    """fwd: sn_sss_forward (saves chunk-entry state checkpoints); bwd: sn_sss_backward accumulating
+    straight into the layer's flat gradient buffer (every ``p.grad`` is a view of it)."""
+
+    @staticmethod
+    def forward(ctx, U, anchor, layer):
+        B = U.shape[0]
+        plan = layer._device_plan(U.device)
+        packed = layer._packed_params(plan)
+        y = torch.empty((B, layer.output_dim), dtype=torch.float32, device=U.device)
+        need_grad = anchor is not None and anchor.requires_grad and torch.is_grad_enabled()
+        ckpt = None
+        if need_grad:
+            nck = _lib.lib().sn_sss_ckpt_floats(ctypes.byref(plan["struct"]), B)
+            ckpt = torch.empty(max(int(nck), 1), dtype=torch.float32, device=U.device)
+        bias = layer.bias if layer.use_bias else None
+        rc = _lib.lib().sn_sss_forward(ctypes.byref(plan["struct"]), _lib.ptr(packed), _lib.ptr(U), U.stride(0),
+                                       _lib.ptr(y), y.stride(0), _lib.ptr(bias), _lib.ptr(ckpt), B, _lib.stream_ptr())
+        _lib.check(rc, "sn_sss_forward")
+        ctx.layer = layer
+        ctx.plan = plan
+        ctx.save_for_backward(U, ckpt, packed)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        layer, plan = ctx.layer, ctx.plan
+        U, ckpt, packed = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("SSSLayer: gradient w.r.t. the input features is not implemented "
+                               "(the reference training loop never requests it, training_helpers.py:34)")
+        grad_y = grad_y.contiguous()
+        if grad_y.dtype != torch.float32:
+            grad_y = grad_y.float()
+        g = layer._prepare_grad_accumulation()
+        gbias = g[:layer.output_dim] if (layer.use_bias and layer.bias.requires_grad) else None
+        rc = _lib.lib().sn_sss_backward(ctypes.byref(plan["struct"]), _lib.ptr(packed), _lib.ptr(U), U.stride(0),
+                                        _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(ckpt), _lib.ptr(g), _lib.ptr(gbias),
+                                        None, 0, U.shape[0], _lib.stream_ptr())
+        _lib.check(rc, "sn_sss_backward")
+        return None, None, None
+
+
+class SSSLayer(FlatParamsMixin, StructuredLayer):
+    def __init__(self, input_dim: int, output_dim: int, nb_params_share: float, use_bias=True, initial_weight_matrix=None,
+                 initial_bias=None, nb_states=None, initial_system_approx=None, use_gpu=False):
+        super(SSSLayer, self).__init__(input_dim=input_dim, output_dim=output_dim, nb_params_share=nb_params_share,
+                                       use_bias=use_bias, initial_weight_matrix=initial_weight_matrix, initial_bias=initial_bias)
+
+        if nb_states is None:
+            nb_states = int(min(input_dim, output_dim) / 2)
+        assert nb_states > 0, "Nb states must be positive"
+
+        assert initial_weight_matrix is None or initial_system_approx is None, "Either pass an initial weight matrix or the initial system approximation - not both"
+        if initial_system_approx is not None:
+            assert len(initial_system_approx.dims_in) == nb_states, "The given system approximation does not match the expected number of states (dims_in)"
+            assert len(initial_system_approx.dims_out) == nb_states, "The given system approximation does not match the expected number of states (dims_out)"
+
+        self.input_dim = input_dim
+        self.nb_states = nb_states
+
+        self.init_state_matrices(nb_params_share=nb_params_share, initial_weight_matrix=initial_weight_matrix, initial_system_approx=initial_system_approx)
+        self.use_gpu = use_gpu
+        self._flatten_parameters()
+
+    def init_state_matrices(self, nb_params_share: float, initial_weight_matrix=None, initial_system_approx=None):
+        """reference layers/sss_layer.py:54-91"""
+        if initial_weight_matrix is None:
+            T_full = get_random_glorot_uniform_matrix(shape=(self.output_dim, self.input_dim))
+        else:
+            T_full = initial_weight_matrix
+
+        self.statespace_dim = get_max_statespace_dim(T_full, nb_params_share=nb_params_share, nb_states=self.nb_states)
+
+        if has_less_parameters_than_allowed(optim_mat=T_full, nb_params_share=nb_params_share, nb_states=self.nb_states, state_space_dim=self.statespace_dim):
+            self.dims_in, self.dims_out = standard_dims_in_dims_out_computation(input_size=self.input_dim, output_size=self.output_dim, nb_states=self.nb_states)
+
+            if initial_system_approx is None:
+                system_approx = _identify_system(T_full, self.dims_in, self.dims_out, self.statespace_dim)
+            else:
+                system_approx = pickle.loads(pickle.dumps(initial_system_approx))
+
+            self.initial_weight_matrix = system_approx.to_matrix()
+
+            A = [stage.A_matrix for stage in system_approx.causal_system.stages]
+            B = [stage.B_matrix for stage in system_approx.causal_system.stages]
+            C = [stage.C_matrix for stage in system_approx.causal_system.stages]
+            D = [stage.D_matrix for stage in system_approx.causal_system.stages]
+            E = [stage.A_matrix for stage in system_approx.anticausal_system.stages]
+            F = [stage.B_matrix for stage in system_approx.anticausal_system.stages]
+            G = [stage.C_matrix for stage in system_approx.anticausal_system.stages]
+
+            mk = lambda mats: nn.ParameterList([nn.Parameter(torch.tensor(np.asarray(m)).float(), requires_grad=True) for m in mats])
+            self.A, self.B, self.C, self.D, self.E, self.F, self.G = mk(A), mk(B), mk(C), mk(D), mk(E), mk(F), mk(G)
+
+            self.state_matrices_initialized = True
+
+    def get_input_index_range_according_to_state(self, state_i):
+        return range(np.sum(self.dims_in[:state_i]), np.sum(self.dims_in[:state_i + 1]))
+
+    def get_output_index_range_according_to_state(self, state_i):
+        return range(np.sum(self.dims_out[:state_i]), np.sum(self.dims_out[:state_i + 1]))
+
+    # ---- device plan --------------------------------------------------------------------------
+    def _on_reflatten(self):
+        self.__dict__["_dev_plan"] = None
+        self.__dict__["_dev_packed"] = None
+        self.__dict__["_dev_packed_version"] = None
+
+    def _param_offsets(self):
+        """{(list name, k): offset in the flat buffer}; flat order = named_parameters() order."""
+        offs = {}
+        params = self._flat_param_list()
+        by_id = {id(p): o for p, o in zip(params, self.__dict__["_flat_offsets"])}
+        for name in "ABCDEFG":
+            for k, p in enumerate(getattr(self, name)):
+                offs[(name, k)] = by_id[id(p)]
+        return offs
+
+    def build_host_plan(self, chunk_len: int = SSS_CHUNK_LEN):
+        """Stage and chunk tables of include/snb200.h (sn_sss_stage / sn_sss_chunk) as numpy int32."""
+        n = self.nb_states
+        offs = self._param_offsets()
+        in_off = np.concatenate([[0], np.cumsum(self.dims_in)]).astype(np.int64)
+        out_off = np.concatenate([[0], np.cumsum(self.dims_out)]).astype(np.int64)
+        stages = np.zeros((2, n, 16), dtype=np.int32)
+        for k in range(n):
+            a, b, c, d = self.A[k], self.B[k], self.C[k], self.D[k]
+            e, f, g = self.E[k], self.F[k], self.G[k]
+            assert a.shape[1] == c.shape[1] and a.shape[0] == b.shape[0], "inconsistent causal stage shapes"
+            assert e.shape[1] == g.shape[1] and e.shape[0] == f.shape[0], "inconsistent anticausal stage shapes"
+            stages[0, k, :12] = [in_off[k], self.dims_in[k], out_off[k], self.dims_out[k], a.shape[1], a.shape[0],
+                                 offs[("C", k)], offs[("D", k)], offs[("A", k)], offs[("B", k)], 0, k]
+            kk = n - 1 - k
+            stages[1, kk, :12] = [in_off[k], self.dims_in[k], out_off[k], self.dims_out[k], e.shape[1], e.shape[0],
+                                  offs[("G", k)], -1, offs[("E", k)], offs[("F", k)], 0, k]
+        for d in range(2):
+            for kk in range(n):
+                if kk > 0:
+                    assert stages[d, kk, 4] == stages[d, kk - 1, 5], "state dimensions of consecutive stages do not chain"
+                else:
+                    assert stages[d, 0, 4] == 0, "the first stage of a sweep must have an empty incoming state"
+        rows = stages[:, :, 3] + stages[:, :, 5]
+        ks = stages[:, :, 1] + stages[:, :, 4]
+        ru4 = lambda v: int(max(4, (int(v) + 3) // 4 * 4))
+        rows_pad, k_pad = ru4(rows.max()), ru4(ks.max())
+        d_pad = ru4(max(stages[:, :, 4].max(), stages[:, :, 5].max()))
+        blk = 2 * rows_pad * k_pad
+        for d in range(2):
+            for kk in range(n):
+                stages[d, kk, 10] = (d * n + kk) * blk
+        # chunks: never straddle the first-visit / second-visit switch
+        h = n // 2
+        first_visit = [h, n - h]
+        chunks = [[], []]
+        for d in range(2):
+            bounds = []
+            for lo, hi, second in ((0, first_visit[d], 0), (first_visit[d], n, 1)):
+                s = lo
+                while s < hi:
+                    e_ = min(s + chunk_len, hi)
+                    bounds.append((s, e_, second))
+                    s = e_
+            for (s, e_, second) in bounds:
+                st = stages[d, s:e_]
+                col0 = int(st[:, 0].min())
+                ncols = int(st[:, 1].sum())
+                row0 = int(st[:, 2].min())
+                nrows = int(st[:, 3].sum())
+                chunks[d].append([s, e_, col0, ncols, row0, nrows, second, 0])
+        assert len(chunks[0]) == len(chunks[1])
+        chunks = np.asarray(chunks, dtype=np.int32)
+        meta = dict(nb_states=n, input_dim=self.input_dim, output_dim=self.output_dim, rows_pad=rows_pad, k_pad=k_pad,
+                    d_pad=d_pad, nchunks=chunks.shape[1], chunk_in_max=int(chunks[:, :, 3].max()),
+                    chunk_out_max=int(max(1, chunks[:, :, 5].max())), chunk_len_max=int((chunks[:, :, 1] - chunks[:, :, 0]).max()),
+                    nparams=int(self.__dict__["_flat_total"]))
+        return stages, chunks, meta
+
+    def _device_plan(self, device):
+        self._ensure_flat()
+        plan = self.__dict__.get("_dev_plan")
+        if plan is not None and plan["device"] == device:
+            return plan
+        stages, chunks, meta = self.build_host_plan()
+        st_dev = torch.from_numpy(stages.reshape(-1)).to(device)
+        ch_dev = torch.from_numpy(chunks.reshape(-1)).to(device)
+        struct = _lib.SnSssPlan()
+        for k, v in meta.items():
+            setattr(struct, k, v)
+        struct.stages = st_dev.data_ptr()
+        struct.chunks = ch_dev.data_ptr()
+        plan = dict(device=device, struct=struct, stages=st_dev, chunks=ch_dev, meta=meta)
+        self.__dict__["_dev_plan"] = plan
+        self.__dict__["_dev_packed"] = None
+        return plan
+
+    def _packed_params(self, plan):
+        """Per-stage re-laid-out copy of the parameters; refreshed when any parameter changed
+        (views share the flat buffer's version counter)."""
+        flat = self.__dict__["_flat"]
+        packed = self.__dict__.get("_dev_packed")
+        if packed is None or packed.device != flat.device:
+            n = _lib.lib().sn_sss_packed_floats(ctypes.byref(plan["struct"]))
+            packed = torch.empty(int(n), dtype=torch.float32, device=flat.device)
+            self.__dict__["_dev_packed"] = packed
+            self.__dict__["_dev_packed_version"] = None
+        if self.__dict__.get("_dev_packed_version") != flat._version:
+            rc = _lib.lib().sn_sss_pack(ctypes.byref(plan["struct"]), _lib.ptr(flat), _lib.ptr(packed), _lib.stream_ptr())
+            _lib.check(rc, "sn_sss_pack")
+            self.__dict__["_dev_packed_version"] = flat._version
+        return packed
+
+    # ---- forward ------------------------------------------------------------------------------
+    def forward(self, U):
+        if hasattr(self, "state_matrices_initialized") and self.state_matrices_initialized:
+            self._require_cuda(U, "SSSLayer.forward")
+            assert U.dim() == 2 and U.shape[1] == self.input_dim, "SSSLayer expects a (batch, input_dim) input"
+            self._ensure_flat()
+            flat = self.__dict__["_flat"]
+            if flat.device != U.device:
+                raise RuntimeError("SSSLayer: module parameters are on %s but the input is on %s" % (flat.device, U.device))
+            if U.dtype != torch.float32:
+                U = U.float()
+            if U.stride(1) != 1:
+                U = U.contiguous()
+            anchor = self.__dict__.get("_dev_anchor")
+            if anchor is None or anchor.device != U.device:
+                anchor = torch.zeros(1, device=U.device, requires_grad=True)
+                self.__dict__["_dev_anchor"] = anchor
+            any_grad = torch.is_grad_enabled() and any(p.requires_grad for p in (self.A[0], self.D[0]))
+            return _SSSFunction.apply(U, anchor if any_grad else None, self)
+        else:
+            # the budget admits not even a block-diagonal D: reference returns zeros (sss_layer.py:130-131)
+            return torch.zeros((U.shape[0], self.output_dim), device=U.device)
+
+    def get_nb_parameters(self) -> int:
+        if hasattr(self, "state_matrices_initialized") and self.state_matrices_initialized:
+            return get_nb_parameters(optim_mat_shape=(self.output_dim, self.input_dim), statespace_dim=self.statespace_dim, nb_states=self.nb_states)
+        else:
+            return 0
