@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the structured-layer hot path (BASELINE.json metric: structured-layer fwd+bwd samples/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sss|lr|psm|hmat|ldr] [--impl ours|reference]
+
+A "step" is one forward + backward (parameter gradients only, as training_helpers.py:141-144 produces)
+of the layer over one batch of synthetic features that are already resident in HBM; for N > 1 the
+batch is sharded over the ranks (data parallel, strong scaling: the global batch is fixed) and the step
+ends with one NCCL all-reduce of the flat gradient buffer.  Prints ONE JSON line (rank 0).
+
+`--impl reference` times the reference's CPU path (oracle port: the same torch CPU ops the reference
+layer issues, autograd backward) on the box's host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import numpy as np
+import torch
+
+HBM_FALLBACK_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
+BF16_FALLBACK_TFLOPS = 1590.0
+FP32_FMA_TFLOPS_NOMINAL = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4: 148 SMs x 128 FMA lanes x 2 flop x max clock
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=float(p["hbm_gbs"]), bf16_tflops=float(p["bf16_tflops"]),
+                    bf16_tflops_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=HBM_FALLBACK_GBS, bf16_tflops=BF16_FALLBACK_TFLOPS, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+# ----------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------
+class SSSWorkload:
+    """BASELINE config C5 (= C1's layer): SSSLayer 4096 -> 1000, 500 stages, statespace dim 16, fp32,
+    global batch 65536 sharded over the ranks."""
+    name = "sss"
+    dtype = "f32"
+    input_dim, output_dim, nb_states, statespace_dim = 4096, 1000, 500, 16
+    global_batch = 65536
+    cpu_sample_batch = 256
+    bytes_per_sample_kernel = 4 * (4096 + 1000)          # one kernel (fwd: read x, write y; bwd: read gy, re-read x)
+    bytes_per_sample = 2 * bytes_per_sample_kernel        # 40 768 B / sample fwd+bwd
+    flop_per_sample = 2277504
+    bound = "hbm"
+
+    def describe(self):
+        return dict(workload="C5: SSS 4096->1000, 500 stages, statespace 16, fp32 fwd+bwd (param grads), global batch 65536",
+                    global_batch=self.global_batch, timed_inputs="resident in HBM; 1 GiB feature matrix per step >> 126 MB L2")
+
+    def system(self):
+        from structurednets_b200.synth import random_mixed_system
+        return random_mixed_system(self.input_dim, self.output_dim, self.nb_states, self.statespace_dim, seed=5000)
+
+    def make_layer(self, device):
+        from structurednets_b200.layers.sss_layer import SSSLayer
+        layer = SSSLayer(self.input_dim, self.output_dim, 0.105, nb_states=self.nb_states, initial_system_approx=self.system())
+        assert layer.statespace_dim == self.statespace_dim
+        return layer.to(device)
+
+    def make_inputs(self, batch, device, seed):
+        g = torch.Generator(device=device).manual_seed(seed)
+        x = torch.rand((batch, self.input_dim), device=device, generator=g) * 2 - 1
+        gy = (torch.rand((batch, self.output_dim), device=device, generator=g) * 2 - 1) / batch
+        labels = torch.randint(0, self.output_dim, (batch,), device=device, generator=g)
+        return x, gy, labels
+
+    def cpu_step_fn(self, batch):
+        """The reference's CPU path for this workload (oracle port of sss_layer.py:99-131 + autograd)."""
+        from oracle import layers_cpu as O
+        sysm = self.system()
+        f32 = lambda m: torch.tensor(np.asarray(m)).float().requires_grad_(True)
+        cs, acs = sysm.causal_system.stages, sysm.anticausal_system.stages
+        lists = [[f32(s.A_matrix) for s in cs], [f32(s.B_matrix) for s in cs], [f32(s.C_matrix) for s in cs],
+                 [f32(s.D_matrix) for s in cs], [f32(s.A_matrix) for s in acs], [f32(s.B_matrix) for s in acs],
+                 [f32(s.C_matrix) for s in acs]]
+        bias = torch.zeros(self.output_dim, requires_grad=True)
+        rng = np.random.default_rng(5000)
+        x = torch.tensor(rng.uniform(-1, 1, size=(batch, self.input_dim)).astype(np.float32))
+        gy = torch.tensor(rng.uniform(-1, 1, size=(batch, self.output_dim)).astype(np.float32)) / batch
+        params = [p for l in lists for p in l] + [bias]
+
+        def step():
+            for p in params:
+                p.grad = None
+            y = O.sss_forward(x, *lists, bias, sysm.dims_in, sysm.dims_out)
+            y.backward(gy)
+        return step
+
+
+WORKLOADS = {"sss": SSSWorkload}
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (recipe's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thr.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def time_cpu_baseline(wl, steps, warmup, budget_s=25.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = wl.cpu_sample_batch
+    step = wl.cpu_step_fn(B)
+    for _ in range(warmup):
+        step()
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s and len(times) >= 2:
+            break
+    med = float(np.median(times))
+    return dict(value=B / med, unit="samples/s", cores=cores, kind="port",
+                sample="%d steps of batch %d (median %.1f ms/step) of the same layer on %s" % (len(times), B, med * 1e3, cpu_model())), med, len(times)
+
+
+# ----------------------------------------------------------------------------------------------
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, med, n = time_cpu_baseline(wl, steps=max(args.steps, 2), warmup=max(args.warmup, 1), budget_s=120.0)
+    cfg = wl.describe()
+    cfg["sample_batch"] = wl.cpu_sample_batch
+    line = dict(metric="structured-layer fwd+bwd samples/sec", value=base["value"], unit="samples/s", n_gpus=args.gpus, steps=n,
+                warmup=max(args.warmup, 1), ms_per_step=med * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None,
+                dtype=wl.dtype, data="synthetic", config=cfg, impl="reference", cpu_baseline=base,
+                e2e=dict(value=base["value"], unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def run_ours(args, wl):
+    import torch.distributed as dist
+    from structurednets_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    n_gpus = world
+
+    peaks = measured_peaks()
+    local_batch = wl.global_batch // n_gpus
+    layer = wl.make_layer(device)
+    x, gy, labels = wl.make_inputs(local_batch, device, seed=5000 + rank)
+    flat_grad = layer.flat_grad()
+    stream = torch.cuda.current_stream()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def step(rec=None):
+        layer.zero_flat_grad()
+        if rec is not None:
+            rec[0].record(stream)
+        y = layer(x)
+        if rec is not None:
+            rec[1].record(stream)
+        y.backward(gy)
+        if rec is not None:
+            rec[2].record(stream)
+        if n_gpus > 1:
+            dist.all_reduce(flat_grad)
+        return y
+
+    def barrier():
+        if n_gpus > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    _lib.reset_launch_count()
+    recs = [(ev(), ev(), ev()) for _ in range(args.steps)]
+    t_begin, t_end = ev(), ev()
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        t_begin.record(stream)
+        for i in range(args.steps):
+            step(recs[i])
+        t_end.record(stream)
+        barrier()
+    launches = _lib.launch_count()
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    if n_gpus > 1:
+        t = torch.tensor([elapsed_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = wl.global_batch / (ms_per_step * 1e-3)
+    fwd_ms = float(np.mean([r[0].elapsed_time(r[1]) for r in recs]))
+    bwd_ms = float(np.mean([r[1].elapsed_time(r[2]) for r in recs]))
+
+    # ---- end to end through the module API with host buffers (pinned H2D + loss + D2H of the loss) ----
+    e2e_steps = max(3, min(args.steps, 5))
+    x_host = torch.empty((local_batch, wl.input_dim), dtype=torch.float32, pin_memory=True)
+    x_host.copy_(x)
+    labels_host = labels.cpu().pin_memory()
+    loss_fn = torch.nn.CrossEntropyLoss()
+
+    def e2e_step():
+        xd = x_host.to(device, non_blocking=True)
+        ld = labels_host.to(device, non_blocking=True)
+        layer.zero_flat_grad()
+        loss = loss_fn(layer(xd), ld)
+        loss.backward()
+        if n_gpus > 1:
+            dist.all_reduce(flat_grad)
+        return float(loss.item())     # device -> host read of the step's result
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if n_gpus > 1:
+        t = torch.tensor([e2e_s], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = dict(value=wl.global_batch / e2e_s, unit="samples/s", h2d_bytes_per_step=int(x_host.numel() * 4 + labels_host.numel() * 8),
+               d2h_bytes_per_step=4, steps=e2e_steps, ms_per_step=e2e_s * 1e3)
+
+    if rank == 0:
+        dom_ms, dom_name = (bwd_ms, "sss_bwd_kernel") if bwd_ms >= fwd_ms else (fwd_ms, "sss_fwd_kernel")
+        achieved = wl.bytes_per_sample_kernel * local_batch / (dom_ms * 1e-3) / 1e9
+        roofline = dict(bound=wl.bound, kernel=dom_name, achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
+                        frac=achieved / peaks["hbm_gbs"], traffic=None, peak_source=peaks["source"],
+                        launch_ms=dom_ms, fwd_ms=fwd_ms, bwd_ms=bwd_ms,
+                        step_hbm_frac=wl.bytes_per_sample * local_batch / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                        fp32_fma_tflops=wl.flop_per_sample * local_batch / (ms_per_step * 1e-3) / 1e12,
+                        fp32_fma_frac_of_nominal=wl.flop_per_sample * local_batch / (ms_per_step * 1e-3) / 1e12 / FP32_FMA_TFLOPS_NOMINAL)
+        cpu_base = None
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            cpu_base, _, _ = time_cpu_baseline(wl, steps=20, warmup=2, budget_s=20.0)
+        cfg = wl.describe()
+        cfg.update(local_batch=local_batch, parallelism="dp%d" % n_gpus, l2_policy="inputs larger than L2 (no flush needed)")
+        line = dict(metric="structured-layer fwd+bwd samples/sec", value=value, unit="samples/s", n_gpus=n_gpus, steps=args.steps,
+                    warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None,
+                    dtype=wl.dtype, data="synthetic", config=cfg, clocks=clocks.summary(), e2e=e2e, gpu_launches=int(launches),
+                    roofline=roofline, cpu_baseline=cpu_base)
+        print(json.dumps(line))
+    if n_gpus > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sss", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]()
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

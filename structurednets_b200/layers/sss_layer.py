@@ -85,7 +85,7 @@ class _SSSFunction(torch.autograd.Function):
         plan = layer._device_plan(U.device)
         packed = layer._packed_params(plan)
         y = torch.empty((B, layer.output_dim), dtype=torch.float32, device=U.device)
-        need_grad = anchor is not None and anchor.requires_grad and torch.is_grad_enabled()
+        need_grad = anchor is not None   # (grad mode is always off inside Function.forward)
         ckpt = None
         if need_grad:
             nck = _lib.lib().sn_sss_ckpt_floats(ctypes.byref(plan["struct"]), B)
