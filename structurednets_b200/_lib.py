@@ -26,6 +26,11 @@ class SnSssPlan(Structure):
                [("stages", c_void_p), ("chunks", c_void_p)]
 
 
+class SnPsmFactor(Structure):
+    _fields_ = [("rows", c_int32), ("cols", c_int32), ("nnz", c_int32), ("reserved", c_int32)] + \
+               [(n, c_void_p) for n in ("rowptr", "colidx", "perm", "cscptr", "rowidx", "permc", "vals", "grad_vals")]
+
+
 _lib = None
 
 
@@ -46,6 +51,35 @@ def _declare(lib):
     lib.sn_sss_backward.restype = c_int
     lib.sn_sss_backward.argtypes = [P, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_int64, c_int64, c_void_p]
+    i64, i32, vp = c_int64, c_int, c_void_p
+    lib.sn_lr_forward_f32.restype = c_int
+    lib.sn_lr_forward_f32.argtypes = [vp, i64, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp]
+    lib.sn_lr_backward_f32.restype = c_int
+    lib.sn_lr_backward_f32.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp]
+    lib.sn_hmat_forward.restype = c_int
+    lib.sn_hmat_forward.argtypes = [vp, i32, vp, vp, i64, vp, i64, vp, i64, i32, i32, vp]
+    lib.sn_hmat_backward.restype = c_int
+    lib.sn_hmat_backward.argtypes = [vp, i32, vp, vp, i64, vp, i64, vp, vp, i64, i32, i32, vp]
+    PF = POINTER(SnPsmFactor)
+    lib.sn_psm_forward.restype = c_int
+    lib.sn_psm_forward.argtypes = [PF, i32, vp, i64, vp, i64, vp, i64, i32, i32, vp]
+    lib.sn_psm_backward.restype = c_int
+    lib.sn_psm_backward.argtypes = [PF, i32, vp, i64, vp, i64, vp, i64, i32, i32, vp]
+    f64 = ctypes.c_double
+    lib.sn_ldr_workspace_doubles.restype = c_size_t
+    lib.sn_ldr_workspace_doubles.argtypes = [i32, i32]
+    lib.sn_ldr_build_weight.restype = c_int
+    lib.sn_ldr_build_weight.argtypes = [i32, i32, vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, f64, vp, POINTER(c_int), vp]
+    lib.sn_ldr_backward.restype = c_int
+    lib.sn_ldr_backward.argtypes = [i32, i32, vp, vp, i32, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.sn_dense_apply.restype = c_int
+    lib.sn_dense_apply.argtypes = [vp, i32, i32, vp, i64, vp, i64, vp, i64, vp]
+    lib.sn_dense_weight_grad.restype = c_int
+    lib.sn_dense_weight_grad.argtypes = [vp, i64, vp, i64, vp, i32, i32, vp, i64, vp]
+    lib.sn_tl_build_weight.restype = c_int
+    lib.sn_tl_build_weight.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.sn_tl_backward.restype = c_int
+    lib.sn_tl_backward.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     for name, fn in _EXTRA_DECLS:
         fn(lib)
 

@@ -1,0 +1,120 @@
+"""Hierarchical-matrix layer on B200.  Drop-in for ``structurednets.layers.hmat_layer.HMatLayer``
+(reference layers/hmat_layer.py:12-52): same constructor, a ``ModuleList`` ``hmatrix_components`` of
+leaves with parameters ``left_lr`` / ``right_lr`` (state_dict keys
+``bias, hmatrix_components.{i}.left_lr, hmatrix_components.{i}.right_lr``), leaves with rank 0 dropped.
+Forward/backward run in csrc/hmat.cu through ``sn_hmat_forward`` / ``sn_hmat_backward``.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from structurednets_b200 import _lib
+from structurednets_b200.hmatrix.hmatrix import HMatrixComponent, approximate_hmatrix
+from structurednets_b200.layers.flat_params import FlatParamsMixin
+from structurednets_b200.layers.layer_helpers import get_random_glorot_uniform_matrix
+from structurednets_b200.layers.structured_layer import StructuredLayer
+
+
+class _HMatFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, U, anchor, layer):
+        B = U.shape[0]
+        table = layer._leaf_table(U.device)
+        flat = layer.flat_parameters()
+        y = torch.empty((B, layer.output_dim), dtype=torch.float32, device=U.device)
+        rc = _lib.lib().sn_hmat_forward(_lib.ptr(table), layer._nleaves, _lib.ptr(flat), _lib.ptr(U), U.stride(0), _lib.ptr(y),
+                                        y.stride(0), _lib.ptr(layer.bias if layer.use_bias else None), B, layer.input_dim,
+                                        layer.output_dim, _lib.stream_ptr())
+        _lib.check(rc, "sn_hmat_forward")
+        ctx.layer = layer
+        ctx.save_for_backward(U, table)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        layer = ctx.layer
+        U, table = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("HMatLayer: gradient w.r.t. the input features is not implemented "
+                               "(the reference training loop never requests it, training_helpers.py:34)")
+        grad_y = grad_y.contiguous().float()
+        g = layer._prepare_grad_accumulation()
+        gb = g[:layer.output_dim] if (layer.use_bias and layer.bias.requires_grad) else None
+        rc = _lib.lib().sn_hmat_backward(_lib.ptr(table), layer._nleaves, _lib.ptr(layer.flat_parameters()), _lib.ptr(U), U.stride(0),
+                                         _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(g), _lib.ptr(gb), U.shape[0], layer.input_dim,
+                                         layer.output_dim, _lib.stream_ptr())
+        _lib.check(rc, "sn_hmat_backward")
+        return None, None, None
+
+
+class HMatLayer(FlatParamsMixin, StructuredLayer):
+    def __init__(self, input_dim: int, output_dim: int, nb_params_share: float, use_bias=True, initial_weight_matrix=None,
+                 initial_bias=None, eta=0.5, initial_hmatrix=None, use_gpu=False):
+        super(HMatLayer, self).__init__(input_dim=input_dim, output_dim=output_dim, nb_params_share=nb_params_share, use_bias=use_bias,
+                                        initial_weight_matrix=initial_weight_matrix, initial_bias=initial_bias)
+        assert initial_weight_matrix is None or initial_hmatrix is None, "You can either pass an initial hmatrix or an initial weight matrix to be used as starting point fo the HMatrixLayer"
+
+        if initial_hmatrix is not None:
+            self.hmatrix = initial_hmatrix.clone()
+        else:
+            if initial_weight_matrix is None:
+                initial_weight_matrix = get_random_glorot_uniform_matrix((output_dim, input_dim))
+            self.hmatrix = approximate_hmatrix(initial_weight_matrix, nb_params_share=nb_params_share, eta=eta)
+
+        self.input_dim = input_dim
+        components = [c for c in self.hmatrix.get_all_hmatrix_components() if c.are_low_rank_components_set()]
+        # re-wrap foreign (e.g. reference) component objects so parameters are float32 leaves we own
+        own = []
+        for c in components:
+            if isinstance(c, HMatrixComponent):
+                own.append(c)
+            else:
+                own.append(HMatrixComponent(c.row_range, c.col_range, c.left_lr.detach(), c.right_lr.detach()))
+        self.hmatrix_components = nn.ModuleList(own)
+        self.use_gpu = use_gpu
+        self._nleaves = len(own)
+        self._flatten_parameters()
+
+    def _on_reflatten(self):
+        self.__dict__["_dev_table"] = None
+
+    def build_leaf_table(self) -> np.ndarray:
+        """(nleaves, 8) int32: row_start, rows, col_start, cols, rank, off_left, off_right, 0 (see csrc/hmat.cu)."""
+        self._ensure_flat()
+        by_id = {id(p): o for p, o in zip(self._flat_param_list(), self.__dict__["_flat_offsets"])}
+        tab = np.zeros((max(self._nleaves, 1), 8), dtype=np.int32)
+        for i, c in enumerate(self.hmatrix_components):
+            k = c.left_lr.shape[1]
+            assert c.left_lr.shape[0] == len(c.row_range) and c.right_lr.shape[1] == len(c.col_range) and c.right_lr.shape[0] == k
+            assert c.row_range.stop <= self.output_dim and c.col_range.stop <= self.input_dim
+            tab[i] = [c.row_range.start, len(c.row_range), c.col_range.start, len(c.col_range), k, by_id[id(c.left_lr)], by_id[id(c.right_lr)], 0]
+        # largest leaves first: better balance of the per-warp round-robin (order does not change the result
+        # beyond fp32 summation order)
+        order = np.argsort(-(tab[:, 4].astype(np.int64) * (tab[:, 1] + tab[:, 3])), kind="stable")
+        return tab[order]
+
+    def _leaf_table(self, device):
+        self._ensure_flat()
+        t = self.__dict__.get("_dev_table")
+        if t is None or t.device != device:
+            t = torch.from_numpy(self.build_leaf_table().reshape(-1)).to(device)
+            self.__dict__["_dev_table"] = t
+        return t
+
+    def forward(self, U):
+        self._require_cuda(U, "HMatLayer.forward")
+        assert U.dim() == 2 and U.shape[1] == self.input_dim, "HMatLayer expects a (batch, input_dim) input"
+        self._ensure_flat()
+        if U.dtype != torch.float32:
+            U = U.float()
+        if U.stride(1) != 1:
+            U = U.contiguous()
+        anchor = self.__dict__.get("_dev_anchor")
+        if anchor is None or anchor.device != U.device:
+            anchor = torch.zeros(1, device=U.device, requires_grad=True)
+            self.__dict__["_dev_anchor"] = anchor
+        needs = torch.is_grad_enabled() and self._nleaves > 0
+        return _HMatFunction.apply(U, anchor if needs else None, self)
+
+    def get_nb_parameters(self) -> int:
+        return self.hmatrix.get_nb_params()

@@ -1,0 +1,186 @@
+"""Product-of-sparse-matrices layer on B200.  Drop-in for ``structurednets.layers.psm_layer.PSMLayer``
+(reference layers/psm_layer.py:13-80): same constructor (note the reference's positional order
+``input_dim, output_dim, use_bias, nb_params_share, ...``), a ``ParameterList`` ``sparse_matrices`` of
+float32 sparse-COO parameters built exactly like ``scipy_csr_to_torch`` (psm_layer.py:30-34) and sparse
+gradients on the same pattern, so the "SGD only" behaviour of the reference is unchanged.
+
+Factor order: the intended chain W = S0 S1 ... S(n-1) (psm_approximator.py:96-105).  The reference's
+forward applies ``[-1], [0], [1], ...`` (psm_layer.py:52-54), which equals the intended order for <= 2
+factors and is a shape error / wrong product for >= 3 (SURVEY.md finding F2).
+"""
+import ctypes
+
+import numpy as np
+import scipy.sparse
+import torch
+import torch.nn as nn
+
+from structurednets_b200 import _lib
+from structurednets_b200.layers.layer_helpers import get_random_glorot_uniform_matrix
+from structurednets_b200.layers.structured_layer import StructuredLayer
+
+
+def _pattern(p: torch.Tensor):
+    """CSR- and CSC-ordered views of an (uncoalesced) sparse-COO pattern, built on the device with
+    sorting only (no host round trip); cached per indices storage."""
+    idx = p._indices()
+    rows, cols = idx[0], idx[1]
+    nr, nc = p.shape
+    perm = torch.argsort(rows * nc + cols, stable=True)
+    permc = torch.argsort(cols * nr + rows, stable=True)
+    i32 = lambda t: t.to(torch.int32).contiguous()
+    z = torch.zeros(1, dtype=torch.int64, device=idx.device)
+    rowptr = torch.cat([z, torch.cumsum(torch.bincount(rows, minlength=nr), 0)])
+    cscptr = torch.cat([z, torch.cumsum(torch.bincount(cols, minlength=nc), 0)])
+    return dict(key=(idx.data_ptr(), idx.shape[1], str(idx.device)), rowptr=i32(rowptr), colidx=i32(cols[perm]), perm=i32(perm),
+                cscptr=i32(cscptr), rowidx=i32(rows[permc]), permc=i32(permc))
+
+
+def _factor_array(patterns, params, gvals):
+    arr = (_lib.SnPsmFactor * len(params))()
+    for k, (pat, p) in enumerate(zip(patterns, params)):
+        f = arr[k]
+        f.rows, f.cols, f.nnz = int(p.shape[0]), int(p.shape[1]), int(p._nnz())
+        for name in ("rowptr", "colidx", "perm", "cscptr", "rowidx", "permc"):
+            setattr(f, name, pat[name].data_ptr())
+        f.vals = p._values().data_ptr()
+        f.grad_vals = gvals[k].data_ptr() if gvals is not None else None
+    return arr
+
+
+class _PSMFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, U, bias, layer, *factors):
+        B = U.shape[0]
+        patterns = layer._patterns(factors)
+        vals = [p._values() for p in factors]
+        assert all(v.dtype == torch.float32 and v.is_contiguous() for v in vals)
+        arr = _factor_array(patterns, factors, None)
+        y = torch.empty((B, layer.output_dim), dtype=torch.float32, device=U.device)
+        rc = _lib.lib().sn_psm_forward(arr, len(factors), _lib.ptr(U), U.stride(0), _lib.ptr(y), y.stride(0), _lib.ptr(bias), B,
+                                       layer.input_dim, layer.output_dim, _lib.stream_ptr())
+        _lib.check(rc, "sn_psm_forward")
+        ctx.layer, ctx.patterns, ctx.has_bias = layer, patterns, bias is not None
+        ctx.save_for_backward(U, *factors)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        U, *factors = ctx.saved_tensors
+        layer = ctx.layer
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("PSMLayer: gradient w.r.t. the input features is not implemented "
+                               "(the reference training loop never requests it, training_helpers.py:34)")
+        grad_y = grad_y.contiguous().float()
+        gvals = [torch.zeros(p._nnz(), dtype=torch.float32, device=U.device) for p in factors]
+        gbias = torch.zeros(layer.output_dim, dtype=torch.float32, device=U.device) if ctx.has_bias else None
+        arr = _factor_array(ctx.patterns, factors, gvals)
+        rc = _lib.lib().sn_psm_backward(arr, len(factors), _lib.ptr(U), U.stride(0), _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(gbias),
+                                        U.shape[0], layer.input_dim, layer.output_dim, _lib.stream_ptr())
+        _lib.check(rc, "sn_psm_backward")
+        # sparse gradients on the parameters' own (uncoalesced) pattern, like autograd's to_dense backward
+        gf = [torch.sparse_coo_tensor(p._indices(), g, p.shape) for p, g in zip(factors, gvals)]
+        return (None, gbias, None, *gf)
+
+
+class PSMLayer(StructuredLayer):
+    # NOTE (reference psm_layer.py:14-15): sparse weight matrices -> sparse gradients -> train with SGD, not Adam.
+    def __init__(self, input_dim: int, output_dim: int, use_bias=True, nb_params_share=None, initial_weight_matrix=None,
+                 initial_bias=None, sparse_matrices=None):
+        super(PSMLayer, self).__init__(input_dim=input_dim, output_dim=output_dim, nb_params_share=nb_params_share, use_bias=use_bias,
+                                       initial_weight_matrix=initial_weight_matrix, initial_bias=initial_bias)
+        assert nb_params_share is not None or sparse_matrices is not None, "Need to pass the nb_params_share or an initial sparse matrices configuration"
+        assert sparse_matrices is None or initial_weight_matrix is None, "Can either pass an initial weight matrix or an initial sparse matrices configuration"
+
+        if sparse_matrices is None:
+            if initial_weight_matrix is None:
+                initial_weight_matrix = get_random_glorot_uniform_matrix((output_dim, input_dim))
+            sparse_matrices = _factorize(initial_weight_matrix, nb_params_share)
+
+        self.input_dim = input_dim
+        self.sparse_matrices = nn.ParameterList([self.scipy_csr_to_torch(mat) for mat in sparse_matrices])
+        shapes = [tuple(p.shape) for p in self.sparse_matrices]
+        assert shapes[0][0] == output_dim and shapes[-1][1] == input_dim, "The sparse factors do not map input_dim -> output_dim"
+        for a, b in zip(shapes[:-1], shapes[1:]):
+            assert a[1] == b[0], "Consecutive sparse factors cannot be multiplied: " + str(shapes)
+
+    def scipy_csr_to_torch(self, mat) -> torch.Tensor:
+        """Same construction as the reference (psm_layer.py:30-34): transpose of the COO with swapped indices."""
+        coo_mat = scipy.sparse.coo_matrix(mat)
+        idx = torch.tensor(np.stack([coo_mat.col, coo_mat.row]).astype(np.int64))
+        res = torch.transpose(torch.sparse_coo_tensor(idx, torch.tensor(coo_mat.data), (coo_mat.shape[1], coo_mat.shape[0])).float(), 0, 1)
+        res.requires_grad_(True)
+        return nn.Parameter(res)
+
+    def _patterns(self, factors):
+        cache = self.__dict__.setdefault("_dev_patterns", {})
+        out = []
+        for k, p in enumerate(factors):
+            idx = p._indices()
+            key = (idx.data_ptr(), idx.shape[1], str(idx.device))
+            pat = cache.get(k)
+            if pat is None or pat["key"] != key:
+                pat = _pattern(p)
+                cache[k] = pat
+            out.append(pat)
+        return out
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_dev_patterns", None)
+        return state
+
+    def forward(self, U):
+        self._require_cuda(U, "PSMLayer.forward")
+        assert U.dim() == 2 and U.shape[1] == self.input_dim, "PSMLayer expects a (batch, input_dim) input"
+        if U.dtype != torch.float32:
+            U = U.float()
+        if U.stride(1) != 1:
+            U = U.contiguous()
+        return _PSMFunction.apply(U, self.bias if self.use_bias else None, self, *self.sparse_matrices)
+
+    forward_sparse = forward   # the reference's alternative torch.sparse.mm path (psm_layer.py:36-45): same math
+
+    def get_nb_parameters(self) -> int:
+        return self.get_nb_parameters_in_weight_matrix() + len(self.bias)
+
+    def get_nb_parameters_in_weight_matrix(self) -> int:
+        return sum([len(mat.coalesce().values()) for mat in self.sparse_matrices])
+
+
+def _factorize(weight: np.ndarray, nb_params_share: float):
+    """The reference fits the factors with pyfaust's hierarchical PALM4MSA (approximators/psm_approximator.py:
+    107-148), an unpinned PyPI dependency whose factorisation values no reference test pins (SURVEY.md
+    section 8c).  Without it, fall back to a budget-respecting two-factor start: the largest-magnitude entries
+    of W times a sparse identity -- enough for training from scratch; pass sparse_matrices=... for anything else."""
+    try:
+        from structurednets.approximators.psm_approximator_wrapper import PSMApproximatorWrapper  # noqa: F401
+        res = PSMApproximatorWrapper().approximate(optim_mat=weight, nb_params_share=nb_params_share)
+        return res["faust_approximation"]
+    except Exception:
+        pass
+    out_dim, in_dim = weight.shape
+    budget = int(nb_params_share * weight.size)
+    mx = max(out_dim, in_dim)
+    eye_nnz = min(in_dim, max(budget // 2, 0))
+    keep = max(budget - eye_nnz, 0)
+    W = np.zeros((out_dim, mx))
+    W[:, :in_dim] = weight
+    if keep < W.size:
+        thresh = np.partition(np.abs(W).ravel(), W.size - keep)[W.size - keep] if keep > 0 else np.inf
+        W = np.where(np.abs(W) >= thresh, W, 0.0)
+        nz = np.flatnonzero(W)
+        if len(nz) > keep:
+            W.ravel()[nz[keep:]] = 0.0
+    E = scipy.sparse.lil_matrix((mx, in_dim))
+    for i in range(eye_nnz):
+        E[i, i] = 1.0
+    return [scipy.sparse.csr_matrix(W), scipy.sparse.csr_matrix(E)]
+
+
+def build_PSMLayer_from_res_dict(res_dict: dict, bias: np.ndarray) -> PSMLayer:
+    """reference layers/psm_layer.py:68-80 (the dense cross-check there needs a forward pass, i.e. a GPU here)."""
+    sparse_matrices = res_dict["faust_approximation"]
+    assert len(sparse_matrices) == res_dict["nb_matrices"], "Mismatch between expected and real number of matrices in the FAUST approximation"
+    shape = res_dict["approx_mat_dense"].shape
+    return PSMLayer(input_dim=shape[1], output_dim=shape[0], sparse_matrices=sparse_matrices, initial_bias=bias)
