@@ -63,7 +63,9 @@ typedef struct sn_sss_chunk {
     int32_t col0, ncols;   /* input columns covered by the chunk  */
     int32_t row0, nrows;   /* output columns covered by the chunk */
     int32_t second_visit;  /* 1: the other direction already wrote y for these stages */
-    int32_t reserved;
+    int32_t kk_mid;        /* the forward stages its input columns in two halves: [kk_begin,kk_mid) and [kk_mid,kk_end) */
+    int32_t col0_a, ncols_a, col0_b, ncols_b; /* input columns of the two halves */
+    int32_t reserved[4];
 } sn_sss_chunk;
 
 typedef struct sn_sss_plan {
@@ -72,7 +74,7 @@ typedef struct sn_sss_plan {
     int32_t nchunks;                /* per direction */
     int32_t chunk_in_max, chunk_out_max, chunk_len_max;
     int32_t nparams;                /* floats in the flat parameter buffer */
-    int32_t reserved;
+    int32_t half_in_max;            /* max input columns of a half chunk */
     const sn_sss_stage* stages; /* device, [2][nb_states] */
     const sn_sss_chunk* chunks; /* device, [2][nchunks]   */
 } sn_sss_plan;

@@ -17,12 +17,13 @@ class SnSssStage(Structure):
 
 
 class SnSssChunk(Structure):
-    _fields_ = [(n, c_int32) for n in ("kk_begin", "kk_end", "col0", "ncols", "row0", "nrows", "second_visit", "reserved")]
+    _fields_ = [(n, c_int32) for n in ("kk_begin", "kk_end", "col0", "ncols", "row0", "nrows", "second_visit", "kk_mid",
+                                      "col0_a", "ncols_a", "col0_b", "ncols_b")] + [("reserved", c_int32 * 4)]
 
 
 class SnSssPlan(Structure):
     _fields_ = [(n, c_int32) for n in ("nb_states", "input_dim", "output_dim", "rows_pad", "k_pad", "d_pad", "nchunks",
-                                      "chunk_in_max", "chunk_out_max", "chunk_len_max", "nparams", "reserved")] + \
+                                      "chunk_in_max", "chunk_out_max", "chunk_len_max", "nparams", "half_in_max")] + \
                [("stages", c_void_p), ("chunks", c_void_p)]
 
 

@@ -29,6 +29,8 @@ namespace {
 using snb::ceil_div;
 using snb::round_up;
 
+constexpr int SSS_HDR = 8;   // floats at the head of every packed stage block: the stage descriptor
+
 struct Geom {
     int rgs;    // row-group slots per warp
     int nq;     // sample quads per warp
@@ -65,7 +67,12 @@ __global__ void sss_pack_kernel(const sn_sss_stage* __restrict__ stages, int tot
     sn_sss_stage st = stages[sidx];
     const int K = st.d_in + st.in_dim;
     const int rows = st.d_out + st.out_dim;
-    float* Pt = packed + st.pack_off;
+    int* hdr = reinterpret_cast<int*>(packed + st.pack_off);
+    if (threadIdx.x < SSS_HDR) {
+        const int h[SSS_HDR] = {st.in_off, st.in_dim, st.out_off, st.out_dim, st.d_in, st.d_out, st.k, 0};
+        hdr[threadIdx.x] = h[threadIdx.x];
+    }
+    float* Pt = packed + st.pack_off + SSS_HDR;
     float* P = Pt + (size_t)KP * RP;
     for (int e = threadIdx.x; e < KP * RP; e += blockDim.x) {
         int i = e / RP, r = e - i * RP;
@@ -100,7 +107,7 @@ __device__ __forceinline__ void fma16(float (&acc)[4][4], const float4& p, const
 __device__ __forceinline__ void stage_step(const sn_sss_stage& st, const float* __restrict__ packed, int RP,
                                            const float* xs, float* xn, const float* uc, float* yc,
                                            int stride, int ucol, int yrow, int nrg, int rg_slot, int rgs, int q) {
-    const float4* Pt4 = reinterpret_cast<const float4*>(packed + st.pack_off);
+    const float4* Pt4 = reinterpret_cast<const float4*>(packed + st.pack_off + SSS_HDR);
     const int RP4 = RP >> 2;
     for (int rg = rg_slot; rg < nrg; rg += rgs) {
         float acc[4][4];
@@ -138,74 +145,275 @@ __device__ __forceinline__ void stage_step(const sn_sss_stage& st, const float* 
 }
 
 // ------------------------------------------------------------------------------------------
-// forward
+// async-copy / mbarrier helpers (sm_90+ PTX; SASS: SYNCS.*, UBLKCP, LDGSTS)
 // ------------------------------------------------------------------------------------------
-constexpr int FWD_PAIRS = 2;  // (causal, anticausal) warp pairs per CTA
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine, completion signalled on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-__global__ void __launch_bounds__(FWD_PAIRS * 64)
+// ------------------------------------------------------------------------------------------
+// forward
+//   CTA = FWD_PAIRS (causal, anticausal) consumer warp pairs + 1 producer warp.
+//   producer : streams the packed stage blocks (descriptor header + Pt) of both directions through a
+//              FWD_SLOTS-deep shared-memory ring with cp.async.bulk + mbarrier (full/empty per slot).
+//   consumer : owns NSW = 4*NQ samples of one direction; input columns of half a chunk are prefetched
+//              with cp.async (double buffered, natural [sample][col] layout, row stride = 4*odd floats so
+//              the 4 scalar reads of a lane's interleaved samples are bank-conflict free); the state lives in a
+//              feature-major ping-pong buffer; y is collected per chunk and flushed with 64 B row segments.
+//   Sample <-> position map inside a warp: position p = 4*q + t  holds local sample  q + NQ*t.
+// ------------------------------------------------------------------------------------------
+constexpr int FWD_PAIRS = 3;
+constexpr int FWD_SLOTS = 4;
+constexpr int FWD_CONSUMERS = 2 * FWD_PAIRS;
+constexpr int FWD_THREADS = (FWD_CONSUMERS + 1) * 32;
+
+struct FwdSmem {
+    int slot_floats;   // one ring slot: header + Pt
+    int ring_off, bar_off, warp_off, per_warp;   // float offsets (bar_off is 8-byte aligned)
+    int uw;            // row stride of the u buffers
+    int xs, xn, ub0, ub1, yb;   // offsets inside a warp's region
+    int total;
+};
+
+inline FwdSmem make_fwd_smem(const sn_sss_plan& p, const Geom& g) {
+    FwdSmem s;
+    s.slot_floats = round_up(SSS_HDR + p.k_pad * p.rows_pad, 4);
+    s.ring_off = 0;
+    s.bar_off = s.ring_off + 2 * FWD_SLOTS * s.slot_floats;
+    s.warp_off = s.bar_off + 2 * (2 * FWD_SLOTS * 2);   // 2 dirs x SLOTS x {full, empty} x 8 bytes
+    s.uw = pad_stride(p.half_in_max + 3);
+    int o = 0;
+    s.xs = o;  o += p.d_pad * g.nswp;
+    s.xn = o;  o += p.d_pad * g.nswp;
+    s.ub0 = o; o += g.nsw * s.uw;
+    s.ub1 = o; o += g.nsw * s.uw;
+    s.yb = o;  o += p.chunk_out_max * g.nswp;
+    s.per_warp = round_up(o, 4);
+    s.total = s.warp_off + FWD_CONSUMERS * s.per_warp;
+    return s;
+}
+
+// input columns [col0, col0+ncols) of the warp's samples -> ub[ls][uoff + (col - col0)]; returns uoff
+__device__ __forceinline__ int issue_u_load(const float* __restrict__ x, long ldx, long s0, long B, int in_dim, int nsw, int uw,
+                                            bool aligned, int col0, int ncols, float* ub, int lane) {
+    if (aligned) {
+        const int col0a = col0 & ~3;
+        const int ngran = (col0 - col0a + ncols + 3) >> 2;
+        for (int r0 = 0; r0 < nsw; r0 += 8) {
+            const int ls = r0 + (lane >> 2);
+            const bool rok = ls < nsw && s0 + ls < B;
+            const float* row = x + (size_t)(s0 + ls) * ldx + col0a;
+            for (int gi = lane & 3; gi < ngran; gi += 4) {
+                const bool ok = rok && (col0a + 4 * gi < in_dim);
+                if (ls < nsw) cp_async16(ub + ls * uw + 4 * gi, ok ? (const void*)(row + 4 * gi) : (const void*)x, ok);
+            }
+        }
+        return col0 - col0a;
+    }
+    for (int ls = 0; ls < nsw; ++ls) {
+        const bool rok = s0 + ls < B;
+        const float* row = x + (size_t)(s0 + ls) * ldx + col0;
+        for (int c = lane; c < ncols; c += 32) cp_async4(ub + ls * uw + c, rok ? (const void*)(row + c) : (const void*)x, rok);
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(FWD_THREADS)
 sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* __restrict__ x, long ldx,
                float* __restrict__ y, long ldy, const float* __restrict__ bias, float* __restrict__ ckpt, long B,
-               Geom g, int per_warp_floats) {
-    extern __shared__ __align__(16) float smem[];
+               Geom g, FwdSmem sm, int x_aligned) {
+    extern __shared__ __align__(128) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pair = warp >> 1, dir = warp & 1;
     const int n = plan.nb_states, DP = plan.d_pad, RP = plan.rows_pad;
+    float* ring = smem + sm.ring_off;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bar_off);   // [dir][slot][full, empty]
+    auto full_bar = [&](int dir, int slot) { return bars + ((dir * FWD_SLOTS + slot) * 2 + 0); };
+    auto empty_bar = [&](int dir, int slot) { return bars + ((dir * FWD_SLOTS + slot) * 2 + 1); };
+
+    if (threadIdx.x == 0) {
+        for (int d = 0; d < 2; ++d)
+            for (int sl = 0; sl < FWD_SLOTS; ++sl) {
+                mbar_init(full_bar(d, sl), 1);
+                mbar_init(empty_bar(d, sl), FWD_PAIRS);
+            }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == FWD_CONSUMERS) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)sm.slot_floats * 4u;
+            const size_t blk = SSS_HDR + 2 * (size_t)plan.k_pad * RP;
+            for (int kk = 0; kk < n; ++kk) {
+                const int sl = kk % FWD_SLOTS, round = kk / FWD_SLOTS;
+                for (int d = 0; d < 2; ++d) {
+                    if (round > 0) mbar_wait(empty_bar(d, sl), (round - 1) & 1);
+                    mbar_arrive_expect_tx(full_bar(d, sl), bytes);
+                    bulk_g2s(ring + (size_t)(d * FWD_SLOTS + sl) * sm.slot_floats, packed + ((size_t)d * n + kk) * blk, bytes, full_bar(d, sl));
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int pair = warp >> 1, dir = warp & 1;
     const long s0 = ((long)blockIdx.x * FWD_PAIRS + pair) * g.nsw;
-    float* wbase = smem + (size_t)warp * per_warp_floats;
-    float* xs = wbase;
-    float* xn = xs + (size_t)DP * g.nswp;
-    float* uc = xn + (size_t)DP * g.nswp;
-    float* yc = uc + (size_t)plan.chunk_in_max * g.nswp;
-    const sn_sss_stage* stages = plan.stages + (size_t)dir * n;
+    float* wbase = smem + sm.warp_off + (size_t)warp * sm.per_warp;
+    float* xs = wbase + sm.xs;
+    float* xn = wbase + sm.xn;
+    float* ubuf[2] = {wbase + sm.ub0, wbase + sm.ub1};
+    float* yb = wbase + sm.yb;
     const sn_sss_chunk* chunks = plan.chunks + (size_t)dir * plan.nchunks;
     const int rg_slot = lane / g.nq, q = lane - rg_slot * g.nq;
     const bool active = rg_slot < g.rgs;
+    const int nswp = g.nswp, uw = sm.uw, nq = g.nq, nsw = g.nsw;
+    const int RP4 = RP >> 2;
     bool did_mid = false;
+    int ubi = 0;         // which u buffer holds the half that is consumed next
+    int uoff_cur;
+
+    sn_sss_chunk c = chunks[0];
+    uoff_cur = issue_u_load(x, ldx, s0, B, plan.input_dim, nsw, uw, x_aligned != 0, c.col0_a, c.ncols_a, ubuf[0], lane);
+    cp_async_commit();
 
     for (int ch = 0; ch < plan.nchunks; ++ch) {
-        const sn_sss_chunk c = chunks[ch];
         if (c.second_visit && !did_mid) {
-            __syncthreads();  // the other direction's first-visit stores to y are now visible
+            named_bar_sync(1, FWD_CONSUMERS * 32);   // the other direction's first-visit stores to y are visible
             did_mid = true;
         }
-        if (ckpt != nullptr) {
-            const int d = stages[c.kk_begin].d_in;
-            float* cbase = ckpt + ((size_t)(dir * plan.nchunks + ch) * DP) * B;
-            for (int e = lane; e < d * g.nsw; e += 32) {
-                int f = e / g.nsw, s = e - f * g.nsw;
-                if (s0 + s < B) cbase[(size_t)f * B + s0 + s] = xs[f * g.nswp + s];
+        sn_sss_chunk cnext = c;
+        if (ch + 1 < plan.nchunks) cnext = chunks[ch + 1];
+        for (int half = 0; half < 2; ++half) {
+            const int kb = half == 0 ? c.kk_begin : c.kk_mid;
+            const int ke = half == 0 ? c.kk_mid : c.kk_end;
+            const int hcol0 = half == 0 ? c.col0_a : c.col0_b;
+            // prefetch the next half (or the first half of the next chunk) into the other buffer
+            int uoff_next = 0;
+            bool issued = false;
+            if (half == 0) {
+                if (c.kk_mid < c.kk_end) { uoff_next = issue_u_load(x, ldx, s0, B, plan.input_dim, nsw, uw, x_aligned != 0, c.col0_b, c.ncols_b, ubuf[ubi ^ 1], lane); issued = true; }
+            } else if (ch + 1 < plan.nchunks) {
+                uoff_next = issue_u_load(x, ldx, s0, B, plan.input_dim, nsw, uw, x_aligned != 0, cnext.col0_a, cnext.ncols_a, ubuf[ubi ^ 1], lane); issued = true;
             }
-        }
-        for (int e = lane; e < g.nsw * c.ncols; e += 32) {
-            int s = e / c.ncols, cc = e - s * c.ncols;
-            float v = 0.f;
-            if (s0 + s < B) v = __ldg(x + (size_t)(s0 + s) * ldx + c.col0 + cc);
-            uc[cc * g.nswp + s] = v;
-        }
-        __syncwarp();
-        for (int kk = c.kk_begin; kk < c.kk_end; ++kk) {
-            const sn_sss_stage st = stages[kk];
-            if (active) {
-                const int nrg = ceil_div(st.d_out + st.out_dim, 4);
-                stage_step(st, packed, RP, xs, xn, uc, yc, g.nswp, st.in_off - c.col0, st.out_off - c.row0, nrg,
-                           rg_slot, g.rgs, q);
-            }
+            cp_async_commit();
+            cp_async_wait<1>();
             __syncwarp();
-            float* t = xs; xs = xn; xn = t;
+            if (kb < ke) {
+                const float* ub = ubuf[ubi];
+                for (int kk = kb; kk < ke; ++kk) {
+                    const int sl = kk % FWD_SLOTS;
+                    mbar_wait(full_bar(dir, sl), (kk / FWD_SLOTS) & 1);
+                    const float* slot = ring + (size_t)(dir * FWD_SLOTS + sl) * sm.slot_floats;
+                    const int* hdr = reinterpret_cast<const int*>(slot);
+                    const int in_off = hdr[0], in_dim = hdr[1], out_off = hdr[2], out_dim = hdr[3], d_in = hdr[4], d_out = hdr[5];
+                    if (ckpt != nullptr && kk == c.kk_begin) {
+                        // checkpoint of the state entering the chunk, in true sample order
+                        float* cbase = ckpt + ((size_t)(dir * plan.nchunks + ch) * DP) * B;
+                        for (int e = lane; e < d_in * nsw; e += 32) {
+                            const int f = e / nsw, ls = e - f * nsw;
+                            const int pos = 4 * (ls % nq) + ls / nq;
+                            if (s0 + ls < B) cbase[(size_t)f * B + s0 + ls] = xs[f * nswp + pos];
+                        }
+                    }
+                    if (active) {
+                        const int nrg = (d_out + out_dim + 3) >> 2;
+                        const float4* Pt4 = reinterpret_cast<const float4*>(slot + SSS_HDR);
+                        const float* u0 = ub + (q)*uw + uoff_cur + (in_off - hcol0);
+                        const float* u1 = u0 + nq * uw;
+                        const float* u2 = u1 + nq * uw;
+                        const float* u3 = u2 + nq * uw;
+                        for (int rg = rg_slot; rg < nrg; rg += g.rgs) {
+                            float acc[4][4];
+#pragma unroll
+                            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                                for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+                            const float4* prow = Pt4 + rg;
+                            const float* xv = xs + 4 * q;
+#pragma unroll 4
+                            for (int i = 0; i < d_in; ++i) {
+                                const float4 p = prow[0];
+                                const float4 v = *reinterpret_cast<const float4*>(xv);
+                                prow += RP4;
+                                xv += nswp;
+                                fma16(acc, p, v);
+                            }
+#pragma unroll 4
+                            for (int i = 0; i < in_dim; ++i) {
+                                const float4 p = prow[0];
+                                prow += RP4;
+                                const float4 v = make_float4(u0[i], u1[i], u2[i], u3[i]);
+                                fma16(acc, p, v);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int r = 4 * rg + j;
+                                const float4 o = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                                if (r < d_out) *reinterpret_cast<float4*>(xn + r * nswp + 4 * q) = o;
+                                else if (r < d_out + out_dim) *reinterpret_cast<float4*>(yb + (out_off - c.row0 + r - d_out) * nswp + 4 * q) = o;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty_bar(dir, sl));
+                    float* t = xs; xs = xn; xn = t;
+                }
+            }
+            if (issued) { ubi ^= 1; uoff_cur = uoff_next; }
         }
-        for (int e = lane; e < g.nsw * c.nrows; e += 32) {
-            int s = e / c.nrows, rr = e - s * c.nrows;
-            if (s0 + s < B) {
-                float v = yc[rr * g.nswp + s];
-                float* dst = y + (size_t)(s0 + s) * ldy + c.row0 + rr;
-                if (c.second_visit) v += __ldcg(dst);
-                else if (bias != nullptr) v += __ldg(bias + c.row0 + rr);
-                *dst = v;
+        // flush the chunk's outputs: y[s0 + ls][row0 + row]
+        for (int ls = 0; ls < nsw; ++ls) {
+            if (s0 + ls >= B) break;
+            const int pos = 4 * (ls % nq) + ls / nq;
+            float* dst = y + (size_t)(s0 + ls) * ldy + c.row0;
+            for (int row = lane; row < c.nrows; row += 32) {
+                float v = yb[row * nswp + pos];
+                if (c.second_visit) v += __ldcg(dst + row);
+                else if (bias != nullptr) v += __ldg(bias + c.row0 + row);
+                dst[row] = v;
             }
         }
         __syncwarp();
+        c = cnext;
     }
-    if (!did_mid) __syncthreads();
+    cp_async_wait<0>();
+    if (!did_mid) named_bar_sync(1, FWD_CONSUMERS * 32);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -310,7 +518,7 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
         // ---- 2. adjoint sweep -----------------------------------------------------------
         for (int j = len - 1; j >= 0; --j) {
             const sn_sss_stage st = stages[c.kk_begin + j];
-            const float4* P4 = reinterpret_cast<const float4*>(packed + st.pack_off + (size_t)KP * RP);
+            const float4* P4 = reinterpret_cast<const float4*>(packed + st.pack_off + SSS_HDR + (size_t)KP * RP);
             const int KP4 = KP >> 2;
             const float* lout = lh + j * hstride + w0;                          // adjoint of s_out
             const float* gyj = gc + (size_t)(st.out_off - c.row0) * NSP + w0;   // adjoint of y_k
@@ -439,7 +647,7 @@ extern "C" {
 
 size_t sn_sss_packed_floats(const sn_sss_plan* p) {
     if (p == nullptr) return 0;
-    return (size_t)2 * p->nb_states * 2 * p->k_pad * p->rows_pad;
+    return (size_t)2 * p->nb_states * (SSS_HDR + 2 * (size_t)p->k_pad * p->rows_pad);
 }
 
 size_t sn_sss_ckpt_floats(const sn_sss_plan* p, int64_t B) {
@@ -463,18 +671,20 @@ int sn_sss_forward(const sn_sss_plan* p, const float* packed, const float* x, in
     SN_CHECK_ARG(ldx >= p->input_dim && ldy >= p->output_dim, "sss_forward: leading dimension too small");
     if (B <= 0) return 0;
     Geom g = make_geom(p->rows_pad);
-    int per_warp = (2 * p->d_pad + p->chunk_in_max + p->chunk_out_max) * g.nswp;
-    size_t smem = (size_t)per_warp * FWD_PAIRS * 2 * sizeof(float);
+    FwdSmem sm = make_fwd_smem(*p, g);
+    size_t smem = (size_t)sm.total * sizeof(float);
     SN_CHECK_ARG(smem <= 227 * 1024, "sss_forward: stage dims need %zu bytes of shared memory (> 227 KB)", smem);
     static size_t configured = 0;
     if (smem > configured) {
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
+    // 16-byte cp.async path needs 16-byte aligned rows whose length is a multiple of 4 floats
+    const int aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldx & 3) == 0 && (p->input_dim & 3) == 0) ? 1 : 0;
     long tile = (long)FWD_PAIRS * g.nsw;
     unsigned grid = (unsigned)((B + tile - 1) / tile);
-    sss_fwd_kernel<<<grid, FWD_PAIRS * 64, smem, snb::as_stream(stream)>>>(*p, packed, x, (long)ldx, y, (long)ldy, bias,
-                                                                           ckpt, (long)B, g, per_warp);
+    sss_fwd_kernel<<<grid, FWD_THREADS, smem, snb::as_stream(stream)>>>(*p, packed, x, (long)ldx, y, (long)ldy, bias, ckpt, (long)B,
+                                                                        g, sm, aligned);
     SN_CHECK_LAUNCH("sss_fwd_kernel");
     return 0;
 }

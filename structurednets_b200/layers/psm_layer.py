@@ -99,6 +99,7 @@ class PSMLayer(StructuredLayer):
 
         self.input_dim = input_dim
         self.sparse_matrices = nn.ParameterList([self.scipy_csr_to_torch(mat) for mat in sparse_matrices])
+        self._base_nnz = [int(p._nnz()) for p in self.sparse_matrices]
         shapes = [tuple(p.shape) for p in self.sparse_matrices]
         assert shapes[0][0] == output_dim and shapes[-1][1] == input_dim, "The sparse factors do not map input_dim -> output_dim"
         for a, b in zip(shapes[:-1], shapes[1:]):
@@ -137,6 +138,13 @@ class PSMLayer(StructuredLayer):
             U = U.float()
         if U.stride(1) != 1:
             U = U.contiguous()
+        # torch's sparse SGD update on CUDA (param.add_(sparse_grad)) concatenates the indices instead of summing
+        # matching entries, so nnz grows with every step; fold duplicates back before using the pattern.
+        for k, p in enumerate(self.sparse_matrices):
+            if p._nnz() != self._base_nnz[k]:
+                with torch.no_grad():
+                    p.data = p.detach().coalesce()
+                self._base_nnz[k] = int(p._nnz())
         return _PSMFunction.apply(U, self.bias if self.use_bias else None, self, *self.sparse_matrices)
 
     forward_sparse = forward   # the reference's alternative torch.sparse.mm path (psm_layer.py:36-45): same math

@@ -222,7 +222,7 @@ class SSSLayer(FlatParamsMixin, StructuredLayer):
         ru4 = lambda v: int(max(4, (int(v) + 3) // 4 * 4))
         rows_pad, k_pad = ru4(rows.max()), ru4(ks.max())
         d_pad = ru4(max(stages[:, :, 4].max(), stages[:, :, 5].max()))
-        blk = 2 * rows_pad * k_pad
+        blk = 8 + 2 * rows_pad * k_pad   # 8-float descriptor header + Pt + P (csrc/sss.cu)
         for d in range(2):
             for kk in range(n):
                 stages[d, kk, 10] = (d * n + kk) * blk
@@ -244,13 +244,17 @@ class SSSLayer(FlatParamsMixin, StructuredLayer):
                 ncols = int(st[:, 1].sum())
                 row0 = int(st[:, 2].min())
                 nrows = int(st[:, 3].sum())
-                chunks[d].append([s, e_, col0, ncols, row0, nrows, second, 0])
+                mid = s + (e_ - s + 1) // 2
+                sa, sb = stages[d, s:mid], stages[d, mid:e_]
+                col0_a, ncols_a = int(sa[:, 0].min()), int(sa[:, 1].sum())
+                col0_b, ncols_b = (int(sb[:, 0].min()), int(sb[:, 1].sum())) if len(sb) else (col0_a, 0)
+                chunks[d].append([s, e_, col0, ncols, row0, nrows, second, mid, col0_a, ncols_a, col0_b, ncols_b, 0, 0, 0, 0])
         assert len(chunks[0]) == len(chunks[1])
         chunks = np.asarray(chunks, dtype=np.int32)
         meta = dict(nb_states=n, input_dim=self.input_dim, output_dim=self.output_dim, rows_pad=rows_pad, k_pad=k_pad,
                     d_pad=d_pad, nchunks=chunks.shape[1], chunk_in_max=int(chunks[:, :, 3].max()),
                     chunk_out_max=int(max(1, chunks[:, :, 5].max())), chunk_len_max=int((chunks[:, :, 1] - chunks[:, :, 0]).max()),
-                    nparams=int(self.__dict__["_flat_total"]))
+                    nparams=int(self.__dict__["_flat_total"]), half_in_max=int(max(chunks[:, :, 9].max(), chunks[:, :, 11].max())))
         return stages, chunks, meta
 
     def _device_plan(self, device):

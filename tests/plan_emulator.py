@@ -35,7 +35,7 @@ def forward(stages, chunks, meta, flat, X, bias):
             order += [(d, ch) for ch in range(chunks.shape[1]) if chunks[d, ch, 6] == second]
     state = {0: np.zeros((0, B), np.float32), 1: np.zeros((0, B), np.float32)}
     for (d, ch) in order:
-        kb, ke, col0, ncols, row0, nrows, second, _ = chunks[d, ch]
+        kb, ke, col0, ncols, row0, nrows, second = chunks[d, ch][:7]
         ckpt[(d, ch)] = state[d].copy()
         yc = np.zeros((nrows, B), np.float32)
         for kk in range(kb, ke):
@@ -59,7 +59,7 @@ def backward(stages, chunks, meta, flat, X, gy, ckpt):
     for d in range(2):
         lcar = np.zeros((0, B), np.float32)
         for ch in range(chunks.shape[1] - 1, -1, -1):
-            kb, ke, col0, ncols, row0, nrows, second, _ = chunks[d, ch]
+            kb, ke, col0, ncols, row0, nrows, second = chunks[d, ch][:7]
             xs = [ckpt[(d, ch)]]
             for kk in range(kb, ke - 1):
                 in_off, in_dim, out_off, out_dim, d_in, d_out = stages[d, kk, :6]
