@@ -330,8 +330,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sss", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--global-batch", type=int, default=None, help="profiling only: override the workload's global batch")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]()
+    if args.global_batch:
+        wl.global_batch = args.global_batch
     if args.impl == "reference":
         run_reference(args, wl)
     else:

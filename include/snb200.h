@@ -90,9 +90,11 @@ int sn_sss_pack(const sn_sss_plan* plan_host, const float* params, float* packed
 int sn_sss_forward(const sn_sss_plan* plan_host, const float* packed, const float* x, int64_t ldx,
                    float* y, int64_t ldy, const float* bias, float* ckpt, int64_t B, sn_stream_t stream);
 /* grad_params (flat, same layout as params) += d loss / d params ; grad_bias (may be NULL) += column
- * sums of grad_y.  grad_x (may be NULL) receives d loss / d x (overwritten). */
+ * sums of grad_y.  grad_x (may be NULL) receives d loss / d x (overwritten).  workspace: scratch of
+ * sn_sss_backward_workspace_floats() floats (packed per-stage gradient accumulators). */
+size_t sn_sss_backward_workspace_floats(const sn_sss_plan* plan_host);
 int sn_sss_backward(const sn_sss_plan* plan_host, const float* packed, const float* x, int64_t ldx,
-                    const float* grad_y, int64_t ldgy, const float* ckpt, float* grad_params,
+                    const float* grad_y, int64_t ldgy, const float* ckpt, float* workspace, float* grad_params,
                     float* grad_bias, float* grad_x, int64_t ldgx, int64_t B, sn_stream_t stream);
 
 #ifdef __cplusplus

@@ -50,7 +50,9 @@ def _declare(lib):
     lib.sn_sss_forward.restype = c_int
     lib.sn_sss_forward.argtypes = [P, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p]
     lib.sn_sss_backward.restype = c_int
-    lib.sn_sss_backward.argtypes = [P, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+    lib.sn_sss_backward_workspace_floats.restype = c_size_t
+    lib.sn_sss_backward_workspace_floats.argtypes = [P]
+    lib.sn_sss_backward.argtypes = [P, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_int64, c_int64, c_void_p]
     i64, i32, vp = c_int64, c_int, c_void_p
     lib.sn_lr_forward_f32.restype = c_int

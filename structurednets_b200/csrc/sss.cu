@@ -157,6 +157,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// producer-side wait: back off between probes so the spinning lane does not steal issue slots from the math warps
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(200);
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -196,7 +210,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 //   Sample <-> position map inside a warp: position p = 4*q + t  holds local sample  q + NQ*t.
 // ------------------------------------------------------------------------------------------
 constexpr int FWD_PAIRS = 3;
-constexpr int FWD_SLOTS = 4;
+constexpr int FWD_SLOTS = 6;
 constexpr int FWD_CONSUMERS = 2 * FWD_PAIRS;
 constexpr int FWD_THREADS = (FWD_CONSUMERS + 1) * 32;
 
@@ -225,6 +239,8 @@ inline FwdSmem make_fwd_smem(const sn_sss_plan& p, const Geom& g) {
     s.total = s.warp_off + FWD_CONSUMERS * s.per_warp;
     return s;
 }
+
+__device__ __forceinline__ int pos_of(int ls, int nq) { return 4 * (ls % nq) + ls / nq; }
 
 // input columns [col0, col0+ncols) of the warp's samples -> ub[ls][uoff + (col - col0)]; returns uoff
 __device__ __forceinline__ int issue_u_load(const float* __restrict__ x, long ldx, long s0, long B, int in_dim, int nsw, int uw,
@@ -276,16 +292,15 @@ sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
 
     if (warp == FWD_CONSUMERS) {
         // ---------------- producer ----------------
-        if (lane == 0) {
+        if (lane < 2) {   // lane d feeds direction d
+            const int d = lane;
             const uint32_t bytes = (uint32_t)sm.slot_floats * 4u;
             const size_t blk = SSS_HDR + 2 * (size_t)plan.k_pad * RP;
             for (int kk = 0; kk < n; ++kk) {
                 const int sl = kk % FWD_SLOTS, round = kk / FWD_SLOTS;
-                for (int d = 0; d < 2; ++d) {
-                    if (round > 0) mbar_wait(empty_bar(d, sl), (round - 1) & 1);
-                    mbar_arrive_expect_tx(full_bar(d, sl), bytes);
-                    bulk_g2s(ring + (size_t)(d * FWD_SLOTS + sl) * sm.slot_floats, packed + ((size_t)d * n + kk) * blk, bytes, full_bar(d, sl));
-                }
+                if (round > 0) mbar_wait_backoff(empty_bar(d, sl), (round - 1) & 1);
+                mbar_arrive_expect_tx(full_bar(d, sl), bytes);
+                bulk_g2s(ring + (size_t)(d * FWD_SLOTS + sl) * sm.slot_floats, packed + ((size_t)d * n + kk) * blk, bytes, full_bar(d, sl));
             }
         }
         return;
@@ -297,7 +312,8 @@ sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
     float* wbase = smem + sm.warp_off + (size_t)warp * sm.per_warp;
     float* xs = wbase + sm.xs;
     float* xn = wbase + sm.xn;
-    float* ubuf[2] = {wbase + sm.ub0, wbase + sm.ub1};
+    float* const ub_a = wbase + sm.ub0;
+    float* const ub_b = wbase + sm.ub1;
     float* yb = wbase + sm.yb;
     const sn_sss_chunk* chunks = plan.chunks + (size_t)dir * plan.nchunks;
     const int rg_slot = lane / g.nq, q = lane - rg_slot * g.nq;
@@ -309,7 +325,7 @@ sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
     int uoff_cur;
 
     sn_sss_chunk c = chunks[0];
-    uoff_cur = issue_u_load(x, ldx, s0, B, plan.input_dim, nsw, uw, x_aligned != 0, c.col0_a, c.ncols_a, ubuf[0], lane);
+    uoff_cur = issue_u_load(x, ldx, s0, B, plan.input_dim, nsw, uw, x_aligned != 0, c.col0_a, c.ncols_a, ub_a, lane);
     cp_async_commit();
 
     for (int ch = 0; ch < plan.nchunks; ++ch) {
@@ -327,15 +343,15 @@ sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
             int uoff_next = 0;
             bool issued = false;
             if (half == 0) {
-                if (c.kk_mid < c.kk_end) { uoff_next = issue_u_load(x, ldx, s0, B, plan.input_dim, nsw, uw, x_aligned != 0, c.col0_b, c.ncols_b, ubuf[ubi ^ 1], lane); issued = true; }
+                if (c.kk_mid < c.kk_end) { uoff_next = issue_u_load(x, ldx, s0, B, plan.input_dim, nsw, uw, x_aligned != 0, c.col0_b, c.ncols_b, (ubi ? ub_a : ub_b), lane); issued = true; }
             } else if (ch + 1 < plan.nchunks) {
-                uoff_next = issue_u_load(x, ldx, s0, B, plan.input_dim, nsw, uw, x_aligned != 0, cnext.col0_a, cnext.ncols_a, ubuf[ubi ^ 1], lane); issued = true;
+                uoff_next = issue_u_load(x, ldx, s0, B, plan.input_dim, nsw, uw, x_aligned != 0, cnext.col0_a, cnext.ncols_a, (ubi ? ub_a : ub_b), lane); issued = true;
             }
             cp_async_commit();
             cp_async_wait<1>();
             __syncwarp();
             if (kb < ke) {
-                const float* ub = ubuf[ubi];
+                const float* ub = ubi ? ub_b : ub_a;
                 for (int kk = kb; kk < ke; ++kk) {
                     const int sl = kk % FWD_SLOTS;
                     mbar_wait(full_bar(dir, sl), (kk / FWD_SLOTS) & 1);
@@ -347,8 +363,7 @@ sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
                         float* cbase = ckpt + ((size_t)(dir * plan.nchunks + ch) * DP) * B;
                         for (int e = lane; e < d_in * nsw; e += 32) {
                             const int f = e / nsw, ls = e - f * nsw;
-                            const int pos = 4 * (ls % nq) + ls / nq;
-                            if (s0 + ls < B) cbase[(size_t)f * B + s0 + ls] = xs[f * nswp + pos];
+                            if (s0 + ls < B) cbase[(size_t)f * B + s0 + ls] = xs[f * nswp + pos_of(ls, nq)];
                         }
                     }
                     if (active) {
@@ -397,16 +412,37 @@ sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
             }
             if (issued) { ubi ^= 1; uoff_cur = uoff_next; }
         }
-        // flush the chunk's outputs: y[s0 + ls][row0 + row]
-        for (int ls = 0; ls < nsw; ++ls) {
-            if (s0 + ls >= B) break;
-            const int pos = 4 * (ls % nq) + ls / nq;
-            float* dst = y + (size_t)(s0 + ls) * ldy + c.row0;
-            for (int row = lane; row < c.nrows; row += 32) {
-                float v = yb[row * nswp + pos];
-                if (c.second_visit) v += __ldcg(dst + row);
-                else if (bias != nullptr) v += __ldg(bias + c.row0 + row);
-                dst[row] = v;
+        // flush the chunk's outputs: y[s0 + ls][row0 + row]; a lane walks rows `lrow + k*rstep` of samples `lsub + k*sstep`
+        {
+            const int rl = c.nrows >= 32 ? 32 : (c.nrows >= 16 ? 16 : (c.nrows >= 8 ? 8 : (c.nrows >= 4 ? 4 : (c.nrows >= 2 ? 2 : 1))));
+            const int spl = 32 / rl;                      // samples handled per warp pass
+            const int lrow = lane % rl, lsub = lane / rl;
+            for (int row = lrow; row < c.nrows; row += rl) {
+                const float bv = (!c.second_visit && bias != nullptr) ? __ldg(bias + c.row0 + row) : 0.f;
+                for (int lsb = 0; lsb < nsw; lsb += 4 * spl) {
+                    float v[4];
+                    float* dst[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int ls = lsb + k * spl + lsub;
+                        const bool ok = ls < nsw && s0 + ls < B;
+                        dst[k] = ok ? y + (size_t)(s0 + ls) * ldy + c.row0 + row : nullptr;
+                        v[k] = ok ? yb[row * nswp + pos_of(ls, nq)] : 0.f;
+                    }
+                    if (c.second_visit) {
+                        float o[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) o[k] = dst[k] ? __ldcg(dst[k]) : 0.f;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) v[k] += o[k];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) v[k] += bv;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (dst[k]) *dst[k] = v[k];
+                }
             }
         }
         __syncwarp();
@@ -417,159 +453,272 @@ sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
 }
 
 // ------------------------------------------------------------------------------------------
-// backward: per (sample tile, direction) CTA; chunks visited in reverse processing order
-//   1. recompute the chunk's entry states from the forward checkpoint          (warp-own samples)
+// backward: CTA = BWD_CONS consumer warps (each owning NSW samples) + 1 producer warp, one direction per CTA
+// (blockIdx.y); chunks are visited in reverse processing order.  Per chunk:
+//   loads   : forward checkpoint, input columns and grad_y rows of the chunk, transposed to feature-major
+//             [feature][position] with 4-byte cp.async, double buffered (issued one chunk ahead);
+//             the chunk's packed parameter blocks (descriptor + Pt + P) arrive as ONE cp.async.bulk issued by
+//             the producer warp while the previous chunk is still in its gradient phase
+//   1. recompute the entry states of the chunk's stages                         (warp-own samples)
 //   2. adjoint sweep  lam_in = P^T [lam_out ; gy]                               (warp-own samples)
-//   3. parameter gradients  dP_k = [lam_out ; gy] [s_in ; u]^T summed over the tile's samples
-//      (warp-own stages, 4x4 register tiles over interleaved rows/cols), atomically added to the
-//      flat gradient buffer at the parameters' natural offsets
+//   3. parameter gradients  dP_k = [lam_out ; gy] [s_in ; u]^T over the tile's samples (warp-own stages,
+//      4x4 register tiles over interleaved rows/cols), atomically accumulated into a packed [r][k_pad]
+//      gradient workspace that sss_unpack_grad_kernel folds into the flat gradient buffer afterwards.
 // ------------------------------------------------------------------------------------------
-constexpr int BWD_WARPS = 2;
+constexpr int BWD_CONS = 2;
+constexpr int BWD_THREADS = (BWD_CONS + 1) * 32;
 
 struct BwdSmem {
-    int nsp;        // padded sample stride of the CTA-wide buffers
-    int xh, lh, lcar, uc, gc, zero, total;  // offsets in floats
+    int nsp;     // padded position stride of the CTA-wide feature-major buffers
+    int blk;     // floats per packed stage block
+    int hs;      // one history entry (d_pad * nsp)
+    int params, bars, xh, lh, lcar0, lcar1, ck0, ck1, ut0, ut1, gt0, gt1, zero, total;   // float offsets
 };
 
 inline BwdSmem make_bwd_smem(const sn_sss_plan& p, const Geom& g) {
     BwdSmem s;
-    int ns = BWD_WARPS * g.nsw;
+    const int ns = BWD_CONS * g.nsw;
     s.nsp = pad_stride(ns);
+    s.blk = SSS_HDR + 2 * p.k_pad * p.rows_pad;
+    s.hs = p.d_pad * s.nsp;
+    const int hist = p.chunk_len_max > 1 ? p.chunk_len_max - 1 : 1;
     int o = 0;
-    s.xh = o;   o += p.chunk_len_max * p.d_pad * s.nsp;
-    s.lh = o;   o += p.chunk_len_max * p.d_pad * s.nsp;
-    s.lcar = o; o += p.d_pad * s.nsp;
-    s.uc = o;   o += p.chunk_in_max * s.nsp;
-    s.gc = o;   o += p.chunk_out_max * s.nsp;
-    s.zero = o; o += s.nsp;
+    s.params = o; o += round_up(p.chunk_len_max * s.blk, 4);
+    s.bars = o;   o += 4;
+    s.xh = o;     o += hist * s.hs;
+    s.lh = o;     o += hist * s.hs;
+    s.lcar0 = o;  o += s.hs;
+    s.lcar1 = o;  o += s.hs;
+    s.ck0 = o;    o += s.hs;
+    s.ck1 = o;    o += s.hs;
+    s.ut0 = o;    o += p.chunk_in_max * s.nsp;
+    s.ut1 = o;    o += p.chunk_in_max * s.nsp;
+    s.gt0 = o;    o += p.chunk_out_max * s.nsp;
+    s.gt1 = o;    o += p.chunk_out_max * s.nsp;
+    s.zero = o;   o += s.nsp;
     s.total = o;
     return s;
 }
 
-__global__ void __launch_bounds__(BWD_WARPS * 32)
+// issue the (transposing) loads of one chunk for the calling warp's samples
+__device__ __forceinline__ void bwd_issue_loads(const sn_sss_plan& plan, const sn_sss_chunk& c, int d_first, int dir, int ch,
+                                                const float* __restrict__ x, long ldx, const float* __restrict__ gy, long ldgy,
+                                                const float* __restrict__ ckpt, long B, long samp0, int w0, int nsw, int nq, int nsp,
+                                                float* ck, float* ut, float* gt, int lane) {
+    const float* cbase = ckpt + ((size_t)(dir * plan.nchunks + ch) * plan.d_pad) * B;
+    for (int ls = lane; ls < nsw; ls += 32) {
+        const int pos = w0 + pos_of(ls, nq);
+        const bool ok = samp0 + ls < B;
+        for (int f = 0; f < d_first; ++f) cp_async4(ck + f * nsp + pos, ok ? (const void*)(cbase + (size_t)f * B + samp0 + ls) : (const void*)x, ok);
+    }
+    for (int ls = 0; ls < nsw; ++ls) {
+        const int pos = w0 + pos_of(ls, nq);
+        const bool ok = samp0 + ls < B;
+        const float* xr = x + (size_t)(samp0 + ls) * ldx + c.col0;
+        for (int cc = lane; cc < c.ncols; cc += 32) cp_async4(ut + cc * nsp + pos, ok ? (const void*)(xr + cc) : (const void*)x, ok);
+        const float* gr = gy + (size_t)(samp0 + ls) * ldgy + c.row0;
+        for (int rr = lane; rr < c.nrows; rr += 32) cp_async4(gt + rr * nsp + pos, ok ? (const void*)(gr + rr) : (const void*)x, ok);
+    }
+}
+
+__global__ void __launch_bounds__(BWD_THREADS)
 sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* __restrict__ x, long ldx,
                const float* __restrict__ gy, long ldgy, const float* __restrict__ ckpt,
-               float* __restrict__ gparams, float* __restrict__ gbias, long B, Geom g, BwdSmem sm) {
-    extern __shared__ __align__(16) float smem[];
+               float* __restrict__ gpacked, float* __restrict__ gbias, long B, Geom g, BwdSmem sm) {
+    extern __shared__ __align__(128) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
     const int n = plan.nb_states, DP = plan.d_pad, RP = plan.rows_pad, KP = plan.k_pad;
-    const int NS = BWD_WARPS * g.nsw, NSP = sm.nsp;
-    const long t0 = (long)blockIdx.x * NS;      // first sample of the tile
-    const int w0 = warp * g.nsw;                // this warp's first column inside the tile
-    float* xh = smem + sm.xh;
-    float* lh = smem + sm.lh;
-    float* lcar = smem + sm.lcar;
-    float* uc = smem + sm.uc;
-    float* gc = smem + sm.gc;
-    float* zr = smem + sm.zero;
-    const sn_sss_stage* stages = plan.stages + (size_t)dir * n;
+    const int NS = BWD_CONS * g.nsw, NSP = sm.nsp, hs = sm.hs;
     const sn_sss_chunk* chunks = plan.chunks + (size_t)dir * plan.nchunks;
-    const int rg_slot = lane / g.nq, q = lane - rg_slot * g.nq;
-    const int rgs_state = (DP / 4 < g.rgs) ? DP / 4 : g.rgs;   // slots used by state-only loops
-    const size_t hstride = (size_t)DP * NSP;                    // one history entry
+    const sn_sss_stage* stages = plan.stages + (size_t)dir * n;
+    float* params = smem + sm.params;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + sm.bars);
+    uint64_t* empty_bar = full_bar + 1;
 
-    for (int e = threadIdx.x; e < NSP; e += blockDim.x) zr[e] = 0.f;
-    for (int e = threadIdx.x; e < DP * NSP; e += blockDim.x) lcar[e] = 0.f;
+    if (threadIdx.x == 0) {
+        mbar_init(full_bar, 1);
+        mbar_init(empty_bar, BWD_CONS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int e = threadIdx.x; e < NSP; e += BWD_THREADS) smem[sm.zero + e] = 0.f;
+    for (int e = threadIdx.x; e < 2 * hs; e += BWD_THREADS) smem[sm.lcar0 + e] = 0.f;   // lcar0 and lcar1 are adjacent
     __syncthreads();
 
-    for (int ch = plan.nchunks - 1; ch >= 0; --ch) {
-        const sn_sss_chunk c = chunks[ch];
-        const int len = c.kk_end - c.kk_begin;
-        // ---- loads (warp-own samples) --------------------------------------------------
-        {
-            const int d = stages[c.kk_begin].d_in;
-            const float* cbase = ckpt + ((size_t)(dir * plan.nchunks + ch) * DP) * B;
-            for (int e = lane; e < d * g.nsw; e += 32) {
-                int f = e / g.nsw, s = e - f * g.nsw;
-                float v = 0.f;
-                if (t0 + w0 + s < B) v = __ldg(cbase + (size_t)f * B + t0 + w0 + s);
-                xh[f * NSP + w0 + s] = v;
-            }
-            for (int e = lane; e < g.nsw * c.ncols; e += 32) {
-                int s = e / c.ncols, cc = e - s * c.ncols;
-                float v = 0.f;
-                if (t0 + w0 + s < B) v = __ldg(x + (size_t)(t0 + w0 + s) * ldx + c.col0 + cc);
-                uc[cc * NSP + w0 + s] = v;
-            }
-            for (int e = lane; e < g.nsw * c.nrows; e += 32) {
-                int s = e / c.nrows, rr = e - s * c.nrows;
-                float v = 0.f;
-                if (t0 + w0 + s < B) v = __ldg(gy + (size_t)(t0 + w0 + s) * ldgy + c.row0 + rr);
-                gc[rr * NSP + w0 + s] = v;
-            }
-            // adjoint of the state leaving the chunk's last stage = carry from the later chunk
-            const int dl = stages[c.kk_end - 1].d_out;
-            for (int e = lane; e < dl * g.nsw; e += 32) {
-                int f = e / g.nsw, s = e - f * g.nsw;
-                lh[(size_t)(len - 1) * hstride + f * NSP + w0 + s] = lcar[f * NSP + w0 + s];
+    if (warp == BWD_CONS) {
+        // ---------------- producer: one bulk copy per chunk ----------------
+        if (lane == 0) {
+            int it = 0;
+            for (int ch = plan.nchunks - 1; ch >= 0; --ch, ++it) {
+                const sn_sss_chunk c = chunks[ch];
+                const uint32_t bytes = (uint32_t)((c.kk_end - c.kk_begin) * sm.blk) * 4u;
+                if (it > 0) mbar_wait_backoff(empty_bar, (it - 1) & 1);
+                mbar_arrive_expect_tx(full_bar, bytes);
+                bulk_g2s(params, packed + ((size_t)dir * n + c.kk_begin) * sm.blk, bytes, full_bar);
             }
         }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const long t0 = (long)blockIdx.x * NS;
+    const int w0 = warp * g.nsw;
+    const long samp0 = t0 + w0;
+    const int nq = g.nq, nsw = g.nsw;
+    const int rg_slot = lane / nq, q = lane - rg_slot * nq;
+    const int rgs_state = (DP / 4 < g.rgs) ? DP / 4 : g.rgs;
+    const int RP4 = RP >> 2, KP4 = KP >> 2;
+    float* xh = smem + sm.xh;
+    float* lh = smem + sm.lh;
+    float* lcar_cur = smem + sm.lcar0;
+    float* lcar_nxt = smem + sm.lcar1;
+    const float* zr = smem + sm.zero;
+    int buf = 0;
+
+    sn_sss_chunk c = chunks[plan.nchunks - 1];
+    int d_first = stages[c.kk_begin].d_in;
+    bwd_issue_loads(plan, c, d_first, dir, plan.nchunks - 1, x, ldx, gy, ldgy, ckpt, B, samp0, w0, nsw, nq, NSP, smem + sm.ck0, smem + sm.ut0,
+                    smem + sm.gt0, lane);
+    cp_async_commit();
+
+    int it = 0;
+    for (int ch = plan.nchunks - 1; ch >= 0; --ch, ++it) {
+        const int len = c.kk_end - c.kk_begin;
+        float* ck = smem + (buf ? sm.ck1 : sm.ck0);
+        float* ut = smem + (buf ? sm.ut1 : sm.ut0);
+        float* gt = smem + (buf ? sm.gt1 : sm.gt0);
+        sn_sss_chunk cn = c;
+        int d_first_n = 0;
+        if (ch > 0) {
+            cn = chunks[ch - 1];
+            d_first_n = stages[cn.kk_begin].d_in;
+            bwd_issue_loads(plan, cn, d_first_n, dir, ch - 1, x, ldx, gy, ldgy, ckpt, B, samp0, w0, nsw, nq, NSP, smem + (buf ? sm.ck0 : sm.ck1),
+                            smem + (buf ? sm.ut0 : sm.ut1), smem + (buf ? sm.gt0 : sm.gt1), lane);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
         __syncwarp();
-        // ---- 1. recompute entry states of stages 1..len-1 ------------------------------
+        mbar_wait(full_bar, it & 1);
+
+        // ---- 1. recompute entry states of stages 1..len-1 (own samples) -------------------------
         for (int j = 0; j + 1 < len; ++j) {
-            const sn_sss_stage st = stages[c.kk_begin + j];
+            const float* slot = params + (size_t)j * sm.blk;
+            const int* hdr = reinterpret_cast<const int*>(slot);
+            const int in_off = hdr[0], in_dim = hdr[1], d_in = hdr[4], d_out = hdr[5];
+            const float* xin = (j == 0 ? ck : xh + (size_t)(j - 1) * hs) + w0 + 4 * q;
+            float* xout = xh + (size_t)j * hs + w0 + 4 * q;
+            const float* uv0 = ut + (size_t)(in_off - c.col0) * NSP + w0 + 4 * q;
             if (rg_slot < rgs_state) {
-                stage_step(st, packed, RP, xh + j * hstride + w0, xh + (j + 1) * hstride + w0, uc + w0, nullptr, NSP,
-                           st.in_off - c.col0, 0, ceil_div(st.d_out, 4), rg_slot, rgs_state, q);
+                const int nrg = (d_out + 3) >> 2;
+                for (int rg = rg_slot; rg < nrg; rg += rgs_state) {
+                    float acc[4][4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+                    const float4* prow = reinterpret_cast<const float4*>(slot + SSS_HDR) + rg;
+                    const float* xv = xin;
+#pragma unroll 4
+                    for (int i = 0; i < d_in; ++i) {
+                        const float4 p = prow[0];
+                        const float4 v = *reinterpret_cast<const float4*>(xv);
+                        prow += RP4; xv += NSP;
+                        fma16(acc, p, v);
+                    }
+                    const float* uv = uv0;
+#pragma unroll 4
+                    for (int i = 0; i < in_dim; ++i) {
+                        const float4 p = prow[0];
+                        const float4 v = *reinterpret_cast<const float4*>(uv);
+                        prow += RP4; uv += NSP;
+                        fma16(acc, p, v);
+                    }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int r = 4 * rg + a;
+                        if (r < d_out) *reinterpret_cast<float4*>(xout + r * NSP) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+                    }
+                }
             }
             __syncwarp();
         }
-        // ---- 2. adjoint sweep -----------------------------------------------------------
+        // ---- 2. adjoint sweep (own samples) -----------------------------------------------------
         for (int j = len - 1; j >= 0; --j) {
-            const sn_sss_stage st = stages[c.kk_begin + j];
-            const float4* P4 = reinterpret_cast<const float4*>(packed + st.pack_off + SSS_HDR + (size_t)KP * RP);
-            const int KP4 = KP >> 2;
-            const float* lout = lh + j * hstride + w0;                          // adjoint of s_out
-            const float* gyj = gc + (size_t)(st.out_off - c.row0) * NSP + w0;   // adjoint of y_k
-            float* lin = (j > 0) ? (lh + (j - 1) * hstride + w0) : (lcar + w0);
-            const int nig = ceil_div(st.d_in, 4);
+            const float* slot = params + (size_t)j * sm.blk;
+            const int* hdr = reinterpret_cast<const int*>(slot);
+            const int out_off = hdr[2], out_dim = hdr[3], d_in = hdr[4], d_out = hdr[5];
+            const float4* P4 = reinterpret_cast<const float4*>(slot + SSS_HDR + KP * RP);
+            const float* lout = (j == len - 1 ? lcar_cur : lh + (size_t)j * hs) + w0 + 4 * q;
+            const float* gyj = gt + (size_t)(out_off - c.row0) * NSP + w0 + 4 * q;
+            float* lin = (j == 0 ? lcar_nxt : lh + (size_t)(j - 1) * hs) + w0 + 4 * q;
             if (rg_slot < rgs_state) {
+                const int nig = (d_in + 3) >> 2;
                 for (int ig = rg_slot; ig < nig; ig += rgs_state) {
                     float acc[4][4];
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
 #pragma unroll
                         for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+                    const float4* prow = P4 + ig;
+                    const float* lv = lout;
 #pragma unroll 4
-                    for (int r = 0; r < st.d_out; ++r) {
-                        float4 p = __ldg(P4 + (size_t)r * KP4 + ig);
-                        float4 v = *reinterpret_cast<const float4*>(lout + r * NSP + 4 * q);
+                    for (int r = 0; r < d_out; ++r) {
+                        const float4 p = prow[0];
+                        const float4 v = *reinterpret_cast<const float4*>(lv);
+                        prow += KP4; lv += NSP;
                         fma16(acc, p, v);
                     }
-                    for (int r = 0; r < st.out_dim; ++r) {
-                        float4 p = __ldg(P4 + (size_t)(st.d_out + r) * KP4 + ig);
-                        float4 v = *reinterpret_cast<const float4*>(gyj + r * NSP + 4 * q);
+                    const float* gv = gyj;
+                    for (int r = 0; r < out_dim; ++r) {
+                        const float4 p = prow[0];
+                        const float4 v = *reinterpret_cast<const float4*>(gv);
+                        prow += KP4; gv += NSP;
                         fma16(acc, p, v);
                     }
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        int i = 4 * ig + jj;
-                        if (i < st.d_in)
-                            *reinterpret_cast<float4*>(lin + i * NSP + 4 * q) =
-                                make_float4(acc[jj][0], acc[jj][1], acc[jj][2], acc[jj][3]);
+                    for (int a = 0; a < 4; ++a) {
+                        const int i = 4 * ig + a;
+                        if (i < d_in) *reinterpret_cast<float4*>(lin + i * NSP) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
                     }
                 }
             }
             __syncwarp();
         }
-        __syncthreads();
-        // ---- 3. parameter gradients (warp-own stages, all samples of the tile) -------------
-        if (gbias != nullptr && dir == 0) {
-            for (int rr = threadIdx.x; rr < c.nrows; rr += blockDim.x) {
-                float s = 0.f;
-                for (int e = 0; e < NS; ++e) s += gc[rr * NSP + e];
-                atomicAdd(gbias + c.row0 + rr, s);
+        // stage descriptors needed by the gradient phase are copied out before the parameter buffer is released
+        int h_in_off[2], h_in_dim[2], h_out_off[2], h_out_dim[2], h_d_in[2], h_d_out[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int j = warp + u * BWD_CONS;
+            if (j < len) {
+                const int* hdr = reinterpret_cast<const int*>(params + (size_t)j * sm.blk);
+                h_in_off[u] = hdr[0]; h_in_dim[u] = hdr[1]; h_out_off[u] = hdr[2]; h_out_dim[u] = hdr[3]; h_d_in[u] = hdr[4]; h_d_out[u] = hdr[5];
             }
         }
-        for (int j = warp; j < len; j += BWD_WARPS) {
-            const sn_sss_stage st = stages[c.kk_begin + j];
-            const int rows = st.d_out + st.out_dim, K = st.d_in + st.in_dim;
-            const int rgn = ceil_div(rows, 4), cgn = ceil_div(K, 4);
-            const float* lout = lh + j * hstride;
-            const float* gyj = gc + (size_t)(st.out_off - c.row0) * NSP;
-            const float* xin = xh + j * hstride;
-            const float* uj = uc + (size_t)(st.in_off - c.col0) * NSP;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar);          // producer may overwrite the parameter buffer now
+        named_bar_sync(1, BWD_CONS * 32);
+        // ---- 3. parameter gradients (own stages, all positions of the tile) -----------------------
+        if (gbias != nullptr && dir == 0) {
+            for (int rr = threadIdx.x; rr < c.nrows; rr += BWD_CONS * 32) {
+                float sacc = 0.f;
+                const float* gr = gt + (size_t)rr * NSP;
+                for (int e = 0; e < NS; ++e) sacc += gr[e];
+                atomicAdd(gbias + c.row0 + rr, sacc);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {            // chunk_len_max <= 2*BWD_CONS is checked on the host
+            const int j = warp + u * BWD_CONS;
+            if (j >= len) break;
+            const int in_off = h_in_off[u], in_dim = h_in_dim[u], out_off = h_out_off[u], out_dim = h_out_dim[u], d_in = h_d_in[u], d_out = h_d_out[u];
+            const int rows = d_out + out_dim, K = d_in + in_dim;
+            const int rgn = (rows + 3) >> 2, cgn = (K + 3) >> 2;
+            const float* lout = (j == len - 1 ? lcar_cur : lh + (size_t)j * hs);
+            const float* gyj = gt + (size_t)(out_off - c.row0) * NSP;
+            const float* xin = (j == 0 ? ck : xh + (size_t)(j - 1) * hs);
+            const float* uj = ut + (size_t)(in_off - c.col0) * NSP;
+            float* gblk = gpacked + ((size_t)dir * n + c.kk_begin + j) * ((size_t)RP * KP);
             for (int t = lane; t < rgn * cgn; t += 32) {
                 const int rg = t / cgn, cg = t - rg * cgn;
                 const float* gp[4];
@@ -577,18 +726,19 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
                 int rr[4], ii[4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
-                    int r = rg + a * rgn;
+                    const int r = rg + a * rgn;
                     rr[a] = r;
-                    gp[a] = (r < st.d_out) ? (lout + r * NSP) : (r < rows ? gyj + (r - st.d_out) * NSP : zr);
-                    int i = cg + a * cgn;
+                    gp[a] = (r < d_out) ? (lout + r * NSP) : (r < rows ? gyj + (r - d_out) * NSP : zr);
+                    const int i = cg + a * cgn;
                     ii[a] = i;
-                    ip[a] = (i < st.d_in) ? (xin + i * NSP) : (i < K ? uj + (i - st.d_in) * NSP : zr);
+                    ip[a] = (i < d_in) ? (xin + i * NSP) : (i < K ? uj + (i - d_in) * NSP : zr);
                 }
                 float acc[4][4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
                     for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 2
                 for (int sq = 0; sq < NS; sq += 4) {
                     float4 gv[4], iv[4];
 #pragma unroll
@@ -608,27 +758,45 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
                 }
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
-                    const int r = rr[a];
-                    if (r >= rows) continue;
+                    if (rr[a] >= rows) continue;
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
-                        const int i = ii[b];
-                        if (i >= K) continue;
-                        int off;
-                        if (r < st.d_out) {
-                            off = (i < st.d_in) ? st.off_ss + r * st.d_in + i : st.off_su + r * st.in_dim + (i - st.d_in);
-                        } else {
-                            const int ry = r - st.d_out;
-                            if (i < st.d_in) off = st.off_ys + ry * st.d_in + i;
-                            else if (st.off_yu >= 0) off = st.off_yu + ry * st.in_dim + (i - st.d_in);
-                            else continue;
-                        }
-                        atomicAdd(gparams + off, acc[a][b]);
+                        if (ii[b] >= K) continue;
+                        atomicAdd(gblk + (size_t)rr[a] * KP + ii[b], acc[a][b]);
                     }
                 }
             }
         }
-        __syncthreads();
+        named_bar_sync(1, BWD_CONS * 32);
+        { float* tsw = lcar_cur; lcar_cur = lcar_nxt; lcar_nxt = tsw; }
+        buf ^= 1;
+        c = cn;
+        d_first = d_first_n;
+    }
+    cp_async_wait<0>();
+}
+
+// flat gradient += packed gradient (one block per (direction, stage); every parameter entry has exactly one
+// packed entry, so no atomics)
+__global__ void sss_unpack_grad_kernel(const sn_sss_stage* __restrict__ stages, int total_stages, int RP, int KP,
+                                       const float* __restrict__ gpacked, float* __restrict__ gflat) {
+    const int sidx = blockIdx.x;
+    if (sidx >= total_stages) return;
+    const sn_sss_stage st = stages[sidx];
+    const int K = st.d_in + st.in_dim, rows = st.d_out + st.out_dim;
+    const float* G = gpacked + (size_t)sidx * RP * KP;
+    for (int e = threadIdx.x; e < rows * K; e += blockDim.x) {
+        const int r = e / K, i = e - r * K;
+        int off;
+        if (r < st.d_out) {
+            off = (i < st.d_in) ? st.off_ss + r * st.d_in + i : st.off_su + r * st.in_dim + (i - st.d_in);
+        } else {
+            const int ry = r - st.d_out;
+            if (i < st.d_in) off = st.off_ys + ry * st.d_in + i;
+            else if (st.off_yu >= 0) off = st.off_yu + ry * st.in_dim + (i - st.d_in);
+            else continue;
+        }
+        gflat[off] += G[(size_t)r * KP + i];
     }
 }
 
@@ -689,29 +857,38 @@ int sn_sss_forward(const sn_sss_plan* p, const float* packed, const float* x, in
     return 0;
 }
 
+size_t sn_sss_backward_workspace_floats(const sn_sss_plan* p) {
+    if (p == nullptr) return 0;
+    return (size_t)2 * p->nb_states * p->rows_pad * p->k_pad;
+}
+
 int sn_sss_backward(const sn_sss_plan* p, const float* packed, const float* x, int64_t ldx, const float* grad_y,
-                    int64_t ldgy, const float* ckpt, float* grad_params, float* grad_bias, float* grad_x, int64_t ldgx,
-                    int64_t B, sn_stream_t stream) {
+                    int64_t ldgy, const float* ckpt, float* workspace, float* grad_params, float* grad_bias, float* grad_x,
+                    int64_t ldgx, int64_t B, sn_stream_t stream) {
     if (int rc = check_plan(p)) return rc;
     (void)ldgx;
-    SN_CHECK_ARG(packed && x && grad_y && ckpt && grad_params, "sss_backward: NULL buffer");
+    SN_CHECK_ARG(packed && x && grad_y && ckpt && grad_params && workspace, "sss_backward: NULL buffer");
     SN_CHECK_ARG(grad_x == nullptr, "sss_backward: grad_x is not implemented (the reference training loop never needs it)");
     SN_CHECK_ARG(ldx >= p->input_dim && ldgy >= p->output_dim, "sss_backward: leading dimension too small");
     if (B <= 0) return 0;
+    cudaStream_t st = snb::as_stream(stream);
     Geom g = make_geom(p->rows_pad);
     BwdSmem sm = make_bwd_smem(*p, g);
     size_t smem = (size_t)sm.total * sizeof(float);
     SN_CHECK_ARG(smem <= 227 * 1024, "sss_backward: stage dims need %zu bytes of shared memory (> 227 KB)", smem);
+    SN_CHECK_ARG(p->chunk_len_max <= 2 * BWD_CONS, "sss_backward: chunks of more than %d stages are not supported", 2 * BWD_CONS);
     static size_t configured = 0;
     if (smem > configured) {
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    long tile = (long)BWD_WARPS * g.nsw;
+    SN_CHECK_CUDA(cudaMemsetAsync(workspace, 0, sn_sss_backward_workspace_floats(p) * sizeof(float), st));
+    long tile = (long)BWD_CONS * g.nsw;
     dim3 grid((unsigned)((B + tile - 1) / tile), 2);
-    sss_bwd_kernel<<<grid, BWD_WARPS * 32, smem, snb::as_stream(stream)>>>(*p, packed, x, (long)ldx, grad_y, (long)ldgy,
-                                                                          ckpt, grad_params, grad_bias, (long)B, g, sm);
+    sss_bwd_kernel<<<grid, BWD_THREADS, smem, st>>>(*p, packed, x, (long)ldx, grad_y, (long)ldgy, ckpt, workspace, grad_bias, (long)B, g, sm);
     SN_CHECK_LAUNCH("sss_bwd_kernel");
+    sss_unpack_grad_kernel<<<2 * p->nb_states, 128, 0, st>>>(p->stages, 2 * p->nb_states, p->rows_pad, p->k_pad, workspace, grad_params);
+    SN_CHECK_LAUNCH("sss_unpack_grad_kernel");
     return 0;
 }
 

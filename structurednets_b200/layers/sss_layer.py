@@ -19,7 +19,7 @@ from structurednets_b200.layers.flat_params import FlatParamsMixin
 from structurednets_b200.layers.layer_helpers import get_random_glorot_uniform_matrix
 from structurednets_b200.layers.structured_layer import StructuredLayer
 
-SSS_CHUNK_LEN = 8  # stages between two state checkpoints (forward saves them, backward recomputes inside)
+SSS_CHUNK_LEN = 4  # stages between two state checkpoints (forward saves them, backward recomputes inside)
 
 
 def get_nb_parameters(optim_mat_shape: tuple, statespace_dim: int, nb_states: int) -> int:
@@ -111,8 +111,9 @@ class _SSSFunction(torch.autograd.Function):
             grad_y = grad_y.float()
         g = layer._prepare_grad_accumulation()
         gbias = g[:layer.output_dim] if (layer.use_bias and layer.bias.requires_grad) else None
+        ws = layer._backward_workspace(plan)
         rc = _lib.lib().sn_sss_backward(ctypes.byref(plan["struct"]), _lib.ptr(packed), _lib.ptr(U), U.stride(0),
-                                        _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(ckpt), _lib.ptr(g), _lib.ptr(gbias),
+                                        _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(ckpt), _lib.ptr(ws), _lib.ptr(g), _lib.ptr(gbias),
                                         None, 0, U.shape[0], _lib.stream_ptr())
         _lib.check(rc, "sn_sss_backward")
         return None, None, None
@@ -183,6 +184,7 @@ class SSSLayer(FlatParamsMixin, StructuredLayer):
         self.__dict__["_dev_plan"] = None
         self.__dict__["_dev_packed"] = None
         self.__dict__["_dev_packed_version"] = None
+        self.__dict__["_dev_bwd_ws"] = None
 
     def _param_offsets(self):
         """{(list name, k): offset in the flat buffer}; flat order = named_parameters() order."""
@@ -274,6 +276,14 @@ class SSSLayer(FlatParamsMixin, StructuredLayer):
         self.__dict__["_dev_plan"] = plan
         self.__dict__["_dev_packed"] = None
         return plan
+
+    def _backward_workspace(self, plan):
+        ws = self.__dict__.get("_dev_bwd_ws")
+        if ws is None or ws.device != plan["device"]:
+            n = _lib.lib().sn_sss_backward_workspace_floats(ctypes.byref(plan["struct"]))
+            ws = torch.empty(int(n), dtype=torch.float32, device=plan["device"])
+            self.__dict__["_dev_bwd_ws"] = ws
+        return ws
 
     def _packed_params(self, plan):
         """Per-stage re-laid-out copy of the parameters; refreshed when any parameter changed

@@ -1,0 +1,187 @@
+"""The call sites of the hot path: the reference's feature-cache training loop, kept signature-compatible.
+
+Mirror of ``structurednets/training_helpers.py`` (reference :1-181): ``get_batch`` (numpy slice -> torch tensor ->
+device, :31-40), ``get_loss_and_accuracy_for_model`` (:57-73), ``train`` (:107-181: Adam/SGD over
+``model.parameters()``, early stopping on patience, best-model snapshot by ``pickle``, 9-tuple return) and
+``train_with_decreasing_lr`` (:75-105: ten rounds, lr halved from 1).  The loop bodies call ``model(X)`` /
+``loss.backward()`` / ``optimizer.step()`` exactly like the reference, so any of the layers in
+``structurednets_b200.layers`` drops in.
+
+Two reference quirks are kept because callers can observe them (SURVEY.md "smaller reference bugs"):
+the per-epoch "validation" history is computed on the TRAINING set (:151), and ``use_gpu`` silently falls
+back to the CPU device string when CUDA is missing (models/visionmodel.py:5-9) -- the layers themselves then
+raise, because they have no CPU path.
+"""
+import math
+import pickle
+
+import numpy as np
+import torch
+from sklearn.model_selection import train_test_split
+from sklearn.utils import shuffle
+
+
+def get_device(use_gpu=True):
+    """reference models/visionmodel.py:5-9"""
+    if use_gpu:
+        return torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+    return 'cpu'
+
+
+def load_features(path: str):
+    """reference asset_helpers.py:41-46: pickle of [X (N,1,F) or (N,F), y, y_pred]"""
+    with open(path, "rb") as f:
+        X, y, y_pred = pickle.load(f)
+    return np.squeeze(X), y, y_pred
+
+
+def get_number_correct_predictions(y_true: torch.Tensor, y_pred: torch.Tensor):
+    return torch.sum(y_pred.argmax(axis=1) == y_true)
+
+
+def get_accuracy_from_nb_correct_predictions(nb_correct_predictions: torch.Tensor, nb_samples: int):
+    return (nb_correct_predictions / nb_samples).cpu().detach().numpy()
+
+
+def get_accuracy(y_true: torch.Tensor, y_pred: torch.Tensor):
+    return get_accuracy_from_nb_correct_predictions(get_number_correct_predictions(y_true=y_true, y_pred=y_pred), nb_samples=len(y_true))
+
+
+def get_loss(y_true: torch.Tensor, y_pred: torch.Tensor, loss_function_class=torch.nn.CrossEntropyLoss):
+    return loss_function_class()(y_pred, target=y_true).cpu().detach().numpy()
+
+
+def get_train_data(features_path: str):
+    X, y, _ = load_features(features_path)
+    X_train, X_val, y_train, y_val = train_test_split(X, y, test_size=0.2, random_state=42, shuffle=True)
+    return X_train, X_val, y_train, y_val
+
+
+def get_batch(X: np.ndarray, y: np.ndarray, batch_size: int, batch_i: int, use_gpu=False):
+    lo = int(batch_i * batch_size)
+    X_batch = X[lo:min(int((batch_i + 1) * batch_size), X.shape[0])]
+    y_batch = y[lo:min(int((batch_i + 1) * batch_size), y.shape[0])]
+    X_batch_t, y_batch_t = map(torch.tensor, (X_batch, y_batch))
+    device = get_device(use_gpu=use_gpu)
+    return X_batch_t.to(device), y_batch_t.to(device)
+
+
+def get_full_batch(X: np.ndarray, y: np.ndarray, use_gpu=False):
+    return get_batch(X=X, y=y, batch_size=X.shape[0], batch_i=0, use_gpu=use_gpu)
+
+
+def transform_feature_dtypes(X_train, X_val, y_train, y_val):
+    return X_train.astype(np.float32), X_val.astype(np.float32), y_train.astype(np.int64), y_val.astype(np.int64)
+
+
+def train_with_features(model, features_path: str, patience=10, batch_size=1000, verbose=False, lr=1e-6, restore_best_model=True,
+                        loss_function_class=torch.nn.CrossEntropyLoss, use_gpu=False):
+    X_train, X_val, y_train, y_val = transform_feature_dtypes(*get_train_data(features_path))
+    return train(model=model, X_train=X_train, X_val=X_val, y_train=y_train, y_val=y_val, patience=patience, batch_size=batch_size,
+                 verbose=verbose, lr=lr, restore_best_model=restore_best_model, loss_function_class=loss_function_class, use_gpu=use_gpu)
+
+
+def get_loss_and_accuracy_for_model(model, X: np.ndarray, y: np.ndarray, loss_function_class=torch.nn.CrossEntropyLoss, batch_size=1000,
+                                    use_gpu=False):
+    nb_batches_per_epoch = np.ceil(X.shape[0] / batch_size).astype("int")
+    cumulated_loss = 0
+    nb_correct_predictions = 0
+    with torch.no_grad():   # evaluation only (the reference builds and drops a graph here)
+        for batch_i in range(nb_batches_per_epoch):
+            X_batch_t, y_batch_t = get_batch(X, y, batch_size=batch_size, batch_i=batch_i, use_gpu=use_gpu)
+            y_pred = model(X_batch_t)
+            cumulated_loss += get_loss(y_batch_t, y_pred, loss_function_class=loss_function_class)
+            target = y_batch_t.argmax(axis=1) if (len(y.shape) == 2 and y.shape[1] > 1) else y_batch_t
+            nb_correct_predictions += get_number_correct_predictions(y_true=target, y_pred=y_pred)
+    loss = cumulated_loss / nb_batches_per_epoch
+    accuracy = get_accuracy_from_nb_correct_predictions(nb_correct_predictions=nb_correct_predictions, nb_samples=len(y))
+    return loss, accuracy
+
+
+def train_with_decreasing_lr(model, X_train, y_train, X_val=None, y_val=None, patience=10, batch_size=1000, verbose=False,
+                             loss_function_class=torch.nn.CrossEntropyLoss, min_patience_improvement=1e-10,
+                             optimizer_class=torch.optim.SGD, use_gpu=False):
+    if X_val is None or y_val is None:
+        X_train, X_val, y_train, y_val = train_test_split(X_train, y_train, test_size=0.2)
+    lr = 1   # halved after every round; the best model is restored between rounds (reference :81-103)
+    trained_model = model
+    histories = [[] for _ in range(8)]
+    for _ in range(10):
+        res = train(model=trained_model, X_train=X_train, y_train=y_train, X_val=X_val, y_val=y_val, patience=patience, batch_size=batch_size,
+                    verbose=verbose, lr=lr, restore_best_model=True, loss_function_class=loss_function_class,
+                    min_patience_improvement=min_patience_improvement, optimizer_class=optimizer_class, use_gpu=use_gpu)
+        trained_model = res[0]
+        for h, v in zip(histories, res[1:]):
+            h.append(v)
+        lr *= 0.5
+    return (trained_model, *histories)
+
+
+def train(model, X_train, y_train, X_val=None, y_val=None, patience=10, batch_size=1000, verbose=False, lr=1e-6, restore_best_model=True,
+          loss_function_class=torch.nn.CrossEntropyLoss, min_patience_improvement=1e-10, optimizer_class=torch.optim.Adam, use_gpu=False,
+          grad_sync=None):
+    """Same contract as the reference ``train`` (:107-181).  ``grad_sync`` (optional, new): a callable invoked between
+    ``loss.backward()`` and ``optimizer.step()`` -- ``structurednets_b200.distributed.GradSynchronizer`` for data-parallel
+    training (one NCCL all-reduce of the flat gradient buffer)."""
+    if X_val is None or y_val is None:
+        X_train, X_val, y_train, y_val = train_test_split(X_train, y_train, test_size=0.2)
+
+    optimizer = optimizer_class(model.parameters(), lr=lr)
+    loss_function = loss_function_class()
+    nb_batches_per_epoch = np.ceil(X_train.shape[0] / batch_size).astype("int")
+    evaluate = lambda X, y: get_loss_and_accuracy_for_model(model=model, X=X, y=y, loss_function_class=loss_function_class,
+                                                             batch_size=batch_size, use_gpu=use_gpu)
+    start_train_loss, start_train_accuracy = evaluate(X_train, y_train)
+    start_val_loss, start_val_accuracy = evaluate(X_val, y_val)
+    if verbose:
+        print("------ Training Start -------")
+        print("Start Train Loss: " + str(start_train_loss))
+        print("Start Val Loss: " + str(start_val_loss))
+        print("Start Train Accuracy: " + str(start_train_accuracy))
+        print("Start Val Accuracy: " + str(start_val_accuracy))
+
+    train_loss_history, train_accuracy_history, val_loss_history, val_accuracy_history = [], [], [], []
+    best_val_loss = start_val_loss
+    best_model = pickle.loads(pickle.dumps(model))   # the modules are picklable by contract
+
+    continue_training = True
+    epoch = 1
+    while continue_training:
+        X_train_shuffled, y_train_shuffled = shuffle(X_train, y_train)
+        for batch_i in range(nb_batches_per_epoch):
+            X_batch_t, y_batch_t = get_batch(X_train_shuffled, y_train_shuffled, batch_size=batch_size, batch_i=batch_i, use_gpu=use_gpu)
+            outputs_train = model(X_batch_t)
+            loss_train = loss_function(outputs_train, target=y_batch_t)
+            optimizer.zero_grad()
+            loss_train.backward()
+            if grad_sync is not None:
+                grad_sync()
+            optimizer.step()
+
+        train_loss, train_accuracy = evaluate(X_train, y_train)
+        train_loss_history.append(train_loss)
+        train_accuracy_history.append(train_accuracy)
+        val_loss, val_accuracy = evaluate(X_train, y_train)   # sic: the reference evaluates the training set here (:151)
+        val_loss_history.append(val_loss)
+        val_accuracy_history.append(val_accuracy)
+        if verbose:
+            print("--- Epoch " + str(epoch) + " ---")
+            print("Train Acc: " + str(train_accuracy_history[-1]))
+            print("Train Loss: " + str(train_loss_history[-1]))
+            print("Val Acc: " + str(val_accuracy_history[-1]))
+            print("Val Loss: " + str(val_loss_history[-1]))
+
+        if len(val_loss_history) > patience \
+                and (np.min(val_loss_history[-patience:]) >= np.min(val_loss_history[:-patience]) - min_patience_improvement
+                     or math.isnan(val_loss_history[-1])):
+            continue_training = False
+        if val_loss_history[-1] < best_val_loss:
+            best_val_loss = val_loss_history[-1]
+            best_model = pickle.loads(pickle.dumps(model))
+            if verbose:
+                print("Updated the best model found - new best val loss is " + str(best_val_loss))
+        epoch += 1
+
+    model_to_return = best_model if restore_best_model else model
+    return (model_to_return, start_train_loss, start_train_accuracy, start_val_loss, start_val_accuracy, train_loss_history,
+            train_accuracy_history, val_loss_history, val_accuracy_history)
