@@ -97,6 +97,73 @@ int sn_sss_backward(const sn_sss_plan* plan_host, const float* packed, const flo
                     const float* grad_y, int64_t ldgy, const float* ckpt, float* workspace, float* grad_params,
                     float* grad_bias, float* grad_x, int64_t ldgx, int64_t B, sn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Low-rank layer, fp32 path -- replaces LRLayer.forward (layers/lr_layer.py:38-46) and its backward.
+ *   left (out_dim x rank), right (rank x in_dim), hidden (B x rank, written by forward, read by backward),
+ *   grad_hidden_ws: scratch (B x rank).  grad_left / grad_right / grad_bias are accumulated; grad_x may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+int sn_lr_forward_f32(const float* x, int64_t ldx, const float* left, const float* right, const float* bias, float* hidden,
+                      float* y, int64_t ldy, int64_t B, int in_dim, int out_dim, int rank, sn_stream_t stream);
+int sn_lr_backward_f32(const float* x, int64_t ldx, const float* grad_y, int64_t ldgy, const float* left, const float* right,
+                       const float* hidden, float* grad_hidden_ws, float* grad_left, float* grad_right, float* grad_bias,
+                       float* grad_x, int64_t ldgx, int64_t B, int in_dim, int out_dim, int rank, sn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * H-matrix layer -- replaces HMatLayer.forward (layers/hmat_layer.py:34-49) and its backward.
+ *   leaves: device table, 8 int32 per leaf {row_start, rows, col_start, cols, rank, off_left, off_right, 0};
+ *   params: flat buffer holding left_lr (rows x rank) / right_lr (rank x cols) of every leaf at those offsets;
+ *   grad_params has the same layout.
+ * ------------------------------------------------------------------------------------------ */
+int sn_hmat_forward(const int32_t* leaves, int nleaves, const float* params, const float* x, int64_t ldx, float* y, int64_t ldy,
+                    const float* bias, int64_t B, int in_dim, int out_dim, sn_stream_t stream);
+int sn_hmat_backward(const int32_t* leaves, int nleaves, const float* params, const float* x, int64_t ldx, const float* grad_y,
+                     int64_t ldgy, float* grad_params, float* grad_bias, int64_t B, int in_dim, int out_dim, sn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * PSM layer -- replaces PSMLayer.forward / forward_sparse (layers/psm_layer.py:36-60) and its backward,
+ * with the intended factor order W = S_0 S_1 ... S_{n-1} (see csrc/psm.cu).  factors_host: host array of nf
+ * descriptors; every pointer inside is a device pointer.  The static pattern is given in CSR and CSC order
+ * with permutations into the parameter's own COO value array; grad_vals is COO-ordered and accumulated.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sn_psm_factor {
+    int32_t rows, cols, nnz, reserved;
+    const int32_t *rowptr, *colidx, *perm, *cscptr, *rowidx, *permc;
+    const float* vals;
+    float* grad_vals;
+} sn_psm_factor;
+int sn_psm_forward(const sn_psm_factor* factors_host, int nf, const float* x, int64_t ldx, float* y, int64_t ldy, const float* bias,
+                   int64_t B, int in_dim, int out_dim, sn_stream_t stream);
+int sn_psm_backward(const sn_psm_factor* factors_host, int nf, const float* x, int64_t ldx, const float* grad_y, int64_t ldgy,
+                    float* grad_bias, int64_t B, int in_dim, int out_dim, sn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LDR layer -- replaces build_weight_matrix_torch (approximators/ldr_approximator.py:29-39) + the matmul of
+ * LDRLayer.forward (layers/ldr_layer.py:54-58) and their backward.  A, B: COO value arrays (float64) with a slot
+ * map per entry into the banded layout {lo[n] | di[n] | up[n] | corner(0,n-1), corner(n-1,0)}; G, H: n x r float64.
+ * sn_ldr_build_weight synchronises `stream` every 8 series terms to test convergence (the one exception to
+ * "never synchronises").  The workspace keeps the prefix sums sn_ldr_backward needs.
+ * ------------------------------------------------------------------------------------------ */
+size_t sn_ldr_workspace_doubles(int n, int max_terms);
+int sn_ldr_build_weight(int n, int r, const double* A_vals, const int32_t* A_slot, int A_nnz, const double* B_vals,
+                        const int32_t* B_slot, int B_nnz, const double* G, const double* H, double* workspace, int max_terms,
+                        double rel_tol, float* W_out, int* terms_out_host, sn_stream_t stream);
+int sn_ldr_backward(int n, int r, const float* dW, const int32_t* A_slot, int A_nnz, const int32_t* B_slot, int B_nnz,
+                    const double* G, const double* H, double* workspace, int terms, double* gA_vals, double* gB_vals, double* gG,
+                    double* gH, sn_stream_t stream);
+/* y = x W^T + bias and dW += grad_y^T x (grad_bias += column sums): the dense apply shared by LDR and TL */
+int sn_dense_apply(const float* W, int n_out, int n_in, const float* x, int64_t ldx, float* y, int64_t ldy, const float* bias,
+                   int64_t B, sn_stream_t stream);
+int sn_dense_weight_grad(const float* x, int64_t ldx, const float* grad_y, int64_t ldgy, float* dW, int n_out, int n_in,
+                         float* grad_bias, int64_t B, sn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Toeplitz-like layer -- replaces the weight construction of TLLayer.forward (layers/tl_layer.py:11-18,59) and
+ * its backward.  G (n x r), H (r x n) float32; K1 (n x rn) and K2 (rn x n) are scratch kept for the backward.
+ * ------------------------------------------------------------------------------------------ */
+int sn_tl_build_weight(int n, int r, const float* G, const float* H, float* K1, float* K2, float* W, sn_stream_t stream);
+int sn_tl_backward(int n, int r, const float* dW, const float* K1, const float* K2, float* dK1, float* dK2, float* gG, float* gH,
+                   sn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

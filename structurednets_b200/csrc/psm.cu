@@ -150,15 +150,6 @@ psm_bwd_kernel(Chain ch, const float* __restrict__ x, long ldx, const float* __r
 
 extern "C" {
 
-// One sparse factor: static pattern in CSR and CSC order (device int32 arrays built once by the host) plus
-// the parameter's COO value array (and, for backward, the COO-ordered gradient value array).
-typedef struct sn_psm_factor {
-    int32_t rows, cols, nnz, reserved;
-    const int32_t *rowptr, *colidx, *perm, *cscptr, *rowidx, *permc;
-    const float* vals;
-    float* grad_vals;
-} sn_psm_factor;
-
 static int make_chain(const sn_psm_factor* f, int nf, int in_dim, int out_dim, Chain* ch) {
     SN_CHECK_ARG(f != nullptr && nf >= 1 && nf <= PSM_MAX_FACTORS, "psm: need 1..%d factors", PSM_MAX_FACTORS);
     ch->nf = nf; ch->in_dim = in_dim; ch->out_dim = out_dim; ch->maxdim = in_dim > out_dim ? in_dim : out_dim;

@@ -200,35 +200,35 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 
 // ------------------------------------------------------------------------------------------
 // forward
-//   CTA = FWD_PAIRS (causal, anticausal) consumer warp pairs + 1 producer warp.
-//   producer : streams the packed stage blocks (descriptor header + Pt) of both directions through a
-//              FWD_SLOTS-deep shared-memory ring with cp.async.bulk + mbarrier (full/empty per slot).
-//   consumer : owns NSW = 4*NQ samples of one direction; input columns of half a chunk are prefetched
-//              with cp.async (double buffered, natural [sample][col] layout, row stride = 4*odd floats so
-//              the 4 scalar reads of a lane's interleaved samples are bank-conflict free); the state lives in a
-//              feature-major ping-pong buffer; y is collected per chunk and flushed with 64 B row segments.
-//   Sample <-> position map inside a warp: position p = 4*q + t  holds local sample  q + NQ*t.
+//   CTA = PAIRS (causal, anticausal) warp pairs; a warp owns NSW = 4*NQ samples of one direction and walks all
+//   stages.  Per chunk of stages (<= 4):
+//     - the chunk's packed parameter blocks (descriptor header + Pt) are fetched with cp.async.bulk (TMA) into a
+//       double-buffered per-direction shared-memory area, one chunk ahead, completion on an mbarrier; the warps of
+//       one direction meet at a named barrier per chunk, after which the leader lane refills the freed buffer;
+//     - the input columns of the chunk are prefetched one chunk ahead with 16-byte cp.async into a natural
+//       [sample][col] buffer whose row stride is 4*odd floats (the 4 scalar reads of a lane's interleaved samples
+//       are bank-conflict free); out-of-range rows / columns are zero-filled by the copy itself;
+//     - the state lives in a feature-major ping-pong buffer, exchanged between lanes with __syncwarp();
+//     - y rows are collected per chunk and flushed with 32 B row segments; the second visitor of a stage adds to
+//       what the first one stored (after a CTA-wide named barrier) -- deterministic, no atomics.
+//   Sample <-> position map inside a warp: position p = 4*q + t holds local sample q + NQ*t (table in smem).
 // ------------------------------------------------------------------------------------------
-constexpr int FWD_PAIRS = 3;
-constexpr int FWD_SLOTS = 6;
-constexpr int FWD_CONSUMERS = 2 * FWD_PAIRS;
-constexpr int FWD_THREADS = (FWD_CONSUMERS + 1) * 32;
-
 struct FwdSmem {
-    int slot_floats;   // one ring slot: header + Pt
-    int ring_off, bar_off, warp_off, per_warp;   // float offsets (bar_off is 8-byte aligned)
+    int slot_floats;   // one stage: header + Pt
+    int pbuf_off, bar_off, pos_off, warp_off, per_warp;   // float offsets
     int uw;            // row stride of the u buffers
     int xs, xn, ub0, ub1, yb;   // offsets inside a warp's region
     int total;
 };
 
-inline FwdSmem make_fwd_smem(const sn_sss_plan& p, const Geom& g) {
+inline FwdSmem make_fwd_smem(const sn_sss_plan& p, const Geom& g, int pairs) {
     FwdSmem s;
     s.slot_floats = round_up(SSS_HDR + p.k_pad * p.rows_pad, 4);
-    s.ring_off = 0;
-    s.bar_off = s.ring_off + 2 * FWD_SLOTS * s.slot_floats;
-    s.warp_off = s.bar_off + 2 * (2 * FWD_SLOTS * 2);   // 2 dirs x SLOTS x {full, empty} x 8 bytes
-    s.uw = pad_stride(p.half_in_max + 3);
+    s.pbuf_off = 0;
+    s.bar_off = s.pbuf_off + 2 * 2 * p.chunk_len_max * s.slot_floats;   // [dir][buf][stage]
+    s.pos_off = s.bar_off + 2 * 4;                                       // 4 mbarriers
+    s.warp_off = round_up(s.pos_off + g.nsw, 4);
+    s.uw = pad_stride(p.chunk_in_max + 3);
     int o = 0;
     s.xs = o;  o += p.d_pad * g.nswp;
     s.xn = o;  o += p.d_pad * g.nswp;
@@ -236,7 +236,7 @@ inline FwdSmem make_fwd_smem(const sn_sss_plan& p, const Geom& g) {
     s.ub1 = o; o += g.nsw * s.uw;
     s.yb = o;  o += p.chunk_out_max * g.nswp;
     s.per_warp = round_up(o, 4);
-    s.total = s.warp_off + FWD_CONSUMERS * s.per_warp;
+    s.total = s.warp_off + 2 * pairs * s.per_warp;
     return s;
 }
 
@@ -248,13 +248,14 @@ __device__ __forceinline__ int issue_u_load(const float* __restrict__ x, long ld
     if (aligned) {
         const int col0a = col0 & ~3;
         const int ngran = (col0 - col0a + ncols + 3) >> 2;
-        for (int r0 = 0; r0 < nsw; r0 += 8) {
-            const int ls = r0 + (lane >> 2);
-            const bool rok = ls < nsw && s0 + ls < B;
+        const int gi0 = lane & 3;
+        for (int ls = lane >> 2; ls < nsw; ls += 8) {
+            const bool rok = s0 + ls < B;
             const float* row = x + (size_t)(s0 + ls) * ldx + col0a;
-            for (int gi = lane & 3; gi < ngran; gi += 4) {
+            float* drow = ub + ls * uw;
+            for (int gi = gi0; gi < ngran; gi += 4) {
                 const bool ok = rok && (col0a + 4 * gi < in_dim);
-                if (ls < nsw) cp_async16(ub + ls * uw + 4 * gi, ok ? (const void*)(row + 4 * gi) : (const void*)x, ok);
+                cp_async16(drow + 4 * gi, ok ? (const void*)(row + 4 * gi) : (const void*)x, ok);
             }
         }
         return col0 - col0a;
@@ -267,48 +268,30 @@ __device__ __forceinline__ int issue_u_load(const float* __restrict__ x, long ld
     return 0;
 }
 
-__global__ void __launch_bounds__(FWD_THREADS)
+template <int PAIRS>
+__global__ void __launch_bounds__(PAIRS * 64)
 sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* __restrict__ x, long ldx,
                float* __restrict__ y, long ldy, const float* __restrict__ bias, float* __restrict__ ckpt, long B,
                Geom g, FwdSmem sm, int x_aligned) {
     extern __shared__ __align__(128) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = plan.nb_states, DP = plan.d_pad, RP = plan.rows_pad;
-    float* ring = smem + sm.ring_off;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bar_off);   // [dir][slot][full, empty]
-    auto full_bar = [&](int dir, int slot) { return bars + ((dir * FWD_SLOTS + slot) * 2 + 0); };
-    auto empty_bar = [&](int dir, int slot) { return bars + ((dir * FWD_SLOTS + slot) * 2 + 1); };
+    const int n = plan.nb_states, DP = plan.d_pad, RP = plan.rows_pad, CL = plan.chunk_len_max;
+    float* pbuf = smem + sm.pbuf_off;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bar_off);   // full[dir][buf]
+    int* pos_tab = reinterpret_cast<int*>(smem + sm.pos_off);
+    const int nswp = g.nswp, uw = sm.uw, nq = g.nq, nsw = g.nsw;
 
     if (threadIdx.x == 0) {
-        for (int d = 0; d < 2; ++d)
-            for (int sl = 0; sl < FWD_SLOTS; ++sl) {
-                mbar_init(full_bar(d, sl), 1);
-                mbar_init(empty_bar(d, sl), FWD_PAIRS);
-            }
+        for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    for (int ls = threadIdx.x; ls < nsw; ls += PAIRS * 64) pos_tab[ls] = pos_of(ls, nq);
     __syncthreads();
 
-    if (warp == FWD_CONSUMERS) {
-        // ---------------- producer ----------------
-        if (lane < 2) {   // lane d feeds direction d
-            const int d = lane;
-            const uint32_t bytes = (uint32_t)sm.slot_floats * 4u;
-            const size_t blk = SSS_HDR + 2 * (size_t)plan.k_pad * RP;
-            for (int kk = 0; kk < n; ++kk) {
-                const int sl = kk % FWD_SLOTS, round = kk / FWD_SLOTS;
-                if (round > 0) mbar_wait_backoff(empty_bar(d, sl), (round - 1) & 1);
-                mbar_arrive_expect_tx(full_bar(d, sl), bytes);
-                bulk_g2s(ring + (size_t)(d * FWD_SLOTS + sl) * sm.slot_floats, packed + ((size_t)d * n + kk) * blk, bytes, full_bar(d, sl));
-            }
-        }
-        return;
-    }
-
-    // ---------------- consumers ----------------
     const int pair = warp >> 1, dir = warp & 1;
-    const long s0 = ((long)blockIdx.x * FWD_PAIRS + pair) * g.nsw;
+    const bool leader = (pair == 0) && (lane == 0);
+    const long s0 = ((long)blockIdx.x * PAIRS + pair) * nsw;
     float* wbase = smem + sm.warp_off + (size_t)warp * sm.per_warp;
     float* xs = wbase + sm.xs;
     float* xn = wbase + sm.xn;
@@ -316,118 +299,121 @@ sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
     float* const ub_b = wbase + sm.ub1;
     float* yb = wbase + sm.yb;
     const sn_sss_chunk* chunks = plan.chunks + (size_t)dir * plan.nchunks;
-    const int rg_slot = lane / g.nq, q = lane - rg_slot * g.nq;
+    const int rg_slot = lane / nq, q = lane - rg_slot * nq;
     const bool active = rg_slot < g.rgs;
-    const int nswp = g.nswp, uw = sm.uw, nq = g.nq, nsw = g.nsw;
     const int RP4 = RP >> 2;
-    bool did_mid = false;
-    int ubi = 0;         // which u buffer holds the half that is consumed next
-    int uoff_cur;
+    const size_t blk = SSS_HDR + 2 * (size_t)plan.k_pad * RP;
+    const uint32_t slot_bytes = (uint32_t)sm.slot_floats * 4u;
+
+    auto issue_params = [&](int ch, const sn_sss_chunk& cc) {
+        const int b = ch & 1, len = cc.kk_end - cc.kk_begin;
+        uint64_t* fb = bars + dir * 2 + b;
+        mbar_arrive_expect_tx(fb, slot_bytes * (uint32_t)len);
+        for (int j = 0; j < len; ++j)
+            bulk_g2s(pbuf + ((size_t)(dir * 2 + b) * CL + j) * sm.slot_floats, packed + ((size_t)dir * n + cc.kk_begin + j) * blk, slot_bytes, fb);
+    };
 
     sn_sss_chunk c = chunks[0];
-    uoff_cur = issue_u_load(x, ldx, s0, B, plan.input_dim, nsw, uw, x_aligned != 0, c.col0_a, c.ncols_a, ub_a, lane);
+    if (leader) issue_params(0, c);
+    int uoff_cur = issue_u_load(x, ldx, s0, B, plan.input_dim, nsw, uw, x_aligned != 0, c.col0, c.ncols, ub_a, lane);
     cp_async_commit();
+    bool did_mid = false;
+    int ubi = 0;
 
     for (int ch = 0; ch < plan.nchunks; ++ch) {
         if (c.second_visit && !did_mid) {
-            named_bar_sync(1, FWD_CONSUMERS * 32);   // the other direction's first-visit stores to y are visible
+            named_bar_sync(1, PAIRS * 64);   // the other direction's first-visit stores to y are visible
             did_mid = true;
         }
         sn_sss_chunk cnext = c;
         if (ch + 1 < plan.nchunks) cnext = chunks[ch + 1];
-        for (int half = 0; half < 2; ++half) {
-            const int kb = half == 0 ? c.kk_begin : c.kk_mid;
-            const int ke = half == 0 ? c.kk_mid : c.kk_end;
-            const int hcol0 = half == 0 ? c.col0_a : c.col0_b;
-            // prefetch the next half (or the first half of the next chunk) into the other buffer
-            int uoff_next = 0;
-            bool issued = false;
-            if (half == 0) {
-                if (c.kk_mid < c.kk_end) { uoff_next = issue_u_load(x, ldx, s0, B, plan.input_dim, nsw, uw, x_aligned != 0, c.col0_b, c.ncols_b, (ubi ? ub_a : ub_b), lane); issued = true; }
-            } else if (ch + 1 < plan.nchunks) {
-                uoff_next = issue_u_load(x, ldx, s0, B, plan.input_dim, nsw, uw, x_aligned != 0, cnext.col0_a, cnext.ncols_a, (ubi ? ub_a : ub_b), lane); issued = true;
-            }
-            cp_async_commit();
-            cp_async_wait<1>();
-            __syncwarp();
-            if (kb < ke) {
-                const float* ub = ubi ? ub_b : ub_a;
-                for (int kk = kb; kk < ke; ++kk) {
-                    const int sl = kk % FWD_SLOTS;
-                    mbar_wait(full_bar(dir, sl), (kk / FWD_SLOTS) & 1);
-                    const float* slot = ring + (size_t)(dir * FWD_SLOTS + sl) * sm.slot_floats;
-                    const int* hdr = reinterpret_cast<const int*>(slot);
-                    const int in_off = hdr[0], in_dim = hdr[1], out_off = hdr[2], out_dim = hdr[3], d_in = hdr[4], d_out = hdr[5];
-                    if (ckpt != nullptr && kk == c.kk_begin) {
-                        // checkpoint of the state entering the chunk, in true sample order
-                        float* cbase = ckpt + ((size_t)(dir * plan.nchunks + ch) * DP) * B;
-                        for (int e = lane; e < d_in * nsw; e += 32) {
-                            const int f = e / nsw, ls = e - f * nsw;
-                            if (s0 + ls < B) cbase[(size_t)f * B + s0 + ls] = xs[f * nswp + pos_of(ls, nq)];
-                        }
-                    }
-                    if (active) {
-                        const int nrg = (d_out + out_dim + 3) >> 2;
-                        const float4* Pt4 = reinterpret_cast<const float4*>(slot + SSS_HDR);
-                        const float* u0 = ub + (q)*uw + uoff_cur + (in_off - hcol0);
-                        const float* u1 = u0 + nq * uw;
-                        const float* u2 = u1 + nq * uw;
-                        const float* u3 = u2 + nq * uw;
-                        for (int rg = rg_slot; rg < nrg; rg += g.rgs) {
-                            float acc[4][4];
-#pragma unroll
-                            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                                for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-                            const float4* prow = Pt4 + rg;
-                            const float* xv = xs + 4 * q;
-#pragma unroll 4
-                            for (int i = 0; i < d_in; ++i) {
-                                const float4 p = prow[0];
-                                const float4 v = *reinterpret_cast<const float4*>(xv);
-                                prow += RP4;
-                                xv += nswp;
-                                fma16(acc, p, v);
-                            }
-#pragma unroll 4
-                            for (int i = 0; i < in_dim; ++i) {
-                                const float4 p = prow[0];
-                                prow += RP4;
-                                const float4 v = make_float4(u0[i], u1[i], u2[i], u3[i]);
-                                fma16(acc, p, v);
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int r = 4 * rg + j;
-                                const float4 o = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-                                if (r < d_out) *reinterpret_cast<float4*>(xn + r * nswp + 4 * q) = o;
-                                else if (r < d_out + out_dim) *reinterpret_cast<float4*>(yb + (out_off - c.row0 + r - d_out) * nswp + 4 * q) = o;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(empty_bar(dir, sl));
-                    float* t = xs; xs = xn; xn = t;
+        named_bar_sync(2 + dir, PAIRS * 32);   // every warp of this direction is done with chunk ch-1: its buffer is free
+        int uoff_next = 0;
+        if (ch + 1 < plan.nchunks) {
+            if (leader) issue_params(ch + 1, cnext);
+            uoff_next = issue_u_load(x, ldx, s0, B, plan.input_dim, nsw, uw, x_aligned != 0, cnext.col0, cnext.ncols, ubi ? ub_a : ub_b, lane);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        mbar_wait(bars + dir * 2 + (ch & 1), (ch >> 1) & 1);
+        const float* ub = ubi ? ub_b : ub_a;
+        const float* cbuf = pbuf + (size_t)(dir * 2 + (ch & 1)) * CL * sm.slot_floats;
+
+        if (ckpt != nullptr) {   // checkpoint of the state entering the chunk, in true sample order
+            const int d_first = reinterpret_cast<const int*>(cbuf)[4];
+            float* cbase = ckpt + ((size_t)(dir * plan.nchunks + ch) * DP) * B + s0;
+            for (int ls = lane; ls < nsw; ls += 32) {
+                if (s0 + ls < B) {
+                    const float* src = xs + pos_tab[ls];
+                    float* dst = cbase + ls;
+                    for (int f = 0; f < d_first; ++f) dst[(size_t)f * B] = src[f * nswp];
                 }
             }
-            if (issued) { ubi ^= 1; uoff_cur = uoff_next; }
         }
-        // flush the chunk's outputs: y[s0 + ls][row0 + row]; a lane walks rows `lrow + k*rstep` of samples `lsub + k*sstep`
+        for (int kk = c.kk_begin; kk < c.kk_end; ++kk) {
+            const float* slot = cbuf + (size_t)(kk - c.kk_begin) * sm.slot_floats;
+            const int* hdr = reinterpret_cast<const int*>(slot);
+            const int in_off = hdr[0], in_dim = hdr[1], out_off = hdr[2], out_dim = hdr[3], d_in = hdr[4], d_out = hdr[5];
+            if (active) {
+                const int nrg = (d_out + out_dim + 3) >> 2;
+                const float4* Pt4 = reinterpret_cast<const float4*>(slot + SSS_HDR);
+                const float* u0 = ub + q * uw + uoff_cur + (in_off - c.col0);
+                const float* u1 = u0 + nq * uw;
+                const float* u2 = u1 + nq * uw;
+                const float* u3 = u2 + nq * uw;
+                for (int rg = rg_slot; rg < nrg; rg += g.rgs) {
+                    float acc[4][4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+                    const float4* prow = Pt4 + rg;
+                    const float* xv = xs + 4 * q;
+#pragma unroll 4
+                    for (int i = 0; i < d_in; ++i) {
+                        const float4 p = prow[0];
+                        const float4 v = *reinterpret_cast<const float4*>(xv);
+                        prow += RP4;
+                        xv += nswp;
+                        fma16(acc, p, v);
+                    }
+#pragma unroll 4
+                    for (int i = 0; i < in_dim; ++i) {
+                        const float4 p = prow[0];
+                        prow += RP4;
+                        const float4 v = make_float4(u0[i], u1[i], u2[i], u3[i]);
+                        fma16(acc, p, v);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = 4 * rg + j;
+                        const float4 o = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                        if (r < d_out) *reinterpret_cast<float4*>(xn + r * nswp + 4 * q) = o;
+                        else if (r < d_out + out_dim) *reinterpret_cast<float4*>(yb + (out_off - c.row0 + r - d_out) * nswp + 4 * q) = o;
+                    }
+                }
+            }
+            __syncwarp();
+            float* t = xs; xs = xn; xn = t;
+        }
+        // flush the chunk's outputs: y[s0 + ls][row0 + row]; lanes = (row, sample-sub), 4 independent samples in flight
         {
             const int rl = c.nrows >= 32 ? 32 : (c.nrows >= 16 ? 16 : (c.nrows >= 8 ? 8 : (c.nrows >= 4 ? 4 : (c.nrows >= 2 ? 2 : 1))));
-            const int spl = 32 / rl;                      // samples handled per warp pass
-            const int lrow = lane % rl, lsub = lane / rl;
+            const int spl = 32 / rl;
+            const int lrow = lane & (rl - 1), lsub = lane / rl;
             for (int row = lrow; row < c.nrows; row += rl) {
                 const float bv = (!c.second_visit && bias != nullptr) ? __ldg(bias + c.row0 + row) : 0.f;
-                for (int lsb = 0; lsb < nsw; lsb += 4 * spl) {
+                const float* ysrc = yb + row * nswp;
+                for (int lsb = lsub; lsb < nsw; lsb += 4 * spl) {
                     float v[4];
                     float* dst[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const int ls = lsb + k * spl + lsub;
+                        const int ls = lsb + k * spl;
                         const bool ok = ls < nsw && s0 + ls < B;
                         dst[k] = ok ? y + (size_t)(s0 + ls) * ldy + c.row0 + row : nullptr;
-                        v[k] = ok ? yb[row * nswp + pos_of(ls, nq)] : 0.f;
+                        v[k] = ok ? ysrc[pos_tab[ls]] : 0.f;
                     }
                     if (c.second_visit) {
                         float o[4];
@@ -446,19 +432,20 @@ sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
             }
         }
         __syncwarp();
+        if (ch + 1 < plan.nchunks) { ubi ^= 1; uoff_cur = uoff_next; }
         c = cnext;
     }
     cp_async_wait<0>();
-    if (!did_mid) named_bar_sync(1, FWD_CONSUMERS * 32);
+    if (!did_mid) named_bar_sync(1, PAIRS * 64);
 }
 
 // ------------------------------------------------------------------------------------------
-// backward: CTA = BWD_CONS consumer warps (each owning NSW samples) + 1 producer warp, one direction per CTA
-// (blockIdx.y); chunks are visited in reverse processing order.  Per chunk:
+// backward: CTA = BWD_CONS warps (each owning NSW samples), one direction per CTA (blockIdx.y); chunks are visited
+// in reverse processing order.  Per chunk:
 //   loads   : forward checkpoint, input columns and grad_y rows of the chunk, transposed to feature-major
-//             [feature][position] with 4-byte cp.async, double buffered (issued one chunk ahead);
-//             the chunk's packed parameter blocks (descriptor + Pt + P) arrive as ONE cp.async.bulk issued by
-//             the producer warp while the previous chunk is still in its gradient phase
+//             [feature][position] with 4-byte cp.async, double buffered (issued one chunk ahead); the chunk's packed
+//             parameter blocks (descriptor + Pt + P) arrive as ONE cp.async.bulk (TMA), issued as soon as the previous
+//             chunk's adjoint sweep has released the parameter buffer, i.e. it lands during the gradient phase
 //   1. recompute the entry states of the chunk's stages                         (warp-own samples)
 //   2. adjoint sweep  lam_in = P^T [lam_out ; gy]                               (warp-own samples)
 //   3. parameter gradients  dP_k = [lam_out ; gy] [s_in ; u]^T over the tile's samples (warp-own stages,
@@ -466,13 +453,13 @@ sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
 //      gradient workspace that sss_unpack_grad_kernel folds into the flat gradient buffer afterwards.
 // ------------------------------------------------------------------------------------------
 constexpr int BWD_CONS = 2;
-constexpr int BWD_THREADS = (BWD_CONS + 1) * 32;
+constexpr int BWD_THREADS = BWD_CONS * 32;
 
 struct BwdSmem {
     int nsp;     // padded position stride of the CTA-wide feature-major buffers
     int blk;     // floats per packed stage block
     int hs;      // one history entry (d_pad * nsp)
-    int params, bars, xh, lh, lcar0, lcar1, ck0, ck1, ut0, ut1, gt0, gt1, zero, total;   // float offsets
+    int params, bars, pos, xh, lh, lcar0, lcar1, ck0, ck1, ut0, ut1, gt0, gt1, zero, total;   // float offsets
 };
 
 inline BwdSmem make_bwd_smem(const sn_sss_plan& p, const Geom& g) {
@@ -485,6 +472,7 @@ inline BwdSmem make_bwd_smem(const sn_sss_plan& p, const Geom& g) {
     int o = 0;
     s.params = o; o += round_up(p.chunk_len_max * s.blk, 4);
     s.bars = o;   o += 4;
+    s.pos = o;    o += round_up(g.nsw, 4);
     s.xh = o;     o += hist * s.hs;
     s.lh = o;     o += hist * s.hs;
     s.lcar0 = o;  o += s.hs;
@@ -500,24 +488,33 @@ inline BwdSmem make_bwd_smem(const sn_sss_plan& p, const Geom& g) {
     return s;
 }
 
-// issue the (transposing) loads of one chunk for the calling warp's samples
+// issue the (transposing) loads of one chunk for the calling warp's samples: dst[feature][w0 + pos(ls)]
 __device__ __forceinline__ void bwd_issue_loads(const sn_sss_plan& plan, const sn_sss_chunk& c, int d_first, int dir, int ch,
                                                 const float* __restrict__ x, long ldx, const float* __restrict__ gy, long ldgy,
-                                                const float* __restrict__ ckpt, long B, long samp0, int w0, int nsw, int nq, int nsp,
-                                                float* ck, float* ut, float* gt, int lane) {
-    const float* cbase = ckpt + ((size_t)(dir * plan.nchunks + ch) * plan.d_pad) * B;
+                                                const float* __restrict__ ckpt, long B, long samp0, int nvalid, int nsw, int nsp,
+                                                const int* pos_tab, float* ck, float* ut, float* gt, int lane) {
+    const float* cbase = ckpt + ((size_t)(dir * plan.nchunks + ch) * plan.d_pad) * B + samp0;
     for (int ls = lane; ls < nsw; ls += 32) {
-        const int pos = w0 + pos_of(ls, nq);
-        const bool ok = samp0 + ls < B;
-        for (int f = 0; f < d_first; ++f) cp_async4(ck + f * nsp + pos, ok ? (const void*)(cbase + (size_t)f * B + samp0 + ls) : (const void*)x, ok);
+        const bool ok = ls < nvalid;
+        float* dst = ck + pos_tab[ls];
+        const float* src = cbase + ls;
+        for (int f = 0; f < d_first; ++f) cp_async4(dst + f * nsp, ok ? (const void*)(src + (size_t)f * B) : (const void*)x, ok);
     }
-    for (int ls = 0; ls < nsw; ++ls) {
-        const int pos = w0 + pos_of(ls, nq);
-        const bool ok = samp0 + ls < B;
-        const float* xr = x + (size_t)(samp0 + ls) * ldx + c.col0;
-        for (int cc = lane; cc < c.ncols; cc += 32) cp_async4(ut + cc * nsp + pos, ok ? (const void*)(xr + cc) : (const void*)x, ok);
-        const float* gr = gy + (size_t)(samp0 + ls) * ldgy + c.row0;
-        for (int rr = lane; rr < c.nrows; rr += 32) cp_async4(gt + rr * nsp + pos, ok ? (const void*)(gr + rr) : (const void*)x, ok);
+    for (int cc = lane; cc < c.ncols; cc += 32) {
+        float* dcol = ut + cc * nsp;
+        const float* src = x + (size_t)samp0 * ldx + c.col0 + cc;
+        for (int ls = 0; ls < nsw; ++ls) {
+            const bool ok = ls < nvalid;
+            cp_async4(dcol + pos_tab[ls], ok ? (const void*)(src + (size_t)ls * ldx) : (const void*)x, ok);
+        }
+    }
+    for (int rr = lane; rr < c.nrows; rr += 32) {
+        float* dcol = gt + rr * nsp;
+        const float* src = gy + (size_t)samp0 * ldgy + c.row0 + rr;
+        for (int ls = 0; ls < nsw; ++ls) {
+            const bool ok = ls < nvalid;
+            cp_async4(dcol + pos_tab[ls], ok ? (const void*)(src + (size_t)ls * ldgy) : (const void*)x, ok);
+        }
     }
 }
 
@@ -534,38 +531,27 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
     const sn_sss_stage* stages = plan.stages + (size_t)dir * n;
     float* params = smem + sm.params;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + sm.bars);
-    uint64_t* empty_bar = full_bar + 1;
+    int* pos_tab = reinterpret_cast<int*>(smem + sm.pos);
+    const int nq = g.nq, nsw = g.nsw;
 
+    sn_sss_chunk c = chunks[plan.nchunks - 1];
     if (threadIdx.x == 0) {
         mbar_init(full_bar, 1);
-        mbar_init(empty_bar, BWD_CONS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t bytes = (uint32_t)((c.kk_end - c.kk_begin) * sm.blk) * 4u;
+        mbar_arrive_expect_tx(full_bar, bytes);
+        bulk_g2s(params, packed + ((size_t)dir * n + c.kk_begin) * sm.blk, bytes, full_bar);
     }
+    for (int ls = threadIdx.x; ls < nsw; ls += BWD_THREADS) pos_tab[ls] = pos_of(ls, nq);
     for (int e = threadIdx.x; e < NSP; e += BWD_THREADS) smem[sm.zero + e] = 0.f;
     for (int e = threadIdx.x; e < 2 * hs; e += BWD_THREADS) smem[sm.lcar0 + e] = 0.f;   // lcar0 and lcar1 are adjacent
     __syncthreads();
 
-    if (warp == BWD_CONS) {
-        // ---------------- producer: one bulk copy per chunk ----------------
-        if (lane == 0) {
-            int it = 0;
-            for (int ch = plan.nchunks - 1; ch >= 0; --ch, ++it) {
-                const sn_sss_chunk c = chunks[ch];
-                const uint32_t bytes = (uint32_t)((c.kk_end - c.kk_begin) * sm.blk) * 4u;
-                if (it > 0) mbar_wait_backoff(empty_bar, (it - 1) & 1);
-                mbar_arrive_expect_tx(full_bar, bytes);
-                bulk_g2s(params, packed + ((size_t)dir * n + c.kk_begin) * sm.blk, bytes, full_bar);
-            }
-        }
-        return;
-    }
-
-    // ---------------- consumers ----------------
     const long t0 = (long)blockIdx.x * NS;
-    const int w0 = warp * g.nsw;
+    const int w0 = warp * nsw;
     const long samp0 = t0 + w0;
-    const int nq = g.nq, nsw = g.nsw;
+    const int nvalid = (int)(B - samp0 < 0 ? 0 : (B - samp0 > nsw ? nsw : B - samp0));
     const int rg_slot = lane / nq, q = lane - rg_slot * nq;
     const int rgs_state = (DP / 4 < g.rgs) ? DP / 4 : g.rgs;
     const int RP4 = RP >> 2, KP4 = KP >> 2;
@@ -576,10 +562,9 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
     const float* zr = smem + sm.zero;
     int buf = 0;
 
-    sn_sss_chunk c = chunks[plan.nchunks - 1];
     int d_first = stages[c.kk_begin].d_in;
-    bwd_issue_loads(plan, c, d_first, dir, plan.nchunks - 1, x, ldx, gy, ldgy, ckpt, B, samp0, w0, nsw, nq, NSP, smem + sm.ck0, smem + sm.ut0,
-                    smem + sm.gt0, lane);
+    bwd_issue_loads(plan, c, d_first, dir, plan.nchunks - 1, x, ldx, gy, ldgy, ckpt, B, samp0, nvalid, nsw, NSP, pos_tab, smem + sm.ck0 + w0,
+                    smem + sm.ut0 + w0, smem + sm.gt0 + w0, lane);
     cp_async_commit();
 
     int it = 0;
@@ -589,12 +574,11 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
         float* ut = smem + (buf ? sm.ut1 : sm.ut0);
         float* gt = smem + (buf ? sm.gt1 : sm.gt0);
         sn_sss_chunk cn = c;
-        int d_first_n = 0;
         if (ch > 0) {
             cn = chunks[ch - 1];
-            d_first_n = stages[cn.kk_begin].d_in;
-            bwd_issue_loads(plan, cn, d_first_n, dir, ch - 1, x, ldx, gy, ldgy, ckpt, B, samp0, w0, nsw, nq, NSP, smem + (buf ? sm.ck0 : sm.ck1),
-                            smem + (buf ? sm.ut0 : sm.ut1), smem + (buf ? sm.gt0 : sm.gt1), lane);
+            const int d_first_n = stages[cn.kk_begin].d_in;
+            bwd_issue_loads(plan, cn, d_first_n, dir, ch - 1, x, ldx, gy, ldgy, ckpt, B, samp0, nvalid, nsw, NSP, pos_tab,
+                            smem + (buf ? sm.ck0 : sm.ck1) + w0, smem + (buf ? sm.ut0 : sm.ut1) + w0, smem + (buf ? sm.gt0 : sm.gt1) + w0, lane);
         }
         cp_async_commit();
         cp_async_wait<1>();
@@ -695,12 +679,15 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
                 h_in_off[u] = hdr[0]; h_in_dim[u] = hdr[1]; h_out_off[u] = hdr[2]; h_out_dim[u] = hdr[3]; h_d_in[u] = hdr[4]; h_d_out[u] = hdr[5];
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty_bar);          // producer may overwrite the parameter buffer now
-        named_bar_sync(1, BWD_CONS * 32);
+        named_bar_sync(1, BWD_THREADS);      // every warp is done with the parameter buffer and its history columns are complete
+        if (threadIdx.x == 0 && ch > 0) {    // refill the parameter buffer for the next chunk; lands during the gradient phase
+            const uint32_t bytes = (uint32_t)((cn.kk_end - cn.kk_begin) * sm.blk) * 4u;
+            mbar_arrive_expect_tx(full_bar, bytes);
+            bulk_g2s(params, packed + ((size_t)dir * n + cn.kk_begin) * sm.blk, bytes, full_bar);
+        }
         // ---- 3. parameter gradients (own stages, all positions of the tile) -----------------------
         if (gbias != nullptr && dir == 0) {
-            for (int rr = threadIdx.x; rr < c.nrows; rr += BWD_CONS * 32) {
+            for (int rr = threadIdx.x; rr < c.nrows; rr += BWD_THREADS) {
                 float sacc = 0.f;
                 const float* gr = gt + (size_t)rr * NSP;
                 for (int e = 0; e < NS; ++e) sacc += gr[e];
@@ -767,11 +754,10 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
                 }
             }
         }
-        named_bar_sync(1, BWD_CONS * 32);
+        named_bar_sync(1, BWD_THREADS);
         { float* tsw = lcar_cur; lcar_cur = lcar_nxt; lcar_nxt = tsw; }
         buf ^= 1;
         c = cn;
-        d_first = d_first_n;
     }
     cp_async_wait<0>();
 }
@@ -809,6 +795,24 @@ int check_plan(const sn_sss_plan* p) {
     return 0;
 }
 
+template <int PAIRS>
+static int launch_fwd(const sn_sss_plan* p, const Geom& g, const float* packed, const float* x, int64_t ldx, float* y, int64_t ldy,
+                      const float* bias, float* ckpt, int64_t B, int aligned, cudaStream_t st) {
+    FwdSmem sm = make_fwd_smem(*p, g, PAIRS);
+    size_t smem = (size_t)sm.total * sizeof(float);
+    SN_CHECK_ARG(smem <= 227 * 1024, "sss_forward: stage dims need %zu bytes of shared memory (> 227 KB)", smem);
+    static size_t configured = 0;
+    if (smem > configured) {
+        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_fwd_kernel<PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    long tile = (long)PAIRS * g.nsw;
+    unsigned grid = (unsigned)((B + tile - 1) / tile);
+    sss_fwd_kernel<PAIRS><<<grid, PAIRS * 64, smem, st>>>(*p, packed, x, (long)ldx, y, (long)ldy, bias, ckpt, (long)B, g, sm, aligned);
+    SN_CHECK_LAUNCH("sss_fwd_kernel");
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -839,22 +843,14 @@ int sn_sss_forward(const sn_sss_plan* p, const float* packed, const float* x, in
     SN_CHECK_ARG(ldx >= p->input_dim && ldy >= p->output_dim, "sss_forward: leading dimension too small");
     if (B <= 0) return 0;
     Geom g = make_geom(p->rows_pad);
-    FwdSmem sm = make_fwd_smem(*p, g);
-    size_t smem = (size_t)sm.total * sizeof(float);
-    SN_CHECK_ARG(smem <= 227 * 1024, "sss_forward: stage dims need %zu bytes of shared memory (> 227 KB)", smem);
-    static size_t configured = 0;
-    if (smem > configured) {
-        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     // 16-byte cp.async path needs 16-byte aligned rows whose length is a multiple of 4 floats
     const int aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldx & 3) == 0 && (p->input_dim & 3) == 0) ? 1 : 0;
-    long tile = (long)FWD_PAIRS * g.nsw;
-    unsigned grid = (unsigned)((B + tile - 1) / tile);
-    sss_fwd_kernel<<<grid, FWD_THREADS, smem, snb::as_stream(stream)>>>(*p, packed, x, (long)ldx, y, (long)ldy, bias, ckpt, (long)B,
-                                                                        g, sm, aligned);
-    SN_CHECK_LAUNCH("sss_fwd_kernel");
-    return 0;
+    cudaStream_t st = snb::as_stream(stream);
+    // big CTAs (6 warp pairs share one parameter stream) once they still fill the chip twice over; small ones otherwise
+    const long big_tiles = (B + 6L * g.nsw - 1) / (6L * g.nsw);
+    if (big_tiles >= 2 * 148 && (size_t)make_fwd_smem(*p, g, 6).total * sizeof(float) <= 227 * 1024)
+        return launch_fwd<6>(p, g, packed, x, ldx, y, ldy, bias, ckpt, B, aligned, st);
+    return launch_fwd<2>(p, g, packed, x, ldx, y, ldy, bias, ckpt, B, aligned, st);
 }
 
 size_t sn_sss_backward_workspace_floats(const sn_sss_plan* p) {
