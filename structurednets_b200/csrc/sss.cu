@@ -102,6 +102,20 @@ __device__ __forceinline__ void fma16(float (&acc)[4][4], const float4& p, const
     acc[3][2] = fmaf(p.w, v.z, acc[3][2]); acc[3][3] = fmaf(p.w, v.w, acc[3][3]);
 }
 
+// acc += sum_{i<CNT} prow[i*PSTRIDE4] (x) xv[i*VSTRIDE]  -- compile-time trip count and strides: fully unrolled,
+// immediate-offset loads the scheduler can hoist (the specialised fast path of the common stage shape)
+template <int CNT, int PSTRIDE4, int VSTRIDE>
+__device__ __forceinline__ void mac_f4(float (&acc)[4][4], const float4* prow, const float* xv) {
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) fma16(acc, prow[i * PSTRIDE4], *reinterpret_cast<const float4*>(xv + i * VSTRIDE));
+}
+// same with the operand gathered from 4 sample rows (natural-layout input buffer of the forward)
+template <int CNT, int PSTRIDE4>
+__device__ __forceinline__ void mac_s4(float (&acc)[4][4], const float4* prow, const float* u0, const float* u1, const float* u2, const float* u3) {
+#pragma unroll
+    for (int i = 0; i < CNT; ++i) fma16(acc, prow[i * PSTRIDE4], make_float4(u0[i], u1[i], u2[i], u3[i]));
+}
+
 // One stage step for the lanes of one warp:  out rows [4*rg, 4*rg+4) for rg in [rg_slot, nrg) step rgs.
 //   state rows -> xn (next state), y rows -> yc (chunk output buffer, may be null: rows skipped)
 __device__ __forceinline__ void stage_step(const sn_sss_stage& st, const float* __restrict__ packed, int RP,
@@ -268,7 +282,9 @@ __device__ __forceinline__ int issue_u_load(const float* __restrict__ x, long ld
     return 0;
 }
 
-template <int PAIRS>
+// RP4T / NSWPT > 0: compile-time rows_pad/4 and state row stride of the specialised instantiation (the 4096->1000,
+// statespace-16 shape: rows_pad 20, 6 sample quads per warp); 0: generic runtime strides.
+template <int PAIRS, int RP4T, int NSWPT>
 __global__ void __launch_bounds__(PAIRS * 64)
 sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* __restrict__ x, long ldx,
                float* __restrict__ y, long ldy, const float* __restrict__ bias, float* __restrict__ ckpt, long B,
@@ -279,7 +295,8 @@ sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
     float* pbuf = smem + sm.pbuf_off;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bar_off);   // full[dir][buf]
     int* pos_tab = reinterpret_cast<int*>(smem + sm.pos_off);
-    const int nswp = g.nswp, uw = sm.uw, nq = g.nq, nsw = g.nsw;
+    constexpr bool FAST = RP4T > 0;
+    const int nswp = FAST ? NSWPT : g.nswp, uw = sm.uw, nq = g.nq, nsw = g.nsw;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
@@ -301,7 +318,7 @@ sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
     const sn_sss_chunk* chunks = plan.chunks + (size_t)dir * plan.nchunks;
     const int rg_slot = lane / nq, q = lane - rg_slot * nq;
     const bool active = rg_slot < g.rgs;
-    const int RP4 = RP >> 2;
+    const int RP4 = FAST ? RP4T : (RP >> 2);
     const size_t blk = SSS_HDR + 2 * (size_t)plan.k_pad * RP;
     const uint32_t slot_bytes = (uint32_t)sm.slot_floats * 4u;
 
@@ -370,20 +387,31 @@ sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
                         for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
                     const float4* prow = Pt4 + rg;
                     const float* xv = xs + 4 * q;
+                    if (FAST && d_in == 16) {
+                        mac_f4<16, RP4T, NSWPT>(acc, prow, xv);
+                        prow += 16 * RP4T;
+                    } else {
 #pragma unroll 4
-                    for (int i = 0; i < d_in; ++i) {
-                        const float4 p = prow[0];
-                        const float4 v = *reinterpret_cast<const float4*>(xv);
-                        prow += RP4;
-                        xv += nswp;
-                        fma16(acc, p, v);
+                        for (int i = 0; i < d_in; ++i) {
+                            const float4 p = prow[0];
+                            const float4 v = *reinterpret_cast<const float4*>(xv);
+                            prow += RP4;
+                            xv += nswp;
+                            fma16(acc, p, v);
+                        }
                     }
+                    if (FAST && in_dim == 8) {
+                        mac_s4<8, RP4T>(acc, prow, u0, u1, u2, u3);
+                    } else if (FAST && in_dim == 9) {
+                        mac_s4<9, RP4T>(acc, prow, u0, u1, u2, u3);
+                    } else {
 #pragma unroll 4
-                    for (int i = 0; i < in_dim; ++i) {
-                        const float4 p = prow[0];
-                        prow += RP4;
-                        const float4 v = make_float4(u0[i], u1[i], u2[i], u3[i]);
-                        fma16(acc, p, v);
+                        for (int i = 0; i < in_dim; ++i) {
+                            const float4 p = prow[0];
+                            prow += RP4;
+                            const float4 v = make_float4(u0[i], u1[i], u2[i], u3[i]);
+                            fma16(acc, p, v);
+                        }
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -518,6 +546,9 @@ __device__ __forceinline__ void bwd_issue_loads(const sn_sss_plan& plan, const s
     }
 }
 
+// RP4T / KP4T / NSPT > 0: compile-time strides of the specialised instantiation (rows_pad 20, k_pad 28, 48 positions
+// per tile padded to 52); 0: generic runtime strides.
+template <int RP4T, int KP4T, int NSPT>
 __global__ void __launch_bounds__(BWD_THREADS)
 sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* __restrict__ x, long ldx,
                const float* __restrict__ gy, long ldgy, const float* __restrict__ ckpt,
@@ -526,7 +557,8 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
     const int n = plan.nb_states, DP = plan.d_pad, RP = plan.rows_pad, KP = plan.k_pad;
-    const int NS = BWD_CONS * g.nsw, NSP = sm.nsp, hs = sm.hs;
+    constexpr bool FAST = RP4T > 0;
+    const int NS = BWD_CONS * g.nsw, NSP = FAST ? NSPT : sm.nsp, hs = sm.hs;
     const sn_sss_chunk* chunks = plan.chunks + (size_t)dir * plan.nchunks;
     const sn_sss_stage* stages = plan.stages + (size_t)dir * n;
     float* params = smem + sm.params;
@@ -554,7 +586,7 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
     const int nvalid = (int)(B - samp0 < 0 ? 0 : (B - samp0 > nsw ? nsw : B - samp0));
     const int rg_slot = lane / nq, q = lane - rg_slot * nq;
     const int rgs_state = (DP / 4 < g.rgs) ? DP / 4 : g.rgs;
-    const int RP4 = RP >> 2, KP4 = KP >> 2;
+    const int RP4 = FAST ? RP4T : (RP >> 2), KP4 = FAST ? KP4T : (KP >> 2);
     float* xh = smem + sm.xh;
     float* lh = smem + sm.lh;
     float* lcar_cur = smem + sm.lcar0;
@@ -603,20 +635,31 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
                         for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
                     const float4* prow = reinterpret_cast<const float4*>(slot + SSS_HDR) + rg;
                     const float* xv = xin;
+                    if (FAST && d_in == 16) {
+                        mac_f4<16, RP4T, NSPT>(acc, prow, xv);
+                        prow += 16 * RP4T;
+                    } else {
 #pragma unroll 4
-                    for (int i = 0; i < d_in; ++i) {
-                        const float4 p = prow[0];
-                        const float4 v = *reinterpret_cast<const float4*>(xv);
-                        prow += RP4; xv += NSP;
-                        fma16(acc, p, v);
+                        for (int i = 0; i < d_in; ++i) {
+                            const float4 p = prow[0];
+                            const float4 v = *reinterpret_cast<const float4*>(xv);
+                            prow += RP4; xv += NSP;
+                            fma16(acc, p, v);
+                        }
                     }
                     const float* uv = uv0;
+                    if (FAST && in_dim == 8) {
+                        mac_f4<8, RP4T, NSPT>(acc, prow, uv);
+                    } else if (FAST && in_dim == 9) {
+                        mac_f4<9, RP4T, NSPT>(acc, prow, uv);
+                    } else {
 #pragma unroll 4
-                    for (int i = 0; i < in_dim; ++i) {
-                        const float4 p = prow[0];
-                        const float4 v = *reinterpret_cast<const float4*>(uv);
-                        prow += RP4; uv += NSP;
-                        fma16(acc, p, v);
+                        for (int i = 0; i < in_dim; ++i) {
+                            const float4 p = prow[0];
+                            const float4 v = *reinterpret_cast<const float4*>(uv);
+                            prow += RP4; uv += NSP;
+                            fma16(acc, p, v);
+                        }
                     }
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
@@ -646,19 +689,28 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
                         for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
                     const float4* prow = P4 + ig;
                     const float* lv = lout;
+                    if (FAST && d_out == 16) {
+                        mac_f4<16, KP4T, NSPT>(acc, prow, lv);
+                        prow += 16 * KP4T;
+                    } else {
 #pragma unroll 4
-                    for (int r = 0; r < d_out; ++r) {
-                        const float4 p = prow[0];
-                        const float4 v = *reinterpret_cast<const float4*>(lv);
-                        prow += KP4; lv += NSP;
-                        fma16(acc, p, v);
+                        for (int r = 0; r < d_out; ++r) {
+                            const float4 p = prow[0];
+                            const float4 v = *reinterpret_cast<const float4*>(lv);
+                            prow += KP4; lv += NSP;
+                            fma16(acc, p, v);
+                        }
                     }
                     const float* gv = gyj;
-                    for (int r = 0; r < out_dim; ++r) {
-                        const float4 p = prow[0];
-                        const float4 v = *reinterpret_cast<const float4*>(gv);
-                        prow += KP4; gv += NSP;
-                        fma16(acc, p, v);
+                    if (FAST && out_dim == 2) {
+                        mac_f4<2, KP4T, NSPT>(acc, prow, gv);
+                    } else {
+                        for (int r = 0; r < out_dim; ++r) {
+                            const float4 p = prow[0];
+                            const float4 v = *reinterpret_cast<const float4*>(gv);
+                            prow += KP4; gv += NSP;
+                            fma16(acc, p, v);
+                        }
                     }
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
@@ -725,8 +777,7 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
                     for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-#pragma unroll 2
-                for (int sq = 0; sq < NS; sq += 4) {
+                auto body = [&](int sq) {
                     float4 gv[4], iv[4];
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
@@ -742,6 +793,13 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
                             acc[a][b] = fmaf(gv[a].z, iv[b].z, acc[a][b]);
                             acc[a][b] = fmaf(gv[a].w, iv[b].w, acc[a][b]);
                         }
+                };
+                if (FAST) {
+#pragma unroll 4
+                    for (int sq = 0; sq < 48; sq += 4) body(sq);
+                } else {
+#pragma unroll 2
+                    for (int sq = 0; sq < NS; sq += 4) body(sq);
                 }
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
@@ -795,7 +853,7 @@ int check_plan(const sn_sss_plan* p) {
     return 0;
 }
 
-template <int PAIRS>
+template <int PAIRS, int RP4T, int NSWPT>
 static int launch_fwd(const sn_sss_plan* p, const Geom& g, const float* packed, const float* x, int64_t ldx, float* y, int64_t ldy,
                       const float* bias, float* ckpt, int64_t B, int aligned, cudaStream_t st) {
     FwdSmem sm = make_fwd_smem(*p, g, PAIRS);
@@ -803,12 +861,12 @@ static int launch_fwd(const sn_sss_plan* p, const Geom& g, const float* packed, 
     SN_CHECK_ARG(smem <= 227 * 1024, "sss_forward: stage dims need %zu bytes of shared memory (> 227 KB)", smem);
     static size_t configured = 0;
     if (smem > configured) {
-        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_fwd_kernel<PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_fwd_kernel<PAIRS, RP4T, NSWPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     long tile = (long)PAIRS * g.nsw;
     unsigned grid = (unsigned)((B + tile - 1) / tile);
-    sss_fwd_kernel<PAIRS><<<grid, PAIRS * 64, smem, st>>>(*p, packed, x, (long)ldx, y, (long)ldy, bias, ckpt, (long)B, g, sm, aligned);
+    sss_fwd_kernel<PAIRS, RP4T, NSWPT><<<grid, PAIRS * 64, smem, st>>>(*p, packed, x, (long)ldx, y, (long)ldy, bias, ckpt, (long)B, g, sm, aligned);
     SN_CHECK_LAUNCH("sss_fwd_kernel");
     return 0;
 }
@@ -848,9 +906,12 @@ int sn_sss_forward(const sn_sss_plan* p, const float* packed, const float* x, in
     cudaStream_t st = snb::as_stream(stream);
     // big CTAs (6 warp pairs share one parameter stream) once they still fill the chip twice over; small ones otherwise
     const long big_tiles = (B + 6L * g.nsw - 1) / (6L * g.nsw);
-    if (big_tiles >= 2 * 148 && (size_t)make_fwd_smem(*p, g, 6).total * sizeof(float) <= 227 * 1024)
-        return launch_fwd<6>(p, g, packed, x, ldx, y, ldy, bias, ckpt, B, aligned, st);
-    return launch_fwd<2>(p, g, packed, x, ldx, y, ldy, bias, ckpt, B, aligned, st);
+    const bool big = big_tiles >= 2 * 148 && (size_t)make_fwd_smem(*p, g, 6).total * sizeof(float) <= 227 * 1024;
+    const bool fast = p->rows_pad == 20 && g.nswp == 28;   // specialised instantiation (compile-time strides)
+    if (fast) return big ? launch_fwd<6, 5, 28>(p, g, packed, x, ldx, y, ldy, bias, ckpt, B, aligned, st)
+                         : launch_fwd<2, 5, 28>(p, g, packed, x, ldx, y, ldy, bias, ckpt, B, aligned, st);
+    return big ? launch_fwd<6, 0, 0>(p, g, packed, x, ldx, y, ldy, bias, ckpt, B, aligned, st)
+               : launch_fwd<2, 0, 0>(p, g, packed, x, ldx, y, ldy, bias, ckpt, B, aligned, st);
 }
 
 size_t sn_sss_backward_workspace_floats(const sn_sss_plan* p) {
@@ -873,15 +934,14 @@ int sn_sss_backward(const sn_sss_plan* p, const float* packed, const float* x, i
     size_t smem = (size_t)sm.total * sizeof(float);
     SN_CHECK_ARG(smem <= 227 * 1024, "sss_backward: stage dims need %zu bytes of shared memory (> 227 KB)", smem);
     SN_CHECK_ARG(p->chunk_len_max <= 2 * BWD_CONS, "sss_backward: chunks of more than %d stages are not supported", 2 * BWD_CONS);
-    static size_t configured = 0;
-    if (smem > configured) {
-        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    const bool fast = p->rows_pad == 20 && p->k_pad == 28 && sm.nsp == 52 && g.nsw == 24;
+    SN_CHECK_CUDA(cudaFuncSetAttribute(sss_bwd_kernel<5, 7, 52>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SN_CHECK_CUDA(cudaFuncSetAttribute(sss_bwd_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SN_CHECK_CUDA(cudaMemsetAsync(workspace, 0, sn_sss_backward_workspace_floats(p) * sizeof(float), st));
     long tile = (long)BWD_CONS * g.nsw;
     dim3 grid((unsigned)((B + tile - 1) / tile), 2);
-    sss_bwd_kernel<<<grid, BWD_THREADS, smem, st>>>(*p, packed, x, (long)ldx, grad_y, (long)ldgy, ckpt, workspace, grad_bias, (long)B, g, sm);
+    if (fast) sss_bwd_kernel<5, 7, 52><<<grid, BWD_THREADS, smem, st>>>(*p, packed, x, (long)ldx, grad_y, (long)ldgy, ckpt, workspace, grad_bias, (long)B, g, sm);
+    else sss_bwd_kernel<0, 0, 0><<<grid, BWD_THREADS, smem, st>>>(*p, packed, x, (long)ldx, grad_y, (long)ldgy, ckpt, workspace, grad_bias, (long)B, g, sm);
     SN_CHECK_LAUNCH("sss_bwd_kernel");
     sss_unpack_grad_kernel<<<2 * p->nb_states, 128, 0, st>>>(p->stages, 2 * p->nb_states, p->rows_pad, p->k_pad, workspace, grad_params);
     SN_CHECK_LAUNCH("sss_unpack_grad_kernel");
