@@ -101,7 +101,188 @@ class SSSWorkload:
         return step
 
 
-WORKLOADS = {"sss": SSSWorkload}
+class _DenseInputsMixin:
+    def make_inputs(self, batch, device, seed):
+        g = torch.Generator(device=device).manual_seed(seed)
+        x = torch.rand((batch, self.input_dim), device=device, generator=g) * 2 - 1
+        gy = (torch.rand((batch, self.output_dim), device=device, generator=g) * 2 - 1) / batch
+        labels = torch.randint(0, self.output_dim, (batch,), device=device, generator=g)
+        return x, gy, labels
+
+    def _cpu_xy(self, batch, seed):
+        rng = np.random.default_rng(seed)
+        x = torch.tensor(rng.uniform(-1, 1, size=(batch, self.input_dim)).astype(np.float32))
+        gy = torch.tensor(rng.uniform(-1, 1, size=(batch, self.output_dim)).astype(np.float32)) / batch
+        return x, gy
+
+
+class LRWorkload(_DenseInputsMixin):
+    """BASELINE config C2 shape: LRLayer 2048 -> 1000, rank 128, batch 8192 (fp32 CUDA-core path of this round)."""
+    name, dtype, bound = "lr", "f32", "hbm"
+    input_dim, output_dim, rank = 2048, 1000, 128
+    global_batch, cpu_sample_batch = 8192, 8192
+    bytes_per_sample_kernel = 4 * (2048 + 1000)
+    bytes_per_sample = 2 * bytes_per_sample_kernel
+    flop_per_sample = 1816576
+    kernels = ("gemm_f32_kernel", "gemm_f32_kernel")
+
+    def describe(self):
+        return dict(workload="C2 shape: low-rank 2048->1000 rank 128, fp32 fwd+bwd, batch 8192 (bf16 tcgen05 path: next)",
+                    global_batch=self.global_batch, timed_inputs="resident in HBM")
+
+    def make_layer(self, device):
+        from structurednets_b200.layers.lr_layer import LRLayer
+        np.random.seed(2000)
+        layer = LRLayer(self.input_dim, self.output_dim, 0.1906)
+        assert layer.left_lr.shape[1] == self.rank
+        return layer.to(device)
+
+    def cpu_step_fn(self, batch):
+        from oracle import layers_cpu as O
+        np.random.seed(2000)
+        lim = lambda shape: np.sqrt(6 / sum(shape))
+        L = torch.tensor(np.random.uniform(-lim((1000, 128)), lim((1000, 128)), (1000, 128)).astype(np.float32), requires_grad=True)
+        R = torch.tensor(np.random.uniform(-lim((128, 2048)), lim((128, 2048)), (128, 2048)).astype(np.float32), requires_grad=True)
+        b = torch.zeros(1000, requires_grad=True)
+        x, gy = self._cpu_xy(batch, 2000)
+
+        def step():
+            for p in (L, R, b):
+                p.grad = None
+            O.lr_forward(x, L, R, b).backward(gy)
+        return step
+
+
+class LRBf16Workload(LRWorkload):
+    """BASELINE config C2: LRLayer 2048 -> 1000, rank 128, bf16 fwd+bwd (tcgen05 / TMEM / TMA), fp32 master parameters."""
+    name, dtype, bound = "lr_bf16", "bf16", "hbm"
+    bytes_per_sample_kernel = 2 * (2048 + 1000)
+    bytes_per_sample = 2 * bytes_per_sample_kernel        # SURVEY.md section 8(d): 12 192 B / sample
+    kernels = ("gemm_bf16_tc_kernel", "gemm_bf16_tc_kernel")
+
+    def describe(self):
+        return dict(workload="C2: low-rank 2048->1000 rank 128, bf16 fwd+bwd on tcgen05 (fp32 accumulate, fp32 master params), batch 8192",
+                    global_batch=self.global_batch, timed_inputs="resident in HBM")
+
+    def make_inputs(self, batch, device, seed):
+        x, gy, labels = super().make_inputs(batch, device, seed)
+        return x.bfloat16(), gy.bfloat16(), labels
+
+
+class PSMWorkload(_DenseInputsMixin):
+    """BASELINE config C3: PSMLayer 4096 -> 1000, 3 factors, nb_params_share 0.1 => 409 599 nnz, batch 8192, intended
+    factor order."""
+    name, dtype, bound = "psm", "f32", "hbm"
+    input_dim, output_dim = 4096, 1000
+    global_batch, cpu_sample_batch = 8192, 512
+    bytes_per_sample_kernel = 4 * (4096 + 1000)
+    bytes_per_sample = 2 * bytes_per_sample_kernel
+    flop_per_sample = 2184528
+    kernels = ("psm_fwd_kernel", "psm_bwd_kernel")
+
+    def describe(self):
+        return dict(workload="C3: PSM 4096->1000, 3 sparse factors, 409 599 nnz (share 0.1), fp32 fwd+bwd, batch 8192",
+                    global_batch=self.global_batch, timed_inputs="resident in HBM")
+
+    def factors(self):
+        import scipy.sparse
+        shapes = [(1000, 4096), (4096, 4096), (4096, 4096)]
+        out = []
+        for k, (r, c) in enumerate(shapes):
+            m = scipy.sparse.random(r, c, density=136533 / (r * c), random_state=3000 + k, format="csr", dtype=np.float64)
+            m.data = np.random.default_rng(3000 + k).uniform(-0.05, 0.05, size=m.data.shape)
+            out.append(m)
+        return out
+
+    def make_layer(self, device):
+        from structurednets_b200.layers.psm_layer import PSMLayer
+        return PSMLayer(self.input_dim, self.output_dim, sparse_matrices=self.factors()).to(device)
+
+    def cpu_step_fn(self, batch):
+        from oracle import layers_cpu as O
+        fs = [torch.tensor(f.toarray()).float().requires_grad_(True) for f in self.factors()]
+        b = torch.zeros(1000, requires_grad=True)
+        x, gy = self._cpu_xy(batch, 3000)
+
+        def step():   # the reference's default path: dense mm chain (psm_layer.py:51-58), corrected factor order
+            for p in fs + [b]:
+                p.grad = None
+            O.psm_forward(x, fs, b).backward(gy)
+        return step
+
+
+class HMatWorkload(_DenseInputsMixin):
+    """BASELINE config C4-H: HMatLayer 2048 -> 1000, eta 0.5, min block 2 => 2560 leaves of rank min(6, dim-1), batch 8192."""
+    name, dtype, bound = "hmat", "f32", "hbm"
+    input_dim, output_dim = 2048, 1000
+    global_batch, cpu_sample_batch = 8192, 64
+    bytes_per_sample_kernel = 4 * (2048 + 1000)
+    bytes_per_sample = 2 * bytes_per_sample_kernel
+    flop_per_sample = 2130000
+    kernels = ("hmat_fwd_kernel", "hmat_bwd_kernel")
+
+    def describe(self):
+        return dict(workload="C4-H: H-matrix 2048->1000, eta 0.5, 2560 leaves (rank <= 6), fp32 fwd+bwd, batch 8192",
+                    global_batch=self.global_batch, timed_inputs="resident in HBM")
+
+    def hmatrix(self):
+        from structurednets_b200.hmatrix import HMatrix, build_hmat_block_cluster_tree
+        rng = np.random.default_rng(4000)
+        tree = build_hmat_block_cluster_tree((1000, 2048), eta=0.5, min_block_size=2)
+        for leaf in tree.get_all_leaf_elements():
+            rows, cols = len(leaf.row_range), len(leaf.col_range)
+            k = min(6, min(rows, cols) - 1)
+            leaf.set_hmatrix_component(torch.tensor(rng.uniform(-1, 1, (rows, k)) / np.sqrt(k)).float(),
+                                       torch.tensor(rng.uniform(-1, 1, (k, cols)) / np.sqrt(cols)).float())
+        return HMatrix(tree, shape=(1000, 2048))
+
+    def make_layer(self, device):
+        from structurednets_b200.layers.hmat_layer import HMatLayer
+        return HMatLayer(self.input_dim, self.output_dim, 0.2, initial_hmatrix=self.hmatrix()).to(device)
+
+    def cpu_step_fn(self, batch):
+        from oracle import layers_cpu as O
+        hm = self.hmatrix()
+        comps = [(c.row_range.start, c.row_range.stop, c.col_range.start, c.col_range.stop, c.left_lr.detach().clone().requires_grad_(True),
+                  c.right_lr.detach().clone().requires_grad_(True)) for c in hm.get_all_hmatrix_components() if c.are_low_rank_components_set()]
+        b = torch.zeros(1000, requires_grad=True)
+        x, gy = self._cpu_xy(batch, 4000)
+
+        def step():
+            for c in comps:
+                c[4].grad = None; c[5].grad = None
+            O.hmat_forward(x, comps, b, 1000).backward(gy)
+        return step
+
+
+class LDRWorkload(_DenseInputsMixin):
+    """BASELINE config C4-L: LDRLayer 2048 -> 2048 (square only), share 0.1 => displacement rank 99, batch 8192."""
+    name, dtype, bound = "ldr", "f64 series + f32 apply", "hbm"
+    input_dim, output_dim = 2048, 2048
+    global_batch, cpu_sample_batch = 8192, 0
+    bytes_per_sample_kernel = 4 * (2048 + 2048)
+    bytes_per_sample = 2 * bytes_per_sample_kernel
+    flop_per_sample = 16.8e6
+    kernels = ("gemm_f32_kernel", "gemm_f32_kernel")
+
+    def describe(self):
+        return dict(workload="C4-L: LDR 2048->2048 (reference is square-only), displacement rank 99, batch 8192; the reference's own "
+                             "construction is O(r n^4 log n) and cannot run at this size", global_batch=self.global_batch,
+                    timed_inputs="resident in HBM")
+
+    def make_layer(self, device):
+        from structurednets_b200.layers.ldr_layer import LDRLayer
+        np.random.seed(4100)
+        layer = LDRLayer(2048, 2048, 0.1)
+        assert layer.representation_matrices[2].shape[1] == 99
+        return layer.to(device)
+
+    def cpu_step_fn(self, batch):
+        return None
+
+
+WORKLOADS = {"sss": SSSWorkload, "lr": LRWorkload, "lr_bf16": LRBf16Workload, "psm": PSMWorkload, "hmat": HMatWorkload, "ldr": LDRWorkload}
+
 
 
 # ----------------------------------------------------------------------------------------------
@@ -189,6 +370,9 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if not wl.cpu_sample_batch:
+        print(json.dumps(dict(impl="reference", unavailable="the reference cannot run this size on a CPU (O(r n^4 log n) weight build)")))
+        return
     base, med, n = time_cpu_baseline(wl, steps=max(args.steps, 2), warmup=max(args.warmup, 1), budget_s=120.0)
     cfg = wl.describe()
     cfg["sample_batch"] = wl.cpu_sample_batch
@@ -220,13 +404,26 @@ def run_ours(args, wl):
     local_batch = wl.global_batch // n_gpus
     layer = wl.make_layer(device)
     x, gy, labels = wl.make_inputs(local_batch, device, seed=5000 + rank)
-    flat_grad = layer.flat_grad()
+    has_flat = hasattr(layer, "flat_grad")
+    flat_grad = layer.flat_grad() if has_flat else None
     stream = torch.cuda.current_stream()
+
+    def zero_grads():
+        if has_flat:
+            layer.zero_flat_grad()
+        for p in layer.parameters():
+            if p.grad is not None and (not has_flat or p.grad.is_sparse or p.dtype != torch.float32):
+                p.grad = None
+
+    def sync_grads():
+        if n_gpus > 1:
+            from structurednets_b200.distributed import GradSynchronizer
+            GradSynchronizer(layer)()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def step(rec=None):
-        layer.zero_flat_grad()
+        zero_grads()
         if rec is not None:
             rec[0].record(stream)
         y = layer(x)
@@ -235,8 +432,7 @@ def run_ours(args, wl):
         y.backward(gy)
         if rec is not None:
             rec[2].record(stream)
-        if n_gpus > 1:
-            dist.all_reduce(flat_grad)
+        sync_grads()
         return y
 
     def barrier():
@@ -270,7 +466,7 @@ def run_ours(args, wl):
 
     # ---- end to end through the module API with host buffers (pinned H2D + loss + D2H of the loss) ----
     e2e_steps = max(3, min(args.steps, 5))
-    x_host = torch.empty((local_batch, wl.input_dim), dtype=torch.float32, pin_memory=True)
+    x_host = torch.empty((local_batch, wl.input_dim), dtype=x.dtype, pin_memory=True)
     x_host.copy_(x)
     labels_host = labels.cpu().pin_memory()
     loss_fn = torch.nn.CrossEntropyLoss()
@@ -278,11 +474,10 @@ def run_ours(args, wl):
     def e2e_step():
         xd = x_host.to(device, non_blocking=True)
         ld = labels_host.to(device, non_blocking=True)
-        layer.zero_flat_grad()
-        loss = loss_fn(layer(xd), ld)
+        zero_grads()
+        loss = loss_fn(layer(xd).float(), ld)
         loss.backward()
-        if n_gpus > 1:
-            dist.all_reduce(flat_grad)
+        sync_grads()
         return float(loss.item())     # device -> host read of the step's result
 
     e2e_step()
@@ -296,20 +491,23 @@ def run_ours(args, wl):
         t = torch.tensor([e2e_s], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = dict(value=wl.global_batch / e2e_s, unit="samples/s", h2d_bytes_per_step=int(x_host.numel() * 4 + labels_host.numel() * 8),
+    e2e = dict(value=wl.global_batch / e2e_s, unit="samples/s", h2d_bytes_per_step=int(x_host.numel() * x_host.element_size() + labels_host.numel() * 8),
                d2h_bytes_per_step=4, steps=e2e_steps, ms_per_step=e2e_s * 1e3)
 
     if rank == 0:
-        dom_ms, dom_name = (bwd_ms, "sss_bwd_kernel") if bwd_ms >= fwd_ms else (fwd_ms, "sss_fwd_kernel")
+        knames = getattr(wl, "kernels", ("sss_fwd_kernel", "sss_bwd_kernel"))
+        dom_ms, dom_name = (bwd_ms, knames[1] + " (backward launch group)") if bwd_ms >= fwd_ms else (fwd_ms, knames[0] + " (forward launch group)")
         achieved = wl.bytes_per_sample_kernel * local_batch / (dom_ms * 1e-3) / 1e9
         roofline = dict(bound=wl.bound, kernel=dom_name, achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s",
                         frac=achieved / peaks["hbm_gbs"], traffic=None, peak_source=peaks["source"],
                         launch_ms=dom_ms, fwd_ms=fwd_ms, bwd_ms=bwd_ms,
                         step_hbm_frac=wl.bytes_per_sample * local_batch / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                        tflops=wl.flop_per_sample * local_batch / (ms_per_step * 1e-3) / 1e12,
+                        bf16_tensor_frac_of_measured=(wl.flop_per_sample * local_batch / (ms_per_step * 1e-3) / 1e12 / peaks["bf16_tflops"]) if wl.dtype == "bf16" else None,
                         fp32_fma_tflops=wl.flop_per_sample * local_batch / (ms_per_step * 1e-3) / 1e12,
                         fp32_fma_frac_of_nominal=wl.flop_per_sample * local_batch / (ms_per_step * 1e-3) / 1e12 / FP32_FMA_TFLOPS_NOMINAL)
         cpu_base = None
-        if n_gpus == 1 and not args.no_cpu_baseline:
+        if n_gpus == 1 and not args.no_cpu_baseline and wl.cpu_sample_batch:
             cpu_base, _, _ = time_cpu_baseline(wl, steps=20, warmup=2, budget_s=20.0)
         cfg = wl.describe()
         cfg.update(local_batch=local_batch, parallelism="dp%d" % n_gpus, l2_policy="inputs larger than L2 (no flush needed)")

@@ -108,6 +108,19 @@ int sn_lr_backward_f32(const float* x, int64_t ldx, const float* grad_y, int64_t
                        const float* hidden, float* grad_hidden_ws, float* grad_left, float* grad_right, float* grad_bias,
                        float* grad_x, int64_t ldgx, int64_t B, int in_dim, int out_dim, int rank, sn_stream_t stream);
 
+/* Low-rank layer, bf16 tensor-core path (tcgen05 / TMEM / TMA; BASELINE config C2).  All bf16 matrices are row-major
+ * with 16-byte aligned rows (row pitch multiple of 8 elements).  sn_lr_tc_cast_params makes the bf16 copies
+ * L (out x rank), L^T (rank x lt_ld) and R (rank x in) of the fp32 master parameters.  Backward scratch (bf16):
+ * ghid (B x rank), gyt (out x ldt), ht (rank x ldt), ght (rank x ldt), xt (in x ldt), ldt = B rounded up to 8;
+ * grad_left / grad_right / grad_bias are fp32 and accumulated. */
+int sn_lr_tc_cast_params(const float* left, const float* right, void* left_bf16, void* left_t_bf16, int64_t lt_ld, void* right_bf16,
+                         int in_dim, int out_dim, int rank, sn_stream_t stream);
+int sn_lr_tc_forward(const void* x, int64_t ldx, const void* left_bf16, const void* right_bf16, const float* bias, void* hidden, void* y,
+                     int64_t ldy, int64_t B, int in_dim, int out_dim, int rank, sn_stream_t stream);
+int sn_lr_tc_backward(const void* x, int64_t ldx, const void* grad_y, int64_t ldgy, const void* left_t_bf16, int64_t lt_ld, const void* hidden,
+                      void* ghid, void* gyt, void* ht, void* ght, void* xt, int64_t ldt, float* grad_left, float* grad_right, float* grad_bias,
+                      int64_t B, int in_dim, int out_dim, int rank, sn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * H-matrix layer -- replaces HMatLayer.forward (layers/hmat_layer.py:34-49) and its backward.
  *   leaves: device table, 8 int32 per leaf {row_start, rows, col_start, cols, rank, off_left, off_right, 0};

@@ -83,6 +83,12 @@ def _declare(lib):
     lib.sn_tl_build_weight.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp]
     lib.sn_tl_backward.restype = c_int
     lib.sn_tl_backward.argtypes = [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.sn_lr_tc_cast_params.restype = c_int
+    lib.sn_lr_tc_cast_params.argtypes = [vp, vp, vp, vp, i64, vp, i32, i32, i32, vp]
+    lib.sn_lr_tc_forward.restype = c_int
+    lib.sn_lr_tc_forward.argtypes = [vp, i64, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp]
+    lib.sn_lr_tc_backward.restype = c_int
+    lib.sn_lr_tc_backward.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, vp]
     for name, fn in _EXTRA_DECLS:
         fn(lib)
 

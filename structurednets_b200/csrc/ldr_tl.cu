@@ -152,12 +152,15 @@ __global__ void row_band_dots_kernel(const double* __restrict__ S, const double*
     }
 }
 // gband(B) += pattern( P^T V ):  dB[b][q] = sum_p P[p][b] V[p][q] for b in {q-1,q,q+1} and corners; thread per column q
+// (blockIdx.y splits the rows p; partial sums are combined with double atomics)
 __global__ void col_band_dots_kernel(const double* __restrict__ P, const double* __restrict__ V, double* __restrict__ gband, int n) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     double a0 = 0, am = 0, ap = 0, ac = 0;   // b = q, q-1, q+1, corner
     const bool hm = q > 0, hp = q + 1 < n, c_first = (n > 2 && q == n - 1), c_last = (n > 2 && q == 0);
-    for (int p = 0; p < n; ++p) {
+    const int rows_per = (n + gridDim.y - 1) / gridDim.y;
+    const int p_begin = blockIdx.y * rows_per, p_end = min(n, p_begin + rows_per);
+    for (int p = p_begin; p < p_end; ++p) {
         const double* pr = P + (size_t)p * n;
         double v = V[(size_t)p * n + q];
         a0 += pr[q] * v;
@@ -166,11 +169,11 @@ __global__ void col_band_dots_kernel(const double* __restrict__ P, const double*
         if (c_first) ac += pr[0] * v;        // dB[0][n-1]
         if (c_last) ac += pr[n - 1] * v;     // dB[n-1][0]
     }
-    gband[n + q] += a0;                       // di[q] = B[q][q]
-    if (hm) gband[2 * n + q - 1] += am;       // B[q-1][q] = up[q-1]
-    if (hp) gband[q + 1] += ap;               // B[q+1][q] = lo[q+1]
-    if (c_first) gband[3 * n] += ac;
-    if (c_last) gband[3 * n + 1] += ac;
+    atomicAdd(gband + n + q, a0);                       // di[q] = B[q][q]
+    if (hm) atomicAdd(gband + 2 * n + q - 1, am);       // B[q-1][q] = up[q-1]
+    if (hp) atomicAdd(gband + q + 1, ap);               // B[q+1][q] = lo[q+1]
+    if (c_first) atomicAdd(gband + 3 * n, ac);
+    if (c_last) atomicAdd(gband + 3 * n + 1, ac);
 }
 
 inline dim3 grid2(int n) { return dim3(snb::ceil_div(n, 128), n); }
@@ -317,7 +320,7 @@ int sn_ldr_backward(int n, int r, const float* dW, const int32_t* A_slot, int A_
         band_right_kernel<<<grid2(n), 128, 0, st>>>(bandB, Pk, tmp, n); SN_CHECK_LAUNCH("band_right_kernel");            // Q = P B
         row_band_dots_kernel<<<snb::ceil_div(n, 4), 128, 0, st>>>(S, tmp, gA, n); SN_CHECK_LAUNCH("row_band_dots_kernel");  // dA += pattern(S Q^T)
         band_left_kernel<<<grid2(n), 128, 0, st>>>(bandAt, S, tmp2, n); SN_CHECK_LAUNCH("band_left_kernel");             // V = A^T S
-        col_band_dots_kernel<<<snb::ceil_div(n, 128), 128, 0, st>>>(Pk, tmp2, gB, n); SN_CHECK_LAUNCH("col_band_dots_kernel"); // dB += pattern(P^T V)
+        col_band_dots_kernel<<<dim3(snb::ceil_div(n, 128), n >= 256 ? 64 : 1), 128, 0, st>>>(Pk, tmp2, gB, n); SN_CHECK_LAUNCH("col_band_dots_kernel"); // dB += pattern(P^T V)
         band_right_kernel<<<grid2(n), 128, 0, st>>>(bandBt, tmp2, S, n); SN_CHECK_LAUNCH("band_right_kernel");           // S = V B^T
     }
     if (gA_vals && A_nnz) { band_scatter_grad_kernel<<<grid1(A_nnz), 256, 0, st>>>(gA, A_slot, A_nnz, gA_vals); SN_CHECK_LAUNCH("band_scatter_grad"); }
