@@ -60,9 +60,20 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(const void* smem_tile
     d |= (uint64_t)2 << 61;                                   // layout type SWIZZLE_128B, bits [61,64)
     return d;
 }
-// Instruction descriptor: D fp32, A/B bf16, both K-major, N at [17,23) in units of 8, M at [24,29) in units of 16.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// Same for an MN-major operand tile (the M or N index is the contiguous one): TMA boxes of [64 K-rows][64 elements = 128 B],
+// SWIZZLE_128B; 8 K-rows are 1024 bytes apart (SBO), consecutive 64-element MN blocks are `mn_block_bytes` apart (LBO).
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(const void* smem_tile, uint32_t mn_block_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem_tile) & 0x3FFFF) >> 4);
+    d |= (uint64_t)((mn_block_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor: D fp32, A/B bf16; bit 15 / 16 = A / B is MN-major; N at [17,23) in units of 8, M at [24,29) in units of 16.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool mn_major = false) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -94,7 +105,9 @@ struct GemmArgs {
 template <int BN>
 constexpr size_t smem_bytes() { return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/; }
 
-template <int BN, int EPI>
+// MN = false: A[M x K], B[N x K] (K contiguous).  MN = true: A given as At[K x M], B as Bt[K x N] (M / N contiguous), i.e.
+// D = At^T Bt -- the batch-reduction GEMMs of a backward pass read activations in their natural [sample][feature] layout.
+template <int BN, int EPI, bool MN>
 __global__ void __launch_bounds__(THREADS)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmArgs args) {
     static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [32, 256] here");
@@ -137,23 +150,33 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const int s = kb % STAGES, round = kb / STAGES;
                 if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
                 mbar_expect_tx(full + s, A_BYTES + B_BYTES);
-                tma_load_2d(sA + s * A_BYTES, &map_a, kbeg + kb * BK, m0, full + s);
-                tma_load_2d(sB + s * B_BYTES, &map_b, kbeg + kb * BK, n0, full + s);
+                if (MN) {
+#pragma unroll
+                    for (int h = 0; h < BM / 64; ++h) tma_load_2d(sA + s * A_BYTES + h * (BK * 128), &map_a, m0 + 64 * h, kbeg + kb * BK, full + s);
+#pragma unroll
+                    for (int h = 0; h < BN / 64; ++h) tma_load_2d(sB + s * B_BYTES + h * (BK * 128), &map_b, n0 + 64 * h, kbeg + kb * BK, full + s);
+                } else {
+                    tma_load_2d(sA + s * A_BYTES, &map_a, kbeg + kb * BK, m0, full + s);
+                    tma_load_2d(sB + s * B_BYTES, &map_b, kbeg + kb * BK, n0, full + s);
+                }
             }
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, MN);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES, round = kb / STAGES;
                 mbar_wait(full + s, round & 1);
                 tc_fence_after();
-                const uint64_t da = make_kmajor_sw128_desc(sA + s * A_BYTES);
-                const uint64_t db = make_kmajor_sw128_desc(sB + s * B_BYTES);
+                const uint64_t da = MN ? make_mnmajor_sw128_desc(sA + s * A_BYTES, BK * 128) : make_kmajor_sw128_desc(sA + s * A_BYTES);
+                const uint64_t db = MN ? make_mnmajor_sw128_desc(sB + s * B_BYTES, BK * 128) : make_kmajor_sw128_desc(sB + s * B_BYTES);
+                // one UMMA K step = 16 bf16: K-major -> 32 bytes along the row (+2 in 16-byte units);
+                //                            MN-major -> 16 rows of 128 bytes (+128 in 16-byte units)
+                constexpr int KSTEP = MN ? 128 : 2;
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)   // 16 bf16 = 32 bytes per UMMA K step: advance the start address by 2 (x16 B)
-                    umma_bf16(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                for (int k = 0; k < BK / 16; ++k)
+                    umma_bf16(tmem_acc, da + KSTEP * k, db + KSTEP * k, idesc, (kb | k) ? 1u : 0u);
                 umma_commit(empty + s);             // frees the smem slot once these MMAs have read it
             }
             umma_commit(acc_ready);                 // accumulator complete
@@ -256,15 +279,22 @@ inline int make_map_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint
     return 0;
 }
 
-// D (+)= alpha * A[M x K] B[N x K]^T ; A, B bf16 K-major with leading dimensions lda, ldb (elements).
+// D (+)= alpha * A[M x K] B[N x K]^T ; A, B bf16 K-major with leading dimensions lda, ldb (elements)          (MN = false)
+// D (+)= alpha * At[K x M]^T Bt[K x N] ; At, Bt bf16 row-major with leading dimensions lda, ldb (elements)     (MN = true)
 // ksplit > 1 requires EPI == ATOMIC_F32 (each K slice adds its partial sum).
-template <int BN, int EPI>
+template <int BN, int EPI, bool MN = false>
 inline int gemm_bf16_tc(int M, int N, int K, const void* A, long lda, const void* B, long ldb, void* D, long ldd, const float* bias,
                         float alpha, int ksplit, cudaStream_t stream) {
+    static_assert(!MN || BN % 64 == 0, "MN-major operands are loaded in 64-element blocks");
     if (M <= 0 || N <= 0) return 0;
     CUtensorMap ma, mb;
-    if (int rc = make_map_bf16(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM)) return rc;
-    if (int rc = make_map_bf16(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN)) return rc;
+    if (MN) {
+        if (int rc = make_map_bf16(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK)) return rc;   // [K rows][M cols], box 64 x 64
+        if (int rc = make_map_bf16(&mb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK)) return rc;
+    } else {
+        if (int rc = make_map_bf16(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM)) return rc;
+        if (int rc = make_map_bf16(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN)) return rc;
+    }
     GemmArgs args;
     args.M = M; args.N = N; args.K = K;
     if (ksplit < 1) ksplit = 1;
@@ -273,8 +303,8 @@ inline int gemm_bf16_tc(int M, int N, int K, const void* A, long lda, const void
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), ceil_div(K > 0 ? K : 1, args.kslice));
     SN_CHECK_ARG(EPI == ATOMIC_F32 || grid.z == 1, "split-K needs the atomic epilogue");
     constexpr size_t smem = smem_bytes<BN>();
-    SN_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_bf16_tc_kernel<BN, EPI><<<grid, THREADS, smem, stream>>>(ma, mb, args);
+    SN_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, EPI, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gemm_bf16_tc_kernel<BN, EPI, MN><<<grid, THREADS, smem, stream>>>(ma, mb, args);
     SN_CHECK_LAUNCH("gemm_bf16_tc_kernel");
     return 0;
 }

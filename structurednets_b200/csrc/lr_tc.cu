@@ -8,8 +8,8 @@
 //              dL += gy^T h          (out x B)(r x B)^T      tcgen05 on transposed copies, split-K over the batch, fp32 atomics
 //              dR += gh^T x          (r x B)(in x B)^T       same
 //              db += colsum(gy)
-// The batch-reduction GEMMs run on bf16 transposes made by a tiled transpose kernel (K must be the contiguous dimension
-// of both UMMA operands here; MN-major descriptors that would avoid the extra pass are the next step).
+// The batch-reduction GEMMs run on bf16 transposes made by a tiled transpose kernel (ranks that are not a multiple of 64);
+// otherwise the activations are consumed in their natural [sample][feature] layout through MN-major UMMA descriptors.
 #include "gemm_tc.cuh"
 
 namespace {
@@ -117,17 +117,26 @@ int sn_lr_tc_backward(const void* x, int64_t ldx, const void* grad_y, int64_t ld
         colsum_bf16_kernel<<<grid, 128, 0, st>>>((const bf16*)grad_y, ldgy, B, out_dim, grad_bias);
         SN_CHECK_LAUNCH("colsum_bf16_kernel");
     }
+    const bool mn_ok = (rank % 64 == 0);   // MN-major operands are fetched in 64-element blocks along M / N
     if (grad_left) {   // dL += gy^T h
-        if (int rc = transpose_bf16((const bf16*)grad_y, ldgy, (bf16*)gyt, ldt, B, out_dim, st)) return rc;
-        if (int rc = transpose_bf16((const bf16*)hidden, rank, (bf16*)ht, ldt, B, rank, st)) return rc;
         const int tiles = snb::ceil_div(out_dim, 128) * snb::ceil_div(rank, 128);
-        if (int rc = gemm_bf16_tc<128, ATOMIC_F32>(out_dim, rank, (int)B, gyt, ldt, ht, ldt, grad_left, rank, nullptr, 1.f, split_for(tiles, B), st)) return rc;
+        if (mn_ok) {   // operands read in their natural [sample][feature] layout through MN-major UMMA descriptors
+            if (int rc = gemm_bf16_tc<128, ATOMIC_F32, true>(out_dim, rank, (int)B, grad_y, ldgy, hidden, rank, grad_left, rank, nullptr, 1.f, split_for(tiles, B), st)) return rc;
+        } else {
+            if (int rc = transpose_bf16((const bf16*)grad_y, ldgy, (bf16*)gyt, ldt, B, out_dim, st)) return rc;
+            if (int rc = transpose_bf16((const bf16*)hidden, rank, (bf16*)ht, ldt, B, rank, st)) return rc;
+            if (int rc = gemm_bf16_tc<128, ATOMIC_F32>(out_dim, rank, (int)B, gyt, ldt, ht, ldt, grad_left, rank, nullptr, 1.f, split_for(tiles, B), st)) return rc;
+        }
     }
     if (grad_right) {  // dR += gh^T x
-        if (int rc = transpose_bf16((const bf16*)ghid, rank, (bf16*)ght, ldt, B, rank, st)) return rc;
-        if (int rc = transpose_bf16((const bf16*)x, ldx, (bf16*)xt, ldt, B, in_dim, st)) return rc;
         const int tiles = snb::ceil_div(rank, 128) * snb::ceil_div(in_dim, 128);
-        if (int rc = gemm_bf16_tc<128, ATOMIC_F32>(rank, in_dim, (int)B, ght, ldt, xt, ldt, grad_right, in_dim, nullptr, 1.f, split_for(tiles, B), st)) return rc;
+        if (mn_ok) {
+            if (int rc = gemm_bf16_tc<128, ATOMIC_F32, true>(rank, in_dim, (int)B, ghid, rank, x, ldx, grad_right, in_dim, nullptr, 1.f, split_for(tiles, B), st)) return rc;
+        } else {
+            if (int rc = transpose_bf16((const bf16*)ghid, rank, (bf16*)ght, ldt, B, rank, st)) return rc;
+            if (int rc = transpose_bf16((const bf16*)x, ldx, (bf16*)xt, ldt, B, in_dim, st)) return rc;
+            if (int rc = gemm_bf16_tc<128, ATOMIC_F32>(rank, in_dim, (int)B, ght, ldt, xt, ldt, grad_right, in_dim, nullptr, 1.f, split_for(tiles, B), st)) return rc;
+        }
     }
     return 0;
 }

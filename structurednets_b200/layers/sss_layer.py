@@ -286,8 +286,9 @@ class SSSLayer(FlatParamsMixin, StructuredLayer):
         return ws
 
     def _packed_params(self, plan):
-        """Per-stage re-laid-out copy of the parameters; refreshed when any parameter changed
-        (views share the flat buffer's version counter)."""
+        """Per-stage re-laid-out copy of the parameters, refreshed on every forward (one ~5 us launch): the
+        parameters are updated in place by optimizers and nothing cheaper than re-packing detects that reliably
+        (``p.data = view`` does not share the flat buffer's version counter)."""
         flat = self.__dict__["_flat"]
         packed = self.__dict__.get("_dev_packed")
         if packed is None or packed.device != flat.device:
@@ -295,10 +296,8 @@ class SSSLayer(FlatParamsMixin, StructuredLayer):
             packed = torch.empty(int(n), dtype=torch.float32, device=flat.device)
             self.__dict__["_dev_packed"] = packed
             self.__dict__["_dev_packed_version"] = None
-        if self.__dict__.get("_dev_packed_version") != flat._version:
-            rc = _lib.lib().sn_sss_pack(ctypes.byref(plan["struct"]), _lib.ptr(flat), _lib.ptr(packed), _lib.stream_ptr())
-            _lib.check(rc, "sn_sss_pack")
-            self.__dict__["_dev_packed_version"] = flat._version
+        rc = _lib.lib().sn_sss_pack(ctypes.byref(plan["struct"]), _lib.ptr(flat), _lib.ptr(packed), _lib.stream_ptr())
+        _lib.check(rc, "sn_sss_pack")
         return packed
 
     # ---- forward ------------------------------------------------------------------------------

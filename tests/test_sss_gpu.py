@@ -92,3 +92,25 @@ def test_linearity_at_full_batch(built_lib):
     rhs = 0.5 * (y1 - y0) + 0.25 * (y2 - y0)
     assert float((lhs - rhs).abs().max()) < 1e-5 * float(rhs.abs().max()) * 10
     torch.testing.assert_close(y0, layer.bias.detach().expand_as(y0))
+
+
+def test_inplace_parameter_updates_are_seen_by_the_next_forward(built_lib):
+    """Optimizers update parameters in place; the packed per-stage copy must follow (regression test)."""
+    layer, _, X = make(CASES[4])
+    layer = layer.to("cuda")
+    Xd = torch.tensor(X, device="cuda")
+    y0 = layer(Xd).detach().clone()
+    with torch.no_grad():
+        for p in layer.D:
+            p.mul_(3.0)
+        layer.B[2].add_(0.5)
+    y1 = layer(Xd).detach()
+    lists = oracle_lists(layer)
+    yo = O.sss_forward(torch.tensor(X), *[[p.cpu() for p in l] for l in lists], layer.bias.detach().cpu(), layer.dims_in, layer.dims_out)
+    assert float((y1 - y0).abs().max()) > 1e-2
+    assert rel_err(y1.cpu().numpy(), yo.detach().numpy()) < RTOL
+    opt = torch.optim.SGD(layer.parameters(), lr=0.05)
+    before = float((layer(Xd) - 1).square().mean())
+    for _ in range(20):
+        opt.zero_grad(); loss = (layer(Xd) - 1).square().mean(); loss.backward(); opt.step()
+    assert float((layer(Xd) - 1).square().mean()) < 0.95 * before
