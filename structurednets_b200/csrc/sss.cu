@@ -356,6 +356,20 @@ sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
         mbar_wait(bars + dir * 2 + (ch & 1), (ch >> 1) & 1);
         const float* ub = ubi ? ub_b : ub_a;
         const float* cbuf = pbuf + (size_t)(dir * 2 + (ch & 1)) * CL * sm.slot_floats;
+        // flush geometry: lanes = (row, sample-sub); the second visitor prefetches what the first one stored so the
+        // read-modify-write at the end of the chunk does not wait on L2
+        const int rl = c.nrows >= 32 ? 32 : (c.nrows >= 16 ? 16 : (c.nrows >= 8 ? 8 : (c.nrows >= 4 ? 4 : (c.nrows >= 2 ? 2 : 1))));
+        const int spl = 32 / rl;
+        const int lrow = lane & (rl - 1), lsub = lane / rl;
+        float yold[8];
+        const bool prefetched = c.second_visit && c.nrows <= rl && nsw <= 8 * spl;
+        if (prefetched) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int ls = lsub + k * spl;
+                yold[k] = (lrow < c.nrows && ls < nsw && s0 + ls < B) ? __ldcg(y + (size_t)(s0 + ls) * ldy + c.row0 + lrow) : 0.f;
+            }
+        }
 
         if (ckpt != nullptr) {   // checkpoint of the state entering the chunk, in true sample order
             const int d_first = reinterpret_cast<const int*>(cbuf)[4];
@@ -426,10 +440,16 @@ sss_fwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
             float* t = xs; xs = xn; xn = t;
         }
         // flush the chunk's outputs: y[s0 + ls][row0 + row]; lanes = (row, sample-sub), 4 independent samples in flight
-        {
-            const int rl = c.nrows >= 32 ? 32 : (c.nrows >= 16 ? 16 : (c.nrows >= 8 ? 8 : (c.nrows >= 4 ? 4 : (c.nrows >= 2 ? 2 : 1))));
-            const int spl = 32 / rl;
-            const int lrow = lane & (rl - 1), lsub = lane / rl;
+        if (prefetched) {
+            if (lrow < c.nrows) {
+                const float* ysrc = yb + lrow * nswp;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int ls = lsub + k * spl;
+                    if (ls < nsw && s0 + ls < B) y[(size_t)(s0 + ls) * ldy + c.row0 + lrow] = ysrc[pos_tab[ls]] + yold[k];
+                }
+            }
+        } else {
             for (int row = lrow; row < c.nrows; row += rl) {
                 const float bv = (!c.second_visit && bias != nullptr) ? __ldg(bias + c.row0 + row) : 0.f;
                 const float* ysrc = yb + row * nswp;
@@ -516,33 +536,41 @@ inline BwdSmem make_bwd_smem(const sn_sss_plan& p, const Geom& g) {
     return s;
 }
 
-// issue the (transposing) loads of one chunk for the calling warp's samples: dst[feature][w0 + pos(ls)]
+// issue the (transposing) loads of one chunk for the calling warp's samples: dst[feature][w0 + ls] (the backward keeps
+// samples in their natural order: position = local sample)
+//   checkpoint [feature][B]   : 16-byte cp.async along the samples when aligned, else 4-byte
+//   x / grad_y [sample][feat] : 4-byte cp.async, lanes along the (contiguous) feature index, pointer increments per sample
 __device__ __forceinline__ void bwd_issue_loads(const sn_sss_plan& plan, const sn_sss_chunk& c, int d_first, int dir, int ch,
                                                 const float* __restrict__ x, long ldx, const float* __restrict__ gy, long ldgy,
                                                 const float* __restrict__ ckpt, long B, long samp0, int nvalid, int nsw, int nsp,
-                                                const int* pos_tab, float* ck, float* ut, float* gt, int lane) {
+                                                float* ck, float* ut, float* gt, int lane) {
     const float* cbase = ckpt + ((size_t)(dir * plan.nchunks + ch) * plan.d_pad) * B + samp0;
-    for (int ls = lane; ls < nsw; ls += 32) {
-        const bool ok = ls < nvalid;
-        float* dst = ck + pos_tab[ls];
-        const float* src = cbase + ls;
-        for (int f = 0; f < d_first; ++f) cp_async4(dst + f * nsp, ok ? (const void*)(src + (size_t)f * B) : (const void*)x, ok);
+    if (((B | samp0) & 3) == 0 && (nsw & 3) == 0) {
+        const int nq4 = nsw >> 2;
+        for (int e = lane; e < d_first * nq4; e += 32) {
+            const int f = e / nq4, q4 = e - f * nq4;
+            const bool ok = 4 * q4 + 3 < nvalid;
+            if (ok || 4 * q4 >= nvalid) {
+                cp_async16(ck + f * nsp + 4 * q4, ok ? (const void*)(cbase + (size_t)f * B + 4 * q4) : (const void*)x, ok);
+            } else {
+                for (int t = 0; t < 4; ++t) cp_async4(ck + f * nsp + 4 * q4 + t, (4 * q4 + t < nvalid) ? (const void*)(cbase + (size_t)f * B + 4 * q4 + t) : (const void*)x, 4 * q4 + t < nvalid);
+            }
+        }
+    } else {
+        for (int ls = lane; ls < nsw; ls += 32) {
+            const bool ok = ls < nvalid;
+            for (int f = 0; f < d_first; ++f) cp_async4(ck + f * nsp + ls, ok ? (const void*)(cbase + (size_t)f * B + ls) : (const void*)x, ok);
+        }
     }
     for (int cc = lane; cc < c.ncols; cc += 32) {
         float* dcol = ut + cc * nsp;
         const float* src = x + (size_t)samp0 * ldx + c.col0 + cc;
-        for (int ls = 0; ls < nsw; ++ls) {
-            const bool ok = ls < nvalid;
-            cp_async4(dcol + pos_tab[ls], ok ? (const void*)(src + (size_t)ls * ldx) : (const void*)x, ok);
-        }
+        for (int ls = 0; ls < nsw; ++ls, src += ldx) cp_async4(dcol + ls, ls < nvalid ? (const void*)src : (const void*)x, ls < nvalid);
     }
     for (int rr = lane; rr < c.nrows; rr += 32) {
         float* dcol = gt + rr * nsp;
         const float* src = gy + (size_t)samp0 * ldgy + c.row0 + rr;
-        for (int ls = 0; ls < nsw; ++ls) {
-            const bool ok = ls < nvalid;
-            cp_async4(dcol + pos_tab[ls], ok ? (const void*)(src + (size_t)ls * ldgy) : (const void*)x, ok);
-        }
+        for (int ls = 0; ls < nsw; ++ls, src += ldgy) cp_async4(dcol + ls, ls < nvalid ? (const void*)src : (const void*)x, ls < nvalid);
     }
 }
 
@@ -563,7 +591,6 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
     const sn_sss_stage* stages = plan.stages + (size_t)dir * n;
     float* params = smem + sm.params;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + sm.bars);
-    int* pos_tab = reinterpret_cast<int*>(smem + sm.pos);
     const int nq = g.nq, nsw = g.nsw;
 
     sn_sss_chunk c = chunks[plan.nchunks - 1];
@@ -575,7 +602,6 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
         mbar_arrive_expect_tx(full_bar, bytes);
         bulk_g2s(params, packed + ((size_t)dir * n + c.kk_begin) * sm.blk, bytes, full_bar);
     }
-    for (int ls = threadIdx.x; ls < nsw; ls += BWD_THREADS) pos_tab[ls] = pos_of(ls, nq);
     for (int e = threadIdx.x; e < NSP; e += BWD_THREADS) smem[sm.zero + e] = 0.f;
     for (int e = threadIdx.x; e < 2 * hs; e += BWD_THREADS) smem[sm.lcar0 + e] = 0.f;   // lcar0 and lcar1 are adjacent
     __syncthreads();
@@ -595,7 +621,7 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
     int buf = 0;
 
     int d_first = stages[c.kk_begin].d_in;
-    bwd_issue_loads(plan, c, d_first, dir, plan.nchunks - 1, x, ldx, gy, ldgy, ckpt, B, samp0, nvalid, nsw, NSP, pos_tab, smem + sm.ck0 + w0,
+    bwd_issue_loads(plan, c, d_first, dir, plan.nchunks - 1, x, ldx, gy, ldgy, ckpt, B, samp0, nvalid, nsw, NSP, smem + sm.ck0 + w0,
                     smem + sm.ut0 + w0, smem + sm.gt0 + w0, lane);
     cp_async_commit();
 
@@ -609,7 +635,7 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
         if (ch > 0) {
             cn = chunks[ch - 1];
             const int d_first_n = stages[cn.kk_begin].d_in;
-            bwd_issue_loads(plan, cn, d_first_n, dir, ch - 1, x, ldx, gy, ldgy, ckpt, B, samp0, nvalid, nsw, NSP, pos_tab,
+            bwd_issue_loads(plan, cn, d_first_n, dir, ch - 1, x, ldx, gy, ldgy, ckpt, B, samp0, nvalid, nsw, NSP,
                             smem + (buf ? sm.ck0 : sm.ck1) + w0, smem + (buf ? sm.ut0 : sm.ut1) + w0, smem + (buf ? sm.gt0 : sm.gt1) + w0, lane);
         }
         cp_async_commit();
