@@ -98,6 +98,44 @@ int sn_sss_backward(const sn_sss_plan* plan_host, const float* packed, const flo
                     float* grad_bias, float* grad_x, int64_t ldgx, int64_t B, sn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * SSS layer, tensor-core path (tcgen05 / TMEM / TMA, 3xTF32 = fp32-accurate) -- same contract as sn_sss_forward /
+ * sn_sss_backward (layers/sss_layer.py:99-131 and its autograd backward), for layers whose stages have state
+ * dimensions <= 16, <= 16 outputs and <= 160 inputs each, with input_dim and output_dim multiples of 4.
+ * The stages are grouped into chunks of consecutive stages (<= 32 outputs, <= 160 inputs, <= 16 stages); the chunk
+ * matrices are rebuilt from the flat parameters by sn_sss_tc_build (call once per parameter update).
+ * `stages` is the same device table as sn_sss_plan.stages.  coef must be zero-initialised once by the caller
+ * (padding entries are never written).
+ * ------------------------------------------------------------------------------------------ */
+#define SN_SSS_TC_DS 16
+#define SN_SSS_TC_PO 32
+#define SN_SSS_TC_KB_MAX 5
+#define SN_SSS_TC_LMAX 16
+typedef struct sn_sss_tc_chunk {
+    int32_t k_begin, k_end; /* natural stages [k_begin, k_end) */
+    int32_t col0, ncols;    /* input columns  */
+    int32_t row0, nrows;    /* output columns */
+    int32_t nkb;            /* ceil(ncols / 32) */
+    int32_t reserved;
+} sn_sss_tc_chunk;
+typedef struct sn_sss_tc_plan {
+    int32_t nb_states, input_dim, output_dim, nchunks;
+    int32_t rows_aligned; /* 1: every chunk's row0 is a multiple of 4 (16-byte y / grad_y accesses) */
+    int32_t reserved[3];
+    const sn_sss_stage* stages;    /* device, [2][nb_states] */
+    const sn_sss_tc_chunk* chunks; /* device, [nchunks] */
+} sn_sss_tc_plan;
+size_t sn_sss_tc_coef_floats(const sn_sss_tc_plan* plan_host);
+size_t sn_sss_tc_rbuf_floats(const sn_sss_tc_plan* plan_host, int64_t B);   /* forward scratch */
+size_t sn_sss_tc_states_floats(const sn_sss_tc_plan* plan_host, int64_t B); /* chunk-boundary states kept for backward */
+size_t sn_sss_tc_backward_workspace_floats(const sn_sss_tc_plan* plan_host, int64_t B);
+int sn_sss_tc_build(const sn_sss_tc_plan* plan_host, const float* params, float* coef, sn_stream_t stream);
+int sn_sss_tc_forward(const sn_sss_tc_plan* plan_host, const float* coef, const float* x, int64_t ldx, float* y, int64_t ldy,
+                      const float* bias, float* rbuf, float* states, int64_t B, sn_stream_t stream);
+int sn_sss_tc_backward(const sn_sss_tc_plan* plan_host, const float* params, const float* coef, const float* x, int64_t ldx,
+                       const float* grad_y, int64_t ldgy, const float* states, float* workspace, float* grad_params,
+                       float* grad_bias, int64_t B, sn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Low-rank layer, fp32 path -- replaces LRLayer.forward (layers/lr_layer.py:38-46) and its backward.
  *   left (out_dim x rank), right (rank x in_dim), hidden (B x rank, written by forward, read by backward),
  *   grad_hidden_ws: scratch (B x rank).  grad_left / grad_right / grad_bias are accumulated; grad_x may be NULL.

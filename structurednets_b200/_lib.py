@@ -27,6 +27,15 @@ class SnSssPlan(Structure):
                [("stages", c_void_p), ("chunks", c_void_p)]
 
 
+class SnSssTcChunk(Structure):
+    _fields_ = [(n, c_int32) for n in ("k_begin", "k_end", "col0", "ncols", "row0", "nrows", "nkb", "reserved")]
+
+
+class SnSssTcPlan(Structure):
+    _fields_ = [(n, c_int32) for n in ("nb_states", "input_dim", "output_dim", "nchunks", "rows_aligned")] + \
+               [("reserved", c_int32 * 3), ("stages", c_void_p), ("chunks", c_void_p)]
+
+
 class SnPsmFactor(Structure):
     _fields_ = [("rows", c_int32), ("cols", c_int32), ("nnz", c_int32), ("reserved", c_int32)] + \
                [(n, c_void_p) for n in ("rowptr", "colidx", "perm", "cscptr", "rowidx", "permc", "vals", "grad_vals")]
@@ -55,6 +64,19 @@ def _declare(lib):
     lib.sn_sss_backward.argtypes = [P, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_int64, c_int64, c_void_p]
     i64, i32, vp = c_int64, c_int, c_void_p
+    PT = POINTER(SnSssTcPlan)
+    for name in ("sn_sss_tc_coef_floats",):
+        getattr(lib, name).restype = c_size_t
+        getattr(lib, name).argtypes = [PT]
+    for name in ("sn_sss_tc_rbuf_floats", "sn_sss_tc_states_floats", "sn_sss_tc_backward_workspace_floats"):
+        getattr(lib, name).restype = c_size_t
+        getattr(lib, name).argtypes = [PT, i64]
+    lib.sn_sss_tc_build.restype = c_int
+    lib.sn_sss_tc_build.argtypes = [PT, vp, vp, vp]
+    lib.sn_sss_tc_forward.restype = c_int
+    lib.sn_sss_tc_forward.argtypes = [PT, vp, vp, i64, vp, i64, vp, vp, vp, i64, vp]
+    lib.sn_sss_tc_backward.restype = c_int
+    lib.sn_sss_tc_backward.argtypes = [PT, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, i64, vp]
     lib.sn_lr_forward_f32.restype = c_int
     lib.sn_lr_forward_f32.argtypes = [vp, i64, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp]
     lib.sn_lr_backward_f32.restype = c_int

@@ -1,0 +1,158 @@
+// tcgen05 / TMEM / TMA / mbarrier primitives shared by the tensor-core kernels (sm_100a inline PTX).
+//   SASS: tcgen05.mma -> UTC*MMA, tcgen05.ld -> LDTM, cp.async.bulk.tensor -> UTMALDG, mbarrier -> SYNCS.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace snb {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ----
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (tensor-core operand reads, TMA stores)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMA ----
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// ---- tcgen05 ----
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {   // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {   // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// Shared-memory matrix descriptors (version 1 = sm_100, layout type 2 = SWIZZLE_128B), rows of 128 bytes.
+// K-major: a row holds 128 bytes of K for one M/N index; 8-row groups are 1024 bytes apart (SBO).
+__device__ __forceinline__ uint64_t desc_kmajor_sw128(const void* tile) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(tile) & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// MN-major, 32-bit elements: a row holds 128 bytes (32 consecutive M/N indices) for one K index.  The only layout the
+// tensor core accepts for MN-major tf32 operands is SWIZZLE_128B_BASE32B (layout type 1: 32-byte chunks XOR-ed with the row
+// index mod 4; TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): groups of 4 K-rows are 512 bytes apart (SBO),
+// consecutive 128-byte M/N blocks are `mn_block_bytes` apart (LBO).
+__device__ __forceinline__ uint64_t desc_mnmajor_sw128_32b(const void* tile, uint32_t mn_block_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(tile) & 0x3FFFF) >> 4);
+    d |= (uint64_t)((mn_block_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
+// Instruction descriptor, kind::tf32: D fp32 (bits 4-5 = 1), A/B tf32 (format 2 at bits 7-9 / 10-12),
+// bit 15 / 16 = A / B MN-major, N >> 3 at [17,23), M >> 4 at [24,29).
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 16 consecutive columns (lane = TMEM lane within the warp's quarter); no wait
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// fp32 -> (hi, lo) with hi = round-to-nearest tf32 and lo = x - hi (exact in fp32); the tensor core reads the top 19 bits
+__device__ __forceinline__ float tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time dependency on libcuda) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// fp32 tensor [d2][d1][d0] (d0 contiguous; strides in elements), box = [1][b1][32 floats = 128 B], SWIZZLE_128B (16-byte chunks)
+// or SWIZZLE_128B_ATOM_32B (32-byte chunks, for MN-major tf32 operands), OOB -> 0.
+// rank 2 when d2 == 0.
+inline int make_map_f32(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t ld1, uint32_t b1, uint64_t d2 = 0,
+                        uint64_t ld2 = 0, bool atom32 = false) {
+    EncodeTiledFn fn = encode_fn();
+    SN_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    SN_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld1 * 4) % 16 == 0 && (ld2 * 4) % 16 == 0,
+                 "TMA needs a 16-byte aligned base and row pitches that are multiples of 16 bytes (ld = %llu floats)", (unsigned long long)ld1);
+    const int rank = d2 ? 3 : 2;
+    cuuint64_t dims[3] = {d0, d1, d2 ? d2 : 1};
+    cuuint64_t strides[2] = {ld1 * 4, ld2 * 4};
+    cuuint32_t box[3] = {32, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SN_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+    return 0;
+}
+
+}  // namespace umma
+}  // namespace snb

@@ -8,6 +8,7 @@ constructor, same ``ParameterList`` names ``A..G`` and shapes (so the same ``sta
 (``sn_sss_pack / sn_sss_forward / sn_sss_backward``, include/snb200.h); there is no CPU path.
 """
 import ctypes
+import os
 import pickle
 
 import numpy as np
@@ -119,6 +120,55 @@ class _SSSFunction(torch.autograd.Function):
         return None, None, None
 
 
+class _SSSTCFunction(torch.autograd.Function):
+    """Tensor-core path (csrc/sss_tc.cu): sn_sss_tc_build + sn_sss_tc_forward, sn_sss_tc_backward."""
+
+    @staticmethod
+    def forward(ctx, U, anchor, layer):
+        B = U.shape[0]
+        L = _lib.lib()
+        tc = layer._tc_plan(U.device)
+        ps = ctypes.byref(tc["struct"])
+        flat = layer.__dict__["_flat"]
+        coef = tc["coef"]
+        _lib.check(L.sn_sss_tc_build(ps, _lib.ptr(flat), _lib.ptr(coef), _lib.stream_ptr()), "sn_sss_tc_build")
+        y = torch.empty((B, layer.output_dim), dtype=torch.float32, device=U.device)
+        rbuf = torch.empty(max(int(L.sn_sss_tc_rbuf_floats(ps, B)), 1), dtype=torch.float32, device=U.device)
+        states = torch.empty(max(int(L.sn_sss_tc_states_floats(ps, B)), 1), dtype=torch.float32, device=U.device)
+        bias = layer.bias if layer.use_bias else None
+        rc = L.sn_sss_tc_forward(ps, _lib.ptr(coef), _lib.ptr(U), U.stride(0), _lib.ptr(y), y.stride(0), _lib.ptr(bias),
+                                 _lib.ptr(rbuf), _lib.ptr(states), B, _lib.stream_ptr())
+        _lib.check(rc, "sn_sss_tc_forward")
+        ctx.layer = layer
+        ctx.tc = tc
+        if anchor is not None:
+            ctx.save_for_backward(U, states)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        layer, tc = ctx.layer, ctx.tc
+        U, states = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("SSSLayer: gradient w.r.t. the input features is not implemented "
+                               "(the reference training loop never requests it, training_helpers.py:34)")
+        grad_y = grad_y.contiguous()
+        if grad_y.dtype != torch.float32:
+            grad_y = grad_y.float()
+        L = _lib.lib()
+        ps = ctypes.byref(tc["struct"])
+        B = U.shape[0]
+        g = layer._prepare_grad_accumulation()
+        gbias = g[:layer.output_dim] if (layer.use_bias and layer.bias.requires_grad) else None
+        ws = torch.empty(max(int(L.sn_sss_tc_backward_workspace_floats(ps, B)), 1), dtype=torch.float32, device=U.device)
+        # tc["coef"] still holds the chunk matrices of the forward (rebuilt at every forward from the flat parameters)
+        rc = L.sn_sss_tc_backward(ps, _lib.ptr(layer.__dict__["_flat"]), _lib.ptr(tc["coef"]), _lib.ptr(U), U.stride(0),
+                                  _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(states), _lib.ptr(ws), _lib.ptr(g), _lib.ptr(gbias),
+                                  B, _lib.stream_ptr())
+        _lib.check(rc, "sn_sss_tc_backward")
+        return None, None, None
+
+
 class SSSLayer(FlatParamsMixin, StructuredLayer):
     def __init__(self, input_dim: int, output_dim: int, nb_params_share: float, use_bias=True, initial_weight_matrix=None,
                  initial_bias=None, nb_states=None, initial_system_approx=None, use_gpu=False):
@@ -185,6 +235,8 @@ class SSSLayer(FlatParamsMixin, StructuredLayer):
         self.__dict__["_dev_packed"] = None
         self.__dict__["_dev_packed_version"] = None
         self.__dict__["_dev_bwd_ws"] = None
+        self.__dict__["_dev_tc_plan"] = None
+        self.__dict__["_tc_eligible"] = None
 
     def _param_offsets(self):
         """{(list name, k): offset in the flat buffer}; flat order = named_parameters() order."""
@@ -277,6 +329,66 @@ class SSSLayer(FlatParamsMixin, StructuredLayer):
         self.__dict__["_dev_packed"] = None
         return plan
 
+    # ---- tensor-core plan (csrc/sss_tc.cu) -------------------------------------------------------
+    TC_DS, TC_PO, TC_KB, TC_KB_MAX, TC_LMAX, TC_SOUT_MAX = 16, 32, 32, 5, 16, 16
+
+    def build_tc_host_plan(self):
+        """Chunk table of include/snb200.h (sn_sss_tc_chunk) or None when the layer does not fit the tensor-core path."""
+        n = self.nb_states
+        if self.input_dim % 4 != 0 or self.output_dim % 4 != 0:
+            return None
+        for k in range(n):
+            dims = (self.A[k].shape[0], self.A[k].shape[1], self.E[k].shape[0], self.E[k].shape[1])
+            if max(dims) > self.TC_DS or self.dims_out[k] > self.TC_SOUT_MAX or self.dims_in[k] > self.TC_KB * self.TC_KB_MAX:
+                return None
+        in_off = np.concatenate([[0], np.cumsum(self.dims_in)]).astype(np.int64)
+        out_off = np.concatenate([[0], np.cumsum(self.dims_out)]).astype(np.int64)
+        chunks = []
+        k = 0
+        while k < n:
+            k0, nin, nout = k, 0, 0
+            while (k < n and k - k0 < self.TC_LMAX and nin + int(self.dims_in[k]) <= self.TC_KB * self.TC_KB_MAX
+                   and nout + int(self.dims_out[k]) <= self.TC_PO):
+                nin += int(self.dims_in[k])
+                nout += int(self.dims_out[k])
+                k += 1
+            chunks.append([k0, k, int(in_off[k0]), nin, int(out_off[k0]), nout, (nin + self.TC_KB - 1) // self.TC_KB, 0])
+        chunks = np.asarray(chunks, dtype=np.int32)
+        rows_aligned = int(np.all(chunks[:, 4] % 4 == 0))
+        return dict(chunks=chunks, rows_aligned=rows_aligned)
+
+    def _tc_plan(self, device):
+        tc = self.__dict__.get("_dev_tc_plan")
+        if tc is not None and tc["device"] == device:
+            return tc
+        plan = self._device_plan(device)
+        host = self.build_tc_host_plan()
+        assert host is not None, "SSSLayer: this layer does not fit the tensor-core path"
+        ch_dev = torch.from_numpy(host["chunks"].reshape(-1)).to(device)
+        struct = _lib.SnSssTcPlan()
+        struct.nb_states, struct.input_dim, struct.output_dim = self.nb_states, self.input_dim, self.output_dim
+        struct.nchunks = host["chunks"].shape[0]
+        struct.rows_aligned = host["rows_aligned"]
+        struct.stages = plan["stages"].data_ptr()
+        struct.chunks = ch_dev.data_ptr()
+        ncoef = int(_lib.lib().sn_sss_tc_coef_floats(ctypes.byref(struct)))
+        coef = torch.zeros(ncoef, dtype=torch.float32, device=device)   # padding entries stay zero for the life of the plan
+        tc = dict(device=device, struct=struct, chunks=ch_dev, stages=plan["stages"], coef=coef, host=host)
+        self.__dict__["_dev_tc_plan"] = tc
+        return tc
+
+    def _use_tc_path(self) -> bool:
+        mode = os.environ.get("SNB200_SSS_PATH", self.__dict__.get("kernel_path", "auto"))
+        if mode == "simt":
+            return False
+        ok = self.__dict__.get("_tc_eligible")
+        if ok is None:
+            ok = self.build_tc_host_plan() is not None
+            self.__dict__["_tc_eligible"] = ok
+        if mode == "tc" and not ok:
+            raise RuntimeError("SSSLayer: SNB200_SSS_PATH=tc but the layer does not fit the tensor-core path")
+        return ok
+
     def _backward_workspace(self, plan):
         ws = self.__dict__.get("_dev_bwd_ws")
         if ws is None or ws.device != plan["device"]:
@@ -318,7 +430,8 @@ class SSSLayer(FlatParamsMixin, StructuredLayer):
                 anchor = torch.zeros(1, device=U.device, requires_grad=True)
                 self.__dict__["_dev_anchor"] = anchor
             any_grad = torch.is_grad_enabled() and any(p.requires_grad for p in (self.A[0], self.D[0]))
-            return _SSSFunction.apply(U, anchor if any_grad else None, self)
+            fn = _SSSTCFunction if self._use_tc_path() else _SSSFunction
+            return fn.apply(U, anchor if any_grad else None, self)
         else:
             # the budget admits not even a block-diagonal D: reference returns zeros (sss_layer.py:130-131)
             return torch.zeros((U.shape[0], self.output_dim), device=U.device)

@@ -1,0 +1,167 @@
+"""Tensor-core SSS path (csrc/sss_tc.cu) on a B200: every kernel's output through the C ABI against the torch emulator
+of the chunked formulation, then the layer against the oracle at 1e-5 relative (north_star's fp32 tolerance)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import layers_cpu as O
+from structurednets_b200 import _lib
+from structurednets_b200.layers.sss_layer import SSSLayer
+from structurednets_b200.synth import random_mixed_system
+from tests import sss_tc_emulator as E
+from tests.test_sss_tc_plan import TC_CASES, make_tc
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def lists32(layer):
+    return [[p.detach().cpu().clone().requires_grad_(True) for p in getattr(layer, n)] for n in "ABCDEFG"]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_each_kernel_against_the_emulator(case, built_lib):
+    layer, X = make_tc(case)
+    dev = torch.device("cuda")
+    B = X.shape[0]
+    rng = np.random.default_rng(7)
+    gy = rng.uniform(-1, 1, size=(B, case["o"])).astype(np.float32)
+    # ---- emulator (fp64 so it is the more accurate side) ----
+    l64 = [[p.detach().double().clone().requires_grad_(True) for p in getattr(layer, n)] for n in "ABCDEFG"]
+    chunks = E.make_chunks(layer.dims_in, layer.dims_out)
+    mats = [tuple(m.detach().clone().requires_grad_(True) for m in E.chunk_matrices(*l64, layer.dims_in, layer.dims_out, k0, k1))
+            for (k0, k1) in chunks]
+    U = torch.tensor(X).double()
+    b64 = layer.bias.detach().double()
+    y_e, info = E.forward_chunked(U, *l64, b64, layer.dims_in, layer.dims_out, return_all=True, mats=mats)
+    (y_e * torch.tensor(gy).double()).sum().backward()
+
+    layer = layer.to(dev)
+    L = _lib.lib()
+    tc = layer._tc_plan(dev)
+    ps = ctypes.byref(tc["struct"])
+    nc = len(chunks)
+    flat = layer.flat_parameters()
+    # 1. build
+    _lib.check(L.sn_sss_tc_build(ps, _lib.ptr(flat), _lib.ptr(tc["coef"]), _lib.stream_ptr()), "build")
+    torch.cuda.synchronize()
+    coef = tc["coef"].cpu().numpy()
+    W = coef[:nc * 128 * 160].reshape(nc, 128, 160)
+    SC = coef[nc * 128 * 160:].reshape(nc, 1536)
+    for j in range(nc):
+        Wj = W[j, :64].astype(np.float64) + W[j, 64:].astype(np.float64)
+        assert rel_err(Wj, mats[j][0].detach().numpy()) < 1e-6, f"W chunk {j}"
+        assert np.all((W[j].view(np.uint32) & 0x1FFF) == 0), "W hi/lo parts must be tf32-representable"
+        ref_sc = np.concatenate([mats[j][1].detach().numpy().reshape(-1), mats[j][2].detach().numpy().reshape(-1),
+                                 mats[j][3].detach().numpy().reshape(-1), mats[j][4].detach().numpy().reshape(-1)])
+        assert rel_err(SC[j], ref_sc) < 1e-6, f"SC chunk {j}"
+    # 2./3. forward
+    Xd = torch.tensor(X, device=dev)
+    y = torch.empty((B, case["o"]), device=dev)
+    rbuf = torch.zeros(int(L.sn_sss_tc_rbuf_floats(ps, B)), device=dev)
+    states = torch.zeros(int(L.sn_sss_tc_states_floats(ps, B)), device=dev)
+    _lib.check(L.sn_sss_tc_forward(ps, _lib.ptr(tc["coef"]), _lib.ptr(Xd), Xd.stride(0), _lib.ptr(y), y.stride(0), _lib.ptr(layer.bias),
+                                   _lib.ptr(rbuf), _lib.ptr(states), B, _lib.stream_ptr()), "forward")
+    torch.cuda.synchronize()
+    r = rbuf.cpu().numpy().reshape(nc, B, 64)
+    st = states.cpu().numpy().reshape(nc, B, 32)
+    for j in range(nc):
+        assert rel_err(r[j], info["loc"][j].detach().numpy()) < RTOL, f"local GEMM chunk {j}"
+    for j in range(nc):
+        assert np.max(np.abs(st[j, :, :16] - info["s"][j].detach().numpy())) < 1e-5 * max(1.0, float(info["s"][j].abs().max())), f"s chunk {j}"
+        assert np.max(np.abs(st[j, :, 16:] - info["e"][j + 1].detach().numpy())) < 1e-5 * max(1.0, float(info["e"][j + 1].abs().max())), f"e chunk {j}"
+    assert rel_err(y.cpu().numpy(), y_e.detach().numpy()) < RTOL
+    # 4./5./6. backward
+    gyd = torch.tensor(gy, device=dev)
+    ws = torch.zeros(int(L.sn_sss_tc_backward_workspace_floats(ps, B)), device=dev)
+    g = torch.zeros_like(flat)
+    gb = torch.zeros(case["o"], device=dev)
+    _lib.check(L.sn_sss_tc_backward(ps, _lib.ptr(flat), _lib.ptr(tc["coef"]), _lib.ptr(Xd), Xd.stride(0), _lib.ptr(gyd), gyd.stride(0),
+                                    _lib.ptr(states), _lib.ptr(ws), _lib.ptr(g), _lib.ptr(gb), B, _lib.stream_ptr()), "backward")
+    torch.cuda.synchronize()
+    wsn = ws.cpu().numpy()
+    dM = wsn[nc * B * 32: nc * B * 32 + nc * 64 * 192].reshape(nc, 64, 192)
+    host = tc["host"]["chunks"]
+    for j in range(nc):
+        ncols, nkb = int(host[j, 3]), int(host[j, 6])
+        gr = lambda t: t.grad.numpy() if t.grad is not None else np.zeros(tuple(t.shape))
+        gW = gr(mats[j][0])
+        scale = max(np.max(np.abs(gW)), 1e-30)
+        nrows = int(host[j, 5])
+        valid = np.r_[0:nrows, 32:64]          # rows nrows..31 of dM hold the next chunk's grad_y columns: never read
+        assert np.max(np.abs(dM[j][valid, :ncols] - gW[valid, :ncols])) / scale < RTOL, f"dM (W part) chunk {j}"
+        c0 = nkb * 32
+        assert np.max(np.abs(dM[j][32:48, c0:c0 + 16] - gr(mats[j][1]))) / scale < RTOL, f"dPhi chunk {j}"
+        assert np.max(np.abs(dM[j][48:64, c0 + 16:c0 + 32] - gr(mats[j][2]))) / scale < RTOL, f"dPhi' chunk {j}"
+        assert np.max(np.abs(dM[j][:nrows, c0:c0 + 16] - gr(mats[j][3])[:nrows])) / scale < RTOL, f"dO chunk {j}"
+        assert np.max(np.abs(dM[j][:nrows, c0 + 16:c0 + 32] - gr(mats[j][4])[:nrows])) / scale < RTOL, f"dO' chunk {j}"
+    assert rel_err(gb.cpu().numpy(), gy.sum(axis=0)) < RTOL
+    # parameter gradients against the oracle
+    l32 = lists32(layer)
+    yo = O.sss_forward(torch.tensor(X), *l32, layer.bias.detach().cpu(), layer.dims_in, layer.dims_out)
+    (yo * torch.tensor(gy)).sum().backward()
+    offs = layer._param_offsets()
+    gn = g.cpu().numpy()
+    for li, name in enumerate("ABCDEFG"):
+        got = np.concatenate([gn[offs[(name, k)]:offs[(name, k)] + p.numel()] for k, p in enumerate(l32[li])])
+        ref = np.concatenate([(p.grad.numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32)).reshape(-1) for p in l32[li]])
+        if ref.size:
+            assert rel_err(got, ref) < RTOL, f"grad {name}"
+
+
+@pytest.mark.parametrize("B", [256, 77, 1000])
+def test_alexnet_last_layer_shape_tc_vs_oracle_and_simt(B, built_lib, monkeypatch):
+    """BASELINE config C1 (4096 -> 1000, 500 stages, statespace 16) through the module: tensor-core path vs oracle and vs the SIMT path."""
+    sysm = random_mixed_system(4096, 1000, 500, 16, seed=1001)
+    layer = SSSLayer(4096, 1000, 0.105, nb_states=500, initial_system_approx=sysm)
+    assert layer._use_tc_path()
+    rng = np.random.default_rng(1001)
+    X = rng.uniform(-1, 1, size=(B, 4096)).astype(np.float32)
+    gy = rng.uniform(-1, 1, size=(B, 1000)).astype(np.float32) / B
+    dev = torch.device("cuda")
+    l32 = lists32(layer)
+    b = layer.bias.detach().clone().requires_grad_(True)
+    yo = O.sss_forward(torch.tensor(X), *l32, b, layer.dims_in, layer.dims_out)
+    (yo * torch.tensor(gy)).sum().backward()
+    layer = layer.to(dev)
+    Xd, gyd = torch.tensor(X, device=dev), torch.tensor(gy, device=dev)
+    res = {}
+    for mode in ("tc", "simt"):
+        monkeypatch.setenv("SNB200_SSS_PATH", mode)
+        for p in layer.parameters():
+            p.grad = None
+        _lib.reset_launch_count()
+        y = layer(Xd)
+        (y * gyd).sum().backward()
+        torch.cuda.synchronize()
+        res[mode] = (y.detach().cpu().numpy(), layer.flat_grad().detach().cpu().numpy().copy(), _lib.launch_count())
+        assert rel_err(res[mode][0], yo.detach().numpy()) < RTOL, mode
+        for li, name in enumerate("ABCDEFG"):
+            got = np.concatenate([p.grad.detach().cpu().numpy().reshape(-1) for p in getattr(layer, name)])
+            ref = np.concatenate([(p.grad.numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32)).reshape(-1) for p in l32[li]])
+            assert rel_err(got, ref) < RTOL, f"{mode}: grad {name}"
+        assert rel_err(layer.bias.grad.cpu().numpy(), b.grad.numpy()) < RTOL
+    assert res["tc"][2] == 6 and res["simt"][2] >= 3     # kernels launched: build, gemm, scan | scan, gemm, build-bwd
+    assert rel_err(res["tc"][1], res["simt"][1]) < RTOL
+
+
+def test_tc_affine_map_at_full_batch(built_lib, monkeypatch):
+    """Size-independent property at B = 8192: SSS(a x1 + b x2) - bias = a (SSS(x1) - bias) + b (SSS(x2) - bias)."""
+    monkeypatch.setenv("SNB200_SSS_PATH", "tc")
+    sysm = random_mixed_system(4096, 1000, 500, 16, seed=5)
+    layer = SSSLayer(4096, 1000, 0.105, nb_states=500, initial_system_approx=sysm).to("cuda")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x1 = torch.rand((8192, 4096), device="cuda", generator=g) * 2 - 1
+    x2 = torch.rand((8192, 4096), device="cuda", generator=g) * 2 - 1
+    with torch.no_grad():
+        y1, y2, y3 = layer(x1), layer(x2), layer(0.5 * x1 - 2.0 * x2)
+        lin = 0.5 * (y1 - layer.bias) - 2.0 * (y2 - layer.bias) + layer.bias
+    assert float((y3 - lin).abs().max() / lin.abs().max()) < 3e-5
