@@ -16,6 +16,7 @@
 //           5. sss_tc_grad_gemm_kernel dM_j = [gy_j | lambda_{j+1} | mu_j]^T [u_j | s_j | e_{j+1}]  (K = samples, MN-major operands
 //                                       straight from the natural [sample][feature] layouts), split over sample ranges
 //           6. sss_tc_build_bwd_kernel chain rule through the chunk-matrix construction: dM -> dA .. dG
+#include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -42,19 +43,43 @@ __device__ __forceinline__ const sn_sss_stage& stage_of(const sn_sss_stage* stag
     return stages[dir * n + (dir == 0 ? k : n - 1 - k)];
 }
 
+// The parameters of one stage, staged in shared memory (compact row-major, as in the flat parameter buffer) with 4-byte
+// cp.async copies: every thread of the build kernels reads the same entries, so the global loads are issued once, coalesced and
+// one stage ahead, and the recursions read broadcast LDS.
+constexpr int STG_IN_MAX = KBW * KB_MAX;   // 160
+struct StageSm {
+    float ss[DS * DS];              // d_out x d_in
+    float ys[SOUT_MAX * DS];        // out_dim x d_in
+    float su[DS * STG_IN_MAX];      // d_out x in_dim
+    float yu[SOUT_MAX * STG_IN_MAX];   // out_dim x in_dim
+};
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void stage_load_async(StageSm& sm, const sn_sss_stage& st, const float* __restrict__ params, int tid, int nthreads) {
+    const int n_ss = st.d_out * st.d_in, n_ys = st.out_dim * st.d_in, n_su = st.d_out * st.in_dim;
+    const int n_yu = st.off_yu >= 0 ? st.out_dim * st.in_dim : 0;
+    for (int i = tid; i < n_ss; i += nthreads) cp_async4(sm.ss + i, params + st.off_ss + i);
+    for (int i = tid; i < n_ys; i += nthreads) cp_async4(sm.ys + i, params + st.off_ys + i);
+    for (int i = tid; i < n_su; i += nthreads) cp_async4(sm.su + i, params + st.off_su + i);
+    for (int i = tid; i < n_yu; i += nthreads) cp_async4(sm.yu + i, params + st.off_yu + i);
+}
+
 // One stage applied to one column of the chunk's "identity input": v (state entering) -> yv (the stage's outputs), v (state leaving)
-__device__ __forceinline__ void stage_apply(const sn_sss_stage& st, const float* __restrict__ params, float (&v)[DS], float (&yv)[SOUT_MAX], bool mine,
-                                            int local) {
+__device__ __forceinline__ void stage_apply(const sn_sss_stage& st, const StageSm& sm, float (&v)[DS], float (&yv)[SOUT_MAX], bool mine, int local) {
     const int d_in = st.d_in, d_out = st.d_out;
 #pragma unroll
     for (int r = 0; r < SOUT_MAX; ++r) {
         float acc = 0.f;
         if (r < st.out_dim) {
-            const float* ys = params + st.off_ys + r * d_in;
+            const float* ys = sm.ys + r * d_in;
 #pragma unroll
             for (int a = 0; a < DS; ++a)
-                if (a < d_in) acc = fmaf(__ldg(ys + a), v[a], acc);
-            if (mine && st.off_yu >= 0) acc += __ldg(params + st.off_yu + r * st.in_dim + local);
+                if (a < d_in) acc = fmaf(ys[a], v[a], acc);
+            if (mine && st.off_yu >= 0) acc += sm.yu[r * st.in_dim + local];
         }
         yv[r] = acc;
     }
@@ -63,11 +88,11 @@ __device__ __forceinline__ void stage_apply(const sn_sss_stage& st, const float*
     for (int b = 0; b < DS; ++b) {
         float acc = 0.f;
         if (b < d_out) {
-            const float* ss = params + st.off_ss + b * d_in;
+            const float* ss = sm.ss + b * d_in;
 #pragma unroll
             for (int a = 0; a < DS; ++a)
-                if (a < d_in) acc = fmaf(__ldg(ss + a), v[a], acc);
-            if (mine) acc += __ldg(params + st.off_su + b * st.in_dim + local);
+                if (a < d_in) acc = fmaf(ss[a], v[a], acc);
+            if (mine) acc += sm.su[b * st.in_dim + local];
         }
         nv[b] = acc;
     }
@@ -87,29 +112,39 @@ __device__ __forceinline__ void store_hi_lo(float* W, int row, int t, float val)
 __global__ void __launch_bounds__(BUILD_THREADS)
 sss_tc_build_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss_tc_chunk* __restrict__ chunks, const float* __restrict__ params,
                     float* __restrict__ Wall, float* __restrict__ SCall) {
+    __shared__ StageSm sm[2];
+    __shared__ sn_sss_stage sdesc[LMAX];
     const sn_sss_tc_chunk c = chunks[blockIdx.x];
     const int dir = blockIdx.y, t = threadIdx.x;
     const bool is_in = t < c.ncols;
     const int sidx = t - c.ncols;
-    if (!is_in && sidx >= DS) return;
+    const bool active = is_in || sidx < DS;
     float* W = Wall + (size_t)blockIdx.x * WROWS * WCOLS;
     float* SC = SCall + (size_t)blockIdx.x * SCF;
     float* Phi = SC + dir * DS * DS;
     float* Omat = SC + 2 * DS * DS + dir * PO * DS;
     const int nst = c.k_end - c.k_begin;
     const int col = c.col0 + t;
+    if (t < nst) sdesc[t] = stage_of(stages, n, dir, dir == 0 ? c.k_begin + t : c.k_end - 1 - t);
+    __syncthreads();
+    stage_load_async(sm[0], sdesc[0], params, t, BUILD_THREADS);
+    cp_async_commit();
     float v[DS], yv[SOUT_MAX];
-    {
-        const sn_sss_stage& st0 = stage_of(stages, n, dir, dir == 0 ? c.k_begin : c.k_end - 1);
 #pragma unroll
-        for (int a = 0; a < DS; ++a) v[a] = (!is_in && a == sidx && sidx < st0.d_in) ? 1.f : 0.f;
-    }
+    for (int a = 0; a < DS; ++a) v[a] = (!is_in && a == sidx && sidx < sdesc[0].d_in) ? 1.f : 0.f;
     bool activated = false;
     for (int i = 0; i < nst; ++i) {
-        const sn_sss_stage st = stage_of(stages, n, dir, dir == 0 ? c.k_begin + i : c.k_end - 1 - i);
+        cp_async_wait_all();
+        __syncthreads();   // stage i is in sm[i & 1]; everybody is done with sm[(i + 1) & 1]
+        if (i + 1 < nst) {
+            stage_load_async(sm[(i + 1) & 1], sdesc[i + 1], params, t, BUILD_THREADS);
+            cp_async_commit();
+        }
+        if (!active) continue;
+        const sn_sss_stage& st = sdesc[i];
         const int local = col - st.in_off;
         const bool mine = is_in && local >= 0 && local < st.in_dim;
-        stage_apply(st, params, v, yv, mine, local);
+        stage_apply(st, sm[i & 1], v, yv, mine, local);
         const int rbase = st.out_off - c.row0;
         const bool wr = dir == 0 ? (activated || mine) : activated;
 #pragma unroll
@@ -124,6 +159,7 @@ sss_tc_build_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss
         }
         if (mine) activated = true;
     }
+    if (!active) return;
 #pragma unroll
     for (int b = 0; b < DS; ++b) {
         if (is_in) store_hi_lo(W, PO + dir * DS + b, t, v[b]);
@@ -145,7 +181,7 @@ __global__ void __launch_bounds__(G1_THREADS, 1)
 sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                          const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, long B, int ntiles, float* __restrict__ rbuf) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + G1_STAGES * G1_STAGE_BYTES);
     uint64_t* conv = full + G1_STAGES;
     uint64_t* empty = conv + G1_STAGES;
@@ -413,6 +449,311 @@ sss_tc_scan_fwd_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, 
 }
 
 // ------------------------------------------------------------------------------------------
+// 2+3 fused (large batches): one CTA walks whole 128-sample tiles chunk by chunk, so the chunk-level scans run in the
+//    epilogue while the tensor core works on the next chunk -- no [yloc | r | r'] round trip through HBM.
+//    warp 0: TMA producer | warp 1: MMA issuer | warps 2-5: hi/lo converters
+//    warps 6-9  : epilogue, thread = sample: TMEM -> registers, causal state recursion, y = yloc + O s + bias, saves s_j and r'_j
+//    warps 10-13: finalizer, thread = sample, one tile behind: anticausal recursion over the saved r'_j, y += O' e, saves e_{j+1}
+// ------------------------------------------------------------------------------------------
+constexpr int F_THREADS = 448;
+constexpr int F_MAX_CHUNKS = 512;
+constexpr int F_SC_HALF = DS * DS + PO * DS + PO;   // 800 floats: one direction's Phi and O, then the chunk's bias entries
+constexpr size_t F_SMEM = (size_t)G1_STAGES * G1_STAGE_BYTES + 256 + F_MAX_CHUNKS * 16 + 4 * F_SC_HALF * 4 + 1024;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);   // round to nearest tf32 (ties away), finite inputs
+    lo = x - hi;
+}
+__device__ __forceinline__ void split_tf32(const float4& v, float4& h, float4& l) {
+    split_tf32(v.x, h.x, l.x);
+    split_tf32(v.y, h.y, l.y);
+    split_tf32(v.z, h.z, l.z);
+    split_tf32(v.w, h.w, l.w);
+}
+
+// cooperative copy of one direction's {Phi (64 float4), O (128 float4)} by 128 threads: registers first (latency hidden behind
+// the barrier wait that follows), shared memory later
+struct ScRegs { float4 a, b; };
+// bias_c (may be NULL): the chunk's bias entries, staged behind the matrices by threads 64..71 (nrows: valid entries)
+__device__ __forceinline__ ScRegs sc_fetch(const float* __restrict__ SCj, int dir, int t, const float* __restrict__ bias_c = nullptr,
+                                           int nrows = 0, int aligned = 0) {
+    const float4* g = reinterpret_cast<const float4*>(SCj);
+    ScRegs r;
+    const int phi0 = dir * (DS * DS / 4), o0 = 2 * (DS * DS / 4) + dir * (PO * DS / 4);
+    r.a = __ldg(g + (t < 64 ? phi0 + t : o0 + (t - 64)));
+    r.b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < 64) {
+        r.b = __ldg(g + o0 + 64 + t);
+    } else if (t < 72 && bias_c != nullptr) {
+        const int c = 4 * (t - 64);
+        if (aligned && c + 4 <= nrows) {
+            r.b = __ldg(reinterpret_cast<const float4*>(bias_c + c));
+        } else {
+            if (c < nrows) r.b.x = __ldg(bias_c + c);
+            if (c + 1 < nrows) r.b.y = __ldg(bias_c + c + 1);
+            if (c + 2 < nrows) r.b.z = __ldg(bias_c + c + 2);
+            if (c + 3 < nrows) r.b.w = __ldg(bias_c + c + 3);
+        }
+    }
+    return r;
+}
+__device__ __forceinline__ void sc_store(float4* buf, const ScRegs& r, int t) {   // buf: [Phi 64][O 128][bias 8] float4
+    buf[t] = r.a;                      // t < 64: Phi[t] ; t >= 64: O[t - 64]  (same index: 64 + (t - 64))
+    if (t < 64) buf[128 + t] = r.b;    // O[64 + t]
+    else if (t < 72) buf[192 + (t - 64)] = r.b;
+}
+
+__global__ void __launch_bounds__(F_THREADS, 1)
+sss_tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                        const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, long B, int ntiles, const float* __restrict__ SCall,
+                        float* __restrict__ states, float* __restrict__ y, long ldy, const float* __restrict__ bias, int aligned) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + G1_STAGES * G1_STAGE_BYTES);
+    uint64_t* conv = full + G1_STAGES;
+    uint64_t* empty = conv + G1_STAGES;
+    uint64_t* acc_full = empty + G1_STAGES;
+    uint64_t* acc_empty = acc_full + 2;
+    uint64_t* tile_done = acc_empty + 2;
+    uint64_t* fin_done = tile_done + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fin_done + 2);
+    int4* ctab = reinterpret_cast<int4*>(smem + G1_STAGES * G1_STAGE_BYTES + 256);        // col0, nkb, row0, nrows
+    float4* scE = reinterpret_cast<float4*>(ctab + F_MAX_CHUNKS);                          // 2 x 192 float4
+    float4* scF = scE + 2 * (F_SC_HALF / 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = (int)((long)blockIdx.x * ntiles / gridDim.x);
+    const int t1 = (int)((long)(blockIdx.x + 1) * ntiles / gridDim.x);
+    if (t0 >= t1) return;
+
+    for (int i = threadIdx.x; i < nchunks; i += F_THREADS) ctab[i] = make_int4(chunks[i].col0, chunks[i].nkb, chunks[i].row0, chunks[i].nrows);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G1_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(conv + s, 128); mbar_init(empty + s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, 128); mbar_init(tile_done + b, 128); mbar_init(fin_done + b, 128); }
+        mbar_fence_init();
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_w);
+    }
+    if (warp == 1) tmem_alloc<256>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = t0; tile < t1; ++tile) {
+                for (int ch = 0; ch < nchunks; ++ch) {
+                    const int4 c = ctab[ch];
+                    for (int kb = 0; kb < c.y; ++kb, ++it) {
+                        const uint32_t s = it % G1_STAGES, round = it / G1_STAGES;
+                        if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
+                        uint8_t* st = smem + s * G1_STAGE_BYTES;
+                        mbar_expect_tx(full + s, 2 * G1_TILE_BYTES);
+                        tma_load_2d(st, &map_x, c.x + kb * KBW, tile * 128, full + s);
+                        tma_load_2d(st + 2 * G1_TILE_BYTES, &map_w, kb * KBW, ch * WROWS, full + s);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc1 = idesc_tf32(128, 128, false, false);
+            constexpr uint32_t idesc2 = idesc_tf32(128, 64, false, false);
+            uint32_t it = 0, ai = 0;
+            for (int tile = t0; tile < t1; ++tile) {
+                for (int ch = 0; ch < nchunks; ++ch, ++ai) {
+                    const int nkb = ctab[ch].y;
+                    const uint32_t b = ai & 1;
+                    if (ai >= 2) mbar_wait(acc_empty + b, ((ai >> 1) - 1) & 1);
+                    tc_fence_after();
+                    const uint32_t acc = tmem_base + b * 128;
+                    for (int kb = 0; kb < nkb; ++kb, ++it) {
+                        const uint32_t s = it % G1_STAGES, round = it / G1_STAGES;
+                        mbar_wait(conv + s, round & 1);
+                        tc_fence_after();
+                        uint8_t* st = smem + s * G1_STAGE_BYTES;
+                        const uint64_t dxh = desc_kmajor_sw128(st);
+                        const uint64_t dxl = desc_kmajor_sw128(st + G1_TILE_BYTES);
+                        const uint64_t dw = desc_kmajor_sw128(st + 2 * G1_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < KBW / 8; ++k) {
+                            mma_tf32(acc, dxh + 2 * k, dw + 2 * k, idesc1, (kb | k) ? 1u : 0u);
+                            mma_tf32(acc, dxl + 2 * k, dw + 2 * k, idesc2, 1u);
+                        }
+                        umma_commit(empty + s);
+                    }
+                    umma_commit(acc_full + b);
+                }
+            }
+        }
+    } else if (warp < 6) {
+        const int ct = threadIdx.x - 64;
+        uint32_t it = 0;
+        for (int tile = t0; tile < t1; ++tile) {
+            for (int ch = 0; ch < nchunks; ++ch) {
+                const int nkb = ctab[ch].y;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const uint32_t s = it % G1_STAGES, round = it / G1_STAGES;
+                    mbar_wait(full + s, round & 1);
+                    float4* xh = reinterpret_cast<float4*>(smem + s * G1_STAGE_BYTES);
+                    float4* xl = xh + G1_TILE_BYTES / 16;
+                    float4 v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = xh[ct + 128 * i];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float4 h, l;
+                        split_tf32(v[i], h, l);
+                        xh[ct + 128 * i] = h;
+                        xl[ct + 128 * i] = l;
+                    }
+                    fence_async_smem();
+                    mbar_arrive(conv + s);
+                }
+            }
+        }
+    } else if (warp < 10) {
+        // ---- epilogue + causal scan ----
+        const int q = warp & 3;
+        const int et = threadIdx.x - 192;
+        uint32_t ai = 0, tl = 0;
+        for (int tile = t0; tile < t1; ++tile, ++tl) {
+            const long row = (long)tile * 128 + q * 32 + lane;
+            const bool valid = row < B;
+            float s[DS];
+#pragma unroll
+            for (int a = 0; a < DS; ++a) s[a] = 0.f;
+            for (int ch = 0; ch < nchunks; ++ch, ++ai) {
+                const int4 c = ctab[ch];
+                const ScRegs scr = sc_fetch(SCall + (size_t)ch * SCF, 0, et, bias != nullptr ? bias + c.z : nullptr, c.w, aligned);
+                const uint32_t b = ai & 1;
+                mbar_wait(acc_full + b, (ai >> 1) & 1);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + b * 128 + ((uint32_t)(q * 32) << 16);
+                float out[64];
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    uint32_t m[16], x2[16];
+                    tmem_ld16_nowait(acc + c0, m);
+                    tmem_ld16_nowait(acc + 64 + c0, x2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) out[c0 + i] = __uint_as_float(m[i]) + __uint_as_float(x2[i]);
+                }
+                tc_fence_before();
+                mbar_arrive(acc_empty + b);
+                float4* sc = scE + (ai & 1) * (F_SC_HALF / 4);
+                sc_store(sc, scr, et);
+                named_bar_sync(1, 128);
+                if (valid) {
+                    float4* sdst = reinterpret_cast<float4*>(states + ((size_t)ch * B + row) * 32);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) sdst[i] = make_float4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) sdst[4 + i] = make_float4(out[48 + 4 * i], out[49 + 4 * i], out[50 + 4 * i], out[51 + 4 * i]);
+                    float* yrow = y + row * ldy + c.z;
+                    const float4* Om = sc + DS * DS / 4;
+#pragma unroll
+                    for (int g = 0; g < PO / 4; ++g) {
+                        if (4 * g < c.w) {
+                            const float4 b4 = sc[192 + g];   // zero when there is no bias
+                            float acc4[4] = {out[4 * g] + b4.x, out[4 * g + 1] + b4.y, out[4 * g + 2] + b4.z, out[4 * g + 3] + b4.w};
+                            matvec_acc<4>(Om + g * 4 * (DS / 4), s, acc4);
+                            if (aligned && 4 * g + 4 <= c.w) {
+                                *reinterpret_cast<float4*>(yrow + 4 * g) = make_float4(acc4[0], acc4[1], acc4[2], acc4[3]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    if (4 * g + i < c.w) yrow[4 * g + i] = acc4[i];
+                            }
+                        }
+                    }
+                }
+                float ns[DS];
+#pragma unroll
+                for (int a = 0; a < DS; ++a) ns[a] = out[32 + a];
+                matvec_acc<DS>(sc, s, ns);
+#pragma unroll
+                for (int a = 0; a < DS; ++a) s[a] = ns[a];
+            }
+            if (tl >= 2) mbar_wait(fin_done + (tl & 1), ((tl >> 1) - 1) & 1);
+            __threadfence_block();
+            mbar_arrive(tile_done + (tl & 1));
+        }
+    } else {
+        // ---- finalizer: anticausal scan, one tile behind the epilogue ----
+        const int ft = threadIdx.x - 320;
+        uint32_t fi = 0, tl = 0;
+        for (int tile = t0; tile < t1; ++tile, ++tl) {
+            mbar_wait(tile_done + (tl & 1), (tl >> 1) & 1);
+            const long row = (long)tile * 128 + ft;
+            const bool valid = row < B;
+            float e[DS];
+#pragma unroll
+            for (int a = 0; a < DS; ++a) e[a] = 0.f;
+            for (int j = nchunks - 1; j >= 0; --j, ++fi) {
+                const ScRegs scr = sc_fetch(SCall + (size_t)j * SCF, 1, ft);
+                const int4 c = ctab[j];
+                float4* sp = reinterpret_cast<float4*>(states + ((size_t)j * B + (valid ? row : 0)) * 32 + DS);
+                float ne[DS];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 r4 = valid ? __ldcg(sp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    ne[4 * i] = r4.x; ne[4 * i + 1] = r4.y; ne[4 * i + 2] = r4.z; ne[4 * i + 3] = r4.w;
+                }
+                float* yrow = y + (valid ? row : 0) * ldy + c.z;
+                float yv[PO];
+#pragma unroll
+                for (int g = 0; g < PO / 4; ++g) {
+                    if (valid && aligned && 4 * g + 4 <= c.w) {
+                        const float4 v = __ldcg(reinterpret_cast<const float4*>(yrow + 4 * g));
+                        yv[4 * g] = v.x; yv[4 * g + 1] = v.y; yv[4 * g + 2] = v.z; yv[4 * g + 3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) yv[4 * g + i] = (valid && 4 * g + i < c.w) ? __ldcg(yrow + 4 * g + i) : 0.f;
+                    }
+                }
+                float4* sc = scF + (fi & 1) * (F_SC_HALF / 4);
+                sc_store(sc, scr, ft);
+                named_bar_sync(2, 128);
+                if (valid) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) sp[i] = make_float4(e[4 * i], e[4 * i + 1], e[4 * i + 2], e[4 * i + 3]);
+                    const float4* Om = sc + DS * DS / 4;
+#pragma unroll
+                    for (int g = 0; g < PO / 4; ++g) {
+                        if (4 * g < c.w) {
+                            matvec_acc<4>(Om + g * 4 * (DS / 4), e, yv + 4 * g);
+                            if (aligned && 4 * g + 4 <= c.w) {
+                                *reinterpret_cast<float4*>(yrow + 4 * g) = make_float4(yv[4 * g], yv[4 * g + 1], yv[4 * g + 2], yv[4 * g + 3]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    if (4 * g + i < c.w) yrow[4 * g + i] = yv[4 * g + i];
+                            }
+                        }
+                    }
+                }
+                matvec_acc<DS>(sc, e, ne);
+#pragma unroll
+                for (int a = 0; a < DS; ++a) e[a] = ne[a];
+            }
+            mbar_arrive(fin_done + (tl & 1));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // 4. adjoint chunk scans.  L[j][row][0..15] = lambda_{j+1} (adjoint of the causal state leaving chunk j),
 //    L[j][row][16..31] = mu_j (adjoint of the anticausal state leaving chunk j).  grad_bias += column sums of gy.
 // ------------------------------------------------------------------------------------------
@@ -501,6 +842,258 @@ sss_tc_scan_bwd_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, 
 }
 
 // ------------------------------------------------------------------------------------------
+// 3'/4'. chunk scans, four threads per sample.  The scans are serial in the chunk index, so the only parallelism is across
+//    samples (65 536 threads would leave the SMs latency-bound); here thread q of a quad owns state components 4q..4q+3 (and
+//    output / grad_y columns 8q..8q+7), forms partial matrix-vector products over its own components and the quad combines
+//    them with a 2-step shuffle reduce-scatter.  Coefficients are double-buffered in shared memory with 16-byte cp.async.
+// ------------------------------------------------------------------------------------------
+constexpr int QS_THREADS = 128;   // 32 samples x 4 threads
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// out (N/4 values: indices q*N/4 ..) = sum over the quad of p[q*N/4 ..]
+template <int N>
+__device__ __forceinline__ void quad_reduce_scatter(const float (&p)[N], int q, float (&out)[N / 4]) {
+    float h[N / 2];
+    const bool hi2 = (q & 2) != 0;
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const float send = hi2 ? p[i] : p[N / 2 + i];
+        const float keep = hi2 ? p[N / 2 + i] : p[i];
+        h[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const bool hi1 = (q & 1) != 0;
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+        const float send = hi1 ? h[i] : h[N / 4 + i];
+        const float keep = hi1 ? h[N / 4 + i] : h[i];
+        out[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+}
+__device__ __forceinline__ float dot4(const float4& m, const float (&v)[4]) {
+    return fmaf(m.w, v[3], fmaf(m.z, v[2], fmaf(m.y, v[1], m.x * v[0])));
+}
+// p[0..15] += w * row (16 floats at M[0..3])
+__device__ __forceinline__ void axpy16(const float4* __restrict__ M, float w, float (&p)[DS]) {
+#pragma unroll
+    for (int a4 = 0; a4 < DS / 4; ++a4) {
+        const float4 m = M[a4];
+        p[4 * a4] = fmaf(m.x, w, p[4 * a4]);
+        p[4 * a4 + 1] = fmaf(m.y, w, p[4 * a4 + 1]);
+        p[4 * a4 + 2] = fmaf(m.z, w, p[4 * a4 + 2]);
+        p[4 * a4 + 3] = fmaf(m.w, w, p[4 * a4 + 3]);
+    }
+}
+__device__ __forceinline__ void sc_prefetch(float4* dst, const float* __restrict__ src, int nfloat4) {
+    for (int i = threadIdx.x; i < nfloat4; i += QS_THREADS) cp_async16(dst + i, reinterpret_cast<const float4*>(src) + i);
+}
+
+__global__ void __launch_bounds__(QS_THREADS)
+sss_tc_scan_fwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, const float* __restrict__ SCall, const float* __restrict__ rbuf,
+                         float* __restrict__ S, float* __restrict__ y, long ldy, const float* __restrict__ bias, long B, int aligned) {
+    __shared__ float4 sc[2][SCF / 4];
+    const int q = threadIdx.x & 3;
+    const long row = (long)blockIdx.x * (QS_THREADS / 4) + (threadIdx.x >> 2);
+    const bool valid = row < B;
+    const long rr = valid ? row : 0;
+    // ---- anticausal states, top chunk first: S[j][row][16..31] = e_{j+1} ----
+    float e4[4] = {0.f, 0.f, 0.f, 0.f};
+    sc_prefetch(sc[0], SCall + (size_t)(nchunks - 1) * SCF + DS * DS, DS * DS / 4);   // Phi'
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    float4 nr4 = valid ? __ldg(reinterpret_cast<const float4*>(rbuf + ((size_t)(nchunks - 1) * B + rr) * 64 + 48) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int jj = 0; jj < nchunks; ++jj) {
+        const int j = nchunks - 1 - jj;
+        const float4* Pp = sc[jj & 1];
+        const float4 r4 = nr4;
+        if (j > 0) {
+            sc_prefetch(sc[(jj + 1) & 1], SCall + (size_t)(j - 1) * SCF + DS * DS, DS * DS / 4);
+            cp_async_commit();
+            if (valid) nr4 = __ldg(reinterpret_cast<const float4*>(rbuf + ((size_t)(j - 1) * B + rr) * 64 + 48) + q);
+        }
+        const size_t base = (size_t)j * B + rr;
+        if (valid) *(reinterpret_cast<float4*>(S + base * 32 + DS) + q) = make_float4(e4[0], e4[1], e4[2], e4[3]);
+        float p[DS];
+#pragma unroll
+        for (int b = 0; b < DS; ++b) p[b] = dot4(Pp[b * 4 + q], e4);
+        float ne[4];
+        quad_reduce_scatter<DS>(p, q, ne);
+        e4[0] = r4.x + ne[0]; e4[1] = r4.y + ne[1]; e4[2] = r4.z + ne[2]; e4[3] = r4.w + ne[3];
+        cp_async_wait_all();
+        __syncthreads();
+    }
+    // ---- causal states bottom up + outputs; the global loads of chunk j + 1 are issued before chunk j is computed ----
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    sc_prefetch(sc[0], SCall, SCF / 4);
+    cp_async_commit();
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 n_yl0 = z4, n_yl1 = z4, n_r4 = z4, n_ev = z4;
+    if (valid) {
+        const float4* rp = reinterpret_cast<const float4*>(rbuf + (size_t)rr * 64);
+        n_yl0 = __ldg(rp + q); n_yl1 = __ldg(rp + 4 + q); n_r4 = __ldg(rp + 8 + q);
+        n_ev = *(reinterpret_cast<const float4*>(S + (size_t)rr * 32) + 4 + q);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    for (int j = 0; j < nchunks; ++j) {
+        const float4* Pm = sc[j & 1];                    // Phi
+        const float4* Om = Pm + 2 * DS * DS / 4;         // O
+        const float4* Opm = Om + PO * DS / 4;            // O'
+        const float4 yl0 = n_yl0, yl1 = n_yl1, r4 = n_r4, ev = n_ev;
+        if (j + 1 < nchunks) {
+            sc_prefetch(sc[(j + 1) & 1], SCall + (size_t)(j + 1) * SCF, SCF / 4);
+            cp_async_commit();
+            if (valid) {
+                const size_t nb = (size_t)(j + 1) * B + rr;
+                const float4* rp = reinterpret_cast<const float4*>(rbuf + nb * 64);
+                n_yl0 = __ldg(rp + q); n_yl1 = __ldg(rp + 4 + q); n_r4 = __ldg(rp + 8 + q);
+                n_ev = *(reinterpret_cast<const float4*>(S + nb * 32) + 4 + q);
+            }
+        }
+        const sn_sss_tc_chunk c = chunks[j];
+        if (valid) *(reinterpret_cast<float4*>(S + ((size_t)j * B + rr) * 32) + q) = make_float4(s4[0], s4[1], s4[2], s4[3]);
+        e4[0] = ev.x; e4[1] = ev.y; e4[2] = ev.z; e4[3] = ev.w;
+        // outputs in two halves of 16 columns: thread q ends up with columns 16 h + 4 q .. + 3
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float py[DS];
+#pragma unroll
+            for (int cc = 0; cc < DS; ++cc) py[cc] = dot4(Om[(16 * h + cc) * 4 + q], s4) + dot4(Opm[(16 * h + cc) * 4 + q], e4);
+            float y4[4];
+            quad_reduce_scatter<DS>(py, q, y4);
+            const float4 yl = h ? yl1 : yl0;
+            y4[0] += yl.x; y4[1] += yl.y; y4[2] += yl.z; y4[3] += yl.w;
+            const int c0 = 16 * h + 4 * q;
+            if (valid && c0 < c.nrows) {
+                float* yp = y + row * ldy + c.row0 + c0;
+                const float* bp = bias != nullptr ? bias + c.row0 + c0 : nullptr;
+                if (aligned && c0 + 4 <= c.nrows) {
+                    float4 b4 = z4;
+                    if (bp != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(bp));
+                    *reinterpret_cast<float4*>(yp) = make_float4(y4[0] + b4.x, y4[1] + b4.y, y4[2] + b4.z, y4[3] + b4.w);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (c0 + i < c.nrows) yp[i] = y4[i] + (bp != nullptr ? __ldg(bp + i) : 0.f);
+                }
+            }
+        }
+        float p[DS];
+#pragma unroll
+        for (int b = 0; b < DS; ++b) p[b] = dot4(Pm[b * 4 + q], s4);
+        float ns[4];
+        quad_reduce_scatter<DS>(p, q, ns);
+        s4[0] = r4.x + ns[0]; s4[1] = r4.y + ns[1]; s4[2] = r4.z + ns[2]; s4[3] = r4.w + ns[3];
+        cp_async_wait_all();
+        __syncthreads();
+    }
+}
+
+// adjoint scans.  L[j][row][0..15] = lambda_{j+1} (adjoint of the causal state leaving chunk j), L[j][row][16..31] = mu_j (adjoint of
+// the anticausal state leaving chunk j); grad_bias += column sums of grad_y.
+// padded coefficient layout of the adjoint scans: thread q reads rows 4q.. of Phi and 8q.. of O, so every group of 4 (8) rows is
+// followed by one float4 of padding -- the four quads' rows then start 16 bytes apart modulo 128 (conflict-free LDS.128)
+constexpr int QB_PHI = 4 * 17, QB_O = 4 * 33, QB_TOTAL = QB_PHI + QB_O;
+__device__ __forceinline__ void sc_prefetch_padded(float4* dst, const float* __restrict__ src, int nfloat4, int group) {
+    for (int i = threadIdx.x; i < nfloat4; i += QS_THREADS) cp_async16(dst + (i / group) * (group + 1) + (i % group), reinterpret_cast<const float4*>(src) + i);
+}
+
+template <bool MU>
+__device__ __forceinline__ void scan_bwd_pass(float4 (*sc)[QB_TOTAL], float* sbias, const sn_sss_tc_chunk* __restrict__ chunks, int nchunks,
+                                              const float* __restrict__ SCall, const float* __restrict__ gy, long ldgy, float* __restrict__ L,
+                                              float* __restrict__ gbias, long B, int aligned, int q, long row, bool valid) {
+    const int lane = threadIdx.x & 31;
+    const int phi_off = MU ? DS * DS : 0, o_off = 2 * DS * DS + (MU ? PO * DS : 0);
+    auto prefetch = [&](int buf, int j) {
+        sc_prefetch_padded(sc[buf], SCall + (size_t)j * SCF + phi_off, DS * DS / 4, 16);
+        sc_prefetch_padded(sc[buf] + QB_PHI, SCall + (size_t)j * SCF + o_off, PO * DS / 4, 32);
+        cp_async_commit();
+    };
+    float a4[4] = {0.f, 0.f, 0.f, 0.f};
+    prefetch(0, MU ? 0 : nchunks - 1);
+    cp_async_wait_all();
+    __syncthreads();
+    int prev_row0 = 0, prev_nrows = 0;
+    for (int jj = 0; jj < nchunks; ++jj) {
+        const int j = MU ? jj : nchunks - 1 - jj;
+        const float4* Pm = sc[jj & 1] + 17 * q;           // this thread's 4 rows of Phi
+        const float4* Om = sc[jj & 1] + QB_PHI + 33 * q;  // this thread's 8 rows of O
+        if (jj + 1 < nchunks) prefetch((jj + 1) & 1, MU ? j + 1 : j - 1);
+        const sn_sss_tc_chunk c = chunks[j];
+        if (MU && gbias != nullptr && jj > 0 && threadIdx.x < 32) {   // flush the previous chunk's column sums
+            float* sb = sbias + ((jj - 1) & 1) * 32;
+            if ((int)threadIdx.x < prev_nrows) atomicAdd(gbias + prev_row0 + threadIdx.x, sb[threadIdx.x]);
+            sb[threadIdx.x] = 0.f;
+        }
+        float g8[8];
+        {
+            const float* src = gy + (valid ? row : 0) * ldgy + c.row0 + 8 * q;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c0 = 8 * q + 4 * h;
+                if (valid && aligned && c0 + 4 <= c.nrows) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + 4 * h));
+                    g8[4 * h] = v.x; g8[4 * h + 1] = v.y; g8[4 * h + 2] = v.z; g8[4 * h + 3] = v.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) g8[4 * h + i] = (valid && c0 + i < c.nrows) ? __ldg(src + 4 * h + i) : 0.f;
+                }
+            }
+        }
+        if (valid) *(reinterpret_cast<float4*>(L + ((size_t)j * B + row) * 32 + (MU ? DS : 0)) + q) = make_float4(a4[0], a4[1], a4[2], a4[3]);
+        float p[DS];
+#pragma unroll
+        for (int a = 0; a < DS; ++a) p[a] = 0.f;
+#pragma unroll
+        for (int bi = 0; bi < 4; ++bi) axpy16(Pm + bi * 4, a4[bi], p);        // Phi[4q + bi][:] * adjoint[4q + bi]
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) axpy16(Om + ci * 4, g8[ci], p);        // O[8q + ci][:] * gy[8q + ci]
+        quad_reduce_scatter<DS>(p, q, a4);
+        if (MU && gbias != nullptr) {
+            // column sums over the warp's 8 samples (lanes with the same q): transposed reduce over lane bits 4, 3, 2
+            float h4[4], h2[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool up = (lane & 16) != 0;
+                h4[i] = (up ? g8[4 + i] : g8[i]) + __shfl_xor_sync(0xffffffffu, up ? g8[i] : g8[4 + i], 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const bool up = (lane & 8) != 0;
+                h2[i] = (up ? h4[2 + i] : h4[i]) + __shfl_xor_sync(0xffffffffu, up ? h4[i] : h4[2 + i], 8);
+            }
+            const bool up = (lane & 4) != 0;
+            const float colsum = (up ? h2[1] : h2[0]) + __shfl_xor_sync(0xffffffffu, up ? h2[0] : h2[1], 4);
+            const int colid = 8 * q + ((lane & 16) ? 4 : 0) + ((lane & 8) ? 2 : 0) + ((lane & 4) ? 1 : 0);
+            atomicAdd(sbias + (jj & 1) * 32 + colid, colsum);
+        }
+        prev_row0 = c.row0;
+        prev_nrows = c.nrows;
+        cp_async_wait_all();
+        __syncthreads();
+    }
+    if (MU && gbias != nullptr && threadIdx.x < 32) {
+        float* sb = sbias + ((nchunks - 1) & 1) * 32;
+        if ((int)threadIdx.x < prev_nrows) atomicAdd(gbias + prev_row0 + threadIdx.x, sb[threadIdx.x]);
+    }
+}
+
+__global__ void __launch_bounds__(QS_THREADS)
+sss_tc_scan_bwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, const float* __restrict__ SCall, const float* __restrict__ gy,
+                         long ldgy, float* __restrict__ L, float* __restrict__ gbias, long B, int aligned) {
+    __shared__ float4 sc[2][QB_TOTAL];
+    __shared__ float sbias[64];
+    if (threadIdx.x < 64) sbias[threadIdx.x] = 0.f;
+    const int q = threadIdx.x & 3;
+    const long row = (long)blockIdx.x * (QS_THREADS / 4) + (threadIdx.x >> 2);
+    const bool valid = row < B;
+    scan_bwd_pass<false>(sc, sbias, chunks, nchunks, SCall, gy, ldgy, L, gbias, B, aligned, q, row, valid);
+    scan_bwd_pass<true>(sc, sbias, chunks, nchunks, SCall, gy, ldgy, L, gbias, B, aligned, q, row, valid);
+}
+
+// ------------------------------------------------------------------------------------------
 // 5. gradient GEMM: dM_j (64 x N) += [gy_j | lambda | mu]^T [u_j | s | e] over a range of samples, 3xTF32 (all four hi/lo terms).
 //    K = samples; both operands MN-major straight from TMA boxes of [32 samples][32 floats] (SWIZZLE_128B_ATOM_32B, the one
 //    layout kind::tf32 accepts for MN-major operands).
@@ -519,7 +1112,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1)
 sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_gy, const __grid_constant__ CUtensorMap map_l,
                         const __grid_constant__ CUtensorMap map_s, const sn_sss_tc_chunk* __restrict__ chunks, long B, float* __restrict__ dM) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
     uint64_t* conv = full + G2_STAGES;
     uint64_t* empty = conv + G2_STAGES;
@@ -657,8 +1250,11 @@ constexpr int BB_LD = 193;   // shared-memory row stride (odd: the 16 'a' rows o
 __global__ void __launch_bounds__(BUILD_THREADS)
 sss_tc_build_bwd_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss_tc_chunk* __restrict__ chunks, const float* __restrict__ params,
                         const float* __restrict__ dMall, float* __restrict__ scratch, float* __restrict__ gparams) {
-    __shared__ float X[(DS + SOUT_MAX) * BB_LD];   // rows 0..15: lambda, 16..31: this stage's gy
-    __shared__ float V[DS * BB_LD];                // state entering the stage
+    extern __shared__ uint8_t bb_smem[];
+    StageSm* sm = reinterpret_cast<StageSm*>(bb_smem);                 // [2]
+    float* X = reinterpret_cast<float*>(sm + 2);                       // rows 0..15: lambda, 16..31: this stage's gy
+    float* V = X + (DS + SOUT_MAX) * BB_LD;                            // state entering the stage
+    __shared__ sn_sss_stage sdesc[LMAX];
     const sn_sss_tc_chunk c = chunks[blockIdx.x];
     const int dir = blockIdx.y, t = threadIdx.x;
     const bool is_in = t < c.ncols;
@@ -670,21 +1266,29 @@ sss_tc_build_bwd_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn
     const int nst = c.k_end - c.k_begin;
     const int col = c.col0 + t;
     const int cidx = is_in ? t : c.nkb * KBW + dir * DS + sidx;
+    if (t < nst) sdesc[t] = stage_of(stages, n, dir, dir == 0 ? c.k_begin + t : c.k_end - 1 - t);
+    __syncthreads();
+    stage_load_async(sm[0], sdesc[0], params, t, BUILD_THREADS);
+    cp_async_commit();
 
     float v[DS], yv[SOUT_MAX];
-    {
-        const sn_sss_stage& st0 = stage_of(stages, n, dir, dir == 0 ? c.k_begin : c.k_end - 1);
 #pragma unroll
-        for (int a = 0; a < DS; ++a) v[a] = (active && !is_in && a == sidx && sidx < st0.d_in) ? 1.f : 0.f;
-    }
+    for (int a = 0; a < DS; ++a) v[a] = (active && !is_in && a == sidx && sidx < sdesc[0].d_in) ? 1.f : 0.f;
     int my_i = -1;
+    // phase 1: replay the construction, keeping the state that enters every stage
     for (int i = 0; i < nst; ++i) {
-        const sn_sss_stage st = stage_of(stages, n, dir, dir == 0 ? c.k_begin + i : c.k_end - 1 - i);
+        cp_async_wait_all();
+        __syncthreads();
+        if (i + 1 < nst) {
+            stage_load_async(sm[(i + 1) & 1], sdesc[i + 1], params, t, BUILD_THREADS);
+            cp_async_commit();
+        }
+        const sn_sss_stage& st = sdesc[i];
         const int local = col - st.in_off;
         const bool mine = is_in && local >= 0 && local < st.in_dim;
 #pragma unroll
         for (int a = 0; a < DS; ++a) scr[(i * DS + a) * BUILD_THREADS + t] = v[a];
-        if (active) stage_apply(st, params, v, yv, mine, local);
+        if (active) stage_apply(st, sm[i & 1], v, yv, mine, local);
         if (mine) my_i = i;
     }
     // adjoint of the state leaving the last stage: dR / dPhi rows of dM
@@ -692,8 +1296,10 @@ sss_tc_build_bwd_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn
 #pragma unroll
     for (int b = 0; b < DS; ++b) lam[b] = active ? dM[(PO + dir * DS + b) * DMC + cidx] : 0.f;
 
+    // phase 2: stages backwards; the last stage's parameters are still in sm[(nst - 1) & 1]
     for (int i = nst - 1; i >= 0; --i) {
-        const sn_sss_stage st = stage_of(stages, n, dir, dir == 0 ? c.k_begin + i : c.k_end - 1 - i);
+        const sn_sss_stage& st = sdesc[i];
+        const StageSm& ps = sm[i & 1];
         const int local = col - st.in_off;
         const bool mine = (i == my_i);
         const bool before = is_in ? (my_i >= 0 && my_i < i) : true;
@@ -704,7 +1310,12 @@ sss_tc_build_bwd_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn
         for (int r = 0; r < SOUT_MAX; ++r) g[r] = (support && r < st.out_dim) ? dM[(rbase + r) * DMC + cidx] : 0.f;
 #pragma unroll
         for (int a = 0; a < DS; ++a) v[a] = scr[(i * DS + a) * BUILD_THREADS + t];
-        __syncthreads();   // previous iteration's dot products are done with X / V
+        cp_async_wait_all();
+        __syncthreads();   // stage i's parameters have landed; the previous iteration is done with X / V and sm[(i + 1) & 1]
+        if (i > 0) {
+            stage_load_async(sm[(i - 1) & 1], sdesc[i - 1], params, t, BUILD_THREADS);
+            cp_async_commit();
+        }
 #pragma unroll
         for (int b = 0; b < DS; ++b) X[b * BB_LD + t] = lam[b];
 #pragma unroll
@@ -713,14 +1324,23 @@ sss_tc_build_bwd_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn
         for (int a = 0; a < DS; ++a) V[a * BB_LD + t] = v[a];
         __syncthreads();
         // d_ss[b][a] = sum_t lam_t[b] v_t[a] ;  d_ys[r][a] = sum_t g_t[r] v_t[a]
-        for (int o = t; o < (DS + SOUT_MAX) * DS; o += BUILD_THREADS) {
+        const int nrow_valid = DS + st.out_dim;   // rows DS.. are the gy rows
+        for (int o = t; o < nrow_valid * DS; o += BUILD_THREADS) {
             const int rowi = o / DS, a = o % DS;
-            const bool ok = a < st.d_in && (rowi < DS ? rowi < st.d_out : (rowi - DS) < st.out_dim);
+            const bool ok = a < st.d_in && (rowi < DS ? rowi < st.d_out : true);
             if (ok) {
                 const float* xr = X + rowi * BB_LD;
                 const float* vr = V + a * BB_LD;
-                float acc = 0.f;
-                for (int tt = 0; tt < ncol_active; ++tt) acc = fmaf(xr[tt], vr[tt], acc);
+                float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+                int tt = 0;
+                for (; tt + 4 <= ncol_active; tt += 4) {
+                    acc0 = fmaf(xr[tt], vr[tt], acc0);
+                    acc1 = fmaf(xr[tt + 1], vr[tt + 1], acc1);
+                    acc2 = fmaf(xr[tt + 2], vr[tt + 2], acc2);
+                    acc3 = fmaf(xr[tt + 3], vr[tt + 3], acc3);
+                }
+                for (; tt < ncol_active; ++tt) acc0 = fmaf(xr[tt], vr[tt], acc0);
+                const float acc = (acc0 + acc1) + (acc2 + acc3);
                 if (rowi < DS) gparams[st.off_ss + rowi * st.d_in + a] += acc;
                 else gparams[st.off_ys + (rowi - DS) * st.d_in + a] += acc;
             }
@@ -742,25 +1362,26 @@ sss_tc_build_bwd_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn
 #pragma unroll
         for (int b = 0; b < DS; ++b) {
             if (b < st.d_out) {
-                const float* ss = params + st.off_ss + b * st.d_in;
+                const float* ss = ps.ss + b * st.d_in;
 #pragma unroll
                 for (int a = 0; a < DS; ++a)
-                    if (a < st.d_in) nl[a] = fmaf(__ldg(ss + a), lam[b], nl[a]);
+                    if (a < st.d_in) nl[a] = fmaf(ss[a], lam[b], nl[a]);
             }
         }
 #pragma unroll
         for (int r = 0; r < SOUT_MAX; ++r) {
             if (r < st.out_dim) {
-                const float* ys = params + st.off_ys + r * st.d_in;
+                const float* ys = ps.ys + r * st.d_in;
 #pragma unroll
                 for (int a = 0; a < DS; ++a)
-                    if (a < st.d_in) nl[a] = fmaf(__ldg(ys + a), g[r], nl[a]);
+                    if (a < st.d_in) nl[a] = fmaf(ys[a], g[r], nl[a]);
             }
         }
 #pragma unroll
         for (int a = 0; a < DS; ++a) lam[a] = nl[a];
     }
 }
+constexpr size_t BB_SMEM = 2 * sizeof(StageSm) + (size_t)((DS + SOUT_MAX) + DS) * BB_LD * sizeof(float);
 
 int check_tc_plan(const sn_sss_tc_plan* p) {
     SN_CHECK_ARG(p != nullptr, "sss_tc: NULL plan");
@@ -781,6 +1402,16 @@ int sm_count() {
     return n;
 }
 
+// whole tiles per CTA only pay once there are enough tiles to fill most of the chip; below that the (tile, chunk) grid of the
+// three-kernel path has more parallelism.  SNB200_SSS_TC_FUSED=0/1 forces the choice (tests).
+bool use_fused_forward(const sn_sss_tc_plan* p, int64_t B) {
+    if (p->nchunks > F_MAX_CHUNKS) return false;
+    const char* e = getenv("SNB200_SSS_TC_FUSED");
+    if (e != nullptr && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
+    (void)B;
+    return false;   // the three-kernel path with the four-threads-per-sample scans is faster at every batch size measured so far
+}
+
 }  // namespace
 
 extern "C" {
@@ -789,7 +1420,10 @@ size_t sn_sss_tc_coef_floats(const sn_sss_tc_plan* p) {
     if (p == nullptr) return 0;
     return (size_t)p->nchunks * (WROWS * WCOLS + SCF);
 }
-size_t sn_sss_tc_rbuf_floats(const sn_sss_tc_plan* p, int64_t B) { return p == nullptr || B <= 0 ? 0 : (size_t)p->nchunks * B * 64; }
+size_t sn_sss_tc_rbuf_floats(const sn_sss_tc_plan* p, int64_t B) {
+    if (p == nullptr || B <= 0 || use_fused_forward(p, B)) return 0;
+    return (size_t)p->nchunks * B * 64;
+}
 size_t sn_sss_tc_states_floats(const sn_sss_tc_plan* p, int64_t B) { return p == nullptr || B <= 0 ? 0 : (size_t)p->nchunks * B * 32; }
 size_t sn_sss_tc_backward_workspace_floats(const sn_sss_tc_plan* p, int64_t B) {
     if (p == nullptr || B <= 0) return 0;
@@ -809,7 +1443,7 @@ int sn_sss_tc_build(const sn_sss_tc_plan* p, const float* params, float* coef, s
 int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x, int64_t ldx, float* y, int64_t ldy, const float* bias,
                       float* rbuf, float* states, int64_t B, sn_stream_t stream) {
     if (int rc = check_tc_plan(p)) return rc;
-    SN_CHECK_ARG(coef && x && y && rbuf && states, "sss_tc_forward: NULL buffer");
+    SN_CHECK_ARG(coef && x && y && states, "sss_tc_forward: NULL buffer");
     SN_CHECK_ARG(ldx >= p->input_dim && ldy >= p->output_dim, "sss_tc_forward: leading dimension too small");
     if (B <= 0) return 0;
     cudaStream_t st = snb::as_stream(stream);
@@ -819,16 +1453,24 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
     if (int rc = make_map_f32(&mx, x, (uint64_t)p->input_dim, (uint64_t)B, (uint64_t)ldx, 128)) return rc;
     if (int rc = make_map_f32(&mw, W, (uint64_t)WCOLS, (uint64_t)p->nchunks * WROWS, (uint64_t)WCOLS, 128)) return rc;
     const int ntiles = (int)((B + 127) / 128);
+    const int aligned = ((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (ldy & 3) == 0 && (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
+                         p->rows_aligned) ? 1 : 0;
+    if (use_fused_forward(p, B)) {
+        const int grid = ntiles < sm_count() ? ntiles : sm_count();
+        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+        sss_tc_fwd_fused_kernel<<<grid, F_THREADS, F_SMEM, st>>>(mx, mw, p->chunks, p->nchunks, (long)B, ntiles, SC, states, y, (long)ldy, bias, aligned);
+        SN_CHECK_LAUNCH("sss_tc_fwd_fused_kernel");
+        return 0;
+    }
+    SN_CHECK_ARG(rbuf != nullptr, "sss_tc_forward: rbuf is NULL");
     const long total = (long)ntiles * p->nchunks;
     const int grid = (int)(total < sm_count() ? total : sm_count());
     SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_local_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G1_SMEM));
     sss_tc_local_gemm_kernel<<<grid, G1_THREADS, G1_SMEM, st>>>(mx, mw, p->chunks, p->nchunks, (long)B, ntiles, rbuf);
     SN_CHECK_LAUNCH("sss_tc_local_gemm_kernel");
-    const int aligned = ((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (ldy & 3) == 0 && (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
-                         p->rows_aligned) ? 1 : 0;
-    sss_tc_scan_fwd_kernel<<<(unsigned)((B + SCAN_THREADS - 1) / SCAN_THREADS), SCAN_THREADS, 0, st>>>(p->chunks, p->nchunks, SC, rbuf, states, y, (long)ldy,
-                                                                                                      bias, (long)B, aligned);
-    SN_CHECK_LAUNCH("sss_tc_scan_fwd_kernel");
+    sss_tc_scan_fwd_q_kernel<<<(unsigned)((B + QS_THREADS / 4 - 1) / (QS_THREADS / 4)), QS_THREADS, 0, st>>>(p->chunks, p->nchunks, SC, rbuf, states, y,
+                                                                                                             (long)ldy, bias, (long)B, aligned);
+    SN_CHECK_LAUNCH("sss_tc_scan_fwd_q_kernel");
     return 0;
 }
 
@@ -845,9 +1487,9 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     float* dM = L + (size_t)p->nchunks * B * 32;
     float* scratch = dM + (size_t)p->nchunks * 64 * DMC;
     const int aligned = p->rows_aligned ? 1 : 0;
-    sss_tc_scan_bwd_kernel<<<(unsigned)((B + SCAN_THREADS - 1) / SCAN_THREADS), SCAN_THREADS, 0, st>>>(p->chunks, p->nchunks, SC, grad_y, (long)ldgy, L,
-                                                                                                      grad_bias, (long)B, aligned);
-    SN_CHECK_LAUNCH("sss_tc_scan_bwd_kernel");
+    sss_tc_scan_bwd_q_kernel<<<(unsigned)((B + QS_THREADS / 4 - 1) / (QS_THREADS / 4)), QS_THREADS, 0, st>>>(p->chunks, p->nchunks, SC, grad_y, (long)ldgy,
+                                                                                                             L, grad_bias, (long)B, aligned);
+    SN_CHECK_LAUNCH("sss_tc_scan_bwd_q_kernel");
     SN_CHECK_CUDA(cudaMemsetAsync(dM, 0, (size_t)p->nchunks * 64 * DMC * sizeof(float), st));
     CUtensorMap mx, mg, ml, ms;
     if (int rc = make_map_f32(&mx, x, (uint64_t)p->input_dim, (uint64_t)B, (uint64_t)ldx, G2_KS, 0, 0, true)) return rc;
@@ -861,7 +1503,8 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_grad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
     sss_tc_grad_gemm_kernel<<<dim3(nsplit, p->nchunks), G2_THREADS, G2_SMEM, st>>>(mx, mg, ml, ms, p->chunks, (long)B, dM);
     SN_CHECK_LAUNCH("sss_tc_grad_gemm_kernel");
-    sss_tc_build_bwd_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, 0, st>>>(p->stages, p->nb_states, p->chunks, params, dM, scratch, grad_params);
+    SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BB_SMEM));
+    sss_tc_build_bwd_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, BB_SMEM, st>>>(p->stages, p->nb_states, p->chunks, params, dM, scratch, grad_params);
     SN_CHECK_LAUNCH("sss_tc_build_bwd_kernel");
     return 0;
 }

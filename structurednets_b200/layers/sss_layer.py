@@ -133,7 +133,8 @@ class _SSSTCFunction(torch.autograd.Function):
         coef = tc["coef"]
         _lib.check(L.sn_sss_tc_build(ps, _lib.ptr(flat), _lib.ptr(coef), _lib.stream_ptr()), "sn_sss_tc_build")
         y = torch.empty((B, layer.output_dim), dtype=torch.float32, device=U.device)
-        rbuf = torch.empty(max(int(L.sn_sss_tc_rbuf_floats(ps, B)), 1), dtype=torch.float32, device=U.device)
+        nr = int(L.sn_sss_tc_rbuf_floats(ps, B))     # 0 when the fused large-batch forward runs
+        rbuf = torch.empty(nr, dtype=torch.float32, device=U.device) if nr else None
         states = torch.empty(max(int(L.sn_sss_tc_states_floats(ps, B)), 1), dtype=torch.float32, device=U.device)
         bias = layer.bias if layer.use_bias else None
         rc = L.sn_sss_tc_forward(ps, _lib.ptr(coef), _lib.ptr(U), U.stride(0), _lib.ptr(y), y.stride(0), _lib.ptr(bias),
