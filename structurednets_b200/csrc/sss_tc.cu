@@ -1094,6 +1094,434 @@ sss_tc_scan_bwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
 }
 
 // ------------------------------------------------------------------------------------------
+// 3''/4''. chunk scans on the tensor core.  A scan step is state' = in + M state with a 16 x 16 (plus output rows) matrix per
+//    chunk -- serial in the chunk index, but for 128 samples at once it is one tiny UMMA: A = the tile's state vectors
+//    [128 x (hi 16 | lo 16)] written to shared memory by the epilogue threads (thread = sample), B = the chunk's packed, pre-split
+//    coefficient tile (TMA), D in TMEM.  The chain  MMA -> TMEM -> registers -> shared memory -> MMA  costs about a microsecond
+//    per step; several CTAs per SM overlap their chains.  Per-sample global traffic (r, yloc, grad_y rows) is prefetched one step
+//    ahead, off the chain.
+//    Coefficient tiles CW[chunk][kind] (96 rows x 32 floats, K-major, SWIZZLE_128B by TMA), kind 0/1 = forward causal/anticausal:
+//       rows n < 48: [Whi(n,:) | Whi(n,:)], rows 48 + n: [Wlo(n,:) | 0], W = [O ; Phi] (48 x 16)   -> D[:, n] + D[:, 48 + n]
+//    kind 2/3 = backward lambda/mu, three 32-row sub-tiles: state (Phi^T), grad_y hi part (O^T), grad_y lo part (O^T).
+// ------------------------------------------------------------------------------------------
+constexpr int CH_THREADS = 160;                 // warps 0-3: epilogue (thread = sample), warp 4: TMA + MMA issuer (one lane)
+constexpr int CW_ROWS = 96;
+constexpr int CW_TILE_FLOATS = CW_ROWS * 32;    // 3072 floats = 12 KB
+constexpr int CW_TILE_BYTES = CW_TILE_FLOATS * 4;
+
+// one thread per (row, k) entry of a tile
+__global__ void __launch_bounds__(256)
+sss_tc_pack_chain_kernel(const float* __restrict__ SCall, float* __restrict__ CWall) {
+    const int ch = blockIdx.x, kind = blockIdx.y;
+    const float* SC = SCall + (size_t)ch * SCF;
+    float* CW = CWall + ((size_t)ch * 4 + kind) * CW_TILE_FLOATS;
+    const int dir = kind & 1;
+    const float* Phi = SC + dir * DS * DS;
+    const float* O = SC + 2 * DS * DS + dir * PO * DS;
+    for (int i = threadIdx.x; i < CW_TILE_FLOATS; i += 256) {
+        const int row = i >> 5, k = i & 31;
+        float out = 0.f;
+        if (kind < 2) {
+            const int n = row % 48, lo = row / 48, a = k & 15;
+            const float w = n < PO ? O[n * DS + a] : Phi[(n - PO) * DS + a];
+            const float hi = tf32_hi(w);
+            out = lo ? (k < 16 ? tf32_hi(w - hi) : 0.f) : hi;
+        } else {
+            const int sub = row >> 5, r = row & 31, a = r & 15, lo = r >> 4;
+            float w;
+            if (sub == 0) w = Phi[(k & 15) * DS + a];   // Phi^T: row a, k = b
+            else w = O[k * DS + a];                      // O^T:  row a, k = c
+            const float hi = tf32_hi(w);
+            if (sub == 0) out = lo ? (k < 16 ? tf32_hi(w - hi) : 0.f) : hi;
+            else if (sub == 1) out = lo ? tf32_hi(w - hi) : hi;
+            else out = lo ? 0.f : hi;
+        }
+        CW[i] = out;
+    }
+}
+
+// thread `row` writes 32 floats (v[0..31]) as its 128-byte row of a K-major SWIZZLE_128B tile
+__device__ __forceinline__ void store_row_sw128(uint8_t* tile, int row, const float (&v)[32]) {
+    uint8_t* base = tile + row * 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(base + ((c ^ (row & 7)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+__device__ __forceinline__ void store_state_hi_lo(uint8_t* tile, int row, const float (&st)[DS]) {
+    float v[32];
+#pragma unroll
+    for (int a = 0; a < DS; ++a) split_tf32(st[a], v[a], v[DS + a]);
+    store_row_sw128(tile, row, v);
+}
+
+// Per-step ring slot (2 slots): coefficient tile (12 KB) + this step's per-sample inputs, all fetched by TMA two steps ahead so
+// that no global load sits between the epilogue threads and their fence.proxy.async (a fence waits for the thread's loads).
+//   forward : `in` = r or r' rows [128][16 floats] (SWIZZLE_64B) and yl = yloc / ytmp rows [128][32] (SWIZZLE_128B)
+//   backward: grad_y rows [128][32] (SWIZZLE_128B)
+struct ChainSmem {
+    uint8_t* state;    // 16 KB: [128][state hi 16 | state lo 16], K-major SWIZZLE_128B
+    uint8_t* in_hi;    // 16 KB (backward only): grad_y hi parts
+    uint8_t* in_lo;    // 16 KB (backward only)
+    uint8_t* slot[2];
+    uint64_t *full, *empty, *state_ready, *acc_full, *chain_done;
+    uint32_t* tmem_slot;
+};
+constexpr int CHF_SLOT = CW_TILE_BYTES + 8192 + 16384;    // W | in (8 KB at +12288) | yl (16 KB at +20480)
+constexpr int CHB_SLOT = CW_TILE_BYTES + 4096 + 16384;    // W | pad | grad_y (16 KB at +16384)
+template <bool BWD>
+__device__ __forceinline__ ChainSmem chain_carve(uint8_t* smem_raw) {
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    ChainSmem c;
+    c.state = smem;
+    c.in_hi = smem + 16384;
+    c.in_lo = smem + 32768;
+    uint8_t* s0 = smem + (BWD ? 49152 : 16384);
+    constexpr int SLOT = BWD ? CHB_SLOT : CHF_SLOT;
+    c.slot[0] = s0;
+    c.slot[1] = s0 + SLOT;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s0 + 2 * SLOT);
+    c.full = bars;
+    c.empty = bars + 2;
+    c.state_ready = bars + 4;
+    c.acc_full = bars + 5;
+    c.chain_done = bars + 6;
+    c.tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    return c;
+}
+constexpr size_t CHF_SMEM = 16384 + 2 * CHF_SLOT + 128 + 1024;
+constexpr size_t CHB_SMEM = 49152 + 2 * CHB_SLOT + 128 + 1024;
+
+// the MMAs of one step (issuer thread)
+template <bool BWD>
+__device__ __forceinline__ void chain_mma(const ChainSmem& sm, const uint8_t* w, uint32_t tmem) {
+    constexpr uint32_t idesc = BWD ? idesc_tf32(128, 32, false, false) : idesc_tf32(128, 96, false, false);
+    const uint64_t dst = desc_kmajor_sw128(sm.state);
+    const uint64_t dw = desc_kmajor_sw128(w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mma_tf32(tmem, dst + 2 * k, dw + 2 * k, idesc, k ? 1u : 0u);
+    if (BWD) {
+        const uint64_t dih = desc_kmajor_sw128(sm.in_hi), dil = desc_kmajor_sw128(sm.in_lo);
+        const uint64_t dw1 = desc_kmajor_sw128(w + 4096), dw2 = desc_kmajor_sw128(w + 8192);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_tf32(tmem, dih + 2 * k, dw1 + 2 * k, idesc, 1u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_tf32(tmem, dil + 2 * k, dw2 + 2 * k, idesc, 1u);
+    }
+}
+
+// row r of a [128][32 floats] SWIZZLE_128B box / a [128][16 floats] SWIZZLE_64B box, as TMA wrote it
+__device__ __forceinline__ void load_row_sw128(const uint8_t* tile, int r, float (&v)[32]) {
+    const uint8_t* base = tile + r * 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 t = *reinterpret_cast<const float4*>(base + ((c ^ (r & 7)) << 4));
+        v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void load_row_sw64(const uint8_t* tile, int r, float (&v)[16]) {
+    const uint8_t* base = tile + r * 64;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float4 t = *reinterpret_cast<const float4*>(base + ((c ^ ((r >> 1) & 3)) << 4));
+        v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+    }
+}
+
+// forward: steps 0..nc-1 = anticausal chain over chunks nc-1..0 (writes e_{j+1}, ytmp = yloc + O' e into rbuf),
+//          steps nc..2nc-1 = causal chain over chunks 0..nc-1 (writes s_j, y = ytmp + O s + bias)
+__global__ void __launch_bounds__(CH_THREADS)
+sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_yl,
+                        const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, float* __restrict__ rbuf, float* __restrict__ S, float* __restrict__ y,
+                        long ldy, const float* __restrict__ bias, long B, int aligned) {
+    extern __shared__ uint8_t smem_raw[];
+    const ChainSmem sm = chain_carve<false>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nsteps = 2 * nchunks;
+    if (threadIdx.x == 0) {
+        mbar_init(sm.full, 1); mbar_init(sm.full + 1, 1); mbar_init(sm.empty, 129); mbar_init(sm.empty + 1, 129);
+        mbar_init(sm.state_ready, 128); mbar_init(sm.acc_full, 1); mbar_init(sm.chain_done, 128);
+        mbar_fence_init();
+        tma_prefetch_desc(&map_cw);
+        tma_prefetch_desc(&map_in);
+        tma_prefetch_desc(&map_yl);
+    }
+    if (warp == 4) tmem_alloc<128>(sm.tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *sm.tmem_slot;
+    auto chunk_of = [&](int t) { return t < nchunks ? nchunks - 1 - t : t - nchunks; };
+
+    if (warp == 4) {
+        if (lane == 0) {
+            auto issue = [&](int t) {
+                const int s = t & 1, j = chunk_of(t);
+                const bool anti = t < nchunks;
+                uint8_t* slot = sm.slot[s];
+                mbar_expect_tx(sm.full + s, CW_TILE_BYTES + 8192 + 16384);
+                tma_load_2d(slot, &map_cw, 0, (j * 4 + (anti ? 1 : 0)) * CW_ROWS, sm.full + s);
+                tma_load_2d(slot + CW_TILE_BYTES, &map_in, anti ? 48 : 32, (int)((long)j * B + (long)blockIdx.x * 128), sm.full + s);
+                tma_load_2d(slot + CW_TILE_BYTES + 8192, &map_yl, 0, (int)((long)j * B + (long)blockIdx.x * 128), sm.full + s);
+            };
+            // the second chain (steps >= nchunks) re-reads through TMA the ytmp rows the first chain wrote with ordinary stores, so
+            // its loads may only be issued once the first chain's last epilogue has fenced them (chain_done): the ring drains once
+            for (int t = 0; t < 2 && t < nchunks; ++t) issue(t);
+            for (int t = 0; t < nsteps; ++t) {
+                const int s = t & 1;
+                mbar_wait(sm.full + s, (t >> 1) & 1);
+                mbar_wait(sm.state_ready, t & 1);
+                tc_fence_after();
+                chain_mma<false>(sm, sm.slot[s], tmem);
+                umma_commit(sm.acc_full);
+                umma_commit(sm.empty + s);           // 1 of 129 arrivals: the MMAs have read the coefficient tile
+                if (t == nchunks - 1) {
+                    mbar_wait(sm.chain_done, 0);
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    for (int q = nchunks; q < nchunks + 2 && q < nsteps; ++q) {
+                        if (q >= 2) mbar_wait(sm.empty + (q & 1), ((q - 2) >> 1) & 1);
+                        issue(q);
+                    }
+                } else if (t + 2 < nsteps && (t + 2 < nchunks || t >= nchunks)) {
+                    mbar_wait(sm.empty + s, (t >> 1) & 1);   // + the 128 epilogue threads have read their inputs
+                    issue(t + 2);
+                }
+            }
+        }
+    } else {
+        const int r = threadIdx.x;                         // TMEM lane = tile row
+        const long row = (long)blockIdx.x * 128 + r;
+        const bool valid = row < B;
+        const uint32_t tacc = tmem + ((uint32_t)(warp * 32) << 16);
+        float st[DS];
+#pragma unroll
+        for (int a = 0; a < DS; ++a) st[a] = 0.f;
+        store_state_hi_lo(sm.state, r, st);
+        fence_async_smem();
+        mbar_arrive(sm.state_ready);
+        for (int t = 0; t < nsteps; ++t) {
+            const bool anti = t < nchunks;
+            const int j = chunk_of(t), s = t & 1;
+            // this step's entering state goes to the checkpoint buffer (kept for the backward)
+            if (valid) {
+                float4* sp = reinterpret_cast<float4*>(S + ((size_t)j * B + row) * 32 + (anti ? DS : 0));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sp[i] = make_float4(st[4 * i], st[4 * i + 1], st[4 * i + 2], st[4 * i + 3]);
+            }
+            mbar_wait(sm.full + s, (t >> 1) & 1);
+            float in[DS], yl[PO];
+            load_row_sw64(sm.slot[s] + CW_TILE_BYTES, r, in);
+            load_row_sw128(sm.slot[s] + CW_TILE_BYTES + 8192, r, yl);
+            mbar_arrive(sm.empty + s);
+            mbar_wait(sm.acc_full, t & 1);
+            tc_fence_after();
+            // state part first: it is the chain
+            uint32_t m[16], l[16];
+            tmem_ld16_nowait(tacc + 32, m);
+            tmem_ld16_nowait(tacc + 80, l);
+            tmem_ld_wait();
+            const bool last_of_chain = (t == nchunks - 1);
+#pragma unroll
+            for (int a = 0; a < DS; ++a) st[a] = last_of_chain ? 0.f : in[a] + (__uint_as_float(m[a]) + __uint_as_float(l[a]));
+            uint32_t ym[32], ylo[32];
+            tmem_ld16_nowait(tacc, reinterpret_cast<uint32_t(&)[16]>(ym[0]));
+            tmem_ld16_nowait(tacc + 16, reinterpret_cast<uint32_t(&)[16]>(ym[16]));
+            tmem_ld16_nowait(tacc + 48, reinterpret_cast<uint32_t(&)[16]>(ylo[0]));
+            tmem_ld16_nowait(tacc + 64, reinterpret_cast<uint32_t(&)[16]>(ylo[16]));
+            tmem_ld_wait();
+            tc_fence_before();
+            store_state_hi_lo(sm.state, r, st);
+            fence_async_smem();
+            mbar_arrive(sm.state_ready);
+            // outputs, off the chain
+            const sn_sss_tc_chunk c = chunks[j];
+            if (valid) {
+                if (anti) {
+                    float4* dst = reinterpret_cast<float4*>(rbuf + ((size_t)j * B + row) * 64);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float4 o;
+                        o.x = yl[4 * i] + (__uint_as_float(ym[4 * i]) + __uint_as_float(ylo[4 * i]));
+                        o.y = yl[4 * i + 1] + (__uint_as_float(ym[4 * i + 1]) + __uint_as_float(ylo[4 * i + 1]));
+                        o.z = yl[4 * i + 2] + (__uint_as_float(ym[4 * i + 2]) + __uint_as_float(ylo[4 * i + 2]));
+                        o.w = yl[4 * i + 3] + (__uint_as_float(ym[4 * i + 3]) + __uint_as_float(ylo[4 * i + 3]));
+                        dst[i] = o;
+                    }
+                } else {
+                    float* yrow = y + row * ldy + c.row0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (4 * i < c.nrows) {
+                            float o[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) o[e] = yl[4 * i + e] + (__uint_as_float(ym[4 * i + e]) + __uint_as_float(ylo[4 * i + e]));
+                            if (aligned && 4 * i + 4 <= c.nrows) {
+                                if (bias != nullptr) {
+                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c.row0 + 4 * i));
+                                    o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
+                                }
+                                *reinterpret_cast<float4*>(yrow + 4 * i) = make_float4(o[0], o[1], o[2], o[3]);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (4 * i + e < c.nrows) yrow[4 * i + e] = o[e] + (bias != nullptr ? __ldg(bias + c.row0 + 4 * i + e) : 0.f);
+                            }
+                        }
+                    }
+                }
+            }
+            if (last_of_chain) {
+                asm volatile("fence.proxy.async;" ::: "memory");   // ytmp stores -> visible to the TMA reads of the second chain
+                mbar_arrive(sm.chain_done);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc<128>(tmem);
+    }
+}
+
+// backward: steps 0..nc-1 = lambda chain over chunks nc-1..0, steps nc..2nc-1 = mu chain over chunks 0..nc-1.
+// L[j][row][0..15] = lambda_{j+1}, L[j][row][16..31] = mu_j ; grad_bias += column sums of grad_y (second chain).
+// Ring slot of step t: coefficient tile of step t + the grad_y rows of step t + 1 (the epilogue of step t splits them into the
+// hi / lo operand tiles of step t + 1's MMAs).  Step 0's rows arrive through a prologue load into the (still unused) lo tile.
+__global__ void __launch_bounds__(CH_THREADS)
+sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid_constant__ CUtensorMap map_gy, const sn_sss_tc_chunk* __restrict__ chunks,
+                        int nchunks, float* __restrict__ L, float* __restrict__ gbias, long B) {
+    extern __shared__ uint8_t smem_raw[];
+    const ChainSmem sm = chain_carve<true>(smem_raw);
+    __shared__ float sbias[2][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nsteps = 2 * nchunks;
+    if (threadIdx.x == 0) {
+        mbar_init(sm.full, 1); mbar_init(sm.full + 1, 1); mbar_init(sm.empty, 129); mbar_init(sm.empty + 1, 129);
+        mbar_init(sm.state_ready, 128); mbar_init(sm.acc_full, 1); mbar_init(sm.chain_done, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&map_cw);
+        tma_prefetch_desc(&map_gy);
+    }
+    if (threadIdx.x < 64) sbias[threadIdx.x >> 5][threadIdx.x & 31] = 0.f;
+    if (warp == 4) tmem_alloc<32>(sm.tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *sm.tmem_slot;
+    auto chunk_of = [&](int t) { return t < nchunks ? nchunks - 1 - t : t - nchunks; };
+
+    if (warp == 4) {
+        if (lane == 0) {
+            auto issue = [&](int t) {
+                const int s = t & 1, j = chunk_of(t);
+                uint8_t* slot = sm.slot[s];
+                const bool has_next = t + 1 < nsteps;
+                mbar_expect_tx(sm.full + s, CW_TILE_BYTES + (has_next ? 16384 : 0));
+                tma_load_2d(slot, &map_cw, 0, (j * 4 + (t < nchunks ? 2 : 3)) * CW_ROWS, sm.full + s);
+                if (has_next) tma_load_2d(slot + 16384, &map_gy, chunks[chunk_of(t + 1)].row0, blockIdx.x * 128, sm.full + s);
+            };
+            mbar_expect_tx(sm.chain_done, 16384);
+            tma_load_2d(sm.in_lo, &map_gy, chunks[chunk_of(0)].row0, blockIdx.x * 128, sm.chain_done);
+            for (int t = 0; t < 2 && t < nsteps; ++t) issue(t);
+            for (int t = 0; t < nsteps; ++t) {
+                const int s = t & 1;
+                mbar_wait(sm.full + s, (t >> 1) & 1);
+                mbar_wait(sm.state_ready, t & 1);
+                tc_fence_after();
+                chain_mma<true>(sm, sm.slot[s], tmem);
+                umma_commit(sm.acc_full);
+                umma_commit(sm.empty + s);
+                if (t + 2 < nsteps) {
+                    mbar_wait(sm.empty + s, (t >> 1) & 1);
+                    issue(t + 2);
+                }
+            }
+        }
+    } else {
+        const int r = threadIdx.x;
+        const long row = (long)blockIdx.x * 128 + r;
+        const bool valid = row < B;
+        const uint32_t tacc = tmem + ((uint32_t)(warp * 32) << 16);
+        auto store_inputs = [&](const float (&gv)[PO]) {
+            float h[PO], l[PO];
+#pragma unroll
+            for (int c = 0; c < PO; ++c) split_tf32(gv[c], h[c], l[c]);
+            store_row_sw128(sm.in_hi, r, h);
+            store_row_sw128(sm.in_lo, r, l);
+        };
+        float st[DS], g[PO];
+#pragma unroll
+        for (int a = 0; a < DS; ++a) st[a] = 0.f;
+        mbar_wait(sm.chain_done, 0);
+        load_row_sw128(sm.in_lo, r, g);        // raw grad_y rows of step 0 (each thread only touches its own 128-byte row)
+        store_state_hi_lo(sm.state, r, st);
+        store_inputs(g);
+        fence_async_smem();
+        mbar_arrive(sm.state_ready);
+        for (int t = 0; t < nsteps; ++t) {
+            const bool second = t >= nchunks;
+            const int j = chunk_of(t), s = t & 1;
+            const bool has_next = t + 1 < nsteps;
+            if (valid) {
+                float4* lp = reinterpret_cast<float4*>(L + ((size_t)j * B + row) * 32 + (second ? DS : 0));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) lp[i] = make_float4(st[4 * i], st[4 * i + 1], st[4 * i + 2], st[4 * i + 3]);
+            }
+            if (second && gbias != nullptr) {
+                // column sums of this chunk's grad_y rows over the warp (lane l ends with column l), then over the 4 warps
+                float v[PO];
+#pragma unroll
+                for (int c = 0; c < PO; ++c) v[c] = g[c];
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+                    for (int i = 0; i < off; ++i) {
+                        const bool up = (lane & off) != 0;
+                        const float send = up ? v[i] : v[i + off];
+                        const float keep = up ? v[i + off] : v[i];
+                        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+                atomicAdd(&sbias[t & 1][lane], v[0]);
+            }
+            mbar_wait(sm.full + s, (t >> 1) & 1);
+            if (has_next) load_row_sw128(sm.slot[s] + 16384, r, g);
+            mbar_arrive(sm.empty + s);
+            mbar_wait(sm.acc_full, t & 1);
+            tc_fence_after();
+            uint32_t m[16], l[16];
+            tmem_ld16_nowait(tacc, m);
+            tmem_ld16_nowait(tacc + 16, l);
+            tmem_ld_wait();
+            tc_fence_before();
+            const bool last_of_chain = (t == nchunks - 1);
+#pragma unroll
+            for (int a = 0; a < DS; ++a) st[a] = last_of_chain ? 0.f : (__uint_as_float(m[a]) + __uint_as_float(l[a]));
+            if (has_next) {
+                store_state_hi_lo(sm.state, r, st);
+                store_inputs(g);
+                fence_async_smem();
+                mbar_arrive(sm.state_ready);
+            }
+            if (second && gbias != nullptr) {
+                named_bar_sync(1, 128);   // all four warps have added this step's column sums
+                if (warp == 0) {
+                    const sn_sss_tc_chunk c = chunks[j];
+                    if (lane < c.nrows) atomicAdd(gbias + c.row0 + lane, sbias[t & 1][lane]);
+                    sbias[t & 1][lane] = 0.f;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc<32>(tmem);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // 5. gradient GEMM: dM_j (64 x N) += [gy_j | lambda | mu]^T [u_j | s | e] over a range of samples, 3xTF32 (all four hi/lo terms).
 //    K = samples; both operands MN-major straight from TMA boxes of [32 samples][32 floats] (SWIZZLE_128B_ATOM_32B, the one
 //    layout kind::tf32 accepts for MN-major operands).
@@ -1412,13 +1840,19 @@ bool use_fused_forward(const sn_sss_tc_plan* p, int64_t B) {
     return false;   // the three-kernel path with the four-threads-per-sample scans is faster at every batch size measured so far
 }
 
+// chunk scans on the tensor core (default) or the SIMT four-threads-per-sample kernels (SNB200_SSS_TC_CHAIN=0; tests)
+bool use_tc_chain() {
+    const char* e = getenv("SNB200_SSS_TC_CHAIN");
+    return !(e != nullptr && e[0] == '0');
+}
+
 }  // namespace
 
 extern "C" {
 
 size_t sn_sss_tc_coef_floats(const sn_sss_tc_plan* p) {
     if (p == nullptr) return 0;
-    return (size_t)p->nchunks * (WROWS * WCOLS + SCF);
+    return (size_t)p->nchunks * (WROWS * WCOLS + SCF + 4 * CW_TILE_FLOATS);
 }
 size_t sn_sss_tc_rbuf_floats(const sn_sss_tc_plan* p, int64_t B) {
     if (p == nullptr || B <= 0 || use_fused_forward(p, B)) return 0;
@@ -1437,6 +1871,9 @@ int sn_sss_tc_build(const sn_sss_tc_plan* p, const float* params, float* coef, s
     float* SC = coef + (size_t)p->nchunks * WROWS * WCOLS;
     sss_tc_build_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, 0, snb::as_stream(stream)>>>(p->stages, p->nb_states, p->chunks, params, W, SC);
     SN_CHECK_LAUNCH("sss_tc_build_kernel");
+    float* CW = SC + (size_t)p->nchunks * SCF;
+    sss_tc_pack_chain_kernel<<<dim3(p->nchunks, 4), 256, 0, snb::as_stream(stream)>>>(SC, CW);
+    SN_CHECK_LAUNCH("sss_tc_pack_chain_kernel");
     return 0;
 }
 
@@ -1468,6 +1905,19 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
     SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_local_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G1_SMEM));
     sss_tc_local_gemm_kernel<<<grid, G1_THREADS, G1_SMEM, st>>>(mx, mw, p->chunks, p->nchunks, (long)B, ntiles, rbuf);
     SN_CHECK_LAUNCH("sss_tc_local_gemm_kernel");
+    if (use_tc_chain()) {
+        CUtensorMap mc;
+        const float* CW = SC + (size_t)p->nchunks * SCF;
+        if (int rc = make_map_f32(&mc, CW, 32, (uint64_t)p->nchunks * 4 * CW_ROWS, 32, CW_ROWS)) return rc;
+        CUtensorMap mi, my;
+        SN_CHECK_ARG((long)p->nchunks * B < 2147483647L, "sss_tc_forward: nchunks * B exceeds the TMA coordinate range");
+        if (int rc = make_map_f32(&mi, rbuf, 64, (uint64_t)p->nchunks * B, 64, 128, 0, 0, false, 16)) return rc;
+        if (int rc = make_map_f32(&my, rbuf, 64, (uint64_t)p->nchunks * B, 64, 128)) return rc;
+        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHF_SMEM));
+        sss_tc_chain_fwd_kernel<<<ntiles, CH_THREADS, CHF_SMEM, st>>>(mc, mi, my, p->chunks, p->nchunks, rbuf, states, y, (long)ldy, bias, (long)B, aligned);
+        SN_CHECK_LAUNCH("sss_tc_chain_fwd_kernel");
+        return 0;
+    }
     sss_tc_scan_fwd_q_kernel<<<(unsigned)((B + QS_THREADS / 4 - 1) / (QS_THREADS / 4)), QS_THREADS, 0, st>>>(p->chunks, p->nchunks, SC, rbuf, states, y,
                                                                                                              (long)ldy, bias, (long)B, aligned);
     SN_CHECK_LAUNCH("sss_tc_scan_fwd_q_kernel");
@@ -1487,9 +1937,20 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     float* dM = L + (size_t)p->nchunks * B * 32;
     float* scratch = dM + (size_t)p->nchunks * 64 * DMC;
     const int aligned = p->rows_aligned ? 1 : 0;
-    sss_tc_scan_bwd_q_kernel<<<(unsigned)((B + QS_THREADS / 4 - 1) / (QS_THREADS / 4)), QS_THREADS, 0, st>>>(p->chunks, p->nchunks, SC, grad_y, (long)ldgy,
+    if (use_tc_chain()) {
+        CUtensorMap mc;
+        const float* CW = SC + (size_t)p->nchunks * SCF;
+        if (int rc = make_map_f32(&mc, CW, 32, (uint64_t)p->nchunks * 4 * CW_ROWS, 32, CW_ROWS)) return rc;
+        CUtensorMap mgy;
+        if (int rc = make_map_f32(&mgy, grad_y, (uint64_t)p->output_dim, (uint64_t)B, (uint64_t)ldgy, 128)) return rc;
+        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHB_SMEM));
+        sss_tc_chain_bwd_kernel<<<(unsigned)((B + 127) / 128), CH_THREADS, CHB_SMEM, st>>>(mc, mgy, p->chunks, p->nchunks, L, grad_bias, (long)B);
+        SN_CHECK_LAUNCH("sss_tc_chain_bwd_kernel");
+    } else {
+        sss_tc_scan_bwd_q_kernel<<<(unsigned)((B + QS_THREADS / 4 - 1) / (QS_THREADS / 4)), QS_THREADS, 0, st>>>(p->chunks, p->nchunks, SC, grad_y, (long)ldgy,
                                                                                                              L, grad_bias, (long)B, aligned);
     SN_CHECK_LAUNCH("sss_tc_scan_bwd_q_kernel");
+    }
     SN_CHECK_CUDA(cudaMemsetAsync(dM, 0, (size_t)p->nchunks * 64 * DMC * sizeof(float), st));
     CUtensorMap mx, mg, ml, ms;
     if (int rc = make_map_f32(&mx, x, (uint64_t)p->input_dim, (uint64_t)B, (uint64_t)ldx, G2_KS, 0, 0, true)) return rc;

@@ -137,7 +137,7 @@ inline EncodeTiledFn encode_fn() {
 // or SWIZZLE_128B_ATOM_32B (32-byte chunks, for MN-major tf32 operands), OOB -> 0.
 // rank 2 when d2 == 0.
 inline int make_map_f32(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t ld1, uint32_t b1, uint64_t d2 = 0,
-                        uint64_t ld2 = 0, bool atom32 = false) {
+                        uint64_t ld2 = 0, bool atom32 = false, uint32_t b0 = 32) {
     EncodeTiledFn fn = encode_fn();
     SN_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     SN_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld1 * 4) % 16 == 0 && (ld2 * 4) % 16 == 0,
@@ -145,10 +145,11 @@ inline int make_map_f32(CUtensorMap* map, const void* base, uint64_t d0, uint64_
     const int rank = d2 ? 3 : 2;
     cuuint64_t dims[3] = {d0, d1, d2 ? d2 : 1};
     cuuint64_t strides[2] = {ld1 * 4, ld2 * 4};
-    cuuint32_t box[3] = {32, b1, 1};
+    cuuint32_t box[3] = {b0, b1, 1};   // b0 = 16: 64-byte rows, SWIZZLE_64B
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    b0 == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SN_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)r);
     return 0;
