@@ -34,6 +34,10 @@ const char* sn_last_error_string(void);
 /* number of kernels this library has launched since load / last reset (bench.py's gpu_launches) */
 long long sn_launch_count(void);
 void sn_reset_launch_count(void);
+/* optional per-kernel timing with CUDA events on the launching stream: enable, run, synchronise the device, then read
+ * "name count total_ms\n" lines (returns the length of the full report) */
+void sn_timing_enable(int on);
+int sn_timing_report(char* buf, int cap);
 
 /* ------------------------------------------------------------------------------------------
  * SSS layer -- replaces SSSLayer.forward (layers/sss_layer.py:99-131) and its autograd backward.

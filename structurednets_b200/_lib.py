@@ -49,6 +49,10 @@ def _declare(lib):
     lib.sn_last_error_string.restype = c_char_p
     lib.sn_launch_count.restype = c_longlong
     lib.sn_reset_launch_count.restype = None
+    lib.sn_timing_enable.restype = None
+    lib.sn_timing_enable.argtypes = [c_int]
+    lib.sn_timing_report.restype = c_int
+    lib.sn_timing_report.argtypes = [c_char_p, c_int]
     P = POINTER(SnSssPlan)
     lib.sn_sss_packed_floats.restype = c_size_t
     lib.sn_sss_packed_floats.argtypes = [P]
@@ -145,6 +149,19 @@ def stream_ptr():
 def ptr(t):
     """Device pointer of a torch tensor (or None)."""
     return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def timing_report() -> dict:
+    """{kernel name: (launches, total ms)} for the launches recorded since the last report (synchronises the device)."""
+    import torch
+    torch.cuda.synchronize()
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib().sn_timing_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        out[name] = (int(cnt), float(ms))
+    return out
 
 
 def launch_count() -> int:

@@ -13,6 +13,9 @@ namespace snb {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// optional per-kernel CUDA-event timing (sn_timing_enable / sn_timing_report; bench.py's roofline uses it)
+void timing_begin(const char* name, cudaStream_t stream);
+void timing_end(cudaStream_t stream);
 
 inline cudaStream_t as_stream(sn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -41,6 +44,15 @@ inline cudaStream_t as_stream(sn_stream_t s) { return reinterpret_cast<cudaStrea
             return 3;                                                                          \
         }                                                                                      \
         snb::count_launch();                                                                   \
+    } while (0)
+
+// launch + event pair around it when timing is on + launch-error check
+#define SN_LAUNCH(name, stream, ...)        \
+    do {                                    \
+        snb::timing_begin(name, stream);    \
+        __VA_ARGS__;                        \
+        snb::timing_end(stream);            \
+        SN_CHECK_LAUNCH(name);              \
     } while (0)
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -112,10 +112,12 @@ inline int gemm_f32(bool ta, bool tb, int M, int N, int K, float alpha, const fl
         grid.z = ceil_div(K, kslice);
         if (grid.z < 2) { grid.z = 2; }
     }
+    snb::timing_begin("gemm_f32_kernel", stream);
     if (!ta && !tb) gemm_f32_kernel<false, false><<<grid, G_THREADS, 0, stream>>>(M, N, K, kslice, alpha, A, lda, B, ldb, beta, C, ldc, bias);
     else if (!ta && tb) gemm_f32_kernel<false, true><<<grid, G_THREADS, 0, stream>>>(M, N, K, kslice, alpha, A, lda, B, ldb, beta, C, ldc, bias);
     else if (ta && !tb) gemm_f32_kernel<true, false><<<grid, G_THREADS, 0, stream>>>(M, N, K, kslice, alpha, A, lda, B, ldb, beta, C, ldc, bias);
     else gemm_f32_kernel<true, true><<<grid, G_THREADS, 0, stream>>>(M, N, K, kslice, alpha, A, lda, B, ldb, beta, C, ldc, bias);
+    snb::timing_end(stream);
     SN_CHECK_LAUNCH("gemm_f32_kernel");
     return 0;
 }

@@ -304,8 +304,7 @@ inline int gemm_bf16_tc(int M, int N, int K, const void* A, long lda, const void
     SN_CHECK_ARG(EPI == ATOMIC_F32 || grid.z == 1, "split-K needs the atomic epilogue");
     constexpr size_t smem = smem_bytes<BN>();
     SN_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, EPI, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gemm_bf16_tc_kernel<BN, EPI, MN><<<grid, THREADS, smem, stream>>>(ma, mb, args);
-    SN_CHECK_LAUNCH("gemm_bf16_tc_kernel");
+    SN_LAUNCH("gemm_bf16_tc_kernel", stream, gemm_bf16_tc_kernel<BN, EPI, MN><<<grid, THREADS, smem, stream>>>(ma, mb, args));
     return 0;
 }
 

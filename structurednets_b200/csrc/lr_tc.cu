@@ -62,8 +62,7 @@ __global__ void colsum_bf16_kernel(const bf16* __restrict__ M, long ld, long row
 
 int transpose_bf16(const bf16* src, long lds, bf16* dst, long ldd, long rows, int cols, cudaStream_t st) {
     dim3 grid(snb::ceil_div(cols, 32), (unsigned)((rows + 31) / 32)), block(32, 8);
-    transpose_bf16_kernel<<<grid, block, 0, st>>>(src, lds, dst, ldd, rows, cols);
-    SN_CHECK_LAUNCH("transpose_bf16_kernel");
+    SN_LAUNCH("transpose_bf16_kernel", st, transpose_bf16_kernel<<<grid, block, 0, st>>>(src, lds, dst, ldd, rows, cols));
     return 0;
 }
 
@@ -82,9 +81,8 @@ extern "C" {
 int sn_lr_tc_cast_params(const float* left, const float* right, void* left_bf16, void* left_t_bf16, int64_t lt_ld, void* right_bf16,
                          int in_dim, int out_dim, int rank, sn_stream_t stream) {
     SN_CHECK_ARG(left && right && left_bf16 && left_t_bf16 && right_bf16, "lr_tc_cast_params: NULL buffer");
-    lr_cast_params_kernel<<<296, 256, 0, snb::as_stream(stream)>>>(left, right, (bf16*)left_bf16, (bf16*)left_t_bf16, (bf16*)right_bf16, out_dim, rank,
-                                                                 in_dim, (int)lt_ld);
-    SN_CHECK_LAUNCH("lr_cast_params_kernel");
+    SN_LAUNCH("lr_cast_params_kernel", snb::as_stream(stream), lr_cast_params_kernel<<<296, 256, 0, snb::as_stream(stream)>>>(left, right, (bf16*)left_bf16, (bf16*)left_t_bf16, (bf16*)right_bf16, out_dim, rank,
+                                                                 in_dim, (int)lt_ld));
     return 0;
 }
 
@@ -114,8 +112,7 @@ int sn_lr_tc_backward(const void* x, int64_t ldx, const void* grad_y, int64_t ld
     if (int rc = gemm_bf16_tc<64, STORE_BF16>((int)B, rank, out_dim, grad_y, ldgy, left_t_bf16, lt_ld, ghid, rank, nullptr, 1.f, 1, st)) return rc;
     if (grad_bias) {
         dim3 grid(snb::ceil_div(out_dim, 128), (unsigned)((B + 255) / 256));
-        colsum_bf16_kernel<<<grid, 128, 0, st>>>((const bf16*)grad_y, ldgy, B, out_dim, grad_bias);
-        SN_CHECK_LAUNCH("colsum_bf16_kernel");
+        SN_LAUNCH("colsum_bf16_kernel", st, colsum_bf16_kernel<<<grid, 128, 0, st>>>((const bf16*)grad_y, ldgy, B, out_dim, grad_bias));
     }
     const bool mn_ok = (rank % 64 == 0);   // MN-major operands are fetched in 64-element blocks along M / N
     if (grad_left) {   // dL += gy^T h

@@ -892,8 +892,7 @@ static int launch_fwd(const sn_sss_plan* p, const Geom& g, const float* packed, 
     }
     long tile = (long)PAIRS * g.nsw;
     unsigned grid = (unsigned)((B + tile - 1) / tile);
-    sss_fwd_kernel<PAIRS, RP4T, NSWPT><<<grid, PAIRS * 64, smem, st>>>(*p, packed, x, (long)ldx, y, (long)ldy, bias, ckpt, (long)B, g, sm, aligned);
-    SN_CHECK_LAUNCH("sss_fwd_kernel");
+    SN_LAUNCH("sss_fwd_kernel", st, sss_fwd_kernel<PAIRS, RP4T, NSWPT><<<grid, PAIRS * 64, smem, st>>>(*p, packed, x, (long)ldx, y, (long)ldy, bias, ckpt, (long)B, g, sm, aligned));
     return 0;
 }
 
@@ -966,8 +965,10 @@ int sn_sss_backward(const sn_sss_plan* p, const float* packed, const float* x, i
     SN_CHECK_CUDA(cudaMemsetAsync(workspace, 0, sn_sss_backward_workspace_floats(p) * sizeof(float), st));
     long tile = (long)BWD_CONS * g.nsw;
     dim3 grid((unsigned)((B + tile - 1) / tile), 2);
+    snb::timing_begin("sss_bwd_kernel", st);
     if (fast) sss_bwd_kernel<5, 7, 52><<<grid, BWD_THREADS, smem, st>>>(*p, packed, x, (long)ldx, grad_y, (long)ldgy, ckpt, workspace, grad_bias, (long)B, g, sm);
     else sss_bwd_kernel<0, 0, 0><<<grid, BWD_THREADS, smem, st>>>(*p, packed, x, (long)ldx, grad_y, (long)ldgy, ckpt, workspace, grad_bias, (long)B, g, sm);
+    snb::timing_end(st);
     SN_CHECK_LAUNCH("sss_bwd_kernel");
     sss_unpack_grad_kernel<<<2 * p->nb_states, 128, 0, st>>>(p->stages, 2 * p->nb_states, p->rows_pad, p->k_pad, workspace, grad_params);
     SN_CHECK_LAUNCH("sss_unpack_grad_kernel");

@@ -68,32 +68,36 @@ __device__ __forceinline__ void stage_load_async(StageSm& sm, const sn_sss_stage
     for (int i = tid; i < n_yu; i += nthreads) cp_async4(sm.yu + i, params + st.off_yu + i);
 }
 
-// One stage applied to one column of the chunk's "identity input": v (state entering) -> yv (the stage's outputs), v (state leaving)
+// One stage applied to one column of the chunk's "identity input": v (state entering) -> yv (the stage's outputs, if WITH_Y), v (state leaving).
+// Loops over the (few) outputs / state rows leave early instead of running 16 predicated-off iterations.
+template <bool WITH_Y>
 __device__ __forceinline__ void stage_apply(const sn_sss_stage& st, const StageSm& sm, float (&v)[DS], float (&yv)[SOUT_MAX], bool mine, int local) {
     const int d_in = st.d_in, d_out = st.d_out;
+    if (WITH_Y) {
 #pragma unroll
-    for (int r = 0; r < SOUT_MAX; ++r) {
-        float acc = 0.f;
-        if (r < st.out_dim) {
+        for (int r = 0; r < SOUT_MAX; ++r) {
+            if (r >= st.out_dim) break;
+            float acc = 0.f;
             const float* ys = sm.ys + r * d_in;
 #pragma unroll
             for (int a = 0; a < DS; ++a)
                 if (a < d_in) acc = fmaf(ys[a], v[a], acc);
             if (mine && st.off_yu >= 0) acc += sm.yu[r * st.in_dim + local];
+            yv[r] = acc;
         }
-        yv[r] = acc;
     }
     float nv[DS];
 #pragma unroll
-    for (int b = 0; b < DS; ++b) {
-        float acc = 0.f;
-        if (b < d_out) {
-            const float* ss = sm.ss + b * d_in;
+    for (int b = 0; b < DS; ++b) nv[b] = 0.f;
 #pragma unroll
-            for (int a = 0; a < DS; ++a)
-                if (a < d_in) acc = fmaf(ss[a], v[a], acc);
-            if (mine) acc += sm.su[b * st.in_dim + local];
-        }
+    for (int b = 0; b < DS; ++b) {
+        if (b >= d_out) break;
+        float acc = 0.f;
+        const float* ss = sm.ss + b * d_in;
+#pragma unroll
+        for (int a = 0; a < DS; ++a)
+            if (a < d_in) acc = fmaf(ss[a], v[a], acc);
+        if (mine) acc += sm.su[b * st.in_dim + local];
         nv[b] = acc;
     }
 #pragma unroll
@@ -144,17 +148,16 @@ sss_tc_build_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss
         const sn_sss_stage& st = sdesc[i];
         const int local = col - st.in_off;
         const bool mine = is_in && local >= 0 && local < st.in_dim;
-        stage_apply(st, sm[i & 1], v, yv, mine, local);
+        stage_apply<true>(st, sm[i & 1], v, yv, mine, local);
         const int rbase = st.out_off - c.row0;
         const bool wr = dir == 0 ? (activated || mine) : activated;
 #pragma unroll
         for (int r = 0; r < SOUT_MAX; ++r) {
-            if (r < st.out_dim) {
-                if (is_in) {
-                    if (wr) store_hi_lo(W, rbase + r, t, yv[r]);
-                } else {
-                    Omat[(rbase + r) * DS + sidx] = yv[r];
-                }
+            if (r >= st.out_dim) break;
+            if (is_in) {
+                if (wr) store_hi_lo(W, rbase + r, t, yv[r]);
+            } else {
+                Omat[(rbase + r) * DS + sidx] = yv[r];
             }
         }
         if (mine) activated = true;
@@ -167,6 +170,17 @@ sss_tc_build_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss
     }
 }
 
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);   // round to nearest tf32 (ties away), finite inputs
+    lo = x - hi;
+}
+__device__ __forceinline__ void split_tf32(const float4& v, float4& h, float4& l) {
+    split_tf32(v.x, h.x, l.x);
+    split_tf32(v.y, h.y, l.y);
+    split_tf32(v.z, h.z, l.z);
+    split_tf32(v.w, h.w, l.w);
+}
+
 // ------------------------------------------------------------------------------------------
 // 2. local GEMM: [yloc | r | r'](128 samples x 64) = u_j (128 x 32 nkb) * W_j^T, 3xTF32
 //    warp 0: TMA producer | warp 1: TMEM alloc + MMA issuer | warps 2-5: hi/lo converters | warps 6-9: epilogue
@@ -175,7 +189,9 @@ constexpr int G1_THREADS = 320;
 constexpr int G1_STAGES = 4;
 constexpr int G1_TILE_BYTES = 128 * 128;              // 128 rows x 128 B
 constexpr int G1_STAGE_BYTES = 3 * G1_TILE_BYTES;     // x (hi in place) | x_lo | W
-constexpr size_t G1_SMEM = (size_t)G1_STAGES * G1_STAGE_BYTES + 1024 + 256;
+constexpr int G1_PF = 3;                             // L2 prefetch distance in work items
+constexpr int G1_MAX_CHUNKS = 1024;
+constexpr size_t G1_SMEM = (size_t)G1_STAGES * G1_STAGE_BYTES + 1024 + 256 + G1_MAX_CHUNKS * 8;
 
 __global__ void __launch_bounds__(G1_THREADS, 1)
 sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -196,6 +212,8 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
     const long w1 = w0 + per < total ? w0 + per : total;
     if (w0 >= w1) return;
 
+    int2* ctab = reinterpret_cast<int2*>(smem + G1_STAGES * G1_STAGE_BYTES + 256);   // (col0, nkb) per chunk: no global load on the issue paths
+    for (int i = threadIdx.x; i < nchunks; i += G1_THREADS) ctab[i] = make_int2(chunks[i].col0, chunks[i].nkb);
     if (threadIdx.x == 0) {
         for (int s = 0; s < G1_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(conv + s, 128); mbar_init(empty + s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, 128); }
@@ -211,10 +229,18 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
 
     if (warp == 0) {
         if (lane == 0) {
+            // x boxes are pulled into L2 G1_PF items ahead of the shared-memory pipeline: 4 stages alone do not cover the HBM latency
+            auto prefetch_item = [&](long w) {
+                const int tile = (int)(w / nchunks), ch = (int)(w % nchunks);
+                const int2 c = ctab[ch];
+                for (int kb = 0; kb < c.y; ++kb) tma_prefetch_l2_2d(&map_x, c.x + kb * KBW, tile * 128);
+            };
+            for (long w = w0; w < w0 + G1_PF && w < w1; ++w) prefetch_item(w);
             uint32_t it = 0;
             for (long w = w0; w < w1; ++w) {
+                if (w + G1_PF < w1) prefetch_item(w + G1_PF);
                 const int tile = (int)(w / nchunks), ch = (int)(w % nchunks);
-                const int nkb = chunks[ch].nkb, col0 = chunks[ch].col0;
+                const int nkb = ctab[ch].y, col0 = ctab[ch].x;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const uint32_t s = it % G1_STAGES, round = it / G1_STAGES;
                     if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
@@ -232,7 +258,7 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
             uint32_t it = 0, ai = 0;
             for (long w = w0; w < w1; ++w, ++ai) {
                 const int ch = (int)(w % nchunks);
-                const int nkb = chunks[ch].nkb;
+                const int nkb = ctab[ch].y;
                 const uint32_t b = ai & 1;
                 if (ai >= 2) mbar_wait(acc_empty + b, ((ai >> 1) - 1) & 1);
                 tc_fence_after();
@@ -260,7 +286,7 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
         const int ct = threadIdx.x - 64;
         uint32_t it = 0;
         for (long w = w0; w < w1; ++w) {
-            const int nkb = chunks[(int)(w % nchunks)].nkb;
+            const int nkb = ctab[(int)(w % nchunks)].y;
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const uint32_t s = it % G1_STAGES, round = it / G1_STAGES;
                 mbar_wait(full + s, round & 1);
@@ -272,8 +298,7 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     float4 h, l;
-                    h.x = tf32_hi(v[i].x); h.y = tf32_hi(v[i].y); h.z = tf32_hi(v[i].z); h.w = tf32_hi(v[i].w);
-                    l.x = v[i].x - h.x; l.y = v[i].y - h.y; l.z = v[i].z - h.z; l.w = v[i].w - h.w;
+                    split_tf32(v[i], h, l);
                     xh[ct + 128 * i] = h;
                     xl[ct + 128 * i] = l;
                 }
@@ -320,7 +345,7 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
 }
 
 // ------------------------------------------------------------------------------------------
-// 3. forward chunk scans + output fix-up; one thread per sample
+// shared-memory matrix-vector helpers of the SIMT scans (thread = sample)
 // ------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 128;
 
@@ -344,110 +369,6 @@ __device__ __forceinline__ void matvec_acc(const float4* __restrict__ M, const f
         out[b] = acc;
     }
 }
-// out[a] += sum_b M[b][a] w[b]   (transposed application)
-template <int ROWS>
-__device__ __forceinline__ void matvec_t_acc(const float4* __restrict__ M, const float* w, float (&out)[DS]) {
-#pragma unroll
-    for (int b = 0; b < ROWS; ++b) {
-        const float wb = w[b];
-#pragma unroll
-        for (int a4 = 0; a4 < DS / 4; ++a4) {
-            const float4 m = M[b * (DS / 4) + a4];
-            out[4 * a4] = fmaf(m.x, wb, out[4 * a4]);
-            out[4 * a4 + 1] = fmaf(m.y, wb, out[4 * a4 + 1]);
-            out[4 * a4 + 2] = fmaf(m.z, wb, out[4 * a4 + 2]);
-            out[4 * a4 + 3] = fmaf(m.w, wb, out[4 * a4 + 3]);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS)
-sss_tc_scan_fwd_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, const float* __restrict__ SCall, const float* __restrict__ rbuf,
-                       float* __restrict__ S, float* __restrict__ y, long ldy, const float* __restrict__ bias, long B, int aligned) {
-    __shared__ float4 sc[SCF / 4];
-    const long row = (long)blockIdx.x * SCAN_THREADS + threadIdx.x;
-    const bool valid = row < B;
-    // anticausal states, top chunk first: S[j][row][16..31] = e_{j+1} (the state entering chunk j from above)
-    float e[DS];
-#pragma unroll
-    for (int a = 0; a < DS; ++a) e[a] = 0.f;
-    for (int j = nchunks - 1; j >= 0; --j) {
-        __syncthreads();
-        load_sc(sc, SCall + (size_t)j * SCF + DS * DS, DS * DS / 4);   // Phi'
-        __syncthreads();
-        if (valid) {
-            const size_t base = (size_t)j * B + row;
-            float4* sdst = reinterpret_cast<float4*>(S + base * 32 + DS);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) sdst[i] = make_float4(e[4 * i], e[4 * i + 1], e[4 * i + 2], e[4 * i + 3]);
-            float ne[DS];
-            const float4* rp = reinterpret_cast<const float4*>(rbuf + base * 64 + 48);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 r4 = __ldg(rp + i);
-                ne[4 * i] = r4.x; ne[4 * i + 1] = r4.y; ne[4 * i + 2] = r4.z; ne[4 * i + 3] = r4.w;
-            }
-            matvec_acc<DS>(sc, e, ne);
-#pragma unroll
-            for (int a = 0; a < DS; ++a) e[a] = ne[a];
-        }
-    }
-    // causal states bottom up + outputs
-    float s[DS];
-#pragma unroll
-    for (int a = 0; a < DS; ++a) s[a] = 0.f;
-    for (int j = 0; j < nchunks; ++j) {
-        __syncthreads();
-        load_sc(sc, SCall + (size_t)j * SCF, SCF / 4);
-        __syncthreads();
-        if (valid) {
-            const sn_sss_tc_chunk c = chunks[j];
-            const size_t base = (size_t)j * B + row;
-            float4* sdst = reinterpret_cast<float4*>(S + base * 32);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) sdst[i] = make_float4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 e4 = sdst[4 + i];
-                e[4 * i] = e4.x; e[4 * i + 1] = e4.y; e[4 * i + 2] = e4.z; e[4 * i + 3] = e4.w;
-            }
-            const float4* rp = reinterpret_cast<const float4*>(rbuf + base * 64);
-            float* yrow = y + row * ldy + c.row0;
-            const float4* Om = sc + 2 * DS * DS / 4;
-            const float4* Opm = Om + PO * DS / 4;
-#pragma unroll
-            for (int g = 0; g < PO / 4; ++g) {
-                if (4 * g < c.nrows) {
-                    const float4 yl = __ldg(rp + g);
-                    float acc[4] = {yl.x, yl.y, yl.z, yl.w};
-                    matvec_acc<4>(Om + g * 4 * (DS / 4), s, acc);
-                    matvec_acc<4>(Opm + g * 4 * (DS / 4), e, acc);
-                    if (aligned && 4 * g + 4 <= c.nrows) {
-                        if (bias != nullptr) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c.row0 + 4 * g));
-                            acc[0] += b4.x; acc[1] += b4.y; acc[2] += b4.z; acc[3] += b4.w;
-                        }
-                        *reinterpret_cast<float4*>(yrow + 4 * g) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (4 * g + i < c.nrows) yrow[4 * g + i] = acc[i] + (bias != nullptr ? __ldg(bias + c.row0 + 4 * g + i) : 0.f);
-                    }
-                }
-            }
-            float ns[DS];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 r4 = __ldg(rp + 8 + i);
-                ns[4 * i] = r4.x; ns[4 * i + 1] = r4.y; ns[4 * i + 2] = r4.z; ns[4 * i + 3] = r4.w;
-            }
-            matvec_acc<DS>(sc, s, ns);
-#pragma unroll
-            for (int a = 0; a < DS; ++a) s[a] = ns[a];
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // 2+3 fused (large batches): one CTA walks whole 128-sample tiles chunk by chunk, so the chunk-level scans run in the
 //    epilogue while the tensor core works on the next chunk -- no [yloc | r | r'] round trip through HBM.
@@ -461,17 +382,6 @@ constexpr int F_SC_HALF = DS * DS + PO * DS + PO;   // 800 floats: one direction
 constexpr size_t F_SMEM = (size_t)G1_STAGES * G1_STAGE_BYTES + 256 + F_MAX_CHUNKS * 16 + 4 * F_SC_HALF * 4 + 1024;
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);   // round to nearest tf32 (ties away), finite inputs
-    lo = x - hi;
-}
-__device__ __forceinline__ void split_tf32(const float4& v, float4& h, float4& l) {
-    split_tf32(v.x, h.x, l.x);
-    split_tf32(v.y, h.y, l.y);
-    split_tf32(v.z, h.z, l.z);
-    split_tf32(v.w, h.w, l.w);
-}
 
 // cooperative copy of one direction's {Phi (64 float4), O (128 float4)} by 128 threads: registers first (latency hidden behind
 // the barrier wait that follows), shared memory later
@@ -754,94 +664,6 @@ sss_tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 }
 
 // ------------------------------------------------------------------------------------------
-// 4. adjoint chunk scans.  L[j][row][0..15] = lambda_{j+1} (adjoint of the causal state leaving chunk j),
-//    L[j][row][16..31] = mu_j (adjoint of the anticausal state leaving chunk j).  grad_bias += column sums of gy.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_gy(const float* __restrict__ gy, long ldgy, long row, const sn_sss_tc_chunk& c, bool valid, int aligned,
-                                        float (&g)[PO]) {
-    const float* src = gy + row * ldgy + c.row0;
-#pragma unroll
-    for (int q = 0; q < PO / 4; ++q) {
-        if (valid && aligned && 4 * q + 4 <= c.nrows) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(src + 4 * q));
-            g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) g[4 * q + i] = (valid && 4 * q + i < c.nrows) ? __ldg(src + 4 * q + i) : 0.f;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS)
-sss_tc_scan_bwd_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, const float* __restrict__ SCall, const float* __restrict__ gy,
-                       long ldgy, float* __restrict__ L, float* __restrict__ gbias, long B, int aligned) {
-    __shared__ float4 sc[(DS * DS + PO * DS) / 4];
-    const long row = (long)blockIdx.x * SCAN_THREADS + threadIdx.x;
-    const bool valid = row < B;
-    const int lane = threadIdx.x & 31;
-    float lam[DS], g[PO];
-#pragma unroll
-    for (int a = 0; a < DS; ++a) lam[a] = 0.f;
-    for (int j = nchunks - 1; j >= 0; --j) {
-        __syncthreads();
-        load_sc(sc, SCall + (size_t)j * SCF, DS * DS / 4);                                       // Phi
-        load_sc(sc + DS * DS / 4, SCall + (size_t)j * SCF + 2 * DS * DS, PO * DS / 4);           // O
-        __syncthreads();
-        const sn_sss_tc_chunk c = chunks[j];
-        load_gy(gy, ldgy, row, c, valid, aligned, g);
-        if (valid) {
-            float4* dst = reinterpret_cast<float4*>(L + ((size_t)j * B + row) * 32);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_float4(lam[4 * i], lam[4 * i + 1], lam[4 * i + 2], lam[4 * i + 3]);
-            float nl[DS];
-#pragma unroll
-            for (int a = 0; a < DS; ++a) nl[a] = 0.f;
-            matvec_t_acc<DS>(sc, lam, nl);
-            matvec_t_acc<PO>(sc + DS * DS / 4, g, nl);
-#pragma unroll
-            for (int a = 0; a < DS; ++a) lam[a] = nl[a];
-        }
-    }
-    float mu[DS];
-#pragma unroll
-    for (int a = 0; a < DS; ++a) mu[a] = 0.f;
-    for (int j = 0; j < nchunks; ++j) {
-        __syncthreads();
-        load_sc(sc, SCall + (size_t)j * SCF + DS * DS, DS * DS / 4);                             // Phi'
-        load_sc(sc + DS * DS / 4, SCall + (size_t)j * SCF + 2 * DS * DS + PO * DS, PO * DS / 4);  // O'
-        __syncthreads();
-        const sn_sss_tc_chunk c = chunks[j];
-        load_gy(gy, ldgy, row, c, valid, aligned, g);
-        if (valid) {
-            float4* dst = reinterpret_cast<float4*>(L + ((size_t)j * B + row) * 32 + DS);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_float4(mu[4 * i], mu[4 * i + 1], mu[4 * i + 2], mu[4 * i + 3]);
-            float nm[DS];
-#pragma unroll
-            for (int a = 0; a < DS; ++a) nm[a] = 0.f;
-            matvec_t_acc<DS>(sc, mu, nm);
-            matvec_t_acc<PO>(sc + DS * DS / 4, g, nm);
-#pragma unroll
-            for (int a = 0; a < DS; ++a) mu[a] = nm[a];
-        }
-        if (gbias != nullptr) {
-            // column sums over the warp's 32 samples: lane l ends up with the sum of column l
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-#pragma unroll
-                for (int i = 0; i < off; ++i) {
-                    const bool up = (lane & off) != 0;
-                    const float send = up ? g[i] : g[i + off];
-                    const float keep = up ? g[i + off] : g[i];
-                    g[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                }
-            }
-            if (lane < c.nrows) atomicAdd(gbias + c.row0 + lane, g[0]);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // 3'/4'. chunk scans, four threads per sample.  The scans are serial in the chunk index, so the only parallelism is across
 //    samples (65 536 threads would leave the SMs latency-bound); here thread q of a quad owns state components 4q..4q+3 (and
 //    output / grad_y columns 8q..8q+7), forms partial matrix-vector products over its own components and the quad combines
@@ -1104,7 +926,7 @@ sss_tc_scan_bwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
 //       rows n < 48: [Whi(n,:) | Whi(n,:)], rows 48 + n: [Wlo(n,:) | 0], W = [O ; Phi] (48 x 16)   -> D[:, n] + D[:, 48 + n]
 //    kind 2/3 = backward lambda/mu, three 32-row sub-tiles: state (Phi^T), grad_y hi part (O^T), grad_y lo part (O^T).
 // ------------------------------------------------------------------------------------------
-constexpr int CH_THREADS = 160;                 // warps 0-3: epilogue (thread = sample), warp 4: TMA + MMA issuer (one lane)
+constexpr int CH_PF = 8;                         // L2 prefetch distance (steps) of the per-sample rows
 constexpr int CW_ROWS = 96;
 constexpr int CW_TILE_FLOATS = CW_ROWS * 32;    // 3072 floats = 12 KB
 constexpr int CW_TILE_BYTES = CW_TILE_FLOATS * 4;
@@ -1154,20 +976,29 @@ __device__ __forceinline__ void store_state_hi_lo(uint8_t* tile, int row, const 
     store_row_sw128(tile, row, v);
 }
 
-// Per-step ring slot (2 slots): coefficient tile (12 KB) + this step's per-sample inputs, all fetched by TMA two steps ahead so
-// that no global load sits between the epilogue threads and their fence.proxy.async (a fence waits for the thread's loads).
-//   forward : `in` = r or r' rows [128][16 floats] (SWIZZLE_64B) and yl = yloc / ytmp rows [128][32] (SWIZZLE_128B)
-//   backward: grad_y rows [128][32] (SWIZZLE_128B)
+// No global memory access sits on the chain: a fence.proxy.async waits for the issuing thread's outstanding loads AND stores,
+// so the epilogue threads (thread = sample) only touch shared memory and TMEM.
+//   * inputs: TMA, two steps ahead, into a 2-slot ring (coefficient tile + this step's per-sample rows); L2 prefetch further ahead
+//   * outputs: each epilogue thread overwrites ITS OWN row of the slot's input areas (same swizzled layout) with the step's
+//     outputs; two writer warps copy the rows to global memory with coalesced stores and then release the slot
+//   forward slot : W 12 KB | `in` = r / r' rows [128][16] (SWIZZLE_64B) -> entering state | yl = yloc / ytmp rows [128][32]
+//                  (SWIZZLE_128B) -> ytmp / y
+//   backward slot: W 8 KB (state sub-tile + grad_y sub-tile) | grad_y rows of the NEXT step [128][32]; checkpoints go through
+//                  a separate single 8 KB staging tile
+constexpr int CH_THREADS = 224;                 // warps 0-3: epilogue (thread = sample), warp 4: TMA + MMA issuer (one lane), warps 5-6: writers
+constexpr int CH_WRITERS = 64;
 struct ChainSmem {
     uint8_t* state;    // 16 KB: [128][state hi 16 | state lo 16], K-major SWIZZLE_128B
     uint8_t* in_hi;    // 16 KB (backward only): grad_y hi parts
     uint8_t* in_lo;    // 16 KB (backward only)
+    uint8_t* lstage;   // 8 KB (backward only): adjoint checkpoints on their way to global memory
     uint8_t* slot[2];
-    uint64_t *full, *empty, *state_ready, *acc_full, *chain_done;
+    uint64_t *full, *out_ready, *slot_free, *state_ready, *acc_full, *chain_done, *lst_ready, *lst_free;
     uint32_t* tmem_slot;
 };
 constexpr int CHF_SLOT = CW_TILE_BYTES + 8192 + 16384;    // W | in (8 KB at +12288) | yl (16 KB at +20480)
-constexpr int CHB_SLOT = CW_TILE_BYTES + 4096 + 16384;    // W | pad | grad_y (16 KB at +16384)
+constexpr int CHB_W_BYTES = 64 * 128;                      // state sub-tile + grad_y sub-tile
+constexpr int CHB_SLOT = CHB_W_BYTES + 16384;              // W | grad_y rows (16 KB at +8192)
 template <bool BWD>
 __device__ __forceinline__ ChainSmem chain_carve(uint8_t* smem_raw) {
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -1175,41 +1006,27 @@ __device__ __forceinline__ ChainSmem chain_carve(uint8_t* smem_raw) {
     c.state = smem;
     c.in_hi = smem + 16384;
     c.in_lo = smem + 32768;
-    uint8_t* s0 = smem + (BWD ? 49152 : 16384);
+    c.lstage = smem + 49152;
+    uint8_t* s0 = smem + (BWD ? 57344 : 16384);
     constexpr int SLOT = BWD ? CHB_SLOT : CHF_SLOT;
     c.slot[0] = s0;
     c.slot[1] = s0 + SLOT;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s0 + 2 * SLOT);
     c.full = bars;
-    c.empty = bars + 2;
-    c.state_ready = bars + 4;
-    c.acc_full = bars + 5;
-    c.chain_done = bars + 6;
-    c.tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    c.out_ready = bars + 2;
+    c.slot_free = bars + 4;
+    c.state_ready = bars + 6;
+    c.acc_full = bars + 7;
+    c.chain_done = bars + 8;
+    c.lst_ready = bars + 9;
+    c.lst_free = bars + 10;
+    c.tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
     return c;
 }
 constexpr size_t CHF_SMEM = 16384 + 2 * CHF_SLOT + 128 + 1024;
-constexpr size_t CHB_SMEM = 49152 + 2 * CHB_SLOT + 128 + 1024;
+constexpr size_t CHB_SMEM = 57344 + 2 * CHB_SLOT + 128 + 1024;
 
-// the MMAs of one step (issuer thread)
-template <bool BWD>
-__device__ __forceinline__ void chain_mma(const ChainSmem& sm, const uint8_t* w, uint32_t tmem) {
-    constexpr uint32_t idesc = BWD ? idesc_tf32(128, 32, false, false) : idesc_tf32(128, 96, false, false);
-    const uint64_t dst = desc_kmajor_sw128(sm.state);
-    const uint64_t dw = desc_kmajor_sw128(w);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) mma_tf32(tmem, dst + 2 * k, dw + 2 * k, idesc, k ? 1u : 0u);
-    if (BWD) {
-        const uint64_t dih = desc_kmajor_sw128(sm.in_hi), dil = desc_kmajor_sw128(sm.in_lo);
-        const uint64_t dw1 = desc_kmajor_sw128(w + 4096), dw2 = desc_kmajor_sw128(w + 8192);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) mma_tf32(tmem, dih + 2 * k, dw1 + 2 * k, idesc, 1u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) mma_tf32(tmem, dil + 2 * k, dw2 + 2 * k, idesc, 1u);
-    }
-}
-
-// row r of a [128][32 floats] SWIZZLE_128B box / a [128][16 floats] SWIZZLE_64B box, as TMA wrote it
+// row r of a [128][32 floats] SWIZZLE_128B tile / a [128][16 floats] SWIZZLE_64B tile, in the layout TMA writes
 __device__ __forceinline__ void load_row_sw128(const uint8_t* tile, int r, float (&v)[32]) {
     const uint8_t* base = tile + r * 128;
 #pragma unroll
@@ -1226,10 +1043,23 @@ __device__ __forceinline__ void load_row_sw64(const uint8_t* tile, int r, float 
         v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
     }
 }
+__device__ __forceinline__ void store_row_sw64(uint8_t* tile, int r, const float (&v)[16]) {
+    uint8_t* base = tile + r * 64;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<float4*>(base + ((c ^ ((r >> 1) & 3)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+// writer side: 16-byte chunk i of a tile (i = row * chunks_per_row + c), coalesced over consecutive threads
+__device__ __forceinline__ float4 read_chunk_sw128(const uint8_t* tile, int row, int c) {
+    return *reinterpret_cast<const float4*>(tile + row * 128 + ((c ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ float4 read_chunk_sw64(const uint8_t* tile, int row, int c) {
+    return *reinterpret_cast<const float4*>(tile + row * 64 + ((c ^ ((row >> 1) & 3)) << 4));
+}
 
-// forward: steps 0..nc-1 = anticausal chain over chunks nc-1..0 (writes e_{j+1}, ytmp = yloc + O' e into rbuf),
-//          steps nc..2nc-1 = causal chain over chunks 0..nc-1 (writes s_j, y = ytmp + O s + bias)
-__global__ void __launch_bounds__(CH_THREADS)
+// forward: steps 0..nc-1 = anticausal chain over chunks nc-1..0 (saves e_{j+1}; ytmp = yloc + O' e goes back into rbuf),
+//          steps nc..2nc-1 = causal chain over chunks 0..nc-1 (saves s_j; y = ytmp + O s + bias)
+__global__ void __launch_bounds__(CH_THREADS, 2)
 sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_yl,
                         const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, float* __restrict__ rbuf, float* __restrict__ S, float* __restrict__ y,
                         long ldy, const float* __restrict__ bias, long B, int aligned) {
@@ -1238,8 +1068,8 @@ sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nsteps = 2 * nchunks;
     if (threadIdx.x == 0) {
-        mbar_init(sm.full, 1); mbar_init(sm.full + 1, 1); mbar_init(sm.empty, 129); mbar_init(sm.empty + 1, 129);
-        mbar_init(sm.state_ready, 128); mbar_init(sm.acc_full, 1); mbar_init(sm.chain_done, 128);
+        for (int i = 0; i < 2; ++i) { mbar_init(sm.full + i, 1); mbar_init(sm.out_ready + i, 128); mbar_init(sm.slot_free + i, CH_WRITERS); }
+        mbar_init(sm.state_ready, 128); mbar_init(sm.acc_full, 1); mbar_init(sm.chain_done, CH_WRITERS);
         mbar_fence_init();
         tma_prefetch_desc(&map_cw);
         tma_prefetch_desc(&map_in);
@@ -1258,39 +1088,52 @@ sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
                 const int s = t & 1, j = chunk_of(t);
                 const bool anti = t < nchunks;
                 uint8_t* slot = sm.slot[s];
+                const int rowc = (int)((long)j * B + (long)blockIdx.x * 128);
                 mbar_expect_tx(sm.full + s, CW_TILE_BYTES + 8192 + 16384);
                 tma_load_2d(slot, &map_cw, 0, (j * 4 + (anti ? 1 : 0)) * CW_ROWS, sm.full + s);
-                tma_load_2d(slot + CW_TILE_BYTES, &map_in, anti ? 48 : 32, (int)((long)j * B + (long)blockIdx.x * 128), sm.full + s);
-                tma_load_2d(slot + CW_TILE_BYTES + 8192, &map_yl, 0, (int)((long)j * B + (long)blockIdx.x * 128), sm.full + s);
+                tma_load_2d(slot + CW_TILE_BYTES, &map_in, anti ? 48 : 32, rowc, sm.full + s);
+                tma_load_2d(slot + CW_TILE_BYTES + 8192, &map_yl, 0, rowc, sm.full + s);
             };
-            // the second chain (steps >= nchunks) re-reads through TMA the ytmp rows the first chain wrote with ordinary stores, so
-            // its loads may only be issued once the first chain's last epilogue has fenced them (chain_done): the ring drains once
+            auto prefetch = [&](int t) {   // into L2 only
+                const int j = chunk_of(t);
+                const int rowc = (int)((long)j * B + (long)blockIdx.x * 128);
+                tma_prefetch_l2_2d(&map_in, t < nchunks ? 48 : 32, rowc);
+                tma_prefetch_l2_2d(&map_yl, 0, rowc);
+            };
+            for (int t = 0; t < CH_PF && t < nsteps; ++t) prefetch(t);
+            // the second chain (steps >= nchunks) re-reads through TMA the ytmp rows the writers stored, so its first load waits
+            // for chain_done (the writers' last ytmp stores + their proxy fence)
             for (int t = 0; t < 2 && t < nchunks; ++t) issue(t);
+            constexpr uint32_t idesc = idesc_tf32(128, 96, false, false);
             for (int t = 0; t < nsteps; ++t) {
                 const int s = t & 1;
+                if (t + CH_PF < nsteps) prefetch(t + CH_PF);
                 mbar_wait(sm.full + s, (t >> 1) & 1);
                 mbar_wait(sm.state_ready, t & 1);
                 tc_fence_after();
-                chain_mma<false>(sm, sm.slot[s], tmem);
+                const uint64_t dst = desc_kmajor_sw128(sm.state);
+                const uint64_t dw = desc_kmajor_sw128(sm.slot[s]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_tf32(tmem, dst + 2 * k, dw + 2 * k, idesc, k ? 1u : 0u);
                 umma_commit(sm.acc_full);
-                umma_commit(sm.empty + s);           // 1 of 129 arrivals: the MMAs have read the coefficient tile
-                if (t == nchunks - 1) {
+                // refill the OTHER slot (step t - 1's) with step t + 1, once the writers have copied step t - 1's outputs out of it
+                const int q = t + 1;
+                if (q >= 2 && q < nsteps) {
+                    mbar_wait(sm.slot_free + (q & 1), ((q - 2) >> 1) & 1);
+                    if (q == nchunks) {
+                        mbar_wait(sm.chain_done, 0);
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                    }
+                    issue(q);
+                } else if (q < 2 && q < nsteps && q >= nchunks) {   // nchunks == 1: step 1 belongs to the second chain
                     mbar_wait(sm.chain_done, 0);
                     asm volatile("fence.proxy.async;" ::: "memory");
-                    for (int q = nchunks; q < nchunks + 2 && q < nsteps; ++q) {
-                        if (q >= 2) mbar_wait(sm.empty + (q & 1), ((q - 2) >> 1) & 1);
-                        issue(q);
-                    }
-                } else if (t + 2 < nsteps && (t + 2 < nchunks || t >= nchunks)) {
-                    mbar_wait(sm.empty + s, (t >> 1) & 1);   // + the 128 epilogue threads have read their inputs
-                    issue(t + 2);
+                    issue(q);
                 }
             }
         }
-    } else {
+    } else if (warp < 4) {
         const int r = threadIdx.x;                         // TMEM lane = tile row
-        const long row = (long)blockIdx.x * 128 + r;
-        const bool valid = row < B;
         const uint32_t tacc = tmem + ((uint32_t)(warp * 32) << 16);
         float st[DS];
 #pragma unroll
@@ -1301,17 +1144,12 @@ sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
         for (int t = 0; t < nsteps; ++t) {
             const bool anti = t < nchunks;
             const int j = chunk_of(t), s = t & 1;
-            // this step's entering state goes to the checkpoint buffer (kept for the backward)
-            if (valid) {
-                float4* sp = reinterpret_cast<float4*>(S + ((size_t)j * B + row) * 32 + (anti ? DS : 0));
-#pragma unroll
-                for (int i = 0; i < 4; ++i) sp[i] = make_float4(st[4 * i], st[4 * i + 1], st[4 * i + 2], st[4 * i + 3]);
-            }
+            uint8_t* slot = sm.slot[s];
             mbar_wait(sm.full + s, (t >> 1) & 1);
             float in[DS], yl[PO];
-            load_row_sw64(sm.slot[s] + CW_TILE_BYTES, r, in);
-            load_row_sw128(sm.slot[s] + CW_TILE_BYTES + 8192, r, yl);
-            mbar_arrive(sm.empty + s);
+            load_row_sw64(slot + CW_TILE_BYTES, r, in);
+            load_row_sw128(slot + CW_TILE_BYTES + 8192, r, yl);
+            store_row_sw64(slot + CW_TILE_BYTES, r, st);     // the state entering this step (checkpoint for the backward)
             mbar_wait(sm.acc_full, t & 1);
             tc_fence_after();
             // state part first: it is the chain
@@ -1332,45 +1170,64 @@ sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
             store_state_hi_lo(sm.state, r, st);
             fence_async_smem();
             mbar_arrive(sm.state_ready);
-            // outputs, off the chain
+            // outputs, off the chain: into this thread's own row of the slot; the writers take them from there
+            const int row0 = anti ? 0 : chunks[j].row0;
+#pragma unroll
+            for (int c = 0; c < PO; ++c) yl[c] += __uint_as_float(ym[c]) + __uint_as_float(ylo[c]);
+            if (!anti && bias != nullptr) {
+                const int nrows = chunks[j].nrows;
+#pragma unroll
+                for (int c = 0; c < PO; ++c)
+                    if (c < nrows) yl[c] += __ldg(bias + row0 + c);
+            }
+            store_row_sw128(slot + CW_TILE_BYTES + 8192, r, yl);
+            mbar_arrive(sm.out_ready + s);
+        }
+    } else {
+        // writers: rows of step t -> global memory, coalesced; then the slot may be refilled
+        const int wt = threadIdx.x - 160;
+        for (int t = 0; t < nsteps; ++t) {
+            const bool anti = t < nchunks;
+            const int j = chunk_of(t), s = t & 1;
+            const uint8_t* slot = sm.slot[s];
             const sn_sss_tc_chunk c = chunks[j];
-            if (valid) {
-                if (anti) {
-                    float4* dst = reinterpret_cast<float4*>(rbuf + ((size_t)j * B + row) * 64);
+            mbar_wait(sm.out_ready + s, (t >> 1) & 1);
+            float4 sv[8], yv[16];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float4 o;
-                        o.x = yl[4 * i] + (__uint_as_float(ym[4 * i]) + __uint_as_float(ylo[4 * i]));
-                        o.y = yl[4 * i + 1] + (__uint_as_float(ym[4 * i + 1]) + __uint_as_float(ylo[4 * i + 1]));
-                        o.z = yl[4 * i + 2] + (__uint_as_float(ym[4 * i + 2]) + __uint_as_float(ylo[4 * i + 2]));
-                        o.w = yl[4 * i + 3] + (__uint_as_float(ym[4 * i + 3]) + __uint_as_float(ylo[4 * i + 3]));
-                        dst[i] = o;
-                    }
-                } else {
-                    float* yrow = y + row * ldy + c.row0;
+            for (int k = 0; k < 8; ++k) { const int i = k * CH_WRITERS + wt; sv[k] = read_chunk_sw64(slot + CW_TILE_BYTES, i >> 2, i & 3); }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (4 * i < c.nrows) {
-                            float o[4];
+            for (int k = 0; k < 16; ++k) { const int i = k * CH_WRITERS + wt; yv[k] = read_chunk_sw128(slot + CW_TILE_BYTES + 8192, i >> 3, i & 7); }
+            mbar_arrive(sm.slot_free + s);
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) o[e] = yl[4 * i + e] + (__uint_as_float(ym[4 * i + e]) + __uint_as_float(ylo[4 * i + e]));
-                            if (aligned && 4 * i + 4 <= c.nrows) {
-                                if (bias != nullptr) {
-                                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c.row0 + 4 * i));
-                                    o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w;
-                                }
-                                *reinterpret_cast<float4*>(yrow + 4 * i) = make_float4(o[0], o[1], o[2], o[3]);
-                            } else {
+            for (int k = 0; k < 8; ++k) {
+                const int i = k * CH_WRITERS + wt;
+                const long row = (long)blockIdx.x * 128 + (i >> 2);
+                if (row < B) *(reinterpret_cast<float4*>(S + ((size_t)j * B + row) * 32 + (anti ? DS : 0)) + (i & 3)) = sv[k];
+            }
 #pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    if (4 * i + e < c.nrows) yrow[4 * i + e] = o[e] + (bias != nullptr ? __ldg(bias + c.row0 + 4 * i + e) : 0.f);
-                            }
+            for (int k = 0; k < 16; ++k) {
+                const int i = k * CH_WRITERS + wt;
+                const long row = (long)blockIdx.x * 128 + (i >> 3);
+                const int c0 = 4 * (i & 7);
+                if (row < B) {
+                    if (anti) {
+                        *(reinterpret_cast<float4*>(rbuf + ((size_t)j * B + row) * 64) + (i & 7)) = yv[k];
+                    } else if (c0 < c.nrows) {
+                        float* yp = y + row * ldy + c.row0 + c0;
+                        if (aligned && c0 + 4 <= c.nrows) {
+                            *reinterpret_cast<float4*>(yp) = yv[k];
+                        } else {
+                            yp[0] = yv[k].x;
+                            if (c0 + 1 < c.nrows) yp[1] = yv[k].y;
+                            if (c0 + 2 < c.nrows) yp[2] = yv[k].z;
+                            if (c0 + 3 < c.nrows) yp[3] = yv[k].w;
                         }
                     }
                 }
             }
-            if (last_of_chain) {
+            if (t == nchunks - 1) {
                 asm volatile("fence.proxy.async;" ::: "memory");   // ytmp stores -> visible to the TMA reads of the second chain
+                __threadfence();
                 mbar_arrive(sm.chain_done);
             }
         }
@@ -1387,7 +1244,7 @@ sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
 // L[j][row][0..15] = lambda_{j+1}, L[j][row][16..31] = mu_j ; grad_bias += column sums of grad_y (second chain).
 // Ring slot of step t: coefficient tile of step t + the grad_y rows of step t + 1 (the epilogue of step t splits them into the
 // hi / lo operand tiles of step t + 1's MMAs).  Step 0's rows arrive through a prologue load into the (still unused) lo tile.
-__global__ void __launch_bounds__(CH_THREADS)
+__global__ void __launch_bounds__(CH_THREADS, 2)
 sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid_constant__ CUtensorMap map_gy, const sn_sss_tc_chunk* __restrict__ chunks,
                         int nchunks, float* __restrict__ L, float* __restrict__ gbias, long B) {
     extern __shared__ uint8_t smem_raw[];
@@ -1396,8 +1253,9 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nsteps = 2 * nchunks;
     if (threadIdx.x == 0) {
-        mbar_init(sm.full, 1); mbar_init(sm.full + 1, 1); mbar_init(sm.empty, 129); mbar_init(sm.empty + 1, 129);
+        for (int i = 0; i < 2; ++i) { mbar_init(sm.full + i, 1); mbar_init(sm.slot_free + i, 129); }
         mbar_init(sm.state_ready, 128); mbar_init(sm.acc_full, 1); mbar_init(sm.chain_done, 1);
+        mbar_init(sm.lst_ready, 128); mbar_init(sm.lst_free, CH_WRITERS);
         mbar_fence_init();
         tma_prefetch_desc(&map_cw);
         tma_prefetch_desc(&map_gy);
@@ -1416,31 +1274,44 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
                 const int s = t & 1, j = chunk_of(t);
                 uint8_t* slot = sm.slot[s];
                 const bool has_next = t + 1 < nsteps;
-                mbar_expect_tx(sm.full + s, CW_TILE_BYTES + (has_next ? 16384 : 0));
+                mbar_expect_tx(sm.full + s, CHB_W_BYTES + (has_next ? 16384 : 0));
                 tma_load_2d(slot, &map_cw, 0, (j * 4 + (t < nchunks ? 2 : 3)) * CW_ROWS, sm.full + s);
-                if (has_next) tma_load_2d(slot + 16384, &map_gy, chunks[chunk_of(t + 1)].row0, blockIdx.x * 128, sm.full + s);
+                if (has_next) tma_load_2d(slot + CHB_W_BYTES, &map_gy, chunks[chunk_of(t + 1)].row0, blockIdx.x * 128, sm.full + s);
             };
+            auto prefetch = [&](int t) { tma_prefetch_l2_2d(&map_gy, chunks[chunk_of(t)].row0, blockIdx.x * 128); };
+            for (int t = 1; t < CH_PF && t < nsteps; ++t) prefetch(t);
             mbar_expect_tx(sm.chain_done, 16384);
             tma_load_2d(sm.in_lo, &map_gy, chunks[chunk_of(0)].row0, blockIdx.x * 128, sm.chain_done);
             for (int t = 0; t < 2 && t < nsteps; ++t) issue(t);
+            constexpr uint32_t idesc32 = idesc_tf32(128, 32, false, false);
+            constexpr uint32_t idesc16 = idesc_tf32(128, 16, false, false);
             for (int t = 0; t < nsteps; ++t) {
                 const int s = t & 1;
+                if (t + CH_PF < nsteps) prefetch(t + CH_PF);
                 mbar_wait(sm.full + s, (t >> 1) & 1);
                 mbar_wait(sm.state_ready, t & 1);
                 tc_fence_after();
-                chain_mma<true>(sm, sm.slot[s], tmem);
+                const uint64_t dst = desc_kmajor_sw128(sm.state), dih = desc_kmajor_sw128(sm.in_hi), dil = desc_kmajor_sw128(sm.in_lo);
+                const uint64_t dw0 = desc_kmajor_sw128(sm.slot[s]), dw1 = desc_kmajor_sw128(sm.slot[s] + 4096);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_tf32(tmem, dst + 2 * k, dw0 + 2 * k, idesc32, k ? 1u : 0u);   // [Phi^T hi | hi ; lo | 0]
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_tf32(tmem, dih + 2 * k, dw1 + 2 * k, idesc32, 1u);            // grad_y hi x [O^T hi ; O^T lo]
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_tf32(tmem, dil + 2 * k, dw1 + 2 * k, idesc16, 1u);            // grad_y lo x  O^T hi
                 umma_commit(sm.acc_full);
-                umma_commit(sm.empty + s);
+                umma_commit(sm.slot_free + s);
                 if (t + 2 < nsteps) {
-                    mbar_wait(sm.empty + s, (t >> 1) & 1);
+                    mbar_wait(sm.slot_free + s, (t >> 1) & 1);
                     issue(t + 2);
                 }
             }
         }
-    } else {
+    } else if (warp < 4) {
         const int r = threadIdx.x;
         const long row = (long)blockIdx.x * 128 + r;
         const bool valid = row < B;
+        (void)valid;
         const uint32_t tacc = tmem + ((uint32_t)(warp * 32) << 16);
         auto store_inputs = [&](const float (&gv)[PO]) {
             float h[PO], l[PO];
@@ -1462,11 +1333,10 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
             const bool second = t >= nchunks;
             const int j = chunk_of(t), s = t & 1;
             const bool has_next = t + 1 < nsteps;
-            if (valid) {
-                float4* lp = reinterpret_cast<float4*>(L + ((size_t)j * B + row) * 32 + (second ? DS : 0));
-#pragma unroll
-                for (int i = 0; i < 4; ++i) lp[i] = make_float4(st[4 * i], st[4 * i + 1], st[4 * i + 2], st[4 * i + 3]);
-            }
+            // checkpoint of the adjoint entering this step -> staging tile (the writers emptied it during the previous step)
+            if (t > 0) mbar_wait(sm.lst_free, (t - 1) & 1);
+            store_row_sw64(sm.lstage, r, st);
+            mbar_arrive(sm.lst_ready);
             if (second && gbias != nullptr) {
                 // column sums of this chunk's grad_y rows over the warp (lane l ends with column l), then over the 4 warps
                 float v[PO];
@@ -1485,8 +1355,8 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
                 atomicAdd(&sbias[t & 1][lane], v[0]);
             }
             mbar_wait(sm.full + s, (t >> 1) & 1);
-            if (has_next) load_row_sw128(sm.slot[s] + 16384, r, g);
-            mbar_arrive(sm.empty + s);
+            if (has_next) load_row_sw128(sm.slot[s] + CHB_W_BYTES, r, g);
+            mbar_arrive(sm.slot_free + s);
             mbar_wait(sm.acc_full, t & 1);
             tc_fence_after();
             uint32_t m[16], l[16];
@@ -1512,6 +1382,23 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
                 }
             }
         }
+    } else {
+        // writers: adjoint checkpoints -> L
+        const int wt = threadIdx.x - 160;
+        for (int t = 0; t < nsteps; ++t) {
+            const int j = chunk_of(t);
+            mbar_wait(sm.lst_ready, t & 1);
+            float4 sv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const int i = k * CH_WRITERS + wt; sv[k] = read_chunk_sw64(sm.lstage, i >> 2, i & 3); }
+            mbar_arrive(sm.lst_free);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = k * CH_WRITERS + wt;
+                const long row = (long)blockIdx.x * 128 + (i >> 2);
+                if (row < B) *(reinterpret_cast<float4*>(L + ((size_t)j * B + row) * 32 + (t >= nchunks ? DS : 0)) + (i & 3)) = sv[k];
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -1534,6 +1421,7 @@ constexpr int G2_BLK = G2_KS * 128;              // one 32-feature block: 4 KB
 constexpr int G2_A_BYTES = 4 * G2_BLK;           // 16 KB
 constexpr int G2_BH_BYTES = (KB_MAX + 1) * G2_BLK;   // 24 KB
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + 2 * G2_BH_BYTES;   // 64 KB
+constexpr int G2_PF = 6;                          // L2 prefetch distance in 32-sample steps
 constexpr size_t G2_SMEM = (size_t)G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
 
 __global__ void __launch_bounds__(G2_THREADS, 1)
@@ -1575,7 +1463,15 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 
     if (warp == 0) {
         if (lane == 0) {
+            auto prefetch_step = [&](int t) {   // into L2 only, G2_PF steps ahead of the 3-stage shared-memory pipeline
+                tma_prefetch_l2_2d(&map_gy, c.row0, t * G2_KS);
+                tma_prefetch_l2_3d(&map_l, 0, t * G2_KS, ch);
+                for (int i = 0; i < nkb; ++i) tma_prefetch_l2_2d(&map_x, c.col0 + i * KBW, t * G2_KS);
+                tma_prefetch_l2_3d(&map_s, 0, t * G2_KS, ch);
+            };
+            for (int t = t0; t < t0 + G2_PF && t < t1; ++t) prefetch_step(t);
             for (int t = t0, it = 0; t < t1; ++t, ++it) {
+                if (t + G2_PF < t1) prefetch_step(t + G2_PF);
                 const int s = it % G2_STAGES, round = it / G2_STAGES;
                 if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
                 uint8_t* st = smem + s * G2_STAGE_BYTES;
@@ -1620,8 +1516,7 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 for (int i = 0; i < 2 * G2_BLK / 16 / 128; ++i) {
                     const float4 v = h[ct + 128 * i];
                     float4 hh, ll;
-                    hh.x = tf32_hi(v.x); hh.y = tf32_hi(v.y); hh.z = tf32_hi(v.z); hh.w = tf32_hi(v.w);
-                    ll.x = v.x - hh.x; ll.y = v.y - hh.y; ll.z = v.z - hh.z; ll.w = v.w - hh.w;
+                    split_tf32(v, hh, ll);
                     h[ct + 128 * i] = hh;
                     l[ct + 128 * i] = ll;
                 }
@@ -1634,8 +1529,7 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 for (int i = ct; i < n16; i += 128) {
                     const float4 v = h[i];
                     float4 hh, ll;
-                    hh.x = tf32_hi(v.x); hh.y = tf32_hi(v.y); hh.z = tf32_hi(v.z); hh.w = tf32_hi(v.w);
-                    ll.x = v.x - hh.x; ll.y = v.y - hh.y; ll.z = v.z - hh.z; ll.w = v.w - hh.w;
+                    split_tf32(v, hh, ll);
                     h[i] = hh;
                     l[i] = ll;
                 }
@@ -1716,7 +1610,7 @@ sss_tc_build_bwd_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn
         const bool mine = is_in && local >= 0 && local < st.in_dim;
 #pragma unroll
         for (int a = 0; a < DS; ++a) scr[(i * DS + a) * BUILD_THREADS + t] = v[a];
-        if (active) stage_apply(st, sm[i & 1], v, yv, mine, local);
+        if (active) stage_apply<false>(st, sm[i & 1], v, yv, mine, local);
         if (mine) my_i = i;
     }
     // adjoint of the state leaving the last stage: dR / dPhi rows of dM
@@ -1735,7 +1629,12 @@ sss_tc_build_bwd_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn
         const int rbase = st.out_off - c.row0;
         float g[SOUT_MAX];
 #pragma unroll
-        for (int r = 0; r < SOUT_MAX; ++r) g[r] = (support && r < st.out_dim) ? dM[(rbase + r) * DMC + cidx] : 0.f;
+        for (int r = 0; r < SOUT_MAX; ++r) g[r] = 0.f;
+#pragma unroll
+        for (int r = 0; r < SOUT_MAX; ++r) {
+            if (r >= st.out_dim) break;
+            if (support) g[r] = dM[(rbase + r) * DMC + cidx];
+        }
 #pragma unroll
         for (int a = 0; a < DS; ++a) v[a] = scr[(i * DS + a) * BUILD_THREADS + t];
         cp_async_wait_all();
@@ -1747,7 +1646,10 @@ sss_tc_build_bwd_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn
 #pragma unroll
         for (int b = 0; b < DS; ++b) X[b * BB_LD + t] = lam[b];
 #pragma unroll
-        for (int r = 0; r < SOUT_MAX; ++r) X[(DS + r) * BB_LD + t] = g[r];
+        for (int r = 0; r < SOUT_MAX; ++r) {
+            if (r >= st.out_dim) break;
+            X[(DS + r) * BB_LD + t] = g[r];
+        }
 #pragma unroll
         for (int a = 0; a < DS; ++a) V[a * BB_LD + t] = v[a];
         __syncthreads();
@@ -1775,12 +1677,16 @@ sss_tc_build_bwd_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn
         }
         if (mine) {
 #pragma unroll
-            for (int b = 0; b < DS; ++b)
-                if (b < st.d_out) gparams[st.off_su + b * st.in_dim + local] += lam[b];
+            for (int b = 0; b < DS; ++b) {
+                if (b >= st.d_out) break;
+                gparams[st.off_su + b * st.in_dim + local] += lam[b];
+            }
             if (st.off_yu >= 0) {
 #pragma unroll
-                for (int r = 0; r < SOUT_MAX; ++r)
-                    if (r < st.out_dim) gparams[st.off_yu + r * st.in_dim + local] += g[r];
+                for (int r = 0; r < SOUT_MAX; ++r) {
+                    if (r >= st.out_dim) break;
+                    gparams[st.off_yu + r * st.in_dim + local] += g[r];
+                }
             }
         }
         // lambda entering the stage: ss^T lam + ys^T g
@@ -1789,21 +1695,19 @@ sss_tc_build_bwd_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn
         for (int a = 0; a < DS; ++a) nl[a] = 0.f;
 #pragma unroll
         for (int b = 0; b < DS; ++b) {
-            if (b < st.d_out) {
-                const float* ss = ps.ss + b * st.d_in;
+            if (b >= st.d_out) break;
+            const float* ss = ps.ss + b * st.d_in;
 #pragma unroll
-                for (int a = 0; a < DS; ++a)
-                    if (a < st.d_in) nl[a] = fmaf(ss[a], lam[b], nl[a]);
-            }
+            for (int a = 0; a < DS; ++a)
+                if (a < st.d_in) nl[a] = fmaf(ss[a], lam[b], nl[a]);
         }
 #pragma unroll
         for (int r = 0; r < SOUT_MAX; ++r) {
-            if (r < st.out_dim) {
-                const float* ys = ps.ys + r * st.d_in;
+            if (r >= st.out_dim) break;
+            const float* ys = ps.ys + r * st.d_in;
 #pragma unroll
-                for (int a = 0; a < DS; ++a)
-                    if (a < st.d_in) nl[a] = fmaf(ys[a], g[r], nl[a]);
-            }
+            for (int a = 0; a < DS; ++a)
+                if (a < st.d_in) nl[a] = fmaf(ys[a], g[r], nl[a]);
         }
 #pragma unroll
         for (int a = 0; a < DS; ++a) lam[a] = nl[a];
@@ -1816,6 +1720,7 @@ int check_tc_plan(const sn_sss_tc_plan* p) {
     SN_CHECK_ARG(p->nb_states > 0 && p->input_dim > 0 && p->output_dim > 0 && p->nchunks > 0, "sss_tc: non-positive plan dimension");
     SN_CHECK_ARG(p->stages != nullptr && p->chunks != nullptr, "sss_tc: plan tables missing");
     SN_CHECK_ARG(p->input_dim % 4 == 0, "sss_tc: input_dim must be a multiple of 4 (TMA row pitch)");
+    SN_CHECK_ARG(p->nchunks <= G1_MAX_CHUNKS, "sss_tc: more than %d chunks", G1_MAX_CHUNKS);
     return 0;
 }
 
@@ -1869,11 +1774,9 @@ int sn_sss_tc_build(const sn_sss_tc_plan* p, const float* params, float* coef, s
     SN_CHECK_ARG(params && coef, "sss_tc_build: NULL buffer");
     float* W = coef;
     float* SC = coef + (size_t)p->nchunks * WROWS * WCOLS;
-    sss_tc_build_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, 0, snb::as_stream(stream)>>>(p->stages, p->nb_states, p->chunks, params, W, SC);
-    SN_CHECK_LAUNCH("sss_tc_build_kernel");
+    SN_LAUNCH("sss_tc_build_kernel", snb::as_stream(stream), sss_tc_build_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, 0, snb::as_stream(stream)>>>(p->stages, p->nb_states, p->chunks, params, W, SC));
     float* CW = SC + (size_t)p->nchunks * SCF;
-    sss_tc_pack_chain_kernel<<<dim3(p->nchunks, 4), 256, 0, snb::as_stream(stream)>>>(SC, CW);
-    SN_CHECK_LAUNCH("sss_tc_pack_chain_kernel");
+    SN_LAUNCH("sss_tc_pack_chain_kernel", snb::as_stream(stream), sss_tc_pack_chain_kernel<<<dim3(p->nchunks, 4), 256, 0, snb::as_stream(stream)>>>(SC, CW));
     return 0;
 }
 
@@ -1887,7 +1790,7 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
     const float* W = coef;
     const float* SC = coef + (size_t)p->nchunks * WROWS * WCOLS;
     CUtensorMap mx, mw;
-    if (int rc = make_map_f32(&mx, x, (uint64_t)p->input_dim, (uint64_t)B, (uint64_t)ldx, 128)) return rc;
+    if (int rc = make_map_f32(&mx, x, (uint64_t)p->input_dim, (uint64_t)B, (uint64_t)ldx, 128, 0, 0, false, 32, true)) return rc;
     if (int rc = make_map_f32(&mw, W, (uint64_t)WCOLS, (uint64_t)p->nchunks * WROWS, (uint64_t)WCOLS, 128)) return rc;
     const int ntiles = (int)((B + 127) / 128);
     const int aligned = ((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (ldy & 3) == 0 && (bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0) &&
@@ -1895,16 +1798,14 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
     if (use_fused_forward(p, B)) {
         const int grid = ntiles < sm_count() ? ntiles : sm_count();
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
-        sss_tc_fwd_fused_kernel<<<grid, F_THREADS, F_SMEM, st>>>(mx, mw, p->chunks, p->nchunks, (long)B, ntiles, SC, states, y, (long)ldy, bias, aligned);
-        SN_CHECK_LAUNCH("sss_tc_fwd_fused_kernel");
+        SN_LAUNCH("sss_tc_fwd_fused_kernel", st, sss_tc_fwd_fused_kernel<<<grid, F_THREADS, F_SMEM, st>>>(mx, mw, p->chunks, p->nchunks, (long)B, ntiles, SC, states, y, (long)ldy, bias, aligned));
         return 0;
     }
     SN_CHECK_ARG(rbuf != nullptr, "sss_tc_forward: rbuf is NULL");
     const long total = (long)ntiles * p->nchunks;
     const int grid = (int)(total < sm_count() ? total : sm_count());
     SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_local_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G1_SMEM));
-    sss_tc_local_gemm_kernel<<<grid, G1_THREADS, G1_SMEM, st>>>(mx, mw, p->chunks, p->nchunks, (long)B, ntiles, rbuf);
-    SN_CHECK_LAUNCH("sss_tc_local_gemm_kernel");
+    SN_LAUNCH("sss_tc_local_gemm_kernel", st, sss_tc_local_gemm_kernel<<<grid, G1_THREADS, G1_SMEM, st>>>(mx, mw, p->chunks, p->nchunks, (long)B, ntiles, rbuf));
     if (use_tc_chain()) {
         CUtensorMap mc;
         const float* CW = SC + (size_t)p->nchunks * SCF;
@@ -1914,13 +1815,11 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
         if (int rc = make_map_f32(&mi, rbuf, 64, (uint64_t)p->nchunks * B, 64, 128, 0, 0, false, 16)) return rc;
         if (int rc = make_map_f32(&my, rbuf, 64, (uint64_t)p->nchunks * B, 64, 128)) return rc;
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHF_SMEM));
-        sss_tc_chain_fwd_kernel<<<ntiles, CH_THREADS, CHF_SMEM, st>>>(mc, mi, my, p->chunks, p->nchunks, rbuf, states, y, (long)ldy, bias, (long)B, aligned);
-        SN_CHECK_LAUNCH("sss_tc_chain_fwd_kernel");
+        SN_LAUNCH("sss_tc_chain_fwd_kernel", st, sss_tc_chain_fwd_kernel<<<ntiles, CH_THREADS, CHF_SMEM, st>>>(mc, mi, my, p->chunks, p->nchunks, rbuf, states, y, (long)ldy, bias, (long)B, aligned));
         return 0;
     }
-    sss_tc_scan_fwd_q_kernel<<<(unsigned)((B + QS_THREADS / 4 - 1) / (QS_THREADS / 4)), QS_THREADS, 0, st>>>(p->chunks, p->nchunks, SC, rbuf, states, y,
-                                                                                                             (long)ldy, bias, (long)B, aligned);
-    SN_CHECK_LAUNCH("sss_tc_scan_fwd_q_kernel");
+    SN_LAUNCH("sss_tc_scan_fwd_q_kernel", st, sss_tc_scan_fwd_q_kernel<<<(unsigned)((B + QS_THREADS / 4 - 1) / (QS_THREADS / 4)), QS_THREADS, 0, st>>>(p->chunks, p->nchunks, SC, rbuf, states, y,
+                                                                                                             (long)ldy, bias, (long)B, aligned));
     return 0;
 }
 
@@ -1943,17 +1842,16 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
         if (int rc = make_map_f32(&mc, CW, 32, (uint64_t)p->nchunks * 4 * CW_ROWS, 32, CW_ROWS)) return rc;
         CUtensorMap mgy;
         if (int rc = make_map_f32(&mgy, grad_y, (uint64_t)p->output_dim, (uint64_t)B, (uint64_t)ldgy, 128)) return rc;
+        if (int rc = make_map_f32(&mc, CW, 32, (uint64_t)p->nchunks * 4 * CW_ROWS, 32, 64)) return rc;   // state + grad_y sub-tiles only
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHB_SMEM));
-        sss_tc_chain_bwd_kernel<<<(unsigned)((B + 127) / 128), CH_THREADS, CHB_SMEM, st>>>(mc, mgy, p->chunks, p->nchunks, L, grad_bias, (long)B);
-        SN_CHECK_LAUNCH("sss_tc_chain_bwd_kernel");
+        SN_LAUNCH("sss_tc_chain_bwd_kernel", st, sss_tc_chain_bwd_kernel<<<(unsigned)((B + 127) / 128), CH_THREADS, CHB_SMEM, st>>>(mc, mgy, p->chunks, p->nchunks, L, grad_bias, (long)B));
     } else {
-        sss_tc_scan_bwd_q_kernel<<<(unsigned)((B + QS_THREADS / 4 - 1) / (QS_THREADS / 4)), QS_THREADS, 0, st>>>(p->chunks, p->nchunks, SC, grad_y, (long)ldgy,
-                                                                                                             L, grad_bias, (long)B, aligned);
-    SN_CHECK_LAUNCH("sss_tc_scan_bwd_q_kernel");
+        SN_LAUNCH("sss_tc_scan_bwd_q_kernel", st, sss_tc_scan_bwd_q_kernel<<<(unsigned)((B + QS_THREADS / 4 - 1) / (QS_THREADS / 4)), QS_THREADS, 0, st>>>(p->chunks, p->nchunks, SC, grad_y, (long)ldgy,
+                                                                                                             L, grad_bias, (long)B, aligned));
     }
     SN_CHECK_CUDA(cudaMemsetAsync(dM, 0, (size_t)p->nchunks * 64 * DMC * sizeof(float), st));
     CUtensorMap mx, mg, ml, ms;
-    if (int rc = make_map_f32(&mx, x, (uint64_t)p->input_dim, (uint64_t)B, (uint64_t)ldx, G2_KS, 0, 0, true)) return rc;
+    if (int rc = make_map_f32(&mx, x, (uint64_t)p->input_dim, (uint64_t)B, (uint64_t)ldx, G2_KS, 0, 0, true, 32, true)) return rc;
     if (int rc = make_map_f32(&mg, grad_y, (uint64_t)p->output_dim, (uint64_t)B, (uint64_t)ldgy, G2_KS, 0, 0, true)) return rc;
     if (int rc = make_map_f32(&ml, L, 32, (uint64_t)B, 32, G2_KS, (uint64_t)p->nchunks, (uint64_t)B * 32, true)) return rc;
     if (int rc = make_map_f32(&ms, states, 32, (uint64_t)B, 32, G2_KS, (uint64_t)p->nchunks, (uint64_t)B * 32, true)) return rc;
@@ -1962,11 +1860,9 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     if (nsplit > ntk) nsplit = ntk;
     if (nsplit < 1) nsplit = 1;
     SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_grad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
-    sss_tc_grad_gemm_kernel<<<dim3(nsplit, p->nchunks), G2_THREADS, G2_SMEM, st>>>(mx, mg, ml, ms, p->chunks, (long)B, dM);
-    SN_CHECK_LAUNCH("sss_tc_grad_gemm_kernel");
+    SN_LAUNCH("sss_tc_grad_gemm_kernel", st, sss_tc_grad_gemm_kernel<<<dim3(nsplit, p->nchunks), G2_THREADS, G2_SMEM, st>>>(mx, mg, ml, ms, p->chunks, (long)B, dM));
     SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BB_SMEM));
-    sss_tc_build_bwd_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, BB_SMEM, st>>>(p->stages, p->nb_states, p->chunks, params, dM, scratch, grad_params);
-    SN_CHECK_LAUNCH("sss_tc_build_bwd_kernel");
+    SN_LAUNCH("sss_tc_build_bwd_kernel", st, sss_tc_build_bwd_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, BB_SMEM, st>>>(p->stages, p->nb_states, p->chunks, params, dM, scratch, grad_params));
     return 0;
 }
 

@@ -46,6 +46,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
                  "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// pull a box into L2 only (no shared-memory destination): hides HBM latency without spending pipeline stages
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -137,7 +144,7 @@ inline EncodeTiledFn encode_fn() {
 // or SWIZZLE_128B_ATOM_32B (32-byte chunks, for MN-major tf32 operands), OOB -> 0.
 // rank 2 when d2 == 0.
 inline int make_map_f32(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t ld1, uint32_t b1, uint64_t d2 = 0,
-                        uint64_t ld2 = 0, bool atom32 = false, uint32_t b0 = 32) {
+                        uint64_t ld2 = 0, bool atom32 = false, uint32_t b0 = 32, bool promote256 = false) {
     EncodeTiledFn fn = encode_fn();
     SN_CHECK_ARG(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     SN_CHECK_ARG((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld1 * 4) % 16 == 0 && (ld2 * 4) % 16 == 0,
@@ -149,8 +156,7 @@ inline int make_map_f32(CUtensorMap* map, const void* base, uint64_t d0, uint64_
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     b0 == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    promote256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SN_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)r);
     return 0;
 }

@@ -18,8 +18,7 @@ static __global__ void colsum_accumulate_kernel(const float* __restrict__ M, lon
 inline int colsum_accumulate(const float* M, long ld, long rows, int cols, float* out, cudaStream_t stream) {
     if (rows <= 0 || cols <= 0) return 0;
     dim3 grid(ceil_div(cols, 128), (unsigned)((rows + 255) / 256));
-    colsum_accumulate_kernel<<<grid, 128, 0, stream>>>(M, ld, rows, cols, out);
-    SN_CHECK_LAUNCH("colsum_accumulate_kernel");
+    SN_LAUNCH("colsum_accumulate_kernel", stream, colsum_accumulate_kernel<<<grid, 128, 0, stream>>>(M, ld, rows, cols, out));
     return 0;
 }
 
