@@ -177,14 +177,25 @@ int sn_hmat_backward(const int32_t* leaves, int nleaves, const float* params, co
 /* ------------------------------------------------------------------------------------------
  * PSM layer -- replaces PSMLayer.forward / forward_sparse (layers/psm_layer.py:36-60) and its backward,
  * with the intended factor order W = S_0 S_1 ... S_{n-1} (see csrc/psm.cu).  factors_host: host array of nf
- * descriptors; every pointer inside is a device pointer.  The static pattern is given in CSR and CSC order
- * with permutations into the parameter's own COO value array; grad_vals is COO-ordered and accumulated.
+ * descriptors; every pointer inside is a device pointer.  The static pattern is given twice in sliced-ELL form
+ * (for S: `fwd`, for S^T: `tr`): rows sorted by length, slices of 32 rows, entry j of a slice's 32 rows contiguous.
+ * `src` maps a packed entry to its index in the parameter's own COO value array (-1 = padding).  val_fwd / val_tr
+ * ([fwd.total] / [tr.total]) and grad_packed ([fwd.total]) are scratch owned by the caller; grad_vals is COO-ordered
+ * and accumulated.  Dimensions up to 65535 (column indices are 16 bit).
  * ------------------------------------------------------------------------------------------ */
+typedef struct sn_psm_ell {
+    int32_t nslices, total;        /* total = padded entry count = slice_off[nslices] */
+    const int32_t* rowmap;         /* [nslices * 32] natural row of position p (-1: none) */
+    const int32_t* slice_off;      /* [nslices + 1], multiples of 32 */
+    const uint16_t* col;           /* [total] */
+    const int32_t* src;            /* [total] */
+} sn_psm_ell;
 typedef struct sn_psm_factor {
     int32_t rows, cols, nnz, reserved;
-    const int32_t *rowptr, *colidx, *perm, *cscptr, *rowidx, *permc;
+    sn_psm_ell fwd, tr;
     const float* vals;
     float* grad_vals;
+    float *val_fwd, *val_tr, *grad_packed;
 } sn_psm_factor;
 int sn_psm_forward(const sn_psm_factor* factors_host, int nf, const float* x, int64_t ldx, float* y, int64_t ldy, const float* bias,
                    int64_t B, int in_dim, int out_dim, sn_stream_t stream);

@@ -36,9 +36,13 @@ class SnSssTcPlan(Structure):
                [("reserved", c_int32 * 3), ("stages", c_void_p), ("chunks", c_void_p)]
 
 
+class SnPsmEll(Structure):
+    _fields_ = [("nslices", c_int32), ("total", c_int32)] + [(n, c_void_p) for n in ("rowmap", "slice_off", "col", "src")]
+
+
 class SnPsmFactor(Structure):
-    _fields_ = [("rows", c_int32), ("cols", c_int32), ("nnz", c_int32), ("reserved", c_int32)] + \
-               [(n, c_void_p) for n in ("rowptr", "colidx", "perm", "cscptr", "rowidx", "permc", "vals", "grad_vals")]
+    _fields_ = [("rows", c_int32), ("cols", c_int32), ("nnz", c_int32), ("reserved", c_int32), ("fwd", SnPsmEll), ("tr", SnPsmEll)] + \
+               [(n, c_void_p) for n in ("vals", "grad_vals", "val_fwd", "val_tr", "grad_packed")]
 
 
 _lib = None

@@ -4,12 +4,14 @@
 // literal loop order of psm_layer.py:52-54 is only correct for <= 2 factors (SURVEY.md finding F2), where
 // both coincide -- and the autograd backward (sparse gradients on the COO pattern).
 //
-// The chain is applied per tile of NS samples with every intermediate activation kept in shared memory,
-// feature-major [feature][NS]: only x and y touch HBM.  Each factor is walked in CSR order (one thread per
-// output row, gathering NS-wide input rows from shared memory); values are read through a permutation from
-// the parameter's own (uncoalesced) COO value array, so nothing is re-sorted per step.  The backward
-// recomputes the intermediates, forms dS_k[j] = sum_s g[row_j][s] * in_k[col_j][s] per tile (atomic add to
-// the COO-ordered gradient values) and pushes g through S_k^T in CSC order.
+// The chain is applied per tile of 4 samples with every intermediate activation kept in shared memory,
+// feature-major [feature][4] (one LDS.128 gathers a feature for the whole tile): only x and y touch HBM.
+// The static sparsity pattern is pre-arranged (once, host side) in sliced-ELL form, for S and for S^T:
+// rows sorted by length, slices of 32 rows, entry j of the slice's rows stored contiguously -- so a warp
+// (lane = row) streams its column indices (uint16) and values with fully coalesced loads, 6 bytes per
+// non-zero, instead of chasing three dependent scattered loads per non-zero.  The values are gathered
+// from the parameter's own COO array into that order once per call (psm_pack_vals_kernel); the backward
+// accumulates dS in the same packed order with coalesced reductions and scatters it back once.
 #include "common.cuh"
 #include "util.cuh"
 
@@ -17,17 +19,21 @@ namespace {
 
 constexpr int PSM_MAX_FACTORS = 8;
 constexpr int PSM_THREADS = 512;
+constexpr int PSM_WARPS = PSM_THREADS / 32;
+constexpr int NS = 4;   // samples per tile
+
+struct Ell {
+    int nrows, nslices, total, pad;
+    const int* rowmap;            // [nslices * 32] natural row of position p, -1 = none
+    const int* slice_off;         // [nslices + 1]
+    const unsigned short* col;    // [total]
+    const float* val;             // [total] packed values (this call's)
+};
 
 struct Factor {
-    int rows, cols, nnz, pad;
-    const int* rowptr;   // rows + 1
-    const int* colidx;   // nnz, CSR order
-    const int* perm;     // nnz, CSR position -> index into the COO value array
-    const int* cscptr;   // cols + 1
-    const int* rowidx;   // nnz, CSC order
-    const int* permc;    // nnz, CSC position -> index into the COO value array
-    const float* vals;   // COO value array (parameter storage)
-    float* gvals;        // COO-ordered gradient values (backward only)
+    int rows, cols;
+    Ell fwd, tr;
+    float* gpacked;   // [fwd.total], backward only
 };
 
 struct Chain {
@@ -35,51 +41,94 @@ struct Chain {
     Factor f[PSM_MAX_FACTORS];
 };
 
-template <int NS>
-__device__ __forceinline__ void load_x(const float* __restrict__ x, long ldx, long t0, long B, int dim, float* dst) {
-    for (int s = 0; s < NS; ++s) {
-        const bool ok = t0 + s < B;
-        const float* row = x + (size_t)(t0 + s) * ldx;
-        for (int f = threadIdx.x; f < dim; f += PSM_THREADS) dst[f * NS + s] = ok ? __ldg(row + f) : 0.f;
+__global__ void psm_pack_vals_kernel(const int* __restrict__ src, const float* __restrict__ vals, float* __restrict__ out, int total) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) {
+        const int s = __ldg(src + i);
+        out[i] = s >= 0 ? __ldg(vals + s) : 0.f;
+    }
+}
+__global__ void psm_unpack_grad_kernel(const int* __restrict__ src, const float* __restrict__ gpacked, float* __restrict__ gvals, int total) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) {
+        const int s = __ldg(src + i);
+        if (s >= 0) gvals[s] += gpacked[i];   // every COO entry appears exactly once
     }
 }
 
-// out[r][:] = sum_j vals[perm[j]] * in[colidx[j]][:]   for all rows r of the factor
-template <int NS>
-__device__ __forceinline__ void spmm_csr(const Factor& F, const float* in, float* out) {
-    for (int r = threadIdx.x; r < F.rows; r += PSM_THREADS) {
-        float acc[NS];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) acc[s] = 0.f;
-        const int j1 = __ldg(F.rowptr + r + 1);
-        for (int j = __ldg(F.rowptr + r); j < j1; ++j) {
-            const float v = __ldg(F.vals + __ldg(F.perm + j));
-            const float* iv = in + (size_t)__ldg(F.colidx + j) * NS;
-            if constexpr (NS == 4) {
-                const float4 t = *reinterpret_cast<const float4*>(iv);
-                acc[0] = fmaf(v, t.x, acc[0]); acc[1] = fmaf(v, t.y, acc[1]);
-                acc[2] = fmaf(v, t.z, acc[2]); acc[3] = fmaf(v, t.w, acc[3]);
-            } else {
-#pragma unroll
-                for (int s = 0; s < NS; ++s) acc[s] = fmaf(v, iv[s], acc[s]);
-            }
+// dst[f][s] = src[t0 + s][f]
+__device__ __forceinline__ void load_tile(const float* __restrict__ x, long ldx, long t0, long B, int dim, float* dst) {
+    for (int f = threadIdx.x; f < dim; f += PSM_THREADS) {
+        float4 v;
+        v.x = t0 + 0 < B ? __ldg(x + (size_t)(t0 + 0) * ldx + f) : 0.f;
+        v.y = t0 + 1 < B ? __ldg(x + (size_t)(t0 + 1) * ldx + f) : 0.f;
+        v.z = t0 + 2 < B ? __ldg(x + (size_t)(t0 + 2) * ldx + f) : 0.f;
+        v.w = t0 + 3 < B ? __ldg(x + (size_t)(t0 + 3) * ldx + f) : 0.f;
+        reinterpret_cast<float4*>(dst)[f] = v;
+    }
+}
+
+// out[r][:] = sum_j val_j * in[col_j][:]  for every row r of the ELL pattern (a warp per slice of 32 rows, lane = row)
+__device__ __forceinline__ void spmm_ell(const Ell& E, const float* in, float* out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float4* in4 = reinterpret_cast<const float4*>(in);
+    for (int sl = warp; sl < E.nslices; sl += PSM_WARPS) {
+        const int base = __ldg(E.slice_off + sl);
+        const int len = (__ldg(E.slice_off + sl + 1) - base) >> 5;
+        const int r = __ldg(E.rowmap + sl * 32 + lane);
+        const unsigned short* cp = E.col + base + lane;
+        const float* vp = E.val + base + lane;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int j = 0;
+        for (; j + 4 <= len; j += 4) {
+            const int c0 = __ldg(cp + (j + 0) * 32), c1 = __ldg(cp + (j + 1) * 32), c2 = __ldg(cp + (j + 2) * 32), c3 = __ldg(cp + (j + 3) * 32);
+            const float v0 = __ldg(vp + (j + 0) * 32), v1 = __ldg(vp + (j + 1) * 32), v2 = __ldg(vp + (j + 2) * 32), v3 = __ldg(vp + (j + 3) * 32);
+            const float4 x0 = in4[c0], x1 = in4[c1], x2 = in4[c2], x3 = in4[c3];
+            acc.x = fmaf(v0, x0.x, acc.x); acc.y = fmaf(v0, x0.y, acc.y); acc.z = fmaf(v0, x0.z, acc.z); acc.w = fmaf(v0, x0.w, acc.w);
+            acc.x = fmaf(v1, x1.x, acc.x); acc.y = fmaf(v1, x1.y, acc.y); acc.z = fmaf(v1, x1.z, acc.z); acc.w = fmaf(v1, x1.w, acc.w);
+            acc.x = fmaf(v2, x2.x, acc.x); acc.y = fmaf(v2, x2.y, acc.y); acc.z = fmaf(v2, x2.z, acc.z); acc.w = fmaf(v2, x2.w, acc.w);
+            acc.x = fmaf(v3, x3.x, acc.x); acc.y = fmaf(v3, x3.y, acc.y); acc.z = fmaf(v3, x3.z, acc.z); acc.w = fmaf(v3, x3.w, acc.w);
         }
-#pragma unroll
-        for (int s = 0; s < NS; ++s) out[(size_t)r * NS + s] = acc[s];
+        for (; j < len; ++j) {
+            const int c0 = __ldg(cp + j * 32);
+            const float v0 = __ldg(vp + j * 32);
+            const float4 x0 = in4[c0];
+            acc.x = fmaf(v0, x0.x, acc.x); acc.y = fmaf(v0, x0.y, acc.y); acc.z = fmaf(v0, x0.z, acc.z); acc.w = fmaf(v0, x0.w, acc.w);
+        }
+        if (r >= 0) reinterpret_cast<float4*>(out)[r] = acc;
     }
 }
 
-template <int NS>
+// gpacked[entry] += sum_s g[row][s] * in[col][s]   (coalesced reductions: the 32 lanes of a warp hit 32 consecutive floats)
+__device__ __forceinline__ void dvals_ell(const Ell& E, const float* g, const float* in, float* __restrict__ gpacked) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float4* in4 = reinterpret_cast<const float4*>(in);
+    for (int sl = warp; sl < E.nslices; sl += PSM_WARPS) {
+        const int base = __ldg(E.slice_off + sl);
+        const int len = (__ldg(E.slice_off + sl + 1) - base) >> 5;
+        const int r = __ldg(E.rowmap + sl * 32 + lane);
+        const float4 gr = r >= 0 ? reinterpret_cast<const float4*>(g)[r] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const unsigned short* cp = E.col + base + lane;
+        float* gp = gpacked + base + lane;
+#pragma unroll 4
+        for (int j = 0; j < len; ++j) {
+            const float4 xv = in4[__ldg(cp + j * 32)];
+            const float d = fmaf(gr.w, xv.w, fmaf(gr.z, xv.z, fmaf(gr.y, xv.y, gr.x * xv.x)));
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(gp + j * 32), "f"(d) : "memory");
+        }
+    }
+}
+
 __global__ void __launch_bounds__(PSM_THREADS)
 psm_fwd_kernel(Chain ch, const float* __restrict__ x, long ldx, float* __restrict__ y, long ldy, const float* __restrict__ bias, long B) {
     extern __shared__ __align__(16) float smem[];
     float* a = smem;
     float* b = smem + (size_t)ch.maxdim * NS;
     const long t0 = (long)blockIdx.x * NS;
-    load_x<NS>(x, ldx, t0, B, ch.in_dim, a);
+    load_tile(x, ldx, t0, B, ch.in_dim, a);
     __syncthreads();
     for (int k = ch.nf - 1; k >= 0; --k) {
-        spmm_csr<NS>(ch.f[k], a, b);
+        spmm_ell(ch.f[k].fwd, a, b);
         __syncthreads();
         float* t = a; a = b; b = t;
     }
@@ -90,132 +139,112 @@ psm_fwd_kernel(Chain ch, const float* __restrict__ x, long ldx, float* __restric
     }
 }
 
-template <int NS>
+// Three buffers: P / Q recompute the input of factor k from x (ping-pong), G holds the gradient that enters factor k from the
+// output side; S_k^T G lands in whichever of P / Q is free and becomes the next G.
 __global__ void __launch_bounds__(PSM_THREADS)
 psm_bwd_kernel(Chain ch, const float* __restrict__ x, long ldx, const float* __restrict__ gy, long ldgy, long B) {
     extern __shared__ __align__(16) float smem[];
     const size_t vec = (size_t)ch.maxdim * NS;
-    // act[k] = input of factor k (k = nf-1 is x); g0/g1 = gradient ping-pong
-    float* act = smem;                        // nf vectors
-    float* g0 = smem + (size_t)ch.nf * vec;
-    float* g1 = g0 + vec;
+    float* P = smem;
+    float* Q = smem + vec;
+    float* G = smem + 2 * vec;
     const long t0 = (long)blockIdx.x * NS;
-    load_x<NS>(x, ldx, t0, B, ch.in_dim, act + (size_t)(ch.nf - 1) * vec);
-    load_x<NS>(gy, ldgy, t0, B, ch.out_dim, g0);
-    __syncthreads();
-    for (int k = ch.nf - 1; k >= 1; --k) {   // recompute the inputs of factors nf-2 .. 0
-        spmm_csr<NS>(ch.f[k], act + (size_t)k * vec, act + (size_t)(k - 1) * vec);
-        __syncthreads();
-    }
+    load_tile(gy, ldgy, t0, B, ch.out_dim, G);
     for (int k = 0; k < ch.nf; ++k) {
-        const Factor& F = ch.f[k];
-        const float* in = act + (size_t)k * vec;
-        // dS_k[j] += sum_s g[row][s] * in[col][s]
-        for (int r = threadIdx.x; r < F.rows; r += PSM_THREADS) {
-            float gr[NS];
-#pragma unroll
-            for (int s = 0; s < NS; ++s) gr[s] = g0[(size_t)r * NS + s];
-            const int j1 = __ldg(F.rowptr + r + 1);
-            for (int j = __ldg(F.rowptr + r); j < j1; ++j) {
-                const float* iv = in + (size_t)__ldg(F.colidx + j) * NS;
-                float d = 0.f;
-#pragma unroll
-                for (int s = 0; s < NS; ++s) d = fmaf(gr[s], iv[s], d);
-                atomicAdd(F.gvals + __ldg(F.perm + j), d);
-            }
-        }
-        // g_next[c][:] = sum_j vals[permc[j]] * g[rowidx[j]][:]   (S_k^T g), not needed after the last factor
-        if (k + 1 < ch.nf) {
-            for (int c = threadIdx.x; c < F.cols; c += PSM_THREADS) {
-                float acc[NS];
-#pragma unroll
-                for (int s = 0; s < NS; ++s) acc[s] = 0.f;
-                const int j1 = __ldg(F.cscptr + c + 1);
-                for (int j = __ldg(F.cscptr + c); j < j1; ++j) {
-                    const float v = __ldg(F.vals + __ldg(F.permc + j));
-                    const float* gv = g0 + (size_t)__ldg(F.rowidx + j) * NS;
-#pragma unroll
-                    for (int s = 0; s < NS; ++s) acc[s] = fmaf(v, gv[s], acc[s]);
-                }
-#pragma unroll
-                for (int s = 0; s < NS; ++s) g1[(size_t)c * NS + s] = acc[s];
-            }
-        }
+        // input of factor k: x pushed through factors nf-1 .. k+1
+        load_tile(x, ldx, t0, B, ch.in_dim, P);
         __syncthreads();
-        float* t = g0; g0 = g1; g1 = t;
+        for (int kk = ch.nf - 1; kk > k; --kk) {
+            spmm_ell(ch.f[kk].fwd, P, Q);
+            __syncthreads();
+            float* t = P; P = Q; Q = t;
+        }
+        dvals_ell(ch.f[k].fwd, G, P, ch.f[k].gpacked);
+        if (k + 1 < ch.nf) {
+            spmm_ell(ch.f[k].tr, G, Q);   // S_k^T G (Q is free: the recomputed input sits in P)
+            __syncthreads();
+            float* t = G; G = Q; Q = t;
+        }
     }
+}
+
+int make_chain(const sn_psm_factor* f, int nf, int in_dim, int out_dim, bool backward, Chain* ch) {
+    SN_CHECK_ARG(f != nullptr && nf >= 1 && nf <= PSM_MAX_FACTORS, "psm: need 1..%d factors", PSM_MAX_FACTORS);
+    ch->nf = nf; ch->in_dim = in_dim; ch->out_dim = out_dim; ch->maxdim = in_dim > out_dim ? in_dim : out_dim;
+    for (int k = 0; k < nf; ++k) {
+        const sn_psm_factor& s = f[k];
+        SN_CHECK_ARG(s.rows > 0 && s.cols > 0 && s.rows <= 65535 && s.cols <= 65535, "psm: factor %d is %d x %d (dimensions must be in 1..65535)", k, s.rows, s.cols);
+        SN_CHECK_ARG(s.fwd.rowmap && s.fwd.slice_off && s.fwd.nslices * 32 >= s.rows && (s.fwd.total == 0 || (s.fwd.col && s.fwd.src && s.val_fwd)),
+                     "psm: factor %d has an incomplete sliced-ELL pattern", k);
+        SN_CHECK_ARG(s.nnz == 0 || s.vals, "psm: factor %d has no value array", k);
+        Factor& F = ch->f[k];
+        F.rows = s.rows; F.cols = s.cols;
+        F.fwd = Ell{s.rows, s.fwd.nslices, s.fwd.total, 0, s.fwd.rowmap, s.fwd.slice_off, s.fwd.col, s.val_fwd};
+        F.tr = Ell{s.cols, s.tr.nslices, s.tr.total, 0, s.tr.rowmap, s.tr.slice_off, s.tr.col, s.val_tr};
+        F.gpacked = s.grad_packed;
+        if (backward) {
+            SN_CHECK_ARG(s.tr.rowmap && s.tr.slice_off && (s.tr.total == 0 || (s.tr.col && s.tr.src && s.val_tr)), "psm: factor %d has no transposed pattern", k);
+            SN_CHECK_ARG(s.fwd.total == 0 || (s.grad_packed && s.grad_vals), "psm_backward: factor %d has no gradient buffer", k);
+        }
+        if (s.rows > ch->maxdim) ch->maxdim = s.rows;
+        if (s.cols > ch->maxdim) ch->maxdim = s.cols;
+        if (k > 0) SN_CHECK_ARG(f[k - 1].cols == s.rows, "psm: factor %d cols (%d) != factor %d rows (%d)", k - 1, f[k - 1].cols, k, s.rows);
+    }
+    SN_CHECK_ARG(f[0].rows == out_dim && f[nf - 1].cols == in_dim, "psm: chain maps %d -> %d, layer is %d -> %d", f[nf - 1].cols, f[0].rows, in_dim, out_dim);
+    return 0;
+}
+
+int pack_vals(const sn_psm_ell& e, const float* vals, float* out, cudaStream_t st) {
+    if (e.total <= 0) return 0;
+    SN_LAUNCH("psm_pack_vals_kernel", st, psm_pack_vals_kernel<<<snb::ceil_div(e.total, 256), 256, 0, st>>>(e.src, vals, out, e.total));
+    return 0;
 }
 
 }  // namespace
 
 extern "C" {
 
-static int make_chain(const sn_psm_factor* f, int nf, int in_dim, int out_dim, Chain* ch) {
-    SN_CHECK_ARG(f != nullptr && nf >= 1 && nf <= PSM_MAX_FACTORS, "psm: need 1..%d factors", PSM_MAX_FACTORS);
-    ch->nf = nf; ch->in_dim = in_dim; ch->out_dim = out_dim; ch->maxdim = in_dim > out_dim ? in_dim : out_dim;
-    for (int k = 0; k < nf; ++k) {
-        SN_CHECK_ARG(f[k].rowptr && f[k].cscptr && (f[k].nnz == 0 || (f[k].colidx && f[k].perm && f[k].rowidx && f[k].permc && f[k].vals)),
-                     "psm: factor %d has NULL arrays", k);
-        ch->f[k] = Factor{f[k].rows, f[k].cols, f[k].nnz, 0, f[k].rowptr, f[k].colidx, f[k].perm, f[k].cscptr, f[k].rowidx, f[k].permc, f[k].vals, f[k].grad_vals};
-        if (f[k].rows > ch->maxdim) ch->maxdim = f[k].rows;
-        if (f[k].cols > ch->maxdim) ch->maxdim = f[k].cols;
-        if (k > 0) SN_CHECK_ARG(f[k - 1].cols == f[k].rows, "psm: factor %d cols (%d) != factor %d rows (%d)", k - 1, f[k - 1].cols, k, f[k].rows);
-    }
-    SN_CHECK_ARG(f[0].rows == out_dim && f[nf - 1].cols == in_dim, "psm: chain maps %d -> %d, layer is %d -> %d", f[nf - 1].cols, f[0].rows, in_dim, out_dim);
-    return 0;
-}
-
 int sn_psm_forward(const sn_psm_factor* factors_host, int nf, const float* x, int64_t ldx, float* y, int64_t ldy, const float* bias,
                    int64_t B, int in_dim, int out_dim, sn_stream_t stream) {
     Chain ch;
-    if (int rc = make_chain(factors_host, nf, in_dim, out_dim, &ch)) return rc;
+    if (int rc = make_chain(factors_host, nf, in_dim, out_dim, false, &ch)) return rc;
     SN_CHECK_ARG(x && y, "psm_forward: NULL buffer");
     if (B <= 0) return 0;
     cudaStream_t st = snb::as_stream(stream);
-#define PSM_FWD(NS)                                                                                                         \
-    {                                                                                                                       \
-        size_t smem = (size_t)2 * ch.maxdim * NS * sizeof(float);                                                           \
-        if (smem <= 227 * 1024) {                                                                                           \
-            SN_CHECK_CUDA(cudaFuncSetAttribute(psm_fwd_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            psm_fwd_kernel<NS><<<(unsigned)((B + NS - 1) / NS), PSM_THREADS, smem, st>>>(ch, x, ldx, y, ldy, bias, B);      \
-            SN_CHECK_LAUNCH("psm_fwd_kernel");                                                                              \
-            return 0;                                                                                                       \
-        }                                                                                                                   \
-    }
-    PSM_FWD(4)
-    PSM_FWD(2)
-    PSM_FWD(1)
-#undef PSM_FWD
-    snb::set_error("psm_forward: factor dimension %d does not fit in shared memory", ch.maxdim);
-    return 1;
+    for (int k = 0; k < nf; ++k)
+        if (int rc = pack_vals(factors_host[k].fwd, factors_host[k].vals, factors_host[k].val_fwd, st)) return rc;
+    const size_t smem = (size_t)2 * ch.maxdim * NS * sizeof(float);
+    SN_CHECK_ARG(smem <= 227 * 1024, "psm_forward: factor dimension %d does not fit in shared memory", ch.maxdim);
+    SN_CHECK_CUDA(cudaFuncSetAttribute(psm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SN_LAUNCH("psm_fwd_kernel", st, psm_fwd_kernel<<<(unsigned)((B + NS - 1) / NS), PSM_THREADS, smem, st>>>(ch, x, ldx, y, ldy, bias, B));
+    return 0;
 }
 
 int sn_psm_backward(const sn_psm_factor* factors_host, int nf, const float* x, int64_t ldx, const float* grad_y, int64_t ldgy,
                     float* grad_bias, int64_t B, int in_dim, int out_dim, sn_stream_t stream) {
     Chain ch;
-    if (int rc = make_chain(factors_host, nf, in_dim, out_dim, &ch)) return rc;
+    if (int rc = make_chain(factors_host, nf, in_dim, out_dim, true, &ch)) return rc;
     SN_CHECK_ARG(x && grad_y, "psm_backward: NULL buffer");
-    for (int k = 0; k < nf; ++k) SN_CHECK_ARG(ch.f[k].gvals != nullptr || ch.f[k].nnz == 0, "psm_backward: factor %d has no gradient buffer", k);
     if (B <= 0) return 0;
     cudaStream_t st = snb::as_stream(stream);
     if (grad_bias)
         if (int rc = snb::colsum_accumulate(grad_y, ldgy, B, out_dim, grad_bias, st)) return rc;
-#define PSM_BWD(NS)                                                                                                         \
-    {                                                                                                                       \
-        size_t smem = (size_t)(ch.nf + 2) * ch.maxdim * NS * sizeof(float);                                                 \
-        if (smem <= 227 * 1024) {                                                                                           \
-            SN_CHECK_CUDA(cudaFuncSetAttribute(psm_bwd_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            psm_bwd_kernel<NS><<<(unsigned)((B + NS - 1) / NS), PSM_THREADS, smem, st>>>(ch, x, ldx, grad_y, ldgy, B);      \
-            SN_CHECK_LAUNCH("psm_bwd_kernel");                                                                              \
-            return 0;                                                                                                       \
-        }                                                                                                                   \
+    for (int k = 0; k < nf; ++k) {
+        const sn_psm_factor& f = factors_host[k];
+        if (int rc = pack_vals(f.fwd, f.vals, f.val_fwd, st)) return rc;
+        if (int rc = pack_vals(f.tr, f.vals, f.val_tr, st)) return rc;
+        if (f.fwd.total > 0) SN_CHECK_CUDA(cudaMemsetAsync(f.grad_packed, 0, (size_t)f.fwd.total * sizeof(float), st));
     }
-    PSM_BWD(4)
-    PSM_BWD(2)
-    PSM_BWD(1)
-#undef PSM_BWD
-    snb::set_error("psm_backward: %d factors of dimension %d do not fit in shared memory", ch.nf, ch.maxdim);
-    return 1;
+    const size_t smem = (size_t)3 * ch.maxdim * NS * sizeof(float);
+    SN_CHECK_ARG(smem <= 227 * 1024, "psm_backward: factor dimension %d does not fit in shared memory", ch.maxdim);
+    SN_CHECK_CUDA(cudaFuncSetAttribute(psm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SN_LAUNCH("psm_bwd_kernel", st, psm_bwd_kernel<<<(unsigned)((B + NS - 1) / NS), PSM_THREADS, smem, st>>>(ch, x, ldx, grad_y, ldgy, B));
+    for (int k = 0; k < nf; ++k) {
+        const sn_psm_factor& f = factors_host[k];
+        if (f.fwd.total > 0)
+            SN_LAUNCH("psm_unpack_grad_kernel", st, psm_unpack_grad_kernel<<<snb::ceil_div(f.fwd.total, 256), 256, 0, st>>>(f.fwd.src, f.grad_packed, f.grad_vals, f.fwd.total));
+    }
+    return 0;
 }
 
 }  // extern "C"

@@ -20,20 +20,54 @@ from structurednets_b200.layers.layer_helpers import get_random_glorot_uniform_m
 from structurednets_b200.layers.structured_layer import StructuredLayer
 
 
+def _sliced_ell(rows: np.ndarray, cols: np.ndarray, nr: int):
+    """Sliced-ELL arrangement of a COO pattern (csrc/psm.cu): rows sorted by length, slices of 32 rows, entry j of the 32 rows
+    of a slice contiguous.  Returns numpy arrays rowmap, slice_off, col (uint16), src (COO index or -1)."""
+    nnz = len(rows)
+    counts = np.bincount(rows, minlength=nr).astype(np.int64)
+    order = np.argsort(-counts, kind="stable")
+    nslices = (nr + 31) // 32
+    rowmap = np.full(nslices * 32, -1, dtype=np.int32)
+    rowmap[:nr] = order
+    pos_of_row = np.empty(nr, dtype=np.int64)
+    pos_of_row[order] = np.arange(nr)
+    padded = np.zeros(nslices * 32, dtype=np.int64)
+    padded[:nr] = counts[order]
+    slice_len = padded.reshape(nslices, 32).max(axis=1)
+    slice_off = np.concatenate([[0], np.cumsum(slice_len * 32)]).astype(np.int64)
+    total = int(slice_off[-1])
+    perm = np.argsort(rows, kind="stable")
+    r_sorted = rows[perm]
+    start = np.cumsum(counts) - counts
+    j = np.arange(nnz) - start[r_sorted]
+    p = pos_of_row[r_sorted]
+    dest = slice_off[p // 32] + j * 32 + (p % 32)
+    col = np.zeros(max(total, 1), dtype=np.uint16)
+    src = np.full(max(total, 1), -1, dtype=np.int32)
+    col[dest] = cols[perm].astype(np.uint16)
+    src[dest] = perm.astype(np.int32)
+    return dict(nslices=nslices, total=total, rowmap=rowmap, slice_off=slice_off.astype(np.int32), col=col, src=src)
+
+
 def _pattern(p: torch.Tensor):
-    """CSR- and CSC-ordered views of an (uncoalesced) sparse-COO pattern, built on the device with
-    sorting only (no host round trip); cached per indices storage."""
+    """Sliced-ELL forms of an (uncoalesced) sparse-COO pattern and of its transpose, plus the per-call scratch the kernels need;
+    cached per indices storage (built on the host once: the pattern is static)."""
     idx = p._indices()
-    rows, cols = idx[0], idx[1]
+    dev = idx.device
+    rows, cols = idx[0].cpu().numpy().astype(np.int64), idx[1].cpu().numpy().astype(np.int64)
     nr, nc = p.shape
-    perm = torch.argsort(rows * nc + cols, stable=True)
-    permc = torch.argsort(cols * nr + rows, stable=True)
-    i32 = lambda t: t.to(torch.int32).contiguous()
-    z = torch.zeros(1, dtype=torch.int64, device=idx.device)
-    rowptr = torch.cat([z, torch.cumsum(torch.bincount(rows, minlength=nr), 0)])
-    cscptr = torch.cat([z, torch.cumsum(torch.bincount(cols, minlength=nc), 0)])
-    return dict(key=(idx.data_ptr(), idx.shape[1], str(idx.device)), rowptr=i32(rowptr), colidx=i32(cols[perm]), perm=i32(perm),
-                cscptr=i32(cscptr), rowidx=i32(rows[permc]), permc=i32(permc))
+    assert nr <= 65535 and nc <= 65535, "PSMLayer: factor dimensions above 65535 are not supported by the CUDA path"
+    out = dict(key=(idx.data_ptr(), idx.shape[1], str(dev)))
+    for name, e in (("fwd", _sliced_ell(rows, cols, nr)), ("tr", _sliced_ell(cols, rows, nc))):
+        d = dict(nslices=e["nslices"], total=e["total"])
+        d["rowmap"] = torch.from_numpy(e["rowmap"]).to(dev)
+        d["slice_off"] = torch.from_numpy(e["slice_off"]).to(dev)
+        d["col"] = torch.from_numpy(e["col"].view(np.int16)).to(dev)
+        d["src"] = torch.from_numpy(e["src"]).to(dev)
+        d["val"] = torch.zeros(max(e["total"], 1), dtype=torch.float32, device=dev)
+        out[name] = d
+    out["grad_packed"] = torch.zeros(max(out["fwd"]["total"], 1), dtype=torch.float32, device=dev)
+    return out
 
 
 def _factor_array(patterns, params, gvals):
@@ -41,9 +75,13 @@ def _factor_array(patterns, params, gvals):
     for k, (pat, p) in enumerate(zip(patterns, params)):
         f = arr[k]
         f.rows, f.cols, f.nnz = int(p.shape[0]), int(p.shape[1]), int(p._nnz())
-        for name in ("rowptr", "colidx", "perm", "cscptr", "rowidx", "permc"):
-            setattr(f, name, pat[name].data_ptr())
+        for name in ("fwd", "tr"):
+            e, d = getattr(f, name), pat[name]
+            e.nslices, e.total = d["nslices"], d["total"]
+            e.rowmap, e.slice_off, e.col, e.src = d["rowmap"].data_ptr(), d["slice_off"].data_ptr(), d["col"].data_ptr(), d["src"].data_ptr()
         f.vals = p._values().data_ptr()
+        f.val_fwd, f.val_tr = pat["fwd"]["val"].data_ptr(), pat["tr"]["val"].data_ptr()
+        f.grad_packed = pat["grad_packed"].data_ptr()
         f.grad_vals = gvals[k].data_ptr() if gvals is not None else None
     return arr
 

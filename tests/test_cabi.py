@@ -42,4 +42,5 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.SnSssStage) == 64
     assert ctypes.sizeof(_lib.SnSssChunk) == 64
     assert ctypes.sizeof(_lib.SnSssPlan) == 12 * 4 + 2 * 8
-    assert ctypes.sizeof(_lib.SnPsmFactor) == 16 + 8 * 8
+    assert ctypes.sizeof(_lib.SnPsmEll) == 8 + 4 * 8
+    assert ctypes.sizeof(_lib.SnPsmFactor) == 16 + 2 * 40 + 5 * 8
