@@ -8,7 +8,9 @@
 // single-pass TF32/BF16 tensor-core product here; the bf16 configuration of the low-rank layer has
 // its own tcgen05 path (lr_tc.cu).
 #pragma once
+#include <stdlib.h>
 #include "common.cuh"
+#include "gemm_tf32x3.cuh"
 
 namespace snb {
 
@@ -100,6 +102,29 @@ gemm_f32_kernel(int M, int N, int Kfull, int kslice, float alpha, const float* _
 inline int gemm_f32(bool ta, bool tb, int M, int N, int K, float alpha, const float* A, long lda, const float* B, long ldb,
                     float beta, float* C, long ldc, const float* bias, cudaStream_t stream, bool accumulate = false) {
     if (M <= 0 || N <= 0) return 0;
+    // tensor-core path (3xTF32, csrc/gemm_tf32x3.cuh) whenever TMA can read the operands; SNB200_GEMM=simt forces the CUDA-core kernel
+    {
+        const char* e = getenv("SNB200_GEMM");
+        const bool force_simt = e != nullptr && e[0] == 's';
+        if (!force_simt && K > 0 && (beta == 0.f || accumulate) && t3::t3_eligible(A, lda, B, ldb) && (!accumulate || beta == 1.f) &&
+            (accumulate || K <= 4096)) {   // a long non-split K would outgrow the four accumulators' error bound
+            int ksplit = 1;
+            if (accumulate) {
+                const int tiles = ceil_div(N, 128) * ceil_div(M, 128);
+                ksplit = ceil_div(2 * 148, tiles);
+                const int maxsplit = ceil_div(K, 256);
+                if (ksplit > maxsplit) ksplit = maxsplit;
+                const int minsplit = ceil_div(K, 2048);   // at most 2048 of K per CTA (4 accumulators x 512): bounds the truncation error
+                if (ksplit < minsplit) ksplit = minsplit;
+                if (ksplit < 1) ksplit = 1;
+            }
+            // op(A) = A^T (ta) means A is stored [K][M] (MN-major); op(B) = B (!tb) means B is stored [K][N] (MN-major)
+            if (!ta && tb) return t3::gemm_tf32x3_launch<false, false>(M, N, K, alpha, A, lda, B, ldb, C, ldc, bias, ksplit, accumulate, stream);
+            if (!ta && !tb) return t3::gemm_tf32x3_launch<false, true>(M, N, K, alpha, A, lda, B, ldb, C, ldc, bias, ksplit, accumulate, stream);
+            if (ta && tb) return t3::gemm_tf32x3_launch<true, false>(M, N, K, alpha, A, lda, B, ldb, C, ldc, bias, ksplit, accumulate, stream);
+            return t3::gemm_tf32x3_launch<true, true>(M, N, K, alpha, A, lda, B, ldb, C, ldc, bias, ksplit, accumulate, stream);
+        }
+    }
     dim3 grid(ceil_div(N, GB_N), ceil_div(M, GB_M), 1);
     int kslice = K > 0 ? K : 1;
     if (accumulate) {

@@ -172,7 +172,8 @@ sss_tc_build_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss
 
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);   // round to nearest tf32 (ties away), finite inputs
-    lo = x - hi;
+    // lo is rounded too: the tensor core truncates its operands, and a truncated remainder biases every product towards zero
+    lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void split_tf32(const float4& v, float4& h, float4& l) {
     split_tf32(v.x, h.x, l.x);
@@ -1455,7 +1456,7 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         tma_prefetch_desc(&map_l);
         tma_prefetch_desc(&map_s);
     }
-    if (warp == 1) tmem_alloc<256>(tmem_slot);
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -1486,18 +1487,23 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = idesc_tf32(128, 32 * nblk, true, true);
+            // the tensor core adds into its accumulator with truncation (an error linear in the number of additions): the CTA's
+            // samples are spread over two TMEM accumulators, and the host keeps the samples per CTA small
+            const int half = (t1 - t0 + 1) / 2;
             for (int t = t0, it = 0; t < t1; ++t, ++it) {
                 const int s = it % G2_STAGES, round = it / G2_STAGES;
                 mbar_wait(conv + s, round & 1);
                 tc_fence_after();
                 uint8_t* st = smem + s * G2_STAGE_BYTES;
+                const uint32_t acc = tmem_base + (it >= half ? 256u : 0u);
+                const int first = (it == 0 || it == half);
 #pragma unroll
                 for (int k = 0; k < G2_KS / 8; ++k) {   // 8 samples = 8 rows of 128 bytes = 1024 bytes per UMMA
                     const uint64_t da = desc_mnmajor_sw128_32b(st + k * 1024, G2_BLK);
                     const uint64_t dbh = desc_mnmajor_sw128_32b(st + G2_A_BYTES + k * 1024, G2_BLK);
                     const uint64_t dbl = desc_mnmajor_sw128_32b(st + G2_A_BYTES + G2_BH_BYTES + k * 1024, G2_BLK);
-                    mma_tf32(tmem_base, da, dbh, idesc, (it | k) ? 1u : 0u);
-                    mma_tf32(tmem_base, da, dbl, idesc, 1u);
+                    mma_tf32(acc, da, dbh, idesc, (first && k == 0) ? 0u : 1u);
+                    mma_tf32(acc, da, dbl, idesc, 1u);
                 }
                 umma_commit(empty + s);
             }
@@ -1544,14 +1550,19 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
         const int m = q * 32 + lane;
         float* drow = dM + ((size_t)ch * 64 + (m & 63)) * DMC;
         const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16);
+        const bool two = (t1 - t0) > 1;
         for (int c0 = 0; c0 < 32 * nblk; c0 += 16) {
-            uint32_t v[16];
+            uint32_t v[16], w[16];
             tmem_ld16_nowait(acc + c0, v);
+            if (two) tmem_ld16_nowait(acc + 256 + c0, w);
             tmem_ld_wait();
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + (two ? __uint_as_float(w[i]) : 0.f);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c0 + 4 * i), "f"(__uint_as_float(v[4 * i])),
-                             "f"(__uint_as_float(v[4 * i + 1])), "f"(__uint_as_float(v[4 * i + 2])), "f"(__uint_as_float(v[4 * i + 3]))
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c0 + 4 * i), "f"(f[4 * i]), "f"(f[4 * i + 1]), "f"(f[4 * i + 2]),
+                             "f"(f[4 * i + 3])
                              : "memory");
         }
     }
@@ -1559,7 +1570,7 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<256>(tmem_base);
+        tmem_dealloc<512>(tmem_base);
     }
 }
 
@@ -1857,6 +1868,8 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     if (int rc = make_map_f32(&ms, states, 32, (uint64_t)B, 32, G2_KS, (uint64_t)p->nchunks, (uint64_t)B * 32, true)) return rc;
     const int ntk = (int)((B + G2_KS - 1) / G2_KS);
     int nsplit = ceil_div(2 * sm_count(), p->nchunks);
+    const int split_for_accuracy = (int)((B + 2047) / 2048);   // <= 2048 samples per CTA, 1024 per TMEM accumulator
+    if (nsplit < split_for_accuracy) nsplit = split_for_accuracy;
     if (nsplit > ntk) nsplit = ntk;
     if (nsplit < 1) nsplit = 1;
     SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_grad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));

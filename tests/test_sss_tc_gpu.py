@@ -176,3 +176,29 @@ def test_tc_affine_map_at_full_batch(fused, built_lib, monkeypatch):
         y1, y2, y3 = layer(x1), layer(x2), layer(0.5 * x1 - 2.0 * x2)
         lin = 0.5 * (y1 - layer.bias) - 2.0 * (y2 - layer.bias) + layer.bias
     assert float((y3 - lin).abs().max() / lin.abs().max()) < 3e-5
+
+
+def test_full_batch_gradients_tc_vs_simt(built_lib, monkeypatch):
+    """BASELINE config C5's batch (65 536): the tensor-core path against the CUDA-core path (fp32 FMA accumulation), outputs and the
+    whole flat gradient.  Guards the accumulation-length bound of the gradient GEMM (the tensor core adds into its fp32 accumulator
+    with truncation; see csrc/sss_tc.cu) -- an error the small-batch oracle comparisons cannot see."""
+    B = 65536
+    sysm = random_mixed_system(4096, 1000, 500, 16, seed=5000)
+    layer = SSSLayer(4096, 1000, 0.105, nb_states=500, initial_system_approx=sysm).to("cuda")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand((B, 4096), device="cuda", generator=g) * 2 - 1
+    gy = (torch.rand((B, 1000), device="cuda", generator=g) * 2 - 1) / B
+    res = {}
+    for mode in ("tc", "simt"):
+        monkeypatch.setenv("SNB200_SSS_PATH", mode)
+        layer.zero_flat_grad()
+        for p in layer.parameters():
+            p.grad = None
+        y = layer(x)
+        y.backward(gy)
+        torch.cuda.synchronize()
+        res[mode] = (y.detach().double(), layer.flat_grad().detach().double().clone())
+        del y
+    ey = float((res["tc"][0] - res["simt"][0]).abs().max() / res["simt"][0].abs().max())
+    eg = float((res["tc"][1] - res["simt"][1]).abs().max() / res["simt"][1].abs().max())
+    assert ey < RTOL and eg < RTOL, (ey, eg)
