@@ -927,7 +927,7 @@ sss_tc_scan_bwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
 //       rows n < 48: [Whi(n,:) | Whi(n,:)], rows 48 + n: [Wlo(n,:) | 0], W = [O ; Phi] (48 x 16)   -> D[:, n] + D[:, 48 + n]
 //    kind 2/3 = backward lambda/mu, three 32-row sub-tiles: state (Phi^T), grad_y hi part (O^T), grad_y lo part (O^T).
 // ------------------------------------------------------------------------------------------
-constexpr int CH_PF = 8;                         // L2 prefetch distance (steps) of the per-sample rows
+constexpr int CH_PF = 3;                         // L2 prefetch distance (steps) of the per-sample rows
 constexpr int CW_ROWS = 96;
 constexpr int CW_TILE_FLOATS = CW_ROWS * 32;    // 3072 floats = 12 KB
 constexpr int CW_TILE_BYTES = CW_TILE_FLOATS * 4;
