@@ -32,8 +32,8 @@ class SnSssTcChunk(Structure):
 
 
 class SnSssTcPlan(Structure):
-    _fields_ = [(n, c_int32) for n in ("nb_states", "input_dim", "output_dim", "nchunks", "rows_aligned")] + \
-               [("reserved", c_int32 * 3), ("stages", c_void_p), ("chunks", c_void_p)]
+    _fields_ = [(n, c_int32) for n in ("nb_states", "input_dim", "output_dim", "nchunks", "rows_aligned", "chunk_param_floats")] + \
+               [("reserved", c_int32 * 2), ("stages", c_void_p), ("chunks", c_void_p)]
 
 
 class SnPsmEll(Structure):

@@ -43,15 +43,12 @@ __device__ __forceinline__ const sn_sss_stage& stage_of(const sn_sss_stage* stag
     return stages[dir * n + (dir == 0 ? k : n - 1 - k)];
 }
 
-// The parameters of one stage, staged in shared memory (compact row-major, as in the flat parameter buffer) with 4-byte
-// cp.async copies: every thread of the build kernels reads the same entries, so the global loads are issued once, coalesced and
-// one stage ahead, and the recursions read broadcast LDS.
+// The parameters of ALL stages of a chunk are copied into shared memory once, up front (compact row-major, as in the flat parameter
+// buffer; 4-byte cp.async, issued coalesced by the whole CTA): the stage recursions of the build kernels then run out of shared
+// memory with broadcast LDS and no global latency between stages.  The plan carries the largest per-chunk parameter count.
 constexpr int STG_IN_MAX = KBW * KB_MAX;   // 160
-struct StageSm {
-    float ss[DS * DS];              // d_out x d_in
-    float ys[SOUT_MAX * DS];        // out_dim x d_in
-    float su[DS * STG_IN_MAX];      // d_out x in_dim
-    float yu[SOUT_MAX * STG_IN_MAX];   // out_dim x in_dim
+struct StageP {
+    const float *ss, *ys, *su, *yu;   // d_out x d_in, out_dim x d_in, d_out x in_dim, out_dim x in_dim
 };
 __device__ __forceinline__ void cp_async4(float* dst, const float* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
@@ -59,19 +56,27 @@ __device__ __forceinline__ void cp_async4(float* dst, const float* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-__device__ __forceinline__ void stage_load_async(StageSm& sm, const sn_sss_stage& st, const float* __restrict__ params, int tid, int nthreads) {
-    const int n_ss = st.d_out * st.d_in, n_ys = st.out_dim * st.d_in, n_su = st.d_out * st.in_dim;
-    const int n_yu = st.off_yu >= 0 ? st.out_dim * st.in_dim : 0;
-    for (int i = tid; i < n_ss; i += nthreads) cp_async4(sm.ss + i, params + st.off_ss + i);
-    for (int i = tid; i < n_ys; i += nthreads) cp_async4(sm.ys + i, params + st.off_ys + i);
-    for (int i = tid; i < n_su; i += nthreads) cp_async4(sm.su + i, params + st.off_su + i);
-    for (int i = tid; i < n_yu; i += nthreads) cp_async4(sm.yu + i, params + st.off_yu + i);
+__device__ __forceinline__ void chunk_params_async(float* pbuf, StageP* ptrs, const sn_sss_stage* sdesc, int nst, const float* __restrict__ params, int tid,
+                                                   int nthreads) {
+    int off = 0;
+    for (int i = 0; i < nst; ++i) {
+        const sn_sss_stage& st = sdesc[i];
+        const int n_ss = st.d_out * st.d_in, n_ys = st.out_dim * st.d_in, n_su = st.d_out * st.in_dim;
+        const int n_yu = st.off_yu >= 0 ? st.out_dim * st.in_dim : 0;
+        float* p = pbuf + off;
+        if (tid == 0) ptrs[i] = StageP{p, p + n_ss, p + n_ss + n_ys, p + n_ss + n_ys + n_su};
+        for (int e = tid; e < n_ss; e += nthreads) cp_async4(p + e, params + st.off_ss + e);
+        for (int e = tid; e < n_ys; e += nthreads) cp_async4(p + n_ss + e, params + st.off_ys + e);
+        for (int e = tid; e < n_su; e += nthreads) cp_async4(p + n_ss + n_ys + e, params + st.off_su + e);
+        for (int e = tid; e < n_yu; e += nthreads) cp_async4(p + n_ss + n_ys + n_su + e, params + st.off_yu + e);
+        off += n_ss + n_ys + n_su + n_yu;
+    }
 }
 
 // One stage applied to one column of the chunk's "identity input": v (state entering) -> yv (the stage's outputs, if WITH_Y), v (state leaving).
 // Loops over the (few) outputs / state rows leave early instead of running 16 predicated-off iterations.
 template <bool WITH_Y>
-__device__ __forceinline__ void stage_apply(const sn_sss_stage& st, const StageSm& sm, float (&v)[DS], float (&yv)[SOUT_MAX], bool mine, int local) {
+__device__ __forceinline__ void stage_apply(const sn_sss_stage& st, const StageP& sm, float (&v)[DS], float (&yv)[SOUT_MAX], bool mine, int local) {
     const int d_in = st.d_in, d_out = st.d_out;
     if (WITH_Y) {
 #pragma unroll
@@ -116,8 +121,9 @@ __device__ __forceinline__ void store_hi_lo(float* W, int row, int t, float val)
 __global__ void __launch_bounds__(BUILD_THREADS)
 sss_tc_build_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss_tc_chunk* __restrict__ chunks, const float* __restrict__ params,
                     float* __restrict__ Wall, float* __restrict__ SCall) {
-    __shared__ StageSm sm[2];
+    extern __shared__ __align__(16) float build_smem[];
     __shared__ sn_sss_stage sdesc[LMAX];
+    __shared__ StageP sptr[LMAX];
     const sn_sss_tc_chunk c = chunks[blockIdx.x];
     const int dir = blockIdx.y, t = threadIdx.x;
     const bool is_in = t < c.ncols;
@@ -131,24 +137,20 @@ sss_tc_build_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss
     const int col = c.col0 + t;
     if (t < nst) sdesc[t] = stage_of(stages, n, dir, dir == 0 ? c.k_begin + t : c.k_end - 1 - t);
     __syncthreads();
-    stage_load_async(sm[0], sdesc[0], params, t, BUILD_THREADS);
+    chunk_params_async(build_smem, sptr, sdesc, nst, params, t, BUILD_THREADS);
     cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    if (!active) return;
     float v[DS], yv[SOUT_MAX];
 #pragma unroll
     for (int a = 0; a < DS; ++a) v[a] = (!is_in && a == sidx && sidx < sdesc[0].d_in) ? 1.f : 0.f;
     bool activated = false;
     for (int i = 0; i < nst; ++i) {
-        cp_async_wait_all();
-        __syncthreads();   // stage i is in sm[i & 1]; everybody is done with sm[(i + 1) & 1]
-        if (i + 1 < nst) {
-            stage_load_async(sm[(i + 1) & 1], sdesc[i + 1], params, t, BUILD_THREADS);
-            cp_async_commit();
-        }
-        if (!active) continue;
         const sn_sss_stage& st = sdesc[i];
         const int local = col - st.in_off;
         const bool mine = is_in && local >= 0 && local < st.in_dim;
-        stage_apply<true>(st, sm[i & 1], v, yv, mine, local);
+        stage_apply<true>(st, sptr[i], v, yv, mine, local);
         const int rbase = st.out_off - c.row0;
         const bool wr = dir == 0 ? (activated || mine) : activated;
 #pragma unroll
@@ -162,7 +164,6 @@ sss_tc_build_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss
         }
         if (mine) activated = true;
     }
-    if (!active) return;
 #pragma unroll
     for (int b = 0; b < DS; ++b) {
         if (is_in) store_hi_lo(W, PO + dir * DS + b, t, v[b]);
@@ -1578,31 +1579,43 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 // 6. chain rule through the chunk-matrix construction.  grid (nchunks, 2); thread = column as in the build kernel.
 //    Phase 1 replays the construction and stores the state entering every stage; phase 2 walks the stages backwards.
 // ------------------------------------------------------------------------------------------
-constexpr int BB_LD = 193;   // shared-memory row stride (odd: the 16 'a' rows of a dot product fall into distinct banks)
+// 6a serial part.  Scratch per (chunk, direction), feature-major over the 192 column threads:
+//      V[stage][16][192] state entering the stage | LAM[stage][16][192] adjoint of the state leaving it | GY[stage][16][192] its gy rows
+// 6b (sss_tc_build_red_kernel) turns them into the parameter gradients that are sums over the chunk's columns.
+constexpr int BB_PLANE = DS * BUILD_THREADS;          // floats of one [16][192] plane
+constexpr int BB_SCR = 3 * LMAX * BB_PLANE;           // per (chunk, direction)
 
 __global__ void __launch_bounds__(BUILD_THREADS)
 sss_tc_build_bwd_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss_tc_chunk* __restrict__ chunks, const float* __restrict__ params,
                         const float* __restrict__ dMall, float* __restrict__ scratch, float* __restrict__ gparams) {
-    extern __shared__ uint8_t bb_smem[];
-    StageSm* sm = reinterpret_cast<StageSm*>(bb_smem);                 // [2]
-    float* X = reinterpret_cast<float*>(sm + 2);                       // rows 0..15: lambda, 16..31: this stage's gy
-    float* V = X + (DS + SOUT_MAX) * BB_LD;                            // state entering the stage
+    extern __shared__ __align__(16) float build_smem[];
     __shared__ sn_sss_stage sdesc[LMAX];
+    __shared__ StageP sptr[LMAX];
+    float* dMs = build_smem;                      // the chunk's dM tile, 64 x 192
+    float* pbuf = build_smem + 64 * DMC;
     const sn_sss_tc_chunk c = chunks[blockIdx.x];
     const int dir = blockIdx.y, t = threadIdx.x;
     const bool is_in = t < c.ncols;
     const int sidx = t - c.ncols;
     const bool active = is_in || sidx < DS;
-    const int ncol_active = c.ncols + DS;
-    const float* dM = dMall + (size_t)blockIdx.x * 64 * DMC;
-    float* scr = scratch + ((size_t)blockIdx.x * 2 + dir) * LMAX * DS * BUILD_THREADS;
+    float* scr = scratch + ((size_t)blockIdx.x * 2 + dir) * BB_SCR;
+    float* Vs = scr;
+    float* Ls = scr + LMAX * BB_PLANE;
+    float* Gs = scr + 2 * LMAX * BB_PLANE;
     const int nst = c.k_end - c.k_begin;
     const int col = c.col0 + t;
     const int cidx = is_in ? t : c.nkb * KBW + dir * DS + sidx;
     if (t < nst) sdesc[t] = stage_of(stages, n, dir, dir == 0 ? c.k_begin + t : c.k_end - 1 - t);
+    {
+        const float4* src = reinterpret_cast<const float4*>(dMall + (size_t)blockIdx.x * 64 * DMC);
+        for (int e = t; e < 64 * DMC / 4; e += BUILD_THREADS)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dMs + 4 * e)), "l"(src + e) : "memory");
+    }
     __syncthreads();
-    stage_load_async(sm[0], sdesc[0], params, t, BUILD_THREADS);
+    chunk_params_async(pbuf, sptr, sdesc, nst, params, t, BUILD_THREADS);
     cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
 
     float v[DS], yv[SOUT_MAX];
 #pragma unroll
@@ -1610,29 +1623,22 @@ sss_tc_build_bwd_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn
     int my_i = -1;
     // phase 1: replay the construction, keeping the state that enters every stage
     for (int i = 0; i < nst; ++i) {
-        cp_async_wait_all();
-        __syncthreads();
-        if (i + 1 < nst) {
-            stage_load_async(sm[(i + 1) & 1], sdesc[i + 1], params, t, BUILD_THREADS);
-            cp_async_commit();
-        }
         const sn_sss_stage& st = sdesc[i];
         const int local = col - st.in_off;
         const bool mine = is_in && local >= 0 && local < st.in_dim;
 #pragma unroll
-        for (int a = 0; a < DS; ++a) scr[(i * DS + a) * BUILD_THREADS + t] = v[a];
-        if (active) stage_apply<false>(st, sm[i & 1], v, yv, mine, local);
+        for (int a = 0; a < DS; ++a) Vs[(i * DS + a) * BUILD_THREADS + t] = v[a];
+        if (active) stage_apply<false>(st, sptr[i], v, yv, mine, local);
         if (mine) my_i = i;
     }
     // adjoint of the state leaving the last stage: dR / dPhi rows of dM
     float lam[DS];
 #pragma unroll
-    for (int b = 0; b < DS; ++b) lam[b] = active ? dM[(PO + dir * DS + b) * DMC + cidx] : 0.f;
-
-    // phase 2: stages backwards; the last stage's parameters are still in sm[(nst - 1) & 1]
+    for (int b = 0; b < DS; ++b) lam[b] = active ? dMs[(PO + dir * DS + b) * DMC + cidx] : 0.f;
+    // phase 2: stages backwards
     for (int i = nst - 1; i >= 0; --i) {
         const sn_sss_stage& st = sdesc[i];
-        const StageSm& ps = sm[i & 1];
+        const StageP& ps = sptr[i];
         const int local = col - st.in_off;
         const bool mine = (i == my_i);
         const bool before = is_in ? (my_i >= 0 && my_i < i) : true;
@@ -1644,48 +1650,11 @@ sss_tc_build_bwd_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn
 #pragma unroll
         for (int r = 0; r < SOUT_MAX; ++r) {
             if (r >= st.out_dim) break;
-            if (support) g[r] = dM[(rbase + r) * DMC + cidx];
+            if (support) g[r] = dMs[(rbase + r) * DMC + cidx];
+            Gs[(i * DS + r) * BUILD_THREADS + t] = g[r];
         }
 #pragma unroll
-        for (int a = 0; a < DS; ++a) v[a] = scr[(i * DS + a) * BUILD_THREADS + t];
-        cp_async_wait_all();
-        __syncthreads();   // stage i's parameters have landed; the previous iteration is done with X / V and sm[(i + 1) & 1]
-        if (i > 0) {
-            stage_load_async(sm[(i - 1) & 1], sdesc[i - 1], params, t, BUILD_THREADS);
-            cp_async_commit();
-        }
-#pragma unroll
-        for (int b = 0; b < DS; ++b) X[b * BB_LD + t] = lam[b];
-#pragma unroll
-        for (int r = 0; r < SOUT_MAX; ++r) {
-            if (r >= st.out_dim) break;
-            X[(DS + r) * BB_LD + t] = g[r];
-        }
-#pragma unroll
-        for (int a = 0; a < DS; ++a) V[a * BB_LD + t] = v[a];
-        __syncthreads();
-        // d_ss[b][a] = sum_t lam_t[b] v_t[a] ;  d_ys[r][a] = sum_t g_t[r] v_t[a]
-        const int nrow_valid = DS + st.out_dim;   // rows DS.. are the gy rows
-        for (int o = t; o < nrow_valid * DS; o += BUILD_THREADS) {
-            const int rowi = o / DS, a = o % DS;
-            const bool ok = a < st.d_in && (rowi < DS ? rowi < st.d_out : true);
-            if (ok) {
-                const float* xr = X + rowi * BB_LD;
-                const float* vr = V + a * BB_LD;
-                float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-                int tt = 0;
-                for (; tt + 4 <= ncol_active; tt += 4) {
-                    acc0 = fmaf(xr[tt], vr[tt], acc0);
-                    acc1 = fmaf(xr[tt + 1], vr[tt + 1], acc1);
-                    acc2 = fmaf(xr[tt + 2], vr[tt + 2], acc2);
-                    acc3 = fmaf(xr[tt + 3], vr[tt + 3], acc3);
-                }
-                for (; tt < ncol_active; ++tt) acc0 = fmaf(xr[tt], vr[tt], acc0);
-                const float acc = (acc0 + acc1) + (acc2 + acc3);
-                if (rowi < DS) gparams[st.off_ss + rowi * st.d_in + a] += acc;
-                else gparams[st.off_ys + (rowi - DS) * st.d_in + a] += acc;
-            }
-        }
+        for (int b = 0; b < DS; ++b) Ls[(i * DS + b) * BUILD_THREADS + t] = lam[b];
         if (mine) {
 #pragma unroll
             for (int b = 0; b < DS; ++b) {
@@ -1724,7 +1693,52 @@ sss_tc_build_bwd_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn
         for (int a = 0; a < DS; ++a) lam[a] = nl[a];
     }
 }
-constexpr size_t BB_SMEM = 2 * sizeof(StageSm) + (size_t)((DS + SOUT_MAX) + DS) * BB_LD * sizeof(float);
+
+// 6b.  grid (nchunks * LMAX, 2): one CTA per (stage, direction): d_ss[b][a] = sum_t lam_t[b] v_t[a], d_ys[r][a] = sum_t g_t[r] v_t[a]
+constexpr int BR_THREADS = 256;
+constexpr int BR_LD = 196;   // floats per staged row (multiple of 4: float4 reads; 196 mod 32 = 4: the 8 lanes of a phase hit distinct bank groups)
+__global__ void __launch_bounds__(BR_THREADS)
+sss_tc_build_red_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss_tc_chunk* __restrict__ chunks, const float* __restrict__ scratch,
+                        float* __restrict__ gparams) {
+    __shared__ __align__(16) float Xs[(DS + SOUT_MAX) * BR_LD];
+    __shared__ __align__(16) float Vt[DS * BR_LD];
+    const int ch = blockIdx.x / LMAX, i = blockIdx.x % LMAX, dir = blockIdx.y;
+    const sn_sss_tc_chunk c = chunks[ch];
+    const int nst = c.k_end - c.k_begin;
+    if (i >= nst) return;
+    const sn_sss_stage st = stage_of(stages, n, dir, dir == 0 ? c.k_begin + i : c.k_end - 1 - i);
+    const float* scr = scratch + ((size_t)ch * 2 + dir) * BB_SCR;
+    const float* Vg = scr + (size_t)i * BB_PLANE;
+    const float* Lg = scr + (size_t)(LMAX + i) * BB_PLANE;
+    const float* Gg = scr + (size_t)(2 * LMAX + i) * BB_PLANE;
+    const int ncol = c.ncols + DS;                 // active columns
+    const int ncol4 = (ncol + 3) & ~3;
+    const int nrow = DS + st.out_dim;
+    for (int e = threadIdx.x; e < DS * ncol4; e += BR_THREADS) {
+        const int a = e / ncol4, tt = e % ncol4;
+        Vt[a * BR_LD + tt] = tt < ncol ? Vg[a * BUILD_THREADS + tt] : 0.f;
+        Xs[a * BR_LD + tt] = tt < ncol ? Lg[a * BUILD_THREADS + tt] : 0.f;
+    }
+    for (int e = threadIdx.x; e < st.out_dim * ncol4; e += BR_THREADS) {
+        const int r = e / ncol4, tt = e % ncol4;
+        Xs[(DS + r) * BR_LD + tt] = tt < ncol ? Gg[r * BUILD_THREADS + tt] : 0.f;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < nrow * DS; o += BR_THREADS) {
+        const int rowi = o / DS, a = o % DS;
+        if (a >= st.d_in || (rowi < DS && rowi >= st.d_out)) continue;
+        const float4* xr = reinterpret_cast<const float4*>(Xs + rowi * BR_LD);
+        const float4* vr = reinterpret_cast<const float4*>(Vt + a * BR_LD);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int q = 0; q < ncol4 / 4; ++q) {
+            const float4 xv = xr[q], vv = vr[q];
+            a0 = fmaf(xv.x, vv.x, a0); a1 = fmaf(xv.y, vv.y, a1); a2 = fmaf(xv.z, vv.z, a2); a3 = fmaf(xv.w, vv.w, a3);
+        }
+        const float acc = (a0 + a1) + (a2 + a3);
+        if (rowi < DS) gparams[st.off_ss + rowi * st.d_in + a] += acc;
+        else gparams[st.off_ys + (rowi - DS) * st.d_in + a] += acc;
+    }
+}
 
 int check_tc_plan(const sn_sss_tc_plan* p) {
     SN_CHECK_ARG(p != nullptr, "sss_tc: NULL plan");
@@ -1732,6 +1746,7 @@ int check_tc_plan(const sn_sss_tc_plan* p) {
     SN_CHECK_ARG(p->stages != nullptr && p->chunks != nullptr, "sss_tc: plan tables missing");
     SN_CHECK_ARG(p->input_dim % 4 == 0, "sss_tc: input_dim must be a multiple of 4 (TMA row pitch)");
     SN_CHECK_ARG(p->nchunks <= G1_MAX_CHUNKS, "sss_tc: more than %d chunks", G1_MAX_CHUNKS);
+    SN_CHECK_ARG(p->chunk_param_floats > 0 && p->chunk_param_floats <= 40960, "sss_tc: chunk_param_floats must be in 1..40960 (got %d)", p->chunk_param_floats);
     return 0;
 }
 
@@ -1756,10 +1771,13 @@ bool use_fused_forward(const sn_sss_tc_plan* p, int64_t B) {
     return false;   // the three-kernel path with the four-threads-per-sample scans is faster at every batch size measured so far
 }
 
-// chunk scans on the tensor core (default) or the SIMT four-threads-per-sample kernels (SNB200_SSS_TC_CHAIN=0; tests)
-bool use_tc_chain() {
+// Chunk scans: the tensor-core chain kernels are bounded below by (2 x chunks) serial steps of ~3 us whatever the batch, the SIMT
+// four-threads-per-sample kernels scale with the batch (8 ns / sample); measured crossover ~48 k samples per GPU.
+// SNB200_SSS_TC_CHAIN=0/1 forces the choice (tests).
+bool use_tc_chain(int64_t B) {
     const char* e = getenv("SNB200_SSS_TC_CHAIN");
-    return !(e != nullptr && e[0] == '0');
+    if (e != nullptr && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
+    return B >= 49152;
 }
 
 }  // namespace
@@ -1777,7 +1795,7 @@ size_t sn_sss_tc_rbuf_floats(const sn_sss_tc_plan* p, int64_t B) {
 size_t sn_sss_tc_states_floats(const sn_sss_tc_plan* p, int64_t B) { return p == nullptr || B <= 0 ? 0 : (size_t)p->nchunks * B * 32; }
 size_t sn_sss_tc_backward_workspace_floats(const sn_sss_tc_plan* p, int64_t B) {
     if (p == nullptr || B <= 0) return 0;
-    return (size_t)p->nchunks * B * 32 + (size_t)p->nchunks * 64 * DMC + (size_t)p->nchunks * 2 * LMAX * DS * BUILD_THREADS;
+    return (size_t)p->nchunks * B * 32 + (size_t)p->nchunks * 64 * DMC + (size_t)p->nchunks * 2 * BB_SCR;
 }
 
 int sn_sss_tc_build(const sn_sss_tc_plan* p, const float* params, float* coef, sn_stream_t stream) {
@@ -1785,7 +1803,9 @@ int sn_sss_tc_build(const sn_sss_tc_plan* p, const float* params, float* coef, s
     SN_CHECK_ARG(params && coef, "sss_tc_build: NULL buffer");
     float* W = coef;
     float* SC = coef + (size_t)p->nchunks * WROWS * WCOLS;
-    SN_LAUNCH("sss_tc_build_kernel", snb::as_stream(stream), sss_tc_build_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, 0, snb::as_stream(stream)>>>(p->stages, p->nb_states, p->chunks, params, W, SC));
+    const size_t bsm = (size_t)p->chunk_param_floats * sizeof(float);
+    SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    SN_LAUNCH("sss_tc_build_kernel", snb::as_stream(stream), sss_tc_build_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, bsm, snb::as_stream(stream)>>>(p->stages, p->nb_states, p->chunks, params, W, SC));
     float* CW = SC + (size_t)p->nchunks * SCF;
     SN_LAUNCH("sss_tc_pack_chain_kernel", snb::as_stream(stream), sss_tc_pack_chain_kernel<<<dim3(p->nchunks, 4), 256, 0, snb::as_stream(stream)>>>(SC, CW));
     return 0;
@@ -1817,7 +1837,7 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
     const int grid = (int)(total < sm_count() ? total : sm_count());
     SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_local_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G1_SMEM));
     SN_LAUNCH("sss_tc_local_gemm_kernel", st, sss_tc_local_gemm_kernel<<<grid, G1_THREADS, G1_SMEM, st>>>(mx, mw, p->chunks, p->nchunks, (long)B, ntiles, rbuf));
-    if (use_tc_chain()) {
+    if (use_tc_chain(B)) {
         CUtensorMap mc;
         const float* CW = SC + (size_t)p->nchunks * SCF;
         if (int rc = make_map_f32(&mc, CW, 32, (uint64_t)p->nchunks * 4 * CW_ROWS, 32, CW_ROWS)) return rc;
@@ -1847,7 +1867,7 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     float* dM = L + (size_t)p->nchunks * B * 32;
     float* scratch = dM + (size_t)p->nchunks * 64 * DMC;
     const int aligned = p->rows_aligned ? 1 : 0;
-    if (use_tc_chain()) {
+    if (use_tc_chain(B)) {
         CUtensorMap mc;
         const float* CW = SC + (size_t)p->nchunks * SCF;
         if (int rc = make_map_f32(&mc, CW, 32, (uint64_t)p->nchunks * 4 * CW_ROWS, 32, CW_ROWS)) return rc;
@@ -1874,8 +1894,10 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     if (nsplit < 1) nsplit = 1;
     SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_grad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
     SN_LAUNCH("sss_tc_grad_gemm_kernel", st, sss_tc_grad_gemm_kernel<<<dim3(nsplit, p->nchunks), G2_THREADS, G2_SMEM, st>>>(mx, mg, ml, ms, p->chunks, (long)B, dM));
-    SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BB_SMEM));
-    SN_LAUNCH("sss_tc_build_bwd_kernel", st, sss_tc_build_bwd_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, BB_SMEM, st>>>(p->stages, p->nb_states, p->chunks, params, dM, scratch, grad_params));
+    const size_t bsm = ((size_t)64 * DMC + p->chunk_param_floats) * sizeof(float);
+    SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    SN_LAUNCH("sss_tc_build_bwd_kernel", st, sss_tc_build_bwd_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, bsm, st>>>(p->stages, p->nb_states, p->chunks, params, dM, scratch, grad_params));
+    SN_LAUNCH("sss_tc_build_red_kernel", st, sss_tc_build_red_kernel<<<dim3(p->nchunks * LMAX, 2), BR_THREADS, 0, st>>>(p->stages, p->nb_states, p->chunks, scratch, grad_params));
     return 0;
 }
 

@@ -356,7 +356,12 @@ class SSSLayer(FlatParamsMixin, StructuredLayer):
             chunks.append([k0, k, int(in_off[k0]), nin, int(out_off[k0]), nout, (nin + self.TC_KB - 1) // self.TC_KB, 0])
         chunks = np.asarray(chunks, dtype=np.int32)
         rows_aligned = int(np.all(chunks[:, 4] % 4 == 0))
-        return dict(chunks=chunks, rows_aligned=rows_aligned)
+        # the build kernels keep every parameter of one direction of a chunk in shared memory
+        per_stage = [(sum(int(getattr(self, nm)[k].numel()) for nm in "ABCD"), sum(int(getattr(self, nm)[k].numel()) for nm in "EFG")) for k in range(n)]
+        pmax = max(max(sum(ps[d] for ps in per_stage[k0:k1]) for d in (0, 1)) for k0, k1 in chunks[:, :2])
+        if pmax > 40960:
+            return None
+        return dict(chunks=chunks, rows_aligned=rows_aligned, chunk_param_floats=max(int(pmax), 1))
 
     def _tc_plan(self, device):
         tc = self.__dict__.get("_dev_tc_plan")
@@ -370,6 +375,7 @@ class SSSLayer(FlatParamsMixin, StructuredLayer):
         struct.nb_states, struct.input_dim, struct.output_dim = self.nb_states, self.input_dim, self.output_dim
         struct.nchunks = host["chunks"].shape[0]
         struct.rows_aligned = host["rows_aligned"]
+        struct.chunk_param_floats = host["chunk_param_floats"]
         struct.stages = plan["stages"].data_ptr()
         struct.chunks = ch_dev.data_ptr()
         ncoef = int(_lib.lib().sn_sss_tc_coef_floats(ctypes.byref(struct)))
