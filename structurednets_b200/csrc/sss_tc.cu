@@ -48,7 +48,7 @@ __device__ __forceinline__ const sn_sss_stage& stage_of(const sn_sss_stage* stag
 // memory with broadcast LDS and no global latency between stages.  The plan carries the largest per-chunk parameter count.
 constexpr int STG_IN_MAX = KBW * KB_MAX;   // 160
 struct StageP {
-    const float *ss, *ys, *su, *yu;   // d_out x d_in, out_dim x d_in, d_out x in_dim, out_dim x in_dim
+    int ss, ys, su, yu;   // float offsets into the chunk's parameter buffer: d_out x d_in, out_dim x d_in, d_out x in_dim, out_dim x in_dim
 };
 __device__ __forceinline__ void cp_async4(float* dst, const float* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
@@ -56,6 +56,8 @@ __device__ __forceinline__ void cp_async4(float* dst, const float* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// every sub-array starts on a 16-byte boundary, so full-width (16-column) rows can be read as float4
+__device__ __forceinline__ int pad4(int x) { return (x + 3) & ~3; }
 __device__ __forceinline__ void chunk_params_async(float* pbuf, StageP* ptrs, const sn_sss_stage* sdesc, int nst, const float* __restrict__ params, int tid,
                                                    int nthreads) {
     int off = 0;
@@ -63,47 +65,82 @@ __device__ __forceinline__ void chunk_params_async(float* pbuf, StageP* ptrs, co
         const sn_sss_stage& st = sdesc[i];
         const int n_ss = st.d_out * st.d_in, n_ys = st.out_dim * st.d_in, n_su = st.d_out * st.in_dim;
         const int n_yu = st.off_yu >= 0 ? st.out_dim * st.in_dim : 0;
-        float* p = pbuf + off;
-        if (tid == 0) ptrs[i] = StageP{p, p + n_ss, p + n_ss + n_ys, p + n_ss + n_ys + n_su};
-        for (int e = tid; e < n_ss; e += nthreads) cp_async4(p + e, params + st.off_ss + e);
-        for (int e = tid; e < n_ys; e += nthreads) cp_async4(p + n_ss + e, params + st.off_ys + e);
-        for (int e = tid; e < n_su; e += nthreads) cp_async4(p + n_ss + n_ys + e, params + st.off_su + e);
-        for (int e = tid; e < n_yu; e += nthreads) cp_async4(p + n_ss + n_ys + n_su + e, params + st.off_yu + e);
-        off += n_ss + n_ys + n_su + n_yu;
+        const int o_ss = off, o_ys = o_ss + pad4(n_ss), o_su = o_ys + pad4(n_ys), o_yu = o_su + pad4(n_su);
+        if (tid == 0) ptrs[i] = StageP{o_ss, o_ys, o_su, o_yu};
+        for (int e = tid; e < n_ss; e += nthreads) cp_async4(pbuf + o_ss + e, params + st.off_ss + e);
+        for (int e = tid; e < n_ys; e += nthreads) cp_async4(pbuf + o_ys + e, params + st.off_ys + e);
+        for (int e = tid; e < n_su; e += nthreads) cp_async4(pbuf + o_su + e, params + st.off_su + e);
+        for (int e = tid; e < n_yu; e += nthreads) cp_async4(pbuf + o_yu + e, params + st.off_yu + e);
+        off = o_yu + pad4(n_yu);
+    }
+}
+
+__device__ __forceinline__ float dot16(const float* __restrict__ row, const float (&v)[DS]) {   // row: 16 floats, 16-byte aligned, shared memory
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 m = r4[q];
+        acc = fmaf(m.x, v[4 * q], acc); acc = fmaf(m.y, v[4 * q + 1], acc); acc = fmaf(m.z, v[4 * q + 2], acc); acc = fmaf(m.w, v[4 * q + 3], acc);
+    }
+    return acc;
+}
+__device__ __forceinline__ void axpy_row16(const float* __restrict__ row, float w, float (&out)[DS]) {   // out[a] += row[a] * w
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 m = r4[q];
+        out[4 * q] = fmaf(m.x, w, out[4 * q]); out[4 * q + 1] = fmaf(m.y, w, out[4 * q + 1]);
+        out[4 * q + 2] = fmaf(m.z, w, out[4 * q + 2]); out[4 * q + 3] = fmaf(m.w, w, out[4 * q + 3]);
     }
 }
 
 // One stage applied to one column of the chunk's "identity input": v (state entering) -> yv (the stage's outputs, if WITH_Y), v (state leaving).
-// Loops over the (few) outputs / state rows leave early instead of running 16 predicated-off iterations.
+// Full-width stages (state dimension 16 in and out: all but the boundary stages) take the float4 path.
 template <bool WITH_Y>
-__device__ __forceinline__ void stage_apply(const sn_sss_stage& st, const StageP& sm, float (&v)[DS], float (&yv)[SOUT_MAX], bool mine, int local) {
+__device__ __forceinline__ void stage_apply(const sn_sss_stage& st, const float* pbuf, const StageP& sp, float (&v)[DS], float (&yv)[SOUT_MAX], bool mine,
+                                            int local) {
     const int d_in = st.d_in, d_out = st.d_out;
+    const float* ss = pbuf + sp.ss;
+    const float* ys = pbuf + sp.ys;
+    const bool wide = d_in == DS;
     if (WITH_Y) {
 #pragma unroll
         for (int r = 0; r < SOUT_MAX; ++r) {
             if (r >= st.out_dim) break;
             float acc = 0.f;
-            const float* ys = sm.ys + r * d_in;
+            if (wide) {
+                acc = dot16(ys + r * DS, v);
+            } else {
 #pragma unroll
-            for (int a = 0; a < DS; ++a)
-                if (a < d_in) acc = fmaf(ys[a], v[a], acc);
-            if (mine && st.off_yu >= 0) acc += sm.yu[r * st.in_dim + local];
+                for (int a = 0; a < DS; ++a)
+                    if (a < d_in) acc = fmaf(ys[r * d_in + a], v[a], acc);
+            }
+            if (mine && st.off_yu >= 0) acc += pbuf[sp.yu + r * st.in_dim + local];
             yv[r] = acc;
         }
     }
     float nv[DS];
+    if (wide && d_out == DS) {
 #pragma unroll
-    for (int b = 0; b < DS; ++b) nv[b] = 0.f;
+        for (int b = 0; b < DS; ++b) nv[b] = dot16(ss + b * DS, v);
+    } else {
 #pragma unroll
-    for (int b = 0; b < DS; ++b) {
-        if (b >= d_out) break;
-        float acc = 0.f;
-        const float* ss = sm.ss + b * d_in;
+        for (int b = 0; b < DS; ++b) nv[b] = 0.f;
 #pragma unroll
-        for (int a = 0; a < DS; ++a)
-            if (a < d_in) acc = fmaf(ss[a], v[a], acc);
-        if (mine) acc += sm.su[b * st.in_dim + local];
-        nv[b] = acc;
+        for (int b = 0; b < DS; ++b) {
+            if (b >= d_out) break;
+            float acc = 0.f;
+#pragma unroll
+            for (int a = 0; a < DS; ++a)
+                if (a < d_in) acc = fmaf(ss[b * d_in + a], v[a], acc);
+            nv[b] = acc;
+        }
+    }
+    if (mine) {
+#pragma unroll
+        for (int b = 0; b < DS; ++b)
+            if (b < d_out) nv[b] += pbuf[sp.su + b * st.in_dim + local];
     }
 #pragma unroll
     for (int b = 0; b < DS; ++b) v[b] = nv[b];
@@ -150,7 +187,7 @@ sss_tc_build_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss
         const sn_sss_stage& st = sdesc[i];
         const int local = col - st.in_off;
         const bool mine = is_in && local >= 0 && local < st.in_dim;
-        stage_apply<true>(st, sptr[i], v, yv, mine, local);
+        stage_apply<true>(st, build_smem, sptr[i], v, yv, mine, local);
         const int rbase = st.out_off - c.row0;
         const bool wr = dir == 0 ? (activated || mine) : activated;
 #pragma unroll
@@ -1628,7 +1665,7 @@ sss_tc_build_bwd_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn
         const bool mine = is_in && local >= 0 && local < st.in_dim;
 #pragma unroll
         for (int a = 0; a < DS; ++a) Vs[(i * DS + a) * BUILD_THREADS + t] = v[a];
-        if (active) stage_apply<false>(st, sptr[i], v, yv, mine, local);
+        if (active) stage_apply<false>(st, pbuf, sptr[i], v, yv, mine, local);
         if (mine) my_i = i;
     }
     // adjoint of the state leaving the last stage: dR / dPhi rows of dM
@@ -1673,21 +1710,30 @@ sss_tc_build_bwd_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn
         float nl[DS];
 #pragma unroll
         for (int a = 0; a < DS; ++a) nl[a] = 0.f;
+        const float* ss = pbuf + ps.ss;
+        const float* ys = pbuf + ps.ys;
+        if (st.d_in == DS && st.d_out == DS) {
 #pragma unroll
-        for (int b = 0; b < DS; ++b) {
-            if (b >= st.d_out) break;
-            const float* ss = ps.ss + b * st.d_in;
+            for (int b = 0; b < DS; ++b) axpy_row16(ss + b * DS, lam[b], nl);
+        } else {
 #pragma unroll
-            for (int a = 0; a < DS; ++a)
-                if (a < st.d_in) nl[a] = fmaf(ss[a], lam[b], nl[a]);
+            for (int b = 0; b < DS; ++b) {
+                if (b >= st.d_out) break;
+#pragma unroll
+                for (int a = 0; a < DS; ++a)
+                    if (a < st.d_in) nl[a] = fmaf(ss[b * st.d_in + a], lam[b], nl[a]);
+            }
         }
 #pragma unroll
         for (int r = 0; r < SOUT_MAX; ++r) {
             if (r >= st.out_dim) break;
-            const float* ys = ps.ys + r * st.d_in;
+            if (st.d_in == DS) {
+                axpy_row16(ys + r * DS, g[r], nl);
+            } else {
 #pragma unroll
-            for (int a = 0; a < DS; ++a)
-                if (a < st.d_in) nl[a] = fmaf(ys[a], g[r], nl[a]);
+                for (int a = 0; a < DS; ++a)
+                    if (a < st.d_in) nl[a] = fmaf(ys[r * st.d_in + a], g[r], nl[a]);
+            }
         }
 #pragma unroll
         for (int a = 0; a < DS; ++a) lam[a] = nl[a];

@@ -357,7 +357,8 @@ class SSSLayer(FlatParamsMixin, StructuredLayer):
         chunks = np.asarray(chunks, dtype=np.int32)
         rows_aligned = int(np.all(chunks[:, 4] % 4 == 0))
         # the build kernels keep every parameter of one direction of a chunk in shared memory
-        per_stage = [(sum(int(getattr(self, nm)[k].numel()) for nm in "ABCD"), sum(int(getattr(self, nm)[k].numel()) for nm in "EFG")) for k in range(n)]
+        pad4 = lambda v: (int(v) + 3) // 4 * 4     # every sub-array starts on a 16-byte boundary in shared memory
+        per_stage = [(sum(pad4(getattr(self, nm)[k].numel()) for nm in "ABCD"), sum(pad4(getattr(self, nm)[k].numel()) for nm in "EFG")) for k in range(n)]
         pmax = max(max(sum(ps[d] for ps in per_stage[k0:k1]) for d in (0, 1)) for k0, k1 in chunks[:, :2])
         if pmax > 40960:
             return None
