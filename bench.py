@@ -418,10 +418,14 @@ def run_ours(args, wl):
         for p in loose:
             p.grad = None
 
+    grad_sync = None
+    if n_gpus > 1:
+        from structurednets_b200.distributed import GradSynchronizer
+        grad_sync = GradSynchronizer(layer)
+
     def sync_grads():
-        if n_gpus > 1:
-            from structurednets_b200.distributed import GradSynchronizer
-            GradSynchronizer(layer)()
+        if grad_sync is not None:
+            grad_sync()
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
@@ -467,10 +471,10 @@ def run_ours(args, wl):
     fwd_ms = float(np.mean([r[0].elapsed_time(r[1]) for r in recs]))
     bwd_ms = float(np.mean([r[1].elapsed_time(r[2]) for r in recs]))
 
-    # ---- pass 2 (single GPU): the same step captured once in a CUDA graph and replayed K times -- launch gaps and host
-    # overhead (autograd, ctypes, tensor-map encoding) leave the timed region; the kernels are the same
+    # ---- pass 2: the same step captured once in a CUDA graph and replayed K times -- launch gaps and host overhead (autograd,
+    # ctypes, tensor-map encoding) leave the timed region; the kernels are the same
     graph_note = "eager launches"
-    if n_gpus == 1 and not args.no_graph:
+    if not args.no_graph:   # multi-GPU: the NCCL all-reduce of the flat gradient is captured with the step
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -486,12 +490,12 @@ def run_ours(args, wl):
             torch.cuda.synchronize()
             g0, g1 = ev(), ev()
             with ClockSampler(local_rank) as clocks:
-                torch.cuda.synchronize()
+                barrier()
                 g0.record()
                 for _ in range(args.steps):
                     graph.replay()
                 g1.record()
-                torch.cuda.synchronize()
+                barrier()
             elapsed_ms = g0.elapsed_time(g1)
             graph_note = "one step captured in a CUDA graph, replayed %d times" % args.steps
         except Exception as e:   # a layer whose step cannot be captured (host synchronisation inside) keeps the eager number
@@ -562,7 +566,12 @@ def run_ours(args, wl):
                     roofline=roofline, cpu_baseline=cpu_base)
         print(json.dumps(line))
     if n_gpus > 1:
-        dist.destroy_process_group()
+        # a captured graph holds NCCL work; tearing the process group down underneath it can hang -- make sure every rank is
+        # done, flush, and leave without running the destructors
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -708,7 +708,7 @@ sss_tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 //    output / grad_y columns 8q..8q+7), forms partial matrix-vector products over its own components and the quad combines
 //    them with a 2-step shuffle reduce-scatter.  Coefficients are double-buffered in shared memory with 16-byte cp.async.
 // ------------------------------------------------------------------------------------------
-constexpr int QS_THREADS = 128;   // 32 samples x 4 threads
+constexpr int QS_THREADS = 128;   // 32 samples x 4 threads (64 threads = 16 samples per CTA below 16 k samples: more CTAs per SM)
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
@@ -747,7 +747,7 @@ __device__ __forceinline__ void axpy16(const float4* __restrict__ M, float w, fl
     }
 }
 __device__ __forceinline__ void sc_prefetch(float4* dst, const float* __restrict__ src, int nfloat4) {
-    for (int i = threadIdx.x; i < nfloat4; i += QS_THREADS) cp_async16(dst + i, reinterpret_cast<const float4*>(src) + i);
+    for (int i = threadIdx.x; i < nfloat4; i += blockDim.x) cp_async16(dst + i, reinterpret_cast<const float4*>(src) + i);
 }
 
 __global__ void __launch_bounds__(QS_THREADS)
@@ -755,7 +755,7 @@ sss_tc_scan_fwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
                          float* __restrict__ S, float* __restrict__ y, long ldy, const float* __restrict__ bias, long B, int aligned) {
     __shared__ float4 sc[2][SCF / 4];
     const int q = threadIdx.x & 3;
-    const long row = (long)blockIdx.x * (QS_THREADS / 4) + (threadIdx.x >> 2);
+    const long row = (long)blockIdx.x * (blockDim.x / 4) + (threadIdx.x >> 2);
     const bool valid = row < B;
     const long rr = valid ? row : 0;
     // ---- anticausal states, top chunk first: S[j][row][16..31] = e_{j+1} ----
@@ -858,7 +858,7 @@ sss_tc_scan_fwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
 // followed by one float4 of padding -- the four quads' rows then start 16 bytes apart modulo 128 (conflict-free LDS.128)
 constexpr int QB_PHI = 4 * 17, QB_O = 4 * 33, QB_TOTAL = QB_PHI + QB_O;
 __device__ __forceinline__ void sc_prefetch_padded(float4* dst, const float* __restrict__ src, int nfloat4, int group) {
-    for (int i = threadIdx.x; i < nfloat4; i += QS_THREADS) cp_async16(dst + (i / group) * (group + 1) + (i % group), reinterpret_cast<const float4*>(src) + i);
+    for (int i = threadIdx.x; i < nfloat4; i += blockDim.x) cp_async16(dst + (i / group) * (group + 1) + (i % group), reinterpret_cast<const float4*>(src) + i);
 }
 
 template <bool MU>
@@ -948,7 +948,7 @@ sss_tc_scan_bwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
     __shared__ float sbias[64];
     if (threadIdx.x < 64) sbias[threadIdx.x] = 0.f;
     const int q = threadIdx.x & 3;
-    const long row = (long)blockIdx.x * (QS_THREADS / 4) + (threadIdx.x >> 2);
+    const long row = (long)blockIdx.x * (blockDim.x / 4) + (threadIdx.x >> 2);
     const bool valid = row < B;
     scan_bwd_pass<false>(sc, sbias, chunks, nchunks, SCall, gy, ldgy, L, gbias, B, aligned, q, row, valid);
     scan_bwd_pass<true>(sc, sbias, chunks, nchunks, SCall, gy, ldgy, L, gbias, B, aligned, q, row, valid);
@@ -1895,7 +1895,8 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
         SN_LAUNCH("sss_tc_chain_fwd_kernel", st, sss_tc_chain_fwd_kernel<<<ntiles, CH_THREADS, CHF_SMEM, st>>>(mc, mi, my, p->chunks, p->nchunks, rbuf, states, y, (long)ldy, bias, (long)B, aligned));
         return 0;
     }
-    SN_LAUNCH("sss_tc_scan_fwd_q_kernel", st, sss_tc_scan_fwd_q_kernel<<<(unsigned)((B + QS_THREADS / 4 - 1) / (QS_THREADS / 4)), QS_THREADS, 0, st>>>(p->chunks, p->nchunks, SC, rbuf, states, y,
+    const int qs_threads = B <= 16384 ? 64 : QS_THREADS;
+    SN_LAUNCH("sss_tc_scan_fwd_q_kernel", st, sss_tc_scan_fwd_q_kernel<<<(unsigned)((B + qs_threads / 4 - 1) / (qs_threads / 4)), qs_threads, 0, st>>>(p->chunks, p->nchunks, SC, rbuf, states, y,
                                                                                                              (long)ldy, bias, (long)B, aligned));
     return 0;
 }
@@ -1923,7 +1924,8 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHB_SMEM));
         SN_LAUNCH("sss_tc_chain_bwd_kernel", st, sss_tc_chain_bwd_kernel<<<(unsigned)((B + 127) / 128), CH_THREADS, CHB_SMEM, st>>>(mc, mgy, p->chunks, p->nchunks, L, grad_bias, (long)B));
     } else {
-        SN_LAUNCH("sss_tc_scan_bwd_q_kernel", st, sss_tc_scan_bwd_q_kernel<<<(unsigned)((B + QS_THREADS / 4 - 1) / (QS_THREADS / 4)), QS_THREADS, 0, st>>>(p->chunks, p->nchunks, SC, grad_y, (long)ldgy,
+        const int qs_threads = B <= 16384 ? 64 : QS_THREADS;
+    SN_LAUNCH("sss_tc_scan_bwd_q_kernel", st, sss_tc_scan_bwd_q_kernel<<<(unsigned)((B + qs_threads / 4 - 1) / (qs_threads / 4)), qs_threads, 0, st>>>(p->chunks, p->nchunks, SC, grad_y, (long)ldgy,
                                                                                                              L, grad_bias, (long)B, aligned));
     }
     SN_CHECK_CUDA(cudaMemsetAsync(dM, 0, (size_t)p->nchunks * 64 * DMC * sizeof(float), st));
