@@ -174,6 +174,13 @@ int sn_hmat_forward(const int32_t* leaves, int nleaves, const float* params, con
                     const float* bias, int64_t B, int in_dim, int out_dim, sn_stream_t stream);
 int sn_hmat_backward(const int32_t* leaves, int nleaves, const float* params, const float* x, int64_t ldx, const float* grad_y,
                      int64_t ldgy, float* grad_params, float* grad_bias, int64_t B, int in_dim, int out_dim, sn_stream_t stream);
+/* Dense-block path (default for layers whose dense matrix fits): W = the H-matrix as a dense (out_dim x in_dim) matrix built from
+ * the leaves (max_rows = the tallest leaf), applied / differentiated with sn_dense_apply / sn_dense_weight_grad on the tensor cores,
+ * and the dense gradient projected back onto the leaf factors (accumulated into grad_params). */
+int sn_hmat_build_dense(const int32_t* leaves, int nleaves, int max_rows, const float* params, float* W, int out_dim, int in_dim,
+                        sn_stream_t stream);
+int sn_hmat_project_grad(const int32_t* leaves, int nleaves, const float* params, const float* dW, int out_dim, int in_dim,
+                         float* grad_params, sn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * PSM layer -- replaces PSMLayer.forward / forward_sparse (layers/psm_layer.py:36-60) and its backward,

