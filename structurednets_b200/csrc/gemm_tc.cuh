@@ -205,9 +205,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * args.alpha;
                 if (EPI == ATOMIC_F32) {
                     float* d = reinterpret_cast<float*>(args.D) + (size_t)row * args.ldd + nbase;
+                    if (nbase + 16 <= args.N && ((reinterpret_cast<uintptr_t>(d) & 15) == 0)) {   // four 16-byte reductions instead of 16 scalar atomics
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (nbase + j < args.N) atomicAdd(d + j, f[j]);
+                        for (int j = 0; j < 4; ++j)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4 * j), "f"(f[4 * j]), "f"(f[4 * j + 1]), "f"(f[4 * j + 2]),
+                                         "f"(f[4 * j + 3])
+                                         : "memory");
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (nbase + j < args.N) atomicAdd(d + j, f[j]);
+                    }
                 } else {
                     if (args.bias != nullptr) {
 #pragma unroll

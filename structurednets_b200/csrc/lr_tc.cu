@@ -50,14 +50,28 @@ __global__ void transpose_bf16_kernel(const bf16* __restrict__ src, long lds, bf
     }
 }
 
+// out[c] += sum_r M[r][c]: a thread owns a pair of columns (one 4-byte load per row, coalesced along the row), 64-row slabs
 __global__ void colsum_bf16_kernel(const bf16* __restrict__ M, long ld, long rows, int cols, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
     if (c >= cols) return;
-    const long r0 = (long)blockIdx.y * 256;
-    const long r1 = r0 + 256 < rows ? r0 + 256 : rows;
-    float s = 0.f;
-    for (long r = r0; r < r1; ++r) s += __bfloat162float(M[r * ld + c]);
-    atomicAdd(out + c, s);
+    const long r0 = (long)blockIdx.y * 64;
+    const long r1 = r0 + 64 < rows ? r0 + 64 : rows;
+    float s0 = 0.f, s1 = 0.f;
+    if (c + 1 < cols && (ld & 1) == 0 && ((reinterpret_cast<uintptr_t>(M) & 3) == 0)) {
+#pragma unroll 8
+        for (long r = r0; r < r1; ++r) {
+            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(M + r * ld + c);
+            s0 += __bfloat162float(v.x);
+            s1 += __bfloat162float(v.y);
+        }
+    } else {
+        for (long r = r0; r < r1; ++r) {
+            s0 += __bfloat162float(M[r * ld + c]);
+            if (c + 1 < cols) s1 += __bfloat162float(M[r * ld + c + 1]);
+        }
+    }
+    atomicAdd(out + c, s0);
+    if (c + 1 < cols) atomicAdd(out + c + 1, s1);
 }
 
 int transpose_bf16(const bf16* src, long lds, bf16* dst, long ldd, long rows, int cols, cudaStream_t st) {
@@ -111,7 +125,7 @@ int sn_lr_tc_backward(const void* x, int64_t ldx, const void* grad_y, int64_t ld
     // gh = gy L : A = gy (B x out), B operand = L^T (rank x out), K = out
     if (int rc = gemm_bf16_tc<64, STORE_BF16>((int)B, rank, out_dim, grad_y, ldgy, left_t_bf16, lt_ld, ghid, rank, nullptr, 1.f, 1, st)) return rc;
     if (grad_bias) {
-        dim3 grid(snb::ceil_div(out_dim, 128), (unsigned)((B + 255) / 256));
+        dim3 grid(snb::ceil_div(out_dim, 256), (unsigned)((B + 63) / 64));
         SN_LAUNCH("colsum_bf16_kernel", st, colsum_bf16_kernel<<<grid, 128, 0, st>>>((const bf16*)grad_y, ldgy, B, out_dim, grad_bias));
     }
     const bool mn_ok = (rank % 64 == 0);   // MN-major operands are fetched in 64-element blocks along M / N
