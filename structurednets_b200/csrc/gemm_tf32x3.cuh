@@ -33,11 +33,11 @@ struct T3Args {
 // hi = round-to-nearest tf32 of x, lo = round-to-nearest tf32 of (x - hi).  The tensor core TRUNCATES the low 13 mantissa bits
 // of its operands; an unrounded lo part would make every product err towards zero, a bias that grows linearly with K.
 __device__ __forceinline__ float t3_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
-__device__ __forceinline__ void t3_split(const float4& v, float4& h, float4& l) {
-    h.x = t3_rn(v.x); l.x = t3_rn(v.x - h.x);
-    h.y = t3_rn(v.y); l.y = t3_rn(v.y - h.y);
-    h.z = t3_rn(v.z); l.z = t3_rn(v.z - h.z);
-    h.w = t3_rn(v.w); l.w = t3_rn(v.w - h.w);
+// lo = rn_tf32(x - trunc_tf32(x)): the raw fp32 tile serves as the hi operand because the tensor core truncates (verified on
+// sm_100a: parity unchanged when the in-place hi store is dropped), so the converters only write the lo tile.
+__device__ __forceinline__ float t3_lo(float x) { return t3_rn(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); }
+__device__ __forceinline__ void t3_lo4(const float4& v, float4& l) {
+    l.x = t3_lo(v.x); l.y = t3_lo(v.y); l.z = t3_lo(v.z); l.w = t3_lo(v.w);
 }
 
 template <bool A_MN, bool B_MN>
@@ -134,9 +134,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 for (int i = 0; i < 8; ++i) v[i] = h[ct + 128 * i];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    float4 hh, ll;
-                    t3_split(v[i], hh, ll);
-                    h[ct + 128 * i] = hh;
+                    float4 ll;
+                    t3_lo4(v[i], ll);
                     l[ct + 128 * i] = ll;
                 }
             }

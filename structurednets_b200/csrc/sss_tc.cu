@@ -213,6 +213,14 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     // lo is rounded too: the tensor core truncates its operands, and a truncated remainder biases every product towards zero
     lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
 }
+// lo part against the TRUNCATED hi part (what the tensor core itself makes of an unsplit fp32 operand)
+__device__ __forceinline__ float lo_of_trunc(float x) {
+    const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    return __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xFFFFE000u);
+}
+__device__ __forceinline__ void lo_of_trunc(const float4& v, float4& l) {
+    l.x = lo_of_trunc(v.x); l.y = lo_of_trunc(v.y); l.z = lo_of_trunc(v.z); l.w = lo_of_trunc(v.w);
+}
 __device__ __forceinline__ void split_tf32(const float4& v, float4& h, float4& l) {
     split_tf32(v.x, h.x, l.x);
     split_tf32(v.y, h.y, l.y);
@@ -336,9 +344,10 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
                 for (int i = 0; i < 8; ++i) v[i] = xh[ct + 128 * i];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    float4 h, l;
-                    split_tf32(v[i], h, l);
-                    xh[ct + 128 * i] = h;
+                    // the tensor core truncates its operands to tf32 (verified: parity is unchanged), so the raw tile already acts as
+                    // hi = trunc(x); only lo = rn(x - trunc(x)) is written
+                    float4 l;
+                    lo_of_trunc(v[i], l);
                     xl[ct + 128 * i] = l;
                 }
                 fence_async_smem();
@@ -1558,10 +1567,8 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 float4* l = h + 2 * G2_BLK / 16;
 #pragma unroll
                 for (int i = 0; i < 2 * G2_BLK / 16 / 128; ++i) {
-                    const float4 v = h[ct + 128 * i];
-                    float4 hh, ll;
-                    split_tf32(v, hh, ll);
-                    h[ct + 128 * i] = hh;
+                    float4 ll;
+                    lo_of_trunc(h[ct + 128 * i], ll);   // hi = the raw tile (the tensor core truncates)
                     l[ct + 128 * i] = ll;
                 }
             }
@@ -1571,10 +1578,8 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 const int n16 = nblk * G2_BLK / 16;
 #pragma unroll 4
                 for (int i = ct; i < n16; i += 128) {
-                    const float4 v = h[i];
-                    float4 hh, ll;
-                    split_tf32(v, hh, ll);
-                    h[i] = hh;
+                    float4 ll;
+                    lo_of_trunc(h[i], ll);
                     l[i] = ll;
                 }
             }
