@@ -378,9 +378,18 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
             mbar_arrive(acc_empty + b);
             const long row = (long)tile * 128 + q * 32 + lane;
             if (row < B) {
-                float4* dst = reinterpret_cast<float4*>(rbuf + ((size_t)ch * B + row) * 64);
+                // scratch layout: three dense arrays Y [chunk][B][32], R [chunk][B][16], R' [chunk][B][16] -- the scans read exactly the
+                // rows they need (a 64-float interleaved row made DRAM fetch the unused half as well)
+                const size_t NB = (size_t)nchunks * B, ri = (size_t)ch * B + row;
+                float4* dy = reinterpret_cast<float4*>(rbuf + ri * 32);
+                float4* dr = reinterpret_cast<float4*>(rbuf + NB * 32 + ri * 16);
+                float4* dp = reinterpret_cast<float4*>(rbuf + NB * 48 + ri * 16);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) dst[i] = make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+                for (int i = 0; i < 8; ++i) dy[i] = make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dr[i] = make_float4(out[32 + 4 * i], out[33 + 4 * i], out[34 + 4 * i], out[35 + 4 * i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dp[i] = make_float4(out[48 + 4 * i], out[49 + 4 * i], out[50 + 4 * i], out[51 + 4 * i]);
             }
         }
     }
@@ -773,7 +782,11 @@ sss_tc_scan_fwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
     cp_async_commit();
     cp_async_wait_all();
     __syncthreads();
-    float4 nr4 = valid ? __ldg(reinterpret_cast<const float4*>(rbuf + ((size_t)(nchunks - 1) * B + rr) * 64 + 48) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t NB = (size_t)nchunks * B;
+    const float* Yb = rbuf;               // [chunk][B][32]
+    const float* Rb = rbuf + NB * 32;     // [chunk][B][16]
+    const float* Rpb = rbuf + NB * 48;    // [chunk][B][16]
+    float4 nr4 = valid ? __ldg(reinterpret_cast<const float4*>(Rpb + ((size_t)(nchunks - 1) * B + rr) * 16) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int jj = 0; jj < nchunks; ++jj) {
         const int j = nchunks - 1 - jj;
         const float4* Pp = sc[jj & 1];
@@ -781,7 +794,7 @@ sss_tc_scan_fwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
         if (j > 0) {
             sc_prefetch(sc[(jj + 1) & 1], SCall + (size_t)(j - 1) * SCF + DS * DS, DS * DS / 4);
             cp_async_commit();
-            if (valid) nr4 = __ldg(reinterpret_cast<const float4*>(rbuf + ((size_t)(j - 1) * B + rr) * 64 + 48) + q);
+            if (valid) nr4 = __ldg(reinterpret_cast<const float4*>(Rpb + ((size_t)(j - 1) * B + rr) * 16) + q);
         }
         const size_t base = (size_t)j * B + rr;
         if (valid) *(reinterpret_cast<float4*>(S + base * 32 + DS) + q) = make_float4(e4[0], e4[1], e4[2], e4[3]);
@@ -801,8 +814,8 @@ sss_tc_scan_fwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 n_yl0 = z4, n_yl1 = z4, n_r4 = z4, n_ev = z4;
     if (valid) {
-        const float4* rp = reinterpret_cast<const float4*>(rbuf + (size_t)rr * 64);
-        n_yl0 = __ldg(rp + q); n_yl1 = __ldg(rp + 4 + q); n_r4 = __ldg(rp + 8 + q);
+        const float4* yp4 = reinterpret_cast<const float4*>(Yb + (size_t)rr * 32);
+        n_yl0 = __ldg(yp4 + q); n_yl1 = __ldg(yp4 + 4 + q); n_r4 = __ldg(reinterpret_cast<const float4*>(Rb + (size_t)rr * 16) + q);
         n_ev = *(reinterpret_cast<const float4*>(S + (size_t)rr * 32) + 4 + q);
     }
     cp_async_wait_all();
@@ -817,8 +830,8 @@ sss_tc_scan_fwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
             cp_async_commit();
             if (valid) {
                 const size_t nb = (size_t)(j + 1) * B + rr;
-                const float4* rp = reinterpret_cast<const float4*>(rbuf + nb * 64);
-                n_yl0 = __ldg(rp + q); n_yl1 = __ldg(rp + 4 + q); n_r4 = __ldg(rp + 8 + q);
+                const float4* yp4 = reinterpret_cast<const float4*>(Yb + nb * 32);
+                n_yl0 = __ldg(yp4 + q); n_yl1 = __ldg(yp4 + 4 + q); n_r4 = __ldg(reinterpret_cast<const float4*>(Rb + nb * 16) + q);
                 n_ev = *(reinterpret_cast<const float4*>(S + nb * 32) + 4 + q);
             }
         }
@@ -1139,13 +1152,13 @@ sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
                 const int rowc = (int)((long)j * B + (long)blockIdx.x * 128);
                 mbar_expect_tx(sm.full + s, CW_TILE_BYTES + 8192 + 16384);
                 tma_load_2d(slot, &map_cw, 0, (j * 4 + (anti ? 1 : 0)) * CW_ROWS, sm.full + s);
-                tma_load_2d(slot + CW_TILE_BYTES, &map_in, anti ? 48 : 32, rowc, sm.full + s);
+                tma_load_2d(slot + CW_TILE_BYTES, &map_in, 0, rowc + (anti ? (int)((long)nchunks * B) : 0), sm.full + s);   // R' rows follow the R rows
                 tma_load_2d(slot + CW_TILE_BYTES + 8192, &map_yl, 0, rowc, sm.full + s);
             };
             auto prefetch = [&](int t) {   // into L2 only
                 const int j = chunk_of(t);
                 const int rowc = (int)((long)j * B + (long)blockIdx.x * 128);
-                tma_prefetch_l2_2d(&map_in, t < nchunks ? 48 : 32, rowc);
+                tma_prefetch_l2_2d(&map_in, 0, rowc + (t < nchunks ? (int)((long)nchunks * B) : 0));
                 tma_prefetch_l2_2d(&map_yl, 0, rowc);
             };
             for (int t = 0; t < CH_PF && t < nsteps; ++t) prefetch(t);
@@ -1259,7 +1272,7 @@ sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
                 const int c0 = 4 * (i & 7);
                 if (row < B) {
                     if (anti) {
-                        *(reinterpret_cast<float4*>(rbuf + ((size_t)j * B + row) * 64) + (i & 7)) = yv[k];
+                        *(reinterpret_cast<float4*>(rbuf + ((size_t)j * B + row) * 32) + (i & 7)) = yv[k];
                     } else if (c0 < c.nrows) {
                         float* yp = y + row * ldy + c.row0 + c0;
                         if (aligned && c0 + 4 <= c.nrows) {
@@ -1894,8 +1907,10 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
         if (int rc = make_map_f32(&mc, CW, 32, (uint64_t)p->nchunks * 4 * CW_ROWS, 32, CW_ROWS)) return rc;
         CUtensorMap mi, my;
         SN_CHECK_ARG((long)p->nchunks * B < 2147483647L, "sss_tc_forward: nchunks * B exceeds the TMA coordinate range");
-        if (int rc = make_map_f32(&mi, rbuf, 64, (uint64_t)p->nchunks * B, 64, 128, 0, 0, false, 16)) return rc;
-        if (int rc = make_map_f32(&my, rbuf, 64, (uint64_t)p->nchunks * B, 64, 128)) return rc;
+        const uint64_t NB = (uint64_t)p->nchunks * B;
+        SN_CHECK_ARG(2 * NB < 2147483647ULL, "sss_tc_forward: 2 * nchunks * B exceeds the TMA coordinate range");
+        if (int rc = make_map_f32(&mi, rbuf + NB * 32, 16, 2 * NB, 16, 128, 0, 0, false, 16)) return rc;   // R rows, then R' rows
+        if (int rc = make_map_f32(&my, rbuf, 32, NB, 32, 128)) return rc;                                     // yloc / ytmp rows
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHF_SMEM));
         SN_LAUNCH("sss_tc_chain_fwd_kernel", st, sss_tc_chain_fwd_kernel<<<ntiles, CH_THREADS, CHF_SMEM, st>>>(mc, mi, my, p->chunks, p->nchunks, rbuf, states, y, (long)ldy, bias, (long)B, aligned));
         return 0;

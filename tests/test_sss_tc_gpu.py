@@ -79,7 +79,9 @@ def test_each_kernel_against_the_emulator(case, fused, chain, built_lib, monkeyp
     torch.cuda.synchronize()
     st = states.cpu().numpy().reshape(nc, B, 32)
     if not fused:
-        r = rbuf.cpu().numpy().reshape(nc, B, 64)
+        rb = rbuf.cpu().numpy()          # three dense arrays: Y [chunk][B][32], R [chunk][B][16], R' [chunk][B][16]
+        NB = nc * B
+        r = np.concatenate([rb[:NB * 32].reshape(nc, B, 32), rb[NB * 32:NB * 48].reshape(nc, B, 16), rb[NB * 48:NB * 64].reshape(nc, B, 16)], axis=2)
         lo = 32 if chain else 0      # the tensor-core scan overwrites yloc (columns 0..31) in place with yloc + O' e
         for j in range(nc):
             assert rel_err(r[j][:, lo:], info["loc"][j].detach().numpy()[:, lo:]) < RTOL, f"local GEMM chunk {j}"
