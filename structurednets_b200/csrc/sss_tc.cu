@@ -874,6 +874,98 @@ sss_tc_scan_fwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
     }
 }
 
+// Small-batch variant of the forward scans: the two state chains are independent of each other (only the OUTPUTS need both), so
+// they run as the two halves of one grid (blockIdx.y = direction, 32 serial iterations of a 16 x 16 product each), and the outputs
+// y_j = yloc_j + O_j s_j + O'_j e_{j+1} + b follow in a kernel that is parallel over (sample, chunk).  Half the serial depth of
+// sss_tc_scan_fwd_q_kernel and a third of its work inside the chains.
+__global__ void __launch_bounds__(QS_THREADS)
+sss_tc_scan_states_q_kernel(int nchunks, const float* __restrict__ SCall, const float* __restrict__ rbuf, float* __restrict__ S, long B) {
+    __shared__ float4 sc[2][DS * DS / 4];
+    const int q = threadIdx.x & 3, dir = blockIdx.y;
+    const long row = (long)blockIdx.x * (blockDim.x / 4) + (threadIdx.x >> 2);
+    const bool valid = row < B;
+    const long rr = valid ? row : 0;
+    const size_t NB = (size_t)nchunks * B;
+    const float* Rin = rbuf + NB * 32 + (dir ? NB * 16 : 0);     // r (causal) or r' (anticausal) rows, [chunk][B][16]
+    const int phi_off = dir * DS * DS;
+    auto chunk_at = [&](int jj) { return dir ? nchunks - 1 - jj : jj; };
+    float st4[4] = {0.f, 0.f, 0.f, 0.f};
+    sc_prefetch(sc[0], SCall + (size_t)chunk_at(0) * SCF + phi_off, DS * DS / 4);
+    cp_async_commit();
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 nr4 = valid ? __ldg(reinterpret_cast<const float4*>(Rin + ((size_t)chunk_at(0) * B + rr) * 16) + q) : z4;
+    cp_async_wait_all();
+    __syncthreads();
+    for (int jj = 0; jj < nchunks; ++jj) {
+        const int j = chunk_at(jj);
+        const float4* Pm = sc[jj & 1];
+        const float4 r4 = nr4;
+        if (jj + 1 < nchunks) {
+            const int jn = chunk_at(jj + 1);
+            sc_prefetch(sc[(jj + 1) & 1], SCall + (size_t)jn * SCF + phi_off, DS * DS / 4);
+            cp_async_commit();
+            if (valid) nr4 = __ldg(reinterpret_cast<const float4*>(Rin + ((size_t)jn * B + rr) * 16) + q);
+        }
+        if (valid) *(reinterpret_cast<float4*>(S + ((size_t)j * B + rr) * 32 + (dir ? DS : 0)) + q) = make_float4(st4[0], st4[1], st4[2], st4[3]);
+        float p[DS];
+#pragma unroll
+        for (int b = 0; b < DS; ++b) p[b] = dot4(Pm[b * 4 + q], st4);
+        float ns[4];
+        quad_reduce_scatter<DS>(p, q, ns);
+        st4[0] = r4.x + ns[0]; st4[1] = r4.y + ns[1]; st4[2] = r4.z + ns[2]; st4[3] = r4.w + ns[3];
+        cp_async_wait_all();
+        __syncthreads();
+    }
+}
+
+// grid (ceil(B / 32), nchunks), 128 threads = 32 samples x 4: the chunk's O and O' in shared memory
+__global__ void __launch_bounds__(QS_THREADS)
+sss_tc_scan_out_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, const float* __restrict__ SCall, const float* __restrict__ rbuf,
+                         const float* __restrict__ S, float* __restrict__ y, long ldy, const float* __restrict__ bias, long B, int aligned) {
+    __shared__ float4 sc[2 * PO * DS / 4];
+    const int j = blockIdx.y, q = threadIdx.x & 3;
+    const sn_sss_tc_chunk c = chunks[j];
+    for (int i = threadIdx.x; i < 2 * PO * DS / 4; i += QS_THREADS) sc[i] = __ldg(reinterpret_cast<const float4*>(SCall + (size_t)j * SCF + 2 * DS * DS) + i);
+    __syncthreads();
+    const float4* Om = sc;
+    const float4* Opm = sc + PO * DS / 4;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+        const long row = (long)blockIdx.x * (QS_THREADS / 4) + (threadIdx.x >> 2);
+        if (row >= B) return;   // whole quads leave together
+        const size_t base = (size_t)j * B + row;
+        const float4* sp = reinterpret_cast<const float4*>(S + base * 32);
+        const float4 sv = __ldg(sp + q), ev = __ldg(sp + 4 + q);
+        const float4* yp4 = reinterpret_cast<const float4*>(rbuf + base * 32);
+        const float4 yl0 = __ldg(yp4 + q), yl1 = __ldg(yp4 + 4 + q);
+        const float s4[4] = {sv.x, sv.y, sv.z, sv.w}, e4[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float py[DS];
+#pragma unroll
+            for (int cc = 0; cc < DS; ++cc) py[cc] = dot4(Om[(16 * h + cc) * 4 + q], s4) + dot4(Opm[(16 * h + cc) * 4 + q], e4);
+            float y4[4];
+            quad_reduce_scatter<DS>(py, q, y4);
+            const float4 yl = h ? yl1 : yl0;
+            y4[0] += yl.x; y4[1] += yl.y; y4[2] += yl.z; y4[3] += yl.w;
+            const int c0 = 16 * h + 4 * q;
+            if (c0 < c.nrows) {
+                float* yo = y + row * ldy + c.row0 + c0;
+                const float* bp = bias != nullptr ? bias + c.row0 + c0 : nullptr;
+                if (aligned && c0 + 4 <= c.nrows) {
+                    float4 b4 = z4;
+                    if (bp != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(bp));
+                    *reinterpret_cast<float4*>(yo) = make_float4(y4[0] + b4.x, y4[1] + b4.y, y4[2] + b4.z, y4[3] + b4.w);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (c0 + i < c.nrows) yo[i] = y4[i] + (bp != nullptr ? __ldg(bp + i) : 0.f);
+                }
+            }
+        }
+    }
+}
+
 // adjoint scans.  L[j][row][0..15] = lambda_{j+1} (adjoint of the causal state leaving chunk j), L[j][row][16..31] = mu_j (adjoint of
 // the anticausal state leaving chunk j); grad_bias += column sums of grad_y.
 // padded coefficient layout of the adjoint scans: thread q reads rows 4q.. of Phi and 8q.. of O, so every group of 4 (8) rows is
@@ -972,8 +1064,9 @@ sss_tc_scan_bwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
     const int q = threadIdx.x & 3;
     const long row = (long)blockIdx.x * (blockDim.x / 4) + (threadIdx.x >> 2);
     const bool valid = row < B;
-    scan_bwd_pass<false>(sc, sbias, chunks, nchunks, SCall, gy, ldgy, L, gbias, B, aligned, q, row, valid);
-    scan_bwd_pass<true>(sc, sbias, chunks, nchunks, SCall, gy, ldgy, L, gbias, B, aligned, q, row, valid);
+    // gridDim.y == 2: one direction per CTA (half the serial depth; small batches); gridDim.y == 1: both, one after the other
+    if (gridDim.y == 1 || blockIdx.y == 0) scan_bwd_pass<false>(sc, sbias, chunks, nchunks, SCall, gy, ldgy, L, gbias, B, aligned, q, row, valid);
+    if (gridDim.y == 1 || blockIdx.y == 1) scan_bwd_pass<true>(sc, sbias, chunks, nchunks, SCall, gy, ldgy, L, gbias, B, aligned, q, row, valid);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1844,6 +1937,13 @@ bool use_tc_chain(int64_t B) {
     return B >= 49152;
 }
 
+// SIMT scans: split by direction (+ a parallel output kernel) by default; SNB200_SSS_SPLIT_SCANS=0 keeps the single-kernel scans
+bool use_split_scans(int64_t B) {
+    (void)B;
+    const char* e = getenv("SNB200_SSS_SPLIT_SCANS");
+    return !(e != nullptr && e[0] == '0');
+}
+
 }  // namespace
 
 extern "C" {
@@ -1916,6 +2016,11 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
         return 0;
     }
     const int qs_threads = B <= 16384 ? 64 : QS_THREADS;
+    if (use_split_scans(B)) {
+        SN_LAUNCH("sss_tc_scan_states_q_kernel", st, sss_tc_scan_states_q_kernel<<<dim3((unsigned)((B + qs_threads / 4 - 1) / (qs_threads / 4)), 2), qs_threads, 0, st>>>(p->nchunks, SC, rbuf, states, (long)B));
+        SN_LAUNCH("sss_tc_scan_out_q_kernel", st, sss_tc_scan_out_q_kernel<<<dim3((unsigned)((B + 31) / 32), p->nchunks), QS_THREADS, 0, st>>>(p->chunks, SC, rbuf, states, y, (long)ldy, bias, (long)B, aligned));
+        return 0;
+    }
     SN_LAUNCH("sss_tc_scan_fwd_q_kernel", st, sss_tc_scan_fwd_q_kernel<<<(unsigned)((B + qs_threads / 4 - 1) / (qs_threads / 4)), qs_threads, 0, st>>>(p->chunks, p->nchunks, SC, rbuf, states, y,
                                                                                                              (long)ldy, bias, (long)B, aligned));
     return 0;
@@ -1945,8 +2050,9 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
         SN_LAUNCH("sss_tc_chain_bwd_kernel", st, sss_tc_chain_bwd_kernel<<<(unsigned)((B + 127) / 128), CH_THREADS, CHB_SMEM, st>>>(mc, mgy, p->chunks, p->nchunks, L, grad_bias, (long)B));
     } else {
         const int qs_threads = B <= 16384 ? 64 : QS_THREADS;
-    SN_LAUNCH("sss_tc_scan_bwd_q_kernel", st, sss_tc_scan_bwd_q_kernel<<<(unsigned)((B + qs_threads / 4 - 1) / (qs_threads / 4)), qs_threads, 0, st>>>(p->chunks, p->nchunks, SC, grad_y, (long)ldgy,
-                                                                                                             L, grad_bias, (long)B, aligned));
+        const unsigned ydim = use_split_scans(B) ? 2u : 1u;
+        SN_LAUNCH("sss_tc_scan_bwd_q_kernel", st, sss_tc_scan_bwd_q_kernel<<<dim3((unsigned)((B + qs_threads / 4 - 1) / (qs_threads / 4)), ydim), qs_threads, 0, st>>>(p->chunks, p->nchunks, SC, grad_y, (long)ldgy,
+                                                                                                                             L, grad_bias, (long)B, aligned));
     }
     SN_CHECK_CUDA(cudaMemsetAsync(dM, 0, (size_t)p->nchunks * 64 * DMC * sizeof(float), st));
     CUtensorMap mx, mg, ml, ms;
