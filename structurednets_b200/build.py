@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-cudart", "static",
     "-I", os.path.join(REPO_DIR, "include"),
     "-I", CSRC,
-]
+] + os.environ.get("SNB200_NVCC_EXTRA", "").split()
 
 
 def sources():

@@ -22,6 +22,19 @@ constexpr int STAGES = 4;
 constexpr int THREADS = 192;  // 6 warps
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// one lane of a converged warp; the compiler then knows the region is single-lane and issues UTCHMMA / UTMALDG / UTCBAR without
+// its per-lane election loop (which costs ~50 cycles per instruction on the chain's critical path)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -148,7 +161,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES, round = kb / STAGES;
                 if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
@@ -166,7 +179,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(BM, BN, MN);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES, round = kb / STAGES;

@@ -75,7 +75,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % T3_STAGES, round = kb / T3_STAGES;
                 if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
@@ -97,7 +97,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = idesc_tf32(128, 128, A_MN, B_MN);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % T3_STAGES, round = kb / T3_STAGES;

@@ -133,7 +133,7 @@ lr_tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int it = 0;
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int s = it % LF_STAGES, round = it / LF_STAGES;
@@ -154,7 +154,7 @@ lr_tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_bf16(128, 128, false);
             int it = 0;
             for (int kb = 0; kb < nkb; ++kb, ++it) {

@@ -275,7 +275,7 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             // x boxes are pulled into L2 G1_PF items ahead of the shared-memory pipeline: 4 stages alone do not cover the HBM latency
             auto prefetch_item = [&](long w) {
                 const int tile = (int)(w / nchunks), ch = (int)(w % nchunks);
@@ -299,7 +299,7 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc1 = idesc_tf32(128, 128, false, false);   // x_hi * [W_hi ; W_lo]
             constexpr uint32_t idesc2 = idesc_tf32(128, 64, false, false);    // x_lo * W_hi
             uint32_t it = 0, ai = 0;
@@ -510,7 +510,7 @@ sss_tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0;
             for (int tile = t0; tile < t1; ++tile) {
                 for (int ch = 0; ch < nchunks; ++ch) {
@@ -527,7 +527,7 @@ sss_tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc1 = idesc_tf32(128, 128, false, false);
             constexpr uint32_t idesc2 = idesc_tf32(128, 64, false, false);
             uint32_t it = 0, ai = 0;
@@ -1116,22 +1116,125 @@ sss_tc_pack_chain_kernel(const float* __restrict__ SCall, float* __restrict__ CW
     }
 }
 
-// thread `row` writes 32 floats (v[0..31]) as its 128-byte row of a K-major SWIZZLE_128B tile
-__device__ __forceinline__ void store_row_sw128(uint8_t* tile, int row, const float (&v)[32]) {
-    uint8_t* base = tile + row * 128;
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<float4*>(base + ((c ^ (row & 7)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+// ---- explicit shared-space accessors (32-bit shared addresses: STS / LDS with immediate offsets, no generic-address arithmetic) ----
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
-__device__ __forceinline__ void store_state_hi_lo(uint8_t* tile, int row, const float (&st)[DS]) {
-    float v[32];
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32_u(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_s(uint32_t slot) {   // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+// byte offsets of the 16-byte chunks of row r in the layouts TMA writes: [rows][32 floats] SWIZZLE_128B / [rows][16 floats] SWIZZLE_64B
+struct RowOffs {
+    uint32_t o128[8], o64[4];
+    __device__ __forceinline__ explicit RowOffs(int r) {
 #pragma unroll
-    for (int a = 0; a < DS; ++a) split_tf32(st[a], v[a], v[DS + a]);
-    store_row_sw128(tile, row, v);
+        for (int c = 0; c < 8; ++c) o128[c] = (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o64[c] = (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+    }
+};
+__device__ __forceinline__ void store_row128_s(uint32_t tile, const RowOffs& ro, const float (&v)[32]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sts128(tile + ro.o128[c], v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+__device__ __forceinline__ void load_row128_s(uint32_t tile, const RowOffs& ro, float (&v)[32]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 t = lds128(tile + ro.o128[c]);
+        v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void store_row64_s(uint32_t tile, const RowOffs& ro, const float (&v)[16]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sts128(tile + ro.o64[c], v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+__device__ __forceinline__ void load_row64_s(uint32_t tile, const RowOffs& ro, float (&v)[16]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float4 t = lds128(tile + ro.o64[c]);
+        v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+    }
+}
+// state operand row [raw 16 | lo 16]: the tensor core truncates the raw half to tf32 itself, lo = rn(x - trunc(x))
+__device__ __forceinline__ void store_state_raw_lo(uint32_t tile, const RowOffs& ro, const float (&st)[DS]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) sts128(tile + ro.o128[c], st[4 * c], st[4 * c + 1], st[4 * c + 2], st[4 * c + 3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        sts128(tile + ro.o128[4 + c], lo_of_trunc(st[4 * c]), lo_of_trunc(st[4 * c + 1]), lo_of_trunc(st[4 * c + 2]), lo_of_trunc(st[4 * c + 3]));
+}
+// writer side: 16-byte chunk c of row `row`
+__device__ __forceinline__ float4 read_chunk128_s(uint32_t tile, int row, int c) { return lds128(tile + row * 128 + ((c ^ (row & 7)) << 4)); }
+__device__ __forceinline__ float4 read_chunk64_s(uint32_t tile, int row, int c) { return lds128(tile + row * 64 + ((c ^ ((row >> 1) & 3)) << 4)); }
+
+__device__ __forceinline__ uint64_t desc_kmajor_sw128_s(uint32_t tile) {
+    uint64_t d = 0;
+    d |= (uint64_t)((tile & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void mbar_init_s(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void umma_commit_s(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_s(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map),
+                 "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
+#ifdef SN_CHAIN_PROF
+#define CHPROF_DECL(n) long long chp_acc[n]; for (int chp_i = 0; chp_i < n; ++chp_i) chp_acc[chp_i] = 0; long long chp_t = 0; (void)chp_t
+#define CHPROF_T0() chp_t = clock64()
+#define CHPROF_LAP(i) do { const long long chp_n = clock64(); chp_acc[i] += chp_n - chp_t; chp_t = chp_n; } while (0)
+#define CHPROF_PRINT(tag, n, steps) do { if (blockIdx.x == 0 || blockIdx.x == 301) for (int chp_i = 0; chp_i < n; ++chp_i) \
+    printf("CHPROF %s blk %d phase %d avg %lld cyc/step\n", tag, (int)blockIdx.x, chp_i, chp_acc[chp_i] / (steps)); } while (0)
+#else
+#define CHPROF_DECL(n)
+#define CHPROF_T0()
+#define CHPROF_LAP(i)
+#define CHPROF_PRINT(tag, n, steps)
+#endif
+
+// The chain is paced by what ONE epilogue thread (thread = sample) does between two MMAs, so that thread's instruction stream is
+// kept minimal: explicit LDS / STS on precomputed swizzled offsets, the raw fp32 value as the hi operand (the tensor core
+// truncates), everything that is not the state recurrence done while the MMA is in flight or by other warps (bias, column sums).
 // No global memory access sits on the chain: a fence.proxy.async waits for the issuing thread's outstanding loads AND stores,
-// so the epilogue threads (thread = sample) only touch shared memory and TMEM.
+// so the epilogue threads only touch shared memory and TMEM.
 //   * inputs: TMA, two steps ahead, into a 2-slot ring (coefficient tile + this step's per-sample rows); L2 prefetch further ahead
 //   * outputs: each epilogue thread overwrites ITS OWN row of the slot's input areas (same swizzled layout) with the step's
 //     outputs; two writer warps copy the rows to global memory with coalesced stores and then release the slot
@@ -1141,112 +1244,67 @@ __device__ __forceinline__ void store_state_hi_lo(uint8_t* tile, int row, const 
 //                  a separate single 8 KB staging tile
 constexpr int CH_THREADS = 224;                 // warps 0-3: epilogue (thread = sample), warp 4: TMA + MMA issuer (one lane), warps 5-6: writers
 constexpr int CH_WRITERS = 64;
-struct ChainSmem {
-    uint8_t* state;    // 16 KB: [128][state hi 16 | state lo 16], K-major SWIZZLE_128B
-    uint8_t* in_hi;    // 16 KB (backward only): grad_y hi parts
-    uint8_t* in_lo;    // 16 KB (backward only)
-    uint8_t* lstage;   // 8 KB (backward only): adjoint checkpoints on their way to global memory
-    uint8_t* slot[2];
-    uint64_t *full, *out_ready, *slot_free, *state_ready, *acc_full, *chain_done, *lst_ready, *lst_free;
-    uint32_t* tmem_slot;
-};
 constexpr int CHF_SLOT = CW_TILE_BYTES + 8192 + 16384;    // W | in (8 KB at +12288) | yl (16 KB at +20480)
 constexpr int CHB_W_BYTES = 64 * 128;                      // state sub-tile + grad_y sub-tile
 constexpr int CHB_SLOT = CHB_W_BYTES + 16384;              // W | grad_y rows (16 KB at +8192)
+// shared-memory map, as byte offsets from the 1024-aligned base (everything a compile-time constant off one register)
 template <bool BWD>
-__device__ __forceinline__ ChainSmem chain_carve(uint8_t* smem_raw) {
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    ChainSmem c;
-    c.state = smem;
-    c.in_hi = smem + 16384;
-    c.in_lo = smem + 32768;
-    c.lstage = smem + 49152;
-    uint8_t* s0 = smem + (BWD ? 57344 : 16384);
-    constexpr int SLOT = BWD ? CHB_SLOT : CHF_SLOT;
-    c.slot[0] = s0;
-    c.slot[1] = s0 + SLOT;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s0 + 2 * SLOT);
-    c.full = bars;
-    c.out_ready = bars + 2;
-    c.slot_free = bars + 4;
-    c.state_ready = bars + 6;
-    c.acc_full = bars + 7;
-    c.chain_done = bars + 8;
-    c.lst_ready = bars + 9;
-    c.lst_free = bars + 10;
-    c.tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
-    return c;
+struct ChainMap {
+    static constexpr uint32_t state = 0;          // 16 KB: [128][state raw 16 | state lo 16], K-major SWIZZLE_128B
+    static constexpr uint32_t in_hi = 16384;      // 16 KB (backward only): raw grad_y rows = hi operand
+    static constexpr uint32_t in_lo = 32768;      // 16 KB (backward only)
+    static constexpr uint32_t lstage = 49152;     // 8 KB (backward only): adjoint checkpoints on their way to global memory
+    static constexpr uint32_t slot0 = BWD ? 57344 : 16384;
+    static constexpr uint32_t slot_bytes = BWD ? CHB_SLOT : CHF_SLOT;
+    static constexpr uint32_t bars = slot0 + 2 * slot_bytes;
+    static constexpr uint32_t full = bars, out_ready = bars + 16, slot_free = bars + 32, state_ready = bars + 48, acc_full = bars + 56,
+                              chain_done = bars + 64, lst_ready = bars + 72, lst_free = bars + 80, tmem_slot = bars + 88;
+};
+__device__ __forceinline__ uint32_t chain_base(uint8_t* smem_raw) {
+    const uint32_t a = smem_u32(smem_raw);
+    return a + ((1024u - (a & 1023u)) & 1023u);
 }
 constexpr size_t CHF_SMEM = 16384 + 2 * CHF_SLOT + 128 + 1024;
 constexpr size_t CHB_SMEM = 57344 + 2 * CHB_SLOT + 128 + 1024;
 
-// row r of a [128][32 floats] SWIZZLE_128B tile / a [128][16 floats] SWIZZLE_64B tile, in the layout TMA writes
-__device__ __forceinline__ void load_row_sw128(const uint8_t* tile, int r, float (&v)[32]) {
-    const uint8_t* base = tile + r * 128;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const float4 t = *reinterpret_cast<const float4*>(base + ((c ^ (r & 7)) << 4));
-        v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
-    }
-}
-__device__ __forceinline__ void load_row_sw64(const uint8_t* tile, int r, float (&v)[16]) {
-    const uint8_t* base = tile + r * 64;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const float4 t = *reinterpret_cast<const float4*>(base + ((c ^ ((r >> 1) & 3)) << 4));
-        v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
-    }
-}
-__device__ __forceinline__ void store_row_sw64(uint8_t* tile, int r, const float (&v)[16]) {
-    uint8_t* base = tile + r * 64;
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<float4*>(base + ((c ^ ((r >> 1) & 3)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-}
-// writer side: 16-byte chunk i of a tile (i = row * chunks_per_row + c), coalesced over consecutive threads
-__device__ __forceinline__ float4 read_chunk_sw128(const uint8_t* tile, int row, int c) {
-    return *reinterpret_cast<const float4*>(tile + row * 128 + ((c ^ (row & 7)) << 4));
-}
-__device__ __forceinline__ float4 read_chunk_sw64(const uint8_t* tile, int row, int c) {
-    return *reinterpret_cast<const float4*>(tile + row * 64 + ((c ^ ((row >> 1) & 3)) << 4));
-}
-
 // forward: steps 0..nc-1 = anticausal chain over chunks nc-1..0 (saves e_{j+1}; ytmp = yloc + O' e goes back into rbuf),
-//          steps nc..2nc-1 = causal chain over chunks 0..nc-1 (saves s_j; y = ytmp + O s + bias)
+//          steps nc..2nc-1 = causal chain over chunks 0..nc-1 (saves s_j; y = ytmp + O s + bias, the bias added by the writers).
+// The accumulator is double-buffered in TMEM, so only the 16 state columns are read between two MMAs of the chain.
 __global__ void __launch_bounds__(CH_THREADS, 2)
 sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_yl,
                         const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, float* __restrict__ rbuf, float* __restrict__ S, float* __restrict__ y,
                         long ldy, const float* __restrict__ bias, long B, int aligned) {
     extern __shared__ uint8_t smem_raw[];
-    const ChainSmem sm = chain_carve<false>(smem_raw);
+    using M = ChainMap<false>;
+    const uint32_t sb = chain_base(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nsteps = 2 * nchunks;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(sm.full + i, 1); mbar_init(sm.out_ready + i, 128); mbar_init(sm.slot_free + i, CH_WRITERS); }
-        mbar_init(sm.state_ready, 128); mbar_init(sm.acc_full, 1); mbar_init(sm.chain_done, CH_WRITERS);
+        for (int i = 0; i < 2; ++i) { mbar_init_s(sb + M::full + 8 * i, 1); mbar_init_s(sb + M::out_ready + 8 * i, 128); mbar_init_s(sb + M::slot_free + 8 * i, CH_WRITERS); }
+        mbar_init_s(sb + M::state_ready, 128); mbar_init_s(sb + M::acc_full, 1); mbar_init_s(sb + M::chain_done, CH_WRITERS);
         mbar_fence_init();
         tma_prefetch_desc(&map_cw);
         tma_prefetch_desc(&map_in);
         tma_prefetch_desc(&map_yl);
     }
-    if (warp == 4) tmem_alloc<128>(sm.tmem_slot);
+    if (warp == 4) tmem_alloc_s<256>(sb + M::tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *sm.tmem_slot;
+    const uint32_t tmem = lds32_u(sb + M::tmem_slot);
     auto chunk_of = [&](int t) { return t < nchunks ? nchunks - 1 - t : t - nchunks; };
 
     if (warp == 4) {
-        if (lane == 0) {
+        if (elect_one()) {
             auto issue = [&](int t) {
                 const int s = t & 1, j = chunk_of(t);
                 const bool anti = t < nchunks;
-                uint8_t* slot = sm.slot[s];
+                const uint32_t slot = sb + M::slot0 + s * M::slot_bytes, fullb = sb + M::full + 8 * s;
                 const int rowc = (int)((long)j * B + (long)blockIdx.x * 128);
-                mbar_expect_tx(sm.full + s, CW_TILE_BYTES + 8192 + 16384);
-                tma_load_2d(slot, &map_cw, 0, (j * 4 + (anti ? 1 : 0)) * CW_ROWS, sm.full + s);
-                tma_load_2d(slot + CW_TILE_BYTES, &map_in, 0, rowc + (anti ? (int)((long)nchunks * B) : 0), sm.full + s);   // R' rows follow the R rows
-                tma_load_2d(slot + CW_TILE_BYTES + 8192, &map_yl, 0, rowc, sm.full + s);
+                mbar_expect_tx_s(fullb, CW_TILE_BYTES + 8192 + 16384);
+                tma_load_2d_s(slot, &map_cw, 0, (j * 4 + (anti ? 1 : 0)) * CW_ROWS, fullb);
+                tma_load_2d_s(slot + CW_TILE_BYTES, &map_in, 0, rowc + (anti ? (int)((long)nchunks * B) : 0), fullb);   // R' rows follow the R rows
+                tma_load_2d_s(slot + CW_TILE_BYTES + 8192, &map_yl, 0, rowc, fullb);
             };
             auto prefetch = [&](int t) {   // into L2 only
                 const int j = chunk_of(t);
@@ -1259,52 +1317,64 @@ sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
             // for chain_done (the writers' last ytmp stores + their proxy fence)
             for (int t = 0; t < 2 && t < nchunks; ++t) issue(t);
             constexpr uint32_t idesc = idesc_tf32(128, 96, false, false);
+            CHPROF_DECL(4);
             for (int t = 0; t < nsteps; ++t) {
                 const int s = t & 1;
                 if (t + CH_PF < nsteps) prefetch(t + CH_PF);
-                mbar_wait(sm.full + s, (t >> 1) & 1);
-                mbar_wait(sm.state_ready, t & 1);
+                CHPROF_T0();
+                mbar_wait_s(sb + M::full + 8 * s, (t >> 1) & 1);
+                CHPROF_LAP(0);
+                mbar_wait_s(sb + M::state_ready, t & 1);
+                CHPROF_LAP(1);
                 tc_fence_after();
-                const uint64_t dst = desc_kmajor_sw128(sm.state);
-                const uint64_t dw = desc_kmajor_sw128(sm.slot[s]);
+                const uint64_t dst = desc_kmajor_sw128_s(sb + M::state);
+                const uint64_t dw = desc_kmajor_sw128_s(sb + M::slot0 + s * M::slot_bytes);
+                const uint32_t acc = tmem + (uint32_t)(s * 128);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) mma_tf32(tmem, dst + 2 * k, dw + 2 * k, idesc, k ? 1u : 0u);
-                umma_commit(sm.acc_full);
+                for (int k = 0; k < 4; ++k) mma_tf32(acc, dst + 2 * k, dw + 2 * k, idesc, k ? 1u : 0u);
+                umma_commit_s(sb + M::acc_full);
+                CHPROF_LAP(2);
                 // refill the OTHER slot (step t - 1's) with step t + 1, once the writers have copied step t - 1's outputs out of it
                 const int q = t + 1;
                 if (q >= 2 && q < nsteps) {
-                    mbar_wait(sm.slot_free + (q & 1), ((q - 2) >> 1) & 1);
+                    mbar_wait_s(sb + M::slot_free + 8 * (q & 1), ((q - 2) >> 1) & 1);
                     if (q == nchunks) {
-                        mbar_wait(sm.chain_done, 0);
+                        mbar_wait_s(sb + M::chain_done, 0);
                         asm volatile("fence.proxy.async;" ::: "memory");
                     }
                     issue(q);
                 } else if (q < 2 && q < nsteps && q >= nchunks) {   // nchunks == 1: step 1 belongs to the second chain
-                    mbar_wait(sm.chain_done, 0);
+                    mbar_wait_s(sb + M::chain_done, 0);
                     asm volatile("fence.proxy.async;" ::: "memory");
                     issue(q);
                 }
+                CHPROF_LAP(3);
             }
+            CHPROF_PRINT("fwd mma", 4, nsteps);
         }
     } else if (warp < 4) {
         const int r = threadIdx.x;                         // TMEM lane = tile row
-        const uint32_t tacc = tmem + ((uint32_t)(warp * 32) << 16);
+        const RowOffs ro(r);
+        const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
         float st[DS];
 #pragma unroll
         for (int a = 0; a < DS; ++a) st[a] = 0.f;
-        store_state_hi_lo(sm.state, r, st);
+        store_state_raw_lo(sb + M::state, ro, st);
         fence_async_smem();
-        mbar_arrive(sm.state_ready);
+        mbar_arrive_s(sb + M::state_ready);
+        CHPROF_DECL(6);
         for (int t = 0; t < nsteps; ++t) {
-            const bool anti = t < nchunks;
-            const int j = chunk_of(t), s = t & 1;
-            uint8_t* slot = sm.slot[s];
-            mbar_wait(sm.full + s, (t >> 1) & 1);
-            float in[DS], yl[PO];
-            load_row_sw64(slot + CW_TILE_BYTES, r, in);
-            load_row_sw128(slot + CW_TILE_BYTES + 8192, r, yl);
-            store_row_sw64(slot + CW_TILE_BYTES, r, st);     // the state entering this step (checkpoint for the backward)
-            mbar_wait(sm.acc_full, t & 1);
+            const int s = t & 1;
+            const uint32_t slot = sb + M::slot0 + s * M::slot_bytes;
+            const uint32_t tacc = tlane + (uint32_t)(s * 128);
+            CHPROF_T0();
+            mbar_wait_s(sb + M::full + 8 * s, (t >> 1) & 1);
+            float in[DS];
+            load_row64_s(slot + CW_TILE_BYTES, ro, in);
+            store_row64_s(slot + CW_TILE_BYTES, ro, st);     // the state entering this step (checkpoint for the backward)
+            CHPROF_LAP(0);
+            mbar_wait_s(sb + M::acc_full, t & 1);
+            CHPROF_LAP(1);
             tc_fence_after();
             // state part first: it is the chain
             uint32_t m[16], l[16];
@@ -1314,44 +1384,55 @@ sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
             const bool last_of_chain = (t == nchunks - 1);
 #pragma unroll
             for (int a = 0; a < DS; ++a) st[a] = last_of_chain ? 0.f : in[a] + (__uint_as_float(m[a]) + __uint_as_float(l[a]));
+            CHPROF_LAP(2);
+            store_state_raw_lo(sb + M::state, ro, st);
+            tc_fence_before();
+            fence_async_smem();
+            mbar_arrive_s(sb + M::state_ready);
+            CHPROF_LAP(3);
+            // outputs, off the chain (this step's accumulator is not rewritten before step t + 2): into this thread's own row of
+            // the slot; the writers take them from there
             uint32_t ym[32], ylo[32];
             tmem_ld16_nowait(tacc, reinterpret_cast<uint32_t(&)[16]>(ym[0]));
             tmem_ld16_nowait(tacc + 16, reinterpret_cast<uint32_t(&)[16]>(ym[16]));
             tmem_ld16_nowait(tacc + 48, reinterpret_cast<uint32_t(&)[16]>(ylo[0]));
             tmem_ld16_nowait(tacc + 64, reinterpret_cast<uint32_t(&)[16]>(ylo[16]));
+            float yl[PO];
+            load_row128_s(slot + CW_TILE_BYTES + 8192, ro, yl);
             tmem_ld_wait();
             tc_fence_before();
-            store_state_hi_lo(sm.state, r, st);
-            fence_async_smem();
-            mbar_arrive(sm.state_ready);
-            // outputs, off the chain: into this thread's own row of the slot; the writers take them from there
-            const int row0 = anti ? 0 : chunks[j].row0;
+            CHPROF_LAP(4);
 #pragma unroll
             for (int c = 0; c < PO; ++c) yl[c] += __uint_as_float(ym[c]) + __uint_as_float(ylo[c]);
-            if (!anti && bias != nullptr) {
-                const int nrows = chunks[j].nrows;
-#pragma unroll
-                for (int c = 0; c < PO; ++c)
-                    if (c < nrows) yl[c] += __ldg(bias + row0 + c);
-            }
-            store_row_sw128(slot + CW_TILE_BYTES + 8192, r, yl);
-            mbar_arrive(sm.out_ready + s);
+            store_row128_s(slot + CW_TILE_BYTES + 8192, ro, yl);
+            mbar_arrive_s(sb + M::out_ready + 8 * s);
+            CHPROF_LAP(5);
         }
+        if (threadIdx.x == 0) { CHPROF_PRINT("fwd epi", 6, nsteps); }
     } else {
         // writers: rows of step t -> global memory, coalesced; then the slot may be refilled
         const int wt = threadIdx.x - 160;
         for (int t = 0; t < nsteps; ++t) {
             const bool anti = t < nchunks;
             const int j = chunk_of(t), s = t & 1;
-            const uint8_t* slot = sm.slot[s];
+            const uint32_t slot = sb + M::slot0 + s * M::slot_bytes;
             const sn_sss_tc_chunk c = chunks[j];
-            mbar_wait(sm.out_ready + s, (t >> 1) & 1);
+            // this thread always handles 16-byte column chunk (wt & 7) of the y rows: its slice of the bias
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!anti && bias != nullptr) {
+                const int c0 = 4 * (wt & 7);
+                if (c0 < c.nrows) b4.x = __ldg(bias + c.row0 + c0);
+                if (c0 + 1 < c.nrows) b4.y = __ldg(bias + c.row0 + c0 + 1);
+                if (c0 + 2 < c.nrows) b4.z = __ldg(bias + c.row0 + c0 + 2);
+                if (c0 + 3 < c.nrows) b4.w = __ldg(bias + c.row0 + c0 + 3);
+            }
+            mbar_wait_s(sb + M::out_ready + 8 * s, (t >> 1) & 1);
             float4 sv[8], yv[16];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { const int i = k * CH_WRITERS + wt; sv[k] = read_chunk_sw64(slot + CW_TILE_BYTES, i >> 2, i & 3); }
+            for (int k = 0; k < 8; ++k) { const int i = k * CH_WRITERS + wt; sv[k] = read_chunk64_s(slot + CW_TILE_BYTES, i >> 2, i & 3); }
 #pragma unroll
-            for (int k = 0; k < 16; ++k) { const int i = k * CH_WRITERS + wt; yv[k] = read_chunk_sw128(slot + CW_TILE_BYTES + 8192, i >> 3, i & 7); }
-            mbar_arrive(sm.slot_free + s);
+            for (int k = 0; k < 16; ++k) { const int i = k * CH_WRITERS + wt; yv[k] = read_chunk128_s(slot + CW_TILE_BYTES + 8192, i >> 3, i & 7); }
+            mbar_arrive_s(sb + M::slot_free + 8 * s);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int i = k * CH_WRITERS + wt;
@@ -1368,13 +1449,14 @@ sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
                         *(reinterpret_cast<float4*>(rbuf + ((size_t)j * B + row) * 32) + (i & 7)) = yv[k];
                     } else if (c0 < c.nrows) {
                         float* yp = y + row * ldy + c.row0 + c0;
+                        const float4 o = make_float4(yv[k].x + b4.x, yv[k].y + b4.y, yv[k].z + b4.z, yv[k].w + b4.w);
                         if (aligned && c0 + 4 <= c.nrows) {
-                            *reinterpret_cast<float4*>(yp) = yv[k];
+                            *reinterpret_cast<float4*>(yp) = o;
                         } else {
-                            yp[0] = yv[k].x;
-                            if (c0 + 1 < c.nrows) yp[1] = yv[k].y;
-                            if (c0 + 2 < c.nrows) yp[2] = yv[k].z;
-                            if (c0 + 3 < c.nrows) yp[3] = yv[k].w;
+                            yp[0] = o.x;
+                            if (c0 + 1 < c.nrows) yp[1] = o.y;
+                            if (c0 + 2 < c.nrows) yp[2] = o.z;
+                            if (c0 + 3 < c.nrows) yp[3] = o.w;
                         }
                     }
                 }
@@ -1382,7 +1464,7 @@ sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
             if (t == nchunks - 1) {
                 asm volatile("fence.proxy.async;" ::: "memory");   // ytmp stores -> visible to the TMA reads of the second chain
                 __threadfence();
-                mbar_arrive(sm.chain_done);
+                mbar_arrive_s(sb + M::chain_done);
             }
         }
     }
@@ -1390,128 +1472,122 @@ sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
     __syncthreads();
     if (warp == 4) {
         tc_fence_after();
-        tmem_dealloc<128>(tmem);
+        tmem_dealloc<256>(tmem);
     }
 }
 
 // backward: steps 0..nc-1 = lambda chain over chunks nc-1..0, steps nc..2nc-1 = mu chain over chunks 0..nc-1.
-// L[j][row][0..15] = lambda_{j+1}, L[j][row][16..31] = mu_j ; grad_bias += column sums of grad_y (second chain).
-// Ring slot of step t: coefficient tile of step t + the grad_y rows of step t + 1 (the epilogue of step t splits them into the
-// hi / lo operand tiles of step t + 1's MMAs).  Step 0's rows arrive through a prologue load into the (still unused) lo tile.
+// L[j][row][0..15] = lambda_{j+1}, L[j][row][16..31] = mu_j ; grad_bias += column sums of grad_y (second chain, by the writer warps).
+// Ring slot of step t: coefficient tile of step t + the grad_y rows of step t + 1.  While the MMA of step t is in flight the
+// epilogue thread fetches its row of step t + 1 and computes its lo part in registers; after the accumulator arrives it only adds,
+// splits the 16 state values and stores the operand rows.  Step 0's rows arrive through a prologue load into the (still unused) lo tile.
 __global__ void __launch_bounds__(CH_THREADS, 2)
 sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid_constant__ CUtensorMap map_gy, const sn_sss_tc_chunk* __restrict__ chunks,
                         int nchunks, float* __restrict__ L, float* __restrict__ gbias, long B) {
     extern __shared__ uint8_t smem_raw[];
-    const ChainSmem sm = chain_carve<true>(smem_raw);
-    __shared__ float sbias[2][32];
+    using M = ChainMap<true>;
+    const uint32_t sb = chain_base(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nsteps = 2 * nchunks;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(sm.full + i, 1); mbar_init(sm.slot_free + i, 129); }
-        mbar_init(sm.state_ready, 128); mbar_init(sm.acc_full, 1); mbar_init(sm.chain_done, 1);
-        mbar_init(sm.lst_ready, 128); mbar_init(sm.lst_free, CH_WRITERS);
+        for (int i = 0; i < 2; ++i) { mbar_init_s(sb + M::full + 8 * i, 1); mbar_init_s(sb + M::slot_free + 8 * i, 129 + CH_WRITERS); }
+        mbar_init_s(sb + M::state_ready, 128); mbar_init_s(sb + M::acc_full, 1); mbar_init_s(sb + M::chain_done, 1);
+        mbar_init_s(sb + M::lst_ready, 128); mbar_init_s(sb + M::lst_free, CH_WRITERS);
         mbar_fence_init();
         tma_prefetch_desc(&map_cw);
         tma_prefetch_desc(&map_gy);
     }
-    if (threadIdx.x < 64) sbias[threadIdx.x >> 5][threadIdx.x & 31] = 0.f;
-    if (warp == 4) tmem_alloc<32>(sm.tmem_slot);
+    if (warp == 4) tmem_alloc_s<32>(sb + M::tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *sm.tmem_slot;
+    const uint32_t tmem = lds32_u(sb + M::tmem_slot);
     auto chunk_of = [&](int t) { return t < nchunks ? nchunks - 1 - t : t - nchunks; };
 
     if (warp == 4) {
-        if (lane == 0) {
+        if (elect_one()) {
             auto issue = [&](int t) {
                 const int s = t & 1, j = chunk_of(t);
-                uint8_t* slot = sm.slot[s];
+                const uint32_t slot = sb + M::slot0 + s * M::slot_bytes, fullb = sb + M::full + 8 * s;
                 const bool has_next = t + 1 < nsteps;
-                mbar_expect_tx(sm.full + s, CHB_W_BYTES + (has_next ? 16384 : 0));
-                tma_load_2d(slot, &map_cw, 0, (j * 4 + (t < nchunks ? 2 : 3)) * CW_ROWS, sm.full + s);
-                if (has_next) tma_load_2d(slot + CHB_W_BYTES, &map_gy, chunks[chunk_of(t + 1)].row0, blockIdx.x * 128, sm.full + s);
+                mbar_expect_tx_s(fullb, CHB_W_BYTES + (has_next ? 16384 : 0));
+                tma_load_2d_s(slot, &map_cw, 0, (j * 4 + (t < nchunks ? 2 : 3)) * CW_ROWS, fullb);
+                if (has_next) tma_load_2d_s(slot + CHB_W_BYTES, &map_gy, chunks[chunk_of(t + 1)].row0, blockIdx.x * 128, fullb);
             };
             auto prefetch = [&](int t) { tma_prefetch_l2_2d(&map_gy, chunks[chunk_of(t)].row0, blockIdx.x * 128); };
             for (int t = 1; t < CH_PF && t < nsteps; ++t) prefetch(t);
-            mbar_expect_tx(sm.chain_done, 16384);
-            tma_load_2d(sm.in_lo, &map_gy, chunks[chunk_of(0)].row0, blockIdx.x * 128, sm.chain_done);
+            mbar_expect_tx_s(sb + M::chain_done, 16384);
+            tma_load_2d_s(sb + M::in_lo, &map_gy, chunks[chunk_of(0)].row0, blockIdx.x * 128, sb + M::chain_done);
             for (int t = 0; t < 2 && t < nsteps; ++t) issue(t);
             constexpr uint32_t idesc32 = idesc_tf32(128, 32, false, false);
             constexpr uint32_t idesc16 = idesc_tf32(128, 16, false, false);
+            CHPROF_DECL(4);
             for (int t = 0; t < nsteps; ++t) {
                 const int s = t & 1;
                 if (t + CH_PF < nsteps) prefetch(t + CH_PF);
-                mbar_wait(sm.full + s, (t >> 1) & 1);
-                mbar_wait(sm.state_ready, t & 1);
+                CHPROF_T0();
+                mbar_wait_s(sb + M::full + 8 * s, (t >> 1) & 1);
+                CHPROF_LAP(0);
+                mbar_wait_s(sb + M::state_ready, t & 1);
+                CHPROF_LAP(1);
                 tc_fence_after();
-                const uint64_t dst = desc_kmajor_sw128(sm.state), dih = desc_kmajor_sw128(sm.in_hi), dil = desc_kmajor_sw128(sm.in_lo);
-                const uint64_t dw0 = desc_kmajor_sw128(sm.slot[s]), dw1 = desc_kmajor_sw128(sm.slot[s] + 4096);
+                const uint32_t slot = sb + M::slot0 + s * M::slot_bytes;
+                const uint64_t dst = desc_kmajor_sw128_s(sb + M::state), dih = desc_kmajor_sw128_s(sb + M::in_hi), dil = desc_kmajor_sw128_s(sb + M::in_lo);
+                const uint64_t dw0 = desc_kmajor_sw128_s(slot), dw1 = desc_kmajor_sw128_s(slot + 4096);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) mma_tf32(tmem, dst + 2 * k, dw0 + 2 * k, idesc32, k ? 1u : 0u);   // [Phi^T hi | hi ; lo | 0]
 #pragma unroll
                 for (int k = 0; k < 4; ++k) mma_tf32(tmem, dih + 2 * k, dw1 + 2 * k, idesc32, 1u);            // grad_y hi x [O^T hi ; O^T lo]
 #pragma unroll
                 for (int k = 0; k < 4; ++k) mma_tf32(tmem, dil + 2 * k, dw1 + 2 * k, idesc16, 1u);            // grad_y lo x  O^T hi
-                umma_commit(sm.acc_full);
-                umma_commit(sm.slot_free + s);
+                umma_commit_s(sb + M::acc_full);
+                umma_commit_s(sb + M::slot_free + 8 * s);
+                CHPROF_LAP(2);
                 if (t + 2 < nsteps) {
-                    mbar_wait(sm.slot_free + s, (t >> 1) & 1);
+                    mbar_wait_s(sb + M::slot_free + 8 * s, (t >> 1) & 1);
                     issue(t + 2);
                 }
+                CHPROF_LAP(3);
             }
+            CHPROF_PRINT("bwd mma", 4, nsteps);
         }
     } else if (warp < 4) {
         const int r = threadIdx.x;
-        const long row = (long)blockIdx.x * 128 + r;
-        const bool valid = row < B;
-        (void)valid;
+        const RowOffs ro(r);
         const uint32_t tacc = tmem + ((uint32_t)(warp * 32) << 16);
-        auto store_inputs = [&](const float (&gv)[PO]) {
-            float h[PO], l[PO];
-#pragma unroll
-            for (int c = 0; c < PO; ++c) split_tf32(gv[c], h[c], l[c]);
-            store_row_sw128(sm.in_hi, r, h);
-            store_row_sw128(sm.in_lo, r, l);
-        };
-        float st[DS], g[PO];
+        float st[DS], g[PO], gl[PO];
 #pragma unroll
         for (int a = 0; a < DS; ++a) st[a] = 0.f;
-        mbar_wait(sm.chain_done, 0);
-        load_row_sw128(sm.in_lo, r, g);        // raw grad_y rows of step 0 (each thread only touches its own 128-byte row)
-        store_state_hi_lo(sm.state, r, st);
-        store_inputs(g);
+        mbar_wait_s(sb + M::chain_done, 0);
+        load_row128_s(sb + M::in_lo, ro, g);        // raw grad_y rows of step 0 (each thread only touches its own 128-byte row)
+#pragma unroll
+        for (int c = 0; c < PO; ++c) gl[c] = lo_of_trunc(g[c]);
+        store_state_raw_lo(sb + M::state, ro, st);
+        store_row128_s(sb + M::in_hi, ro, g);
+        store_row128_s(sb + M::in_lo, ro, gl);
         fence_async_smem();
-        mbar_arrive(sm.state_ready);
+        mbar_arrive_s(sb + M::state_ready);
+        CHPROF_DECL(6);
         for (int t = 0; t < nsteps; ++t) {
-            const bool second = t >= nchunks;
-            const int j = chunk_of(t), s = t & 1;
+            const int s = t & 1;
             const bool has_next = t + 1 < nsteps;
+            CHPROF_T0();
             // checkpoint of the adjoint entering this step -> staging tile (the writers emptied it during the previous step)
-            if (t > 0) mbar_wait(sm.lst_free, (t - 1) & 1);
-            store_row_sw64(sm.lstage, r, st);
-            mbar_arrive(sm.lst_ready);
-            if (second && gbias != nullptr) {
-                // column sums of this chunk's grad_y rows over the warp (lane l ends with column l), then over the 4 warps
-                float v[PO];
+            if (t > 0) mbar_wait_s(sb + M::lst_free, (t - 1) & 1);
+            store_row64_s(sb + M::lstage, ro, st);
+            mbar_arrive_s(sb + M::lst_ready);
+            CHPROF_LAP(0);
+            // next step's grad_y row and its lo part, while this step's MMA runs
+            mbar_wait_s(sb + M::full + 8 * s, (t >> 1) & 1);
+            if (has_next) {
+                load_row128_s(sb + M::slot0 + s * M::slot_bytes + CHB_W_BYTES, ro, g);
 #pragma unroll
-                for (int c = 0; c < PO; ++c) v[c] = g[c];
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-#pragma unroll
-                    for (int i = 0; i < off; ++i) {
-                        const bool up = (lane & off) != 0;
-                        const float send = up ? v[i] : v[i + off];
-                        const float keep = up ? v[i + off] : v[i];
-                        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                    }
-                }
-                atomicAdd(&sbias[t & 1][lane], v[0]);
+                for (int c = 0; c < PO; ++c) gl[c] = lo_of_trunc(g[c]);
             }
-            mbar_wait(sm.full + s, (t >> 1) & 1);
-            if (has_next) load_row_sw128(sm.slot[s] + CHB_W_BYTES, r, g);
-            mbar_arrive(sm.slot_free + s);
-            mbar_wait(sm.acc_full, t & 1);
+            mbar_arrive_s(sb + M::slot_free + 8 * s);
+            CHPROF_LAP(1);
+            mbar_wait_s(sb + M::acc_full, t & 1);
+            CHPROF_LAP(2);
             tc_fence_after();
             uint32_t m[16], l[16];
             tmem_ld16_nowait(tacc, m);
@@ -1521,36 +1597,53 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
             const bool last_of_chain = (t == nchunks - 1);
 #pragma unroll
             for (int a = 0; a < DS; ++a) st[a] = last_of_chain ? 0.f : (__uint_as_float(m[a]) + __uint_as_float(l[a]));
+            CHPROF_LAP(3);
             if (has_next) {
-                store_state_hi_lo(sm.state, r, st);
-                store_inputs(g);
+                store_state_raw_lo(sb + M::state, ro, st);
+                store_row128_s(sb + M::in_hi, ro, g);
+                store_row128_s(sb + M::in_lo, ro, gl);
+                CHPROF_LAP(4);
                 fence_async_smem();
-                mbar_arrive(sm.state_ready);
-            }
-            if (second && gbias != nullptr) {
-                named_bar_sync(1, 128);   // all four warps have added this step's column sums
-                if (warp == 0) {
-                    const sn_sss_tc_chunk c = chunks[j];
-                    if (lane < c.nrows) atomicAdd(gbias + c.row0 + lane, sbias[t & 1][lane]);
-                    sbias[t & 1][lane] = 0.f;
-                }
+                mbar_arrive_s(sb + M::state_ready);
+                CHPROF_LAP(5);
             }
         }
+        if (threadIdx.x == 0) { CHPROF_PRINT("bwd epi", 6, nsteps); }
     } else {
-        // writers: adjoint checkpoints -> L
+        // writers: adjoint checkpoints -> L; column sums of the second chain's grad_y rows -> grad_bias
         const int wt = threadIdx.x - 160;
         for (int t = 0; t < nsteps; ++t) {
-            const int j = chunk_of(t);
-            mbar_wait(sm.lst_ready, t & 1);
+            const int j = chunk_of(t), s = t & 1;
+            mbar_wait_s(sb + M::lst_ready, t & 1);
             float4 sv[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { const int i = k * CH_WRITERS + wt; sv[k] = read_chunk_sw64(sm.lstage, i >> 2, i & 3); }
-            mbar_arrive(sm.lst_free);
+            for (int k = 0; k < 8; ++k) { const int i = k * CH_WRITERS + wt; sv[k] = read_chunk64_s(sb + M::lstage, i >> 2, i & 3); }
+            mbar_arrive_s(sb + M::lst_free);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int i = k * CH_WRITERS + wt;
                 const long row = (long)blockIdx.x * 128 + (i >> 2);
                 if (row < B) *(reinterpret_cast<float4*>(L + ((size_t)j * B + row) * 32 + (t >= nchunks ? DS : 0)) + (i & 3)) = sv[k];
+            }
+            // the slot of step t holds the grad_y rows of step t + 1: thread = (column, half of the rows); rows past B are zero (TMA fill)
+            mbar_wait_s(sb + M::full + 8 * s, (t >> 1) & 1);
+            if (gbias != nullptr && t + 1 >= nchunks && t + 1 < nsteps) {
+                const uint32_t tile = sb + M::slot0 + s * M::slot_bytes + CHB_W_BYTES;
+                const int col = wt & 31, r0 = (wt >> 5) * 64;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+                for (int rr = 0; rr < 64; rr += 4) {
+                    const int row = r0 + rr;     // row & 7 takes the values (rr & 7) + 0..3: the swizzle term is per row
+                    a0 += lds32(tile + row * 128 + (((col >> 2) ^ (row & 7)) << 4) + (col & 3) * 4);
+                    a1 += lds32(tile + (row + 1) * 128 + (((col >> 2) ^ ((row + 1) & 7)) << 4) + (col & 3) * 4);
+                    a2 += lds32(tile + (row + 2) * 128 + (((col >> 2) ^ ((row + 2) & 7)) << 4) + (col & 3) * 4);
+                    a3 += lds32(tile + (row + 3) * 128 + (((col >> 2) ^ ((row + 3) & 7)) << 4) + (col & 3) * 4);
+                }
+                mbar_arrive_s(sb + M::slot_free + 8 * s);
+                const sn_sss_tc_chunk c = chunks[chunk_of(t + 1)];
+                if (col < c.nrows) atomicAdd(gbias + c.row0 + col, (a0 + a1) + (a2 + a3));
+            } else {
+                mbar_arrive_s(sb + M::slot_free + 8 * s);
             }
         }
     }
@@ -1616,7 +1709,7 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             auto prefetch_step = [&](int t) {   // into L2 only, G2_PF steps ahead of the 3-stage shared-memory pipeline
                 tma_prefetch_l2_2d(&map_gy, c.row0, t * G2_KS);
                 tma_prefetch_l2_3d(&map_l, 0, t * G2_KS, ch);
@@ -1638,7 +1731,7 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = idesc_tf32(128, 32 * nblk, true, true);
             // the tensor core adds into its accumulator with truncation (an error linear in the number of additions): the CTA's
             // samples are spread over two TMEM accumulators, and the host keeps the samples per CTA small
