@@ -230,9 +230,10 @@ __device__ __forceinline__ void split_tf32(const float4& v, float4& h, float4& l
 
 // ------------------------------------------------------------------------------------------
 // 2. local GEMM: [yloc | r | r'](128 samples x 64) = u_j (128 x 32 nkb) * W_j^T, 3xTF32
-//    warp 0: TMA producer | warp 1: TMEM alloc + MMA issuer | warps 2-5: hi/lo converters | warps 6-9: epilogue
+//    warp 0: TMA producer | warp 1: TMEM alloc + MMA issuer | warps 2-9: lo-part converters | warps 10-13: epilogue
 // ------------------------------------------------------------------------------------------
-constexpr int G1_THREADS = 320;
+constexpr int G1_CONV = 256;                          // converter threads (8 warps: two per SM sub-partition)
+constexpr int G1_THREADS = 64 + G1_CONV + 128;
 constexpr int G1_STAGES = 4;
 constexpr int G1_TILE_BYTES = 128 * 128;              // 128 rows x 128 B
 constexpr int G1_STAGE_BYTES = 3 * G1_TILE_BYTES;     // x (hi in place) | x_lo | W
@@ -262,7 +263,7 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
     int2* ctab = reinterpret_cast<int2*>(smem + G1_STAGES * G1_STAGE_BYTES + 256);   // (col0, nkb) per chunk: no global load on the issue paths
     for (int i = threadIdx.x; i < nchunks; i += G1_THREADS) ctab[i] = make_int2(chunks[i].col0, chunks[i].nkb);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < G1_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(conv + s, 128); mbar_init(empty + s, 1); }
+        for (int s = 0; s < G1_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(conv + s, G1_CONV); mbar_init(empty + s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, 128); }
         mbar_fence_init();
         tma_prefetch_desc(&map_x);
@@ -328,7 +329,7 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
                 umma_commit(acc_full + b);
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < 2 + G1_CONV / 32) {
         // converters: x -> hi (in place), lo (second tile); identical swizzled layout, so plain 16-byte chunks
         const int ct = threadIdx.x - 64;
         uint32_t it = 0;
@@ -339,16 +340,17 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
                 mbar_wait(full + s, round & 1);
                 float4* xh = reinterpret_cast<float4*>(smem + s * G1_STAGE_BYTES);
                 float4* xl = xh + G1_TILE_BYTES / 16;
-                float4 v[8];
+                constexpr int NV = 1024 / G1_CONV;
+                float4 v[NV];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = xh[ct + 128 * i];
+                for (int i = 0; i < NV; ++i) v[i] = xh[ct + G1_CONV * i];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < NV; ++i) {
                     // the tensor core truncates its operands to tf32 (verified: parity is unchanged), so the raw tile already acts as
                     // hi = trunc(x); only lo = rn(x - trunc(x)) is written
                     float4 l;
                     lo_of_trunc(v[i], l);
-                    xl[ct + 128 * i] = l;
+                    xl[ct + G1_CONV * i] = l;
                 }
                 fence_async_smem();
                 mbar_arrive(conv + s);
@@ -1661,7 +1663,8 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
 //    layout kind::tf32 accepts for MN-major operands).
 //    A (M = 128): blocks gy_hi, L_hi, gy_lo, L_lo;  B (N = 32 (nkb+1)): x blocks then the state block; hi and lo tiles.
 // ------------------------------------------------------------------------------------------
-constexpr int G2_THREADS = 320;
+constexpr int G2_CONV = 256;                     // converter threads (8 warps: two per SM sub-partition)
+constexpr int G2_THREADS = 64 + G2_CONV + 128;
 constexpr int G2_STAGES = 3;
 constexpr int G2_KS = 32;                        // samples per stage
 constexpr int G2_BLK = G2_KS * 128;              // one 32-feature block: 4 KB
@@ -1694,7 +1697,7 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     if (t0 >= t1) return;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(conv + s, 128); mbar_init(empty + s, 1); }
+        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(conv + s, G2_CONV); mbar_init(empty + s, 1); }
         mbar_init(acc_full, 1);
         mbar_fence_init();
         tma_prefetch_desc(&map_x);
@@ -1755,7 +1758,7 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             }
             umma_commit(acc_full);
         }
-    } else if (warp < 6) {
+    } else if (warp < 2 + G2_CONV / 32) {
         const int ct = threadIdx.x - 64;
         for (int t = t0, it = 0; t < t1; ++t, ++it) {
             const int s = it % G2_STAGES, round = it / G2_STAGES;
@@ -1765,10 +1768,10 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 float4* h = reinterpret_cast<float4*>(st);
                 float4* l = h + 2 * G2_BLK / 16;
 #pragma unroll
-                for (int i = 0; i < 2 * G2_BLK / 16 / 128; ++i) {
+                for (int i = 0; i < 2 * G2_BLK / 16 / G2_CONV; ++i) {
                     float4 ll;
-                    lo_of_trunc(h[ct + 128 * i], ll);   // hi = the raw tile (the tensor core truncates)
-                    l[ct + 128 * i] = ll;
+                    lo_of_trunc(h[ct + G2_CONV * i], ll);   // hi = the raw tile (the tensor core truncates)
+                    l[ct + G2_CONV * i] = ll;
                 }
             }
             {   // B: x blocks + state block -> lo at +24 KB
@@ -1776,7 +1779,7 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 float4* l = h + G2_BH_BYTES / 16;
                 const int n16 = nblk * G2_BLK / 16;
 #pragma unroll 4
-                for (int i = ct; i < n16; i += 128) {
+                for (int i = ct; i < n16; i += G2_CONV) {
                     float4 ll;
                     lo_of_trunc(h[i], ll);
                     l[i] = ll;
