@@ -16,7 +16,8 @@ namespace t3 {
 using namespace snb::umma;
 
 constexpr int T3_STAGES = 3;
-constexpr int T3_THREADS = 320;
+constexpr int T3_CONV = 128 * T3_STAGES;            // converter threads: one group of four warps per pipeline stage
+constexpr int T3_THREADS = 64 + T3_CONV + 128;
 constexpr int T3_TILE = 128 * 128;                 // bytes: 128 rows x 32 floats (K-major) or 4 blocks of 32 k-rows x 32 floats (MN-major)
 constexpr int T3_STAGE = 4 * T3_TILE;              // A hi | A lo | B hi | B lo
 constexpr size_t T3_SMEM = (size_t)T3_STAGES * T3_STAGE + 1024 + 256;
@@ -119,10 +120,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
             umma_commit(acc_full);
         }
-    } else if (warp < 6) {
-        const int ct = threadIdx.x - 64;
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % T3_STAGES, round = kb / T3_STAGES;
+    } else if (warp < 2 + T3_CONV / 32) {
+        // A stage costs a converter warp a full LDS -> STS -> proxy-fence round trip (~3 000 cycles for the two tiles, against ~800
+        // cycles of MMA): one group of four warps per stage keeps every stage in conversion at once.  A group owns its stage, so it
+        // never skips a phase of that stage's `full` barrier.
+        const int grp = (warp - 2) >> 2, ct = (threadIdx.x - 64) & 127;
+        for (int kb = grp; kb < nkb; kb += T3_STAGES) {
+            const int s = grp, round = kb / T3_STAGES;
             mbar_wait(full + s, round & 1);
             uint8_t* st = smem + s * T3_STAGE;
 #pragma unroll

@@ -228,13 +228,27 @@ __device__ __forceinline__ void split_tf32(const float4& v, float4& h, float4& l
     split_tf32(v.w, h.w, l.w);
 }
 
+#ifdef SN_CHAIN_PROF
+#define CHPROF_DECL(n) long long chp_acc[n]; for (int chp_i = 0; chp_i < n; ++chp_i) chp_acc[chp_i] = 0; long long chp_t = 0; (void)chp_t
+#define CHPROF_T0() chp_t = clock64()
+#define CHPROF_LAP(i) do { const long long chp_n = clock64(); chp_acc[i] += chp_n - chp_t; chp_t = chp_n; } while (0)
+#define CHPROF_PRINT(tag, n, steps) do { if (blockIdx.x == 0 || blockIdx.x == 301) for (int chp_i = 0; chp_i < n; ++chp_i) \
+    printf("CHPROF %s blk %d phase %d avg %lld cyc/step\n", tag, (int)blockIdx.x, chp_i, chp_acc[chp_i] / (steps)); } while (0)
+#else
+#define CHPROF_DECL(n)
+#define CHPROF_T0()
+#define CHPROF_LAP(i)
+#define CHPROF_PRINT(tag, n, steps)
+#endif
+
 // ------------------------------------------------------------------------------------------
 // 2. local GEMM: [yloc | r | r'](128 samples x 64) = u_j (128 x 32 nkb) * W_j^T, 3xTF32
 //    warp 0: TMA producer | warp 1: TMEM alloc + MMA issuer | warps 2-9: lo-part converters | warps 10-13: epilogue
 // ------------------------------------------------------------------------------------------
-constexpr int G1_CONV = 256;                          // converter threads (8 warps: two per SM sub-partition)
+constexpr int G1_CONV = 256;                          // converter threads: two groups of four warps on alternate stages
 constexpr int G1_THREADS = 64 + G1_CONV + 128;
 constexpr int G1_STAGES = 4;
+static_assert(G1_STAGES % 2 == 0, "a converter group must own its stages (stage parity = group)");
 constexpr int G1_TILE_BYTES = 128 * 128;              // 128 rows x 128 B
 constexpr int G1_STAGE_BYTES = 3 * G1_TILE_BYTES;     // x (hi in place) | x_lo | W
 constexpr int G1_PF = 3;                             // L2 prefetch distance in work items
@@ -263,7 +277,7 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
     int2* ctab = reinterpret_cast<int2*>(smem + G1_STAGES * G1_STAGE_BYTES + 256);   // (col0, nkb) per chunk: no global load on the issue paths
     for (int i = threadIdx.x; i < nchunks; i += G1_THREADS) ctab[i] = make_int2(chunks[i].col0, chunks[i].nkb);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < G1_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(conv + s, G1_CONV); mbar_init(empty + s, 1); }
+        for (int s = 0; s < G1_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(conv + s, 128); mbar_init(empty + s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, 128); }
         mbar_fence_init();
         tma_prefetch_desc(&map_x);
@@ -285,35 +299,45 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
             };
             for (long w = w0; w < w0 + G1_PF && w < w1; ++w) prefetch_item(w);
             uint32_t it = 0;
+            CHPROF_DECL(2);
             for (long w = w0; w < w1; ++w) {
                 if (w + G1_PF < w1) prefetch_item(w + G1_PF);
                 const int tile = (int)(w / nchunks), ch = (int)(w % nchunks);
                 const int nkb = ctab[ch].y, col0 = ctab[ch].x;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const uint32_t s = it % G1_STAGES, round = it / G1_STAGES;
+                    CHPROF_T0();
                     if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
+                    CHPROF_LAP(0);
                     uint8_t* st = smem + s * G1_STAGE_BYTES;
                     mbar_expect_tx(full + s, 2 * G1_TILE_BYTES);
                     tma_load_2d(st, &map_x, col0 + kb * KBW, tile * 128, full + s);
                     tma_load_2d(st + 2 * G1_TILE_BYTES, &map_w, kb * KBW, ch * WROWS, full + s);
+                    CHPROF_LAP(1);
                 }
             }
+            CHPROF_PRINT("lg prod", 2, (int)it);
         }
     } else if (warp == 1) {
         if (elect_one()) {
             constexpr uint32_t idesc1 = idesc_tf32(128, 128, false, false);   // x_hi * [W_hi ; W_lo]
             constexpr uint32_t idesc2 = idesc_tf32(128, 64, false, false);    // x_lo * W_hi
             uint32_t it = 0, ai = 0;
+            CHPROF_DECL(3);
             for (long w = w0; w < w1; ++w, ++ai) {
                 const int ch = (int)(w % nchunks);
                 const int nkb = ctab[ch].y;
                 const uint32_t b = ai & 1;
+                CHPROF_T0();
                 if (ai >= 2) mbar_wait(acc_empty + b, ((ai >> 1) - 1) & 1);
+                CHPROF_LAP(0);
                 tc_fence_after();
                 const uint32_t acc = tmem_base + b * 128;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const uint32_t s = it % G1_STAGES, round = it / G1_STAGES;
+                    CHPROF_T0();
                     mbar_wait(conv + s, round & 1);
+                    CHPROF_LAP(1);
                     tc_fence_after();
                     uint8_t* st = smem + s * G1_STAGE_BYTES;
                     const uint64_t dxh = desc_kmajor_sw128(st);
@@ -325,45 +349,59 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
                         mma_tf32(acc, dxl + 2 * k, dw + 2 * k, idesc2, 1u);
                     }
                     umma_commit(empty + s);
+                    CHPROF_LAP(2);
                 }
                 umma_commit(acc_full + b);
             }
+            CHPROF_PRINT("lg mma", 3, (int)it);
         }
     } else if (warp < 2 + G1_CONV / 32) {
-        // converters: x -> hi (in place), lo (second tile); identical swizzled layout, so plain 16-byte chunks
-        const int ct = threadIdx.x - 64;
+        // converters: only lo = rn(x - trunc(x)) is written (second tile; identical swizzled layout, so plain 16-byte chunks).
+        // A stage costs one converter warp a full LDS -> STS -> proxy-fence round trip, so two groups of four warps take alternate
+        // stages (stage parity = group: a group never skips a phase of a `full` barrier): two stages are always in conversion.
+        const int grp = (warp - 2) >> 2, ct = (threadIdx.x - 64) & 127;
         uint32_t it = 0;
+        CHPROF_DECL(4);
         for (long w = w0; w < w1; ++w) {
             const int nkb = ctab[(int)(w % nchunks)].y;
             for (int kb = 0; kb < nkb; ++kb, ++it) {
+                if ((int)(it & 1) != grp) continue;
                 const uint32_t s = it % G1_STAGES, round = it / G1_STAGES;
+                CHPROF_T0();
                 mbar_wait(full + s, round & 1);
+                CHPROF_LAP(0);
                 float4* xh = reinterpret_cast<float4*>(smem + s * G1_STAGE_BYTES);
                 float4* xl = xh + G1_TILE_BYTES / 16;
-                constexpr int NV = 1024 / G1_CONV;
-                float4 v[NV];
+                float4 v[8];
 #pragma unroll
-                for (int i = 0; i < NV; ++i) v[i] = xh[ct + G1_CONV * i];
+                for (int i = 0; i < 8; ++i) v[i] = xh[ct + 128 * i];
 #pragma unroll
-                for (int i = 0; i < NV; ++i) {
+                for (int i = 0; i < 8; ++i) {
                     // the tensor core truncates its operands to tf32 (verified: parity is unchanged), so the raw tile already acts as
-                    // hi = trunc(x); only lo = rn(x - trunc(x)) is written
+                    // hi = trunc(x)
                     float4 l;
                     lo_of_trunc(v[i], l);
-                    xl[ct + G1_CONV * i] = l;
+                    xl[ct + 128 * i] = l;
                 }
+                CHPROF_LAP(1);
                 fence_async_smem();
+                CHPROF_LAP(2);
                 mbar_arrive(conv + s);
+                CHPROF_LAP(3);
             }
         }
+        if (ct == 0) { CHPROF_PRINT("lg conv", 4, (int)(it / 2)); }
     } else {
         // epilogue: TMEM lane quarter = warp % 4; thread = one sample row
         const int q = warp & 3;
         uint32_t ai = 0;
+        CHPROF_DECL(3);
         for (long w = w0; w < w1; ++w, ++ai) {
             const int tile = (int)(w / nchunks), ch = (int)(w % nchunks);
             const uint32_t b = ai & 1;
+            CHPROF_T0();
             mbar_wait(acc_full + b, (ai >> 1) & 1);
+            CHPROF_LAP(0);
             tc_fence_after();
             const uint32_t acc = tmem_base + b * 128 + ((uint32_t)(q * 32) << 16);
             float out[64];
@@ -378,6 +416,7 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
             }
             tc_fence_before();
             mbar_arrive(acc_empty + b);
+            CHPROF_LAP(1);
             const long row = (long)tile * 128 + q * 32 + lane;
             if (row < B) {
                 // scratch layout: three dense arrays Y [chunk][B][32], R [chunk][B][16], R' [chunk][B][16] -- the scans read exactly the
@@ -393,7 +432,9 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
 #pragma unroll
                 for (int i = 0; i < 4; ++i) dp[i] = make_float4(out[48 + 4 * i], out[49 + 4 * i], out[50 + 4 * i], out[51 + 4 * i]);
             }
+            CHPROF_LAP(2);
         }
+        if (q == 0 && lane == 0) { CHPROF_PRINT("lg epi", 3, (int)ai); }
     }
     tc_fence_before();
     __syncthreads();
@@ -1219,18 +1260,6 @@ __device__ __forceinline__ void tma_load_2d_s(uint32_t dst, const CUtensorMap* m
                  "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
-#ifdef SN_CHAIN_PROF
-#define CHPROF_DECL(n) long long chp_acc[n]; for (int chp_i = 0; chp_i < n; ++chp_i) chp_acc[chp_i] = 0; long long chp_t = 0; (void)chp_t
-#define CHPROF_T0() chp_t = clock64()
-#define CHPROF_LAP(i) do { const long long chp_n = clock64(); chp_acc[i] += chp_n - chp_t; chp_t = chp_n; } while (0)
-#define CHPROF_PRINT(tag, n, steps) do { if (blockIdx.x == 0 || blockIdx.x == 301) for (int chp_i = 0; chp_i < n; ++chp_i) \
-    printf("CHPROF %s blk %d phase %d avg %lld cyc/step\n", tag, (int)blockIdx.x, chp_i, chp_acc[chp_i] / (steps)); } while (0)
-#else
-#define CHPROF_DECL(n)
-#define CHPROF_T0()
-#define CHPROF_LAP(i)
-#define CHPROF_PRINT(tag, n, steps)
-#endif
 
 // The chain is paced by what ONE epilogue thread (thread = sample) does between two MMAs, so that thread's instruction stream is
 // kept minimal: explicit LDS / STS on precomputed swizzled offsets, the raw fp32 value as the hi operand (the tensor core
@@ -1663,9 +1692,9 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
 //    layout kind::tf32 accepts for MN-major operands).
 //    A (M = 128): blocks gy_hi, L_hi, gy_lo, L_lo;  B (N = 32 (nkb+1)): x blocks then the state block; hi and lo tiles.
 // ------------------------------------------------------------------------------------------
-constexpr int G2_CONV = 256;                     // converter threads (8 warps: two per SM sub-partition)
-constexpr int G2_THREADS = 64 + G2_CONV + 128;
 constexpr int G2_STAGES = 3;
+constexpr int G2_CONV = 128 * G2_STAGES;         // converter threads: one group of four warps per pipeline stage
+constexpr int G2_THREADS = 64 + G2_CONV + 128;
 constexpr int G2_KS = 32;                        // samples per stage
 constexpr int G2_BLK = G2_KS * 128;              // one 32-feature block: 4 KB
 constexpr int G2_A_BYTES = 4 * G2_BLK;           // 16 KB
@@ -1697,7 +1726,7 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     if (t0 >= t1) return;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(conv + s, G2_CONV); mbar_init(empty + s, 1); }
+        for (int s = 0; s < G2_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(conv + s, 128); mbar_init(empty + s, 1); }
         mbar_init(acc_full, 1);
         mbar_fence_init();
         tma_prefetch_desc(&map_x);
@@ -1759,8 +1788,11 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             umma_commit(acc_full);
         }
     } else if (warp < 2 + G2_CONV / 32) {
-        const int ct = threadIdx.x - 64;
+        // one group of four converter warps per stage (see the local GEMM; a group must own its stages, or it would skip phases
+        // of their `full` barriers)
+        const int grp = (warp - 2) >> 2, ct = (threadIdx.x - 64) & 127;
         for (int t = t0, it = 0; t < t1; ++t, ++it) {
+            if (it % G2_STAGES != grp) continue;
             const int s = it % G2_STAGES, round = it / G2_STAGES;
             mbar_wait(full + s, round & 1);
             uint8_t* st = smem + s * G2_STAGE_BYTES;
@@ -1768,10 +1800,10 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 float4* h = reinterpret_cast<float4*>(st);
                 float4* l = h + 2 * G2_BLK / 16;
 #pragma unroll
-                for (int i = 0; i < 2 * G2_BLK / 16 / G2_CONV; ++i) {
+                for (int i = 0; i < 2 * G2_BLK / 16 / 128; ++i) {
                     float4 ll;
-                    lo_of_trunc(h[ct + G2_CONV * i], ll);   // hi = the raw tile (the tensor core truncates)
-                    l[ct + G2_CONV * i] = ll;
+                    lo_of_trunc(h[ct + 128 * i], ll);   // hi = the raw tile (the tensor core truncates)
+                    l[ct + 128 * i] = ll;
                 }
             }
             {   // B: x blocks + state block -> lo at +24 KB
@@ -1779,7 +1811,7 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                 float4* l = h + G2_BH_BYTES / 16;
                 const int n16 = nblk * G2_BLK / 16;
 #pragma unroll 4
-                for (int i = ct; i < n16; i += G2_CONV) {
+                for (int i = ct; i < n16; i += 128) {
                     float4 ll;
                     lo_of_trunc(h[i], ll);
                     l[i] = ll;
