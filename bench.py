@@ -56,6 +56,10 @@ class SSSWorkload:
     bytes_per_sample = 2 * bytes_per_sample_kernel        # 40 768 B / sample fwd+bwd
     flop_per_sample = 2277504
     bound = "hbm"
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch at local batch 65 536, from the `ncu --set full` capture
+    # profiles/r1p_sss_tc_top_kernels.md (cold-cache replays of the same bench command)
+    traffic_bytes = {"sss_tc_local_gemm_kernel": 1.3121e9 + 0.5069e9, "sss_tc_chain_fwd_kernel": 0.8983e9 + 0.7659e9,
+                     "sss_tc_chain_bwd_kernel": 0.4709e9 + 0.2513e9, "sss_tc_grad_gemm_kernel": 1.9837e9 + 0.0067e9}
 
     def describe(self):
         return dict(workload="C5: SSS 4096->1000, 500 stages, statespace 16, fp32 fwd+bwd (param grads), global batch 65536",
@@ -577,7 +581,7 @@ def run_ours(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sss", choices=sorted(WORKLOADS))

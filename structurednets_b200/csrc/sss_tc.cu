@@ -241,29 +241,42 @@ __device__ __forceinline__ void split_tf32(const float4& v, float4& h, float4& l
 #define CHPROF_PRINT(tag, n, steps)
 #endif
 
+// shared memory (TMA swizzled layout) -> global tensor box; rows past the tensor's extent are clipped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // ------------------------------------------------------------------------------------------
 // 2. local GEMM: [yloc | r | r'](128 samples x 64) = u_j (128 x 32 nkb) * W_j^T, 3xTF32
 //    warp 0: TMA producer | warp 1: TMEM alloc + MMA issuer | warps 2-9: lo-part converters | warps 10-13: epilogue
 // ------------------------------------------------------------------------------------------
 constexpr int G1_CONV = 256;                          // converter threads: two groups of four warps on alternate stages
 constexpr int G1_THREADS = 64 + G1_CONV + 128;
-constexpr int G1_STAGES = 4;
-static_assert(G1_STAGES % 2 == 0, "a converter group must own its stages (stage parity = group)");
+// Three rings of 16 KB tiles with their own depths: the x boxes come from HBM and need the most loads in flight, the W boxes are
+// L2 hits, the lo tiles only live between a converter group and the MMA.
+constexpr int G1_XS = 4, G1_WS = 4, G1_LS = 2;
+static_assert(G1_XS % G1_LS == 0 && G1_LS == 2, "a converter group (= lo slot) must own its x slots: it never skips a barrier phase");
 constexpr int G1_TILE_BYTES = 128 * 128;              // 128 rows x 128 B
-constexpr int G1_STAGE_BYTES = 3 * G1_TILE_BYTES;     // x (hi in place) | x_lo | W
+constexpr int G1_X_OFF = 0, G1_W_OFF = G1_XS * G1_TILE_BYTES, G1_L_OFF = G1_W_OFF + G1_WS * G1_TILE_BYTES;
+constexpr int G1_OUT_OFF = G1_L_OFF + G1_LS * G1_TILE_BYTES;   // output staging: Y [128][32] (SWIZZLE_128B) | R [128][16] | R' [128][16] (SWIZZLE_64B)
+constexpr int G1_BAR_OFF = G1_OUT_OFF + 2 * G1_TILE_BYTES;
 constexpr int G1_PF = 3;                             // L2 prefetch distance in work items
 constexpr int G1_MAX_CHUNKS = 1024;
-constexpr size_t G1_SMEM = (size_t)G1_STAGES * G1_STAGE_BYTES + 1024 + 256 + G1_MAX_CHUNKS * 8;
+constexpr size_t G1_SMEM = (size_t)G1_BAR_OFF + 1024 + 256 + G1_MAX_CHUNKS * 8;
 
 __global__ void __launch_bounds__(G1_THREADS, 1)
-sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                         const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, long B, int ntiles, float* __restrict__ rbuf) {
+sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_oy,
+                         const __grid_constant__ CUtensorMap map_or, const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, long B, int ntiles) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + G1_STAGES * G1_STAGE_BYTES);
-    uint64_t* conv = full + G1_STAGES;
-    uint64_t* empty = conv + G1_STAGES;
-    uint64_t* acc_full = empty + G1_STAGES;
+    uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + G1_BAR_OFF);
+    uint64_t* x_empty = x_full + G1_XS;
+    uint64_t* w_full = x_empty + G1_XS;
+    uint64_t* w_empty = w_full + G1_WS;
+    uint64_t* conv = w_empty + G1_WS;
+    uint64_t* l_empty = conv + G1_LS;
+    uint64_t* acc_full = l_empty + G1_LS;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -274,134 +287,132 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
     const long w1 = w0 + per < total ? w0 + per : total;
     if (w0 >= w1) return;
 
-    int2* ctab = reinterpret_cast<int2*>(smem + G1_STAGES * G1_STAGE_BYTES + 256);   // (col0, nkb) per chunk: no global load on the issue paths
+    int2* ctab = reinterpret_cast<int2*>(smem + G1_BAR_OFF + 256);   // (col0, nkb) per chunk: no global load on the issue paths
     for (int i = threadIdx.x; i < nchunks; i += G1_THREADS) ctab[i] = make_int2(chunks[i].col0, chunks[i].nkb);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < G1_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(conv + s, 128); mbar_init(empty + s, 1); }
+        for (int s = 0; s < G1_XS; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, 1); }
+        for (int s = 0; s < G1_WS; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
+        for (int s = 0; s < G1_LS; ++s) { mbar_init(conv + s, 128); mbar_init(l_empty + s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, 128); }
         mbar_fence_init();
         tma_prefetch_desc(&map_x);
         tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_oy);
+        tma_prefetch_desc(&map_or);
     }
     if (warp == 1) tmem_alloc<256>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int tile0 = (int)(w0 / nchunks), ch0 = (int)(w0 % nchunks);   // every role walks (tile, chunk) incrementally: no 64-bit divisions in the loops
 
     if (warp == 0) {
         if (elect_one()) {
-            // x boxes are pulled into L2 G1_PF items ahead of the shared-memory pipeline: 4 stages alone do not cover the HBM latency
-            auto prefetch_item = [&](long w) {
-                const int tile = (int)(w / nchunks), ch = (int)(w % nchunks);
-                const int2 c = ctab[ch];
-                for (int kb = 0; kb < c.y; ++kb) tma_prefetch_l2_2d(&map_x, c.x + kb * KBW, tile * 128);
+            // x boxes are pulled into L2 G1_PF items ahead of the shared-memory pipeline
+            int ptile = tile0, pch = ch0;
+            auto prefetch_next = [&]() {
+                const int2 c = ctab[pch];
+                for (int kb = 0; kb < c.y; ++kb) tma_prefetch_l2_2d(&map_x, c.x + kb * KBW, ptile * 128);
+                if (++pch == nchunks) { pch = 0; ++ptile; }
             };
-            for (long w = w0; w < w0 + G1_PF && w < w1; ++w) prefetch_item(w);
+            for (long w = w0; w < w0 + G1_PF && w < w1; ++w) prefetch_next();
             uint32_t it = 0;
-            CHPROF_DECL(2);
+            int tile = tile0, ch = ch0;
             for (long w = w0; w < w1; ++w) {
-                if (w + G1_PF < w1) prefetch_item(w + G1_PF);
-                const int tile = (int)(w / nchunks), ch = (int)(w % nchunks);
+                if (w + G1_PF < w1) prefetch_next();
                 const int nkb = ctab[ch].y, col0 = ctab[ch].x;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const uint32_t s = it % G1_STAGES, round = it / G1_STAGES;
-                    CHPROF_T0();
-                    if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
-                    CHPROF_LAP(0);
-                    uint8_t* st = smem + s * G1_STAGE_BYTES;
-                    mbar_expect_tx(full + s, 2 * G1_TILE_BYTES);
-                    tma_load_2d(st, &map_x, col0 + kb * KBW, tile * 128, full + s);
-                    tma_load_2d(st + 2 * G1_TILE_BYTES, &map_w, kb * KBW, ch * WROWS, full + s);
-                    CHPROF_LAP(1);
+                    const uint32_t xs = it % G1_XS, xr = it / G1_XS, ws = it % G1_WS, wr = it / G1_WS;
+                    if (xr > 0) mbar_wait(x_empty + xs, (xr - 1) & 1);
+                    mbar_expect_tx(x_full + xs, G1_TILE_BYTES);
+                    tma_load_2d(smem + G1_X_OFF + xs * G1_TILE_BYTES, &map_x, col0 + kb * KBW, tile * 128, x_full + xs);
+                    if (wr > 0) mbar_wait(w_empty + ws, (wr - 1) & 1);
+                    mbar_expect_tx(w_full + ws, G1_TILE_BYTES);
+                    tma_load_2d(smem + G1_W_OFF + ws * G1_TILE_BYTES, &map_w, kb * KBW, ch * WROWS, w_full + ws);
                 }
+                if (++ch == nchunks) { ch = 0; ++tile; }
             }
-            CHPROF_PRINT("lg prod", 2, (int)it);
         }
     } else if (warp == 1) {
         if (elect_one()) {
             constexpr uint32_t idesc1 = idesc_tf32(128, 128, false, false);   // x_hi * [W_hi ; W_lo]
             constexpr uint32_t idesc2 = idesc_tf32(128, 64, false, false);    // x_lo * W_hi
             uint32_t it = 0, ai = 0;
-            CHPROF_DECL(3);
+            int ch = ch0;
             for (long w = w0; w < w1; ++w, ++ai) {
-                const int ch = (int)(w % nchunks);
                 const int nkb = ctab[ch].y;
                 const uint32_t b = ai & 1;
-                CHPROF_T0();
                 if (ai >= 2) mbar_wait(acc_empty + b, ((ai >> 1) - 1) & 1);
-                CHPROF_LAP(0);
                 tc_fence_after();
                 const uint32_t acc = tmem_base + b * 128;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const uint32_t s = it % G1_STAGES, round = it / G1_STAGES;
-                    CHPROF_T0();
-                    mbar_wait(conv + s, round & 1);
-                    CHPROF_LAP(1);
+                    const uint32_t xs = it % G1_XS, ws = it % G1_WS, wr = it / G1_WS, ls = it % G1_LS, lr = it / G1_LS;
+                    mbar_wait(w_full + ws, wr & 1);
+                    mbar_wait(conv + ls, lr & 1);          // the converters waited for the x box
                     tc_fence_after();
-                    uint8_t* st = smem + s * G1_STAGE_BYTES;
-                    const uint64_t dxh = desc_kmajor_sw128(st);
-                    const uint64_t dxl = desc_kmajor_sw128(st + G1_TILE_BYTES);
-                    const uint64_t dw = desc_kmajor_sw128(st + 2 * G1_TILE_BYTES);
+                    const uint64_t dxh = desc_kmajor_sw128(smem + G1_X_OFF + xs * G1_TILE_BYTES);
+                    const uint64_t dxl = desc_kmajor_sw128(smem + G1_L_OFF + ls * G1_TILE_BYTES);
+                    const uint64_t dw = desc_kmajor_sw128(smem + G1_W_OFF + ws * G1_TILE_BYTES);
 #pragma unroll
                     for (int k = 0; k < KBW / 8; ++k) {   // one tf32 UMMA = 8 floats = 32 bytes of K (+2 in 16-byte units)
                         mma_tf32(acc, dxh + 2 * k, dw + 2 * k, idesc1, (kb | k) ? 1u : 0u);
                         mma_tf32(acc, dxl + 2 * k, dw + 2 * k, idesc2, 1u);
                     }
-                    umma_commit(empty + s);
-                    CHPROF_LAP(2);
+                    umma_commit(l_empty + ls);
+                    umma_commit(x_empty + xs);
+                    umma_commit(w_empty + ws);
                 }
                 umma_commit(acc_full + b);
+                if (++ch == nchunks) ch = 0;
             }
-            CHPROF_PRINT("lg mma", 3, (int)it);
         }
     } else if (warp < 2 + G1_CONV / 32) {
-        // converters: only lo = rn(x - trunc(x)) is written (second tile; identical swizzled layout, so plain 16-byte chunks).
+        // converters: the raw tile is the hi operand (the tensor core truncates its operands to tf32; verified: parity is unchanged),
+        // only lo = rn(x - trunc(x)) is written, into the lo ring (identical swizzled layout, so plain 16-byte chunks).
         // A stage costs one converter warp a full LDS -> STS -> proxy-fence round trip, so two groups of four warps take alternate
-        // stages (stage parity = group: a group never skips a phase of a `full` barrier): two stages are always in conversion.
+        // stages (group = lo slot; it owns x slots of its own parity and never skips a phase of their barriers).
         const int grp = (warp - 2) >> 2, ct = (threadIdx.x - 64) & 127;
         uint32_t it = 0;
-        CHPROF_DECL(4);
+        int ch = ch0;
         for (long w = w0; w < w1; ++w) {
-            const int nkb = ctab[(int)(w % nchunks)].y;
+            const int nkb = ctab[ch].y;
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 if ((int)(it & 1) != grp) continue;
-                const uint32_t s = it % G1_STAGES, round = it / G1_STAGES;
-                CHPROF_T0();
-                mbar_wait(full + s, round & 1);
-                CHPROF_LAP(0);
-                float4* xh = reinterpret_cast<float4*>(smem + s * G1_STAGE_BYTES);
-                float4* xl = xh + G1_TILE_BYTES / 16;
+                const uint32_t xs = it % G1_XS, xr = it / G1_XS, lr = it / G1_LS;
+                mbar_wait(x_full + xs, xr & 1);
+                const float4* xh = reinterpret_cast<const float4*>(smem + G1_X_OFF + xs * G1_TILE_BYTES);
+                float4* xl = reinterpret_cast<float4*>(smem + G1_L_OFF + grp * G1_TILE_BYTES);
                 float4 v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = xh[ct + 128 * i];
+                if (lr > 0) mbar_wait(l_empty + grp, (lr - 1) & 1);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    // the tensor core truncates its operands to tf32 (verified: parity is unchanged), so the raw tile already acts as
-                    // hi = trunc(x)
                     float4 l;
                     lo_of_trunc(v[i], l);
                     xl[ct + 128 * i] = l;
                 }
-                CHPROF_LAP(1);
                 fence_async_smem();
-                CHPROF_LAP(2);
-                mbar_arrive(conv + s);
-                CHPROF_LAP(3);
+                mbar_arrive(conv + grp);
             }
+            if (++ch == nchunks) ch = 0;
         }
-        if (ct == 0) { CHPROF_PRINT("lg conv", 4, (int)(it / 2)); }
     } else {
-        // epilogue: TMEM lane quarter = warp % 4; thread = one sample row
+        // epilogue: TMEM lane quarter = warp % 4; thread = one sample row.  The rows go through a swizzled staging tile and leave as
+        // three TMA tensor stores (Y [chunk][B][32], R and R' [chunk][B][16]: 16 + 8 + 8 KB of contiguous global memory per item).
+        // Per-thread 16-byte stores at a 128-byte lane stride filled every 32-byte sector in two halves: the L2 fetched the sectors
+        // from DRAM to merge them (+0.24 GB read per launch) and the kernel was a third slower.
         const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const bool leader = (warp == 2 + G1_CONV / 32) && lane == 0;
+        const uint32_t sy = smem_u32(smem + G1_OUT_OFF), sr = sy + G1_TILE_BYTES, sp = sr + G1_TILE_BYTES / 2;
+        const uint32_t oy = sy + r * 128, orr = sr + r * 64, opp = sp + r * 64;
         uint32_t ai = 0;
-        CHPROF_DECL(3);
+        int tile = tile0, ch = ch0;
         for (long w = w0; w < w1; ++w, ++ai) {
-            const int tile = (int)(w / nchunks), ch = (int)(w % nchunks);
             const uint32_t b = ai & 1;
-            CHPROF_T0();
             mbar_wait(acc_full + b, (ai >> 1) & 1);
-            CHPROF_LAP(0);
             tc_fence_after();
             const uint32_t acc = tmem_base + b * 128 + ((uint32_t)(q * 32) << 16);
             float out[64];
@@ -416,25 +427,30 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
             }
             tc_fence_before();
             mbar_arrive(acc_empty + b);
-            CHPROF_LAP(1);
-            const long row = (long)tile * 128 + q * 32 + lane;
-            if (row < B) {
-                // scratch layout: three dense arrays Y [chunk][B][32], R [chunk][B][16], R' [chunk][B][16] -- the scans read exactly the
-                // rows they need (a 64-float interleaved row made DRAM fetch the unused half as well)
-                const size_t NB = (size_t)nchunks * B, ri = (size_t)ch * B + row;
-                float4* dy = reinterpret_cast<float4*>(rbuf + ri * 32);
-                float4* dr = reinterpret_cast<float4*>(rbuf + NB * 32 + ri * 16);
-                float4* dp = reinterpret_cast<float4*>(rbuf + NB * 48 + ri * 16);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) dy[i] = make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dr[i] = make_float4(out[32 + 4 * i], out[33 + 4 * i], out[34 + 4 * i], out[35 + 4 * i]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dp[i] = make_float4(out[48 + 4 * i], out[49 + 4 * i], out[50 + 4 * i], out[51 + 4 * i]);
+            if (ai > 0) {   // the previous item's stores have read the staging tile
+                if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                named_bar_sync(1, 128);
             }
-            CHPROF_LAP(2);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(oy + ((c ^ (r & 7)) << 4)), "f"(out[4 * c]), "f"(out[4 * c + 1]), "f"(out[4 * c + 2]), "f"(out[4 * c + 3]) : "memory");
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t o = (uint32_t)((c ^ ((r >> 1) & 3)) << 4);
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(orr + o), "f"(out[32 + 4 * c]), "f"(out[33 + 4 * c]), "f"(out[34 + 4 * c]), "f"(out[35 + 4 * c]) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(opp + o), "f"(out[48 + 4 * c]), "f"(out[49 + 4 * c]), "f"(out[50 + 4 * c]), "f"(out[51 + 4 * c]) : "memory");
+            }
+            fence_async_smem();
+            named_bar_sync(1, 128);
+            if (leader) {
+                tma_store_3d(&map_oy, sy, 0, tile * 128, ch);
+                tma_store_3d(&map_or, sr, 0, tile * 128, ch);
+                tma_store_3d(&map_or, sp, 0, tile * 128, nchunks + ch);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (++ch == nchunks) { ch = 0; ++tile; }
         }
-        if (q == 0 && lane == 0) { CHPROF_PRINT("lg epi", 3, (int)ai); }
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -479,9 +495,11 @@ __device__ __forceinline__ void matvec_acc(const float4* __restrict__ M, const f
 constexpr int F_THREADS = 448;
 constexpr int F_MAX_CHUNKS = 512;
 constexpr int F_SC_HALF = DS * DS + PO * DS + PO;   // 800 floats: one direction's Phi and O, then the chunk's bias entries
+// the fused variant keeps the original 4-stage ring of (x | x_lo | W) tiles
+constexpr int G1_STAGES = 4;
+constexpr int G1_STAGE_BYTES = 3 * G1_TILE_BYTES;
 constexpr size_t F_SMEM = (size_t)G1_STAGES * G1_STAGE_BYTES + 256 + F_MAX_CHUNKS * 16 + 4 * F_SC_HALF * 4 + 1024;
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // cooperative copy of one direction's {Phi (64 float4), O (128 float4)} by 128 threads: registers first (latency hidden behind
 // the barrier wait that follows), shared memory later
@@ -2128,7 +2146,13 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
     const long total = (long)ntiles * p->nchunks;
     const int grid = (int)(total < sm_count() ? total : sm_count());
     SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_local_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G1_SMEM));
-    SN_LAUNCH("sss_tc_local_gemm_kernel", st, sss_tc_local_gemm_kernel<<<grid, G1_THREADS, G1_SMEM, st>>>(mx, mw, p->chunks, p->nchunks, (long)B, ntiles, rbuf));
+    CUtensorMap moy, mor;   // output boxes: Y [chunk][B][32], then R [chunk][B][16] and R' [chunk][B][16] back to back (chunk index nchunks + ch)
+    {
+        const uint64_t NBo = (uint64_t)p->nchunks * B;
+        if (int rc = make_map_f32(&moy, rbuf, 32, (uint64_t)B, 32, 128, (uint64_t)p->nchunks, (uint64_t)B * 32)) return rc;
+        if (int rc = make_map_f32(&mor, rbuf + NBo * 32, 16, (uint64_t)B, 16, 128, (uint64_t)2 * p->nchunks, (uint64_t)B * 16, false, 16)) return rc;
+    }
+    SN_LAUNCH("sss_tc_local_gemm_kernel", st, sss_tc_local_gemm_kernel<<<grid, G1_THREADS, G1_SMEM, st>>>(mx, mw, moy, mor, p->chunks, p->nchunks, (long)B, ntiles));
     if (use_tc_chain(B)) {
         CUtensorMap mc;
         const float* CW = SC + (size_t)p->nchunks * SCF;
