@@ -1527,33 +1527,42 @@ sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
 
 // backward: steps 0..nc-1 = lambda chain over chunks nc-1..0, steps nc..2nc-1 = mu chain over chunks 0..nc-1.
 // L[j][row][0..15] = lambda_{j+1}, L[j][row][16..31] = mu_j ; grad_bias += column sums of grad_y (second chain, by the writer warps).
-// Ring slot of step t: coefficient tile of step t + the grad_y rows of step t + 1.  While the MMA of step t is in flight the
-// epilogue thread fetches its row of step t + 1 and computes its lo part in registers; after the accumulator arrives it only adds,
-// splits the 16 state values and stores the operand rows.  Step 0's rows arrive through a prologue load into the (still unused) lo tile.
-__global__ void __launch_bounds__(CH_THREADS, 2)
+// Ring slot of step t: coefficient tile of step t + the grad_y rows of step t + 1.  The chain is paced by the instruction stream of
+// the epilogue threads between two MMAs, so a sample row is shared by TWO threads (warps w and w + 4 read the same TMEM lanes):
+// each takes half of the grad_y row and half of the state.  While the MMA of step t is in flight a thread fetches its half row of
+// step t + 1 and computes the lo part in registers; after the accumulator arrives it only adds, splits its 8 state values and stores
+// the operand rows.  Step 0's rows arrive through a prologue load into the (still unused) lo tile.
+constexpr int CHB_EPI = 256;                       // warps 0-7: epilogue, warp 8: TMA + MMA issuer (one lane), warps 9-10: writers
+constexpr int CHB_THREADS = CHB_EPI + 32 + CH_WRITERS;
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+__global__ void __launch_bounds__(CHB_THREADS, 2)
 sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid_constant__ CUtensorMap map_gy, const sn_sss_tc_chunk* __restrict__ chunks,
                         int nchunks, float* __restrict__ L, float* __restrict__ gbias, long B) {
     extern __shared__ uint8_t smem_raw[];
     using M = ChainMap<true>;
     const uint32_t sb = chain_base(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const int nsteps = 2 * nchunks;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init_s(sb + M::full + 8 * i, 1); mbar_init_s(sb + M::slot_free + 8 * i, 129 + CH_WRITERS); }
-        mbar_init_s(sb + M::state_ready, 128); mbar_init_s(sb + M::acc_full, 1); mbar_init_s(sb + M::chain_done, 1);
-        mbar_init_s(sb + M::lst_ready, 128); mbar_init_s(sb + M::lst_free, CH_WRITERS);
+        for (int i = 0; i < 2; ++i) { mbar_init_s(sb + M::full + 8 * i, 1); mbar_init_s(sb + M::slot_free + 8 * i, CHB_EPI + 1 + CH_WRITERS); }
+        mbar_init_s(sb + M::state_ready, CHB_EPI); mbar_init_s(sb + M::acc_full, 1); mbar_init_s(sb + M::chain_done, 1);
+        mbar_init_s(sb + M::lst_ready, CHB_EPI); mbar_init_s(sb + M::lst_free, CH_WRITERS);
         mbar_fence_init();
         tma_prefetch_desc(&map_cw);
         tma_prefetch_desc(&map_gy);
     }
-    if (warp == 4) tmem_alloc_s<32>(sb + M::tmem_slot);
+    if (warp == 8) tmem_alloc_s<32>(sb + M::tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = lds32_u(sb + M::tmem_slot);
     auto chunk_of = [&](int t) { return t < nchunks ? nchunks - 1 - t : t - nchunks; };
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (elect_one()) {
             auto issue = [&](int t) {
                 const int s = t & 1, j = chunk_of(t);
@@ -1600,20 +1609,48 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
             }
             CHPROF_PRINT("bwd mma", 4, nsteps);
         }
-    } else if (warp < 4) {
-        const int r = threadIdx.x;
-        const RowOffs ro(r);
-        const uint32_t tacc = tmem + ((uint32_t)(warp * 32) << 16);
-        float st[DS], g[PO], gl[PO];
+    } else if (warp < 8) {
+        const int r = threadIdx.x & 127, h = threadIdx.x >> 7;          // tile row, half
+        // byte offsets of this thread's 16-byte chunks (runtime half -> computed here, not indexed out of a table)
+        uint32_t og[4], osr[2], osl[2], ock[2];
 #pragma unroll
-        for (int a = 0; a < DS; ++a) st[a] = 0.f;
+        for (int c = 0; c < 4; ++c) og[c] = (uint32_t)(r * 128 + (((4 * h + c) ^ (r & 7)) << 4));
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            osr[c] = (uint32_t)(r * 128 + (((2 * h + c) ^ (r & 7)) << 4));
+            osl[c] = (uint32_t)(r * 128 + (((4 + 2 * h + c) ^ (r & 7)) << 4));
+            ock[c] = (uint32_t)(r * 64 + (((2 * h + c) ^ ((r >> 1) & 3)) << 4));
+        }
+        const uint32_t tacc = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        // this thread's 16-byte chunks: grad_y row chunks 4h..4h+3, state raw chunks 2h, 2h+1 and lo chunks 4+2h, 5+2h, checkpoint chunks 2h, 2h+1
+        float st[8], g[16], gl[16];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) st[a] = 0.f;
+        auto load_g = [&](uint32_t tile) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float4 v = lds128(tile + og[c]);
+                g[4 * c] = v.x; g[4 * c + 1] = v.y; g[4 * c + 2] = v.z; g[4 * c + 3] = v.w;
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) gl[c] = lo_of_trunc(g[c]);
+        };
+        auto store_operands = [&]() {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                sts128(sb + M::state + osr[c], st[4 * c], st[4 * c + 1], st[4 * c + 2], st[4 * c + 3]);
+                sts128(sb + M::state + osl[c], lo_of_trunc(st[4 * c]), lo_of_trunc(st[4 * c + 1]), lo_of_trunc(st[4 * c + 2]),
+                       lo_of_trunc(st[4 * c + 3]));
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                sts128(sb + M::in_hi + og[c], g[4 * c], g[4 * c + 1], g[4 * c + 2], g[4 * c + 3]);
+                sts128(sb + M::in_lo + og[c], gl[4 * c], gl[4 * c + 1], gl[4 * c + 2], gl[4 * c + 3]);
+            }
+        };
         mbar_wait_s(sb + M::chain_done, 0);
-        load_row128_s(sb + M::in_lo, ro, g);        // raw grad_y rows of step 0 (each thread only touches its own 128-byte row)
-#pragma unroll
-        for (int c = 0; c < PO; ++c) gl[c] = lo_of_trunc(g[c]);
-        store_state_raw_lo(sb + M::state, ro, st);
-        store_row128_s(sb + M::in_hi, ro, g);
-        store_row128_s(sb + M::in_lo, ro, gl);
+        load_g(sb + M::in_lo);        // raw grad_y rows of step 0 (each thread only touches its own half row)
+        store_operands();
         fence_async_smem();
         mbar_arrive_s(sb + M::state_ready);
         CHPROF_DECL(6);
@@ -1623,34 +1660,29 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
             CHPROF_T0();
             // checkpoint of the adjoint entering this step -> staging tile (the writers emptied it during the previous step)
             if (t > 0) mbar_wait_s(sb + M::lst_free, (t - 1) & 1);
-            store_row64_s(sb + M::lstage, ro, st);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) sts128(sb + M::lstage + ock[c], st[4 * c], st[4 * c + 1], st[4 * c + 2], st[4 * c + 3]);
             mbar_arrive_s(sb + M::lst_ready);
             CHPROF_LAP(0);
-            // next step's grad_y row and its lo part, while this step's MMA runs
+            // next step's grad_y half row and its lo part, while this step's MMA runs
             mbar_wait_s(sb + M::full + 8 * s, (t >> 1) & 1);
-            if (has_next) {
-                load_row128_s(sb + M::slot0 + s * M::slot_bytes + CHB_W_BYTES, ro, g);
-#pragma unroll
-                for (int c = 0; c < PO; ++c) gl[c] = lo_of_trunc(g[c]);
-            }
+            if (has_next) load_g(sb + M::slot0 + s * M::slot_bytes + CHB_W_BYTES);
             mbar_arrive_s(sb + M::slot_free + 8 * s);
             CHPROF_LAP(1);
             mbar_wait_s(sb + M::acc_full, t & 1);
             CHPROF_LAP(2);
             tc_fence_after();
-            uint32_t m[16], l[16];
-            tmem_ld16_nowait(tacc, m);
-            tmem_ld16_nowait(tacc + 16, l);
+            uint32_t m[8], l[8];
+            tmem_ld8_nowait(tacc + 8 * h, m);
+            tmem_ld8_nowait(tacc + 16 + 8 * h, l);
             tmem_ld_wait();
             tc_fence_before();
             const bool last_of_chain = (t == nchunks - 1);
 #pragma unroll
-            for (int a = 0; a < DS; ++a) st[a] = last_of_chain ? 0.f : (__uint_as_float(m[a]) + __uint_as_float(l[a]));
+            for (int a = 0; a < 8; ++a) st[a] = last_of_chain ? 0.f : (__uint_as_float(m[a]) + __uint_as_float(l[a]));
             CHPROF_LAP(3);
             if (has_next) {
-                store_state_raw_lo(sb + M::state, ro, st);
-                store_row128_s(sb + M::in_hi, ro, g);
-                store_row128_s(sb + M::in_lo, ro, gl);
+                store_operands();
                 CHPROF_LAP(4);
                 fence_async_smem();
                 mbar_arrive_s(sb + M::state_ready);
@@ -1660,7 +1692,7 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
         if (threadIdx.x == 0) { CHPROF_PRINT("bwd epi", 6, nsteps); }
     } else {
         // writers: adjoint checkpoints -> L; column sums of the second chain's grad_y rows -> grad_bias
-        const int wt = threadIdx.x - 160;
+        const int wt = threadIdx.x - (CHB_EPI + 32);
         for (int t = 0; t < nsteps; ++t) {
             const int j = chunk_of(t), s = t & 1;
             mbar_wait_s(sb + M::lst_ready, t & 1);
@@ -1682,7 +1714,7 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 4
                 for (int rr = 0; rr < 64; rr += 4) {
-                    const int row = r0 + rr;     // row & 7 takes the values (rr & 7) + 0..3: the swizzle term is per row
+                    const int row = r0 + rr;
                     a0 += lds32(tile + row * 128 + (((col >> 2) ^ (row & 7)) << 4) + (col & 3) * 4);
                     a1 += lds32(tile + (row + 1) * 128 + (((col >> 2) ^ ((row + 1) & 7)) << 4) + (col & 3) * 4);
                     a2 += lds32(tile + (row + 2) * 128 + (((col >> 2) ^ ((row + 2) & 7)) << 4) + (col & 3) * 4);
@@ -1698,7 +1730,7 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc<32>(tmem);
     }
@@ -2199,7 +2231,7 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
         if (int rc = make_map_f32(&mgy, grad_y, (uint64_t)p->output_dim, (uint64_t)B, (uint64_t)ldgy, 128)) return rc;
         if (int rc = make_map_f32(&mc, CW, 32, (uint64_t)p->nchunks * 4 * CW_ROWS, 32, 64)) return rc;   // state + grad_y sub-tiles only
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHB_SMEM));
-        SN_LAUNCH("sss_tc_chain_bwd_kernel", st, sss_tc_chain_bwd_kernel<<<(unsigned)((B + 127) / 128), CH_THREADS, CHB_SMEM, st>>>(mc, mgy, p->chunks, p->nchunks, L, grad_bias, (long)B));
+        SN_LAUNCH("sss_tc_chain_bwd_kernel", st, sss_tc_chain_bwd_kernel<<<(unsigned)((B + 127) / 128), CHB_THREADS, CHB_SMEM, st>>>(mc, mgy, p->chunks, p->nchunks, L, grad_bias, (long)B));
     } else {
         const int qs_threads = B <= 16384 ? 64 : QS_THREADS;
         const unsigned ydim = use_split_scans(B) ? 2u : 1u;
