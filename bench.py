@@ -303,7 +303,30 @@ class ClockSampler:
         self._stop = threading.Event()
         self._thr = None
 
+    def _run_nvml(self):
+        """NVML (nvidia_ml_py) sampling every ~5 ms: the timed region of a fast workload is shorter than one nvidia-smi call."""
+        import pynvml as N
+        N.nvmlInit()
+        h = N.nvmlDeviceGetHandleByIndex(self.gpu_index)
+        mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+        bits = (("hw_slowdown", N.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", N.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", N.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", N.nvmlClocksThrottleReasonSwPowerCap))
+        while not self._stop.is_set():
+            sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+            r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            try:
+                pw = N.nvmlDeviceGetPowerUsage(h) / 1000.0
+            except Exception:
+                pw = 0.0
+            self.rows.append([str(self.gpu_index), str(sm), str(mx), str(pw)] + ["Active" if (r & b) else "Not Active" for _, b in bits])
+            self._stop.wait(0.005)
+
     def _run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],

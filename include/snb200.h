@@ -210,6 +210,28 @@ int sn_psm_forward(const sn_psm_factor* factors_host, int nf, const float* x, in
 int sn_psm_backward(const sn_psm_factor* factors_host, int nf, const float* x, int64_t ldx, const float* grad_y, int64_t ldgy,
                     float* grad_bias, int64_t B, int in_dim, int out_dim, sn_stream_t stream);
 
+/* Dense-product path of the PSM layer for large batches (csrc/psm.cu): the batch-independent product W = S_0 .. S_{n-1} is
+ * multiplied out once per call (transposed prefix products, kept in `prefix` for the backward), applied / differentiated on the
+ * tensor cores, and the dense gradient is projected back onto every factor's pattern.  The reference's default forward also
+ * multiplies the densified factors with dense GEMMs (layers/psm_layer.py:47-60).  csr_* / csc_*: the pattern by rows / by
+ * columns (ptr [rows + 1] / [cols + 1], idx = column / row index, src = index into the parameter's COO value array);
+ * coo_row / coo_col: the COO indices as int32.  output_dim must be a multiple of 4. */
+typedef struct sn_psm_dense_factor {
+    int32_t rows, cols, nnz, reserved;
+    const int32_t *csr_ptr, *csr_idx, *csr_src;
+    const int32_t *csc_ptr, *csc_idx, *csc_src;
+    const int32_t *coo_row, *coo_col;
+    const float* vals;
+    float* grad_vals;
+} sn_psm_dense_factor;
+size_t sn_psm_dense_prefix_floats(const sn_psm_dense_factor* factors_host, int nf, int out_dim);
+size_t sn_psm_dense_backward_floats(const sn_psm_dense_factor* factors_host, int nf, int out_dim);
+int sn_psm_dense_forward(const sn_psm_dense_factor* factors_host, int nf, const float* x, int64_t ldx, float* y, int64_t ldy,
+                         const float* bias, float* prefix, int64_t B, int in_dim, int out_dim, sn_stream_t stream);
+int sn_psm_dense_backward(const sn_psm_dense_factor* factors_host, int nf, const float* x, int64_t ldx, const float* grad_y,
+                          int64_t ldgy, const float* prefix, float* work, float* grad_bias, int64_t B, int in_dim, int out_dim,
+                          sn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * LDR layer -- replaces build_weight_matrix_torch (approximators/ldr_approximator.py:29-39) + the matmul of
  * LDRLayer.forward (layers/ldr_layer.py:54-58) and their backward.  A, B: COO value arrays (float64) with a slot

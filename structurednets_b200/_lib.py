@@ -45,6 +45,11 @@ class SnPsmFactor(Structure):
                [(n, c_void_p) for n in ("vals", "grad_vals", "val_fwd", "val_tr", "grad_packed")]
 
 
+class SnPsmDenseFactor(Structure):
+    _fields_ = [("rows", c_int32), ("cols", c_int32), ("nnz", c_int32), ("reserved", c_int32)] + \
+               [(n, c_void_p) for n in ("csr_ptr", "csr_idx", "csr_src", "csc_ptr", "csc_idx", "csc_src", "coo_row", "coo_col", "vals", "grad_vals")]
+
+
 _lib = None
 
 
@@ -102,6 +107,15 @@ def _declare(lib):
     lib.sn_psm_forward.argtypes = [PF, i32, vp, i64, vp, i64, vp, i64, i32, i32, vp]
     lib.sn_psm_backward.restype = c_int
     lib.sn_psm_backward.argtypes = [PF, i32, vp, i64, vp, i64, vp, i64, i32, i32, vp]
+    PD = POINTER(SnPsmDenseFactor)
+    lib.sn_psm_dense_prefix_floats.restype = c_size_t
+    lib.sn_psm_dense_prefix_floats.argtypes = [PD, i32, i32]
+    lib.sn_psm_dense_backward_floats.restype = c_size_t
+    lib.sn_psm_dense_backward_floats.argtypes = [PD, i32, i32]
+    lib.sn_psm_dense_forward.restype = c_int
+    lib.sn_psm_dense_forward.argtypes = [PD, i32, vp, i64, vp, i64, vp, vp, i64, i32, i32, vp]
+    lib.sn_psm_dense_backward.restype = c_int
+    lib.sn_psm_dense_backward.argtypes = [PD, i32, vp, i64, vp, i64, vp, vp, vp, i64, i32, i32, vp]
     f64 = ctypes.c_double
     lib.sn_ldr_workspace_doubles.restype = c_size_t
     lib.sn_ldr_workspace_doubles.argtypes = [i32, i32]

@@ -14,6 +14,7 @@
 // accumulates dS in the same packed order with coalesced reductions and scatters it back once.
 #include "common.cuh"
 #include "util.cuh"
+#include "gemm_f32.cuh"
 
 namespace {
 
@@ -200,6 +201,71 @@ int pack_vals(const sn_psm_ell& e, const float* vals, float* out, cudaStream_t s
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Dense-product path (large batches).  The product of the factors is batch independent, so for B >> dims the step is cheapest as
+//   W^T = (S_0 S_1 ... S_{n-1})^T built once per call by sparse-times-dense row combinations (all matrices kept TRANSPOSED,
+//   [dim][out_dim], so every row operation is a coalesced stream of out_dim floats),
+//   y = x W^T^T + b and G^T = x^T grad_y on the tensor cores (3xTF32, csrc/gemm_tf32x3.cuh),
+//   dS_k[m][j] = < L_k^T[m][:], H_k^T[j][:] > on the pattern, with the prefix products L_k = S_0 .. S_{k-1} kept from the forward and the
+//   suffix recursion H_{k-1}^T = S_k H_k^T, H_{n-1}^T = G^T.
+// This is also what the reference's default forward does (dense GEMMs on the densified factors, layers/psm_layer.py:47-60).
+// ------------------------------------------------------------------------------------------
+// Out[r][:] = sum over the entries e of row r of the sparse matrix: vals[src[e]] * In[idx[e]][:]   (In == nullptr: identity rows)
+__global__ void __launch_bounds__(256)
+psm_rowcomb_kernel(const int* __restrict__ ptr, const int* __restrict__ idx, const int* __restrict__ src, const float* __restrict__ vals,
+                   const float* __restrict__ In, float* __restrict__ Out, int width) {
+    const int r = blockIdx.x;
+    const int e0 = ptr[r], e1 = ptr[r + 1];
+    float* out = Out + (size_t)r * width;
+    if (In == nullptr) {   // the first factor: row r of S_0^T scattered into a zero row
+        for (int c = threadIdx.x; c < width; c += blockDim.x) out[c] = 0.f;
+        __syncthreads();
+        for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) atomicAdd(out + idx[e], vals[src[e]]);
+        return;
+    }
+    const int w4 = width >> 2;
+    for (int c = threadIdx.x; c < w4; c += blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = e0; e < e1; ++e) {
+            const float v = __ldg(vals + __ldg(src + e));
+            const float4 x = __ldg(reinterpret_cast<const float4*>(In + (size_t)__ldg(idx + e) * width) + c);
+            acc.x = fmaf(v, x.x, acc.x); acc.y = fmaf(v, x.y, acc.y); acc.z = fmaf(v, x.z, acc.z); acc.w = fmaf(v, x.w, acc.w);
+        }
+        reinterpret_cast<float4*>(out)[c] = acc;
+    }
+}
+// one warp per non-zero e = (m, j): g[e] += < Lt[m][:], Ht[j][:] >;  Lt == nullptr (first factor, L_0 = I): g[e] += Ht[j][m]
+__global__ void __launch_bounds__(256)
+psm_masked_dot_kernel(const int* __restrict__ row, const int* __restrict__ col, int nnz, const float* __restrict__ Lt, const float* __restrict__ Ht,
+                      float* __restrict__ g, int width) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nnz) return;
+    const int m = row[warp], j = col[warp];
+    if (Lt == nullptr) {
+        if (lane == 0) g[warp] += Ht[(size_t)j * width + m];
+        return;
+    }
+    const float4* a = reinterpret_cast<const float4*>(Lt + (size_t)m * width);
+    const float4* b = reinterpret_cast<const float4*>(Ht + (size_t)j * width);
+    float acc = 0.f;
+    for (int c = lane; c < (width >> 2); c += 32) {
+        const float4 x = __ldg(a + c), y = __ldg(b + c);
+        acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) g[warp] += acc;
+}
+
+int check_dense_chain(const sn_psm_dense_factor* f, int nf, int in_dim, int out_dim) {
+    SN_CHECK_ARG(f != nullptr && nf >= 1 && nf <= PSM_MAX_FACTORS, "psm_dense: need 1..%d factors", PSM_MAX_FACTORS);
+    SN_CHECK_ARG(out_dim % 4 == 0, "psm_dense: output_dim must be a multiple of 4");
+    SN_CHECK_ARG(f[0].rows == out_dim && f[nf - 1].cols == in_dim, "psm_dense: the factors do not map input_dim -> output_dim");
+    for (int k = 0; k + 1 < nf; ++k) SN_CHECK_ARG(f[k].cols == f[k + 1].rows, "psm_dense: factors %d and %d cannot be multiplied", k, k + 1);
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -243,6 +309,66 @@ int sn_psm_backward(const sn_psm_factor* factors_host, int nf, const float* x, i
         const sn_psm_factor& f = factors_host[k];
         if (f.fwd.total > 0)
             SN_LAUNCH("psm_unpack_grad_kernel", st, psm_unpack_grad_kernel<<<snb::ceil_div(f.fwd.total, 256), 256, 0, st>>>(f.fwd.src, f.grad_packed, f.grad_vals, f.fwd.total));
+    }
+    return 0;
+}
+
+
+size_t sn_psm_dense_prefix_floats(const sn_psm_dense_factor* f, int nf, int out_dim) {
+    size_t n = 0;
+    for (int k = 0; f != nullptr && k < nf; ++k) n += (size_t)f[k].cols * out_dim;
+    return n;
+}
+size_t sn_psm_dense_backward_floats(const sn_psm_dense_factor* f, int nf, int out_dim) {
+    size_t n = 0;
+    for (int k = 0; f != nullptr && k < nf; ++k) n += (size_t)f[k].cols * out_dim;
+    return n;
+}
+/* prefix: L_1^T | L_2^T | ... | L_n^T = W^T ([cols_{k-1}][out_dim] each), kept by the caller for the backward */
+int sn_psm_dense_forward(const sn_psm_dense_factor* f, int nf, const float* x, int64_t ldx, float* y, int64_t ldy, const float* bias,
+                         float* prefix, int64_t B, int in_dim, int out_dim, sn_stream_t stream) {
+    if (int rc = check_dense_chain(f, nf, in_dim, out_dim)) return rc;
+    SN_CHECK_ARG(x && y && prefix, "psm_dense_forward: NULL buffer");
+    if (B <= 0) return 0;
+    cudaStream_t st = snb::as_stream(stream);
+    float* cur = prefix;
+    const float* prev = nullptr;
+    for (int k = 0; k < nf; ++k) {
+        // L_{k+1}^T = S_k^T L_k^T: the rows of S_k^T are the columns of S_k (csc)
+        SN_LAUNCH("psm_rowcomb_kernel", st, psm_rowcomb_kernel<<<f[k].cols, 256, 0, st>>>(f[k].csc_ptr, f[k].csc_idx, f[k].csc_src, f[k].vals, prev, cur, out_dim));
+        prev = cur;
+        cur += (size_t)f[k].cols * out_dim;
+    }
+    // y = x W^T^T + b: W^T is stored [in_dim][out_dim]
+    return snb::gemm_f32(false, false, (int)B, out_dim, in_dim, 1.f, x, ldx, prev, out_dim, 0.f, y, ldy, bias, st);
+}
+/* work: sn_psm_dense_backward_floats floats; grad_vals of every factor (COO order) and grad_bias are accumulated into */
+int sn_psm_dense_backward(const sn_psm_dense_factor* f, int nf, const float* x, int64_t ldx, const float* grad_y, int64_t ldgy,
+                          const float* prefix, float* work, float* grad_bias, int64_t B, int in_dim, int out_dim, sn_stream_t stream) {
+    if (int rc = check_dense_chain(f, nf, in_dim, out_dim)) return rc;
+    SN_CHECK_ARG(x && grad_y && prefix && work, "psm_dense_backward: NULL buffer");
+    if (B <= 0) return 0;
+    cudaStream_t st = snb::as_stream(stream);
+    if (grad_bias)
+        if (int rc = snb::colsum_accumulate(grad_y, ldgy, B, out_dim, grad_bias, st)) return rc;
+    // work: H_{n-1}^T = G^T [in_dim][out_dim], then H_{n-2}^T [rows_{n-1}][out_dim], ...
+    float* Ht = work;
+    SN_CHECK_CUDA(cudaMemsetAsync(Ht, 0, (size_t)in_dim * out_dim * sizeof(float), st));
+    if (int rc = snb::gemm_f32(true, false, in_dim, out_dim, (int)B, 1.f, x, ldx, grad_y, ldgy, 1.f, Ht, out_dim, nullptr, st, true)) return rc;
+    // prefix offsets: L_k^T for k >= 1 starts after the first k - 1 blocks
+    size_t off[PSM_MAX_FACTORS + 1];
+    off[0] = 0;
+    for (int k = 0; k < nf; ++k) off[k + 1] = off[k] + (size_t)f[k].cols * out_dim;
+    for (int k = nf - 1; k >= 0; --k) {
+        const float* Lt = k == 0 ? nullptr : prefix + off[k - 1];
+        if (f[k].nnz > 0 && f[k].grad_vals != nullptr)
+            SN_LAUNCH("psm_masked_dot_kernel", st, psm_masked_dot_kernel<<<(unsigned)(((size_t)f[k].nnz * 32 + 255) / 256), 256, 0, st>>>(
+                f[k].coo_row, f[k].coo_col, f[k].nnz, Lt, Ht, f[k].grad_vals, out_dim));
+        if (k > 0) {
+            float* Hn = Ht + (size_t)f[k].cols * out_dim;   // H_{k-1}^T = S_k H_k^T: [rows_k][out_dim]
+            SN_LAUNCH("psm_rowcomb_kernel", st, psm_rowcomb_kernel<<<f[k].rows, 256, 0, st>>>(f[k].csr_ptr, f[k].csr_idx, f[k].csr_src, f[k].vals, Ht, Hn, out_dim));
+            Ht = Hn;
+        }
     }
     return 0;
 }

@@ -70,6 +70,75 @@ def _pattern(p: torch.Tensor):
     return out
 
 
+def _dense_pattern(p: torch.Tensor):
+    """CSR / CSC / COO (int32) forms of a sparse-COO pattern for the dense-product path (csrc/psm.cu), built once on the host."""
+    idx = p._indices()
+    dev = idx.device
+    rows, cols = idx[0].cpu().numpy().astype(np.int64), idx[1].cpu().numpy().astype(np.int64)
+    nr, nc = p.shape
+    out = dict(key=(idx.data_ptr(), idx.shape[1], str(dev)))
+    for name, major, minor, n in (("csr", rows, cols, nr), ("csc", cols, rows, nc)):
+        order = np.argsort(major, kind="stable")
+        ptr = np.concatenate([[0], np.cumsum(np.bincount(major, minlength=n))]).astype(np.int32)
+        out[name + "_ptr"] = torch.from_numpy(ptr).to(dev)
+        out[name + "_idx"] = torch.from_numpy(minor[order].astype(np.int32)).to(dev)
+        out[name + "_src"] = torch.from_numpy(order.astype(np.int32)).to(dev)
+    out["coo_row"] = torch.from_numpy(rows.astype(np.int32)).to(dev)
+    out["coo_col"] = torch.from_numpy(cols.astype(np.int32)).to(dev)
+    return out
+
+
+def _dense_factor_array(patterns, params, gvals):
+    arr = (_lib.SnPsmDenseFactor * len(params))()
+    for k, (pat, p) in enumerate(zip(patterns, params)):
+        f = arr[k]
+        f.rows, f.cols, f.nnz = int(p.shape[0]), int(p.shape[1]), int(p._nnz())
+        for n in ("csr_ptr", "csr_idx", "csr_src", "csc_ptr", "csc_idx", "csc_src", "coo_row", "coo_col"):
+            setattr(f, n, pat[n].data_ptr())
+        f.vals = p._values().data_ptr()
+        f.grad_vals = gvals[k].data_ptr() if gvals is not None else None
+    return arr
+
+
+class _PSMDenseFunction(torch.autograd.Function):
+    """Large-batch path: the factors are multiplied out once per call, the batch goes through the tensor-core GEMMs."""
+
+    @staticmethod
+    def forward(ctx, U, bias, layer, *factors):
+        B = U.shape[0]
+        patterns = layer._dense_patterns(factors)
+        assert all(p._values().dtype == torch.float32 and p._values().is_contiguous() for p in factors)
+        arr = _dense_factor_array(patterns, factors, None)
+        L = _lib.lib()
+        prefix = torch.empty(L.sn_psm_dense_prefix_floats(arr, len(factors), layer.output_dim), dtype=torch.float32, device=U.device)
+        y = torch.empty((B, layer.output_dim), dtype=torch.float32, device=U.device)
+        rc = L.sn_psm_dense_forward(arr, len(factors), _lib.ptr(U), U.stride(0), _lib.ptr(y), y.stride(0), _lib.ptr(bias), _lib.ptr(prefix), B,
+                                    layer.input_dim, layer.output_dim, _lib.stream_ptr())
+        _lib.check(rc, "sn_psm_dense_forward")
+        ctx.layer, ctx.patterns, ctx.has_bias = layer, patterns, bias is not None
+        ctx.save_for_backward(U, prefix, *factors)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        U, prefix, *factors = ctx.saved_tensors
+        layer = ctx.layer
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("PSMLayer: gradient w.r.t. the input features is not implemented "
+                               "(the reference training loop never requests it, training_helpers.py:34)")
+        grad_y = grad_y.contiguous().float()
+        gvals = [torch.zeros(p._nnz(), dtype=torch.float32, device=U.device) for p in factors]
+        gbias = torch.zeros(layer.output_dim, dtype=torch.float32, device=U.device) if ctx.has_bias else None
+        arr = _dense_factor_array(ctx.patterns, factors, gvals)
+        L = _lib.lib()
+        work = torch.empty(L.sn_psm_dense_backward_floats(arr, len(factors), layer.output_dim), dtype=torch.float32, device=U.device)
+        rc = L.sn_psm_dense_backward(arr, len(factors), _lib.ptr(U), U.stride(0), _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(prefix),
+                                     _lib.ptr(work), _lib.ptr(gbias), U.shape[0], layer.input_dim, layer.output_dim, _lib.stream_ptr())
+        _lib.check(rc, "sn_psm_dense_backward")
+        gf = [torch.sparse_coo_tensor(p._indices(), g, p.shape) for p, g in zip(factors, gvals)]
+        return (None, gbias, None, *gf)
+
+
 def _factor_array(patterns, params, gvals):
     arr = (_lib.SnPsmFactor * len(params))()
     for k, (pat, p) in enumerate(zip(patterns, params)):
@@ -164,9 +233,37 @@ class PSMLayer(StructuredLayer):
             out.append(pat)
         return out
 
+    def _dense_patterns(self, factors):
+        cache = self.__dict__.setdefault("_dev_dense_patterns", {})
+        out = []
+        for k, p in enumerate(factors):
+            idx = p._indices()
+            key = (idx.data_ptr(), idx.shape[1], str(idx.device))
+            pat = cache.get(k)
+            if pat is None or pat["key"] != key:
+                pat = _dense_pattern(p)
+                cache[k] = pat
+            out.append(pat)
+        return out
+
+    def use_dense_path(self, batch: int) -> bool:
+        """The batch-independent product of the factors is multiplied out (dense-product path) when the batch is large enough to
+        amortise it; the sparse chain kernel (intermediates in shared memory) serves small batches and very wide factors.
+        SNB200_PSM_PATH=dense|sparse forces a path."""
+        import os
+        forced = os.environ.get("SNB200_PSM_PATH", "")
+        eligible = self.output_dim % 4 == 0 and max(max(p.shape) for p in self.sparse_matrices) <= 16384
+        if forced == "dense":
+            assert eligible, "PSMLayer: the dense-product path needs output_dim % 4 == 0 and factor dimensions <= 16384"
+            return True
+        if forced == "sparse":
+            return False
+        return eligible and batch >= 1024
+
     def __getstate__(self):
         state = self.__dict__.copy()
         state.pop("_dev_patterns", None)
+        state.pop("_dev_dense_patterns", None)
         return state
 
     def forward(self, U):
@@ -183,7 +280,8 @@ class PSMLayer(StructuredLayer):
                 with torch.no_grad():
                     p.data = p.detach().coalesce()
                 self._base_nnz[k] = int(p._nnz())
-        return _PSMFunction.apply(U, self.bias if self.use_bias else None, self, *self.sparse_matrices)
+        fn = _PSMDenseFunction if self.use_dense_path(U.shape[0]) else _PSMFunction
+        return fn.apply(U, self.bias if self.use_bias else None, self, *self.sparse_matrices)
 
     forward_sparse = forward   # the reference's alternative torch.sparse.mm path (psm_layer.py:36-45): same math
 

@@ -75,8 +75,11 @@ def test_psm_two_factors_matches_reference_fixture(built_lib):
     assert list(layer.state_dict().keys()) == ["bias", "sparse_matrices.0", "sparse_matrices.1"]
 
 
-def test_psm_three_factors_intended_order_and_sgd_step(built_lib):
-    """3 factors, rectangular -- compared with the corrected-order restatement."""
+@pytest.mark.parametrize("path", ["sparse", "dense"])
+def test_psm_three_factors_intended_order_and_sgd_step(built_lib, monkeypatch, path):
+    """3 factors, rectangular -- compared with the corrected-order restatement; both CUDA paths (sparse chain with
+    the intermediates in shared memory / batch-independent dense product on the tensor cores)."""
+    monkeypatch.setenv("SNB200_PSM_PATH", path)
     rng = np.random.default_rng(3003)
     i, o, B = 96, 40, 37
     mx = max(i, o)
@@ -101,6 +104,35 @@ def test_psm_three_factors_intended_order_and_sgd_step(built_lib):
         opt.zero_grad(); loss = (layer(Xd) - 1).square().mean(); loss.backward(); opt.step()
     assert float((layer(Xd) - 1).square().mean()) < before
     assert all(p._nnz() == s.nnz for p, s in zip(layer.sparse_matrices, S))
+
+
+def test_psm_dense_product_path_large_batch_vs_oracle(built_lib, monkeypatch):
+    """The path a large batch takes by default (B >= 1024): W^T multiplied out once, tensor-core GEMMs, gradient projected onto
+    every factor's pattern -- against the oracle, and against the sparse chain kernel on the same inputs."""
+    rng = np.random.default_rng(3004)
+    i, o, B, mx = 512, 200, 2048, 512
+    S = [scipy.sparse.random(o, mx, density=0.05, random_state=4, format="csr"), scipy.sparse.random(mx, mx, density=0.05, random_state=5, format="csr"),
+         scipy.sparse.random(mx, i, density=0.05, random_state=6, format="csr")]
+    X = rng.uniform(-1, 1, size=(B, i)).astype(np.float32); gy = rng.uniform(-1, 1, size=(B, o)).astype(np.float32) / B
+    ref = PSMLayer(i, o, sparse_matrices=S)
+    dense = [torch.tensor(s.toarray()).float().requires_grad_(True) for s in S]
+    b = ref.bias.detach().clone().requires_grad_(True)
+    yo = O.psm_forward(torch.tensor(X), dense, b); (yo * torch.tensor(gy)).sum().backward()
+    outs = {}
+    for path in ("dense", "sparse"):
+        monkeypatch.setenv("SNB200_PSM_PATH", path)
+        layer = PSMLayer(i, o, sparse_matrices=S, initial_bias=ref.bias.detach().numpy()).to(DEV)
+        assert layer.use_dense_path(B) == (path == "dense")
+        y = layer(torch.tensor(X, device=DEV)); (y * torch.tensor(gy, device=DEV)).sum().backward()
+        assert rel_err(y.detach().cpu().numpy(), yo.detach().numpy()) < RTOL
+        assert rel_err(layer.bias.grad.cpu().numpy(), b.grad.numpy()) < RTOL
+        for k, p in enumerate(layer.sparse_matrices):
+            assert p.grad.is_sparse and p.grad._nnz() == p._nnz()
+            assert rel_err(dense_grad(p), dense[k].grad.numpy() * (S[k].toarray() != 0)) < RTOL
+        outs[path] = y.detach().cpu().numpy()
+    monkeypatch.delenv("SNB200_PSM_PATH")
+    assert PSMLayer(i, o, sparse_matrices=S).use_dense_path(B) and not PSMLayer(i, o, sparse_matrices=S).use_dense_path(64)
+    assert rel_err(outs["dense"], outs["sparse"]) < RTOL
 
 
 def _hmat_from_fixture(z):
