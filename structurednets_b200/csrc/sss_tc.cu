@@ -2106,13 +2106,14 @@ bool use_fused_forward(const sn_sss_tc_plan* p, int64_t B) {
     return false;   // the three-kernel path with the four-threads-per-sample scans is faster at every batch size measured so far
 }
 
-// Chunk scans: the tensor-core chain kernels are bounded below by (2 x chunks) serial steps of ~3 us whatever the batch, the SIMT
-// four-threads-per-sample kernels scale with the batch (8 ns / sample); measured crossover ~48 k samples per GPU.
-// SNB200_SSS_TC_CHAIN=0/1 forces the choice (tests).
+// Chunk scans: the tensor-core chain kernels are bounded below by (2 x chunks) serial steps of ~1.5 us whatever the batch (forward
+// ~110 us, backward ~80 us with one CTA per SM), the SIMT four-threads-per-sample kernels scale with the batch (~18 ns / sample
+// for the three of them).  Measured (r1q): 12 288 samples 188 vs 230 us, 16 384: 192 vs 289 us, 32 768: 285 vs 534 us; about equal
+// at 8 192.  SNB200_SSS_TC_CHAIN=0/1 forces the choice (tests).
 bool use_tc_chain(int64_t B) {
     const char* e = getenv("SNB200_SSS_TC_CHAIN");
     if (e != nullptr && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
-    return B >= 49152;
+    return B >= 10240;
 }
 
 // SIMT scans: split by direction (+ a parallel output kernel) by default; SNB200_SSS_SPLIT_SCANS=0 keeps the single-kernel scans
