@@ -255,13 +255,24 @@ constexpr int G1_CONV = 256;                          // converter threads: two 
 constexpr int G1_THREADS = 64 + G1_CONV + 128;
 // Three rings of 16 KB tiles with their own depths: the x boxes come from HBM and need the most loads in flight, the W boxes are
 // L2 hits, the lo tiles only live between a converter group and the MMA.
-constexpr int G1_XS = 4, G1_WS = 4, G1_LS = 2;
+#ifndef SN_G1_XS
+#define SN_G1_XS 4
+#define SN_G1_WS 4
+#endif
+constexpr int G1_XS = SN_G1_XS, G1_WS = SN_G1_WS, G1_LS = 2;
 static_assert(G1_XS % G1_LS == 0 && G1_LS == 2, "a converter group (= lo slot) must own its x slots: it never skips a barrier phase");
 constexpr int G1_TILE_BYTES = 128 * 128;              // 128 rows x 128 B
 constexpr int G1_X_OFF = 0, G1_W_OFF = G1_XS * G1_TILE_BYTES, G1_L_OFF = G1_W_OFF + G1_WS * G1_TILE_BYTES;
 constexpr int G1_OUT_OFF = G1_L_OFF + G1_LS * G1_TILE_BYTES;   // output staging: Y [128][32] (SWIZZLE_128B) | R [128][16] | R' [128][16] (SWIZZLE_64B)
 constexpr int G1_BAR_OFF = G1_OUT_OFF + 2 * G1_TILE_BYTES;
-constexpr int G1_PF = 3;                             // L2 prefetch distance in work items
+#ifndef SN_G1_PF
+#define SN_G1_PF 0
+#endif
+constexpr int G1_PF = SN_G1_PF;                      // L2 prefetch distance in work items
+#ifndef SN_G1_PFG
+#define SN_G1_PFG 1
+#endif
+constexpr int G1_PFG = SN_G1_PFG;                    // work items per prefetch burst
 constexpr int G1_MAX_CHUNKS = 1024;
 constexpr size_t G1_SMEM = (size_t)G1_BAR_OFF + 1024 + 256 + G1_MAX_CHUNKS * 8;
 
@@ -316,11 +327,14 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
                 for (int kb = 0; kb < c.y; ++kb) tma_prefetch_l2_2d(&map_x, c.x + kb * KBW, ptile * 128);
                 if (++pch == nchunks) { pch = 0; ++ptile; }
             };
-            for (long w = w0; w < w0 + G1_PF && w < w1; ++w) prefetch_next();
+            // in groups of G1_PFG items, so that DRAM sees G1_PFG x 640 contiguous bytes of every sample row at a time
+            long pw = w0;
+            for (; pw < w0 + G1_PF + G1_PFG && pw < w1; ++pw) prefetch_next();
             uint32_t it = 0;
             int tile = tile0, ch = ch0;
             for (long w = w0; w < w1; ++w) {
-                if (w + G1_PF < w1) prefetch_next();
+                if (pw < w1 && pw - w <= G1_PF)
+                    for (int g = 0; g < G1_PFG && pw < w1; ++g, ++pw) prefetch_next();
                 const int nkb = ctab[ch].y, col0 = ctab[ch].x;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const uint32_t xs = it % G1_XS, xr = it / G1_XS, ws = it % G1_WS, wr = it / G1_WS;
@@ -1141,7 +1155,10 @@ sss_tc_scan_bwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
 //       rows n < 48: [Whi(n,:) | Whi(n,:)], rows 48 + n: [Wlo(n,:) | 0], W = [O ; Phi] (48 x 16)   -> D[:, n] + D[:, 48 + n]
 //    kind 2/3 = backward lambda/mu, three 32-row sub-tiles: state (Phi^T), grad_y hi part (O^T), grad_y lo part (O^T).
 // ------------------------------------------------------------------------------------------
-constexpr int CH_PF = 3;                         // L2 prefetch distance (steps) of the per-sample rows
+#ifndef SN_CH_PF
+#define SN_CH_PF 1
+#endif
+constexpr int CH_PF = SN_CH_PF;                  // L2 prefetch distance (steps) of the per-sample rows
 constexpr int CW_ROWS = 96;
 constexpr int CW_TILE_FLOATS = CW_ROWS * 32;    // 3072 floats = 12 KB
 constexpr int CW_TILE_BYTES = CW_TILE_FLOATS * 4;
@@ -1750,7 +1767,10 @@ constexpr int G2_BLK = G2_KS * 128;              // one 32-feature block: 4 KB
 constexpr int G2_A_BYTES = 4 * G2_BLK;           // 16 KB
 constexpr int G2_BH_BYTES = (KB_MAX + 1) * G2_BLK;   // 24 KB
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + 2 * G2_BH_BYTES;   // 64 KB
-constexpr int G2_PF = 6;                          // L2 prefetch distance in 32-sample steps
+#ifndef SN_G2_PF
+#define SN_G2_PF 2
+#endif
+constexpr int G2_PF = SN_G2_PF;                   // L2 prefetch distance in 32-sample steps
 constexpr size_t G2_SMEM = (size_t)G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
 
 __global__ void __launch_bounds__(G2_THREADS, 1)
