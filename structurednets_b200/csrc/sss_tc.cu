@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "umma.cuh"
+#include "util.cuh"
 
 namespace {
 
@@ -1542,7 +1543,7 @@ sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
     }
 }
 
-// backward: steps 0..nc-1 = lambda chain over chunks nc-1..0, steps nc..2nc-1 = mu chain over chunks 0..nc-1.
+// backward: the lambda chain over chunks nc-1..0 and the mu chain over chunks 0..nc-1, one per CTA (blockIdx.y).
 // L[j][row][0..15] = lambda_{j+1}, L[j][row][16..31] = mu_j ; grad_bias += column sums of grad_y (second chain, by the writer warps).
 // Ring slot of step t: coefficient tile of step t + the grad_y rows of step t + 1.  The chain is paced by the instruction stream of
 // the epilogue threads between two MMAs, so a sample row is shared by TWO threads (warps w and w + 4 read the same TMEM lanes):
@@ -1563,7 +1564,9 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
     using M = ChainMap<true>;
     const uint32_t sb = chain_base(smem_raw);
     const int warp = threadIdx.x >> 5;
-    const int nsteps = 2 * nchunks;
+    // grid.y = 2: one adjoint chain per CTA (0: lambda over chunks nc-1..0, 1: mu over chunks 0..nc-1); the two are independent
+    const int dir = blockIdx.y;
+    const int nsteps = nchunks;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init_s(sb + M::full + 8 * i, 1); mbar_init_s(sb + M::slot_free + 8 * i, CHB_EPI + 1 + CH_WRITERS); }
         mbar_init_s(sb + M::state_ready, CHB_EPI); mbar_init_s(sb + M::acc_full, 1); mbar_init_s(sb + M::chain_done, 1);
@@ -1577,7 +1580,7 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = lds32_u(sb + M::tmem_slot);
-    auto chunk_of = [&](int t) { return t < nchunks ? nchunks - 1 - t : t - nchunks; };
+    auto chunk_of = [&](int t) { return dir ? t : nchunks - 1 - t; };
 
     if (warp == 8) {
         if (elect_one()) {
@@ -1586,7 +1589,7 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
                 const uint32_t slot = sb + M::slot0 + s * M::slot_bytes, fullb = sb + M::full + 8 * s;
                 const bool has_next = t + 1 < nsteps;
                 mbar_expect_tx_s(fullb, CHB_W_BYTES + (has_next ? 16384 : 0));
-                tma_load_2d_s(slot, &map_cw, 0, (j * 4 + (t < nchunks ? 2 : 3)) * CW_ROWS, fullb);
+                tma_load_2d_s(slot, &map_cw, 0, (j * 4 + (dir ? 3 : 2)) * CW_ROWS, fullb);
                 if (has_next) tma_load_2d_s(slot + CHB_W_BYTES, &map_gy, chunks[chunk_of(t + 1)].row0, blockIdx.x * 128, fullb);
             };
             auto prefetch = [&](int t) { tma_prefetch_l2_2d(&map_gy, chunks[chunk_of(t)].row0, blockIdx.x * 128); };
@@ -1694,9 +1697,8 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
             tmem_ld8_nowait(tacc + 16 + 8 * h, l);
             tmem_ld_wait();
             tc_fence_before();
-            const bool last_of_chain = (t == nchunks - 1);
 #pragma unroll
-            for (int a = 0; a < 8; ++a) st[a] = last_of_chain ? 0.f : (__uint_as_float(m[a]) + __uint_as_float(l[a]));
+            for (int a = 0; a < 8; ++a) st[a] = __uint_as_float(m[a]) + __uint_as_float(l[a]);
             CHPROF_LAP(3);
             if (has_next) {
                 store_operands();
@@ -1721,11 +1723,13 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
             for (int k = 0; k < 8; ++k) {
                 const int i = k * CH_WRITERS + wt;
                 const long row = (long)blockIdx.x * 128 + (i >> 2);
-                if (row < B) *(reinterpret_cast<float4*>(L + ((size_t)j * B + row) * 32 + (t >= nchunks ? DS : 0)) + (i & 3)) = sv[k];
+                if (row < B) *(reinterpret_cast<float4*>(L + ((size_t)j * B + row) * 32 + (dir ? DS : 0)) + (i & 3)) = sv[k];
             }
             // the slot of step t holds the grad_y rows of step t + 1: thread = (column, half of the rows); rows past B are zero (TMA fill)
             mbar_wait_s(sb + M::full + 8 * s, (t >> 1) & 1);
-            if (gbias != nullptr && t + 1 >= nchunks && t + 1 < nsteps) {
+            // column sums: the mu CTA covers chunks 1..nc-1 (the rows its slots carry), the lambda CTA adds chunk 0 (its last step's rows);
+            // a single-chunk layer has no slot rows at all: the host sums that case
+            if (gbias != nullptr && t + 1 < nsteps && (dir == 1 || t + 2 == nsteps)) {
                 const uint32_t tile = sb + M::slot0 + s * M::slot_bytes + CHB_W_BYTES;
                 const int col = wt & 31, r0 = (wt >> 5) * 64;
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -2252,7 +2256,9 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
         if (int rc = make_map_f32(&mgy, grad_y, (uint64_t)p->output_dim, (uint64_t)B, (uint64_t)ldgy, 128)) return rc;
         if (int rc = make_map_f32(&mc, CW, 32, (uint64_t)p->nchunks * 4 * CW_ROWS, 32, 64)) return rc;   // state + grad_y sub-tiles only
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHB_SMEM));
-        SN_LAUNCH("sss_tc_chain_bwd_kernel", st, sss_tc_chain_bwd_kernel<<<(unsigned)((B + 127) / 128), CHB_THREADS, CHB_SMEM, st>>>(mc, mgy, p->chunks, p->nchunks, L, grad_bias, (long)B));
+        SN_LAUNCH("sss_tc_chain_bwd_kernel", st, sss_tc_chain_bwd_kernel<<<dim3((unsigned)((B + 127) / 128), 2), CHB_THREADS, CHB_SMEM, st>>>(mc, mgy, p->chunks, p->nchunks, L, grad_bias, (long)B));
+        if (p->nchunks == 1 && grad_bias != nullptr)
+            if (int rc = snb::colsum_accumulate(grad_y, ldgy, B, p->output_dim, grad_bias, st)) return rc;
     } else {
         const int qs_threads = B <= 16384 ? 64 : QS_THREADS;
         const unsigned ydim = use_split_scans(B) ? 2u : 1u;
