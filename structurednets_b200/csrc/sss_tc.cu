@@ -77,14 +77,15 @@ __device__ __forceinline__ void chunk_params_async(float* pbuf, StageP* ptrs, co
 }
 
 __device__ __forceinline__ float dot16(const float* __restrict__ row, const float (&v)[DS]) {   // row: 16 floats, 16-byte aligned, shared memory
+    // four partial sums (one per float4 lane): a single accumulator is a chain of 16 dependent FFMAs (64 cycles for 16 issue slots),
+    // and the build kernels run 1.5 warps per scheduler -- nothing else hides that latency
     const float4* r4 = reinterpret_cast<const float4*>(row);
-    float acc = 0.f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float4 m = r4[q];
-        acc = fmaf(m.x, v[4 * q], acc); acc = fmaf(m.y, v[4 * q + 1], acc); acc = fmaf(m.z, v[4 * q + 2], acc); acc = fmaf(m.w, v[4 * q + 3], acc);
-    }
-    return acc;
+    const float4 m0 = r4[0], m1 = r4[1], m2 = r4[2], m3 = r4[3];
+    float a0 = m0.x * v[0], a1 = m0.y * v[1], a2 = m0.z * v[2], a3 = m0.w * v[3];
+    a0 = fmaf(m1.x, v[4], a0); a1 = fmaf(m1.y, v[5], a1); a2 = fmaf(m1.z, v[6], a2); a3 = fmaf(m1.w, v[7], a3);
+    a0 = fmaf(m2.x, v[8], a0); a1 = fmaf(m2.y, v[9], a1); a2 = fmaf(m2.z, v[10], a2); a3 = fmaf(m2.w, v[11], a3);
+    a0 = fmaf(m3.x, v[12], a0); a1 = fmaf(m3.y, v[13], a1); a2 = fmaf(m3.z, v[14], a2); a3 = fmaf(m3.w, v[15], a3);
+    return (a0 + a1) + (a2 + a3);
 }
 __device__ __forceinline__ void axpy_row16(const float* __restrict__ row, float w, float (&out)[DS]) {   // out[a] += row[a] * w
     const float4* r4 = reinterpret_cast<const float4*>(row);
