@@ -57,9 +57,9 @@ class SSSWorkload:
     flop_per_sample = 2277504
     bound = "hbm"
     # dram__bytes_read.sum + dram__bytes_write.sum per launch at local batch 65 536, from the `ncu --set full` capture
-    # profiles/r1p_sss_tc_top_kernels.md (cold-cache replays of the same bench command)
-    traffic_bytes = {"sss_tc_local_gemm_kernel": 1.3121e9 + 0.5069e9, "sss_tc_chain_fwd_kernel": 0.8983e9 + 0.7659e9,
-                     "sss_tc_chain_bwd_kernel": 0.4709e9 + 0.2513e9, "sss_tc_grad_gemm_kernel": 1.9837e9 + 0.0067e9}
+    # profiles/r1q_sss_tc_top_kernels.md (cold-cache replays of the same bench command, final kernels of round 1)
+    traffic_bytes = {"sss_tc_local_gemm_kernel": 1.0775e9 + 0.5094e9, "sss_tc_chain_fwd_kernel": 0.7607e9 + 0.7648e9,
+                     "sss_tc_chain_bwd_kernel": 0.5354e9 + 0.2493e9, "sss_tc_grad_gemm_kernel": 1.9521e9 + 0.0074e9}
 
     def describe(self):
         return dict(workload="C5: SSS 4096->1000, 500 stages, statespace 16, fp32 fwd+bwd (param grads), global batch 65536",

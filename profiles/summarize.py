@@ -25,22 +25,28 @@ def launches(path):
     rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
     hdr = rows[0]
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
-    agg, order, total = {}, [], 0.0
+    mi = hdr.index("Metric Name")
+    agg, order, total, nl = {}, [], 0.0, 0
     for r in rows[1:]:
         name = r[ki].split("(")[0].replace("<unnamed>::", "")[:90]
         v = float(r[vi].replace(",", ""))
-        v = v / 1e3 if r[ui] in ("ns", "nsecond") else (v * 1e3 if r[ui] in ("ms", "msecond") else v)   # -> us
         if name not in agg:
-            agg[name] = [0, 0.0]
+            agg[name] = [0, 0.0, 0.0]
             order.append(name)
-        agg[name][0] += 1
-        agg[name][1] += v
-        total += v
-    print("| kernel | launches | total us | share | avg us |\n|---|---:|---:|---:|---:|")
+        if r[mi] == "gpu__time_duration.sum":
+            v = v / 1e3 if r[ui] in ("ns", "nsecond") else (v * 1e3 if r[ui] in ("ms", "msecond") else v)   # -> us
+            agg[name][0] += 1
+            agg[name][1] += v
+            total += v
+            nl += 1
+        elif r[mi].startswith("dram__bytes"):
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[ui], 1.0)
+            agg[name][2] += v * scale
+    print("| kernel | launches | total us | share | avg us | avg DRAM MB (read + write) |\n|---|---:|---:|---:|---:|---:|")
     for name in sorted(order, key=lambda n: -agg[n][1]):
-        c, t = agg[name]
-        print(f"| `{name}` | {c} | {t:.1f} | {100 * t / total:.1f}% | {t / c:.1f} |")
-    print(f"\ntotal {total:.1f} us over {len(rows) - 1} launches (ncu --metrics gpu__time_duration.sum --clock-control none: cold-cache, serialised)")
+        c, t, b = agg[name]
+        print(f"| `{name}` | {c} | {t:.1f} | {100 * t / total:.1f}% | {t / c:.1f} | {b / c / 1e6:.1f} |")
+    print(f"\ntotal {total:.1f} us over {nl} launches (ncu --metrics gpu__time_duration.sum[,dram__bytes_*] --clock-control none: cold-cache, serialised)")
 
 
 def report(path):
