@@ -185,3 +185,134 @@ def train(model, X_train, y_train, X_val=None, y_val=None, patience=10, batch_si
     model_to_return = best_model if restore_best_model else model
     return (model_to_return, start_train_loss, start_train_accuracy, start_val_loss, start_val_accuracy, train_loss_history,
             train_accuracy_history, val_loss_history, val_accuracy_history)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Device-resident training loop.  Same signature, same 9-tuple, same early stopping and the same
+# batch order as ``train`` for a given numpy seed -- but the features are uploaded ONCE (pinned, asynchronous), every epoch's
+# shuffle is an index permutation gathered on the device, and loss / accuracy are accumulated in device tensors: one host
+# synchronisation per evaluation pass instead of one per batch (reference training_helpers.py:17,24,31-40,147-153).
+# ----------------------------------------------------------------------------------------------------------------------
+def _to_device_once(a: np.ndarray, device):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if torch.device(device).type == "cuda":
+        return t.pin_memory().to(device, non_blocking=True)
+    return t.to(device)
+
+
+def _evaluate_resident(model, Xd: torch.Tensor, yd: torch.Tensor, loss_function, batch_size: int):
+    """``get_loss_and_accuracy_for_model`` (:57-73) on resident tensors: the float32 batch losses are summed in the same order,
+    the division by the (numpy int) batch count happens on the host like in the reference, so the returned values are identical."""
+    n = Xd.shape[0]
+    nb_batches = np.ceil(n / batch_size).astype("int")
+    cumulated_loss, nb_correct = None, None
+    one_hot = yd.dim() == 2 and yd.shape[1] > 1
+    with torch.no_grad():
+        for batch_i in range(nb_batches):
+            lo, hi = int(batch_i * batch_size), min(int((batch_i + 1) * batch_size), n)
+            y_pred = model(Xd[lo:hi])
+            loss = loss_function(y_pred, target=yd[lo:hi]).detach()
+            target = yd[lo:hi].argmax(axis=1) if one_hot else yd[lo:hi]
+            correct = torch.sum(y_pred.argmax(axis=1) == target)
+            cumulated_loss = loss if cumulated_loss is None else cumulated_loss + loss
+            nb_correct = correct if nb_correct is None else nb_correct + correct
+    loss = (0 + cumulated_loss.cpu().numpy()) / nb_batches          # one synchronisation for the whole pass
+    accuracy = (nb_correct / len(yd)).cpu().detach().numpy()
+    return loss, accuracy
+
+
+class FlatSGD:
+    """Plain SGD over a layer's flat parameter / gradient buffers: one fused kernel instead of one update per parameter tensor (the
+    SSS layer has 3 501).  Loose parameters (sparse / float64 ones that do not live in the flat buffer) keep torch's SGD, so the
+    reference's "sparse parameters: SGD only" rule (psm_layer.py:14-15) is unchanged.  Pass as ``optimizer_class=FlatSGD.for_model(model)``."""
+
+    def __init__(self, model, params, lr):
+        self.lr = lr
+        self.flat_p = model.flat_parameters() if hasattr(model, "flat_parameters") else None
+        self.flat_g = model.flat_grad() if hasattr(model, "flat_grad") else None
+        self.model = model
+        flat_ptr = (self.flat_p.data_ptr(), self.flat_p.data_ptr() + self.flat_p.numel() * 4) if self.flat_p is not None else (0, 0)
+        loose = [p for p in params if p.is_sparse or not (flat_ptr[0] <= p.data_ptr() < flat_ptr[1])]
+        self.loose = torch.optim.SGD(loose, lr=lr) if loose else None
+
+    @classmethod
+    def for_model(cls, model):
+        return lambda params, lr: cls(model, list(params), lr)
+
+    def zero_grad(self, set_to_none=True):
+        if self.flat_g is not None:
+            self.model.zero_flat_grad()
+        if self.loose is not None:
+            self.loose.zero_grad(set_to_none=set_to_none)
+
+    def step(self):
+        if self.flat_p is not None:
+            with torch.no_grad():
+                self.flat_p.add_(self.flat_g, alpha=-self.lr)
+        if self.loose is not None:
+            self.loose.step()
+
+
+def train_resident(model, X_train, y_train, X_val=None, y_val=None, patience=10, batch_size=1000, verbose=False, lr=1e-6,
+                   restore_best_model=True, loss_function_class=torch.nn.CrossEntropyLoss, min_patience_improvement=1e-10,
+                   optimizer_class=torch.optim.Adam, use_gpu=False, grad_sync=None):
+    """Drop-in for ``train`` with the data resident on the device.  Consumes the numpy RNG exactly like ``train`` (one
+    ``sklearn.utils.shuffle`` per epoch), so both loops see the same batches for the same seed."""
+    if X_val is None or y_val is None:
+        X_train, X_val, y_train, y_val = train_test_split(X_train, y_train, test_size=0.2)
+    device = get_device(use_gpu=use_gpu)
+    Xd, yd = _to_device_once(X_train, device), _to_device_once(y_train, device)
+    Xv, yv = _to_device_once(X_val, device), _to_device_once(y_val, device)
+
+    optimizer = optimizer_class(model.parameters(), lr=lr)
+    loss_function = loss_function_class()
+    n = Xd.shape[0]
+    nb_batches_per_epoch = np.ceil(n / batch_size).astype("int")
+    evaluate = lambda X, y: _evaluate_resident(model, X, y, loss_function, batch_size)
+    start_train_loss, start_train_accuracy = evaluate(Xd, yd)
+    start_val_loss, start_val_accuracy = evaluate(Xv, yv)
+    if verbose:
+        print("------ Training Start -------")
+        print("Start Train Loss: " + str(start_train_loss))
+        print("Start Val Loss: " + str(start_val_loss))
+
+    train_loss_history, train_accuracy_history, val_loss_history, val_accuracy_history = [], [], [], []
+    best_val_loss = start_val_loss
+    best_model = pickle.loads(pickle.dumps(model))
+    continue_training = True
+    epoch = 1
+    index = np.arange(n)
+    while continue_training:
+        perm = _to_device_once(shuffle(index), device)          # same RNG consumption as shuffle(X_train, y_train) in train()
+        for batch_i in range(nb_batches_per_epoch):
+            sel = perm[int(batch_i * batch_size):min(int((batch_i + 1) * batch_size), n)]
+            outputs_train = model(Xd.index_select(0, sel))
+            loss_train = loss_function(outputs_train, target=yd.index_select(0, sel))
+            optimizer.zero_grad()
+            loss_train.backward()
+            if grad_sync is not None:
+                grad_sync()
+            optimizer.step()
+
+        train_loss, train_accuracy = evaluate(Xd, yd)
+        train_loss_history.append(train_loss)
+        train_accuracy_history.append(train_accuracy)
+        val_loss_history.append(train_loss)          # sic: the reference's "validation" pass runs on the training set (:151);
+        val_accuracy_history.append(train_accuracy)  # it is the same deterministic forward pass, so it is not repeated
+        if verbose:
+            print("--- Epoch " + str(epoch) + " ---")
+            print("Train Acc: " + str(train_accuracy_history[-1]))
+            print("Train Loss: " + str(train_loss_history[-1]))
+
+        if len(val_loss_history) > patience \
+                and (np.min(val_loss_history[-patience:]) >= np.min(val_loss_history[:-patience]) - min_patience_improvement
+                     or math.isnan(val_loss_history[-1])):
+            continue_training = False
+        if val_loss_history[-1] < best_val_loss:
+            best_val_loss = val_loss_history[-1]
+            best_model = pickle.loads(pickle.dumps(model))
+        epoch += 1
+
+    model_to_return = best_model if restore_best_model else model
+    return (model_to_return, start_train_loss, start_train_accuracy, start_val_loss, start_val_accuracy, train_loss_history,
+            train_accuracy_history, val_loss_history, val_accuracy_history)

@@ -75,3 +75,56 @@ def test_train_improvement_all_layers(built_lib):
                                loss_function_class=torch.nn.MSELoss, min_patience_improvement=1e6, optimizer_class=torch.optim.SGD, use_gpu=True)
         after = float((trained(Xt).detach() - 1).abs().max())
         assert after < before, type(layer).__name__ + " failed to improve the error"
+
+
+def test_train_resident_matches_train_exactly_on_cpu():
+    """Device-resident loop: same RNG consumption, same batches, same float32 accumulation order -> the same
+    9-tuple as the reference-shaped loop, bit for bit on a deterministic (CPU) module."""
+    X, y = toy(n=230)
+    Xv, yv = toy(n=50, seed=3)
+    outs = []
+    for fn in (TH.train, TH.train_resident):
+        torch.manual_seed(1)
+        np.random.seed(7)
+        model = torch.nn.Linear(12, 5)
+        outs.append(fn(model, X, y, X_val=Xv, y_val=yv, patience=2, batch_size=64, lr=5e-2, min_patience_improvement=1e-3,
+                       optimizer_class=torch.optim.SGD))
+    a, b = outs
+    assert len(b) == 9 and len(a[5]) == len(b[5]) >= 3
+    for i in range(1, 9):
+        np.testing.assert_array_equal(np.asarray(a[i]), np.asarray(b[i]))
+        assert np.asarray(a[i]).dtype == np.asarray(b[i]).dtype
+    for pa, pb in zip(a[0].parameters(), b[0].parameters()):
+        assert torch.equal(pa, pb)
+
+
+def test_train_resident_one_hot_mse_targets():
+    X, y = toy(n=120)
+    Y = np.eye(5, dtype=np.float32)[y]
+    np.random.seed(0)
+    res = TH.train_resident(torch.nn.Linear(12, 5), X, Y, patience=1, batch_size=50, lr=1e-2, loss_function_class=torch.nn.MSELoss,
+                            min_patience_improvement=1e6, optimizer_class=torch.optim.SGD)
+    assert len(res) == 9 and len(res[5]) == 2 and res[5][-1] < res[1]
+
+
+@pytest.mark.gpu
+def test_train_resident_on_the_cuda_layers_with_flat_sgd(built_lib):
+    """train() vs train_resident() with the fused flat-buffer SGD on an SSS layer (3 501 parameter tensors -> one update kernel)."""
+    from structurednets_b200.layers.sss_layer import SSSLayer
+    from structurednets_b200.synth import random_mixed_system
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-1, 1, size=(600, 128)).astype(np.float32)
+    y = rng.integers(0, 24, size=600).astype(np.int64)
+    hist = []
+    for fn, flat in ((TH.train, False), (TH.train_resident, True)):
+        np.random.seed(11)
+        layer = SSSLayer(128, 24, 0.9, nb_states=12, initial_system_approx=random_mixed_system(128, 24, 12, 16, seed=11)).to("cuda")
+        opt = TH.FlatSGD.for_model(layer) if flat else torch.optim.SGD
+        res = fn(layer, X, y, X_val=X[:100], y_val=y[:100], patience=1, batch_size=200, lr=1e-1, restore_best_model=False,
+                 min_patience_improvement=1e6, optimizer_class=opt, use_gpu=True)
+        hist.append(res)
+    a, b = hist
+    assert len(a[5]) == len(b[5]) == 2
+    np.testing.assert_allclose(np.asarray(a[5], dtype=np.float64), np.asarray(b[5], dtype=np.float64), rtol=1e-5)
+    np.testing.assert_allclose(np.asarray(a[1], dtype=np.float64), np.asarray(b[1], dtype=np.float64), rtol=1e-6)
+    assert b[5][-1] < b[1]
