@@ -14,4 +14,10 @@ oracle is pinned against outputs of the *unmodified reference modules* imported 
 the build container (``oracle/ref_import.py`` + ``tests/golden/make_golden.py``);
 the resulting fixtures are committed under ``tests/golden/`` and checked by
 ``tests/test_oracle_golden.py``.
+
+Second, torch-independent pin for the SSS forward: the reference's own C program
+``speed_comparison/run.c`` is compiled unmodified from where it lies into
+``oracle/_ref/run`` (``oracle/run_c.py``, ``oracle/Makefile``; git-ignored) and must accept
+the oracle's output -- and the CUDA kernels' -- as its "checksum" vector
+(``tests/test_run_c_reference.py``).
 """
