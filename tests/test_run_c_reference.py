@@ -60,3 +60,42 @@ def test_reference_c_program_accepts_the_cuda_forward(case, path, built_lib, mon
     y = layer(torch.tensor(X, device="cuda")).detach().cpu().numpy()[17]
     ok, out = run_c.run_reference_check(*params, bias, u, y)
     assert ok, out
+
+
+def test_layer_description_round_trip_through_the_parser(tmp_path):
+    """structurednets_b200.speed_comparison.run reads what prepare_run.py writes (same text format as oracle/run_c.py emits)."""
+    from structurednets_b200.speed_comparison.run import parse_layer_description, sss_layer_from_description
+    layer, u = _layer(CASES[0])
+    lists = _lists(layer)
+    y = np.arange(CASES[0]["o"], dtype=np.float32)
+    p = str(tmp_path / "layer_description.txt")
+    run_c.write_layer_description(p, *lists, layer.bias.detach().numpy(), u, y)
+    d = parse_layer_description(p)
+    assert d["input_size"] == 76 and d["output_size"] == 14 and d["nb_states"] == 7
+    np.testing.assert_allclose(d["checksum_inp"].reshape(-1), u.reshape(-1), rtol=1e-7)
+    np.testing.assert_allclose(d["sss_checksum_out"].reshape(-1), y)
+    rebuilt = sss_layer_from_description(d)
+    for name, mats in zip("ABCDEFG", lists):
+        for a, b in zip(getattr(rebuilt, name), mats):
+            np.testing.assert_allclose(a.detach().numpy(), b, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(rebuilt.bias.detach().numpy(), layer.bias.detach().numpy(), rtol=1e-6)
+
+
+@pytest.mark.gpu
+def test_batched_run_tool_checks_like_run_c(tmp_path, built_lib, capsys):
+    """The B200 counterpart of run.c: same file, same checksum protocol, batches 1 and 300; a wrong checksum fails with run.c's message."""
+    from structurednets_b200.speed_comparison.run import run
+    layer, u = _layer(CASES[2])
+    lists = [[p.detach() for p in getattr(layer, n)] for n in "ABCDEFG"]
+    y = O.sss_forward(torch.tensor(u), *lists, layer.bias.detach(), layer.dims_in, layer.dims_out).numpy().reshape(-1)
+    p = str(tmp_path / "layer_description.txt")
+    rng = np.random.default_rng(1)
+    W = rng.uniform(-1, 1, size=(CASES[2]["o"], CASES[2]["i"])).astype(np.float32)
+    run_c.write_layer_description(p, *_lists(layer), layer.bias.detach().numpy(), u, y, W=W, standard_bias=np.ones(CASES[2]["o"], dtype=np.float32))
+    assert run(p, batches=(1, 300), iterations=3) == 0
+    out = capsys.readouterr().out
+    assert out.count("dense_time:") == 2 and out.count("sss_time:") == 2 and "ERROR" not in out
+    y[5] += 0.01
+    run_c.write_layer_description(p, *_lists(layer), layer.bias.detach().numpy(), u, y, W=W, standard_bias=np.ones(CASES[2]["o"], dtype=np.float32))
+    assert run(p, batches=(1,), iterations=1) == 1
+    assert "ERROR: Checksum mismatch for the SSS layer in dimension 5" in capsys.readouterr().out
