@@ -5,8 +5,8 @@ on BASELINE config C1: SSSLayer 4096 -> 1000, 500 stages, statespace 16, batch 2
 
     python scripts/train_loop_bench.py [--samples 8192] [--batch 256]
 
-Prints one JSON line: wall seconds of the whole call (2 start evaluations + 2 epochs, each epoch = training pass + evaluation
-pass(es)) and training samples per second."""
+Prints one JSON line: wall seconds of whole calls with 2, 6 and 10 epochs (2 start evaluations + epochs, each epoch = training pass +
+evaluation pass(es)), the steady-state seconds per epoch from the difference of the last two and the training samples per second it implies."""
 import argparse
 import json
 import os
@@ -33,23 +33,29 @@ def main():
     Xv, yv = X[:1024], y[:1024]
     sysm = random_mixed_system(4096, 1000, 500, 16, seed=5000)
     out = {}
-    for name, fn, flat in (("train", TH.train, False), ("train_resident", TH.train_resident, False),
-                           ("train_resident_flat_sgd", TH.train_resident, True)):
+    for name, fn, flat, graph in (("train", TH.train, False, False), ("train_resident", TH.train_resident, False, False),
+                                  ("train_resident_flat_sgd", TH.train_resident, True, False),
+                                  ("train_resident_flat_sgd_cuda_graph", TH.train_resident, True, True)):
         layer = SSSLayer(4096, 1000, 0.105, nb_states=500, initial_system_approx=sysm).to("cuda")
         opt = TH.FlatSGD.for_model(layer) if flat else torch.optim.SGD
         kw = dict(X_val=Xv, y_val=yv, patience=1, batch_size=args.batch, lr=1e-3, restore_best_model=False, min_patience_improvement=1e6,
                   optimizer_class=opt, use_gpu=True)
+        if graph:
+            kw["cuda_graph"] = True
         np.random.seed(0)
         fn(layer, X[:2 * args.batch], y[:2 * args.batch], **kw)     # warm-up (plans, allocator)
         torch.cuda.synchronize()
-        np.random.seed(0)
-        t0 = time.perf_counter()
-        res = fn(layer, X, y, **kw)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        epochs = len(res[5])
-        out[name] = dict(seconds=round(dt, 4), epochs=epochs, train_samples_per_s=round(epochs * args.samples / dt, 1),
-                         final_train_loss=float(res[5][-1]))
+        times = {}
+        for pat in (1, 5, 9):        # 2, 6 and 10 epochs: the difference of the last two is 4 steady-state epochs (training + evaluation)
+            kw["patience"] = pat
+            np.random.seed(0)
+            t0 = time.perf_counter()
+            res = fn(layer, X, y, **kw)
+            torch.cuda.synchronize()
+            times[pat] = (time.perf_counter() - t0, len(res[5]))
+        per_epoch = (times[9][0] - times[5][0]) / (times[9][1] - times[5][1])
+        out[name] = dict(seconds_2_epochs=round(times[1][0], 4), seconds_6_epochs=round(times[5][0], 4), seconds_10_epochs=round(times[9][0], 4), seconds_per_epoch=round(per_epoch, 4),
+                         train_samples_per_s=round(args.samples / per_epoch, 1), final_train_loss=float(res[5][-1]))
     out["config"] = dict(workload="C1: SSS 4096->1000, 500 stages, d=16, fp32, batch %d, %d host samples" % (args.batch, args.samples))
     print(json.dumps(out))
 

@@ -1277,6 +1277,14 @@ __device__ __forceinline__ void mbar_init_s(uint32_t bar, uint32_t count) { asm 
 __device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Releasing a buffer to the async proxy (a TMA refill) after reading it with ld.shared: the arrive must not be performed before the
+// loads have RETURNED.  An mbarrier.arrive issued right behind the ld.shared instructions was measured to overtake them about once in
+// eight forward passes (scripts/stress_states.py: a few rows of the saved states then held the NEXT step's TMA data), so the arrive
+// takes one register of every outstanding 16-byte load as a (otherwise unused) operand, or is placed behind the instructions that
+// consume the loaded values.
+__device__ __forceinline__ void mbar_arrive_after_s(uint32_t bar, float a, float b, float c, float d) {
+    asm volatile("{\n.reg .f32 dep;\nadd.f32 dep, %1, %2;\nadd.f32 dep, dep, %3;\nadd.f32 dep, dep, %4;\nmbarrier.arrive.shared::cta.b64 _, [%0];\n}" ::"r"(bar), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_s(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -1500,7 +1508,6 @@ sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
             for (int k = 0; k < 8; ++k) { const int i = k * CH_WRITERS + wt; sv[k] = read_chunk64_s(slot + CW_TILE_BYTES, i >> 2, i & 3); }
 #pragma unroll
             for (int k = 0; k < 16; ++k) { const int i = k * CH_WRITERS + wt; yv[k] = read_chunk128_s(slot + CW_TILE_BYTES + 8192, i >> 3, i & 7); }
-            mbar_arrive_s(sb + M::slot_free + 8 * s);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int i = k * CH_WRITERS + wt;
@@ -1529,6 +1536,8 @@ sss_tc_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
                     }
                 }
             }
+            // release the slot only now: the stores above have consumed every loaded value (see mbar_arrive_after_s)
+            mbar_arrive_after_s(sb + M::slot_free + 8 * s, sv[0].x, sv[7].x, yv[0].x, yv[15].x);
             if (t == nchunks - 1) {
                 asm volatile("fence.proxy.async;" ::: "memory");   // ytmp stores -> visible to the TMA reads of the second chain
                 __threadfence();
@@ -1688,7 +1697,7 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
             // next step's grad_y half row and its lo part, while this step's MMA runs
             mbar_wait_s(sb + M::full + 8 * s, (t >> 1) & 1);
             if (has_next) load_g(sb + M::slot0 + s * M::slot_bytes + CHB_W_BYTES);
-            mbar_arrive_s(sb + M::slot_free + 8 * s);
+            mbar_arrive_after_s(sb + M::slot_free + 8 * s, g[0], g[4], g[8], g[12]);   // only once the four 16-byte loads have returned
             CHPROF_LAP(1);
             mbar_wait_s(sb + M::acc_full, t & 1);
             CHPROF_LAP(2);
@@ -1719,13 +1728,13 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
             float4 sv[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) { const int i = k * CH_WRITERS + wt; sv[k] = read_chunk64_s(sb + M::lstage, i >> 2, i & 3); }
-            mbar_arrive_s(sb + M::lst_free);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int i = k * CH_WRITERS + wt;
                 const long row = (long)blockIdx.x * 128 + (i >> 2);
                 if (row < B) *(reinterpret_cast<float4*>(L + ((size_t)j * B + row) * 32 + (dir ? DS : 0)) + (i & 3)) = sv[k];
             }
+            mbar_arrive_after_s(sb + M::lst_free, sv[0].x, sv[2].x, sv[5].x, sv[7].x);   // the staging tile is rewritten by generic stores, but keep one rule
             // the slot of step t holds the grad_y rows of step t + 1: thread = (column, half of the rows); rows past B are zero (TMA fill)
             mbar_wait_s(sb + M::full + 8 * s, (t >> 1) & 1);
             // column sums: the mu CTA covers chunks 1..nc-1 (the rows its slots carry), the lambda CTA adds chunk 0 (its last step's rows);
@@ -1742,7 +1751,7 @@ sss_tc_chain_bwd_kernel(const __grid_constant__ CUtensorMap map_cw, const __grid
                     a2 += lds32(tile + (row + 2) * 128 + (((col >> 2) ^ ((row + 2) & 7)) << 4) + (col & 3) * 4);
                     a3 += lds32(tile + (row + 3) * 128 + (((col >> 2) ^ ((row + 3) & 7)) << 4) + (col & 3) * 4);
                 }
-                mbar_arrive_s(sb + M::slot_free + 8 * s);
+                mbar_arrive_after_s(sb + M::slot_free + 8 * s, a0, a1, a2, a3);          // the sums depend on every load
                 const sn_sss_tc_chunk c = chunks[chunk_of(t + 1)];
                 if (col < c.nrows) atomicAdd(gbias + c.row0 + col, (a0 + a1) + (a2 + a3));
             } else {

@@ -116,15 +116,17 @@ def test_train_resident_on_the_cuda_layers_with_flat_sgd(built_lib):
     X = rng.uniform(-1, 1, size=(600, 128)).astype(np.float32)
     y = rng.integers(0, 24, size=600).astype(np.int64)
     hist = []
-    for fn, flat in ((TH.train, False), (TH.train_resident, True)):
+    for fn, flat, graph in ((TH.train, False, False), (TH.train_resident, True, False), (TH.train_resident, True, True)):
         np.random.seed(11)
         layer = SSSLayer(128, 24, 0.9, nb_states=12, initial_system_approx=random_mixed_system(128, 24, 12, 16, seed=11)).to("cuda")
         opt = TH.FlatSGD.for_model(layer) if flat else torch.optim.SGD
+        extra = dict(cuda_graph=True) if graph else {}
         res = fn(layer, X, y, X_val=X[:100], y_val=y[:100], patience=1, batch_size=200, lr=1e-1, restore_best_model=False,
-                 min_patience_improvement=1e6, optimizer_class=opt, use_gpu=True)
+                 min_patience_improvement=1e6, optimizer_class=opt, use_gpu=True, **extra)
         hist.append(res)
-    a, b = hist
-    assert len(a[5]) == len(b[5]) == 2
-    np.testing.assert_allclose(np.asarray(a[5], dtype=np.float64), np.asarray(b[5], dtype=np.float64), rtol=1e-5)
-    np.testing.assert_allclose(np.asarray(a[1], dtype=np.float64), np.asarray(b[1], dtype=np.float64), rtol=1e-6)
-    assert b[5][-1] < b[1]
+    a = hist[0]
+    for b in hist[1:]:     # eager resident loop, then the CUDA-graph replayed step: same losses as train()
+        assert len(a[5]) == len(b[5]) == 2
+        np.testing.assert_allclose(np.asarray(a[5], dtype=np.float64), np.asarray(b[5], dtype=np.float64), rtol=1e-5)
+        np.testing.assert_allclose(np.asarray(a[1], dtype=np.float64), np.asarray(b[1], dtype=np.float64), rtol=1e-6)
+        assert b[5][-1] < b[1]
