@@ -232,7 +232,7 @@ class FlatSGD:
         self.flat_g = model.flat_grad() if hasattr(model, "flat_grad") else None
         self.model = model
         flat_ptr = (self.flat_p.data_ptr(), self.flat_p.data_ptr() + self.flat_p.numel() * 4) if self.flat_p is not None else (0, 0)
-        loose = [p for p in params if p.is_sparse or not (flat_ptr[0] <= p.data_ptr() < flat_ptr[1])]
+        loose = [p for p in params if p.is_sparse or (p.numel() > 0 and not (flat_ptr[0] <= p.data_ptr() < flat_ptr[1]))]   # empty boundary blocks: nothing to update
         self.loose = torch.optim.SGD(loose, lr=lr) if loose else None
 
     @classmethod

@@ -130,3 +130,26 @@ def test_train_resident_on_the_cuda_layers_with_flat_sgd(built_lib):
         np.testing.assert_allclose(np.asarray(a[5], dtype=np.float64), np.asarray(b[5], dtype=np.float64), rtol=1e-5)
         np.testing.assert_allclose(np.asarray(a[1], dtype=np.float64), np.asarray(b[1], dtype=np.float64), rtol=1e-6)
         assert b[5][-1] < b[1]
+
+
+def test_flat_sgd_equals_torch_sgd_on_the_flat_buffer():
+    """FlatSGD (one update over the layer's flat parameter buffer) against torch.optim.SGD over the 3n+1 parameter views (host logic:
+    no kernels run, the gradients are synthetic)."""
+    from structurednets_b200.layers.sss_layer import SSSLayer
+    from structurednets_b200.synth import random_mixed_system
+    layers = [SSSLayer(64, 16, 0.9, nb_states=4, initial_bias=np.linspace(-1, 1, 16), initial_system_approx=random_mixed_system(64, 16, 4, 8, seed=2))
+              for _ in range(2)]
+    opts = [TH.FlatSGD.for_model(layers[0])(layers[0].parameters(), 0.25), torch.optim.SGD(layers[1].parameters(), lr=0.25)]
+    g = torch.Generator().manual_seed(0)
+    for layer, opt in zip(layers, opts):
+        layer._ensure_flat()
+        opt.zero_grad()
+    noise = torch.randn(layers[0].flat_parameters().numel(), generator=g)
+    for layer in layers:
+        layer._prepare_grad_accumulation().copy_(noise)
+    for opt in opts:
+        opt.step()
+    assert opts[0].loose is None
+    assert torch.equal(layers[0].flat_parameters(), layers[1].flat_parameters())
+    for a, b in zip(layers[0].parameters(), layers[1].parameters()):
+        assert torch.equal(a, b)
