@@ -60,17 +60,17 @@ def standard_dims_in_dims_out_computation(input_size: int, output_size: int, nb_
 
 
 def _identify_system(T_full: np.ndarray, dims_in, dims_out, statespace_dim: int):
-    """tvsclib path of the reference constructor (layers/sss_layer.py:66-68); tvsclib is a git-only,
-    unpinned dependency (reference setup.py:33)."""
+    """The state-space realisation of a dense matrix: tvsclib's Hankel-SVD identification when it is installed (the reference
+    constructor, layers/sss_layer.py:66-68; a git-only, unpinned dependency, reference setup.py:33), otherwise this package's own
+    implementation of the same method (structurednets_b200/sss_identification.py).  Either result is a valid realisation --
+    they agree up to a state-space similarity, which no reference test pins."""
     try:
         from tvsclib.mixed_system import MixedSystem
         from tvsclib.toeplitz_operator import ToeplitzOperator
         from tvsclib.system_identification_svd import SystemIdentificationSVD
-    except ImportError as e:
-        raise ImportError(
-            "SSSLayer: building the state-space realisation from a dense matrix needs tvsclib "
-            "(git+https://github.com/MatthiasKi/tvsclib), which is not installed; pass "
-            "initial_system_approx=<mixed system> instead") from e
+    except ImportError:
+        from structurednets_b200.sss_identification import identify_mixed_system
+        return identify_mixed_system(T_full, dims_in, dims_out, statespace_dim)
     T_operator = ToeplitzOperator(T_full, dims_in, dims_out)
     S = SystemIdentificationSVD(toeplitz=T_operator, max_states_local=statespace_dim)
     return MixedSystem(S)
