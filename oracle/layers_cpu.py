@@ -156,12 +156,23 @@ def ldr_weight_literal(rep: Sequence[torch.Tensor], shape) -> torch.Tensor:
     return res
 
 
-def ldr_weight(rep: Sequence[torch.Tensor], shape) -> torch.Tensor:
+def ldr_tail_bound(rep: Sequence[torch.Tensor], nb_terms: int) -> float:
+    """Upper bound of everything ``ldr_weight(..., nb_terms=nb_terms)`` leaves out, relative to the j = 0 term's bound:
+    sum_{j >= nb_terms} (|A|_inf |B|_1)^j -- meaningful only when the operators' norms are below 1."""
+    Ad = (rep[0].to_dense() if rep[0].is_sparse else rep[0]).detach().abs()
+    Bd = (rep[1].to_dense() if rep[1].is_sparse else rep[1]).detach().abs()
+    q = float(Ad.sum(1).max() * Ad.sum(0).max()) ** 0.5 * float(Bd.sum(1).max() * Bd.sum(0).max()) ** 0.5
+    return float("inf") if q >= 1 else q ** nb_terms / (1 - q)
+
+
+def ldr_weight(rep: Sequence[torch.Tensor], shape, nb_terms: Optional[int] = None) -> torch.Tensor:
     """Same matrix as ``ldr_approximator.py:29-39`` with the Krylov matrices built by the
     recurrence k_{j+1} = M k_j (as the reference's own numpy TL code does,
     approximators/tl_approximator.py:14-19) in float64, accumulated into float32 per term like
-    ``:31,37``.  Differentiable (autograd through the recurrence)."""
-    n = shape[0]
+    ``:31,37``.  Differentiable (autograd through the recurrence).  ``nb_terms`` (tests at n = 2048 only): keep the
+    first nb_terms of the n Krylov powers; the caller asserts with :func:`ldr_tail_bound` that the dropped tail is below
+    float64 resolution, so the matrix is the same."""
+    n = shape[0] if nb_terms is None else min(shape[0], nb_terms)
     Ad = rep[0].to_dense() if rep[0].is_sparse else rep[0]
     Bd = rep[1].to_dense() if rep[1].is_sparse else rep[1]
     BdT = torch.transpose(Bd, 0, 1)
@@ -177,8 +188,8 @@ def ldr_weight(rep: Sequence[torch.Tensor], shape) -> torch.Tensor:
     return W.float()
 
 
-def ldr_forward(U, rep, bias, shape, literal=False):
-    W = ldr_weight_literal(rep, shape) if literal else ldr_weight(rep, shape)
+def ldr_forward(U, rep, bias, shape, literal=False, nb_terms=None):
+    W = ldr_weight_literal(rep, shape) if literal else ldr_weight(rep, shape, nb_terms=nb_terms)
     y = torch.matmul(W, U.T).T           # ldr_layer.py:54-55
     if bias is not None:
         y = y + bias                     # :57-58

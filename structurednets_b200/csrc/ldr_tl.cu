@@ -190,7 +190,7 @@ __global__ void tl_k1_kernel(const float* __restrict__ G, float* __restrict__ K1
 }
 // K2[j*n+i][q] = v_j[(i-q) mod n] * (i < q ? -1 : 1),  v_j[m] = H[j][n-1-m]     (Krylov(Z_-1, flip(H[j,:])))
 __global__ void tl_k2_kernel(const float* __restrict__ H, float* __restrict__ K2, int n, int r) {
-    int q = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;  // row = j*n + i
+    int q = blockIdx.y * blockDim.x + threadIdx.x, row = blockIdx.x;  // row = j*n + i  (n*r rows: on grid.x, grid.y stops at 65 535)
     if (q >= n) return;
     int j = row / n, i = row - j * n;
     int m = i - q; if (m < 0) m += n;
@@ -350,7 +350,7 @@ int sn_tl_build_weight(int n, int r, const float* G, const float* H, float* K1, 
     SN_CHECK_ARG(n > 0 && r > 0 && G && H && K1 && K2 && W, "tl_build_weight: bad arguments");
     cudaStream_t st = snb::as_stream(stream);
     tl_k1_kernel<<<dim3(snb::ceil_div(n * r, 128), n), 128, 0, st>>>(G, K1, n, r); SN_CHECK_LAUNCH("tl_k1_kernel");
-    tl_k2_kernel<<<dim3(snb::ceil_div(n, 128), n * r), 128, 0, st>>>(H, K2, n, r); SN_CHECK_LAUNCH("tl_k2_kernel");
+    tl_k2_kernel<<<dim3(n * r, snb::ceil_div(n, 128)), 128, 0, st>>>(H, K2, n, r); SN_CHECK_LAUNCH("tl_k2_kernel");
     return snb::gemm_f32(false, false, n, n, n * r, 0.5f, K1, (long)n * r, K2, n, 0.f, W, n, nullptr, st);
 }
 // dK1 / dK2: scratch of the same sizes as K1 / K2; gG (n x r), gH (r x n) are accumulated into.

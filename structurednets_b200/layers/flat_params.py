@@ -170,8 +170,11 @@ class FlatParamsMixin:
         g = self.flat_grad()
         params = self._flat_param_list()
         views = self.__dict__["_flat_grad_views"]
-        if params and (params[0].grad is None or params[-1].grad is None
-                       or params[0].grad.data_ptr() != views[0].data_ptr()):
+        # sentinels: the first and the last parameter that TAKE a gradient (a frozen parameter's .grad stays None for ever; using it
+        # as a sentinel would clear the buffer in every backward and lose gradient accumulation)
+        live = [i for i, p in enumerate(params) if p.requires_grad]
+        if live and (params[live[0]].grad is None or params[live[-1]].grad is None
+                     or params[live[0]].grad.data_ptr() != views[live[0]].data_ptr()):
             g.zero_()
             for p, v in zip(params, views):
                 if p.requires_grad:

@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from structurednets_b200 import _lib
-from structurednets_b200.hmatrix.hmatrix import HMatrixComponent, approximate_hmatrix
+from structurednets_b200.hmatrix.hmatrix import BlockClusterTree, HMatrix, HMatrixComponent, TreeElement, approximate_hmatrix
 from structurednets_b200.layers.flat_params import FlatParamsMixin
 from structurednets_b200.layers.layer_helpers import get_random_glorot_uniform_matrix
 from structurednets_b200.layers.structured_layer import StructuredLayer
@@ -120,6 +120,40 @@ class HMatLayer(FlatParamsMixin, StructuredLayer):
         self._nleaves = len(own)
         self._max_leaf_rows = max([len(c.row_range) for c in own], default=1)
         self._flatten_parameters()
+
+    # ---- pickling: the tree in ``self.hmatrix`` references the same leaf modules as ``hmatrix_components``; pickled as it is, every
+    # leaf parameter (a view of the flat buffer) would carry the whole flat storage.  Only the tree's ranges are stored, the leaves
+    # are re-bound to ``hmatrix_components`` on load, so ``hmatrix.to_dense()`` keeps tracking the trained parameters.
+    def __getstate__(self):
+        state = super().__getstate__()
+        hm = state.get("hmatrix")
+        if isinstance(hm, HMatrix) and isinstance(hm.block_cluster_tree, BlockClusterTree):
+            index = {id(c): i for i, c in enumerate(self.hmatrix_components)}
+
+            def skeleton(el):
+                if el.is_leaf():
+                    return (el.row_range, el.col_range, index.get(id(el.hmatrix_component), -1))
+                return (el.row_range, el.col_range, [skeleton(ch) for ch in el.children])
+            state["hmatrix"] = None
+            state["_hmatrix_skeleton"] = (skeleton(hm.block_cluster_tree.root), getattr(hm, "shape", None))
+        return state
+
+    def __setstate__(self, state):
+        state = dict(state)
+        sk = state.pop("_hmatrix_skeleton", None)
+        super().__setstate__(state)
+        if sk is not None:
+            comps = list(self.hmatrix_components)
+
+            def rebuild(node):
+                rows, cols, rest = node
+                el = TreeElement(None, rows, cols)
+                if isinstance(rest, list):
+                    el.children = [rebuild(ch) for ch in rest]
+                elif rest >= 0:
+                    el.hmatrix_component = comps[rest]
+                return el
+            self.hmatrix = HMatrix(BlockClusterTree(rebuild(sk[0])), shape=sk[1])
 
     DENSE_PATH_MAX_ELEMENTS = 1 << 26   # dense (out x in) fp32 copies of at most 256 MB each
 

@@ -98,6 +98,44 @@ def get_loss_and_accuracy_for_model(model, X: np.ndarray, y: np.ndarray, loss_fu
     return loss, accuracy
 
 
+def _dp_world(grad_sync):
+    """(group, world size) of a data-parallel run, or (None, 1).  Only a ``grad_sync`` with a process group behind it counts."""
+    if grad_sync is None:
+        return None, 1
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return None, 1
+    group = getattr(grad_sync, "group", None)
+    return group, dist.get_world_size(group)
+
+
+def _dp_check_equal_steps(grad_sync, nb_batches_per_epoch, device):
+    """Every rank must run the same number of optimizer steps per epoch: a rank that stops early leaves the others waiting in
+    the all-reduce of the next step."""
+    group, world = _dp_world(grad_sync)
+    if world == 1:
+        return
+    import torch.distributed as dist
+    t = torch.tensor([int(nb_batches_per_epoch), -int(nb_batches_per_epoch)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    assert int(t[0]) == -int(t[1]), ("data-parallel training needs the same number of batches per epoch on every rank "
+                                     "(got between %d and %d): shard the samples evenly or pad the shards" % (-int(t[1]), int(t[0])))
+
+
+def _dp_reduce_stats(grad_sync, loss, accuracy, nb_samples, device):
+    """Loss and accuracy of the GLOBAL data set from every rank's shard values, identical on all ranks, so that early stopping and
+    the best-model choice (reference :161-170) are taken in lockstep.  Loss: mean of the ranks' per-shard values (each is a mean over
+    equally many batches); accuracy: correct predictions over all samples."""
+    group, world = _dp_world(grad_sync)
+    if world == 1:
+        return loss, accuracy
+    import torch.distributed as dist
+    t = torch.tensor([float(loss), float(accuracy) * nb_samples, float(nb_samples)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    t = t.cpu().numpy()
+    return np.float32(t[0] / world), np.float32(t[1] / t[2])
+
+
 def train_with_decreasing_lr(model, X_train, y_train, X_val=None, y_val=None, patience=10, batch_size=1000, verbose=False,
                              loss_function_class=torch.nn.CrossEntropyLoss, min_patience_improvement=1e-10,
                              optimizer_class=torch.optim.SGD, use_gpu=False):
@@ -122,15 +160,19 @@ def train(model, X_train, y_train, X_val=None, y_val=None, patience=10, batch_si
           grad_sync=None):
     """Same contract as the reference ``train`` (:107-181).  ``grad_sync`` (optional, new): a callable invoked between
     ``loss.backward()`` and ``optimizer.step()`` -- ``structurednets_b200.distributed.GradSynchronizer`` for data-parallel
-    training (one NCCL all-reduce of the flat gradient buffer)."""
+    training (one NCCL all-reduce of the flat gradient buffer).  With a process group behind ``grad_sync`` the epoch losses and
+    accuracies are reduced over the ranks before the patience and best-model decisions, so all ranks stop in the same epoch and
+    return the same model; ranks must hold equally many batches per epoch (asserted)."""
     if X_val is None or y_val is None:
         X_train, X_val, y_train, y_val = train_test_split(X_train, y_train, test_size=0.2)
 
     optimizer = optimizer_class(model.parameters(), lr=lr)
     loss_function = loss_function_class()
     nb_batches_per_epoch = np.ceil(X_train.shape[0] / batch_size).astype("int")
-    evaluate = lambda X, y: get_loss_and_accuracy_for_model(model=model, X=X, y=y, loss_function_class=loss_function_class,
-                                                             batch_size=batch_size, use_gpu=use_gpu)
+    stats_device = get_device(use_gpu=use_gpu)
+    _dp_check_equal_steps(grad_sync, nb_batches_per_epoch, stats_device)
+    evaluate = lambda X, y: _dp_reduce_stats(grad_sync, *get_loss_and_accuracy_for_model(
+        model=model, X=X, y=y, loss_function_class=loss_function_class, batch_size=batch_size, use_gpu=use_gpu), len(y), stats_device)
     start_train_loss, start_train_accuracy = evaluate(X_train, y_train)
     start_val_loss, start_val_accuracy = evaluate(X_val, y_val)
     if verbose:
@@ -312,7 +354,8 @@ def train_resident(model, X_train, y_train, X_val=None, y_val=None, patience=10,
     loss_function = loss_function_class()
     n = Xd.shape[0]
     nb_batches_per_epoch = np.ceil(n / batch_size).astype("int")
-    evaluate = lambda X, y: _evaluate_resident(model, X, y, loss_function, batch_size)
+    _dp_check_equal_steps(grad_sync, nb_batches_per_epoch, device)
+    evaluate = lambda X, y: _dp_reduce_stats(grad_sync, *_evaluate_resident(model, X, y, loss_function, batch_size), len(y), device)
     start_train_loss, start_train_accuracy = evaluate(Xd, yd)
     start_val_loss, start_val_accuracy = evaluate(Xv, yv)
     if verbose:
