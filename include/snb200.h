@@ -231,24 +231,33 @@ int sn_psm_dense_forward(const sn_psm_dense_factor* factors_host, int nf, const 
 int sn_psm_dense_backward(const sn_psm_dense_factor* factors_host, int nf, const float* x, int64_t ldx, const float* grad_y,
                           int64_t ldgy, const float* prefix, float* work, float* grad_bias, int64_t B, int in_dim, int out_dim,
                           sn_stream_t stream);
+/* grad_x = grad_y W (gradient w.r.t. the input features) from the product kept in `prefix` by sn_psm_dense_forward */
+int sn_psm_dense_input_grad(const sn_psm_dense_factor* factors, int nf, const float* prefix, const float* grad_y, int64_t ldgy,
+                            float* grad_x, int64_t ldgx, int64_t B, int in_dim, int out_dim, sn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * LDR layer -- replaces build_weight_matrix_torch (approximators/ldr_approximator.py:29-39) + the matmul of
  * LDRLayer.forward (layers/ldr_layer.py:54-58) and their backward.  A, B: COO value arrays (float64) with a slot
  * map per entry into the banded layout {lo[n] | di[n] | up[n] | corner(0,n-1), corner(n-1,0)}; G, H: n x r float64.
- * sn_ldr_build_weight synchronises `stream` every 8 series terms to test convergence (the one exception to
- * "never synchronises").  The workspace keeps the prefix sums sn_ldr_backward needs.
+ * The Krylov blocks KA_j = A^j G, KB_j = (B^T)^j H are built by recurrence (one kernel, float64) for j < max_terms, and
+ * W = [KA_0 | KA_1 | ..][KB_0 | KB_1 | ..]^T is one tensor-core contraction whose length (the number of powers that matter,
+ * found on the device) travels through `status` (device int[4]: {powers used, K, converged, max_terms}).  Nothing here
+ * synchronises the stream; the caller reads `status` when it wants to know whether max_terms was enough.
+ * The workspace (sn_ldr_workspace_bytes) keeps what sn_ldr_backward needs.  n must be a multiple of 4 and <= 4096.
  * ------------------------------------------------------------------------------------------ */
-size_t sn_ldr_workspace_doubles(int n, int max_terms);
+size_t sn_ldr_workspace_bytes(int n, int r, int max_terms);
 int sn_ldr_build_weight(int n, int r, const double* A_vals, const int32_t* A_slot, int A_nnz, const double* B_vals,
-                        const int32_t* B_slot, int B_nnz, const double* G, const double* H, double* workspace, int max_terms,
-                        double rel_tol, float* W_out, int* terms_out_host, sn_stream_t stream);
+                        const int32_t* B_slot, int B_nnz, const double* G, const double* H, void* workspace, int max_terms,
+                        double rel_tol, float* W_out, int* status_dev, sn_stream_t stream);
 int sn_ldr_backward(int n, int r, const float* dW, const int32_t* A_slot, int A_nnz, const int32_t* B_slot, int B_nnz,
-                    const double* G, const double* H, double* workspace, int terms, double* gA_vals, double* gB_vals, double* gG,
+                    void* workspace, int max_terms, const int* status_dev, double* gA_vals, double* gB_vals, double* gG,
                     double* gH, sn_stream_t stream);
 /* y = x W^T + bias and dW += grad_y^T x (grad_bias += column sums): the dense apply shared by LDR and TL */
 int sn_dense_apply(const float* W, int n_out, int n_in, const float* x, int64_t ldx, float* y, int64_t ldy, const float* bias,
                    int64_t B, sn_stream_t stream);
+/* grad_x = grad_y W: gradient w.r.t. the input features for every layer that materialises its weight matrix */
+int sn_dense_input_grad(const float* W, int n_out, int n_in, const float* grad_y, int64_t ldgy, float* grad_x, int64_t ldgx,
+                        int64_t B, sn_stream_t stream);
 int sn_dense_weight_grad(const float* x, int64_t ldx, const float* grad_y, int64_t ldgy, float* dW, int n_out, int n_in,
                          float* grad_bias, int64_t B, sn_stream_t stream);
 

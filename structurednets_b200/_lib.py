@@ -116,13 +116,17 @@ def _declare(lib):
     lib.sn_psm_dense_forward.argtypes = [PD, i32, vp, i64, vp, i64, vp, vp, i64, i32, i32, vp]
     lib.sn_psm_dense_backward.restype = c_int
     lib.sn_psm_dense_backward.argtypes = [PD, i32, vp, i64, vp, i64, vp, vp, vp, i64, i32, i32, vp]
+    lib.sn_psm_dense_input_grad.restype = c_int
+    lib.sn_psm_dense_input_grad.argtypes = [PD, i32, vp, vp, i64, vp, i64, i64, i32, i32, vp]
     f64 = ctypes.c_double
-    lib.sn_ldr_workspace_doubles.restype = c_size_t
-    lib.sn_ldr_workspace_doubles.argtypes = [i32, i32]
+    lib.sn_ldr_workspace_bytes.restype = c_size_t
+    lib.sn_ldr_workspace_bytes.argtypes = [i32, i32, i32]
     lib.sn_ldr_build_weight.restype = c_int
-    lib.sn_ldr_build_weight.argtypes = [i32, i32, vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, f64, vp, POINTER(c_int), vp]
+    lib.sn_ldr_build_weight.argtypes = [i32, i32, vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, f64, vp, vp, vp]
     lib.sn_ldr_backward.restype = c_int
-    lib.sn_ldr_backward.argtypes = [i32, i32, vp, vp, i32, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    lib.sn_ldr_backward.argtypes = [i32, i32, vp, vp, i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.sn_dense_input_grad.restype = c_int
+    lib.sn_dense_input_grad.argtypes = [vp, i32, i32, vp, i64, vp, i64, i64, vp]
     lib.sn_dense_apply.restype = c_int
     lib.sn_dense_apply.argtypes = [vp, i32, i32, vp, i64, vp, i64, vp, i64, vp]
     lib.sn_dense_weight_grad.restype = c_int

@@ -100,7 +100,8 @@ gemm_f32_kernel(int M, int N, int Kfull, int kslice, float alpha, const float* _
 // returns 0 / error code like the C ABI functions
 // accumulate = true: C += alpha * op(A) op(B) with split-K over the whole chip (C must hold the running sum)
 inline int gemm_f32(bool ta, bool tb, int M, int N, int K, float alpha, const float* A, long lda, const float* B, long ldb,
-                    float beta, float* C, long ldc, const float* bias, cudaStream_t stream, bool accumulate = false) {
+                    float beta, float* C, long ldc, const float* bias, cudaStream_t stream, bool accumulate = false,
+                    const int* kdev = nullptr, const int* mdev = nullptr) {
     if (M <= 0 || N <= 0) return 0;
     // tensor-core path (3xTF32, csrc/gemm_tf32x3.cuh) whenever TMA can read the operands; SNB200_GEMM=simt forces the CUDA-core kernel
     {
@@ -119,12 +120,14 @@ inline int gemm_f32(bool ta, bool tb, int M, int N, int K, float alpha, const fl
                 if (ksplit < 1) ksplit = 1;
             }
             // op(A) = A^T (ta) means A is stored [K][M] (MN-major); op(B) = B (!tb) means B is stored [K][N] (MN-major)
-            if (!ta && tb) return t3::gemm_tf32x3_launch<false, false>(M, N, K, alpha, A, lda, B, ldb, C, ldc, bias, ksplit, accumulate, stream);
-            if (!ta && !tb) return t3::gemm_tf32x3_launch<false, true>(M, N, K, alpha, A, lda, B, ldb, C, ldc, bias, ksplit, accumulate, stream);
-            if (ta && tb) return t3::gemm_tf32x3_launch<true, false>(M, N, K, alpha, A, lda, B, ldb, C, ldc, bias, ksplit, accumulate, stream);
-            return t3::gemm_tf32x3_launch<true, true>(M, N, K, alpha, A, lda, B, ldb, C, ldc, bias, ksplit, accumulate, stream);
+            if (!ta && tb) return t3::gemm_tf32x3_launch<false, false>(M, N, K, alpha, A, lda, B, ldb, C, ldc, bias, ksplit, accumulate, stream, kdev, mdev);
+            if (!ta && !tb) return t3::gemm_tf32x3_launch<false, true>(M, N, K, alpha, A, lda, B, ldb, C, ldc, bias, ksplit, accumulate, stream, kdev, mdev);
+            if (ta && tb) return t3::gemm_tf32x3_launch<true, false>(M, N, K, alpha, A, lda, B, ldb, C, ldc, bias, ksplit, accumulate, stream, kdev, mdev);
+            return t3::gemm_tf32x3_launch<true, true>(M, N, K, alpha, A, lda, B, ldb, C, ldc, bias, ksplit, accumulate, stream, kdev, mdev);
         }
     }
+    SN_CHECK_ARG(kdev == nullptr && mdev == nullptr, "gemm_f32: device-side extents need the tensor-core path (16-byte aligned operands, "
+                 "row pitches multiples of 4, K <= 4096 or an accumulating epilogue)");
     dim3 grid(ceil_div(N, GB_N), ceil_div(M, GB_M), 1);
     int kslice = K > 0 ? K : 1;
     if (accumulate) {

@@ -29,6 +29,10 @@ struct T3Args {
     const float* bias;
     float alpha;
     int atomic;
+    // Extents known only on the device (the LDR layer's Krylov series length): *kdev caps K (and the K slices of a split-K launch
+    // are cut from the capped extent), CTAs whose rows start at or beyond *mdev leave at once.  NULL = use M / K as given.
+    const int* kdev;
+    const int* mdev;
 };
 
 // hi = round-to-nearest tf32 of x, lo = round-to-nearest tf32 of (x - hi).  The tensor core TRUNCATES the low 13 mantissa bits
@@ -54,9 +58,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
-    const int kbeg = blockIdx.z * args.kslice;
-    const int kend = min(args.K, kbeg + args.kslice);
-    const int nkb = (kend - kbeg + 31) / 32;
+    if (args.mdev != nullptr && m0 >= __ldg(args.mdev)) return;     // uniform over the CTA, before any barrier or TMEM allocation
+    int Kl = args.K, kslice = args.kslice;
+    if (args.kdev != nullptr) {
+        Kl = min(Kl, __ldg(args.kdev));
+        kslice = round_up(ceil_div(Kl > 0 ? Kl : 1, (int)gridDim.z), 32);
+    }
+    const int kbeg = blockIdx.z * kslice;
+    const int kend = min(Kl, kbeg + kslice);
+    const int nkb = kend > kbeg ? (kend - kbeg + 31) / 32 : 0;
+    if (args.kdev != nullptr && args.atomic && nkb == 0) return;    // an empty K slice of an accumulating launch adds nothing
     // The tensor core adds products into its fp32 accumulator with truncation, an error that grows linearly with the length of
     // the sum; K is therefore spread over up to four TMEM accumulators that the epilogue adds with ordinary fp32 rounding.
     const int chunk = (nkb + 3) / 4 > 0 ? (nkb + 3) / 4 : 1;
@@ -216,7 +227,7 @@ inline bool t3_eligible(const float* A, long lda, const float* B, long ldb) {
 // a_mn: A is stored [K][M]; b_mn: B is stored [K][N].  ksplit > 1 (or atomic) accumulates into D with reductions.
 template <bool A_MN, bool B_MN>
 inline int gemm_tf32x3_launch(int M, int N, int K, float alpha, const float* A, long lda, const float* B, long ldb, float* D, long ldd, const float* bias,
-                              int ksplit, bool atomic, cudaStream_t stream) {
+                              int ksplit, bool atomic, cudaStream_t stream, const int* kdev = nullptr, const int* mdev = nullptr) {
     CUtensorMap ma, mb;
     if (A_MN) { if (int rc = make_map_f32(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 32, 0, 0, true)) return rc; }
     else      { if (int rc = make_map_f32(&ma, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 128)) return rc; }
@@ -227,6 +238,7 @@ inline int gemm_tf32x3_launch(int M, int N, int K, float alpha, const float* A, 
     if (ksplit < 1) ksplit = 1;
     args.kslice = round_up(ceil_div(K > 0 ? K : 1, ksplit), 32);
     args.D = D; args.ldd = ldd; args.bias = bias; args.alpha = alpha; args.atomic = atomic ? 1 : 0;
+    args.kdev = kdev; args.mdev = mdev;
     dim3 grid(ceil_div(N, 128), ceil_div(M, 128), ceil_div(K > 0 ? K : 1, args.kslice));
     SN_CHECK_ARG(atomic || grid.z == 1, "gemm_tf32x3: split-K needs the accumulating epilogue");
     SN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3_SMEM));

@@ -3,15 +3,16 @@
 // LDR replaces LDRLayer.forward = build_weight_matrix_torch + matmul (reference layers/ldr_layer.py:44-61,
 // approximators/ldr_approximator.py:29-39) and its autograd backward.  The reference materialises
 //     W = sum_i K(A, g_i) K(B^T, h_i)^T ,   K(M, v) = [v, Mv, ..., M^{n-1} v]
-// with matrix_power per column (O(r n^4 log n)).  Since K(A,g_i) K(B^T,h_i)^T = sum_j A^j g_i h_i^T B^j,
-//     W = sum_{j=0}^{n-1} T_j ,   T_0 = G H^T ,   T_{j+1} = A T_j B ,
-// and A, B are tridiagonal + two corners, so each step is two O(n^2) banded passes in float64 (the
-// parameters are float64).  The series is summed until a term is numerically zero relative to
-// W (or j = n-1): for Glorot-scale operators it converges after a few dozen terms instead of n.
-// Backward (exact gradient of the summed series, J = last term):
-//     S_0 = dW, S_{l+1} = A^T S_l B^T ;  dM = sum_l S_l ;  dG = dM H ;  dH = dM^T G
-//     dA = sum_{l<J} pattern( S_l (P_{J-1-l} B)^T ) ;  dB = sum_{l<J} pattern( P_{J-1-l}^T (A^T S_l) )
-// with the prefix sums P_k = sum_{m<=k} T_m saved by the forward.
+// with matrix_power per column (O(r n^4 log n)).  Here the Krylov blocks are built by the recurrence
+//     KA_0 = G, KA_{j+1} = A KA_j ;   KB_0 = H, KB_{j+1} = B^T KB_j          (n x r each, float64, banded operator: O(n r) per step)
+// by ONE kernel per call (a CTA keeps a few columns in shared memory and walks all the powers), and
+//     W = sum_j KA_j KB_j^T = [KA_0 | KA_1 | ...] [KB_0 | KB_1 | ...]^T
+// is a single dense contraction over K = r J on the tensor cores (3xTF32, fp32-accurate: the reference accumulates its float64
+// terms into a float32 matrix, approximators/ldr_approximator.py:31,37).  J, the number of powers that matter, is found ON THE
+// DEVICE from the columns' max-norms (term j is bounded by sum_i |KA_j[:,i]|_inf |KB_j[:,i]|_inf) and handed to the GEMM through
+// device memory (gemm_tf32x3's kdev / mdev): no host synchronisation, the whole step can be captured in a CUDA graph.
+// Backward: dKA = dW KB, dKB = dW^T KA (two tensor-core GEMMs), then the adjoint recurrences in float64 (one kernel)
+//     abar_{J-1} = dK_{J-1}, abar_j = dK_j + M^T abar_{j+1} ;   dM += pattern( abar_{j+1} K_j^T ) ;   dG (dH) = abar_0 .
 //
 // Toeplitz-like replaces TLLayer.forward (reference layers/tl_layer.py:11-18,51-68):
 //     W = 1/2 sum_j Krylov(Z_1, G[:,j]) Krylov(Z_-1, flip(H[j,:]))
@@ -21,14 +22,8 @@
 
 namespace {
 
-struct Band {           // tridiagonal-plus-corners n x n operator M
-    const double* lo;   // lo[p] = M[p][p-1]   (lo[0] unused = 0)
-    const double* di;   // di[p] = M[p][p]
-    const double* up;   // up[p] = M[p][p+1]   (up[n-1] unused = 0)
-    const double* cn;   // cn[0] = M[0][n-1], cn[1] = M[n-1][0]  (0 when n <= 2)
-};
-
 // slot map entry: 0..n-1 -> lo, n..2n-1 -> di, 2n..3n-1 -> up, 3n -> corner(0,n-1), 3n+1 -> corner(n-1,0)
+//   lo[p] = M[p][p-1] (lo[0] unused = 0), di[p] = M[p][p], up[p] = M[p][p+1] (up[n-1] unused = 0)
 __global__ void band_gather_kernel(const double* __restrict__ vals, const int* __restrict__ slot, int nnz, double* __restrict__ band) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < nnz) atomicAdd(band + slot[e], vals[e]);
@@ -48,132 +43,161 @@ __global__ void band_transpose_kernel(const double* __restrict__ b, double* __re
     if (p == 0) { t[3 * n] = b[3 * n + 1]; t[3 * n + 1] = b[3 * n]; }
 }
 
-__device__ __forceinline__ Band as_band(const double* b, int n) { return Band{b, b + n, b + 2 * n, b + 3 * n}; }
+constexpr int KR_THREADS = 1024;
+__host__ __device__ inline int kr_cols_fwd(int n) { int c = 12800 / n; return c > 8 ? 8 : c; }          // 2 buffers of n x C doubles <= 200 KB
+__host__ __device__ inline int kr_cols_bwd(int n) { int c = (25600 / n - 3) / 2; return c > 8 ? 8 : c; }  // 2 buffers + 3 n-vectors of band gradients
 
-// out = M T   (rows mix)
-__global__ void band_left_kernel(const double* __restrict__ band, const double* __restrict__ T, double* __restrict__ out, int n) {
-    int q = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
-    if (q >= n) return;
-    Band M = as_band(band, n);
-    double v = M.di[p] * T[(size_t)p * n + q];
-    if (p > 0) v += M.lo[p] * T[(size_t)(p - 1) * n + q];
-    if (p + 1 < n) v += M.up[p] * T[(size_t)(p + 1) * n + q];
-    if (n > 2) {
-        if (p == 0) v += M.cn[0] * T[(size_t)(n - 1) * n + q];
-        if (p == n - 1) v += M.cn[1] * T[q];
+// Krylov blocks of one operator (blockIdx.y = 0: M = A, start G; 1: M = B^T, start H) for the CTA's columns [c0, c0 + C):
+//   K64[op][j][i][p]  (float64, p contiguous)  and  K32[op][j r + i][p]  (float32, the MN-major GEMM operand), j < J;
+//   colnorm[op][j][i] = max_p |K_j[p][i]|.
+__global__ void __launch_bounds__(KR_THREADS)
+ldr_krylov_kernel(int n, int r, int J, int C, const double* __restrict__ bands, const double* __restrict__ G, const double* __restrict__ H,
+                  double* __restrict__ K64, float* __restrict__ K32, long k32_rows, double* __restrict__ colnorm) {
+    extern __shared__ __align__(16) double kr_smem[];
+    __shared__ double red[32];
+    const int op = blockIdx.y, c0 = blockIdx.x * C, nc = min(C, r - c0), tid = threadIdx.x;
+    const double* band = bands + (size_t)op * (3 * n + 2);
+    const double* lo = band, *di = band + n, *up = band + 2 * n;
+    const double cn0 = n > 2 ? band[3 * n] : 0.0, cn1 = n > 2 ? band[3 * n + 1] : 0.0;
+    const double* src = op == 0 ? G : H;
+    double* cur = kr_smem;
+    double* nxt = kr_smem + (size_t)C * n;
+    for (int e = tid; e < nc * n; e += KR_THREADS) {       // e = p * nc + c: the n x r row-major source is read nc-contiguous
+        const int p = e / nc, c = e - p * nc;
+        cur[(size_t)c * n + p] = src[(size_t)p * r + c0 + c];
     }
-    out[(size_t)p * n + q] = v;
-}
-// out = T M   (columns mix)
-__global__ void band_right_kernel(const double* __restrict__ band, const double* __restrict__ T, double* __restrict__ out, int n) {
-    int q = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
-    if (q >= n) return;
-    Band M = as_band(band, n);
-    const double* row = T + (size_t)p * n;
-    double v = row[q] * M.di[q];
-    if (q > 0) v += row[q - 1] * M.up[q - 1];
-    if (q + 1 < n) v += row[q + 1] * M.lo[q + 1];
-    if (n > 2) {
-        if (q == n - 1) v += row[0] * M.cn[0];
-        if (q == 0) v += row[n - 1] * M.cn[1];
-    }
-    out[(size_t)p * n + q] = v;
-}
-// acc += T ; optionally snapshot = acc ; block-wise max |T| -> atomicMax on the bit pattern (non-negative doubles order like uint64)
-__global__ void accumulate_kernel(const double* __restrict__ T, double* __restrict__ acc, double* __restrict__ snapshot, size_t n2,
-                                  unsigned long long* __restrict__ maxabs_bits) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double a = 0.0;
-    if (i < n2) {
-        double t = T[i];
-        double w = acc[i] + t;
-        acc[i] = w;
-        if (snapshot) snapshot[i] = w;
-        a = fabs(t);
-    }
-    for (int o = 16; o > 0; o >>= 1) a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
-    if ((threadIdx.x & 31) == 0 && a > 0.0) atomicMax(maxabs_bits, (unsigned long long)__double_as_longlong(a));
-}
-// C[n x n] = G H^T  (double)
-__global__ void ght_kernel(const double* __restrict__ G, const double* __restrict__ H, double* __restrict__ C, int n, int r) {
-    int q = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
-    if (q >= n) return;
-    double v = 0.0;
-    for (int i = 0; i < r; ++i) v += G[(size_t)p * r + i] * H[(size_t)q * r + i];
-    C[(size_t)p * n + q] = v;
-}
-// dG[p][i] += sum_q dM[p][q] H[q][i] ; dH[q][i] += sum_p dM[p][q] G[p][i]
-__global__ void dgh_kernel(const double* __restrict__ dM, const double* __restrict__ G, const double* __restrict__ H,
-                           double* __restrict__ dG, double* __restrict__ dH, int n, int r) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x, p = blockIdx.y;
-    if (i >= r) return;
-    double a = 0.0, b = 0.0;
-    for (int q = 0; q < n; ++q) {
-        a += dM[(size_t)p * n + q] * H[(size_t)q * r + i];
-        b += dM[(size_t)q * n + p] * G[(size_t)q * r + i];
-    }
-    dG[(size_t)p * r + i] += a;
-    dH[(size_t)p * r + i] += b;
-}
-__global__ void cast_f64_f32_kernel(const double* __restrict__ a, float* __restrict__ b, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) b[i] = (float)a[i];
-}
-__global__ void cast_f32_f64_kernel(const float* __restrict__ a, double* __restrict__ b, size_t n) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) b[i] = (double)a[i];
-}
-// gband(A) += pattern( S Q^T ):  dA[p][a] = sum_q S[p][q] Q[a][q]  for a in {p-1, p, p+1} and the corners; one warp per row p
-__global__ void row_band_dots_kernel(const double* __restrict__ S, const double* __restrict__ Q, double* __restrict__ gband, int n) {
-    int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (p >= n) return;
-    const double* s = S + (size_t)p * n;
-    const double* q0 = Q + (size_t)p * n;
-    const double* qm = p > 0 ? q0 - n : nullptr;
-    const double* qp = p + 1 < n ? q0 + n : nullptr;
-    const double* qc = (n > 2 && p == 0) ? Q + (size_t)(n - 1) * n : ((n > 2 && p == n - 1) ? Q : nullptr);
-    double a0 = 0, am = 0, ap = 0, ac = 0;
-    for (int q = lane; q < n; q += 32) {
-        double sv = s[q];
-        a0 += sv * q0[q];
-        if (qm) am += sv * qm[q];
-        if (qp) ap += sv * qp[q];
-        if (qc) ac += sv * qc[q];
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, o); am += __shfl_xor_sync(0xffffffffu, am, o);
-        ap += __shfl_xor_sync(0xffffffffu, ap, o); ac += __shfl_xor_sync(0xffffffffu, ac, o);
-    }
-    if (lane == 0) {
-        gband[n + p] += a0;
-        if (qm) gband[p] += am;
-        if (qp) gband[2 * n + p] += ap;
-        if (qc) gband[3 * n + (p == 0 ? 0 : 1)] += ac;
+    __syncthreads();
+    double* k64 = K64 + (size_t)op * J * r * n;
+    float* k32 = K32 + (size_t)op * k32_rows * n;
+    for (int j = 0; j < J; ++j) {
+        for (int c = 0; c < nc; ++c) {
+            const double* v = cur + (size_t)c * n;
+            double* w = nxt + (size_t)c * n;
+            double* o64 = k64 + ((size_t)j * r + c0 + c) * n;
+            float* o32 = k32 + ((size_t)j * r + c0 + c) * n;
+            double mx = 0.0;
+            for (int p = tid; p < n; p += KR_THREADS) {
+                const double x = v[p];
+                o64[p] = x;
+                o32[p] = (float)x;
+                mx = fmax(mx, fabs(x));
+                double acc = di[p] * x;
+                if (p > 0) acc += lo[p] * v[p - 1];
+                if (p + 1 < n) acc += up[p] * v[p + 1];
+                if (p == 0) acc += cn0 * v[n - 1];
+                if (p == n - 1) acc += cn1 * v[0];
+                w[p] = acc;
+            }
+            for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if ((tid & 31) == 0) red[tid >> 5] = mx;
+            __syncthreads();
+            if (tid < 32) {
+                double m = red[tid];
+                for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (tid == 0) colnorm[((size_t)op * J + j) * r + c0 + c] = m;
+            }
+            __syncthreads();
+        }
+        double* t = cur; cur = nxt; nxt = t;
     }
 }
-// gband(B) += pattern( P^T V ):  dB[b][q] = sum_p P[p][b] V[p][q] for b in {q-1,q,q+1} and corners; thread per column q
-// (blockIdx.y splits the rows p; partial sums are combined with double atomics)
-__global__ void col_band_dots_kernel(const double* __restrict__ P, const double* __restrict__ V, double* __restrict__ gband, int n) {
-    int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    double a0 = 0, am = 0, ap = 0, ac = 0;   // b = q, q-1, q+1, corner
-    const bool hm = q > 0, hp = q + 1 < n, c_first = (n > 2 && q == n - 1), c_last = (n > 2 && q == 0);
-    const int rows_per = (n + gridDim.y - 1) / gridDim.y;
-    const int p_begin = blockIdx.y * rows_per, p_end = min(n, p_begin + rows_per);
-    for (int p = p_begin; p < p_end; ++p) {
-        const double* pr = P + (size_t)p * n;
-        double v = V[(size_t)p * n + q];
-        a0 += pr[q] * v;
-        if (hm) am += pr[q - 1] * v;
-        if (hp) ap += pr[q + 1] * v;
-        if (c_first) ac += pr[0] * v;        // dB[0][n-1]
-        if (c_last) ac += pr[n - 1] * v;     // dB[n-1][0]
+
+// status[0] = J_eff (powers that matter), status[1] = K_eff = min(round_up(J_eff r, 32), k32_rows), status[2] = 1 when the series
+// ended inside the J computed powers (or J = n: the reference sums exactly n powers), status[3] = J.
+__global__ void ldr_terms_kernel(int n, int r, int J, long k32_rows, double rel_tol, const double* __restrict__ colnorm, int* __restrict__ status) {
+    __shared__ double bound[1024];
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        double b = 0.0;
+        for (int i = 0; i < r; ++i) b += colnorm[(size_t)j * r + i] * colnorm[((size_t)J + j) * r + i];
+        bound[j] = b;
     }
-    atomicAdd(gband + n + q, a0);                       // di[q] = B[q][q]
-    if (hm) atomicAdd(gband + 2 * n + q - 1, am);       // B[q-1][q] = up[q-1]
-    if (hp) atomicAdd(gband + q + 1, ap);               // B[q+1][q] = lo[q+1]
-    if (c_first) atomicAdd(gband + 3 * n, ac);
-    if (c_last) atomicAdd(gband + 3 * n + 1, ac);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double mx = 0.0;
+        int terms = J, conv = (J >= n) ? 1 : 0;
+        for (int j = 0; j < J; ++j) {
+            const double b = bound[j];
+            if (j > 0 && !(b > rel_tol * mx)) { terms = j; conv = 1; break; }
+            mx = fmax(mx, b);
+        }
+        long k = ((long)terms * r + 31) / 32 * 32;
+        if (k > k32_rows) k = k32_rows;
+        status[0] = terms; status[1] = (int)k; status[2] = conv; status[3] = J;
+    }
+}
+
+// Adjoint recurrences for the CTA's columns; gband[op] += band gradient of M (atomics over CTAs), gsrc (gG or gH, n x r) += abar_0.
+// Column i takes part in the powers j < J_i = number of its rows below K_eff in the stacked operand (the GEMM rounds K up to 32).
+__global__ void __launch_bounds__(KR_THREADS)
+ldr_krylov_bwd_kernel(int n, int r, int J, int C, const double* __restrict__ bands, const double* __restrict__ K64, const float* __restrict__ dK32,
+                      long k32_rows, const int* __restrict__ status, double* __restrict__ gbands, double* __restrict__ gG, double* __restrict__ gH) {
+    extern __shared__ __align__(16) double kr_smem[];
+    const int op = blockIdx.y, c0 = blockIdx.x * C, nc = min(C, r - c0), tid = threadIdx.x;
+    const double* band = bands + (size_t)op * (3 * n + 2);
+    const double* lo = band, *di = band + n, *up = band + 2 * n;
+    const double cn0 = n > 2 ? band[3 * n] : 0.0, cn1 = n > 2 ? band[3 * n + 1] : 0.0;
+    const int k_eff = status[1];
+    double* cur = kr_smem;                       // abar_{j+1}
+    double* nxt = kr_smem + (size_t)C * n;
+    double* glo = kr_smem + (size_t)2 * C * n, *gdi = glo + n, *gup = gdi + n;
+    __shared__ double gcn[2];
+    for (int p = tid; p < n; p += KR_THREADS) { glo[p] = 0.0; gdi[p] = 0.0; gup[p] = 0.0; }
+    if (tid < 2) gcn[tid] = 0.0;
+    const double* k64 = K64 + (size_t)op * J * r * n;
+    const float* dk = dK32 + (size_t)op * k32_rows * n;
+    int jmax = 0;                                // powers of the CTA's first column (the largest count among its columns)
+    if (k_eff > c0) jmax = (k_eff - c0 + r - 1) / r;
+    if (jmax > J) jmax = J;
+    for (int e = tid; e < C * n; e += KR_THREADS) cur[e] = 0.0;
+    __syncthreads();
+    for (int j = jmax - 1; j >= 0; --j) {
+        for (int c = 0; c < nc; ++c) {
+            const bool live = (long)j * r + c0 + c < k_eff;           // uniform over the CTA
+            const double* a = cur + (size_t)c * n;                   // abar_{j+1} (zero when j is the column's last power)
+            double* w = nxt + (size_t)c * n;
+            const double* kj = k64 + ((size_t)j * r + c0 + c) * n;   // K_j
+            const float* dkj = dk + ((size_t)j * r + c0 + c) * n;
+            double c0acc = 0.0, c1acc = 0.0;
+            for (int p = tid; p < n; p += KR_THREADS) {
+                const double ap = a[p];
+                // band gradient of the step K_{j+1} = M K_j:  dM[p][p'] += abar_{j+1}[p] K_j[p']
+                const double kp = kj[p];
+                gdi[p] += ap * kp;
+                if (p > 0) glo[p] += ap * kj[p - 1];
+                if (p + 1 < n) gup[p] += ap * kj[p + 1];
+                if (p == 0) c0acc += ap * kj[n - 1];
+                if (p == n - 1) c1acc += ap * kj[0];
+                // abar_j = dK_j + M^T abar_{j+1}
+                double acc = di[p] * ap;
+                if (p + 1 < n) acc += lo[p + 1] * a[p + 1];
+                if (p > 0) acc += up[p - 1] * a[p - 1];
+                if (p == n - 1) acc += cn0 * a[0];
+                if (p == 0) acc += cn1 * a[n - 1];
+                w[p] = live ? acc + (double)dkj[p] : 0.0;
+            }
+            if (n > 2) {
+                if (tid == 0) gcn[0] += c0acc;                          // p = 0 belongs to thread 0
+                if (tid == (n - 1) % KR_THREADS) gcn[1] += c1acc;       // p = n - 1 belongs to exactly this thread
+            }
+        }
+        __syncthreads();
+        double* t = cur; cur = nxt; nxt = t;
+    }
+    // cur = abar_0 of the CTA's columns
+    double* gsrc = op == 0 ? gG : gH;
+    if (gsrc != nullptr)
+        for (int e = tid; e < nc * n; e += KR_THREADS) {
+            const int p = e / nc, c = e - p * nc;
+            gsrc[(size_t)p * r + c0 + c] += cur[(size_t)c * n + p];
+        }
+    double* gb = gbands + (size_t)op * (3 * n + 2);
+    for (int p = tid; p < n; p += KR_THREADS) {
+        if (p > 0) atomicAdd(gb + p, glo[p]);
+        atomicAdd(gb + n + p, gdi[p]);
+        if (p + 1 < n) atomicAdd(gb + 2 * n + p, gup[p]);
+    }
+    __syncthreads();
+    if (tid == 0 && n > 2) { atomicAdd(gb + 3 * n, gcn[0]); atomicAdd(gb + 3 * n + 1, gcn[1]); }
 }
 
 inline dim3 grid2(int n) { return dim3(snb::ceil_div(n, 128), n); }
@@ -225,107 +249,115 @@ __global__ void tl_dh_kernel(const float* __restrict__ dK2, float* __restrict__ 
 
 extern "C" {
 
-// Workspace (doubles) for the LDR weight build of size n with up to `max_terms` stored prefix sums.
-size_t sn_ldr_workspace_doubles(int n, int max_terms) {
-    size_t n2 = (size_t)n * n;
-    return n2 * (4 + (size_t)max_terms) + 6 * (3 * (size_t)n + 2) + 8;
+// Workspace layout (bytes, every part 256-byte aligned); J = max_terms powers are computed, K32 rows = round_up(J r, 32):
+//   bands [2][3n+2] f64 (A, B^T) | gbands [2][3n+2] f64 | scratch band [3n+2] f64 | colnorm [2][J][r] f64 | K64 [2][J][r][n] f64
+//   | K32 [2][rows][n] f32 | dK32 [2][rows][n] f32
+namespace {
+struct LdrWs {
+    size_t bands, gbands, tmpband, colnorm, k64, k32, dk32, total;
+    long rows;
+};
+inline LdrWs ldr_layout(int n, int r, int J) {
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    LdrWs w;
+    const size_t nb = 3 * (size_t)n + 2;
+    w.rows = ((long)J * r + 31) / 32 * 32;
+    if (w.rows < 32) w.rows = 32;
+    size_t off = 0;
+    w.bands = off; off = al(off + 2 * nb * 8);
+    w.gbands = off; off = al(off + 2 * nb * 8);
+    w.tmpband = off; off = al(off + nb * 8);
+    w.colnorm = off; off = al(off + 2 * (size_t)J * r * 8);
+    w.k64 = off; off = al(off + 2 * (size_t)J * r * n * 8);
+    w.k32 = off; off = al(off + 2 * (size_t)w.rows * n * 4);
+    w.dk32 = off; off = al(off + 2 * (size_t)w.rows * n * 4);
+    w.total = off;
+    return w;
+}
+}  // namespace
+
+size_t sn_ldr_workspace_bytes(int n, int r, int max_terms) {
+    if (n <= 0 || r < 0 || max_terms < 1) return 0;
+    return ldr_layout(n, r, max_terms).total;
 }
 
-// Builds W (n x n float32, row-major) from the representation (A, B: COO value arrays + slot maps; G, H: n x r
-// float64 row-major).  `slot` maps each COO entry to lo/di/up/corner (see band_gather_kernel).  Terms are summed
-// until max|T_j| <= rel_tol * max_j max|T_j| or j = n-1 or j = max_terms-1 (then returns an error).  Synchronises
-// `stream` every 8 terms to read the convergence flag.  terms_out (host) receives J+1, the number of summed terms;
-// prefix sums P_0..P_J are left in the workspace for sn_ldr_backward.
+// Builds W (n x n float32, row-major) from the representation (A, B: COO value arrays + slot maps; G, H: n x r float64
+// row-major).  `slot` maps each COO entry to lo/di/up/corner (see band_gather_kernel).  max_terms <= min(n, 1024) Krylov powers are
+// computed; status (device int[4]) receives {powers used J_eff, K_eff, converged, max_terms}: converged = 0 means the series had
+// not decayed below rel_tol within max_terms powers -- the caller re-runs with a larger max_terms (W is then a truncated sum).
+// Never synchronises; the workspace keeps what sn_ldr_backward needs.
 int sn_ldr_build_weight(int n, int r, const double* A_vals, const int32_t* A_slot, int A_nnz, const double* B_vals,
-                        const int32_t* B_slot, int B_nnz, const double* G, const double* H, double* ws, int max_terms,
-                        double rel_tol, float* W_out, int* terms_out, sn_stream_t stream) {
-    SN_CHECK_ARG(n > 0 && r >= 0 && ws && W_out && terms_out && max_terms >= 1, "ldr_build_weight: bad arguments");
+                        const int32_t* B_slot, int B_nnz, const double* G, const double* H, void* ws, int max_terms,
+                        double rel_tol, float* W_out, int* status, sn_stream_t stream) {
+    SN_CHECK_ARG(n > 0 && r >= 0 && ws && W_out && status && max_terms >= 1 && max_terms <= 1024, "ldr_build_weight: bad arguments");
+    SN_CHECK_ARG(n % 4 == 0, "ldr_build_weight: n must be a multiple of 4 (TMA row pitch of the Krylov operands), got %d", n);
+    SN_CHECK_ARG(n <= 4096, "ldr_build_weight: n = %d is too large for the shared-memory Krylov kernels and the unsplit gradient GEMMs (n <= 4096)", n);
     cudaStream_t st = snb::as_stream(stream);
-    const size_t n2 = (size_t)n * n, nb = 3 * (size_t)n + 2;
-    double* acc = ws;                 // running sum W
-    double* T = acc + n2;             // current term
-    double* tmp = T + n2;             // scratch
-    double* tmp2 = tmp + n2;
-    double* bandA = tmp2 + n2;
-    double* bandB = bandA + nb;
-    double* bandAt = bandB + nb;
-    double* bandBt = bandAt + nb;
-    unsigned long long* flag = reinterpret_cast<unsigned long long*>(bandBt + nb);   // [0] = max|T_j| bits
-    double* P = bandBt + nb + 8 + 2 * nb;   // stored prefix sums (after the flag words and the gradient bands)
-    SN_CHECK_CUDA(cudaMemsetAsync(ws, 0, (4 * n2 + 4 * nb + 8) * sizeof(double), st));
-    if (A_nnz) { band_gather_kernel<<<grid1(A_nnz), 256, 0, st>>>(A_vals, A_slot, A_nnz, bandA); SN_CHECK_LAUNCH("band_gather"); }
-    if (B_nnz) { band_gather_kernel<<<grid1(B_nnz), 256, 0, st>>>(B_vals, B_slot, B_nnz, bandB); SN_CHECK_LAUNCH("band_gather"); }
-    band_transpose_kernel<<<snb::ceil_div(n, 128), 128, 0, st>>>(bandA, bandAt, n); SN_CHECK_LAUNCH("band_transpose");
-    band_transpose_kernel<<<snb::ceil_div(n, 128), 128, 0, st>>>(bandB, bandBt, n); SN_CHECK_LAUNCH("band_transpose");
-    int terms = 0;
-    if (r > 0) {
-        ght_kernel<<<grid2(n), 128, 0, st>>>(G, H, T, n, r); SN_CHECK_LAUNCH("ght_kernel");
-        double global_max = 0.0;
-        const int limit = n < max_terms ? n : max_terms;
-        bool converged = false;
-        for (int j = 0; j < limit; ++j) {
-            accumulate_kernel<<<grid1(n2), 256, 0, st>>>(T, acc, P + (size_t)j * n2, n2, flag); SN_CHECK_LAUNCH("accumulate_kernel");
-            terms = j + 1;
-            const bool last = (j + 1 == limit);
-            if ((j & 7) == 7 || last) {
-                unsigned long long bits = 0;
-                SN_CHECK_CUDA(cudaMemcpyAsync(&bits, flag, sizeof(bits), cudaMemcpyDeviceToHost, st));
-                SN_CHECK_CUDA(cudaMemsetAsync(flag, 0, sizeof(bits), st));
-                SN_CHECK_CUDA(cudaStreamSynchronize(st));
-                double m;
-                memcpy(&m, &bits, sizeof(m));   // max |T| over the last <= 8 terms
-                if (m > global_max) global_max = m;
-                if (!(m > rel_tol * global_max) || m == 0.0) { converged = true; break; }
-            }
-            if (last) break;
-            band_left_kernel<<<grid2(n), 128, 0, st>>>(bandA, T, tmp, n); SN_CHECK_LAUNCH("band_left_kernel");
-            band_right_kernel<<<grid2(n), 128, 0, st>>>(bandB, tmp, T, n); SN_CHECK_LAUNCH("band_right_kernel");
-        }
-        SN_CHECK_ARG(converged || terms == n, "ldr_build_weight: the Krylov series did not converge within %d stored terms (n = %d); "
-                     "raise max_terms (workspace) or reduce the norm of A, B", max_terms, n);
+    const int J = max_terms < n ? max_terms : n;
+    const LdrWs L = ldr_layout(n, r, max_terms);
+    uint8_t* base = static_cast<uint8_t*>(ws);
+    const size_t nb = 3 * (size_t)n + 2, n2 = (size_t)n * n;
+    double* bands = reinterpret_cast<double*>(base + L.bands);
+    double* tmpband = reinterpret_cast<double*>(base + L.tmpband);
+    float* K32 = reinterpret_cast<float*>(base + L.k32);
+    SN_CHECK_CUDA(cudaMemsetAsync(W_out, 0, n2 * sizeof(float), st));
+    if (r == 0) {
+        SN_CHECK_CUDA(cudaMemsetAsync(status, 0, 4 * sizeof(int), st));
+        return 0;
     }
-    cast_f64_f32_kernel<<<grid1(n2), 256, 0, st>>>(acc, W_out, n2); SN_CHECK_LAUNCH("cast_f64_f32_kernel");
-    *terms_out = terms;
-    return 0;
+    SN_CHECK_CUDA(cudaMemsetAsync(bands, 0, nb * sizeof(double), st));
+    SN_CHECK_CUDA(cudaMemsetAsync(tmpband, 0, nb * sizeof(double), st));
+    if (A_nnz) { band_gather_kernel<<<grid1(A_nnz), 256, 0, st>>>(A_vals, A_slot, A_nnz, bands); SN_CHECK_LAUNCH("band_gather"); }
+    if (B_nnz) { band_gather_kernel<<<grid1(B_nnz), 256, 0, st>>>(B_vals, B_slot, B_nnz, tmpband); SN_CHECK_LAUNCH("band_gather"); }
+    band_transpose_kernel<<<snb::ceil_div(n, 128), 128, 0, st>>>(tmpband, bands + nb, n); SN_CHECK_LAUNCH("band_transpose");
+    // rows of the stacked operands beyond J r (K is rounded up to the GEMM's 32-row boxes) stay zero
+    if (L.rows > (long)J * r) {
+        for (int op = 0; op < 2; ++op)
+            SN_CHECK_CUDA(cudaMemsetAsync(K32 + ((size_t)op * L.rows + (size_t)J * r) * n, 0, (size_t)(L.rows - (long)J * r) * n * sizeof(float), st));
+    }
+    const int C = kr_cols_fwd(n);
+    const size_t smem = (size_t)2 * C * n * sizeof(double);
+    SN_CHECK_CUDA(cudaFuncSetAttribute(ldr_krylov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SN_LAUNCH("ldr_krylov_kernel", st, ldr_krylov_kernel<<<dim3(snb::ceil_div(r, C), 2), KR_THREADS, smem, st>>>(
+        n, r, J, C, bands, G, H, reinterpret_cast<double*>(base + L.k64), K32, L.rows, reinterpret_cast<double*>(base + L.colnorm)));
+    SN_LAUNCH("ldr_terms_kernel", st, ldr_terms_kernel<<<1, 256, 0, st>>>(n, r, J, L.rows, rel_tol, reinterpret_cast<double*>(base + L.colnorm), status));
+    // W[p][q] = sum_k KA[k][p] KB[k][q]: both operands MN-major, K = status[1] on the device, split-K with reductions into the zeroed W
+    return snb::gemm_f32(true, false, n, n, (int)L.rows, 1.f, K32, n, K32 + (size_t)L.rows * n, n, 1.f, W_out, n, nullptr, st, true, status + 1, nullptr);
 }
 
 // Backward of the weight build.  dW: n x n float32 (d loss / d W).  Accumulates into gA_vals / gB_vals (COO order,
-// float64), gG, gH (n x r float64).  `ws` must be the workspace sn_ldr_build_weight left behind, `terms` its terms_out.
+// float64), gG, gH (n x r float64).  `ws`, `max_terms`, `status` as left behind by sn_ldr_build_weight.
 int sn_ldr_backward(int n, int r, const float* dW, const int32_t* A_slot, int A_nnz, const int32_t* B_slot, int B_nnz,
-                    const double* G, const double* H, double* ws, int terms, double* gA_vals, double* gB_vals, double* gG,
-                    double* gH, sn_stream_t stream) {
-    SN_CHECK_ARG(n > 0 && dW && ws, "ldr_backward: bad arguments");
-    if (r == 0 || terms == 0) return 0;
+                    void* ws, int max_terms, const int* status, double* gA_vals, double* gB_vals, double* gG, double* gH, sn_stream_t stream) {
+    SN_CHECK_ARG(n > 0 && dW && ws && status && max_terms >= 1, "ldr_backward: bad arguments");
+    if (r == 0) return 0;
     cudaStream_t st = snb::as_stream(stream);
-    const size_t n2 = (size_t)n * n, nb = 3 * (size_t)n + 2;
-    double* dM = ws;                  // reuse: running sum of S_l
-    double* S = dM + n2;
-    double* tmp = S + n2;
-    double* tmp2 = tmp + n2;
-    double* bandA = tmp2 + n2;
-    double* bandB = bandA + nb;
-    double* bandAt = bandB + nb;
-    double* bandBt = bandAt + nb;
-    double* gA = bandBt + nb + 8;     // gradient bands of A and B
-    double* gB = gA + nb;
-    double* P = gB + nb;
-    SN_CHECK_CUDA(cudaMemsetAsync(dM, 0, n2 * sizeof(double), st));
-    SN_CHECK_CUDA(cudaMemsetAsync(gA, 0, 2 * nb * sizeof(double), st));
-    cast_f32_f64_kernel<<<grid1(n2), 256, 0, st>>>(dW, S, n2); SN_CHECK_LAUNCH("cast_f32_f64_kernel");
-    const int J = terms - 1;
-    for (int l = 0; l <= J; ++l) {
-        accumulate_kernel<<<grid1(n2), 256, 0, st>>>(S, dM, nullptr, n2, reinterpret_cast<unsigned long long*>(bandBt + nb)); SN_CHECK_LAUNCH("accumulate_kernel");
-        if (l == J) break;
-        const double* Pk = P + (size_t)(J - 1 - l) * n2;
-        band_right_kernel<<<grid2(n), 128, 0, st>>>(bandB, Pk, tmp, n); SN_CHECK_LAUNCH("band_right_kernel");            // Q = P B
-        row_band_dots_kernel<<<snb::ceil_div(n, 4), 128, 0, st>>>(S, tmp, gA, n); SN_CHECK_LAUNCH("row_band_dots_kernel");  // dA += pattern(S Q^T)
-        band_left_kernel<<<grid2(n), 128, 0, st>>>(bandAt, S, tmp2, n); SN_CHECK_LAUNCH("band_left_kernel");             // V = A^T S
-        col_band_dots_kernel<<<dim3(snb::ceil_div(n, 128), n >= 256 ? 64 : 1), 128, 0, st>>>(Pk, tmp2, gB, n); SN_CHECK_LAUNCH("col_band_dots_kernel"); // dB += pattern(P^T V)
-        band_right_kernel<<<grid2(n), 128, 0, st>>>(bandBt, tmp2, S, n); SN_CHECK_LAUNCH("band_right_kernel");           // S = V B^T
+    const int J = max_terms < n ? max_terms : n;
+    const LdrWs L = ldr_layout(n, r, max_terms);
+    uint8_t* base = static_cast<uint8_t*>(ws);
+    const size_t nb = 3 * (size_t)n + 2;
+    double* bands = reinterpret_cast<double*>(base + L.bands);
+    double* gbands = reinterpret_cast<double*>(base + L.gbands);
+    double* tmpband = reinterpret_cast<double*>(base + L.tmpband);
+    float* K32 = reinterpret_cast<float*>(base + L.k32);
+    float* dK32 = reinterpret_cast<float*>(base + L.dk32);
+    const float* KA = K32, *KB = K32 + (size_t)L.rows * n;
+    // dKA[k][p] = sum_q KB[k][q] dW[p][q]  (A operand K-major, B operand = dW as [N = p][K = q], K-major); rows k < K_eff only
+    if (int rc = snb::gemm_f32(false, true, (int)L.rows, n, n, 1.f, KB, n, dW, n, 0.f, dK32, n, nullptr, st, false, nullptr, status + 1)) return rc;
+    // dKB[k][q] = sum_p KA[k][p] dW[p][q]  (B operand = dW as [K = p][N = q], MN-major)
+    if (int rc = snb::gemm_f32(false, false, (int)L.rows, n, n, 1.f, KA, n, dW, n, 0.f, dK32 + (size_t)L.rows * n, n, nullptr, st, false, nullptr, status + 1)) return rc;
+    SN_CHECK_CUDA(cudaMemsetAsync(gbands, 0, 2 * nb * sizeof(double), st));
+    const int C = kr_cols_bwd(n);
+    const size_t smem = ((size_t)2 * C * n + 3 * (size_t)n) * sizeof(double);
+    SN_CHECK_CUDA(cudaFuncSetAttribute(ldr_krylov_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SN_LAUNCH("ldr_krylov_bwd_kernel", st, ldr_krylov_bwd_kernel<<<dim3(snb::ceil_div(r, C), 2), KR_THREADS, smem, st>>>(
+        n, r, J, C, bands, reinterpret_cast<const double*>(base + L.k64), dK32, L.rows, status, gbands, gG, gH));
+    if (gA_vals && A_nnz) { band_scatter_grad_kernel<<<grid1(A_nnz), 256, 0, st>>>(gbands, A_slot, A_nnz, gA_vals); SN_CHECK_LAUNCH("band_scatter_grad"); }
+    if (gB_vals && B_nnz) {
+        // the second operator is B^T: its band gradient transposed is the band gradient of B
+        band_transpose_kernel<<<snb::ceil_div(n, 128), 128, 0, st>>>(gbands + nb, tmpband, n); SN_CHECK_LAUNCH("band_transpose");
+        band_scatter_grad_kernel<<<grid1(B_nnz), 256, 0, st>>>(tmpband, B_slot, B_nnz, gB_vals); SN_CHECK_LAUNCH("band_scatter_grad");
     }
-    if (gA_vals && A_nnz) { band_scatter_grad_kernel<<<grid1(A_nnz), 256, 0, st>>>(gA, A_slot, A_nnz, gA_vals); SN_CHECK_LAUNCH("band_scatter_grad"); }
-    if (gB_vals && B_nnz) { band_scatter_grad_kernel<<<grid1(B_nnz), 256, 0, st>>>(gB, B_slot, B_nnz, gB_vals); SN_CHECK_LAUNCH("band_scatter_grad"); }
-    if (gG && gH) { dgh_kernel<<<dim3(snb::ceil_div(r, 32), n), 32, 0, st>>>(dM, G, H, gG, gH, n, r); SN_CHECK_LAUNCH("dgh_kernel"); }
     return 0;
 }
 
@@ -342,6 +374,12 @@ int sn_dense_weight_grad(const float* x, int64_t ldx, const float* gy, int64_t l
     if (grad_bias)
         if (int rc = snb::colsum_accumulate(gy, ldgy, B, n_out, grad_bias, st)) return rc;
     return snb::gemm_f32(true, false, n_out, n_in, (int)B, 1.f, gy, ldgy, x, ldx, 1.f, dW, n_in, nullptr, st, true);
+}
+
+// grad_x[B x n_in] = grad_y[B x n_out] W  (the gradient w.r.t. the input features of every layer that materialises W)
+int sn_dense_input_grad(const float* W, int n_out, int n_in, const float* gy, int64_t ldgy, float* gx, int64_t ldgx, int64_t B, sn_stream_t stream) {
+    SN_CHECK_ARG(W && gy && gx, "dense_input_grad: NULL buffer");
+    return snb::gemm_f32(false, false, (int)B, n_in, n_out, 1.f, gy, ldgy, W, n_in, 0.f, gx, ldgx, nullptr, snb::as_stream(stream));
 }
 
 // Toeplitz-like weight: W (n x n) from G (n x r), H (r x n); K1 (n x rn) and K2 (rn x n) are caller-provided scratch

@@ -342,6 +342,16 @@ int sn_psm_dense_forward(const sn_psm_dense_factor* f, int nf, const float* x, i
     // y = x W^T^T + b: W^T is stored [in_dim][out_dim]
     return snb::gemm_f32(false, false, (int)B, out_dim, in_dim, 1.f, x, ldx, prev, out_dim, 0.f, y, ldy, bias, st);
 }
+/* grad_x = grad_y W from the multiplied-out product the forward left in `prefix` (W^T = its last block, [in_dim][out_dim]) */
+int sn_psm_dense_input_grad(const sn_psm_dense_factor* f, int nf, const float* prefix, const float* grad_y, int64_t ldgy, float* grad_x,
+                            int64_t ldgx, int64_t B, int in_dim, int out_dim, sn_stream_t stream) {
+    if (int rc = check_dense_chain(f, nf, in_dim, out_dim)) return rc;
+    SN_CHECK_ARG(prefix && grad_y && grad_x, "psm_dense_input_grad: NULL buffer");
+    if (B <= 0) return 0;
+    size_t off = 0;
+    for (int k = 0; k + 1 < nf; ++k) off += (size_t)f[k].cols * out_dim;
+    return snb::gemm_f32(false, true, (int)B, in_dim, out_dim, 1.f, grad_y, ldgy, prefix + off, out_dim, 0.f, grad_x, ldgx, nullptr, snb::as_stream(stream));
+}
 /* work: sn_psm_dense_backward_floats floats; grad_vals of every factor (COO order) and grad_bias are accumulated into */
 int sn_psm_dense_backward(const sn_psm_dense_factor* f, int nf, const float* x, int64_t ldx, const float* grad_y, int64_t ldgy,
                           const float* prefix, float* work, float* grad_bias, int64_t B, int in_dim, int out_dim, sn_stream_t stream) {

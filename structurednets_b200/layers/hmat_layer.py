@@ -39,8 +39,8 @@ class _HMatFunction(torch.autograd.Function):
         layer = ctx.layer
         U, table = ctx.saved_tensors
         if ctx.needs_input_grad[0]:
-            raise RuntimeError("HMatLayer: gradient w.r.t. the input features is not implemented "
-                               "(the reference training loop never requests it, training_helpers.py:34)")
+            raise RuntimeError("HMatLayer: the leaf-by-leaf kernels do not return the gradient w.r.t. the input features; the dense-block "
+                               "path (default up to 2^26 matrix elements) does")
         grad_y = grad_y.contiguous().float()
         g = layer._prepare_grad_accumulation()
         gb = g[:layer.output_dim] if (layer.use_bias and layer.bias.requires_grad) else None
@@ -76,11 +76,15 @@ class _HMatDenseFunction(torch.autograd.Function):
     def backward(ctx, grad_y):
         layer = ctx.layer
         U, table = ctx.saved_tensors
-        if ctx.needs_input_grad[0]:
-            raise RuntimeError("HMatLayer: gradient w.r.t. the input features is not implemented "
-                               "(the reference training loop never requests it, training_helpers.py:34)")
         grad_y = grad_y.contiguous().float()
         L = _lib.lib()
+        grad_x = None
+        if ctx.needs_input_grad[0]:
+            # the dense W of this layer's last forward (a layer-wide buffer: forward -> backward without another forward in between)
+            W = layer._dense_buffer("_dev_W", U.device)
+            grad_x = torch.empty_like(U)
+            _lib.check(L.sn_dense_input_grad(_lib.ptr(W), layer.output_dim, layer.input_dim, _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(grad_x),
+                                             grad_x.stride(0), U.shape[0], _lib.stream_ptr()), "sn_dense_input_grad")
         g = layer._prepare_grad_accumulation()
         gb = g[:layer.output_dim] if (layer.use_bias and layer.bias.requires_grad) else None
         dW = layer._dense_buffer("_dev_dW", U.device)
@@ -89,7 +93,7 @@ class _HMatDenseFunction(torch.autograd.Function):
                                           layer.input_dim, _lib.ptr(gb), U.shape[0], _lib.stream_ptr()), "sn_dense_weight_grad")
         _lib.check(L.sn_hmat_project_grad(_lib.ptr(table), layer._nleaves, _lib.ptr(layer.flat_parameters()), _lib.ptr(dW), layer.output_dim,
                                           layer.input_dim, _lib.ptr(g), _lib.stream_ptr()), "sn_hmat_project_grad")
-        return None, None, None
+        return grad_x, None, None
 
 
 class HMatLayer(FlatParamsMixin, StructuredLayer):

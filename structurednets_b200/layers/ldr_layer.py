@@ -4,10 +4,10 @@
 A, B (float64 sparse COO, tridiagonal plus two corners, 3n entries) and G, H (float64, n x r); the rank
 formula and the "displacement rank < 0 -> dummy parameter, zero output" rule are kept.
 
-The weight is built by the float64 banded series of csrc/ldr_tl.cu (same matrix as the reference's
-matrix_power construction, in O(n^2) per term instead of O(n^4 log n) in total) and applied with fp32 GEMMs.
+The weight is built by csrc/ldr_tl.cu: float64 Krylov recurrences (O(n r) per power) and one tensor-core contraction
+over the powers that matter -- the same matrix as the reference's matrix_power construction (O(r n^4 log n)) -- and
+applied with fp32-accurate tensor-core GEMMs.
 """
-import os
 import pickle
 
 import numpy as np
@@ -18,8 +18,8 @@ from structurednets_b200 import _lib
 from structurednets_b200.layers.layer_helpers import get_random_glorot_uniform_matrix_torch
 from structurednets_b200.layers.structured_layer import StructuredLayer
 
-LDR_REL_TOL = 1e-24          # a Krylov term this small relative to the largest one cannot change a float64 sum
-LDR_WS_CAP_BYTES = int(float(os.environ.get("SNB200_LDR_WS_GB", "48")) * 2 ** 30)
+LDR_REL_TOL = 1e-14          # a Krylov power whose bound is this small relative to the largest one cannot change the float32 weight
+LDR_TERMS_START = 32         # powers computed by default; quadrupled (up to n) whenever the device reports "not converged"
 
 
 def get_max_ld_rank_wrt_max_nb_free_parameters(max_nb_free_parameters: int, target_shape_mat: tuple):
@@ -73,61 +73,72 @@ def band_slots(indices: torch.Tensor, n: int) -> torch.Tensor:
 
 
 class _LDRFunction(torch.autograd.Function):
+    """sn_ldr_build_weight + sn_dense_apply / sn_dense_weight_grad + sn_ldr_backward (csrc/ldr_tl.cu).  Nothing on this path
+    synchronises while a CUDA graph is being captured; outside a capture the 16-byte status word is read back after the Krylov
+    kernels so that a series longer than the powers computed is re-run with more (and ``last_nb_terms`` stays observable)."""
+
     @staticmethod
     def forward(ctx, U, bias, layer, A, Bm, G, H):
         n, r = G.shape
         dev = U.device
+        L = _lib.lib()
         slots = layer._slots(A, Bm)
         Av, Bv = A._values().contiguous(), Bm._values().contiguous()
         Gc, Hc = G.contiguous(), H.contiguous()
         assert Av.dtype == torch.float64 and Gc.dtype == torch.float64, "LDR representation matrices are float64 (SURVEY.md F4)"
         W = torch.empty((n, n), dtype=torch.float32, device=dev)
-        terms = _lib.ctypes.c_int(0)
-        max_terms = min(n, 64)
+        status = torch.zeros(4, dtype=torch.int32, device=dev)
+        capturing = torch.cuda.is_current_stream_capturing()
+        max_terms = min(n, 1024, int(layer.__dict__.get("_terms_cap", LDR_TERMS_START)))
         while True:
-            nd = _lib.lib().sn_ldr_workspace_doubles(n, max_terms)
-            if nd * 8 > LDR_WS_CAP_BYTES:
-                raise RuntimeError("LDRLayer: the Krylov series of this (A, B) does not converge within a %.0f GB workspace at n=%d; "
-                                   "set SNB200_LDR_WS_GB higher or rescale A, B" % (LDR_WS_CAP_BYTES / 2 ** 30, n))
-            ws = torch.empty(nd, dtype=torch.float64, device=dev)
-            rc = _lib.lib().sn_ldr_build_weight(n, r, _lib.ptr(Av), _lib.ptr(slots[0]), Av.numel(), _lib.ptr(Bv), _lib.ptr(slots[1]), Bv.numel(),
-                                                _lib.ptr(Gc), _lib.ptr(Hc), _lib.ptr(ws), max_terms, LDR_REL_TOL, _lib.ptr(W),
-                                                _lib.ctypes.byref(terms), _lib.stream_ptr())
-            if rc == 0:
+            ws = torch.empty(int(L.sn_ldr_workspace_bytes(n, r, max_terms)), dtype=torch.uint8, device=dev)
+            rc = L.sn_ldr_build_weight(n, r, _lib.ptr(Av), _lib.ptr(slots[0]), Av.numel(), _lib.ptr(Bv), _lib.ptr(slots[1]), Bv.numel(),
+                                       _lib.ptr(Gc), _lib.ptr(Hc), _lib.ptr(ws), max_terms, LDR_REL_TOL, _lib.ptr(W), _lib.ptr(status), _lib.stream_ptr())
+            _lib.check(rc, "sn_ldr_build_weight")
+            if capturing:
                 break
-            if max_terms >= n:
-                _lib.check(rc, "sn_ldr_build_weight")
-            max_terms = min(n, max_terms * 4)
-        layer.last_nb_terms = int(terms.value)
+            st = status.tolist()
+            layer.last_nb_terms = int(st[0])
+            if st[2] or max_terms >= min(n, 1024):
+                if not st[2]:
+                    raise RuntimeError("LDRLayer: the Krylov series of this (A, B) has not decayed after %d powers (n = %d); the operators' "
+                                       "norms are too close to (or above) 1 for the truncated construction" % (max_terms, n))
+                break
+            max_terms = min(n, 1024, max_terms * 4)
+            layer.__dict__["_terms_cap"] = max_terms
         y = torch.empty((U.shape[0], n), dtype=torch.float32, device=dev)
-        rc = _lib.lib().sn_dense_apply(_lib.ptr(W), n, n, _lib.ptr(U), U.stride(0), _lib.ptr(y), y.stride(0), _lib.ptr(bias), U.shape[0], _lib.stream_ptr())
+        rc = L.sn_dense_apply(_lib.ptr(W), n, n, _lib.ptr(U), U.stride(0), _lib.ptr(y), y.stride(0), _lib.ptr(bias), U.shape[0], _lib.stream_ptr())
         _lib.check(rc, "sn_dense_apply")
-        ctx.layer, ctx.terms, ctx.slots, ctx.has_bias = layer, int(terms.value), slots, bias is not None
-        ctx.save_for_backward(U, ws, A, Bm, Gc, Hc)
+        ctx.max_terms, ctx.slots, ctx.has_bias = max_terms, slots, bias is not None
+        ctx.save_for_backward(U, ws, status, W, A, Bm, Gc, Hc)
         return y
 
     @staticmethod
     def backward(ctx, grad_y):
-        U, ws, A, Bm, G, H = ctx.saved_tensors
-        if ctx.needs_input_grad[0]:
-            raise RuntimeError("LDRLayer: gradient w.r.t. the input features is not implemented")
+        U, ws, status, W, A, Bm, G, H = ctx.saved_tensors
         n, r = G.shape
         dev = U.device
+        L = _lib.lib()
         grad_y = grad_y.contiguous().float()
+        grad_x = None
+        if ctx.needs_input_grad[0]:
+            grad_x = torch.empty_like(U)
+            _lib.check(L.sn_dense_input_grad(_lib.ptr(W), n, n, _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(grad_x), grad_x.stride(0),
+                                             U.shape[0], _lib.stream_ptr()), "sn_dense_input_grad")
         dW = torch.zeros((n, n), dtype=torch.float32, device=dev)
         gbias = torch.zeros(n, dtype=torch.float32, device=dev) if ctx.has_bias else None
-        rc = _lib.lib().sn_dense_weight_grad(_lib.ptr(U), U.stride(0), _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(dW), n, n, _lib.ptr(gbias),
-                                             U.shape[0], _lib.stream_ptr())
+        rc = L.sn_dense_weight_grad(_lib.ptr(U), U.stride(0), _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(dW), n, n, _lib.ptr(gbias),
+                                    U.shape[0], _lib.stream_ptr())
         _lib.check(rc, "sn_dense_weight_grad")
         gA = torch.zeros(A._nnz(), dtype=torch.float64, device=dev)
         gB = torch.zeros(Bm._nnz(), dtype=torch.float64, device=dev)
         gG, gH = torch.zeros_like(G), torch.zeros_like(H)
-        rc = _lib.lib().sn_ldr_backward(n, r, _lib.ptr(dW), _lib.ptr(ctx.slots[0]), gA.numel(), _lib.ptr(ctx.slots[1]), gB.numel(), _lib.ptr(G),
-                                        _lib.ptr(H), _lib.ptr(ws), ctx.terms, _lib.ptr(gA), _lib.ptr(gB), _lib.ptr(gG), _lib.ptr(gH), _lib.stream_ptr())
+        rc = L.sn_ldr_backward(n, r, _lib.ptr(dW), _lib.ptr(ctx.slots[0]), gA.numel(), _lib.ptr(ctx.slots[1]), gB.numel(), _lib.ptr(ws),
+                               ctx.max_terms, _lib.ptr(status), _lib.ptr(gA), _lib.ptr(gB), _lib.ptr(gG), _lib.ptr(gH), _lib.stream_ptr())
         _lib.check(rc, "sn_ldr_backward")
         gAs = torch.sparse_coo_tensor(A._indices(), gA, A.shape)   # sparse grads on the parameters' own pattern (SURVEY.md F4)
         gBs = torch.sparse_coo_tensor(Bm._indices(), gB, Bm.shape)
-        return None, gbias, None, gAs, gBs, gG, gH
+        return grad_x, gbias, None, gAs, gBs, gG, gH
 
 
 class LDRLayer(StructuredLayer):
@@ -164,7 +175,7 @@ class LDRLayer(StructuredLayer):
 
     def _slots(self, A, Bm):
         cache = self.__dict__.get("_dev_slots")
-        key = (A._indices().data_ptr(), Bm._indices().data_ptr(), str(A.device))
+        key = (A._indices().data_ptr(), A._nnz(), Bm._indices().data_ptr(), Bm._nnz(), str(A.device))
         if cache is None or cache[0] != key:
             n = self.output_dim
             cache = (key, (band_slots(A._indices(), n), band_slots(Bm._indices(), n)))

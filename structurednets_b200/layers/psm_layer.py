@@ -123,9 +123,6 @@ class _PSMDenseFunction(torch.autograd.Function):
     def backward(ctx, grad_y):
         U, prefix, *factors = ctx.saved_tensors
         layer = ctx.layer
-        if ctx.needs_input_grad[0]:
-            raise RuntimeError("PSMLayer: gradient w.r.t. the input features is not implemented "
-                               "(the reference training loop never requests it, training_helpers.py:34)")
         grad_y = grad_y.contiguous().float()
         gvals = [torch.zeros(p._nnz(), dtype=torch.float32, device=U.device) for p in factors]
         gbias = torch.zeros(layer.output_dim, dtype=torch.float32, device=U.device) if ctx.has_bias else None
@@ -135,8 +132,13 @@ class _PSMDenseFunction(torch.autograd.Function):
         rc = L.sn_psm_dense_backward(arr, len(factors), _lib.ptr(U), U.stride(0), _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(prefix),
                                      _lib.ptr(work), _lib.ptr(gbias), U.shape[0], layer.input_dim, layer.output_dim, _lib.stream_ptr())
         _lib.check(rc, "sn_psm_dense_backward")
+        grad_x = None
+        if ctx.needs_input_grad[0]:
+            grad_x = torch.empty_like(U)
+            _lib.check(L.sn_psm_dense_input_grad(arr, len(factors), _lib.ptr(prefix), _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(grad_x),
+                                                 grad_x.stride(0), U.shape[0], layer.input_dim, layer.output_dim, _lib.stream_ptr()), "sn_psm_dense_input_grad")
         gf = [torch.sparse_coo_tensor(p._indices(), g, p.shape) for p, g in zip(factors, gvals)]
-        return (None, gbias, None, *gf)
+        return (grad_x, gbias, None, *gf)
 
 
 def _factor_array(patterns, params, gvals):
@@ -176,8 +178,8 @@ class _PSMFunction(torch.autograd.Function):
         U, *factors = ctx.saved_tensors
         layer = ctx.layer
         if ctx.needs_input_grad[0]:
-            raise RuntimeError("PSMLayer: gradient w.r.t. the input features is not implemented "
-                               "(the reference training loop never requests it, training_helpers.py:34)")
+            raise RuntimeError("PSMLayer: the sparse-chain kernels do not return the gradient w.r.t. the input features; the dense-product "
+                               "path does (SNB200_PSM_PATH=dense, or any batch >= 1024)")
         grad_y = grad_y.contiguous().float()
         gvals = [torch.zeros(p._nnz(), dtype=torch.float32, device=U.device) for p in factors]
         gbias = torch.zeros(layer.output_dim, dtype=torch.float32, device=U.device) if ctx.has_bias else None
@@ -295,14 +297,8 @@ class PSMLayer(StructuredLayer):
 def _factorize(weight: np.ndarray, nb_params_share: float):
     """The reference fits the factors with pyfaust's hierarchical PALM4MSA (approximators/psm_approximator.py:
     107-148), an unpinned PyPI dependency whose factorisation values no reference test pins (SURVEY.md
-    section 8c).  Without it, fall back to a budget-respecting two-factor start: the largest-magnitude entries
+    section 8c) and which is out of scope here: a budget-respecting two-factor start: the largest-magnitude entries
     of W times a sparse identity -- enough for training from scratch; pass sparse_matrices=... for anything else."""
-    try:
-        from structurednets.approximators.psm_approximator_wrapper import PSMApproximatorWrapper  # noqa: F401
-        res = PSMApproximatorWrapper().approximate(optim_mat=weight, nb_params_share=nb_params_share)
-        return res["faust_approximation"]
-    except Exception:
-        pass
     out_dim, in_dim = weight.shape
     budget = int(nb_params_share * weight.size)
     mx = max(out_dim, in_dim)

@@ -31,18 +31,21 @@ class _TLFunction(torch.autograd.Function):
                                        _lib.ptr(layer.bias if layer.use_bias else None), U.shape[0], _lib.stream_ptr())
         _lib.check(rc, "sn_dense_apply")
         ctx.layer = layer
-        ctx.save_for_backward(U, K1, K2)
+        ctx.save_for_backward(U, K1, K2, W)
         return y
 
     @staticmethod
     def backward(ctx, grad_y):
         layer = ctx.layer
-        U, K1, K2 = ctx.saved_tensors
-        if ctx.needs_input_grad[0]:
-            raise RuntimeError("TLLayer: gradient w.r.t. the input features is not implemented")
+        U, K1, K2, W = ctx.saved_tensors
         n, r = layer.G.shape
         dev = U.device
         grad_y = grad_y.contiguous().float()
+        grad_x = None
+        if ctx.needs_input_grad[0]:
+            grad_x = torch.empty_like(U)
+            _lib.check(_lib.lib().sn_dense_input_grad(_lib.ptr(W), n, n, _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(grad_x), grad_x.stride(0),
+                                                      U.shape[0], _lib.stream_ptr()), "sn_dense_input_grad")
         layer._prepare_grad_accumulation()
         dW = torch.zeros((n, n), dtype=torch.float32, device=dev)
         gb = layer.bias.grad if (layer.use_bias and layer.bias.requires_grad) else None
@@ -53,7 +56,7 @@ class _TLFunction(torch.autograd.Function):
         rc = _lib.lib().sn_tl_backward(n, r, _lib.ptr(dW), _lib.ptr(K1), _lib.ptr(K2), _lib.ptr(dK1), _lib.ptr(dK2), _lib.ptr(layer.G.grad),
                                        _lib.ptr(layer.H.grad), _lib.stream_ptr())
         _lib.check(rc, "sn_tl_backward")
-        return None, None, None
+        return grad_x, None, None
 
 
 class TLLayer(FlatParamsMixin, StructuredLayer):

@@ -177,3 +177,40 @@ def test_tl_more_than_65535_krylov_rows(built_lib):
     y = layer(torch.tensor(X, device=DEV)); (y * torch.tensor(gy, device=DEV)).sum().backward()
     assert rel_err(y.detach().cpu().numpy(), yo.detach().numpy()) < RTOL
     assert rel_err(dense_grad(layer.G), Gt.grad.numpy()) < 2 * RTOL and rel_err(dense_grad(layer.H), Ht.grad.numpy()) < 2 * RTOL
+
+
+def test_input_gradients_of_the_layers_that_materialise_their_weight(built_lib, monkeypatch):
+    """``grad_x`` is nullable in every backward; the reference gets it from autograd whenever the features
+    require a gradient (a layer in the middle of a network).  TL, LDR, H-matrix (dense-block path) and PSM (dense-product path)
+    return it from one more tensor-core GEMM; compared with autograd through the oracle."""
+    import scipy.sparse
+    from structurednets_b200.layers.psm_layer import PSMLayer
+    rng = np.random.default_rng(9090)
+
+    def check(layer, oracle_fn, n_in, n_out, B=24, tol=RTOL):
+        X = rng.uniform(-1, 1, size=(B, n_in)).astype(np.float32); gy = rng.uniform(-1, 1, size=(B, n_out)).astype(np.float32)
+        xo = torch.tensor(X, requires_grad=True)
+        (oracle_fn(xo) * torch.tensor(gy)).sum().backward()
+        lay = layer.to(DEV)
+        xd = torch.tensor(X, device=DEV, requires_grad=True)
+        (lay(xd) * torch.tensor(gy, device=DEV)).sum().backward()
+        assert xd.grad is not None and rel_err(xd.grad.cpu().numpy(), xo.grad.numpy()) < tol
+
+    n = 64
+    tl = TLLayer(n, n, 0.3)
+    check(tl, lambda x: O.tl_forward(x, tl.G.detach().cpu(), tl.H.detach().cpu(), tl.bias.detach().cpu()), n, n)
+    np.random.seed(3)
+    ldr = LDRLayer(n, n, 0.4)
+    rep = [p.detach().clone() for p in ldr.representation_matrices]
+    check(ldr, lambda x: O.ldr_forward(x, rep, ldr.bias.detach().cpu(), (n, n)), n, n, tol=1e-4)
+    monkeypatch.setenv("SNB200_HMAT_PATH", "dense")
+    hm = HMatLayer(64, 40, 0.6)
+    comps = [(c.row_range.start, c.row_range.stop, c.col_range.start, c.col_range.stop, c.left_lr.detach().clone(), c.right_lr.detach().clone())
+             for c in hm.hmatrix_components]
+    check(hm, lambda x: O.hmat_forward(x, comps, hm.bias.detach().cpu(), 40), 64, 40)
+    monkeypatch.setenv("SNB200_PSM_PATH", "dense")
+    S = [scipy.sparse.random(40, 96, density=0.1, random_state=1, format="csr"), scipy.sparse.random(96, 96, density=0.1, random_state=2, format="csr"),
+         scipy.sparse.random(96, 96, density=0.1, random_state=3, format="csr")]
+    psm = PSMLayer(96, 40, sparse_matrices=S)
+    dense = [torch.tensor(s.toarray()).float() for s in S]
+    check(psm, lambda x: O.psm_forward(x, dense, psm.bias.detach().cpu()), 96, 40)
