@@ -1,4 +1,6 @@
-"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference layers' forward passes.
+"""TEST INFRASTRUCTURE ONLY -- restatement of the reference layers' forward passes with the reference's own torch ops
+(CPU tensors in the tests and the CPU baseline; bench.py's ``gpu_aten_baseline`` leg feeds the same functions CUDA tensors, which
+is what the reference's ``use_gpu=True`` does: the same ATen ops on the device).
 
 Every function here follows one ``forward`` of ``/root/reference/src/structurednets/layers``
 op-for-op with torch CPU ops, so torch autograd supplies exactly the backward the
@@ -28,9 +30,10 @@ def sss_forward(U: torch.Tensor, A: Sequence[torch.Tensor], B: Sequence[torch.Te
     in_off = np.concatenate([[0], np.cumsum(dims_in)]).astype(int)    # sss_layer.py:93-94
     out_off = np.concatenate([[0], np.cumsum(dims_out)]).astype(int)  # sss_layer.py:96-97
     Ut = torch.transpose(U, 1, 0)
-    y = torch.zeros((int(out_off[-1]), U.shape[0]), dtype=U.dtype)    # sss_layer.py:101
-    x = torch.zeros((0, U.shape[0]), dtype=U.dtype)                   # :103
-    z = torch.zeros((0, U.shape[0]), dtype=U.dtype)                   # :104
+    dev = U.device                                                    # sss_layer.py:106-109 (`.to(device)` when use_gpu)
+    y = torch.zeros((int(out_off[-1]), U.shape[0]), dtype=U.dtype, device=dev)    # sss_layer.py:101
+    x = torch.zeros((0, U.shape[0]), dtype=U.dtype, device=dev)                   # :103
+    z = torch.zeros((0, U.shape[0]), dtype=U.dtype, device=dev)                   # :104
     for k in range(n):
         u_k = Ut[in_off[k]:in_off[k + 1], :]                                              # :114
         y[out_off[k]:out_off[k + 1], :] += torch.matmul(C[k], x) + torch.matmul(D[k], u_k)  # :115
@@ -118,7 +121,7 @@ def lr_forward(U, left_lr, right_lr, bias):
 def hmat_forward(U, components: Sequence[Tuple[int, int, int, int, torch.Tensor, torch.Tensor]], bias, output_dim: int):
     """``components``: (row_start, row_stop, col_start, col_stop, left_lr, right_lr) per leaf with
     rank > 0, in the reference's traversal order (hmat_layer.py:26-28)."""
-    res = torch.zeros((output_dim, U.shape[0]), dtype=U.dtype)                  # :35
+    res = torch.zeros((output_dim, U.shape[0]), dtype=U.dtype, device=U.device)  # :35-37 (`.to(device)` when use_gpu)
     U_T = U.T                                                                   # :39
     for (r0, r1, c0, c1, L, R) in components:
         res[r0:r1, :] += torch.matmul(L, torch.matmul(R, U_T[c0:c1, :]))        # :43

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(KR_THREADS)
 ldr_krylov_kernel(int n, int r, int J, int C, const double* __restrict__ bands, const double* __restrict__ G, const double* __restrict__ H,
                   double* __restrict__ K64, float* __restrict__ K32, long k32_rows, double* __restrict__ colnorm) {
     extern __shared__ __align__(16) double kr_smem[];
-    __shared__ double red[32];
+    __shared__ double red[8][32];
     const int op = blockIdx.y, c0 = blockIdx.x * C, nc = min(C, r - c0), tid = threadIdx.x;
     const double* band = bands + (size_t)op * (3 * n + 2);
     const double* lo = band, *di = band + n, *up = band + 2 * n;
@@ -70,34 +70,43 @@ ldr_krylov_kernel(int n, int r, int J, int C, const double* __restrict__ bands, 
     double* k64 = K64 + (size_t)op * J * r * n;
     float* k32 = K32 + (size_t)op * k32_rows * n;
     for (int j = 0; j < J; ++j) {
-        for (int c = 0; c < nc; ++c) {
-            const double* v = cur + (size_t)c * n;
-            double* w = nxt + (size_t)c * n;
-            double* o64 = k64 + ((size_t)j * r + c0 + c) * n;
-            float* o32 = k32 + ((size_t)j * r + c0 + c) * n;
-            double mx = 0.0;
-            for (int p = tid; p < n; p += KR_THREADS) {
+        // one pass over the rows for all of the CTA's columns: two barriers per power (norms, buffer swap)
+        double mx[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mx[c] = 0.0;
+        for (int p = tid; p < n; p += KR_THREADS) {
+            const double dp = di[p], lp = p > 0 ? lo[p] : 0.0, upp = p + 1 < n ? up[p] : 0.0;
+            const int pm = p > 0 ? p - 1 : 0, pp = p + 1 < n ? p + 1 : p;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (c >= nc) break;
+                const double* v = cur + (size_t)c * n;
                 const double x = v[p];
-                o64[p] = x;
-                o32[p] = (float)x;
-                mx = fmax(mx, fabs(x));
-                double acc = di[p] * x;
-                if (p > 0) acc += lo[p] * v[p - 1];
-                if (p + 1 < n) acc += up[p] * v[p + 1];
+                const size_t row = ((size_t)j * r + c0 + c) * n + p;
+                k64[row] = x;
+                k32[row] = (float)x;
+                mx[c] = fmax(mx[c], fabs(x));
+                double acc = dp * x + lp * v[pm] + upp * v[pp];
                 if (p == 0) acc += cn0 * v[n - 1];
                 if (p == n - 1) acc += cn1 * v[0];
-                w[p] = acc;
+                nxt[(size_t)c * n + p] = acc;
             }
-            for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if ((tid & 31) == 0) red[tid >> 5] = mx;
-            __syncthreads();
-            if (tid < 32) {
-                double m = red[tid];
-                for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-                if (tid == 0) colnorm[((size_t)op * J + j) * r + c0 + c] = m;
-            }
-            __syncthreads();
         }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c >= nc) break;
+            double m = mx[c];
+            for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if ((tid & 31) == 0) red[c][tid >> 5] = m;
+        }
+        __syncthreads();
+        if (tid < 32 * nc) {
+            const int c = tid >> 5;
+            double m = red[c][tid & 31];
+            for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if ((tid & 31) == 0) colnorm[((size_t)op * J + j) * r + c0 + c] = m;
+        }
+        __syncthreads();
         double* t = cur; cur = nxt; nxt = t;
     }
 }
@@ -106,10 +115,12 @@ ldr_krylov_kernel(int n, int r, int J, int C, const double* __restrict__ bands, 
 // ended inside the J computed powers (or J = n: the reference sums exactly n powers), status[3] = J.
 __global__ void ldr_terms_kernel(int n, int r, int J, long k32_rows, double rel_tol, const double* __restrict__ colnorm, int* __restrict__ status) {
     __shared__ double bound[1024];
-    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int j = warp; j < J; j += nwarps) {       // one warp per power: coalesced reads of the two norm rows
         double b = 0.0;
-        for (int i = 0; i < r; ++i) b += colnorm[(size_t)j * r + i] * colnorm[((size_t)J + j) * r + i];
-        bound[j] = b;
+        for (int i = lane; i < r; i += 32) b += colnorm[(size_t)j * r + i] * colnorm[((size_t)J + j) * r + i];
+        for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+        if (lane == 0) bound[j] = b;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -151,34 +162,35 @@ ldr_krylov_bwd_kernel(int n, int r, int J, int C, const double* __restrict__ ban
     for (int e = tid; e < C * n; e += KR_THREADS) cur[e] = 0.0;
     __syncthreads();
     for (int j = jmax - 1; j >= 0; --j) {
-        for (int c = 0; c < nc; ++c) {
-            const bool live = (long)j * r + c0 + c < k_eff;           // uniform over the CTA
-            const double* a = cur + (size_t)c * n;                   // abar_{j+1} (zero when j is the column's last power)
-            double* w = nxt + (size_t)c * n;
-            const double* kj = k64 + ((size_t)j * r + c0 + c) * n;   // K_j
-            const float* dkj = dk + ((size_t)j * r + c0 + c) * n;
-            double c0acc = 0.0, c1acc = 0.0;
-            for (int p = tid; p < n; p += KR_THREADS) {
+        double c0acc = 0.0, c1acc = 0.0;
+        for (int p = tid; p < n; p += KR_THREADS) {
+            const double dp = di[p], lnext = p + 1 < n ? lo[p + 1] : 0.0, uprev = p > 0 ? up[p - 1] : 0.0;
+            const int pm = p > 0 ? p - 1 : 0, pp = p + 1 < n ? p + 1 : p;
+            double g_lo = 0.0, g_di = 0.0, g_up = 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (c >= nc) break;
+                const bool live = (long)j * r + c0 + c < k_eff;           // uniform over the CTA
+                const double* a = cur + (size_t)c * n;                   // abar_{j+1} (zero when j is the column's last power)
+                const double* kj = k64 + ((size_t)j * r + c0 + c) * n;   // K_j
                 const double ap = a[p];
                 // band gradient of the step K_{j+1} = M K_j:  dM[p][p'] += abar_{j+1}[p] K_j[p']
-                const double kp = kj[p];
-                gdi[p] += ap * kp;
-                if (p > 0) glo[p] += ap * kj[p - 1];
-                if (p + 1 < n) gup[p] += ap * kj[p + 1];
+                g_di += ap * kj[p];
+                if (p > 0) g_lo += ap * kj[pm];
+                if (p + 1 < n) g_up += ap * kj[pp];
                 if (p == 0) c0acc += ap * kj[n - 1];
                 if (p == n - 1) c1acc += ap * kj[0];
                 // abar_j = dK_j + M^T abar_{j+1}
-                double acc = di[p] * ap;
-                if (p + 1 < n) acc += lo[p + 1] * a[p + 1];
-                if (p > 0) acc += up[p - 1] * a[p - 1];
+                double acc = dp * ap + lnext * a[pp] + uprev * a[pm];
                 if (p == n - 1) acc += cn0 * a[0];
                 if (p == 0) acc += cn1 * a[n - 1];
-                w[p] = live ? acc + (double)dkj[p] : 0.0;
+                nxt[(size_t)c * n + p] = live ? acc + (double)dk[((size_t)j * r + c0 + c) * n + p] : 0.0;
             }
-            if (n > 2) {
-                if (tid == 0) gcn[0] += c0acc;                          // p = 0 belongs to thread 0
-                if (tid == (n - 1) % KR_THREADS) gcn[1] += c1acc;       // p = n - 1 belongs to exactly this thread
-            }
+            glo[p] += g_lo; gdi[p] += g_di; gup[p] += g_up;
+        }
+        if (n > 2) {
+            if (tid == 0) gcn[0] += c0acc;                          // p = 0 belongs to thread 0
+            if (tid == (n - 1) % KR_THREADS) gcn[1] += c1acc;       // p = n - 1 belongs to exactly this thread
         }
         __syncthreads();
         double* t = cur; cur = nxt; nxt = t;
@@ -320,7 +332,7 @@ int sn_ldr_build_weight(int n, int r, const double* A_vals, const int32_t* A_slo
     SN_CHECK_CUDA(cudaFuncSetAttribute(ldr_krylov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SN_LAUNCH("ldr_krylov_kernel", st, ldr_krylov_kernel<<<dim3(snb::ceil_div(r, C), 2), KR_THREADS, smem, st>>>(
         n, r, J, C, bands, G, H, reinterpret_cast<double*>(base + L.k64), K32, L.rows, reinterpret_cast<double*>(base + L.colnorm)));
-    SN_LAUNCH("ldr_terms_kernel", st, ldr_terms_kernel<<<1, 256, 0, st>>>(n, r, J, L.rows, rel_tol, reinterpret_cast<double*>(base + L.colnorm), status));
+    SN_LAUNCH("ldr_terms_kernel", st, ldr_terms_kernel<<<1, 1024, 0, st>>>(n, r, J, L.rows, rel_tol, reinterpret_cast<double*>(base + L.colnorm), status));
     // W[p][q] = sum_k KA[k][p] KB[k][q]: both operands MN-major, K = status[1] on the device, split-K with reductions into the zeroed W
     return snb::gemm_f32(true, false, n, n, (int)L.rows, 1.f, K32, n, K32 + (size_t)L.rows * n, n, 1.f, W_out, n, nullptr, st, true, status + 1, nullptr);
 }

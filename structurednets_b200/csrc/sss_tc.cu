@@ -210,6 +210,166 @@ sss_tc_build_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// 1'. chunk matrices, four threads per column.  grid (nchunks, 2 directions, B4_SPLIT column groups).  The serial depth of kernel 1
+//     is 16 stages x a 16 x 16 matrix-vector product per thread; here lane q of a quad owns state components 4q .. 4q+3 (64 FMAs per
+//     stage), the quad all-gathers the new state with shuffles, and the columns of a (chunk, direction) are spread over B4_SPLIT CTAs
+//     (256 CTAs of 6 warps instead of 64): the kernel is latency-bound, so it gets ~5x faster.  Warps whose columns are all
+//     still "not activated" (their stages come later in the sweep) skip the stage.
+// ------------------------------------------------------------------------------------------
+constexpr int B4_SPLIT = 4;
+constexpr int B4_COLS = (COLT + B4_SPLIT - 1) / B4_SPLIT;      // 44 columns per CTA
+constexpr int B4_LD = 48;                                       // columns padded to a multiple of 4 (float4 rows in shared memory)
+constexpr int B4_THREADS = 4 * B4_LD;                           // 192: thread = (column lc = tid / 4, component quad q = tid % 4)
+static_assert(B4_COLS <= B4_LD, "column group wider than the thread block");
+
+// rows of the state matrices are read four at a time by the four lanes of a quad: 4 floats of padding after every 4 rows put the
+// lanes' 16-byte reads into different banks
+__device__ __forceinline__ int ss_off(int b, int d_in) { return b * d_in + (b >> 2) * 4; }
+__device__ __forceinline__ int ss_floats(int d_out, int d_in) { return pad4(d_out * d_in) + ((d_out + 3) >> 2) * 4; }
+
+__device__ __forceinline__ void chunk_params_async_q(float* pbuf, StageP* ptrs, const sn_sss_stage* sdesc, int nst, const float* __restrict__ params, int tid,
+                                                     int nthreads) {
+    int off = 0;
+    for (int i = 0; i < nst; ++i) {
+        const sn_sss_stage& st = sdesc[i];
+        const int n_ss = st.d_out * st.d_in, n_ys = st.out_dim * st.d_in, n_su = st.d_out * st.in_dim;
+        const int n_yu = st.off_yu >= 0 ? st.out_dim * st.in_dim : 0;
+        const int o_ss = off, o_ys = o_ss + ss_floats(st.d_out, st.d_in), o_su = o_ys + pad4(n_ys), o_yu = o_su + pad4(n_su);
+        if (tid == 0) ptrs[i] = StageP{o_ss, o_ys, o_su, o_yu};
+        for (int e = tid; e < n_ss; e += nthreads) {
+            const int b = e / st.d_in;
+            cp_async4(pbuf + o_ss + e + (b >> 2) * 4, params + st.off_ss + e);
+        }
+        for (int e = tid; e < n_ys; e += nthreads) cp_async4(pbuf + o_ys + e, params + st.off_ys + e);
+        for (int e = tid; e < n_su; e += nthreads) cp_async4(pbuf + o_su + e, params + st.off_su + e);
+        for (int e = tid; e < n_yu; e += nthreads) cp_async4(pbuf + o_yu + e, params + st.off_yu + e);
+        off = o_yu + pad4(n_yu);
+    }
+}
+
+// all-gather of the quad's four 4-component pieces: v[4k + j] = piece j of lane k of the quad
+__device__ __forceinline__ void quad_allgather(const float (&mine4)[4], float (&v)[DS], int lane) {
+    const int qb = lane & ~3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[4 * k + j] = __shfl_sync(0xffffffffu, mine4[j], qb + k);
+}
+
+// One stage for one column, quad layout: lane q computes the outputs r = q, q+4, .. (WITH_Y) and the state components 4q .. 4q+3.
+template <bool WITH_Y>
+__device__ __forceinline__ void stage_apply_q(const sn_sss_stage& st, const float* pbuf, const StageP& sp, float (&v)[DS], float (&own)[4], float (&yv)[4],
+                                              bool mine, int local, int q, int lane) {
+    const int d_in = st.d_in, d_out = st.d_out;
+    const float* ys = pbuf + sp.ys;
+    const bool wide = d_in == DS;
+    if (WITH_Y) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = q + 4 * j;
+            float acc = 0.f;
+            if (r < st.out_dim) {
+                if (wide) {
+                    acc = dot16(ys + r * DS, v);
+                } else {
+#pragma unroll
+                    for (int a = 0; a < DS; ++a)
+                        if (a < d_in) acc = fmaf(ys[r * d_in + a], v[a], acc);
+                }
+                if (mine && st.off_yu >= 0) acc += pbuf[sp.yu + r * st.in_dim + local];
+            }
+            yv[j] = acc;
+        }
+    }
+    float nv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int b = 4 * q + j;
+        float acc = 0.f;
+        if (b < d_out) {
+            const float* row = pbuf + sp.ss + ss_off(b, d_in);
+            if (wide) {
+                acc = dot16(row, v);
+            } else {
+#pragma unroll
+                for (int a = 0; a < DS; ++a)
+                    if (a < d_in) acc = fmaf(row[a], v[a], acc);
+            }
+            if (mine) acc += pbuf[sp.su + b * st.in_dim + local];
+        }
+        nv[j] = acc;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) own[j] = nv[j];       // the lane's own components stay addressable without a run-time register index
+    quad_allgather(nv, v, lane);
+}
+
+__global__ void __launch_bounds__(B4_THREADS)
+sss_tc_build4_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss_tc_chunk* __restrict__ chunks, const float* __restrict__ params,
+                     float* __restrict__ Wall, float* __restrict__ SCall) {
+    extern __shared__ __align__(16) float build_smem[];
+    __shared__ sn_sss_stage sdesc[LMAX];
+    __shared__ StageP sptr[LMAX];
+    const sn_sss_tc_chunk c = chunks[blockIdx.x];
+    const int dir = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const int lc = tid >> 2, q = tid & 3;
+    const int t = blockIdx.z * B4_COLS + lc;                 // column of the chunk: inputs first, then the 16 unit states
+    const bool active = lc < B4_COLS && t < c.ncols + DS;
+    const bool is_in = t < c.ncols;
+    const int sidx = t - c.ncols;
+    float* W = Wall + (size_t)blockIdx.x * WROWS * WCOLS;
+    float* SC = SCall + (size_t)blockIdx.x * SCF;
+    float* Phi = SC + dir * DS * DS;
+    float* Omat = SC + 2 * DS * DS + dir * PO * DS;
+    const int nst = c.k_end - c.k_begin;
+    const int col = c.col0 + t;
+    if (blockIdx.z * B4_COLS >= c.ncols + DS) return;        // no column of this group exists (uniform over the CTA)
+    if (tid < nst) sdesc[tid] = stage_of(stages, n, dir, dir == 0 ? c.k_begin + tid : c.k_end - 1 - tid);
+    __syncthreads();
+    chunk_params_async_q(build_smem, sptr, sdesc, nst, params, tid, B4_THREADS);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    float v[DS], own[4], yv[4];
+#pragma unroll
+    for (int a = 0; a < DS; ++a) v[a] = (active && !is_in && a == sidx && sidx < sdesc[0].d_in) ? 1.f : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) own[j] = (active && !is_in && 4 * q + j == sidx && sidx < sdesc[0].d_in) ? 1.f : 0.f;
+    bool activated = false;
+    for (int i = 0; i < nst; ++i) {
+        const sn_sss_stage& st = sdesc[i];
+        const int local = col - st.in_off;
+        const bool mine = active && is_in && local >= 0 && local < st.in_dim;
+        const bool live = active && (!is_in || activated || mine);
+        if (!__any_sync(0xffffffffu, live)) continue;        // every column of the warp still waits for its stage
+        stage_apply_q<true>(st, build_smem, sptr[i], v, own, yv, mine, local, q, lane);
+        const int rbase = st.out_off - c.row0;
+        const bool wr = dir == 0 ? (activated || mine) : activated;
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = q + 4 * j;
+                if (r >= st.out_dim) break;
+                if (is_in) {
+                    if (wr) store_hi_lo(W, rbase + r, t, yv[j]);
+                } else {
+                    Omat[(rbase + r) * DS + sidx] = yv[j];
+                }
+            }
+        }
+        if (mine) activated = true;
+    }
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int b = 4 * q + j;
+            if (is_in) store_hi_lo(W, PO + dir * DS + b, t, own[j]);
+            else Phi[b * DS + sidx] = own[j];
+        }
+    }
+}
+
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);   // round to nearest tf32 (ties away), finite inputs
     // lo is rounded too: the tensor core truncates its operands, and a truncated remainder biases every product towards zero
@@ -2109,6 +2269,172 @@ sss_tc_build_red_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// 6'. chain rule through the chunk-matrix construction, four threads per column, reductions fused.  grid (nchunks, 2, B4_SPLIT).
+//     Phase 1 replays the construction keeping the state entering every stage in shared memory (V[stage][16][column]); phase 2 walks
+//     the stages backwards (lane q of a quad owns adjoint components 4q .. 4q+3, all-gather by shuffles) and, per stage, reduces
+//     d_ss[b][a] = sum_t lam_t[b] v_t[a] and d_ys[r][a] = sum_t g_t[r] v_t[a] over the CTA's columns straight from shared memory
+//     (one atomic per parameter and column group) -- the 37 MB V / LAM / GY scratch round trip of kernels 6a + 6b is gone.
+// ------------------------------------------------------------------------------------------
+constexpr int BB4_V = LMAX * DS * B4_LD;            // floats: V[stage][a][lc]
+constexpr int BB4_DM = 64 * B4_LD;                  // the CTA's columns of the chunk's dM tile
+constexpr int BB4_X = 2 * (DS + SOUT_MAX) * B4_LD;  // double-buffered [lam (16 rows) ; g (16 rows)][lc]
+constexpr int BB4_FIXED = BB4_V + BB4_DM + BB4_X;
+
+__global__ void __launch_bounds__(B4_THREADS)
+sss_tc_build_bwd4_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss_tc_chunk* __restrict__ chunks, const float* __restrict__ params,
+                         const float* __restrict__ dMall, float* __restrict__ gparams) {
+    extern __shared__ __align__(16) float build_smem[];
+    __shared__ sn_sss_stage sdesc[LMAX];
+    __shared__ StageP sptr[LMAX];
+    float* Vs = build_smem;
+    float* dMs = Vs + BB4_V;
+    float* Xs = dMs + BB4_DM;
+    float* pbuf = Xs + BB4_X;
+    const sn_sss_tc_chunk c = chunks[blockIdx.x];
+    const int dir = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const int lc = tid >> 2, q = tid & 3;
+    const int t = blockIdx.z * B4_COLS + lc;
+    const bool active = lc < B4_COLS && t < c.ncols + DS;
+    const bool is_in = t < c.ncols;
+    const int sidx = t - c.ncols;
+    const int nst = c.k_end - c.k_begin;
+    const int col = c.col0 + t;
+    if (blockIdx.z * B4_COLS >= c.ncols + DS) return;
+    if (tid < nst) sdesc[tid] = stage_of(stages, n, dir, dir == 0 ? c.k_begin + tid : c.k_end - 1 - tid);
+    {
+        // the CTA's columns of dM (64 x 192 per chunk): input column t, or the state column nkb * 32 + dir * 16 + sidx
+        const float* src = dMall + (size_t)blockIdx.x * 64 * DMC;
+        for (int e = tid; e < 64 * B4_LD; e += B4_THREADS) {
+            const int row = e / B4_LD, l = e - row * B4_LD;
+            const int tt = blockIdx.z * B4_COLS + l;
+            const bool ok = l < B4_COLS && tt < c.ncols + DS;
+            const int cidx = tt < c.ncols ? tt : c.nkb * KBW + dir * DS + (tt - c.ncols);
+            dMs[e] = ok ? __ldg(src + row * DMC + cidx) : 0.f;
+        }
+    }
+    __syncthreads();
+    chunk_params_async_q(pbuf, sptr, sdesc, nst, params, tid, B4_THREADS);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+
+    float v[DS], own[4], yv[4];
+#pragma unroll
+    for (int a = 0; a < DS; ++a) v[a] = (active && !is_in && a == sidx && sidx < sdesc[0].d_in) ? 1.f : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) own[j] = (active && !is_in && 4 * q + j == sidx && sidx < sdesc[0].d_in) ? 1.f : 0.f;
+    int my_i = -1;
+    // phase 1: replay the construction, keeping the state that enters every stage
+    {
+        bool activated = false;
+        for (int i = 0; i < nst; ++i) {
+            const sn_sss_stage& st = sdesc[i];
+            const int local = col - st.in_off;
+            const bool mine = active && is_in && local >= 0 && local < st.in_dim;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Vs[(i * DS + 4 * q + j) * B4_LD + lc] = own[j];
+            const bool live = active && (!is_in || activated || mine);
+            if (__any_sync(0xffffffffu, live)) stage_apply_q<false>(st, pbuf, sptr[i], v, own, yv, mine, local, q, lane);
+            if (mine) { my_i = i; activated = true; }
+        }
+    }
+    // adjoint of the state leaving the last stage: the dR / dPhi rows of dM
+    float lam[DS], lown[4];
+#pragma unroll
+    for (int b = 0; b < DS; ++b) lam[b] = dMs[(PO + dir * DS + b) * B4_LD + lc];      // zero for inactive columns
+#pragma unroll
+    for (int j = 0; j < 4; ++j) lown[j] = dMs[(PO + dir * DS + 4 * q + j) * B4_LD + lc];
+    // phase 2: stages backwards
+    for (int i = nst - 1; i >= 0; --i) {
+        const sn_sss_stage& st = sdesc[i];
+        const StageP& ps = sptr[i];
+        const int local = col - st.in_off;
+        const bool mine = (i == my_i);
+        const bool before = is_in ? (my_i >= 0 && my_i < i) : true;
+        const bool support = active && (is_in ? (dir == 0 ? (before || mine) : before) : true);
+        const int rbase = st.out_off - c.row0;
+        float* Xb = Xs + (i & 1) * (DS + SOUT_MAX) * B4_LD;
+        float g[SOUT_MAX], gown[4];
+#pragma unroll
+        for (int r = 0; r < SOUT_MAX; ++r) g[r] = (r < st.out_dim && support) ? dMs[(rbase + r) * B4_LD + lc] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gown[j] = (q + 4 * j < st.out_dim && support) ? dMs[(rbase + q + 4 * j) * B4_LD + lc] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            Xb[(4 * q + j) * B4_LD + lc] = lown[j];
+            Xb[(DS + q + 4 * j) * B4_LD + lc] = gown[j];
+        }
+        if (mine) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int b = 4 * q + j;
+                if (b < st.d_out) gparams[st.off_su + b * st.in_dim + local] += lown[j];
+            }
+            if (st.off_yu >= 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = q + 4 * j;
+                    if (r < st.out_dim) gparams[st.off_yu + r * st.in_dim + local] += gown[j];
+                }
+            }
+        }
+        // lambda entering the stage, components a = 4q .. 4q+3: ss^T lam + ys^T g
+        float nl[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* ys = pbuf + ps.ys;
+        if (st.d_in == DS) {
+#pragma unroll
+            for (int b = 0; b < DS; ++b) {
+                if (b >= st.d_out) break;
+                const float4 m = *reinterpret_cast<const float4*>(pbuf + ps.ss + ss_off(b, DS) + 4 * q);
+                nl[0] = fmaf(m.x, lam[b], nl[0]); nl[1] = fmaf(m.y, lam[b], nl[1]); nl[2] = fmaf(m.z, lam[b], nl[2]); nl[3] = fmaf(m.w, lam[b], nl[3]);
+            }
+#pragma unroll
+            for (int r = 0; r < SOUT_MAX; ++r) {
+                if (r >= st.out_dim) break;
+                const float4 m = *reinterpret_cast<const float4*>(ys + r * DS + 4 * q);
+                nl[0] = fmaf(m.x, g[r], nl[0]); nl[1] = fmaf(m.y, g[r], nl[1]); nl[2] = fmaf(m.z, g[r], nl[2]); nl[3] = fmaf(m.w, g[r], nl[3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int a = 4 * q + j;
+                if (a >= st.d_in) continue;
+                float acc = 0.f;
+#pragma unroll
+                for (int b = 0; b < DS; ++b)
+                    if (b < st.d_out) acc = fmaf(pbuf[ps.ss + ss_off(b, st.d_in) + a], lam[b], acc);
+#pragma unroll
+                for (int r = 0; r < SOUT_MAX; ++r)
+                    if (r < st.out_dim) acc = fmaf(ys[r * st.d_in + a], g[r], acc);
+                nl[j] = acc;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) lown[j] = nl[j];
+        quad_allgather(nl, lam, lane);
+        __syncthreads();      // Xb complete (the other buffer was last read before the previous iteration's barrier)
+        // reductions over the CTA's columns: rows 0..15 = d_ss, rows 16.. = d_ys
+        const float* Vi = Vs + (size_t)i * DS * B4_LD;
+        const int nout = (DS + st.out_dim) * DS;
+        for (int o = tid; o < nout; o += B4_THREADS) {
+            const int rowi = o >> 4, a = o & 15;
+            if (a >= st.d_in || (rowi < DS && rowi >= st.d_out)) continue;
+            const float4* xr = reinterpret_cast<const float4*>(Xb + rowi * B4_LD);
+            const float4* vr = reinterpret_cast<const float4*>(Vi + a * B4_LD);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < B4_LD / 4; ++k) {
+                const float4 xv = xr[k], vv = vr[k];
+                a0 = fmaf(xv.x, vv.x, a0); a1 = fmaf(xv.y, vv.y, a1); a2 = fmaf(xv.z, vv.z, a2); a3 = fmaf(xv.w, vv.w, a3);
+            }
+            const float acc = (a0 + a1) + (a2 + a3);
+            if (rowi < DS) atomicAdd(gparams + st.off_ss + rowi * st.d_in + a, acc);
+            else atomicAdd(gparams + st.off_ys + (rowi - DS) * st.d_in + a, acc);
+        }
+    }
+}
+
 int check_tc_plan(const sn_sss_tc_plan* p) {
     SN_CHECK_ARG(p != nullptr, "sss_tc: NULL plan");
     SN_CHECK_ARG(p->nb_states > 0 && p->input_dim > 0 && p->output_dim > 0 && p->nchunks > 0, "sss_tc: non-positive plan dimension");
@@ -2150,6 +2476,12 @@ bool use_tc_chain(int64_t B) {
     return B >= 10240;
 }
 
+// build / build-backward with four threads per column (default) or the one-thread-per-column kernels (SNB200_SSS_BUILD=col)
+bool use_quad_build() {
+    const char* e = getenv("SNB200_SSS_BUILD");
+    return !(e != nullptr && e[0] == 'c');
+}
+
 // SIMT scans: split by direction (+ a parallel output kernel) by default; SNB200_SSS_SPLIT_SCANS=0 keeps the single-kernel scans
 bool use_split_scans(int64_t B) {
     (void)B;
@@ -2180,9 +2512,15 @@ int sn_sss_tc_build(const sn_sss_tc_plan* p, const float* params, float* coef, s
     SN_CHECK_ARG(params && coef, "sss_tc_build: NULL buffer");
     float* W = coef;
     float* SC = coef + (size_t)p->nchunks * WROWS * WCOLS;
-    const size_t bsm = (size_t)p->chunk_param_floats * sizeof(float);
-    SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
-    SN_LAUNCH("sss_tc_build_kernel", snb::as_stream(stream), sss_tc_build_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, bsm, snb::as_stream(stream)>>>(p->stages, p->nb_states, p->chunks, params, W, SC));
+    if (use_quad_build()) {
+        const size_t bsm = ((size_t)p->chunk_param_floats + 4 * LMAX * 4) * sizeof(float);    // + the quad padding of the state matrices
+        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+        SN_LAUNCH("sss_tc_build4_kernel", snb::as_stream(stream), sss_tc_build4_kernel<<<dim3(p->nchunks, 2, B4_SPLIT), B4_THREADS, bsm, snb::as_stream(stream)>>>(p->stages, p->nb_states, p->chunks, params, W, SC));
+    } else {
+        const size_t bsm = (size_t)p->chunk_param_floats * sizeof(float);
+        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+        SN_LAUNCH("sss_tc_build_kernel", snb::as_stream(stream), sss_tc_build_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, bsm, snb::as_stream(stream)>>>(p->stages, p->nb_states, p->chunks, params, W, SC));
+    }
     float* CW = SC + (size_t)p->nchunks * SCF;
     SN_LAUNCH("sss_tc_pack_chain_kernel", snb::as_stream(stream), sss_tc_pack_chain_kernel<<<dim3(p->nchunks, 4), 256, 0, snb::as_stream(stream)>>>(SC, CW));
     return 0;
@@ -2289,6 +2627,12 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     if (nsplit < 1) nsplit = 1;
     SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_grad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
     SN_LAUNCH("sss_tc_grad_gemm_kernel", st, sss_tc_grad_gemm_kernel<<<dim3(nsplit, p->nchunks), G2_THREADS, G2_SMEM, st>>>(mx, mg, ml, ms, p->chunks, (long)B, dM));
+    const size_t bsm4 = ((size_t)BB4_FIXED + p->chunk_param_floats + 4 * LMAX * 4) * sizeof(float);
+    if (use_quad_build() && bsm4 <= 227 * 1024) {
+        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm4));
+        SN_LAUNCH("sss_tc_build_bwd4_kernel", st, sss_tc_build_bwd4_kernel<<<dim3(p->nchunks, 2, B4_SPLIT), B4_THREADS, bsm4, st>>>(p->stages, p->nb_states, p->chunks, params, dM, grad_params));
+        return 0;
+    }
     const size_t bsm = ((size_t)64 * DMC + p->chunk_param_floats) * sizeof(float);
     SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
     SN_LAUNCH("sss_tc_build_bwd_kernel", st, sss_tc_build_bwd_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, bsm, st>>>(p->stages, p->nb_states, p->chunks, params, dM, scratch, grad_params));

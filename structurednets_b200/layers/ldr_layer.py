@@ -100,6 +100,8 @@ class _LDRFunction(torch.autograd.Function):
             st = status.tolist()
             layer.last_nb_terms = int(st[0])
             if st[2] or max_terms >= min(n, 1024):
+                if st[2]:   # next call computes a few powers more than this one needed, not LDR_TERMS_START
+                    layer.__dict__["_terms_cap"] = min(n, 1024, max(8, (int(st[0]) + 4 + 3) // 4 * 4))
                 if not st[2]:
                     raise RuntimeError("LDRLayer: the Krylov series of this (A, B) has not decayed after %d powers (n = %d); the operators' "
                                        "norms are too close to (or above) 1 for the truncated construction" % (max_terms, n))
