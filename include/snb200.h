@@ -269,6 +269,18 @@ int sn_tl_build_weight(int n, int r, const float* G, const float* H, float* K1, 
 int sn_tl_backward(int n, int r, const float* dW, const float* K1, const float* K2, float* dK1, float* dK2, float* gG, float* gH,
                    sn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training-loop call sites (reference training_helpers.py:57-73, 139-153): fused loss + accuracy + logit gradient, and optimizer
+ * steps over a layer's flat parameter / gradient buffers (csrc/train.cu).  loss_sum / correct are accumulated into.
+ * ------------------------------------------------------------------------------------------ */
+int sn_ce_loss(const float* logits, int64_t ld, const int64_t* targets, int64_t B, int C, float* loss_sum, int* correct,
+               float* grad_logits /* nullable */, int64_t ldg, sn_stream_t stream);
+int sn_mse_loss(const float* x, int64_t ld, const float* target, int64_t ldt, int64_t B, int C, float* loss_sum, int* correct,
+                float* grad_x /* nullable */, int64_t ldg, sn_stream_t stream);
+int sn_flat_sgd(float* params, const float* grads, int64_t n, float lr, float grad_scale, sn_stream_t stream);
+int sn_flat_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                 float eps, float grad_scale, int* step_dev /* nullable */, int step_host, sn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,6 +141,15 @@ def _declare(lib):
     lib.sn_lr_tc_forward.argtypes = [vp, i64, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp]
     lib.sn_lr_tc_backward.restype = c_int
     lib.sn_lr_tc_backward.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, i64, i32, i32, i32, vp]
+    f32 = ctypes.c_float
+    lib.sn_ce_loss.restype = c_int
+    lib.sn_ce_loss.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i64, vp]
+    lib.sn_mse_loss.restype = c_int
+    lib.sn_mse_loss.argtypes = [vp, i64, vp, i64, i64, i32, vp, vp, vp, i64, vp]
+    lib.sn_flat_sgd.restype = c_int
+    lib.sn_flat_sgd.argtypes = [vp, vp, i64, f32, f32, vp]
+    lib.sn_flat_adam.restype = c_int
+    lib.sn_flat_adam.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp, i32, vp]
     for name, fn in _EXTRA_DECLS:
         fn(lib)
 

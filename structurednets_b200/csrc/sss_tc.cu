@@ -211,63 +211,97 @@ sss_tc_build_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss
 }
 
 // ------------------------------------------------------------------------------------------
-// 1'. chunk matrices, four threads per column.  grid (nchunks, 2 directions, B4_SPLIT column groups).  The serial depth of kernel 1
-//     is 16 stages x a 16 x 16 matrix-vector product per thread; here lane q of a quad owns state components 4q .. 4q+3 (64 FMAs per
-//     stage), the quad all-gathers the new state with shuffles, and the columns of a (chunk, direction) are spread over B4_SPLIT CTAs
-//     (256 CTAs of 6 warps instead of 64): the kernel is latency-bound, so it gets ~5x faster.  Warps whose columns are all
-//     still "not activated" (their stages come later in the sweep) skip the stage.
+// 1'. chunk matrices, B4_LPC threads per column.  grid (nchunks, 2 directions, B4_SPLIT column groups).  The serial depth of kernel 1
+//     is 16 stages x a 16 x 16 matrix-vector product per thread, and it ran 1.5 warps per scheduler: pure instruction latency.  Here
+//     lane o of a group of B4_LPC lanes owns 16 / B4_LPC state components, the group all-gathers the new state with shuffles, and
+//     the columns of a (chunk, direction) are spread over B4_SPLIT CTAs: 4-16x the warps, about the same number of instructions.
+//     Warps whose columns are all still "not activated" (their stages come later in the sweep) skip the stage.
 // ------------------------------------------------------------------------------------------
+#ifndef SN_B4_LPC
+#define SN_B4_LPC 16
+#endif
+constexpr int B4_LPC = SN_B4_LPC;                               // lanes per column: 4, 8 or 16
+constexpr int B4_NC = DS / B4_LPC;                              // state components (and output rows) per lane
 constexpr int B4_SPLIT = 4;
 constexpr int B4_COLS = (COLT + B4_SPLIT - 1) / B4_SPLIT;      // 44 columns per CTA
-constexpr int B4_LD = 48;                                       // columns padded to a multiple of 4 (float4 rows in shared memory)
-constexpr int B4_THREADS = 4 * B4_LD;                           // 192: thread = (column lc = tid / 4, component quad q = tid % 4)
-static_assert(B4_COLS <= B4_LD, "column group wider than the thread block");
+constexpr int B4_LD = 52;                                       // shared-memory row pitch (floats): a multiple of 4 with LD mod 32 = 20, so the
+                                                                // float4 row reads of 8 consecutive rows fall into 8 different bank groups
+constexpr int B4_THREADS = B4_LPC * ((B4_COLS * B4_LPC + 31) / 32 * 32 / B4_LPC);   // whole warps
+constexpr int B4_TCOLS = B4_THREADS / B4_LPC;                   // columns the thread block has lanes for (>= B4_COLS)
+static_assert(B4_LPC == 4 || B4_LPC == 8 || B4_LPC == 16, "lanes per column");
+static_assert(B4_TCOLS <= B4_LD && B4_COLS <= B4_TCOLS, "column group wider than the shared-memory rows");
 
-// rows of the state matrices are read four at a time by the four lanes of a quad: 4 floats of padding after every 4 rows put the
-// lanes' 16-byte reads into different banks
-__device__ __forceinline__ int ss_off(int b, int d_in) { return b * d_in + (b >> 2) * 4; }
-__device__ __forceinline__ int ss_floats(int d_out, int d_in) { return pad4(d_out * d_in) + ((d_out + 3) >> 2) * 4; }
+// rows of the state matrices are read B4_NC at a time by the lanes of a column group: 4 floats of padding after every B4_NC rows put
+// the lanes' 16-byte reads into different banks
+__device__ __forceinline__ int ss_off(int b, int d_in) { return b * d_in + (b / B4_NC) * 4; }
+__device__ __forceinline__ int ss_floats(int d_out, int d_in) { return pad4(d_out * d_in) + ((d_out + B4_NC - 1) / B4_NC) * 4; }
 
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// n floats, 16 bytes at a time when source and count allow it (the destination always starts on a 16-byte boundary)
+__device__ __forceinline__ void copy_async(float* dst, const float* __restrict__ src, int nfl, int tid, int nthreads) {
+    if (((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (nfl & 3) == 0) {
+        for (int e = tid; e < (nfl >> 2); e += nthreads) cp_async16(dst + 4 * e, src + 4 * e);
+    } else {
+        for (int e = tid; e < nfl; e += nthreads) cp_async4(dst + e, src + e);
+    }
+}
 __device__ __forceinline__ void chunk_params_async_q(float* pbuf, StageP* ptrs, const sn_sss_stage* sdesc, int nst, const float* __restrict__ params, int tid,
                                                      int nthreads) {
     int off = 0;
     for (int i = 0; i < nst; ++i) {
         const sn_sss_stage& st = sdesc[i];
-        const int n_ss = st.d_out * st.d_in, n_ys = st.out_dim * st.d_in, n_su = st.d_out * st.in_dim;
+        const int n_ys = st.out_dim * st.d_in, n_su = st.d_out * st.in_dim;
         const int n_yu = st.off_yu >= 0 ? st.out_dim * st.in_dim : 0;
         const int o_ss = off, o_ys = o_ss + ss_floats(st.d_out, st.d_in), o_su = o_ys + pad4(n_ys), o_yu = o_su + pad4(n_su);
         if (tid == 0) ptrs[i] = StageP{o_ss, o_ys, o_su, o_yu};
-        for (int e = tid; e < n_ss; e += nthreads) {
-            const int b = e / st.d_in;
-            cp_async4(pbuf + o_ss + e + (b >> 2) * 4, params + st.off_ss + e);
+        // state matrix: groups of B4_NC rows are contiguous in the source and in the padded destination
+        const int grp = B4_NC * st.d_in;
+        if (grp > 0) {
+            const int ngrp = st.d_out / B4_NC, rest = (st.d_out - ngrp * B4_NC) * st.d_in;
+            if ((grp & 3) == 0 && ((reinterpret_cast<uintptr_t>(params + st.off_ss) & 15) == 0)) {
+                const int per = grp >> 2;
+                for (int e = tid; e < ngrp * per; e += nthreads) {
+                    const int g = e / per, w = e - g * per;
+                    cp_async16(pbuf + o_ss + g * (grp + 4) + 4 * w, params + st.off_ss + g * grp + 4 * w);
+                }
+            } else {
+                for (int e = tid; e < ngrp * grp; e += nthreads) {
+                    const int g = e / grp;
+                    cp_async4(pbuf + o_ss + e + 4 * g, params + st.off_ss + e);
+                }
+            }
+            for (int e = tid; e < rest; e += nthreads) cp_async4(pbuf + o_ss + ngrp * (grp + 4) + e, params + st.off_ss + ngrp * grp + e);
         }
-        for (int e = tid; e < n_ys; e += nthreads) cp_async4(pbuf + o_ys + e, params + st.off_ys + e);
-        for (int e = tid; e < n_su; e += nthreads) cp_async4(pbuf + o_su + e, params + st.off_su + e);
-        for (int e = tid; e < n_yu; e += nthreads) cp_async4(pbuf + o_yu + e, params + st.off_yu + e);
+        copy_async(pbuf + o_ys, params + st.off_ys, n_ys, tid, nthreads);
+        copy_async(pbuf + o_su, params + st.off_su, n_su, tid, nthreads);
+        copy_async(pbuf + o_yu, params + st.off_yu, n_yu, tid, nthreads);
         off = o_yu + pad4(n_yu);
     }
 }
 
-// all-gather of the quad's four 4-component pieces: v[4k + j] = piece j of lane k of the quad
-__device__ __forceinline__ void quad_allgather(const float (&mine4)[4], float (&v)[DS], int lane) {
-    const int qb = lane & ~3;
+// all-gather inside a column group: v[B4_NC k + j] = piece j of lane k of the group
+__device__ __forceinline__ void group_allgather(const float (&mine)[B4_NC], float (&v)[DS], int lane) {
+    const int gb = lane & ~(B4_LPC - 1);
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < B4_LPC; ++k)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[4 * k + j] = __shfl_sync(0xffffffffu, mine4[j], qb + k);
+        for (int j = 0; j < B4_NC; ++j) v[B4_NC * k + j] = __shfl_sync(0xffffffffu, mine[j], gb + k);
 }
 
-// One stage for one column, quad layout: lane q computes the outputs r = q, q+4, .. (WITH_Y) and the state components 4q .. 4q+3.
+// One stage for one column: lane o of the group computes the outputs r = o, o + LPC, .. (WITH_Y) and the state components
+// B4_NC o .. B4_NC o + B4_NC - 1, which it also keeps in `own` (addressable without a run-time register index).
 template <bool WITH_Y>
-__device__ __forceinline__ void stage_apply_q(const sn_sss_stage& st, const float* pbuf, const StageP& sp, float (&v)[DS], float (&own)[4], float (&yv)[4],
-                                              bool mine, int local, int q, int lane) {
+__device__ __forceinline__ void stage_apply_q(const sn_sss_stage& st, const float* pbuf, const StageP& sp, float (&v)[DS], float (&own)[B4_NC], float (&yv)[B4_NC],
+                                              bool mine, int local, int o, int lane) {
     const int d_in = st.d_in, d_out = st.d_out;
     const float* ys = pbuf + sp.ys;
     const bool wide = d_in == DS;
     if (WITH_Y) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int r = q + 4 * j;
+        for (int j = 0; j < B4_NC; ++j) {
+            const int r = o + B4_LPC * j;
             float acc = 0.f;
             if (r < st.out_dim) {
                 if (wide) {
@@ -282,10 +316,9 @@ __device__ __forceinline__ void stage_apply_q(const sn_sss_stage& st, const floa
             yv[j] = acc;
         }
     }
-    float nv[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int b = 4 * q + j;
+    for (int j = 0; j < B4_NC; ++j) {
+        const int b = B4_NC * o + j;
         float acc = 0.f;
         if (b < d_out) {
             const float* row = pbuf + sp.ss + ss_off(b, d_in);
@@ -298,11 +331,9 @@ __device__ __forceinline__ void stage_apply_q(const sn_sss_stage& st, const floa
             }
             if (mine) acc += pbuf[sp.su + b * st.in_dim + local];
         }
-        nv[j] = acc;
+        own[j] = acc;
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) own[j] = nv[j];       // the lane's own components stay addressable without a run-time register index
-    quad_allgather(nv, v, lane);
+    group_allgather(own, v, lane);
 }
 
 __global__ void __launch_bounds__(B4_THREADS)
@@ -313,7 +344,7 @@ sss_tc_build4_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_ss
     __shared__ StageP sptr[LMAX];
     const sn_sss_tc_chunk c = chunks[blockIdx.x];
     const int dir = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
-    const int lc = tid >> 2, q = tid & 3;
+    const int lc = tid / B4_LPC, o = tid % B4_LPC;
     const int t = blockIdx.z * B4_COLS + lc;                 // column of the chunk: inputs first, then the 16 unit states
     const bool active = lc < B4_COLS && t < c.ncols + DS;
     const bool is_in = t < c.ncols;
@@ -331,11 +362,11 @@ sss_tc_build4_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_ss
     cp_async_commit();
     cp_async_wait_all();
     __syncthreads();
-    float v[DS], own[4], yv[4];
+    float v[DS], own[B4_NC], yv[B4_NC];
 #pragma unroll
     for (int a = 0; a < DS; ++a) v[a] = (active && !is_in && a == sidx && sidx < sdesc[0].d_in) ? 1.f : 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) own[j] = (active && !is_in && 4 * q + j == sidx && sidx < sdesc[0].d_in) ? 1.f : 0.f;
+    for (int j = 0; j < B4_NC; ++j) own[j] = (active && !is_in && B4_NC * o + j == sidx && sidx < sdesc[0].d_in) ? 1.f : 0.f;
     bool activated = false;
     for (int i = 0; i < nst; ++i) {
         const sn_sss_stage& st = sdesc[i];
@@ -343,13 +374,13 @@ sss_tc_build4_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_ss
         const bool mine = active && is_in && local >= 0 && local < st.in_dim;
         const bool live = active && (!is_in || activated || mine);
         if (!__any_sync(0xffffffffu, live)) continue;        // every column of the warp still waits for its stage
-        stage_apply_q<true>(st, build_smem, sptr[i], v, own, yv, mine, local, q, lane);
+        stage_apply_q<true>(st, build_smem, sptr[i], v, own, yv, mine, local, o, lane);
         const int rbase = st.out_off - c.row0;
         const bool wr = dir == 0 ? (activated || mine) : activated;
         if (active) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int r = q + 4 * j;
+            for (int j = 0; j < B4_NC; ++j) {
+                const int r = o + B4_LPC * j;
                 if (r >= st.out_dim) break;
                 if (is_in) {
                     if (wr) store_hi_lo(W, rbase + r, t, yv[j]);
@@ -362,8 +393,8 @@ sss_tc_build4_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_ss
     }
     if (active) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int b = 4 * q + j;
+        for (int j = 0; j < B4_NC; ++j) {
+            const int b = B4_NC * o + j;
             if (is_in) store_hi_lo(W, PO + dir * DS + b, t, own[j]);
             else Phi[b * DS + sidx] = own[j];
         }
@@ -2270,11 +2301,11 @@ sss_tc_build_red_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn
 }
 
 // ------------------------------------------------------------------------------------------
-// 6'. chain rule through the chunk-matrix construction, four threads per column, reductions fused.  grid (nchunks, 2, B4_SPLIT).
+// 6'. chain rule through the chunk-matrix construction, B4_LPC threads per column, reductions fused.  grid (nchunks, 2, B4_SPLIT).
 //     Phase 1 replays the construction keeping the state entering every stage in shared memory (V[stage][16][column]); phase 2 walks
-//     the stages backwards (lane q of a quad owns adjoint components 4q .. 4q+3, all-gather by shuffles) and, per stage, reduces
-//     d_ss[b][a] = sum_t lam_t[b] v_t[a] and d_ys[r][a] = sum_t g_t[r] v_t[a] over the CTA's columns straight from shared memory
-//     (one atomic per parameter and column group) -- the 37 MB V / LAM / GY scratch round trip of kernels 6a + 6b is gone.
+//     the stages backwards (lane o of a column group owns 16 / B4_LPC adjoint components, all-gather by shuffles) and, per stage,
+//     reduces d_ss[b][a] = sum_t lam_t[b] v_t[a] and d_ys[r][a] = sum_t g_t[r] v_t[a] over the CTA's columns straight from shared
+//     memory (one atomic per parameter and column group) -- the 37 MB V / LAM / GY scratch round trip of kernels 6a + 6b is gone.
 // ------------------------------------------------------------------------------------------
 constexpr int BB4_V = LMAX * DS * B4_LD;            // floats: V[stage][a][lc]
 constexpr int BB4_DM = 64 * B4_LD;                  // the CTA's columns of the chunk's dM tile
@@ -2293,7 +2324,7 @@ sss_tc_build_bwd4_kernel(const sn_sss_stage* __restrict__ stages, int n, const s
     float* pbuf = Xs + BB4_X;
     const sn_sss_tc_chunk c = chunks[blockIdx.x];
     const int dir = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
-    const int lc = tid >> 2, q = tid & 3;
+    const int lc = tid / B4_LPC, o = tid % B4_LPC;
     const int t = blockIdx.z * B4_COLS + lc;
     const bool active = lc < B4_COLS && t < c.ncols + DS;
     const bool is_in = t < c.ncols;
@@ -2312,6 +2343,11 @@ sss_tc_build_bwd4_kernel(const sn_sss_stage* __restrict__ stages, int n, const s
             const int cidx = tt < c.ncols ? tt : c.nkb * KBW + dir * DS + (tt - c.ncols);
             dMs[e] = ok ? __ldg(src + row * DMC + cidx) : 0.f;
         }
+        // columns of V and X that no thread owns stay zero in the reductions
+        for (int e = tid; e < BB4_V; e += B4_THREADS)
+            if (e % B4_LD >= B4_TCOLS) Vs[e] = 0.f;
+        for (int e = tid; e < BB4_X; e += B4_THREADS)
+            if (e % B4_LD >= B4_TCOLS) Xs[e] = 0.f;
     }
     __syncthreads();
     chunk_params_async_q(pbuf, sptr, sdesc, nst, params, tid, B4_THREADS);
@@ -2319,11 +2355,11 @@ sss_tc_build_bwd4_kernel(const sn_sss_stage* __restrict__ stages, int n, const s
     cp_async_wait_all();
     __syncthreads();
 
-    float v[DS], own[4], yv[4];
+    float v[DS], own[B4_NC], yv[B4_NC];
 #pragma unroll
     for (int a = 0; a < DS; ++a) v[a] = (active && !is_in && a == sidx && sidx < sdesc[0].d_in) ? 1.f : 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) own[j] = (active && !is_in && 4 * q + j == sidx && sidx < sdesc[0].d_in) ? 1.f : 0.f;
+    for (int j = 0; j < B4_NC; ++j) own[j] = (active && !is_in && B4_NC * o + j == sidx && sidx < sdesc[0].d_in) ? 1.f : 0.f;
     int my_i = -1;
     // phase 1: replay the construction, keeping the state that enters every stage
     {
@@ -2333,18 +2369,18 @@ sss_tc_build_bwd4_kernel(const sn_sss_stage* __restrict__ stages, int n, const s
             const int local = col - st.in_off;
             const bool mine = active && is_in && local >= 0 && local < st.in_dim;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) Vs[(i * DS + 4 * q + j) * B4_LD + lc] = own[j];
+            for (int j = 0; j < B4_NC; ++j) Vs[(i * DS + B4_NC * o + j) * B4_LD + lc] = own[j];
             const bool live = active && (!is_in || activated || mine);
-            if (__any_sync(0xffffffffu, live)) stage_apply_q<false>(st, pbuf, sptr[i], v, own, yv, mine, local, q, lane);
+            if (__any_sync(0xffffffffu, live)) stage_apply_q<false>(st, pbuf, sptr[i], v, own, yv, mine, local, o, lane);
             if (mine) { my_i = i; activated = true; }
         }
     }
     // adjoint of the state leaving the last stage: the dR / dPhi rows of dM
-    float lam[DS], lown[4];
+    float lam[DS], lown[B4_NC];
 #pragma unroll
     for (int b = 0; b < DS; ++b) lam[b] = dMs[(PO + dir * DS + b) * B4_LD + lc];      // zero for inactive columns
 #pragma unroll
-    for (int j = 0; j < 4; ++j) lown[j] = dMs[(PO + dir * DS + 4 * q + j) * B4_LD + lc];
+    for (int j = 0; j < B4_NC; ++j) lown[j] = dMs[(PO + dir * DS + B4_NC * o + j) * B4_LD + lc];
     // phase 2: stages backwards
     for (int i = nst - 1; i >= 0; --i) {
         const sn_sss_stage& st = sdesc[i];
@@ -2355,70 +2391,77 @@ sss_tc_build_bwd4_kernel(const sn_sss_stage* __restrict__ stages, int n, const s
         const bool support = active && (is_in ? (dir == 0 ? (before || mine) : before) : true);
         const int rbase = st.out_off - c.row0;
         float* Xb = Xs + (i & 1) * (DS + SOUT_MAX) * B4_LD;
-        float g[SOUT_MAX], gown[4];
+        float g[SOUT_MAX], gown[B4_NC];
 #pragma unroll
         for (int r = 0; r < SOUT_MAX; ++r) g[r] = (r < st.out_dim && support) ? dMs[(rbase + r) * B4_LD + lc] : 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) gown[j] = (q + 4 * j < st.out_dim && support) ? dMs[(rbase + q + 4 * j) * B4_LD + lc] : 0.f;
+        for (int j = 0; j < B4_NC; ++j) gown[j] = (o + B4_LPC * j < st.out_dim && support) ? dMs[(rbase + o + B4_LPC * j) * B4_LD + lc] : 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            Xb[(4 * q + j) * B4_LD + lc] = lown[j];
-            Xb[(DS + q + 4 * j) * B4_LD + lc] = gown[j];
+        for (int j = 0; j < B4_NC; ++j) {
+            Xb[(B4_NC * o + j) * B4_LD + lc] = lown[j];
+            Xb[(DS + o + B4_LPC * j) * B4_LD + lc] = gown[j];
         }
         if (mine) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int b = 4 * q + j;
+            for (int j = 0; j < B4_NC; ++j) {
+                const int b = B4_NC * o + j;
                 if (b < st.d_out) gparams[st.off_su + b * st.in_dim + local] += lown[j];
             }
             if (st.off_yu >= 0) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int r = q + 4 * j;
+                for (int j = 0; j < B4_NC; ++j) {
+                    const int r = o + B4_LPC * j;
                     if (r < st.out_dim) gparams[st.off_yu + r * st.in_dim + local] += gown[j];
                 }
             }
         }
-        // lambda entering the stage, components a = 4q .. 4q+3: ss^T lam + ys^T g
-        float nl[4] = {0.f, 0.f, 0.f, 0.f};
+        // lambda entering the stage, components a = B4_NC o .. : ss^T lam + ys^T g
+        float nl[B4_NC];
+#pragma unroll
+        for (int j = 0; j < B4_NC; ++j) nl[j] = 0.f;
         const float* ys = pbuf + ps.ys;
-        if (st.d_in == DS) {
+        const bool live = active && (!is_in || my_i >= 0);       // adjoints of columns whose stage lies later in the sweep stay zero
+        if (__any_sync(0xffffffffu, live && (!is_in || my_i <= i))) {
+            if (st.d_in == DS) {
 #pragma unroll
-            for (int b = 0; b < DS; ++b) {
-                if (b >= st.d_out) break;
-                const float4 m = *reinterpret_cast<const float4*>(pbuf + ps.ss + ss_off(b, DS) + 4 * q);
-                nl[0] = fmaf(m.x, lam[b], nl[0]); nl[1] = fmaf(m.y, lam[b], nl[1]); nl[2] = fmaf(m.z, lam[b], nl[2]); nl[3] = fmaf(m.w, lam[b], nl[3]);
+                for (int b = 0; b < DS; ++b) {
+                    if (b >= st.d_out) break;
+                    const float* m = pbuf + ps.ss + ss_off(b, DS) + B4_NC * o;
+#pragma unroll
+                    for (int j = 0; j < B4_NC; ++j) nl[j] = fmaf(m[j], lam[b], nl[j]);
+                }
+#pragma unroll
+                for (int r = 0; r < SOUT_MAX; ++r) {
+                    if (r >= st.out_dim) break;
+                    const float* m = ys + r * DS + B4_NC * o;
+#pragma unroll
+                    for (int j = 0; j < B4_NC; ++j) nl[j] = fmaf(m[j], g[r], nl[j]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < B4_NC; ++j) {
+                    const int a = B4_NC * o + j;
+                    if (a >= st.d_in) continue;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int b = 0; b < DS; ++b)
+                        if (b < st.d_out) acc = fmaf(pbuf[ps.ss + ss_off(b, st.d_in) + a], lam[b], acc);
+#pragma unroll
+                    for (int r = 0; r < SOUT_MAX; ++r)
+                        if (r < st.out_dim) acc = fmaf(ys[r * st.d_in + a], g[r], acc);
+                    nl[j] = acc;
+                }
             }
 #pragma unroll
-            for (int r = 0; r < SOUT_MAX; ++r) {
-                if (r >= st.out_dim) break;
-                const float4 m = *reinterpret_cast<const float4*>(ys + r * DS + 4 * q);
-                nl[0] = fmaf(m.x, g[r], nl[0]); nl[1] = fmaf(m.y, g[r], nl[1]); nl[2] = fmaf(m.z, g[r], nl[2]); nl[3] = fmaf(m.w, g[r], nl[3]);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int a = 4 * q + j;
-                if (a >= st.d_in) continue;
-                float acc = 0.f;
-#pragma unroll
-                for (int b = 0; b < DS; ++b)
-                    if (b < st.d_out) acc = fmaf(pbuf[ps.ss + ss_off(b, st.d_in) + a], lam[b], acc);
-#pragma unroll
-                for (int r = 0; r < SOUT_MAX; ++r)
-                    if (r < st.out_dim) acc = fmaf(ys[r * st.d_in + a], g[r], acc);
-                nl[j] = acc;
-            }
+            for (int j = 0; j < B4_NC; ++j) lown[j] = nl[j];
+            group_allgather(nl, lam, lane);
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) lown[j] = nl[j];
-        quad_allgather(nl, lam, lane);
         __syncthreads();      // Xb complete (the other buffer was last read before the previous iteration's barrier)
         // reductions over the CTA's columns: rows 0..15 = d_ss, rows 16.. = d_ys
         const float* Vi = Vs + (size_t)i * DS * B4_LD;
         const int nout = (DS + st.out_dim) * DS;
-        for (int o = tid; o < nout; o += B4_THREADS) {
-            const int rowi = o >> 4, a = o & 15;
+        for (int oo = tid; oo < nout; oo += B4_THREADS) {
+            const int rowi = oo >> 4, a = oo & 15;
             if (a >= st.d_in || (rowi < DS && rowi >= st.d_out)) continue;
             const float4* xr = reinterpret_cast<const float4*>(Xb + rowi * B4_LD);
             const float4* vr = reinterpret_cast<const float4*>(Vi + a * B4_LD);
@@ -2513,7 +2556,7 @@ int sn_sss_tc_build(const sn_sss_tc_plan* p, const float* params, float* coef, s
     float* W = coef;
     float* SC = coef + (size_t)p->nchunks * WROWS * WCOLS;
     if (use_quad_build()) {
-        const size_t bsm = ((size_t)p->chunk_param_floats + 4 * LMAX * 4) * sizeof(float);    // + the quad padding of the state matrices
+        const size_t bsm = ((size_t)p->chunk_param_floats + B4_LPC * LMAX * 4) * sizeof(float);    // + the bank padding of the state matrices
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
         SN_LAUNCH("sss_tc_build4_kernel", snb::as_stream(stream), sss_tc_build4_kernel<<<dim3(p->nchunks, 2, B4_SPLIT), B4_THREADS, bsm, snb::as_stream(stream)>>>(p->stages, p->nb_states, p->chunks, params, W, SC));
     } else {
@@ -2627,7 +2670,7 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     if (nsplit < 1) nsplit = 1;
     SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_grad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
     SN_LAUNCH("sss_tc_grad_gemm_kernel", st, sss_tc_grad_gemm_kernel<<<dim3(nsplit, p->nchunks), G2_THREADS, G2_SMEM, st>>>(mx, mg, ml, ms, p->chunks, (long)B, dM));
-    const size_t bsm4 = ((size_t)BB4_FIXED + p->chunk_param_floats + 4 * LMAX * 4) * sizeof(float);
+    const size_t bsm4 = ((size_t)BB4_FIXED + p->chunk_param_floats + B4_LPC * LMAX * 4) * sizeof(float);
     if (use_quad_build() && bsm4 <= 227 * 1024) {
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm4));
         SN_LAUNCH("sss_tc_build_bwd4_kernel", st, sss_tc_build_bwd4_kernel<<<dim3(p->nchunks, 2, B4_SPLIT), B4_THREADS, bsm4, st>>>(p->stages, p->nb_states, p->chunks, params, dM, grad_params));

@@ -242,6 +242,20 @@ def _to_device_once(a: np.ndarray, device):
     return t.to(device)
 
 
+def _evaluate_resident_fused(model, Xd: torch.Tensor, yd: torch.Tensor, fused: "FusedLoss", batch_size: int):
+    """One device pass: every batch's loss and correct-prediction count are accumulated by the fused kernel into two device scalars,
+    read once at the end (reference training_helpers.py:57-73 synchronises twice per batch)."""
+    n = Xd.shape[0]
+    nb_batches = np.ceil(n / batch_size).astype("int")
+    fused.reset()
+    with torch.no_grad():
+        for batch_i in range(nb_batches):
+            lo, hi = int(batch_i * batch_size), min(int((batch_i + 1) * batch_size), n)
+            fused(model(Xd[lo:hi]), yd[lo:hi])
+    both = torch.cat([fused.loss_sum, fused.correct.float()]).cpu().numpy()        # one synchronisation for the whole pass
+    return np.float32(both[0]) / nb_batches, np.float32(both[1] / len(yd))
+
+
 def _evaluate_resident(model, Xd: torch.Tensor, yd: torch.Tensor, loss_function, batch_size: int):
     """``get_loss_and_accuracy_for_model`` (:57-73) on resident tensors: the float32 batch losses are summed in the same order,
     the division by the (numpy int) batch count happens on the host like in the reference, so the returned values are identical."""
@@ -263,23 +277,88 @@ def _evaluate_resident(model, Xd: torch.Tensor, yd: torch.Tensor, loss_function,
     return loss, accuracy
 
 
-class FlatSGD:
-    """Plain SGD over a layer's flat parameter / gradient buffers: one fused kernel instead of one update per parameter tensor (the
-    SSS layer has 3 501).  Loose parameters (sparse / float64 ones that do not live in the flat buffer) keep torch's SGD, so the
-    reference's "sparse parameters: SGD only" rule (psm_layer.py:14-15) is unchanged.  Pass as ``optimizer_class=FlatSGD.for_model(model)``."""
+class _FusedLossFn(torch.autograd.Function):
+    """Loss value + gradient of the model output in ONE kernel (csrc/train.cu: sn_ce_loss / sn_mse_loss); the number of correct
+    predictions of the batch is counted in the same pass (``counters``: device float loss sum, device int correct count -- both are
+    accumulated into, so an evaluation pass reads them once at its end)."""
 
-    def __init__(self, model, params, lr):
-        self.lr = lr
+    @staticmethod
+    def forward(ctx, outputs, target, kind, counters, want_grad):
+        from structurednets_b200 import _lib
+        L = _lib.lib()
+        outputs = outputs.contiguous()
+        B, C = outputs.shape
+        loss_sum, correct = counters
+        before = loss_sum.clone()
+        grad = torch.empty_like(outputs) if want_grad else None
+        if kind == "ce":
+            rc = L.sn_ce_loss(_lib.ptr(outputs), outputs.stride(0), _lib.ptr(target), B, C, _lib.ptr(loss_sum), _lib.ptr(correct),
+                              _lib.ptr(grad), grad.stride(0) if grad is not None else 0, _lib.stream_ptr())
+        else:
+            target = target.contiguous()
+            rc = L.sn_mse_loss(_lib.ptr(outputs), outputs.stride(0), _lib.ptr(target), target.stride(0), B, C, _lib.ptr(loss_sum),
+                               _lib.ptr(correct if C > 1 else None), _lib.ptr(grad), grad.stride(0) if grad is not None else 0, _lib.stream_ptr())
+        _lib.check(rc, "fused loss")
+        ctx.grad = grad
+        return (loss_sum - before).reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return ctx.grad * grad_out, None, None, None, None
+
+
+class FusedLoss:
+    """Drop-in for ``torch.nn.CrossEntropyLoss()`` / ``torch.nn.MSELoss()`` (mean reduction, as the reference constructs them,
+    training_helpers.py:110) on float32 CUDA outputs; also counts correct predictions (``.correct``) and sums batch losses
+    (``.loss_sum``) on the device.  Anything else (CPU tensors, other dtypes) goes to the torch loss it wraps."""
+
+    def __init__(self, loss_function_class, device):
+        self.torch_loss = loss_function_class()
+        self.kind = "ce" if isinstance(self.torch_loss, torch.nn.CrossEntropyLoss) else ("mse" if isinstance(self.torch_loss, torch.nn.MSELoss) else None)
+        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=device)
+        self.correct = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def usable(self, outputs, target):
+        if self.kind is None or not outputs.is_cuda or outputs.dtype != torch.float32 or outputs.dim() != 2:
+            return False
+        if self.kind == "ce":
+            return target.dtype == torch.int64 and target.dim() == 1
+        return target.dtype == torch.float32 and target.shape == outputs.shape
+
+    def reset(self):
+        self.loss_sum.zero_()
+        self.correct.zero_()
+
+    def __call__(self, outputs, target):
+        if not self.usable(outputs, target):
+            return self.torch_loss(outputs, target=target)
+        return _FusedLossFn.apply(outputs, target, self.kind, (self.loss_sum, self.correct), torch.is_grad_enabled() and outputs.requires_grad)
+
+
+class FlatSGD:
+    """Plain SGD over a layer's flat parameter / gradient buffers: one fused kernel (sn_flat_sgd) instead of one update per parameter
+    tensor (the SSS layer has 3 501).  Loose parameters (sparse / float64 ones that do not live in the flat buffer) keep torch's SGD,
+    so the reference's "sparse parameters: SGD only" rule (psm_layer.py:14-15) is unchanged.  ``grad_scale`` folds the data-parallel
+    1 / world-size factor into the update (use ``GradSynchronizer(model)`` without ``scale`` then).  Pass as
+    ``optimizer_class=FlatSGD.for_model(model)``."""
+
+    def __init__(self, model, params, lr, grad_scale=1.0):
+        self.lr, self.grad_scale = lr, grad_scale
         self.flat_p = model.flat_parameters() if hasattr(model, "flat_parameters") else None
         self.flat_g = model.flat_grad() if hasattr(model, "flat_grad") else None
         self.model = model
         flat_ptr = (self.flat_p.data_ptr(), self.flat_p.data_ptr() + self.flat_p.numel() * 4) if self.flat_p is not None else (0, 0)
         loose = [p for p in params if p.is_sparse or (p.numel() > 0 and not (flat_ptr[0] <= p.data_ptr() < flat_ptr[1]))]   # empty boundary blocks: nothing to update
-        self.loose = torch.optim.SGD(loose, lr=lr) if loose else None
+        self.loose_params = loose
+        self.loose = self._loose_optimizer(loose, lr) if loose else None
+
+    @staticmethod
+    def _loose_optimizer(loose, lr):
+        return torch.optim.SGD(loose, lr=lr)
 
     @classmethod
-    def for_model(cls, model):
-        return lambda params, lr: cls(model, list(params), lr)
+    def for_model(cls, model, grad_scale=1.0):
+        return lambda params, lr: cls(model, list(params), lr, grad_scale=grad_scale)
 
     def zero_grad(self, set_to_none=True):
         if self.flat_g is not None:
@@ -287,12 +366,60 @@ class FlatSGD:
         if self.loose is not None:
             self.loose.zero_grad(set_to_none=set_to_none)
 
+    def _flat_step(self):
+        if self.flat_p.is_cuda:
+            from structurednets_b200 import _lib
+            _lib.check(_lib.lib().sn_flat_sgd(_lib.ptr(self.flat_p), _lib.ptr(self.flat_g), self.flat_p.numel(), float(self.lr), float(self.grad_scale),
+                                              _lib.stream_ptr()), "sn_flat_sgd")
+        else:
+            with torch.no_grad():
+                self.flat_p.add_(self.flat_g, alpha=-self.lr * self.grad_scale)
+
     def step(self):
         if self.flat_p is not None:
-            with torch.no_grad():
-                self.flat_p.add_(self.flat_g, alpha=-self.lr)
+            self._flat_step()
         if self.loose is not None:
+            if self.grad_scale != 1.0:
+                with torch.no_grad():
+                    for p in self.loose_params:
+                        if p.grad is not None:
+                            (p.grad._values() if p.grad.is_sparse else p.grad).mul_(self.grad_scale)
             self.loose.step()
+
+
+class FlatAdam(FlatSGD):
+    """Adam (torch.optim.Adam defaults: betas (0.9, 0.999), eps 1e-8, no weight decay, no amsgrad -- what the reference's
+    ``optimizer_class=torch.optim.Adam`` default of ``train`` uses, training_helpers.py:107,111) over the flat buffers in one kernel
+    (sn_flat_adam); the step counter lives on the device so that the step can be captured in a CUDA graph.  Loose dense parameters keep
+    torch's Adam; sparse ones raise like torch does (reference: "SGD only", psm_layer.py:14-15)."""
+
+    def __init__(self, model, params, lr, grad_scale=1.0, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(model, params, lr, grad_scale=grad_scale)
+        self.betas, self.eps = betas, eps
+        if self.flat_p is not None:
+            self.exp_avg = torch.zeros_like(self.flat_p)
+            self.exp_avg_sq = torch.zeros_like(self.flat_p)
+            self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.flat_p.device)
+            self.step_host = 0
+
+    @staticmethod
+    def _loose_optimizer(loose, lr):
+        return torch.optim.Adam(loose, lr=lr)
+
+    def _flat_step(self):
+        if self.flat_p.is_cuda:
+            from structurednets_b200 import _lib
+            _lib.check(_lib.lib().sn_flat_adam(_lib.ptr(self.flat_p), _lib.ptr(self.flat_g), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                                               self.flat_p.numel(), float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                                               float(self.grad_scale), _lib.ptr(self.step_dev), 0, _lib.stream_ptr()), "sn_flat_adam")
+        else:
+            self.step_host += 1
+            with torch.no_grad():
+                g = self.flat_g * self.grad_scale
+                self.exp_avg.mul_(self.betas[0]).add_(g, alpha=1 - self.betas[0])
+                self.exp_avg_sq.mul_(self.betas[1]).addcmul_(g, g, value=1 - self.betas[1])
+                bc1, bc2 = 1 - self.betas[0] ** self.step_host, 1 - self.betas[1] ** self.step_host
+                self.flat_p.addcdiv_(self.exp_avg, (self.exp_avg_sq.sqrt() / math.sqrt(bc2)).add_(self.eps), value=-self.lr / bc1)
 
 
 class _GraphedStep:
@@ -340,10 +467,12 @@ class _GraphedStep:
 
 def train_resident(model, X_train, y_train, X_val=None, y_val=None, patience=10, batch_size=1000, verbose=False, lr=1e-6,
                    restore_best_model=True, loss_function_class=torch.nn.CrossEntropyLoss, min_patience_improvement=1e-10,
-                   optimizer_class=torch.optim.Adam, use_gpu=False, grad_sync=None, cuda_graph=False):
+                   optimizer_class=torch.optim.Adam, use_gpu=False, grad_sync=None, cuda_graph=False, fused_loss=False):
     """Drop-in for ``train`` with the data resident on the device.  Consumes the numpy RNG exactly like ``train`` (one
     ``sklearn.utils.shuffle`` per epoch), so both loops see the same batches for the same seed.  ``cuda_graph=True`` replays the
-    full-size training step from a CUDA graph (see ``_GraphedStep``; use with ``FlatSGD``)."""
+    full-size training step from a CUDA graph (see ``_GraphedStep``; use with ``FlatSGD`` / ``FlatAdam``).  ``fused_loss=True``
+    computes loss, accuracy and the gradient of the model output in one kernel (``FusedLoss``; CrossEntropyLoss / MSELoss on CUDA):
+    the same numbers to float32 rounding (the summation order differs from ATen's), not bit for bit."""
     if X_val is None or y_val is None:
         X_train, X_val, y_train, y_val = train_test_split(X_train, y_train, test_size=0.2)
     device = get_device(use_gpu=use_gpu)
@@ -351,11 +480,17 @@ def train_resident(model, X_train, y_train, X_val=None, y_val=None, patience=10,
     Xv, yv = _to_device_once(X_val, device), _to_device_once(y_val, device)
 
     optimizer = optimizer_class(model.parameters(), lr=lr)
-    loss_function = loss_function_class()
+    fused = FusedLoss(loss_function_class, device) if (fused_loss and torch.device(device).type == "cuda") else None
+    if fused is not None and fused.kind is None:
+        fused = None
+    loss_function = fused if fused is not None else loss_function_class()
     n = Xd.shape[0]
     nb_batches_per_epoch = np.ceil(n / batch_size).astype("int")
     _dp_check_equal_steps(grad_sync, nb_batches_per_epoch, device)
-    evaluate = lambda X, y: _dp_reduce_stats(grad_sync, *_evaluate_resident(model, X, y, loss_function, batch_size), len(y), device)
+    if fused is not None:
+        evaluate = lambda X, y: _dp_reduce_stats(grad_sync, *_evaluate_resident_fused(model, X, y, fused, batch_size), len(y), device)
+    else:
+        evaluate = lambda X, y: _dp_reduce_stats(grad_sync, *_evaluate_resident(model, X, y, loss_function, batch_size), len(y), device)
     start_train_loss, start_train_accuracy = evaluate(Xd, yd)
     start_val_loss, start_val_accuracy = evaluate(Xv, yv)
     if verbose:

@@ -160,5 +160,43 @@ def main():
     print("golden fixtures written to", HERE)
 
 
+def train_case():
+    """Seeded data, model and numpy RNG of the training-loop fixture (shared with tests/test_training_helpers.py)."""
+    rng = np.random.default_rng(77)
+    X = rng.uniform(-1, 1, size=(230, 12)).astype(np.float32)
+    Wt = rng.uniform(-1, 1, size=(12, 5)).astype(np.float32)
+    y = (X @ Wt).argmax(1).astype(np.int64)
+    Xv = rng.uniform(-1, 1, size=(40, 12)).astype(np.float32)
+    yv = (Xv @ Wt).argmax(1).astype(np.int64)
+    return X, y, Xv, yv
+
+
+def train_fixture():
+    """The reference's own training loop (training_helpers.train, :107-181) on a seeded torch.nn.Linear: the 9-tuple it returns and
+    the trained weights, for two optimizers and both restore_best_model settings.  ``sklearn.utils.shuffle`` draws from numpy's
+    global RNG, seeded here; the ragged last batch (230 = 4 x 50 + 30) is part of the case."""
+    load_reference()
+    from structurednets import training_helpers as RTH
+    X, y, Xv, yv = train_case()
+    out = {}
+    for tag, opt, restore in (("sgd_best", torch.optim.SGD, True), ("adam_last", torch.optim.Adam, False)):
+        torch.manual_seed(5)
+        np.random.seed(11)
+        model = torch.nn.Linear(12, 5)
+        res = RTH.train(model, X, y, X_val=Xv, y_val=yv, patience=3, batch_size=50, lr=5e-2, restore_best_model=restore,
+                        min_patience_improvement=1e-3, optimizer_class=opt)
+        out[tag + "_start"] = np.asarray([float(v) for v in res[1:5]], dtype=np.float64)
+        for name, h in zip(("tl", "ta", "vl", "va"), res[5:9]):
+            out[tag + "_" + name] = np.asarray([float(v) for v in h], dtype=np.float64)
+        out[tag + "_W"] = res[0].weight.detach().numpy().copy()
+        out[tag + "_b"] = res[0].bias.detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "train_linear.npz"), **out)
+    print("train fixture written:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        train_fixture()
+    else:
+        main()
+        train_fixture()

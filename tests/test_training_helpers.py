@@ -153,3 +153,46 @@ def test_flat_sgd_equals_torch_sgd_on_the_flat_buffer():
     assert torch.equal(layers[0].flat_parameters(), layers[1].flat_parameters())
     for a, b in zip(layers[0].parameters(), layers[1].parameters()):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("loop", ["train", "train_resident"])
+@pytest.mark.parametrize("tag,opt,restore", [("sgd_best", torch.optim.SGD, True), ("adam_last", torch.optim.Adam, False)])
+def test_train_equals_the_reference_train_bit_for_bit(loop, tag, opt, restore):
+    """tests/golden/train_linear.npz holds what the REFERENCE's training_helpers.train (:107-181) returns on a seeded
+    torch.nn.Linear (generated by tests/golden/make_golden.py from the unmodified reference): start losses / accuracies, the four
+    per-epoch histories (so also the epoch at which early stopping fires) and the weights of the returned model.  This repo's
+    train and train_resident must reproduce all of it exactly."""
+    from tests import golden_io as GIO
+    from tests.golden.make_golden import train_case
+    z = GIO.load("train_linear")
+    X, y, Xv, yv = train_case()
+    torch.manual_seed(5)
+    np.random.seed(11)
+    model = torch.nn.Linear(12, 5)
+    res = getattr(TH, loop)(model, X, y, X_val=Xv, y_val=yv, patience=3, batch_size=50, lr=5e-2, restore_best_model=restore,
+                            min_patience_improvement=1e-3, optimizer_class=opt)
+    np.testing.assert_array_equal(np.asarray([float(v) for v in res[1:5]]), z[tag + "_start"])
+    for name, h in zip(("tl", "ta", "vl", "va"), res[5:9]):
+        np.testing.assert_array_equal(np.asarray([float(v) for v in h]), z[tag + "_" + name], err_msg=name)
+    np.testing.assert_array_equal(res[0].weight.detach().numpy(), z[tag + "_W"])
+    np.testing.assert_array_equal(res[0].bias.detach().numpy(), z[tag + "_b"])
+
+
+def test_live_reference_train_when_the_reference_tree_is_present():
+    """Same comparison against the imported reference itself (build container only; skipped on the GPU box)."""
+    from oracle.ref_import import load_reference, reference_available
+    if not reference_available():
+        pytest.skip("/root/reference is not present")
+    load_reference()
+    from structurednets import training_helpers as RTH
+    from tests.golden.make_golden import train_case
+    X, y, Xv, yv = train_case()
+    out = []
+    for mod in (RTH, TH):
+        torch.manual_seed(3)
+        np.random.seed(4)
+        res = mod.train(torch.nn.Linear(12, 5), X, y, X_val=Xv, y_val=yv, patience=2, batch_size=64, lr=1e-1, optimizer_class=torch.optim.SGD,
+                        min_patience_improvement=1e-4)
+        out.append(([float(v) for v in res[1:5]], [[float(v) for v in h] for h in res[5:9]], res[0].weight.detach().numpy()))
+    assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
+    np.testing.assert_array_equal(out[0][2], out[1][2])
