@@ -125,7 +125,8 @@ typedef struct sn_sss_tc_plan {
     int32_t nb_states, input_dim, output_dim, nchunks;
     int32_t rows_aligned; /* 1: every chunk's row0 is a multiple of 4 (16-byte y / grad_y accesses) */
     int32_t chunk_param_floats; /* largest number of parameters (floats) of one direction of one chunk; <= 40960 */
-    int32_t reserved[2];
+    int32_t reserved[2];        /* reserved[0] = 1: in the flat parameter buffer the entries of each of the lists A..G for consecutive
+                                   stages are adjacent (the layout FlatParamsMixin produces): a chunk's parameters are 4 contiguous ranges */
     const sn_sss_stage* stages;    /* device, [2][nb_states] */
     const sn_sss_tc_chunk* chunks; /* device, [nchunks] */
 } sn_sss_tc_plan;

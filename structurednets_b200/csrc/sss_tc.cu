@@ -218,7 +218,7 @@ sss_tc_build_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss
 //     Warps whose columns are all still "not activated" (their stages come later in the sweep) skip the stage.
 // ------------------------------------------------------------------------------------------
 #ifndef SN_B4_LPC
-#define SN_B4_LPC 16
+#define SN_B4_LPC 8
 #endif
 constexpr int B4_LPC = SN_B4_LPC;                               // lanes per column: 4, 8 or 16
 constexpr int B4_NC = DS / B4_LPC;                              // state components (and output rows) per lane
@@ -398,6 +398,240 @@ sss_tc_build4_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_ss
             if (is_in) store_hi_lo(W, PO + dir * DS + b, t, own[j]);
             else Phi[b * DS + sidx] = own[j];
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 1''. chunk matrices on the warp-level tensor-core path (mma.sync m16n8k8 tf32, 3xTF32).  The SIMT build kernels above are
+//     instruction-bound: 8.4 M warp instructions of which 9 % are FFMAs (ncu: IMAD / ISETP / LDS / BRA dominate), whatever the
+//     number of lanes per column.  Here a warp owns a tile of 16 columns of the chunk's "identity input" and keeps their states as
+//     the D fragment of V (16 columns x 16 states); one stage is  V <- V A_i^T (+ B_i columns),  Y = V C_i^T (+ D_i)  -- four + two
+//     MMAs (x3 for the hi/lo split) whose A operand IS the previous D fragment: with the K index permuted (logical k = t <-> state
+//     2t, k = t + 4 <-> state 2t + 1 inside each group of 8) the accumulator registers of one product are the operand registers
+//     of the next, no shuffle and no shared-memory round trip.  The B operands (A_i, C_i) come from shared
+//     memory (raw fp32, split in registers).  ~110 instructions per stage and 16 columns instead of
+//     ~300 per 8 columns.  grid (nchunks, 2 directions, BM_SPLIT); tiles 0..9 = input columns, tile 10 = the 16 unit states.
+// ------------------------------------------------------------------------------------------
+constexpr int BM_TILES = COLT / 16;                                  // 11
+constexpr int BM_SPLIT = 2;
+constexpr int BM_WARPS = (BM_TILES + BM_SPLIT - 1) / BM_SPLIT;       // 6 warps per CTA
+constexpr int BM_THREADS = BM_WARPS * 32;
+static_assert(COLT % 16 == 0 && WCOLS % 16 == 0, "input columns and unit states must fall into separate 16-column tiles");
+
+// The chunk's parameters are staged RAW by cp.async.  In the flat parameter buffer (state_dict order: bias, A.0 .. A.n-1, B.*, C.*, D.*,
+// E.*, F.*, G.*) the entries of one list for consecutive stages are adjacent, so a (chunk, direction) needs FOUR contiguous ranges
+// (three for the anticausal direction): four copy loops of 16-byte cp.async instead of one small loop per stage and array -- the
+// per-array loops cost every thread ~2 000 instructions (17 us of a 40 us kernel, measured by ablation).
+struct ListRange { int lo, n, sm; };     // first float in the flat buffer (rounded down to a multiple of 4), floats to copy, shared-memory offset
+__device__ __forceinline__ ListRange list_range(int off_first, int n_first, int off_last, int n_last, int sm) {
+    int lo = off_first < off_last ? off_first : off_last;
+    const int e1 = off_first + n_first, e2 = off_last + n_last;
+    const int hi = e1 > e2 ? e1 : e2;
+    lo &= ~3;
+    return ListRange{lo, hi - lo, sm};
+}
+__device__ __forceinline__ void copy_range_async(float* pbuf, const float* __restrict__ params, const ListRange& r, int tid, int nthreads) {
+    // params + lo is 16-byte aligned when the flat buffer is (torch allocations are); otherwise fall back to 4-byte copies
+    const float* src = params + r.lo;
+    float* dst = pbuf + r.sm;
+    const int n4 = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? (r.n >> 2) : 0;
+    for (int e = tid; e < n4; e += nthreads) cp_async16(dst + 4 * e, src + 4 * e);
+    for (int e = 4 * n4 + tid; e < r.n; e += nthreads) cp_async4(dst + e, src + e);
+}
+// returns the floats of shared memory used; ptrs[i] = offsets of stage i's matrices inside pbuf
+__device__ __forceinline__ int chunk_params_ranges(float* pbuf, StageP* ptrs, const sn_sss_stage* sdesc, int nst, const float* __restrict__ params, int tid,
+                                                   int nthreads) {
+    const sn_sss_stage& f = sdesc[0];
+    const sn_sss_stage& l = sdesc[nst - 1];
+    const bool has_yu = f.off_yu >= 0;
+    ListRange r_ss = list_range(f.off_ss, f.d_out * f.d_in, l.off_ss, l.d_out * l.d_in, 0);
+    ListRange r_ys = list_range(f.off_ys, f.out_dim * f.d_in, l.off_ys, l.out_dim * l.d_in, pad4(r_ss.n));
+    ListRange r_su = list_range(f.off_su, f.d_out * f.in_dim, l.off_su, l.d_out * l.in_dim, r_ys.sm + pad4(r_ys.n));
+    ListRange r_yu = has_yu ? list_range(f.off_yu, f.out_dim * f.in_dim, l.off_yu, l.out_dim * l.in_dim, r_su.sm + pad4(r_su.n)) : ListRange{0, 0, r_su.sm + pad4(r_su.n)};
+    copy_range_async(pbuf, params, r_ss, tid, nthreads);
+    copy_range_async(pbuf, params, r_ys, tid, nthreads);
+    copy_range_async(pbuf, params, r_su, tid, nthreads);
+    if (has_yu) copy_range_async(pbuf, params, r_yu, tid, nthreads);
+    if (tid < nst) {
+        const sn_sss_stage& st = sdesc[tid];
+        ptrs[tid] = StageP{r_ss.sm + st.off_ss - r_ss.lo, r_ys.sm + st.off_ys - r_ys.lo, r_su.sm + st.off_su - r_su.lo, has_yu ? r_yu.sm + st.off_yu - r_yu.lo : 0};
+    }
+    return r_yu.sm + pad4(r_yu.n);
+}
+
+// B fragment (M[row][col], M[row][col + 1]) of a compact row-major [nrows][ncols] matrix, zero outside; split into tf32 hi / lo
+__device__ __forceinline__ void frag_b(const float* M, int row, int nrows, int col, int ncols, float2& hi, float2& lo) {
+    float2 r = make_float2(0.f, 0.f);
+    if (row < nrows) {
+        if (ncols == DS && (reinterpret_cast<uintptr_t>(M) & 7) == 0) {
+            r = *reinterpret_cast<const float2*>(M + row * DS + col);
+        } else {
+            if (col < ncols) r.x = M[row * ncols + col];
+            if (col + 1 < ncols) r.y = M[row * ncols + col + 1];
+        }
+    }
+    hi.x = tf32_hi(r.x); hi.y = tf32_hi(r.y);
+    lo.x = tf32_hi(r.x - hi.x); lo.y = tf32_hi(r.y - hi.y);
+}
+
+__device__ __forceinline__ void mma_1688(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+struct Frag3 { uint32_t hi[4], lo[4]; };
+// D fragment (row g: columns 2t, 2t+1; row g+8: columns 2t, 2t+1) -> A fragment of the next product, K permuted as described above
+__device__ __forceinline__ void split_frag(const float (&d)[4], Frag3& f) {
+    const float v[4] = {d[0], d[2], d[1], d[3]};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float hi = tf32_hi(v[i]);
+        f.hi[i] = __float_as_uint(hi);
+        f.lo[i] = __float_as_uint(tf32_hi(v[i] - hi));
+    }
+}
+// d += A B with B given pre-split (hi pair, lo pair); small terms first
+__device__ __forceinline__ void mma3(float (&d)[4], const Frag3& a, const float2 bh, const float2 bl) {
+    mma_1688(d, a.lo, __float_as_uint(bh.x), __float_as_uint(bh.y));
+    mma_1688(d, a.hi, __float_as_uint(bl.x), __float_as_uint(bl.y));
+    mma_1688(d, a.hi, __float_as_uint(bh.x), __float_as_uint(bh.y));
+}
+
+// the two columns (fragment rows g and g + 8) a lane looks after
+struct ColPair {
+    int tcol[2];      // column of the chunk (input tiles) or unit-state index (state tile)
+    bool valid[2];
+    bool act[2];
+};
+
+// V <- V ss^T (+ su columns of the columns whose stage this is): d[hp] = states 8 hp .. 8 hp + 7 of the tile's 16 columns
+__device__ __forceinline__ void mma_state_update(float (&d)[2][4], const Frag3 (&a)[2], const float* pbuf, const StageP& m, const sn_sss_stage& st,
+                                                 const bool (&mine)[2], const int (&local)[2], int g, int t) {
+#pragma unroll
+    for (int hp = 0; hp < 2; ++hp) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float2 bh, bl;
+            frag_b(pbuf + m.ss, 8 * hp + g, st.d_out, 8 * h + 2 * t, st.d_in, bh, bl);
+            mma3(acc, a[h], bh, bl);
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            if (mine[rr]) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int b = 8 * hp + 2 * t + e;
+                    if (b < st.d_out) acc[2 * rr + e] += pbuf[m.su + b * st.in_dim + local[rr]];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d[hp][k] = acc[k];
+    }
+}
+
+__global__ void __launch_bounds__(BM_THREADS)
+sss_tc_buildm_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss_tc_chunk* __restrict__ chunks, const float* __restrict__ params,
+                     float* __restrict__ Wall, float* __restrict__ SCall, int lists_contiguous) {
+    extern __shared__ __align__(16) float build_smem[];
+    __shared__ sn_sss_stage sdesc[LMAX];
+    __shared__ StageP smt[LMAX];
+    const sn_sss_tc_chunk c = chunks[blockIdx.x];
+    const int dir = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int nst = c.k_end - c.k_begin;
+    float* W = Wall + (size_t)blockIdx.x * WROWS * WCOLS;
+    float* SC = SCall + (size_t)blockIdx.x * SCF;
+    float* Phi = SC + dir * DS * DS;
+    float* Omat = SC + 2 * DS * DS + dir * PO * DS;
+    if (tid < nst) sdesc[tid] = stage_of(stages, n, dir, dir == 0 ? c.k_begin + tid : c.k_end - 1 - tid);
+    __syncthreads();
+    if (lists_contiguous) chunk_params_ranges(build_smem, smt, sdesc, nst, params, tid, BM_THREADS);
+    else chunk_params_async(build_smem, smt, sdesc, nst, params, tid, BM_THREADS);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+#if defined(SN_BUILD_ABL) && SN_BUILD_ABL == 1
+    return;                                                 // ablation: parameter staging only
+#endif
+    const int tile = BM_SPLIT * warp + blockIdx.z;
+    if (tile >= BM_TILES) return;
+    const bool state_tile = tile == BM_TILES - 1;
+    if (!state_tile && 16 * tile >= c.ncols) return;          // no input column in this tile
+    ColPair cp;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        cp.tcol[rr] = state_tile ? g + 8 * rr : 16 * tile + g + 8 * rr;
+        cp.valid[rr] = state_tile || cp.tcol[rr] < c.ncols;
+        cp.act[rr] = false;
+    }
+    float d[2][4];
+#pragma unroll
+    for (int hp = 0; hp < 2; ++hp)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int sidx = cp.tcol[k >> 1], a = 8 * hp + 2 * t + (k & 1);
+            d[hp][k] = (state_tile && a == sidx && sidx < sdesc[0].d_in) ? 1.f : 0.f;
+        }
+    for (int i = 0; i < nst; ++i) {
+        const sn_sss_stage& st = sdesc[i];
+        const StageP& m = smt[i];
+        int local[2];
+        bool mine[2];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            local[rr] = c.col0 + cp.tcol[rr] - st.in_off;
+            mine[rr] = !state_tile && cp.valid[rr] && local[rr] >= 0 && local[rr] < st.in_dim;
+        }
+        const bool live = state_tile || cp.act[0] || cp.act[1] || mine[0] || mine[1];
+        if (!__any_sync(0xffffffffu, live)) continue;          // every column of the tile still waits for its stage
+        Frag3 a[2];
+        split_frag(d[0], a[0]);
+        split_frag(d[1], a[1]);
+        const int rbase = st.out_off - c.row0;
+        // outputs of the stage from the state ENTERING it: Y = V ys^T (+ yu)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            if (8 * nt >= st.out_dim) break;
+            float y[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float2 bh, bl;
+                frag_b(build_smem + m.ys, 8 * nt + g, st.out_dim, 8 * h + 2 * t, st.d_in, bh, bl);
+                mma3(y, a[h], bh, bl);
+            }
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                if (!cp.valid[rr]) continue;
+                const bool wr = dir == 0 ? (cp.act[rr] || mine[rr]) : cp.act[rr];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int r = 8 * nt + 2 * t + e;
+                    if (r >= st.out_dim) continue;
+                    float val = y[2 * rr + e];
+                    if (mine[rr] && st.off_yu >= 0) val += build_smem[m.yu + r * st.in_dim + local[rr]];
+                    if (state_tile) Omat[(rbase + r) * DS + cp.tcol[rr]] = val;
+                    else if (wr) store_hi_lo(W, rbase + r, cp.tcol[rr], val);
+                }
+            }
+        }
+        mma_state_update(d, a, build_smem, m, st, mine, local, g, t);
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) cp.act[rr] = cp.act[rr] || mine[rr];
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+        if (!cp.valid[rr]) continue;
+#pragma unroll
+        for (int hp = 0; hp < 2; ++hp)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int b = 8 * hp + 2 * t + e;
+                const float val = d[hp][2 * rr + e];
+                if (state_tile) Phi[b * DS + cp.tcol[rr]] = val;
+                else store_hi_lo(W, PO + dir * DS + b, cp.tcol[rr], val);
+            }
     }
 }
 
@@ -2519,11 +2753,15 @@ bool use_tc_chain(int64_t B) {
     return B >= 10240;
 }
 
-// build / build-backward with four threads per column (default) or the one-thread-per-column kernels (SNB200_SSS_BUILD=col)
-bool use_quad_build() {
+// build / build-backward: 2 = warp-level tensor-core kernels (default), 1 = SIMT with several lanes per column
+// (SNB200_SSS_BUILD=quad), 0 = SIMT with one thread per column (SNB200_SSS_BUILD=col)
+int build_mode() {
     const char* e = getenv("SNB200_SSS_BUILD");
-    return !(e != nullptr && e[0] == 'c');
+    if (e != nullptr && e[0] == 'c') return 0;
+    if (e != nullptr && e[0] == 'q') return 1;
+    return 2;
 }
+bool use_quad_build() { return build_mode() >= 1; }
 
 // SIMT scans: split by direction (+ a parallel output kernel) by default; SNB200_SSS_SPLIT_SCANS=0 keeps the single-kernel scans
 bool use_split_scans(int64_t B) {
@@ -2555,7 +2793,11 @@ int sn_sss_tc_build(const sn_sss_tc_plan* p, const float* params, float* coef, s
     SN_CHECK_ARG(params && coef, "sss_tc_build: NULL buffer");
     float* W = coef;
     float* SC = coef + (size_t)p->nchunks * WROWS * WCOLS;
-    if (use_quad_build()) {
+    if (build_mode() == 2) {
+        const size_t bsm = ((size_t)p->chunk_param_floats + 32) * sizeof(float);     // four contiguous list ranges, each with <= 3 floats of lead-in
+        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_buildm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+        SN_LAUNCH("sss_tc_buildm_kernel", snb::as_stream(stream), sss_tc_buildm_kernel<<<dim3(p->nchunks, 2, BM_SPLIT), BM_THREADS, bsm, snb::as_stream(stream)>>>(p->stages, p->nb_states, p->chunks, params, W, SC, p->reserved[0]));
+    } else if (use_quad_build()) {
         const size_t bsm = ((size_t)p->chunk_param_floats + B4_LPC * LMAX * 4) * sizeof(float);    // + the bank padding of the state matrices
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
         SN_LAUNCH("sss_tc_build4_kernel", snb::as_stream(stream), sss_tc_build4_kernel<<<dim3(p->nchunks, 2, B4_SPLIT), B4_THREADS, bsm, snb::as_stream(stream)>>>(p->stages, p->nb_states, p->chunks, params, W, SC));

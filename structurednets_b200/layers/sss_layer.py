@@ -377,6 +377,8 @@ class SSSLayer(FlatParamsMixin, StructuredLayer):
         struct.nchunks = host["chunks"].shape[0]
         struct.rows_aligned = host["rows_aligned"]
         struct.chunk_param_floats = host["chunk_param_floats"]
+        offs = self._param_offsets()
+        struct.reserved[0] = int(all(offs[(nm, k + 1)] == offs[(nm, k)] + getattr(self, nm)[k].numel() for nm in "ABCDEFG" for k in range(self.nb_states - 1)))
         struct.stages = plan["stages"].data_ptr()
         struct.chunks = ch_dev.data_ptr()
         ncoef = int(_lib.lib().sn_sss_tc_coef_floats(ctypes.byref(struct)))
