@@ -180,8 +180,8 @@ int sn_hmat_backward(const int32_t* leaves, int nleaves, const float* params, co
  * and the dense gradient projected back onto the leaf factors (accumulated into grad_params). */
 int sn_hmat_build_dense(const int32_t* leaves, int nleaves, int max_rows, const float* params, float* W, int out_dim, int in_dim,
                         sn_stream_t stream);
-int sn_hmat_project_grad(const int32_t* leaves, int nleaves, const float* params, const float* dW, int out_dim, int in_dim,
-                         float* grad_params, sn_stream_t stream);
+int sn_hmat_project_grad(const int32_t* leaves, int nleaves, const int32_t* slabs /* (leaf, first row) per 32 rows of every leaf */, int nslabs,
+                         const float* params, const float* dW, int out_dim, int in_dim, float* grad_params, sn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * PSM layer -- replaces PSMLayer.forward / forward_sparse (layers/psm_layer.py:36-60) and its backward,

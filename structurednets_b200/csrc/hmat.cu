@@ -178,40 +178,69 @@ hmat_build_dense_kernel(const Leaf* __restrict__ leaves, const float* __restrict
     }
 }
 
-// blockIdx.y == 0: dL[i][k] += sum_j dW[i][j] R[k][j]  (a warp per output, lanes along j)
-// blockIdx.y == 1: dR[k][j] += sum_i L[i][k] dW[i][j]  (a thread per column j, k in registers)
+// One CTA per 32-row slab of a leaf (work list built by the host: the 6 + 16 largest leaves of the 2048 -> 1000 layer have 250 / 125
+// rows, and one CTA per leaf spent 200 us in them at one outstanding load per thread).
+// blockIdx.y == 0: dL[i][k] += sum_j dW[i][j] R[k][j]   warp per row i, lanes along j, eight ranks k at a time in registers
+// blockIdx.y == 1: dR[k][j] += sum_i L[i][k] dW[i][j]   thread per column j over the slab's rows (eight loads in flight), atomics
+//                                                        across the slabs of a leaf
+constexpr int HP_SLAB = 32;
 __global__ void __launch_bounds__(HD_THREADS)
-hmat_project_grad_kernel(const Leaf* __restrict__ leaves, const float* __restrict__ params, const float* __restrict__ dW, int ldw,
-                         float* __restrict__ gparams) {
-    const Leaf lf = leaves[blockIdx.x];
+hmat_project_grad_kernel(const Leaf* __restrict__ leaves, const int2* __restrict__ slabs, const float* __restrict__ params, const float* __restrict__ dW,
+                         int ldw, float* __restrict__ gparams) {
+    const int2 sl = slabs[blockIdx.x];
+    const Leaf lf = leaves[sl.x];
+    const int r0 = sl.y, nr = min(HP_SLAB, lf.rows - r0);
     const float* L = params + lf.offL;
     const float* R = params + lf.offR;
-    const float* D = dW + (size_t)lf.r0 * ldw + lf.c0;
+    const float* D = dW + (size_t)(lf.r0 + r0) * ldw + lf.c0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (blockIdx.y == 0) {
-        for (int o = warp; o < lf.rows * lf.k; o += HD_THREADS / 32) {
-            const int i = o / lf.k, k = o % lf.k;
-            float acc = 0.f;
-            for (int j = lane; j < lf.cols; j += 32) acc = fmaf(__ldg(D + (size_t)i * ldw + j), __ldg(R + k * lf.cols + j), acc);
+        for (int i = warp; i < nr; i += HD_THREADS / 32) {
+            for (int k0 = 0; k0 < lf.k; k0 += 8) {
+                float acc[8];
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-            if (lane == 0) gparams[lf.offL + o] += acc;
+                for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+                for (int j = lane; j < lf.cols; j += 32) {
+                    const float w = __ldg(D + (size_t)i * ldw + j);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (k0 + q < lf.k) acc[q] = fmaf(w, __ldg(R + (k0 + q) * lf.cols + j), acc[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float a = acc[q];
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+                    if (lane == 0 && k0 + q < lf.k) gparams[lf.offL + (r0 + i) * lf.k + k0 + q] += a;      // one owner per (row, rank)
+                }
+            }
         }
     } else {
+        const bool single = lf.rows <= HP_SLAB;      // one slab: plain accumulation, no atomics needed
         for (int j = threadIdx.x; j < lf.cols; j += HD_THREADS) {
             for (int k0 = 0; k0 < lf.k; k0 += 8) {
                 float acc[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-                for (int i = 0; i < lf.rows; ++i) {
-                    const float w = __ldg(D + (size_t)i * ldw + j);
+                for (int i0 = 0; i0 < nr; i0 += 8) {
+                    float w[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        if (k0 + q < lf.k) acc[q] = fmaf(__ldg(L + i * lf.k + k0 + q), w, acc[q]);
+                    for (int u = 0; u < 8; ++u) w[u] = i0 + u < nr ? __ldg(D + (size_t)(i0 + u) * ldw + j) : 0.f;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (i0 + u >= nr) break;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (k0 + q < lf.k) acc[q] = fmaf(__ldg(L + (r0 + i0 + u) * lf.k + k0 + q), w[u], acc[q]);
+                    }
                 }
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (k0 + q < lf.k) gparams[lf.offR + (k0 + q) * lf.cols + j] += acc[q];
+                for (int q = 0; q < 8; ++q) {
+                    if (k0 + q >= lf.k) break;
+                    float* dst = gparams + lf.offR + (k0 + q) * lf.cols + j;
+                    if (single) *dst += acc[q];
+                    else atomicAdd(dst, acc[q]);
+                }
             }
         }
     }
@@ -286,14 +315,15 @@ int sn_hmat_build_dense(const int32_t* leaves, int nleaves, int max_rows, const 
     SN_LAUNCH("hmat_build_dense_kernel", st, hmat_build_dense_kernel<<<grid, HD_THREADS, 0, st>>>(reinterpret_cast<const Leaf*>(leaves), params, W, in_dim));
     return 0;
 }
-// grad_params (flat, accumulated) += the dense block gradients dW projected onto the leaf factors
-int sn_hmat_project_grad(const int32_t* leaves, int nleaves, const float* params, const float* dW, int out_dim, int in_dim, float* grad_params,
-                         sn_stream_t stream) {
+// grad_params (flat, accumulated) += the dense block gradients dW projected onto the leaf factors.  slabs: device int32 pairs
+// (leaf index in `leaves`, first row of the slab inside the leaf), one per 32 rows of every leaf.
+int sn_hmat_project_grad(const int32_t* leaves, int nleaves, const int32_t* slabs, int nslabs, const float* params, const float* dW, int out_dim, int in_dim,
+                         float* grad_params, sn_stream_t stream) {
     (void)out_dim;
-    if (nleaves <= 0) return 0;
-    SN_CHECK_ARG(leaves && params && dW && grad_params, "hmat_project_grad: NULL buffer");
+    if (nleaves <= 0 || nslabs <= 0) return 0;
+    SN_CHECK_ARG(leaves && slabs && params && dW && grad_params, "hmat_project_grad: NULL buffer");
     cudaStream_t st = snb::as_stream(stream);
-    SN_LAUNCH("hmat_project_grad_kernel", st, hmat_project_grad_kernel<<<dim3(nleaves, 2), HD_THREADS, 0, st>>>(reinterpret_cast<const Leaf*>(leaves), params, dW, in_dim, grad_params));
+    SN_LAUNCH("hmat_project_grad_kernel", st, hmat_project_grad_kernel<<<dim3(nslabs, 2), HD_THREADS, 0, st>>>(reinterpret_cast<const Leaf*>(leaves), reinterpret_cast<const int2*>(slabs), params, dW, in_dim, grad_params));
     return 0;
 }
 

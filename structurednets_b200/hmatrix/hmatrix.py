@@ -144,7 +144,30 @@ class HMatrix:
         return pickle.loads(pickle.dumps(self))
 
 
-def approximate_hmatrix(optim_mat: np.ndarray, nb_params_share: float, eta: float = 0.5, min_block_size: int = 2) -> HMatrix:
+def _leaf_svds(optim_mat: np.ndarray, leaves, device=None):
+    """One (U, S, Vh) per leaf block.  On a CUDA device the leaves are grouped by shape and every group is ONE batched float64 SVD
+    (cuSOLVER through torch.linalg.svd): the 2048 -> 1000 layer has 2 560 leaves, 1 574 of them 4 x 8."""
+    blocks = [optim_mat[l.row_range.start:l.row_range.stop, l.col_range.start:l.col_range.stop] for l in leaves]
+    if device is None:
+        return [np.linalg.svd(b, full_matrices=False) for b in blocks]
+    out = [None] * len(leaves)
+    groups = {}
+    for i, b in enumerate(blocks):
+        groups.setdefault(b.shape, []).append(i)
+    for shape, idx in groups.items():
+        if min(shape) == 0:
+            for i in idx:
+                out[i] = (np.zeros((shape[0], 0)), np.zeros((0,)), np.zeros((0, shape[1])))
+            continue
+        batch = torch.as_tensor(np.stack([blocks[i] for i in idx]), dtype=torch.float64, device=device)
+        U, S, Vh = torch.linalg.svd(batch, full_matrices=False)
+        U, S, Vh = U.cpu().numpy(), S.cpu().numpy(), Vh.cpu().numpy()
+        for j, i in enumerate(idx):
+            out[i] = (U[j], S[j], Vh[j])
+    return out
+
+
+def approximate_hmatrix(optim_mat: np.ndarray, nb_params_share: float, eta: float = 0.5, min_block_size: int = 2, device=None) -> HMatrix:
     """Greedy singular-value allocation: while the budget allows, give one more singular value to the leaf
     whose squared-error reduction per added parameter, sigma_{k+1}^2 / (rows + cols), is largest; a leaf
     can grow while its rank is below both of its dimensions (reference hmatrix/hmatrix.py:41-64,
@@ -153,13 +176,11 @@ def approximate_hmatrix(optim_mat: np.ndarray, nb_params_share: float, eta: floa
     tree = build_hmat_block_cluster_tree(shape, eta=eta, min_block_size=min_block_size)
     budget = int(shape[0] * shape[1] * nb_params_share)
     leaves = tree.get_all_leaf_elements()
-    svds, ranks, heap = [], [0] * len(leaves), []
+    svds, ranks, heap = _leaf_svds(np.asarray(optim_mat), leaves, device), [0] * len(leaves), []
     for i, leaf in enumerate(leaves):
-        blk = optim_mat[leaf.row_range.start:leaf.row_range.stop, leaf.col_range.start:leaf.col_range.stop]
-        U, S, Vh = np.linalg.svd(blk, full_matrices=False)
-        svds.append((U, S, Vh))
+        S = svds[i][1]
         cost = len(leaf.row_range) + len(leaf.col_range)
-        if min(blk.shape) > 0:
+        if len(S) > 0:
             heapq.heappush(heap, (-(S[0] ** 2) / cost, i))
     used = 0
     while heap:

@@ -91,8 +91,9 @@ class _HMatDenseFunction(torch.autograd.Function):
         dW.zero_()
         _lib.check(L.sn_dense_weight_grad(_lib.ptr(U), U.stride(0), _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(dW), layer.output_dim,
                                           layer.input_dim, _lib.ptr(gb), U.shape[0], _lib.stream_ptr()), "sn_dense_weight_grad")
-        _lib.check(L.sn_hmat_project_grad(_lib.ptr(table), layer._nleaves, _lib.ptr(layer.flat_parameters()), _lib.ptr(dW), layer.output_dim,
-                                          layer.input_dim, _lib.ptr(g), _lib.stream_ptr()), "sn_hmat_project_grad")
+        slabs = layer._slab_table(U.device)
+        _lib.check(L.sn_hmat_project_grad(_lib.ptr(table), layer._nleaves, _lib.ptr(slabs), slabs.numel() // 2, _lib.ptr(layer.flat_parameters()),
+                                          _lib.ptr(dW), layer.output_dim, layer.input_dim, _lib.ptr(g), _lib.stream_ptr()), "sn_hmat_project_grad")
         return grad_x, None, None
 
 
@@ -108,7 +109,10 @@ class HMatLayer(FlatParamsMixin, StructuredLayer):
         else:
             if initial_weight_matrix is None:
                 initial_weight_matrix = get_random_glorot_uniform_matrix((output_dim, input_dim))
-            self.hmatrix = approximate_hmatrix(initial_weight_matrix, nb_params_share=nb_params_share, eta=eta)
+            # use_gpu (reference hmat_layer.py:13,36-37: "put the scratch tensors on the GPU") also moves the per-leaf SVDs of the
+            # initialisation to the GPU, batched by leaf shape
+            svd_device = "cuda" if (use_gpu and torch.cuda.is_available()) else None
+            self.hmatrix = approximate_hmatrix(initial_weight_matrix, nb_params_share=nb_params_share, eta=eta, device=svd_device)
 
         self.input_dim = input_dim
         components = [c for c in self.hmatrix.get_all_hmatrix_components() if c.are_low_rank_components_set()]
@@ -163,6 +167,7 @@ class HMatLayer(FlatParamsMixin, StructuredLayer):
 
     def _on_reflatten(self):
         self.__dict__["_dev_table"] = None
+        self.__dict__["_dev_slabs"] = None
         self.__dict__["_dev_W"] = None
         self.__dict__["_dev_dW"] = None
 
@@ -193,6 +198,16 @@ class HMatLayer(FlatParamsMixin, StructuredLayer):
         # beyond fp32 summation order)
         order = np.argsort(-(tab[:, 4].astype(np.int64) * (tab[:, 1] + tab[:, 3])), kind="stable")
         return tab[order]
+
+    def _slab_table(self, device):
+        """(leaf index in the device leaf table, first row) per 32 rows of every leaf: the work list of sn_hmat_project_grad."""
+        t = self.__dict__.get("_dev_slabs")
+        if t is None or t.device != device:
+            tab = self.build_leaf_table()
+            pairs = [(i, r0) for i in range(self._nleaves) for r0 in range(0, int(tab[i, 1]), 32)]
+            t = torch.tensor(np.asarray(pairs, dtype=np.int32).reshape(-1), device=device)
+            self.__dict__["_dev_slabs"] = t
+        return t
 
     def _leaf_table(self, device):
         self._ensure_flat()

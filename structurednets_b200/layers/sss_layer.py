@@ -59,7 +59,7 @@ def standard_dims_in_dims_out_computation(input_size: int, output_size: int, nb_
     return dims_in, dims_out
 
 
-def _identify_system(T_full: np.ndarray, dims_in, dims_out, statespace_dim: int):
+def _identify_system(T_full: np.ndarray, dims_in, dims_out, statespace_dim: int, device=None):
     """The state-space realisation of a dense matrix: tvsclib's Hankel-SVD identification when it is installed (the reference
     constructor, layers/sss_layer.py:66-68; a git-only, unpinned dependency, reference setup.py:33), otherwise this package's own
     implementation of the same method (structurednets_b200/sss_identification.py).  Either result is a valid realisation --
@@ -70,7 +70,7 @@ def _identify_system(T_full: np.ndarray, dims_in, dims_out, statespace_dim: int)
         from tvsclib.system_identification_svd import SystemIdentificationSVD
     except ImportError:
         from structurednets_b200.sss_identification import identify_mixed_system
-        return identify_mixed_system(T_full, dims_in, dims_out, statespace_dim)
+        return identify_mixed_system(T_full, dims_in, dims_out, statespace_dim, device=device)
     T_operator = ToeplitzOperator(T_full, dims_in, dims_out)
     S = SystemIdentificationSVD(toeplitz=T_operator, max_states_local=statespace_dim)
     return MixedSystem(S)
@@ -188,8 +188,8 @@ class SSSLayer(FlatParamsMixin, StructuredLayer):
         self.input_dim = input_dim
         self.nb_states = nb_states
 
-        self.init_state_matrices(nb_params_share=nb_params_share, initial_weight_matrix=initial_weight_matrix, initial_system_approx=initial_system_approx)
         self.use_gpu = use_gpu
+        self.init_state_matrices(nb_params_share=nb_params_share, initial_weight_matrix=initial_weight_matrix, initial_system_approx=initial_system_approx)
         self._flatten_parameters()
 
     def init_state_matrices(self, nb_params_share: float, initial_weight_matrix=None, initial_system_approx=None):
@@ -205,7 +205,9 @@ class SSSLayer(FlatParamsMixin, StructuredLayer):
             self.dims_in, self.dims_out = standard_dims_in_dims_out_computation(input_size=self.input_dim, output_size=self.output_dim, nb_states=self.nb_states)
 
             if initial_system_approx is None:
-                system_approx = _identify_system(T_full, self.dims_in, self.dims_out, self.statespace_dim)
+                # use_gpu also moves the Hankel SVDs of the initialisation to the GPU (cuSOLVER, float64)
+                svd_device = "cuda" if (getattr(self, "use_gpu", False) and torch.cuda.is_available()) else None
+                system_approx = _identify_system(T_full, self.dims_in, self.dims_out, self.statespace_dim, device=svd_device)
             else:
                 system_approx = pickle.loads(pickle.dumps(initial_system_approx))
 

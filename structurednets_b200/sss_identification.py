@@ -18,18 +18,39 @@ import numpy as np
 
 from structurednets_b200.synth import SyntheticMixedSystem, _Stage
 
+_SVD_DEVICE = None     # set by identify_mixed_system(device=...): the Hankel SVDs then run in cuSOLVER through torch.linalg.svd
+
+
+def _svd(H: np.ndarray):
+    if _SVD_DEVICE is None:
+        return np.linalg.svd(H, full_matrices=False)
+    import torch
+    U, S, Vt = torch.linalg.svd(torch.as_tensor(H, dtype=torch.float64, device=_SVD_DEVICE), full_matrices=False)
+    return U.cpu().numpy(), S.cpu().numpy(), Vt.cpu().numpy()
+
 
 def _factor(H: np.ndarray, max_states: int, rel_tol: float):
     """H ~ O R with O = U sqrt(S), R = sqrt(S) V^T, at most max_states columns; also returns pinv(R) = V / sqrt(S)."""
     if H.shape[0] == 0 or H.shape[1] == 0 or max_states <= 0:
         return np.zeros((H.shape[0], 0)), np.zeros((0, H.shape[1])), np.zeros((H.shape[1], 0))
-    U, S, Vt = np.linalg.svd(H, full_matrices=False)
+    U, S, Vt = _svd(H)
     d = int(min(max_states, np.sum(S > rel_tol * max(S[0], 1e-300))))
     rs = np.sqrt(S[:d])
     return U[:, :d] * rs, rs[:, None] * Vt[:d], Vt[:d].T / rs
 
 
-def identify_mixed_system(T, dims_in, dims_out, max_states: int, rel_tol: float = 1e-12) -> SyntheticMixedSystem:
+def identify_mixed_system(T, dims_in, dims_out, max_states: int, rel_tol: float = 1e-12, device=None) -> SyntheticMixedSystem:
+    """``device`` (e.g. "cuda"): run the 2 (n - 1) Hankel-block SVDs on that device in float64 (cuSOLVER via torch.linalg.svd) --
+    SURVEY.md section 8f rank 3, "GPU-side structured initialisation"; the realisation is the same up to the SVD's sign choices."""
+    global _SVD_DEVICE
+    prev, _SVD_DEVICE = _SVD_DEVICE, device
+    try:
+        return _identify(T, dims_in, dims_out, max_states, rel_tol)
+    finally:
+        _SVD_DEVICE = prev
+
+
+def _identify(T, dims_in, dims_out, max_states: int, rel_tol: float) -> SyntheticMixedSystem:
     T = np.asarray(T, dtype=np.float64)
     dims_in, dims_out = np.asarray(dims_in, dtype=int), np.asarray(dims_out, dtype=int)
     n = len(dims_in)

@@ -214,3 +214,26 @@ def test_input_gradients_of_the_layers_that_materialise_their_weight(built_lib, 
     psm = PSMLayer(96, 40, sparse_matrices=S)
     dense = [torch.tensor(s.toarray()).float() for s in S]
     check(psm, lambda x: O.psm_forward(x, dense, psm.bias.detach().cpu()), 96, 40)
+
+
+def test_structured_initialisation_on_the_gpu_matches_the_host(built_lib):
+    """Hankel-SVD identification of an SSS layer and the per-leaf truncated SVDs of an H-matrix layer
+    with the SVDs on the GPU (cuSOLVER through torch.linalg.svd, batched by leaf shape) give the same structured matrices as the
+    numpy path (the factors themselves are unique only up to signs / a state-space similarity)."""
+    from structurednets_b200.hmatrix.hmatrix import approximate_hmatrix
+    from structurednets_b200.sss_identification import identify_mixed_system
+    from structurednets_b200.synth import standard_dims
+    rng = np.random.default_rng(8080)
+    T = rng.uniform(-1, 1, size=(60, 96))
+    di, do = standard_dims(96, 60, 12)
+    host = identify_mixed_system(T, di, do, 4).to_matrix()
+    dev = identify_mixed_system(T, di, do, 4, device="cuda").to_matrix()
+    assert np.abs(host - dev).max() < 1e-9 * np.abs(host).max()
+    W = rng.uniform(-1, 1, size=(200, 256))
+    h_host = approximate_hmatrix(W, 0.3).to_dense_numpy()
+    h_dev = approximate_hmatrix(W, 0.3, device="cuda").to_dense_numpy()
+    assert np.abs(h_host - h_dev).max() < 1e-5 * np.abs(h_host).max()
+    layer = HMatLayer(256, 200, 0.3, initial_weight_matrix=W, use_gpu=True)       # constructor path
+    assert np.abs(layer.hmatrix.to_dense_numpy() - h_host).max() < 1e-5 * np.abs(h_host).max()
+    sss = SSSLayer(96, 60, 0.5, nb_states=12, initial_weight_matrix=T, use_gpu=True)
+    assert sss.statespace_dim > 0 and np.abs(sss.initial_weight_matrix - identify_mixed_system(T, di, do, sss.statespace_dim).to_matrix()).max() < 1e-8
