@@ -757,6 +757,16 @@ sss_bwd_kernel(sn_sss_plan plan, const float* __restrict__ packed, const float* 
                 h_in_off[u] = hdr[0]; h_in_dim[u] = hdr[1]; h_out_off[u] = hdr[2]; h_out_dim[u] = hdr[3]; h_d_in[u] = hdr[4]; h_d_out[u] = hdr[5];
             }
         }
+        // The header words above are ld.shared results that nothing has consumed yet: a barrier does not wait for loads in flight,
+        // and the bulk copy issued right after it overwrites the very words they read (seen as an intermittent, large gradient error:
+        // a stage's block accumulated with the NEXT chunk's dimensions).  Consume them before arriving.
+        {
+            int chk = 0;
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (warp + u * BWD_CONS < len) chk ^= h_in_off[u] ^ h_in_dim[u] ^ h_out_off[u] ^ h_out_dim[u] ^ h_d_in[u] ^ h_d_out[u];
+            asm volatile("{\n.reg .pred p;\nsetp.eq.s32 p, %0, 0x7fffffff;\n@p trap;\n}" ::"r"(chk) : "memory");
+        }
         named_bar_sync(1, BWD_THREADS);      // every warp is done with the parameter buffer and its history columns are complete
         if (threadIdx.x == 0 && ch > 0) {    // refill the parameter buffer for the next chunk; lands during the gradient phase
             const uint32_t bytes = (uint32_t)((cn.kk_end - cn.kk_begin) * sm.blk) * 4u;
