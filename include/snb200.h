@@ -206,10 +206,13 @@ typedef struct sn_psm_factor {
     float* grad_vals;
     float *val_fwd, *val_tr, *grad_packed;
 } sn_psm_factor;
+/* acts (nullable): sn_psm_acts_floats floats; the forward keeps the input of every factor but the last there ([B][cols_k] row-major,
+ * factor 0 first) and the backward reads them instead of recomputing them from x */
+size_t sn_psm_acts_floats(const sn_psm_factor* factors_host, int nf, int64_t B);
 int sn_psm_forward(const sn_psm_factor* factors_host, int nf, const float* x, int64_t ldx, float* y, int64_t ldy, const float* bias,
-                   int64_t B, int in_dim, int out_dim, sn_stream_t stream);
+                   float* acts, int64_t B, int in_dim, int out_dim, sn_stream_t stream);
 int sn_psm_backward(const sn_psm_factor* factors_host, int nf, const float* x, int64_t ldx, const float* grad_y, int64_t ldgy,
-                    float* grad_bias, int64_t B, int in_dim, int out_dim, sn_stream_t stream);
+                    const float* acts, float* grad_bias, int64_t B, int in_dim, int out_dim, sn_stream_t stream);
 
 /* Dense-product path of the PSM layer for large batches (csrc/psm.cu): the batch-independent product W = S_0 .. S_{n-1} is
  * multiplied out once per call (transposed prefix products, kept in `prefix` for the backward), applied / differentiated on the

@@ -104,9 +104,11 @@ def _declare(lib):
     lib.sn_hmat_project_grad.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, vp, vp]
     PF = POINTER(SnPsmFactor)
     lib.sn_psm_forward.restype = c_int
-    lib.sn_psm_forward.argtypes = [PF, i32, vp, i64, vp, i64, vp, i64, i32, i32, vp]
+    lib.sn_psm_forward.argtypes = [PF, i32, vp, i64, vp, i64, vp, vp, i64, i32, i32, vp]
     lib.sn_psm_backward.restype = c_int
-    lib.sn_psm_backward.argtypes = [PF, i32, vp, i64, vp, i64, vp, i64, i32, i32, vp]
+    lib.sn_psm_backward.argtypes = [PF, i32, vp, i64, vp, i64, vp, vp, i64, i32, i32, vp]
+    lib.sn_psm_acts_floats.restype = c_size_t
+    lib.sn_psm_acts_floats.argtypes = [PF, i32, i64]
     PD = POINTER(SnPsmDenseFactor)
     lib.sn_psm_dense_prefix_floats.restype = c_size_t
     lib.sn_psm_dense_prefix_floats.argtypes = [PD, i32, i32]

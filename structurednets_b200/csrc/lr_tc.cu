@@ -90,11 +90,15 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[1
 }
 constexpr int LF_THREADS = 192;
 constexpr int LF_STAGES = 5;
-constexpr int LF_TILE = 128 * 128;                    // 128 rows x 64 bf16 = 16 KB
+constexpr int LF_TILE = 128 * 128;                    // 128 rows x 64 bf16 = 16 KB (the A tile of the 64-sample variant uses half of it)
 constexpr int LF_STAGE = 2 * LF_TILE;                 // A tile | B tile
 constexpr int LF_MAX_OUT = 4096;                      // bias staged in shared memory
 constexpr size_t LF_SMEM = (size_t)LF_STAGES * LF_STAGE + 2 * LF_TILE + 1024 + 256 + LF_MAX_OUT * 4;
 
+// BM = samples per CTA: 128 (UMMA M = 128, thread = TMEM lane = sample) or 64 (UMMA M = 64: rows 16 q .. 16 q + 15 of the tile live in
+// the first 16 lanes of sub-partition q) -- at B = 8192 the 128-sample tiles fill only 64 of the 148 SMs and every CTA is bound by its
+// own share of the HBM bandwidth; 64-sample tiles double the CTAs in flight.
+template <int BM>
 __global__ void __launch_bounds__(LF_THREADS, 1)
 lr_tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_l,
                        const float* __restrict__ bias, bf16* __restrict__ hidden, bf16* __restrict__ y, long ldy, long B, int in_dim, int out_dim) {
@@ -111,7 +115,8 @@ lr_tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_empty + 2);
     float* sbias = reinterpret_cast<float*>(htile + 2 * LF_TILE + 256);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * 128;
+    const int m0 = blockIdx.x * BM;
+    constexpr uint32_t A_BYTES = BM * 128;            // BM rows x 64 bf16
     const int nkb = (in_dim + 63) / 64;
     const int ntile = (out_dim + 127) / 128;
     for (int i = threadIdx.x; i < ntile * 128; i += LF_THREADS) sbias[i] = (bias != nullptr && i < out_dim) ? __ldg(bias + i) : 0.f;
@@ -139,7 +144,7 @@ lr_tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                 const int s = it % LF_STAGES, round = it / LF_STAGES;
                 if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
                 uint8_t* st = smem + s * LF_STAGE;
-                mbar_expect_tx(full + s, 2 * LF_TILE);
+                mbar_expect_tx(full + s, A_BYTES + LF_TILE);
                 tma_load_2d(st, &map_x, kb * 64, m0, full + s);
                 tma_load_2d(st + LF_TILE, &map_r, kb * 64, 0, full + s);
             }
@@ -155,7 +160,7 @@ lr_tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, 128, false);
+            constexpr uint32_t idesc = make_idesc_bf16(BM, 128, false);
             int it = 0;
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int s = it % LF_STAGES, round = it / LF_STAGES;
@@ -190,8 +195,9 @@ lr_tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         }
     } else {
         const int q = warp & 3;
-        const int r = q * 32 + lane;                  // row of the tile = TMEM lane
-        const long row = (long)m0 + r;
+        const bool has_row = BM == 128 || lane < 16;  // M = 64: 16 rows per sub-partition, lanes 16..31 hold nothing
+        const int r = BM == 128 ? q * 32 + lane : q * 16 + (lane & 15);   // row of the tile
+        const long row = has_row ? (long)m0 + r : B;  // lanes without a row never store
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
         mbar_wait(h_full, 0);
         tc_fence_after();
@@ -211,10 +217,12 @@ lr_tc_fwd_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                 hp[0] = lo4;
                 hp[1] = hi4;
             }
-            uint8_t* trow = htile + (c0 >> 6) * LF_TILE + r * 128;
-            const int ch = (c0 & 63) >> 3;            // 16-byte chunk index of the first 8 columns within the 128-byte row
-            *reinterpret_cast<uint4*>(trow + (((ch) ^ (r & 7)) << 4)) = lo4;
-            *reinterpret_cast<uint4*>(trow + (((ch + 1) ^ (r & 7)) << 4)) = hi4;
+            if (has_row) {
+                uint8_t* trow = htile + (c0 >> 6) * LF_TILE + r * 128;
+                const int ch = (c0 & 63) >> 3;        // 16-byte chunk index of the first 8 columns within the 128-byte row
+                *reinterpret_cast<uint4*>(trow + (((ch) ^ (r & 7)) << 4)) = lo4;
+                *reinterpret_cast<uint4*>(trow + (((ch + 1) ^ (r & 7)) << 4)) = hi4;
+            }
         }
         tc_fence_before();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -268,6 +276,27 @@ int transpose_bf16(const bf16* src, long lds, bf16* dst, long ldd, long rows, in
     return 0;
 }
 
+// A second stream for the two halves of the backward that do not depend on each other (dL and the bias gradient next to gh -> dR):
+// each of the four kernels is a short, partly filled grid, so they overlap almost completely.  Fork / join with events keeps the
+// caller's stream semantics and is capturable in a CUDA graph.
+struct SideStream {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+inline SideStream* side_stream() {
+    static thread_local SideStream sd;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    if (sd.device != dev) {
+        if (cudaStreamCreateWithFlags(&sd.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        sd.device = dev;
+    }
+    return &sd;
+}
+
 inline int split_for(int tiles, long K) {
     int want = snb::ceil_div(148, tiles > 0 ? tiles : 1);
     long maxs = (K + 511) / 512;   // at least 512 of K per slice
@@ -300,12 +329,19 @@ int sn_lr_tc_forward(const void* x, int64_t ldx, const void* left_bf16, const vo
         const char* e = getenv("SNB200_LR_FUSED");
         const bool allow = !(e != nullptr && e[0] == '0');
         if (allow && rank == 128 && in_dim % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && out_dim <= LF_MAX_OUT - 128) {
+            const char* e64 = getenv("SNB200_LR_BM");
+            const bool bm64 = e64 != nullptr ? (e64[0] == '6') : ((B + 127) / 128 < 120);    // 128-sample tiles would leave SMs idle
             CUtensorMap mx, mr, ml;
-            if (int rc = make_map_bf16(&mx, x, (uint64_t)B, (uint64_t)in_dim, (uint64_t)ldx, 128)) return rc;
+            if (int rc = make_map_bf16(&mx, x, (uint64_t)B, (uint64_t)in_dim, (uint64_t)ldx, bm64 ? 64 : 128)) return rc;
             if (int rc = make_map_bf16(&mr, right_bf16, (uint64_t)rank, (uint64_t)in_dim, (uint64_t)in_dim, 128)) return rc;
             if (int rc = make_map_bf16(&ml, left_bf16, (uint64_t)out_dim, (uint64_t)rank, (uint64_t)rank, 128)) return rc;
-            SN_CHECK_CUDA(cudaFuncSetAttribute(lr_tc_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LF_SMEM));
-            SN_LAUNCH("lr_tc_fwd_fused_kernel", st, lr_tc_fwd_fused_kernel<<<(unsigned)((B + 127) / 128), LF_THREADS, LF_SMEM, st>>>(mx, mr, ml, bias, (bf16*)hidden, (bf16*)y, (long)ldy, (long)B, in_dim, out_dim));
+            if (bm64) {
+                SN_CHECK_CUDA(cudaFuncSetAttribute(lr_tc_fwd_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LF_SMEM));
+                SN_LAUNCH("lr_tc_fwd_fused_kernel", st, lr_tc_fwd_fused_kernel<64><<<(unsigned)((B + 63) / 64), LF_THREADS, LF_SMEM, st>>>(mx, mr, ml, bias, (bf16*)hidden, (bf16*)y, (long)ldy, (long)B, in_dim, out_dim));
+            } else {
+                SN_CHECK_CUDA(cudaFuncSetAttribute(lr_tc_fwd_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LF_SMEM));
+                SN_LAUNCH("lr_tc_fwd_fused_kernel", st, lr_tc_fwd_fused_kernel<128><<<(unsigned)((B + 127) / 128), LF_THREADS, LF_SMEM, st>>>(mx, mr, ml, bias, (bf16*)hidden, (bf16*)y, (long)ldy, (long)B, in_dim, out_dim));
+            }
             return 0;
         }
     }
@@ -323,13 +359,29 @@ int sn_lr_tc_backward(const void* x, int64_t ldx, const void* grad_y, int64_t ld
     if (B <= 0) return 0;
     cudaStream_t st = snb::as_stream(stream);
     using namespace snb::tc;
+    // side stream: bias gradient and dL (they need grad_y and the hidden activations only); main stream: gh, then dR
+    SideStream* sd = nullptr;
+    {
+        const char* e = getenv("SNB200_LR_SIDE_STREAM");
+        if (!(e != nullptr && e[0] == '0')) sd = side_stream();
+    }
+    cudaStream_t s2 = st;
+    if (sd != nullptr) {
+        SN_CHECK_CUDA(cudaEventRecord(sd->fork, st));
+        SN_CHECK_CUDA(cudaStreamWaitEvent(sd->stream, sd->fork, 0));
+        s2 = sd->stream;
+    }
     // gh = gy L : A = gy (B x out), B operand = L^T (rank x out), K = out
     if (int rc = gemm_bf16_tc<64, STORE_BF16>((int)B, rank, out_dim, grad_y, ldgy, left_t_bf16, lt_ld, ghid, rank, nullptr, 1.f, 1, st)) return rc;
     if (grad_bias) {
         dim3 grid(snb::ceil_div(out_dim, 256), (unsigned)((B + 63) / 64));
-        SN_LAUNCH("colsum_bf16_kernel", st, colsum_bf16_kernel<<<grid, 128, 0, st>>>((const bf16*)grad_y, ldgy, B, out_dim, grad_bias));
+        SN_LAUNCH("colsum_bf16_kernel", s2, colsum_bf16_kernel<<<grid, 128, 0, s2>>>((const bf16*)grad_y, ldgy, B, out_dim, grad_bias));
     }
     const bool mn_ok = (rank % 64 == 0);   // MN-major operands are fetched in 64-element blocks along M / N
+    {
+        cudaStream_t st_main = st;
+        cudaStream_t st = s2;      // the dL block below runs on the side stream
+        (void)st_main;
     if (grad_left) {   // dL += gy^T h
         const int tiles = snb::ceil_div(out_dim, 128) * snb::ceil_div(rank, 128);
         if (mn_ok) {   // operands read in their natural [sample][feature] layout through MN-major UMMA descriptors
@@ -340,6 +392,7 @@ int sn_lr_tc_backward(const void* x, int64_t ldx, const void* grad_y, int64_t ld
             if (int rc = gemm_bf16_tc<128, ATOMIC_F32>(out_dim, rank, (int)B, gyt, ldt, ht, ldt, grad_left, rank, nullptr, 1.f, split_for(tiles, B), st)) return rc;
         }
     }
+    }
     if (grad_right) {  // dR += gh^T x
         const int tiles = snb::ceil_div(rank, 128) * snb::ceil_div(in_dim, 128);
         if (mn_ok) {
@@ -349,6 +402,10 @@ int sn_lr_tc_backward(const void* x, int64_t ldx, const void* grad_y, int64_t ld
             if (int rc = transpose_bf16((const bf16*)x, ldx, (bf16*)xt, ldt, B, in_dim, st)) return rc;
             if (int rc = gemm_bf16_tc<128, ATOMIC_F32>(rank, in_dim, (int)B, ght, ldt, xt, ldt, grad_right, in_dim, nullptr, 1.f, split_for(tiles, B), st)) return rc;
         }
+    }
+    if (sd != nullptr) {
+        SN_CHECK_CUDA(cudaEventRecord(sd->join, sd->stream));
+        SN_CHECK_CUDA(cudaStreamWaitEvent(st, sd->join, 0));
     }
     return 0;
 }

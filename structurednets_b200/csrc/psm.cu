@@ -120,8 +120,22 @@ __device__ __forceinline__ void dvals_ell(const Ell& E, const float* g, const fl
     }
 }
 
+// dst[t0 + s][f] = src[f][s]   (each warp writes 32 consecutive floats of a sample row)
+__device__ __forceinline__ void store_tile(float* __restrict__ dst, long ld, long t0, long B, int dim, const float* src) {
+    for (int f = threadIdx.x; f < dim; f += PSM_THREADS) {
+        const float4 v = reinterpret_cast<const float4*>(src)[f];
+        if (t0 + 0 < B) dst[(size_t)(t0 + 0) * ld + f] = v.x;
+        if (t0 + 1 < B) dst[(size_t)(t0 + 1) * ld + f] = v.y;
+        if (t0 + 2 < B) dst[(size_t)(t0 + 2) * ld + f] = v.z;
+        if (t0 + 3 < B) dst[(size_t)(t0 + 3) * ld + f] = v.w;
+    }
+}
+
+// acts (nullable): the input of every factor but the last, [B][cols_k] row-major, factor 0 first -- kept for the backward, which then
+// needs no recomputation (two 16 KB rows per sample and factor through HBM against a whole sparse pass over the pattern)
 __global__ void __launch_bounds__(PSM_THREADS)
-psm_fwd_kernel(Chain ch, const float* __restrict__ x, long ldx, float* __restrict__ y, long ldy, const float* __restrict__ bias, long B) {
+psm_fwd_kernel(Chain ch, const float* __restrict__ x, long ldx, float* __restrict__ y, long ldy, const float* __restrict__ bias, long B,
+               float* __restrict__ acts) {
     extern __shared__ __align__(16) float smem[];
     float* a = smem;
     float* b = smem + (size_t)ch.maxdim * NS;
@@ -131,12 +145,43 @@ psm_fwd_kernel(Chain ch, const float* __restrict__ x, long ldx, float* __restric
     for (int k = ch.nf - 1; k >= 0; --k) {
         spmm_ell(ch.f[k].fwd, a, b);
         __syncthreads();
+        if (acts != nullptr && k > 0) {       // b = output of factor k = input of factor k - 1
+            size_t off = 0;
+            for (int j = 0; j < k - 1; ++j) off += (size_t)B * ch.f[j].cols;
+            store_tile(acts + off, ch.f[k - 1].cols, t0, B, ch.f[k - 1].cols, b);
+        }
         float* t = a; a = b; b = t;
     }
     for (int s = 0; s < NS; ++s) {
         if (t0 + s >= B) break;
         float* row = y + (size_t)(t0 + s) * ldy;
         for (int o = threadIdx.x; o < ch.out_dim; o += PSM_THREADS) row[o] = a[(size_t)o * NS + s] + (bias ? __ldg(bias + o) : 0.f);
+    }
+}
+
+// Backward with the activations the forward kept: two buffers.  G holds the gradient entering factor k from the output side, P the
+// input of factor k; after dS_k the product S_k^T G overwrites P and becomes the next G.
+__global__ void __launch_bounds__(PSM_THREADS)
+psm_bwd_acts_kernel(Chain ch, const float* __restrict__ x, long ldx, const float* __restrict__ gy, long ldgy, long B, const float* __restrict__ acts) {
+    extern __shared__ __align__(16) float smem[];
+    const size_t vec = (size_t)ch.maxdim * NS;
+    float* G = smem;
+    float* P = smem + vec;
+    const long t0 = (long)blockIdx.x * NS;
+    load_tile(gy, ldgy, t0, B, ch.out_dim, G);
+    size_t off = 0;
+    for (int k = 0; k < ch.nf; ++k) {
+        if (k == ch.nf - 1) load_tile(x, ldx, t0, B, ch.in_dim, P);
+        else load_tile(acts + off, ch.f[k].cols, t0, B, ch.f[k].cols, P);
+        off += (size_t)B * ch.f[k].cols;
+        __syncthreads();
+        dvals_ell(ch.f[k].fwd, G, P, ch.f[k].gpacked);
+        if (k + 1 < ch.nf) {
+            __syncthreads();                      // every warp is done reading P
+            spmm_ell(ch.f[k].tr, G, P);           // S_k^T G
+            __syncthreads();
+            float* t = G; G = P; P = t;
+        }
     }
 }
 
@@ -270,8 +315,14 @@ int check_dense_chain(const sn_psm_dense_factor* f, int nf, int in_dim, int out_
 
 extern "C" {
 
+size_t sn_psm_acts_floats(const sn_psm_factor* f, int nf, int64_t B) {
+    size_t n = 0;
+    for (int k = 0; f != nullptr && k + 1 < nf; ++k) n += (size_t)B * f[k].cols;
+    return n;
+}
+
 int sn_psm_forward(const sn_psm_factor* factors_host, int nf, const float* x, int64_t ldx, float* y, int64_t ldy, const float* bias,
-                   int64_t B, int in_dim, int out_dim, sn_stream_t stream) {
+                   float* acts, int64_t B, int in_dim, int out_dim, sn_stream_t stream) {
     Chain ch;
     if (int rc = make_chain(factors_host, nf, in_dim, out_dim, false, &ch)) return rc;
     SN_CHECK_ARG(x && y, "psm_forward: NULL buffer");
@@ -282,12 +333,12 @@ int sn_psm_forward(const sn_psm_factor* factors_host, int nf, const float* x, in
     const size_t smem = (size_t)2 * ch.maxdim * NS * sizeof(float);
     SN_CHECK_ARG(smem <= 227 * 1024, "psm_forward: factor dimension %d does not fit in shared memory", ch.maxdim);
     SN_CHECK_CUDA(cudaFuncSetAttribute(psm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SN_LAUNCH("psm_fwd_kernel", st, psm_fwd_kernel<<<(unsigned)((B + NS - 1) / NS), PSM_THREADS, smem, st>>>(ch, x, ldx, y, ldy, bias, B));
+    SN_LAUNCH("psm_fwd_kernel", st, psm_fwd_kernel<<<(unsigned)((B + NS - 1) / NS), PSM_THREADS, smem, st>>>(ch, x, ldx, y, ldy, bias, B, acts));
     return 0;
 }
 
 int sn_psm_backward(const sn_psm_factor* factors_host, int nf, const float* x, int64_t ldx, const float* grad_y, int64_t ldgy,
-                    float* grad_bias, int64_t B, int in_dim, int out_dim, sn_stream_t stream) {
+                    const float* acts, float* grad_bias, int64_t B, int in_dim, int out_dim, sn_stream_t stream) {
     Chain ch;
     if (int rc = make_chain(factors_host, nf, in_dim, out_dim, true, &ch)) return rc;
     SN_CHECK_ARG(x && grad_y, "psm_backward: NULL buffer");
@@ -301,10 +352,17 @@ int sn_psm_backward(const sn_psm_factor* factors_host, int nf, const float* x, i
         if (int rc = pack_vals(f.tr, f.vals, f.val_tr, st)) return rc;
         if (f.fwd.total > 0) SN_CHECK_CUDA(cudaMemsetAsync(f.grad_packed, 0, (size_t)f.fwd.total * sizeof(float), st));
     }
-    const size_t smem = (size_t)3 * ch.maxdim * NS * sizeof(float);
-    SN_CHECK_ARG(smem <= 227 * 1024, "psm_backward: factor dimension %d does not fit in shared memory", ch.maxdim);
-    SN_CHECK_CUDA(cudaFuncSetAttribute(psm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SN_LAUNCH("psm_bwd_kernel", st, psm_bwd_kernel<<<(unsigned)((B + NS - 1) / NS), PSM_THREADS, smem, st>>>(ch, x, ldx, grad_y, ldgy, B));
+    if (acts != nullptr) {
+        const size_t smem = (size_t)2 * ch.maxdim * NS * sizeof(float);
+        SN_CHECK_ARG(smem <= 227 * 1024, "psm_backward: factor dimension %d does not fit in shared memory", ch.maxdim);
+        SN_CHECK_CUDA(cudaFuncSetAttribute(psm_bwd_acts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SN_LAUNCH("psm_bwd_acts_kernel", st, psm_bwd_acts_kernel<<<(unsigned)((B + NS - 1) / NS), PSM_THREADS, smem, st>>>(ch, x, ldx, grad_y, ldgy, B, acts));
+    } else {
+        const size_t smem = (size_t)3 * ch.maxdim * NS * sizeof(float);
+        SN_CHECK_ARG(smem <= 227 * 1024, "psm_backward: factor dimension %d does not fit in shared memory", ch.maxdim);
+        SN_CHECK_CUDA(cudaFuncSetAttribute(psm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SN_LAUNCH("psm_bwd_kernel", st, psm_bwd_kernel<<<(unsigned)((B + NS - 1) / NS), PSM_THREADS, smem, st>>>(ch, x, ldx, grad_y, ldgy, B));
+    }
     for (int k = 0; k < nf; ++k) {
         const sn_psm_factor& f = factors_host[k];
         if (f.fwd.total > 0)

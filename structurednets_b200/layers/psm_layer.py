@@ -166,16 +166,22 @@ class _PSMFunction(torch.autograd.Function):
         assert all(v.dtype == torch.float32 and v.is_contiguous() for v in vals)
         arr = _factor_array(patterns, factors, None)
         y = torch.empty((B, layer.output_dim), dtype=torch.float32, device=U.device)
-        rc = _lib.lib().sn_psm_forward(arr, len(factors), _lib.ptr(U), U.stride(0), _lib.ptr(y), y.stride(0), _lib.ptr(bias), B,
+        # the inputs of the inner factors are kept for the backward (no recomputation) when anything takes a gradient
+        needs = any(ctx.needs_input_grad[3:]) or (bias is not None and ctx.needs_input_grad[1])
+        acts = None
+        if needs and len(factors) > 1:
+            acts = torch.empty(int(_lib.lib().sn_psm_acts_floats(arr, len(factors), B)), dtype=torch.float32, device=U.device)
+        rc = _lib.lib().sn_psm_forward(arr, len(factors), _lib.ptr(U), U.stride(0), _lib.ptr(y), y.stride(0), _lib.ptr(bias), _lib.ptr(acts), B,
                                        layer.input_dim, layer.output_dim, _lib.stream_ptr())
         _lib.check(rc, "sn_psm_forward")
-        ctx.layer, ctx.patterns, ctx.has_bias = layer, patterns, bias is not None
-        ctx.save_for_backward(U, *factors)
+        ctx.layer, ctx.patterns, ctx.has_bias, ctx.has_acts = layer, patterns, bias is not None, acts is not None
+        ctx.save_for_backward(U, acts if acts is not None else U.new_empty(0), *factors)
         return y
 
     @staticmethod
     def backward(ctx, grad_y):
-        U, *factors = ctx.saved_tensors
+        U, acts, *factors = ctx.saved_tensors
+        acts = acts if ctx.has_acts else None
         layer = ctx.layer
         if ctx.needs_input_grad[0]:
             raise RuntimeError("PSMLayer: the sparse-chain kernels do not return the gradient w.r.t. the input features; the dense-product "
@@ -184,7 +190,7 @@ class _PSMFunction(torch.autograd.Function):
         gvals = [torch.zeros(p._nnz(), dtype=torch.float32, device=U.device) for p in factors]
         gbias = torch.zeros(layer.output_dim, dtype=torch.float32, device=U.device) if ctx.has_bias else None
         arr = _factor_array(ctx.patterns, factors, gvals)
-        rc = _lib.lib().sn_psm_backward(arr, len(factors), _lib.ptr(U), U.stride(0), _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(gbias),
+        rc = _lib.lib().sn_psm_backward(arr, len(factors), _lib.ptr(U), U.stride(0), _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(acts), _lib.ptr(gbias),
                                         U.shape[0], layer.input_dim, layer.output_dim, _lib.stream_ptr())
         _lib.check(rc, "sn_psm_backward")
         # sparse gradients on the parameters' own (uncoalesced) pattern, like autograd's to_dense backward

@@ -34,7 +34,7 @@ def test_argument_errors_are_reported_not_thrown(built_lib):
     lib = _lib.lib()
     rc = lib.sn_sss_pack(None, None, None, None)
     assert rc != 0 and b"plan" in lib.sn_last_error_string()
-    rc = lib.sn_psm_forward(None, 0, None, 0, None, 0, None, 4, 3, 2, None)
+    rc = lib.sn_psm_forward(None, 0, None, 0, None, 0, None, None, 4, 3, 2, None)
     assert rc != 0 and b"psm" in lib.sn_last_error_string()
 
 
