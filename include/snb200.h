@@ -138,8 +138,9 @@ int sn_sss_tc_build(const sn_sss_tc_plan* plan_host, const float* params, float*
 int sn_sss_tc_forward(const sn_sss_tc_plan* plan_host, const float* coef, const float* x, int64_t ldx, float* y, int64_t ldy,
                       const float* bias, float* rbuf, float* states, int64_t B, sn_stream_t stream);
 int sn_sss_tc_backward(const sn_sss_tc_plan* plan_host, const float* params, const float* coef, const float* x, int64_t ldx,
-                       const float* grad_y, int64_t ldgy, const float* states, float* workspace, float* grad_params,
-                       float* grad_bias, int64_t B, sn_stream_t stream);
+                       const float* grad_y, int64_t ldgy, const float* states, float* workspace, float* grad_params, float* grad_bias,
+                       float* grad_x /* nullable: gradient w.r.t. the input features, (B x input_dim), written */, int64_t ldgx,
+                       int64_t B, sn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Low-rank layer, fp32 path -- replaces LRLayer.forward (layers/lr_layer.py:38-46) and its backward.

@@ -23,7 +23,7 @@ _lib.check(L.sn_sss_tc_forward(ps, _lib.ptr(tc["coef"]), _lib.ptr(Xd), Xd.stride
 gyd = torch.tensor(gy, device=dev)
 ws = torch.zeros(int(L.sn_sss_tc_backward_workspace_floats(ps, B)), device=dev)
 g = torch.zeros_like(flat); gb = torch.zeros(case["o"], device=dev)
-_lib.check(L.sn_sss_tc_backward(ps, _lib.ptr(flat), _lib.ptr(tc["coef"]), _lib.ptr(Xd), Xd.stride(0), _lib.ptr(gyd), gyd.stride(0), _lib.ptr(states), _lib.ptr(ws), _lib.ptr(g), _lib.ptr(gb), B, _lib.stream_ptr()), "bwd")
+_lib.check(L.sn_sss_tc_backward(ps, _lib.ptr(flat), _lib.ptr(tc["coef"]), _lib.ptr(Xd), Xd.stride(0), _lib.ptr(gyd), gyd.stride(0), _lib.ptr(states), _lib.ptr(ws), _lib.ptr(g), _lib.ptr(gb), None, 0, B, _lib.stream_ptr()), "bwd")
 torch.cuda.synchronize()
 wsn = ws.cpu().numpy()
 Lb = wsn[:nc*B*32].reshape(nc, B, 32)

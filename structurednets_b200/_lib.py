@@ -89,7 +89,7 @@ def _declare(lib):
     lib.sn_sss_tc_forward.restype = c_int
     lib.sn_sss_tc_forward.argtypes = [PT, vp, vp, i64, vp, i64, vp, vp, vp, i64, vp]
     lib.sn_sss_tc_backward.restype = c_int
-    lib.sn_sss_tc_backward.argtypes = [PT, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, i64, vp]
+    lib.sn_sss_tc_backward.argtypes = [PT, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, i64, i64, vp]
     lib.sn_lr_forward_f32.restype = c_int
     lib.sn_lr_forward_f32.argtypes = [vp, i64, vp, vp, vp, vp, vp, i64, i64, i32, i32, i32, vp]
     lib.sn_lr_backward_f32.restype = c_int

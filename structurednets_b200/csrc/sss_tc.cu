@@ -17,9 +17,11 @@
 //                                       straight from the natural [sample][feature] layouts), split over sample ranges
 //           6. sss_tc_build_bwd_kernel chain rule through the chunk-matrix construction: dM -> dA .. dG
 #include <stdlib.h>
+#include <vector>
 #include "common.cuh"
 #include "umma.cuh"
 #include "util.cuh"
+#include "gemm_f32.cuh"
 
 namespace {
 
@@ -2712,6 +2714,13 @@ sss_tc_build_bwd4_kernel(const sn_sss_stage* __restrict__ stages, int n, const s
     }
 }
 
+// Wsum[chunk][r][c] = W_hi + W_lo (the fp32 chunk matrix [T ; R ; R'] back from its split form), for the input-gradient GEMMs
+__global__ void sss_tc_wsum_kernel(const float* __restrict__ Wall, float* __restrict__ Wsum) {
+    const float* W = Wall + (size_t)blockIdx.x * WROWS * WCOLS;
+    float* o = Wsum + (size_t)blockIdx.x * 64 * WCOLS;
+    for (int e = threadIdx.x; e < 64 * WCOLS; e += blockDim.x) o[e] = W[e] + W[64 * WCOLS + e];
+}
+
 int check_tc_plan(const sn_sss_tc_plan* p) {
     SN_CHECK_ARG(p != nullptr, "sss_tc: NULL plan");
     SN_CHECK_ARG(p->nb_states > 0 && p->input_dim > 0 && p->output_dim > 0 && p->nchunks > 0, "sss_tc: non-positive plan dimension");
@@ -2785,7 +2794,8 @@ size_t sn_sss_tc_rbuf_floats(const sn_sss_tc_plan* p, int64_t B) {
 size_t sn_sss_tc_states_floats(const sn_sss_tc_plan* p, int64_t B) { return p == nullptr || B <= 0 ? 0 : (size_t)p->nchunks * B * 32; }
 size_t sn_sss_tc_backward_workspace_floats(const sn_sss_tc_plan* p, int64_t B) {
     if (p == nullptr || B <= 0) return 0;
-    return (size_t)p->nchunks * B * 32 + (size_t)p->nchunks * 64 * DMC + (size_t)p->nchunks * 2 * BB_SCR;
+    // adjoints L | dM | per-stage scratch of the one-thread-per-column build-backward kernels | W_hi + W_lo (input gradient only)
+    return (size_t)p->nchunks * B * 32 + (size_t)p->nchunks * 64 * DMC + (size_t)p->nchunks * 2 * BB_SCR + (size_t)p->nchunks * 64 * WCOLS;
 }
 
 int sn_sss_tc_build(const sn_sss_tc_plan* p, const float* params, float* coef, sn_stream_t stream) {
@@ -2869,7 +2879,8 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
 }
 
 int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float* coef, const float* x, int64_t ldx, const float* grad_y,
-                       int64_t ldgy, const float* states, float* workspace, float* grad_params, float* grad_bias, int64_t B, sn_stream_t stream) {
+                       int64_t ldgy, const float* states, float* workspace, float* grad_params, float* grad_bias, float* grad_x, int64_t ldgx,
+                       int64_t B, sn_stream_t stream) {
     if (int rc = check_tc_plan(p)) return rc;
     SN_CHECK_ARG(params && coef && x && grad_y && states && workspace && grad_params, "sss_tc_backward: NULL buffer");
     SN_CHECK_ARG(ldx >= p->input_dim && ldgy >= p->output_dim, "sss_tc_backward: leading dimension too small");
@@ -2897,6 +2908,23 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
         const unsigned ydim = use_split_scans(B) ? 2u : 1u;
         SN_LAUNCH("sss_tc_scan_bwd_q_kernel", st, sss_tc_scan_bwd_q_kernel<<<dim3((unsigned)((B + qs_threads / 4 - 1) / (qs_threads / 4)), ydim), qs_threads, 0, st>>>(p->chunks, p->nchunks, SC, grad_y, (long)ldgy,
                                                                                                                              L, grad_bias, (long)B, aligned));
+    }
+    if (grad_x != nullptr) {
+        // grad_u_j = [gy_j | lambda_{j+1} | mu_j] W_j  (W_j = [T_j ; R_j ; R'_j], 64 x 160): two small tensor-core GEMMs per chunk on the
+        // adjoints the scans just left in L.  Optional path (the reference training loop never asks for it, training_helpers.py:34).
+        SN_CHECK_ARG(ldgx >= p->input_dim, "sss_tc_backward: grad_x leading dimension too small");
+        float* Wsum = scratch + (size_t)p->nchunks * 2 * BB_SCR;
+        SN_LAUNCH("sss_tc_wsum_kernel", st, sss_tc_wsum_kernel<<<p->nchunks, 256, 0, st>>>(coef, Wsum));
+        std::vector<sn_sss_tc_chunk> hc(p->nchunks);
+        SN_CHECK_CUDA(cudaMemcpyAsync(hc.data(), p->chunks, sizeof(sn_sss_tc_chunk) * p->nchunks, cudaMemcpyDeviceToHost, st));
+        SN_CHECK_CUDA(cudaStreamSynchronize(st));      // the chunk table lives on the device; this optional path reads it back
+        for (int j = 0; j < p->nchunks; ++j) {
+            const float* Wj = Wsum + (size_t)j * 64 * WCOLS;
+            float* gxj = grad_x + hc[j].col0;
+            const int kout = hc[j].nrows;
+            if (int rc = snb::gemm_f32(false, false, (int)B, hc[j].ncols, kout, 1.f, grad_y + hc[j].row0, ldgy, Wj, WCOLS, 0.f, gxj, ldgx, nullptr, st)) return rc;
+            if (int rc = snb::gemm_f32(false, false, (int)B, hc[j].ncols, 32, 1.f, L + (size_t)j * B * 32, 32, Wj + (size_t)PO * WCOLS, WCOLS, 1.f, gxj, ldgx, nullptr, st, true)) return rc;
+        }
     }
     SN_CHECK_CUDA(cudaMemsetAsync(dM, 0, (size_t)p->nchunks * 64 * DMC * sizeof(float), st));
     CUtensorMap mx, mg, ml, ms;

@@ -105,8 +105,8 @@ class _SSSFunction(torch.autograd.Function):
         layer, plan = ctx.layer, ctx.plan
         U, ckpt, packed = ctx.saved_tensors
         if ctx.needs_input_grad[0]:
-            raise RuntimeError("SSSLayer: gradient w.r.t. the input features is not implemented "
-                               "(the reference training loop never requests it, training_helpers.py:34)")
+            raise RuntimeError("SSSLayer: the SIMT kernels (layers outside the tensor-core path's limits) do not return the gradient "
+                               "w.r.t. the input features; the tensor-core path does")
         grad_y = grad_y.contiguous()
         if grad_y.dtype != torch.float32:
             grad_y = grad_y.float()
@@ -150,9 +150,7 @@ class _SSSTCFunction(torch.autograd.Function):
     def backward(ctx, grad_y):
         layer, tc = ctx.layer, ctx.tc
         U, states = ctx.saved_tensors
-        if ctx.needs_input_grad[0]:
-            raise RuntimeError("SSSLayer: gradient w.r.t. the input features is not implemented "
-                               "(the reference training loop never requests it, training_helpers.py:34)")
+        grad_x = torch.empty_like(U) if ctx.needs_input_grad[0] else None
         grad_y = grad_y.contiguous()
         if grad_y.dtype != torch.float32:
             grad_y = grad_y.float()
@@ -165,9 +163,9 @@ class _SSSTCFunction(torch.autograd.Function):
         # tc["coef"] still holds the chunk matrices of the forward (rebuilt at every forward from the flat parameters)
         rc = L.sn_sss_tc_backward(ps, _lib.ptr(layer.__dict__["_flat"]), _lib.ptr(tc["coef"]), _lib.ptr(U), U.stride(0),
                                   _lib.ptr(grad_y), grad_y.stride(0), _lib.ptr(states), _lib.ptr(ws), _lib.ptr(g), _lib.ptr(gbias),
-                                  B, _lib.stream_ptr())
+                                  _lib.ptr(grad_x), grad_x.stride(0) if grad_x is not None else 0, B, _lib.stream_ptr())
         _lib.check(rc, "sn_sss_tc_backward")
-        return None, None, None
+        return grad_x, None, None
 
 
 class SSSLayer(FlatParamsMixin, StructuredLayer):

@@ -237,3 +237,25 @@ def test_structured_initialisation_on_the_gpu_matches_the_host(built_lib):
     assert np.abs(layer.hmatrix.to_dense_numpy() - h_host).max() < 1e-5 * np.abs(h_host).max()
     sss = SSSLayer(96, 60, 0.5, nb_states=12, initial_weight_matrix=T, use_gpu=True)
     assert sss.statespace_dim > 0 and np.abs(sss.initial_weight_matrix - identify_mixed_system(T, di, do, sss.statespace_dim).to_matrix()).max() < 1e-8
+
+
+@pytest.mark.parametrize("B", [64, 300])
+def test_sss_input_gradient_vs_oracle(built_lib, B):
+    """The tensor-core SSS path returns the gradient w.r.t. the input features (``grad_x`` nullable) from the
+    adjoints its scans compute anyway: grad_u_j = [gy_j | lambda_{j+1} | mu_j] W_j per chunk.  C1's layer, against autograd through
+    the oracle; the parameter gradients of the same backward must be unchanged."""
+    layer = SSSLayer(4096, 1000, 0.105, nb_states=500, initial_system_approx=random_mixed_system(4096, 1000, 500, 16, seed=1003))
+    rng = np.random.default_rng(1003)
+    X = rng.uniform(-1, 1, size=(B, 4096)).astype(np.float32); gy = rng.uniform(-1, 1, size=(B, 1000)).astype(np.float32) / B
+    l32 = [[p.detach().clone().requires_grad_(True) for p in getattr(layer, n)] for n in "ABCDEFG"]
+    xo = torch.tensor(X, requires_grad=True)
+    yo = O.sss_forward(xo, *l32, layer.bias.detach().clone(), layer.dims_in, layer.dims_out); (yo * torch.tensor(gy)).sum().backward()
+    layer = layer.to(DEV)
+    xd = torch.tensor(X, device=DEV, requires_grad=True)
+    y = layer(xd); (y * torch.tensor(gy, device=DEV)).sum().backward()
+    assert xd.grad is not None and xd.grad.shape == (B, 4096)
+    assert rel_err(xd.grad.cpu().numpy(), xo.grad.numpy()) < RTOL
+    assert rms_rel_err(xd.grad.cpu().numpy(), xo.grad.numpy()) < RTOL
+    got = np.concatenate([p.grad.detach().cpu().numpy().reshape(-1) for p in layer.B])
+    ref = np.concatenate([(p.grad.numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32)).reshape(-1) for p in l32[1]])
+    assert rel_err(got, ref) < RTOL

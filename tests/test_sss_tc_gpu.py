@@ -95,7 +95,7 @@ def test_each_kernel_against_the_emulator(case, fused, chain, built_lib, monkeyp
     g = torch.zeros_like(flat)
     gb = torch.zeros(case["o"], device=dev)
     _lib.check(L.sn_sss_tc_backward(ps, _lib.ptr(flat), _lib.ptr(tc["coef"]), _lib.ptr(Xd), Xd.stride(0), _lib.ptr(gyd), gyd.stride(0),
-                                    _lib.ptr(states), _lib.ptr(ws), _lib.ptr(g), _lib.ptr(gb), B, _lib.stream_ptr()), "backward")
+                                    _lib.ptr(states), _lib.ptr(ws), _lib.ptr(g), _lib.ptr(gb), None, 0, B, _lib.stream_ptr()), "backward")
     torch.cuda.synchronize()
     wsn = ws.cpu().numpy()
     dM = wsn[nc * B * 32: nc * B * 32 + nc * 64 * 192].reshape(nc, 64, 192)
