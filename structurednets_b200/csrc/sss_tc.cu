@@ -1574,6 +1574,288 @@ sss_tc_scan_bwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
 }
 
 // ------------------------------------------------------------------------------------------
+// 3m/4m. small-batch chunk scans on the warp-level tensor cores (mma.sync m16n8k8 tf32, 3xTF32).  The four-threads-per-sample
+//    scans above are instruction-bound (ncu at 8 192 samples: 219 warp instructions per chunk step and 8 samples for 64 useful
+//    FFMA issues).  Here a warp owns 16 samples and keeps their state as the D fragment of a 16 x 16 tile; a step is
+//        state' = r + state Phi^T      (r is the accumulator's initial value, the previous D fragment is the next A fragment --
+//                                       same register chaining as the build kernel, no shuffle, no shared-memory round trip)
+//    with Phi / O staged in shared memory through a ring of QM slots filled QM - 1 steps ahead.  ~5x fewer instructions per sample.
+//    Requires the 16-byte aligned layouts (`aligned`); otherwise the SIMT scans run.
+// ------------------------------------------------------------------------------------------
+constexpr int QM = 4;                       // ring slots (shared memory: coefficients)
+constexpr int QPF = 4;                      // register ring depth (per-sample rows from HBM)
+constexpr int SM_THREADS = 128;             // 4 warps x 16 samples
+template <int N>
+__device__ __forceinline__ void cp_async_wait_n() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// (hi, lo) parts of the B fragment (M[row][col], M[row][col + 1]) of a row-major matrix with 16 columns in shared memory
+__device__ __forceinline__ void frag_b16(const float* M, int row, int col, float2& hi, float2& lo) {
+    const float2 r = *reinterpret_cast<const float2*>(M + row * DS + col);
+    hi.x = tf32_hi(r.x); hi.y = tf32_hi(r.y);
+    lo.x = tf32_hi(r.x - hi.x); lo.y = tf32_hi(r.y - hi.y);
+}
+// A fragment with the K index permuted like split_frag's (logical k = t <-> physical column 2t, k = t + 4 <-> 2t + 1 of the group of 8),
+// from two consecutive floats of rows g and g + 8
+__device__ __forceinline__ void frag_a_from(const float2 row_a, const float2 row_b, Frag3& f) {
+    const float v[4] = {row_a.x, row_b.x, row_a.y, row_b.y};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float h = tf32_hi(v[i]);
+        f.hi[i] = __float_as_uint(h);
+        f.lo[i] = __float_as_uint(tf32_hi(v[i] - h));
+    }
+}
+
+// forward state chains: blockIdx.y = direction (0: s_{j+1} = r_j + Phi_j s_j ascending, 1: e_j = r'_j + Phi'_j e_{j+1} descending);
+// saves the state ENTERING every chunk: S[j][row][0..15] = s_j, S[j][row][16..31] = e_{j+1}
+__global__ void __launch_bounds__(SM_THREADS)
+sss_tc_scan_states_m_kernel(int nchunks, const float* __restrict__ SCall, const float* __restrict__ rbuf, float* __restrict__ S, long B) {
+    __shared__ __align__(16) float sc[QM][DS * DS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, dir = blockIdx.y;
+    const long row0 = ((long)blockIdx.x * (SM_THREADS / 32) + warp) * 16;
+    const long rowa = row0 + g, rowb = row0 + g + 8;
+    const bool va = rowa < B, vb = rowb < B;
+    const size_t NB = (size_t)nchunks * B;
+    const float* Rin = rbuf + NB * 32 + (dir ? NB * 16 : 0);     // r (causal) or r' (anticausal) rows, [chunk][B][16]
+    const int phi_off = dir * DS * DS;
+    auto chunk_at = [&](int jj) { return dir ? nchunks - 1 - jj : jj; };
+    auto issue = [&](int jj) {
+        if (jj < nchunks) {
+            const float* src = SCall + (size_t)chunk_at(jj) * SCF + phi_off;
+            for (int i = threadIdx.x; i < DS * DS / 4; i += SM_THREADS) cp_async16(sc[jj % QM] + 4 * i, src + 4 * i);
+        }
+        cp_async_commit();
+    };
+    auto load_r = [&](int jj, float2 (&rv)[2][2]) {     // [n-tile][row a / b]: the step's r values in accumulator layout
+        const float2 z = make_float2(0.f, 0.f);
+        if (jj < nchunks) {
+            const size_t base = (size_t)chunk_at(jj) * B;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                rv[nt][0] = va ? __ldg(reinterpret_cast<const float2*>(Rin + (base + rowa) * 16 + 8 * nt + 2 * t)) : z;
+                rv[nt][1] = vb ? __ldg(reinterpret_cast<const float2*>(Rin + (base + rowb) * 16 + 8 * nt + 2 * t)) : z;
+            }
+        }
+    };
+#pragma unroll
+    for (int s0 = 0; s0 < QM - 1; ++s0) issue(s0);
+    float d[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d[nt][k] = 0.f;
+    // the r rows come from HBM (each is read exactly once): a register ring keeps QPF steps of them in flight -- with one step of
+    // lookahead every step waited ~1 us on the accumulator's initial value (ncu: half of all samples on the first HMMA of the step)
+    float2 rq[QPF][2][2];
+#pragma unroll
+    for (int u = 0; u < QPF; ++u) load_r(u, rq[u]);
+    for (int jj0 = 0; jj0 < nchunks; jj0 += QPF) {
+#pragma unroll
+        for (int u = 0; u < QPF; ++u) {
+            const int jj = jj0 + u;
+            if (jj >= nchunks) break;
+            cp_async_wait_n<QM - 2>();
+            __syncthreads();
+            issue(jj + QM - 1);
+            const int j = chunk_at(jj);
+            const float* Phi = sc[jj % QM];
+            // the state entering chunk j
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                if (va) *reinterpret_cast<float2*>(S + ((size_t)j * B + rowa) * 32 + (dir ? DS : 0) + 8 * nt + 2 * t) = make_float2(d[nt][0], d[nt][1]);
+                if (vb) *reinterpret_cast<float2*>(S + ((size_t)j * B + rowb) * 32 + (dir ? DS : 0) + 8 * nt + 2 * t) = make_float2(d[nt][2], d[nt][3]);
+            }
+            Frag3 a[2];
+            split_frag(d[0], a[0]);
+            split_frag(d[1], a[1]);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                float acc[4] = {rq[u][nt][0].x, rq[u][nt][0].y, rq[u][nt][1].x, rq[u][nt][1].y};
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    float2 bh, bl;
+                    frag_b16(Phi, 8 * nt + g, 8 * ks + 2 * t, bh, bl);      // B[k <-> a][n = b] = Phi[b][a]
+                    mma3(acc, a[ks], bh, bl);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) d[nt][k] = acc[k];
+            }
+            load_r(jj + QPF, rq[u]);
+        }
+    }
+    cp_async_wait_all();
+}
+
+// outputs y_j = yloc_j + O_j s_j + O'_j e_{j+1} + b, parallel over (sample, chunk): grid (ceil(B / (64 * QMO_SUB)), nchunks); a warp
+// walks QMO_SUB sub-tiles of 16 samples with the chunk's 16 B fragments (K = [s | e] = 32, N = 32 outputs) split once, in registers.
+constexpr int QMO_SUB = 2;
+__global__ void __launch_bounds__(SM_THREADS)
+sss_tc_scan_out_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, const float* __restrict__ SCall, const float* __restrict__ rbuf,
+                         const float* __restrict__ S, float* __restrict__ y, long ldy, const float* __restrict__ bias, long B) {
+    __shared__ __align__(16) float sc[2 * PO * DS];       // O (32 x 16) then O' (32 x 16)
+    const int j = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const sn_sss_tc_chunk c = chunks[j];
+    for (int i = threadIdx.x; i < 2 * PO * DS / 4; i += SM_THREADS)
+        reinterpret_cast<float4*>(sc)[i] = __ldg(reinterpret_cast<const float4*>(SCall + (size_t)j * SCF + 2 * DS * DS) + i);
+    __syncthreads();
+    // B fragments: k-steps 0, 1 = s (O), 2, 3 = e (O'); n-tiles 0..3 = outputs 8 nt .. 8 nt + 7
+    float2 bh[4][4], bl[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) frag_b16(sc + (ks >> 1) * PO * DS, 8 * nt + g, 8 * (ks & 1) + 2 * t, bh[ks][nt], bl[ks][nt]);
+    float2 bias2[4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const int n = 8 * nt + 2 * t;
+        bias2[nt].x = (bias != nullptr && n < c.nrows) ? __ldg(bias + c.row0 + n) : 0.f;
+        bias2[nt].y = (bias != nullptr && n + 1 < c.nrows) ? __ldg(bias + c.row0 + n + 1) : 0.f;
+    }
+    const float2 z = make_float2(0.f, 0.f);
+    // loads of ALL the warp's sub-tiles first (they come from HBM / L2 and nothing else hides their latency), arithmetic afterwards
+    float2 av[QMO_SUB][4][2], yl[QMO_SUB][4][2];
+#pragma unroll
+    for (int u = 0; u < QMO_SUB; ++u) {
+        const long row0 = (((long)blockIdx.x * QMO_SUB + u) * (SM_THREADS / 32) + warp) * 16;
+        const long rowa = row0 + g, rowb = row0 + g + 8;
+        const bool va = rowa < B, vb = rowb < B;
+        const float* sa = S + ((size_t)j * B + rowa) * 32;
+        const float* sb = S + ((size_t)j * B + rowb) * 32;
+        const float* ya = rbuf + ((size_t)j * B + rowa) * 32;
+        const float* yb = rbuf + ((size_t)j * B + rowb) * 32;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            av[u][ks][0] = va ? __ldg(reinterpret_cast<const float2*>(sa + 8 * ks + 2 * t)) : z;
+            av[u][ks][1] = vb ? __ldg(reinterpret_cast<const float2*>(sb + 8 * ks + 2 * t)) : z;
+            yl[u][ks][0] = va ? __ldg(reinterpret_cast<const float2*>(ya + 8 * ks + 2 * t)) : z;
+            yl[u][ks][1] = vb ? __ldg(reinterpret_cast<const float2*>(yb + 8 * ks + 2 * t)) : z;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < QMO_SUB; ++u) {
+        const long row0 = (((long)blockIdx.x * QMO_SUB + u) * (SM_THREADS / 32) + warp) * 16;
+        const long rowa = row0 + g, rowb = row0 + g + 8;
+        const bool va = rowa < B, vb = rowb < B;
+        Frag3 a[4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) frag_a_from(av[u][ks][0], av[u][ks][1], a[ks]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            float acc[4] = {yl[u][nt][0].x + bias2[nt].x, yl[u][nt][0].y + bias2[nt].y, yl[u][nt][1].x + bias2[nt].x, yl[u][nt][1].y + bias2[nt].y};
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) mma3(acc, a[ks], bh[ks][nt], bl[ks][nt]);
+            const int n = 8 * nt + 2 * t;
+            if (n + 1 < c.nrows) {
+                if (va) *reinterpret_cast<float2*>(y + rowa * ldy + c.row0 + n) = make_float2(acc[0], acc[1]);
+                if (vb) *reinterpret_cast<float2*>(y + rowb * ldy + c.row0 + n) = make_float2(acc[2], acc[3]);
+            } else if (n < c.nrows) {
+                if (va) y[rowa * ldy + c.row0 + n] = acc[0];
+                if (vb) y[rowb * ldy + c.row0 + n] = acc[2];
+            }
+        }
+    }
+}
+
+// adjoint chains: blockIdx.y = 0: lambda_j = Phi_j^T lambda_{j+1} + O_j^T gy_j (descending), 1: mu likewise with Phi', O' (ascending).
+// L[j][row][0..15] = lambda_{j+1}, L[j][row][16..31] = mu_j: the adjoint of the state LEAVING chunk j, i.e. the value before the step.
+// Slot layout: PhiT [16][16] (PhiT[a][b] = Phi[b][a]) then OT [16][32] (OT[a][r] = O[r][a]), transposed while staging so that the B
+// fragments are 8-byte loads.
+__global__ void __launch_bounds__(SM_THREADS)
+sss_tc_scan_bwd_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, const float* __restrict__ SCall, const float* __restrict__ gy,
+                         long ldgy, float* __restrict__ L, long B) {
+    __shared__ __align__(16) float sc[QM][DS * DS + DS * PO];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, mu = blockIdx.y;
+    const long row0 = ((long)blockIdx.x * (SM_THREADS / 32) + warp) * 16;
+    const long rowa = row0 + g, rowb = row0 + g + 8;
+    const bool va = rowa < B, vb = rowb < B;
+    const int phi_off = mu ? DS * DS : 0, o_off = 2 * DS * DS + (mu ? PO * DS : 0);
+    auto chunk_at = [&](int jj) { return mu ? jj : nchunks - 1 - jj; };
+    auto issue = [&](int jj) {
+        if (jj < nchunks) {
+            const float* src = SCall + (size_t)chunk_at(jj) * SCF;
+            float* dst = sc[jj % QM];
+            for (int e = threadIdx.x; e < DS * DS; e += SM_THREADS) cp_async4(dst + (e & 15) * DS + (e >> 4), src + phi_off + e);               // Phi[b][a] -> PhiT[a][b]
+            for (int e = threadIdx.x; e < PO * DS; e += SM_THREADS) cp_async4(dst + DS * DS + (e & 15) * PO + (e >> 4), src + o_off + e);      // O[r][a] -> OT[a][r]
+        }
+        cp_async_commit();
+    };
+    // grad_y of the chunk as A fragments (K = the chunk's 32 output rows, permuted like split_frag): 8-byte loads, zero past nrows
+    auto load_g = [&](int jj, float2 (&gv)[4][2]) {
+        const float2 z = make_float2(0.f, 0.f);
+        if (jj < nchunks) {
+            const sn_sss_tc_chunk c = chunks[chunk_at(jj)];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int r = 8 * ks + 2 * t;
+                float2 x0 = z, x1 = z;
+                if (r + 1 < c.nrows) {
+                    if (va) x0 = __ldg(reinterpret_cast<const float2*>(gy + rowa * ldgy + c.row0 + r));
+                    if (vb) x1 = __ldg(reinterpret_cast<const float2*>(gy + rowb * ldgy + c.row0 + r));
+                } else if (r < c.nrows) {
+                    if (va) x0.x = __ldg(gy + rowa * ldgy + c.row0 + r);
+                    if (vb) x1.x = __ldg(gy + rowb * ldgy + c.row0 + r);
+                }
+                gv[ks][0] = x0; gv[ks][1] = x1;
+            }
+        }
+    };
+#pragma unroll
+    for (int s0 = 0; s0 < QM - 1; ++s0) issue(s0);
+    float d[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d[nt][k] = 0.f;
+    float2 gq[QPF][4][2];
+#pragma unroll
+    for (int u = 0; u < QPF; ++u) load_g(u, gq[u]);
+    for (int jj0 = 0; jj0 < nchunks; jj0 += QPF) {
+#pragma unroll
+        for (int u = 0; u < QPF; ++u) {
+            const int jj = jj0 + u;
+            if (jj >= nchunks) break;
+            cp_async_wait_n<QM - 2>();
+            __syncthreads();
+            issue(jj + QM - 1);
+            const int j = chunk_at(jj);
+            const float* PhiT = sc[jj % QM];
+            const float* OT = PhiT + DS * DS;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                if (va) *reinterpret_cast<float2*>(L + ((size_t)j * B + rowa) * 32 + (mu ? DS : 0) + 8 * nt + 2 * t) = make_float2(d[nt][0], d[nt][1]);
+                if (vb) *reinterpret_cast<float2*>(L + ((size_t)j * B + rowb) * 32 + (mu ? DS : 0) + 8 * nt + 2 * t) = make_float2(d[nt][2], d[nt][3]);
+            }
+            Frag3 a[2], ag[4];
+            split_frag(d[0], a[0]);
+            split_frag(d[1], a[1]);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) frag_a_from(gq[u][ks][0], gq[u][ks][1], ag[ks]);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {      // O^T gy: B[k <-> r][n = a] = O[r][a] = OT[a][r]
+                    const float2 r2 = *reinterpret_cast<const float2*>(OT + (8 * nt + g) * PO + 8 * ks + 2 * t);
+                    float2 bh, bl;
+                    bh.x = tf32_hi(r2.x); bh.y = tf32_hi(r2.y); bl.x = tf32_hi(r2.x - bh.x); bl.y = tf32_hi(r2.y - bh.y);
+                    mma3(acc, ag[ks], bh, bl);
+                }
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {      // Phi^T adjoint: B[k <-> b][n = a] = Phi[b][a] = PhiT[a][b]
+                    float2 bh, bl;
+                    frag_b16(PhiT, 8 * nt + g, 8 * ks + 2 * t, bh, bl);
+                    mma3(acc, a[ks], bh, bl);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) d[nt][k] = acc[k];
+            }
+            load_g(jj + QPF, gq[u]);
+        }
+    }
+    cp_async_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------
 // 3''/4''. chunk scans on the tensor core.  A scan step is state' = in + M state with a 16 x 16 (plus output rows) matrix per
 //    chunk -- serial in the chunk index, but for 128 samples at once it is one tiny UMMA: A = the tile's state vectors
 //    [128 x (hi 16 | lo 16)] written to shared memory by the epilogue threads (thread = sample), B = the chunk's packed, pre-split
@@ -2772,6 +3054,12 @@ int build_mode() {
 }
 bool use_quad_build() { return build_mode() >= 1; }
 
+// small-batch scans on the warp-level tensor cores (default) or the SIMT four-threads-per-sample kernels (SNB200_SSS_SCAN=simt)
+bool use_mma_scans() {
+    const char* e = getenv("SNB200_SSS_SCAN");
+    return !(e != nullptr && e[0] == 's');
+}
+
 // SIMT scans: split by direction (+ a parallel output kernel) by default; SNB200_SSS_SPLIT_SCANS=0 keeps the single-kernel scans
 bool use_split_scans(int64_t B) {
     (void)B;
@@ -2867,6 +3155,11 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
         SN_LAUNCH("sss_tc_chain_fwd_kernel", st, sss_tc_chain_fwd_kernel<<<ntiles, CH_THREADS, CHF_SMEM, st>>>(mc, mi, my, p->chunks, p->nchunks, rbuf, states, y, (long)ldy, bias, (long)B, aligned));
         return 0;
     }
+    if (use_mma_scans() && aligned && ((reinterpret_cast<uintptr_t>(y) & 7) == 0) && (ldy & 1) == 0) {
+        SN_LAUNCH("sss_tc_scan_states_m_kernel", st, sss_tc_scan_states_m_kernel<<<dim3((unsigned)((B + 63) / 64), 2), SM_THREADS, 0, st>>>(p->nchunks, SC, rbuf, states, (long)B));
+        SN_LAUNCH("sss_tc_scan_out_m_kernel", st, sss_tc_scan_out_m_kernel<<<dim3((unsigned)((B + 64 * QMO_SUB - 1) / (64 * QMO_SUB)), p->nchunks), SM_THREADS, 0, st>>>(p->chunks, SC, rbuf, states, y, (long)ldy, bias, (long)B));
+        return 0;
+    }
     const int qs_threads = B <= 16384 ? 64 : QS_THREADS;
     if (use_split_scans(B)) {
         SN_LAUNCH("sss_tc_scan_states_q_kernel", st, sss_tc_scan_states_q_kernel<<<dim3((unsigned)((B + qs_threads / 4 - 1) / (qs_threads / 4)), 2), qs_threads, 0, st>>>(p->nchunks, SC, rbuf, states, (long)B));
@@ -2902,6 +3195,10 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHB_SMEM));
         SN_LAUNCH("sss_tc_chain_bwd_kernel", st, sss_tc_chain_bwd_kernel<<<dim3((unsigned)((B + 127) / 128), 2), CHB_THREADS, CHB_SMEM, st>>>(mc, mgy, p->chunks, p->nchunks, L, grad_bias, (long)B));
         if (p->nchunks == 1 && grad_bias != nullptr)
+            if (int rc = snb::colsum_accumulate(grad_y, ldgy, B, p->output_dim, grad_bias, st)) return rc;
+    } else if (use_mma_scans() && aligned) {
+        SN_LAUNCH("sss_tc_scan_bwd_m_kernel", st, sss_tc_scan_bwd_m_kernel<<<dim3((unsigned)((B + 63) / 64), 2), SM_THREADS, 0, st>>>(p->chunks, p->nchunks, SC, grad_y, (long)ldgy, L, (long)B));
+        if (grad_bias != nullptr)
             if (int rc = snb::colsum_accumulate(grad_y, ldgy, B, p->output_dim, grad_bias, st)) return rc;
     } else {
         const int qs_threads = B <= 16384 ? 64 : QS_THREADS;
