@@ -406,6 +406,16 @@ class FlatAdam(FlatSGD):
     def _loose_optimizer(loose, lr):
         return torch.optim.Adam(loose, lr=lr)
 
+    # the warm-up passes of a CUDA-graph capture must leave no trace in the moment estimates or the step counter
+    def snapshot_state(self):
+        return None if self.flat_p is None else (self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_dev.clone(), self.step_host)
+
+    def restore_state(self, snap):
+        if snap is not None:
+            with torch.no_grad():
+                self.exp_avg.copy_(snap[0]); self.exp_avg_sq.copy_(snap[1]); self.step_dev.copy_(snap[2])
+            self.step_host = snap[3]
+
     def _flat_step(self):
         if self.flat_p.is_cuda:
             from structurednets_b200 import _lib
@@ -444,6 +454,7 @@ class _GraphedStep:
             return loss.detach()
 
         params = [p.detach().clone() for p in model.parameters()]      # the warm-up steps must not train
+        opt_state = optimizer.snapshot_state() if hasattr(optimizer, "snapshot_state") else None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -453,11 +464,15 @@ class _GraphedStep:
         with torch.no_grad():
             for p, q in zip(model.parameters(), params):
                 p.copy_(q)
+        if hasattr(optimizer, "restore_state"):
+            optimizer.restore_state(opt_state)
         with torch.cuda.graph(self.graph):
             self.loss = body()
         with torch.no_grad():                                            # the capture itself does not run the kernels, but be explicit
             for p, q in zip(model.parameters(), params):
                 p.copy_(q)
+        if hasattr(optimizer, "restore_state"):
+            optimizer.restore_state(opt_state)
 
     def __call__(self, sel):
         self.sel.copy_(sel, non_blocking=True)

@@ -196,3 +196,85 @@ def test_live_reference_train_when_the_reference_tree_is_present():
         out.append(([float(v) for v in res[1:5]], [[float(v) for v in h] for h in res[5:9]], res[0].weight.detach().numpy()))
     assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
     np.testing.assert_array_equal(out[0][2], out[1][2])
+
+
+@pytest.mark.gpu
+def test_fused_loss_kernels_match_torch(built_lib):
+    """sn_ce_loss / sn_mse_loss (csrc/train.cu) through FusedLoss: loss value, gradient of the model output and the number of correct
+    predictions against torch.nn.CrossEntropyLoss / MSELoss + argmax (reference training_helpers.py:10-29,57-73)."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for B, C in ((256, 1000), (77, 10), (1000, 24)):
+        logits = (torch.randn((B, C), device="cuda", generator=g) * 3).requires_grad_(True)
+        target = torch.randint(0, C, (B,), device="cuda", generator=g)
+        ref = torch.nn.CrossEntropyLoss()(logits, target)
+        gref, = torch.autograd.grad(ref, logits)
+        fused = TH.FusedLoss(torch.nn.CrossEntropyLoss, "cuda")
+        loss = fused(logits, target)
+        gf, = torch.autograd.grad(loss, logits)
+        assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+        assert float((gf - gref).abs().max()) < 1e-6 * float(gref.abs().max()) + 1e-9
+        assert int(fused.correct) == int((logits.argmax(1) == target).sum())
+        onehot = torch.nn.functional.one_hot(target, C).float()
+        refm = torch.nn.MSELoss()(logits, onehot)
+        gm, = torch.autograd.grad(refm, logits)
+        fm = TH.FusedLoss(torch.nn.MSELoss, "cuda")
+        lm = fm(logits, onehot)
+        gfm, = torch.autograd.grad(lm, logits)
+        assert abs(float(lm) - float(refm)) < 1e-5 * abs(float(refm))
+        assert float((gfm - gm).abs().max()) < 1e-6 * float(gm.abs().max()) + 1e-12
+        assert int(fm.correct) == int((logits.argmax(1) == target).sum())
+    # accumulation over batches + reset, evaluation under no_grad
+    fused = TH.FusedLoss(torch.nn.CrossEntropyLoss, "cuda")
+    with torch.no_grad():
+        a = fused(logits.detach()[:100], target[:100]); b = fused(logits.detach()[100:], target[100:])
+    assert abs(float(fused.loss_sum) - float(a) - float(b)) < 1e-5
+    fused.reset()
+    assert float(fused.loss_sum) == 0.0 and int(fused.correct) == 0
+
+
+@pytest.mark.gpu
+def test_flat_adam_and_sgd_kernels_match_torch(built_lib):
+    """FlatAdam / FlatSGD (sn_flat_adam / sn_flat_sgd over the layer's flat buffers) against torch.optim.Adam / SGD over the parameter
+    views, ten steps of synthetic gradients; grad_scale folds the data-parallel 1 / world factor in."""
+    from structurednets_b200.layers.lr_layer import LRLayer
+    for cls, tcls, kw in ((TH.FlatAdam, torch.optim.Adam, {}), (TH.FlatSGD, torch.optim.SGD, {})):
+        np.random.seed(1)
+        la = LRLayer(96, 40, 0.5).to("cuda")
+        np.random.seed(1)
+        lb = LRLayer(96, 40, 0.5).to("cuda")
+        oa = cls.for_model(la, grad_scale=0.5)(la.parameters(), 1e-2)
+        ob = tcls(lb.parameters(), lr=1e-2)
+        g = torch.Generator(device="cuda").manual_seed(3)
+        for step in range(10):
+            noise = torch.randn(la.flat_parameters().numel(), device="cuda", generator=g)
+            la._prepare_grad_accumulation().copy_(noise)
+            lb._prepare_grad_accumulation().copy_(noise * 0.5)
+            oa.step(); ob.step()
+        err = float((la.flat_parameters() - lb.flat_parameters()).abs().max())
+        assert err < 2e-6, (cls.__name__, err)
+
+
+@pytest.mark.gpu
+def test_train_resident_with_fused_loss_and_flat_adam(built_lib):
+    """The device-resident loop with the fused loss / accuracy kernel and the flat Adam kernel (optionally replayed from a CUDA graph)
+    follows train() with torch's CrossEntropyLoss + Adam on the same layer to float32 rounding."""
+    from structurednets_b200.layers.sss_layer import SSSLayer
+    from structurednets_b200.synth import random_mixed_system
+    rng = np.random.default_rng(6)
+    X = rng.uniform(-1, 1, size=(600, 128)).astype(np.float32)
+    y = rng.integers(0, 24, size=600).astype(np.int64)
+    hist = []
+    for fn, fused, graph in ((TH.train, False, False), (TH.train_resident, True, False), (TH.train_resident, True, True)):
+        np.random.seed(12)
+        layer = SSSLayer(128, 24, 0.9, nb_states=12, initial_system_approx=random_mixed_system(128, 24, 12, 16, seed=12)).to("cuda")
+        opt = TH.FlatAdam.for_model(layer) if fused else torch.optim.Adam
+        extra = dict(fused_loss=True, cuda_graph=graph) if fused else {}
+        res = fn(layer, X, y, X_val=X[:100], y_val=y[:100], patience=2, batch_size=200, lr=1e-3, restore_best_model=False,
+                 min_patience_improvement=1e6, optimizer_class=opt, use_gpu=True, **extra)
+        hist.append(res)
+    a = hist[0]
+    for b in hist[1:]:
+        assert len(a[5]) == len(b[5]) == 3
+        np.testing.assert_allclose(np.asarray(a[5], dtype=np.float64), np.asarray(b[5], dtype=np.float64), rtol=2e-5)
+        np.testing.assert_allclose(np.asarray(a[6], dtype=np.float64), np.asarray(b[6], dtype=np.float64), atol=1e-6)
+        np.testing.assert_allclose(np.asarray(a[1], dtype=np.float64), np.asarray(b[1], dtype=np.float64), rtol=1e-6)
