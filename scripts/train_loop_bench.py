@@ -33,15 +33,20 @@ def main():
     Xv, yv = X[:1024], y[:1024]
     sysm = random_mixed_system(4096, 1000, 500, 16, seed=5000)
     out = {}
-    for name, fn, flat, graph in (("train", TH.train, False, False), ("train_resident", TH.train_resident, False, False),
-                                  ("train_resident_flat_sgd", TH.train_resident, True, False),
-                                  ("train_resident_flat_sgd_cuda_graph", TH.train_resident, True, True)):
+    for name, fn, flat, graph, fused in (("train", TH.train, None, False, False), ("train_resident", TH.train_resident, None, False, False),
+                                         ("train_resident_flat_sgd", TH.train_resident, TH.FlatSGD, False, False),
+                                         ("train_resident_flat_sgd_cuda_graph", TH.train_resident, TH.FlatSGD, True, False),
+                                         ("train_resident_flat_sgd_fused_loss_cuda_graph", TH.train_resident, TH.FlatSGD, True, True),
+                                         ("train_adam", TH.train, "adam", False, False),
+                                         ("train_resident_flat_adam_fused_loss_cuda_graph", TH.train_resident, TH.FlatAdam, True, True)):
         layer = SSSLayer(4096, 1000, 0.105, nb_states=500, initial_system_approx=sysm).to("cuda")
-        opt = TH.FlatSGD.for_model(layer) if flat else torch.optim.SGD
+        opt = torch.optim.Adam if flat == "adam" else (flat.for_model(layer) if flat is not None else torch.optim.SGD)
         kw = dict(X_val=Xv, y_val=yv, patience=1, batch_size=args.batch, lr=1e-3, restore_best_model=False, min_patience_improvement=1e6,
                   optimizer_class=opt, use_gpu=True)
         if graph:
             kw["cuda_graph"] = True
+        if fused:
+            kw["fused_loss"] = True
         np.random.seed(0)
         fn(layer, X[:2 * args.batch], y[:2 * args.batch], **kw)     # warm-up (plans, allocator)
         torch.cuda.synchronize()

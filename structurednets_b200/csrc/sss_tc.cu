@@ -535,7 +535,7 @@ __device__ __forceinline__ void mma_state_update(float (&d)[2][4], const Frag3 (
 
 __global__ void __launch_bounds__(BM_THREADS)
 sss_tc_buildm_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss_tc_chunk* __restrict__ chunks, const float* __restrict__ params,
-                     float* __restrict__ Wall, float* __restrict__ SCall, int lists_contiguous) {
+                     float* __restrict__ Wall, float* __restrict__ SCall, float* __restrict__ VG, int lists_contiguous) {
     extern __shared__ __align__(16) float build_smem[];
     __shared__ sn_sss_stage sdesc[LMAX];
     __shared__ StageP smt[LMAX];
@@ -585,6 +585,15 @@ sss_tc_buildm_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_ss
         for (int rr = 0; rr < 2; ++rr) {
             local[rr] = c.col0 + cp.tcol[rr] - st.in_off;
             mine[rr] = !state_tile && cp.valid[rr] && local[rr] >= 0 && local[rr] < st.in_dim;
+        }
+        // the state entering the stage, kept for the backward of the construction: VG[chunk][dir][stage][column][component]
+        {
+            float* vi = VG + (((size_t)(blockIdx.x * 2 + dir) * LMAX + i) * COLT + 16 * tile) * DS;
+#pragma unroll
+            for (int hp = 0; hp < 2; ++hp) {
+                *reinterpret_cast<float2*>(vi + g * DS + 8 * hp + 2 * t) = make_float2(d[hp][0], d[hp][1]);
+                *reinterpret_cast<float2*>(vi + (g + 8) * DS + 8 * hp + 2 * t) = make_float2(d[hp][2], d[hp][3]);
+            }
         }
         const bool live = state_tile || cp.act[0] || cp.act[1] || mine[0] || mine[1];
         if (!__any_sync(0xffffffffu, live)) continue;          // every column of the tile still waits for its stage
@@ -3003,6 +3012,251 @@ __global__ void sss_tc_wsum_kernel(const float* __restrict__ Wall, float* __rest
     for (int e = threadIdx.x; e < 64 * WCOLS; e += blockDim.x) o[e] = W[e] + W[64 * WCOLS + e];
 }
 
+// ------------------------------------------------------------------------------------------
+// 6m. chain rule through the chunk-matrix construction on the warp-level tensor cores.  grid (nchunks, 2, BM_SPLIT), warp = tile of
+//     16 columns as in the build kernel, which left the state entering every stage in VG (no replay).
+//     Phase A walks the stages backwards:  lam <- lam ss + G ys  (lam = adjoint of the state; the D fragment of one product is the A
+//     fragment of the next, as in the build kernel) and leaves every stage's lam in shared memory.
+//     Phase B is parallel over the stages (warp w takes stages w, w + 6, ..):
+//       d_ss^T[a][b] = sum_col V[col][a] lam[col][b] ,  d_ys^T[a][r] = sum_col V[col][a] G[col][r]     over the CTA's 96 columns,
+//     V^T as the A operand straight from global memory, lam / G as B fragments from shared memory; the sums leave as one global
+//     atomic per parameter and CTA.  G = the chunk's dM rows, staged per tile with the entries outside a column's support zeroed.
+//     (A first version accumulated per-stage partial sums of every warp with shared-memory atomics inside the stage loop and was
+//     slower than the SIMT kernel: 1 350 instructions per stage, 16 shared atomics per lane.)
+// ------------------------------------------------------------------------------------------
+constexpr int BWM_DLD = 20;                                   // pitch of a tile's dM block [64 rows][16 columns]
+constexpr int BWM_DM = 64 * BWM_DLD;                          // floats per tile
+constexpr int BWM_LLD = 20;                                   // pitch of the lam rows [column][16 components]
+constexpr int BWM_NCOL = 16 * BM_WARPS;                       // columns per CTA (96)
+constexpr int BWM_LALL = LMAX * BWM_NCOL * BWM_LLD;           // lam of every stage
+constexpr int BWM_FIXED = BM_WARPS * BWM_DM + BWM_LALL;
+
+// lam <- lam ss + G ys for one tile.  FAST: full-width stage (16 x 16 state matrix) with at most 8 outputs.
+template <bool FAST>
+__device__ __forceinline__ void bwm_chain_step(float (&d)[2][4], const float* pbuf, const StageP& m, const sn_sss_stage& st, const float* dMw, int rbase,
+                                               int g, int t) {
+    Frag3 al[2];
+    split_frag(d[0], al[0]);
+    split_frag(d[1], al[1]);
+    const int d_in = FAST ? DS : st.d_in, d_out = FAST ? DS : st.d_out;
+    const int ntr = FAST ? 1 : (st.out_dim + 7) >> 3;
+#pragma unroll
+    for (int hp = 0; hp < 2; ++hp) {
+        float r4[4] = {0.f, 0.f, 0.f, 0.f};
+        const int a = 8 * hp + g;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                         // B[k <-> b][n = a] = ss[b][a]
+            const int b0 = 8 * h + 2 * t;
+            float x0, x1;
+            if (FAST) {
+                x0 = pbuf[m.ss + b0 * DS + a];
+                x1 = pbuf[m.ss + (b0 + 1) * DS + a];
+            } else {
+                x0 = (b0 < d_out && a < d_in) ? pbuf[m.ss + b0 * d_in + a] : 0.f;
+                x1 = (b0 + 1 < d_out && a < d_in) ? pbuf[m.ss + (b0 + 1) * d_in + a] : 0.f;
+            }
+            float2 bh, bl;
+            bh.x = tf32_hi(x0); bh.y = tf32_hi(x1); bl.x = tf32_hi(x0 - bh.x); bl.y = tf32_hi(x1 - bh.y);
+            mma3(r4, al[h], bh, bl);
+        }
+        for (int hr = 0; hr < ntr; ++hr) {                    // G as an A fragment (rows = columns g, g + 8; k <-> outputs r0, r0 + 1)
+            const int r0 = 8 * hr + 2 * t;
+            const bool k0 = r0 < st.out_dim, k1 = r0 + 1 < st.out_dim;
+            const float ga0 = k0 ? dMw[(rbase + r0) * BWM_DLD + g] : 0.f, gb0 = k0 ? dMw[(rbase + r0) * BWM_DLD + g + 8] : 0.f;
+            const float ga1 = k1 ? dMw[(rbase + r0 + 1) * BWM_DLD + g] : 0.f, gb1 = k1 ? dMw[(rbase + r0 + 1) * BWM_DLD + g + 8] : 0.f;
+            Frag3 ag;
+            frag_a_from(make_float2(ga0, ga1), make_float2(gb0, gb1), ag);
+            const float x0 = (k0 && a < d_in) ? pbuf[m.ys + r0 * d_in + a] : 0.f;
+            const float x1 = (k1 && a < d_in) ? pbuf[m.ys + (r0 + 1) * d_in + a] : 0.f;
+            float2 bh, bl;
+            bh.x = tf32_hi(x0); bh.y = tf32_hi(x1); bl.x = tf32_hi(x0 - bh.x); bl.y = tf32_hi(x1 - bh.y);
+            mma3(r4, ag, bh, bl);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d[hp][k] = r4[k];
+    }
+}
+
+__global__ void __launch_bounds__(BM_THREADS)
+sss_tc_build_bwdm_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss_tc_chunk* __restrict__ chunks, const float* __restrict__ params,
+                         const float* __restrict__ dMall, const float* __restrict__ VG, float* __restrict__ gparams, int lists_contiguous) {
+    extern __shared__ __align__(16) float build_smem[];
+    __shared__ sn_sss_stage sdesc[LMAX];
+    __shared__ StageP smt[LMAX];
+    __shared__ int rowst[PO];          // sweep position of the stage that owns each output row of the chunk (-1: padding row)
+    float* dMs = build_smem;
+    float* Lall = dMs + BM_WARPS * BWM_DM;
+    float* pbuf = Lall + BWM_LALL;
+    const sn_sss_tc_chunk c = chunks[blockIdx.x];
+    const int dir = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int nst = c.k_end - c.k_begin;
+    if (tid < nst) sdesc[tid] = stage_of(stages, n, dir, dir == 0 ? c.k_begin + tid : c.k_end - 1 - tid);
+    __syncthreads();
+    if (tid < PO) {
+        int ir = -1;
+        for (int i = 0; i < nst; ++i) {
+            const int rl = c.row0 + tid - sdesc[i].out_off;
+            if (rl >= 0 && rl < sdesc[i].out_dim) ir = i;
+        }
+        rowst[tid] = ir;
+    }
+    if (lists_contiguous) chunk_params_ranges(pbuf, smt, sdesc, nst, params, tid, BM_THREADS);
+    else chunk_params_async(pbuf, smt, sdesc, nst, params, tid, BM_THREADS);
+    cp_async_commit();
+    __syncthreads();
+
+    const int tile = BM_SPLIT * warp + blockIdx.z;
+    const bool state_tile = tile == BM_TILES - 1;
+    const bool has_tile = tile < BM_TILES && (state_tile || 16 * tile < c.ncols);
+    float* dMw = dMs + warp * BWM_DM;
+    // the warp's 16 columns of the chunk's dM tile; T rows (stage outputs) are kept only where the column has support:
+    // causal sweep: rows of the column's own stage and of later stages; anticausal sweep: rows of stages strictly after it in the sweep
+    {
+        const float* src = dMall + (size_t)blockIdx.x * 64 * DMC;
+        const int l = lane & 15;
+        const int tcol = state_tile ? l : 16 * tile + l;
+        const bool ok = has_tile && (state_tile || tcol < c.ncols);
+        const int cidx = state_tile ? c.nkb * KBW + dir * DS + l : tcol;
+        int ic = -1;
+        if (ok && !state_tile)
+            for (int i = 0; i < nst; ++i) {
+                const int cl = c.col0 + tcol - sdesc[i].in_off;
+                if (cl >= 0 && cl < sdesc[i].in_dim) ic = i;
+            }
+        for (int row = lane >> 4; row < 64; row += 2) {
+            float v = ok ? __ldg(src + row * DMC + cidx) : 0.f;
+            if (ok && !state_tile && row < PO) {
+                const int ir = rowst[row];
+                const bool keep = ir >= 0 && ic >= 0 && (dir == 0 ? ic <= ir : ic < ir);
+                if (!keep) v = 0.f;
+            }
+            dMw[row * BWM_DLD + l] = v;
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- phase A: the adjoint chain of the warp's tile; lam of every stage goes to Lall[stage][16 warp + column][component] ----
+    {
+        int tcol[2], my_i[2];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            tcol[rr] = state_tile ? g + 8 * rr : 16 * tile + g + 8 * rr;
+            my_i[rr] = -1;
+            if (has_tile && !state_tile && tcol[rr] < c.ncols)
+                for (int i = 0; i < nst; ++i) {
+                    const int cl = c.col0 + tcol[rr] - sdesc[i].in_off;
+                    if (cl >= 0 && cl < sdesc[i].in_dim) my_i[rr] = i;
+                }
+        }
+        // adjoint of the state leaving the last stage: the dR / dPhi rows of dM, as the D fragment (column g / g + 8, components 2t, 2t+1)
+        float d[2][4];
+#pragma unroll
+        for (int hp = 0; hp < 2; ++hp)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) d[hp][k] = dMw[(PO + dir * DS + 8 * hp + 2 * t + (k & 1)) * BWM_DLD + g + 8 * (k >> 1)];
+        for (int i = nst - 1; i >= 0; --i) {
+            const sn_sss_stage& st = sdesc[i];
+            const StageP& m = smt[i];
+            const int rbase = st.out_off - c.row0;
+            float* Li = Lall + ((size_t)i * BWM_NCOL + 16 * warp) * BWM_LLD;
+#pragma unroll
+            for (int hp = 0; hp < 2; ++hp) {
+                *reinterpret_cast<float2*>(Li + g * BWM_LLD + 8 * hp + 2 * t) = make_float2(d[hp][0], d[hp][1]);
+                *reinterpret_cast<float2*>(Li + (g + 8) * BWM_LLD + 8 * hp + 2 * t) = make_float2(d[hp][2], d[hp][3]);
+            }
+            if (!has_tile) continue;                       // (warp-uniform) nothing but zeros in this tile
+            // parameter gradients that belong to single columns: d su[b][local] = lam[col][b], d yu[r][local] = G[col][r]
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                if (i != my_i[rr]) continue;
+                const int local = c.col0 + tcol[rr] - st.in_off;
+#pragma unroll
+                for (int hp = 0; hp < 2; ++hp)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int b = 8 * hp + 2 * t + e;
+                        if (b < st.d_out) gparams[st.off_su + b * st.in_dim + local] += d[hp][2 * rr + e];
+                    }
+                if (st.off_yu >= 0)
+                    for (int r = t; r < st.out_dim; r += 4) gparams[st.off_yu + r * st.in_dim + local] += dMw[(rbase + r) * BWM_DLD + g + 8 * rr];
+            }
+            if (i == 0) break;                              // the adjoint entering the first stage is not needed
+            if (st.d_in == DS && st.d_out == DS && st.out_dim <= 8) bwm_chain_step<true>(d, pbuf, m, st, dMw, rbase, g, t);
+            else bwm_chain_step<false>(d, pbuf, m, st, dMw, rbase, g, t);
+        }
+    }
+    __syncthreads();
+    // ---- phase B: stage-parallel reductions over the CTA's columns ----
+    for (int i = warp; i < nst; i += BM_WARPS) {
+        const sn_sss_stage& st = sdesc[i];
+        const int rbase = st.out_off - c.row0;
+        const int ntr = (st.out_dim + 7) >> 3;
+        const float* Li = Lall + (size_t)i * BWM_NCOL * BWM_LLD;
+        float rss[2][4], rys[2][4];
+#pragma unroll
+        for (int hn = 0; hn < 2; ++hn)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { rss[hn][k] = 0.f; rys[hn][k] = 0.f; }
+        for (int w2 = 0; w2 < BM_WARPS; ++w2) {            // the tile of warp w2
+            const int tile2 = BM_SPLIT * w2 + blockIdx.z;
+            if (tile2 >= BM_TILES) break;
+            if (tile2 != BM_TILES - 1 && 16 * tile2 >= c.ncols) continue;
+            const float* vi = VG + (((size_t)(blockIdx.x * 2 + dir) * LMAX + i) * COLT + 16 * tile2) * DS;
+            const float* dM2 = dMs + w2 * BWM_DM;
+            const float* L2 = Li + 16 * w2 * BWM_LLD;
+#pragma unroll
+            for (int hk = 0; hk < 2; ++hk) {
+                // A = V^T: [m = component][k = column]
+                float va[4];
+                va[0] = __ldg(vi + (8 * hk + t) * DS + g);
+                va[1] = __ldg(vi + (8 * hk + t) * DS + g + 8);
+                va[2] = __ldg(vi + (8 * hk + t + 4) * DS + g);
+                va[3] = __ldg(vi + (8 * hk + t + 4) * DS + g + 8);
+                Frag3 av;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const float h = tf32_hi(va[q4]);
+                    av.hi[q4] = __float_as_uint(h);
+                    av.lo[q4] = __float_as_uint(tf32_hi(va[q4] - h));
+                }
+#pragma unroll
+                for (int hn = 0; hn < 2; ++hn) {
+                    const float x0 = L2[(8 * hk + t) * BWM_LLD + 8 * hn + g], x1 = L2[(8 * hk + t + 4) * BWM_LLD + 8 * hn + g];
+                    float2 bh, bl;
+                    bh.x = tf32_hi(x0); bh.y = tf32_hi(x1); bl.x = tf32_hi(x0 - bh.x); bl.y = tf32_hi(x1 - bh.y);
+                    mma3(rss[hn], av, bh, bl);
+                }
+#pragma unroll
+                for (int hn = 0; hn < 2; ++hn) {
+                    if (hn >= ntr) break;
+                    const int r = 8 * hn + g;
+                    const float x0 = r < st.out_dim ? dM2[(rbase + r) * BWM_DLD + 8 * hk + t] : 0.f;
+                    const float x1 = r < st.out_dim ? dM2[(rbase + r) * BWM_DLD + 8 * hk + t + 4] : 0.f;
+                    float2 bh, bl;
+                    bh.x = tf32_hi(x0); bh.y = tf32_hi(x1); bl.x = tf32_hi(x0 - bh.x); bl.y = tf32_hi(x1 - bh.y);
+                    mma3(rys[hn], av, bh, bl);
+                }
+            }
+        }
+        // D fragments: rows a = g, g + 8; columns 8 hn + 2t, + 1 (b of d_ss, r of d_ys)
+#pragma unroll
+        for (int hn = 0; hn < 2; ++hn)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int a = g + 8 * (k >> 1), x = 8 * hn + 2 * t + (k & 1);
+                if (a < st.d_in) {
+                    if (x < st.d_out) atomicAdd(gparams + st.off_ss + x * st.d_in + a, rss[hn][k]);
+                    if (x < st.out_dim) atomicAdd(gparams + st.off_ys + x * st.d_in + a, rys[hn][k]);
+                }
+            }
+    }
+}
+
+inline float* vg_of(const sn_sss_tc_plan* p, const float* coef) {
+    return const_cast<float*>(coef) + (size_t)p->nchunks * (WROWS * WCOLS + SCF + 4 * CW_TILE_FLOATS);
+}
+
 int check_tc_plan(const sn_sss_tc_plan* p) {
     SN_CHECK_ARG(p != nullptr, "sss_tc: NULL plan");
     SN_CHECK_ARG(p->nb_states > 0 && p->input_dim > 0 && p->output_dim > 0 && p->nchunks > 0, "sss_tc: non-positive plan dimension");
@@ -3073,7 +3327,8 @@ extern "C" {
 
 size_t sn_sss_tc_coef_floats(const sn_sss_tc_plan* p) {
     if (p == nullptr) return 0;
-    return (size_t)p->nchunks * (WROWS * WCOLS + SCF + 4 * CW_TILE_FLOATS);
+    // W | SC | chain tiles | VG: the states entering every stage of every chunk's construction (tensor-core build -> its backward)
+    return (size_t)p->nchunks * (WROWS * WCOLS + SCF + 4 * CW_TILE_FLOATS) + (size_t)p->nchunks * 2 * LMAX * COLT * DS;
 }
 size_t sn_sss_tc_rbuf_floats(const sn_sss_tc_plan* p, int64_t B) {
     if (p == nullptr || B <= 0 || use_fused_forward(p, B)) return 0;
@@ -3094,7 +3349,7 @@ int sn_sss_tc_build(const sn_sss_tc_plan* p, const float* params, float* coef, s
     if (build_mode() == 2) {
         const size_t bsm = ((size_t)p->chunk_param_floats + 32) * sizeof(float);     // four contiguous list ranges, each with <= 3 floats of lead-in
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_buildm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
-        SN_LAUNCH("sss_tc_buildm_kernel", snb::as_stream(stream), sss_tc_buildm_kernel<<<dim3(p->nchunks, 2, BM_SPLIT), BM_THREADS, bsm, snb::as_stream(stream)>>>(p->stages, p->nb_states, p->chunks, params, W, SC, p->reserved[0]));
+        SN_LAUNCH("sss_tc_buildm_kernel", snb::as_stream(stream), sss_tc_buildm_kernel<<<dim3(p->nchunks, 2, BM_SPLIT), BM_THREADS, bsm, snb::as_stream(stream)>>>(p->stages, p->nb_states, p->chunks, params, W, SC, vg_of(p, coef), p->reserved[0]));
     } else if (use_quad_build()) {
         const size_t bsm = ((size_t)p->chunk_param_floats + B4_LPC * LMAX * 4) * sizeof(float);    // + the bank padding of the state matrices
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
@@ -3237,6 +3492,13 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     if (nsplit < 1) nsplit = 1;
     SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_grad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
     SN_LAUNCH("sss_tc_grad_gemm_kernel", st, sss_tc_grad_gemm_kernel<<<dim3(nsplit, p->nchunks), G2_THREADS, G2_SMEM, st>>>(mx, mg, ml, ms, p->chunks, (long)B, dM));
+    const size_t bsmm = ((size_t)BWM_FIXED + p->chunk_param_floats + 32) * sizeof(float);
+    if (build_mode() == 2 && bsmm <= 227 * 1024) {
+        // needs the states the tensor-core build kernel of THIS forward left in coef (same build mode on both sides)
+        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_bwdm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmm));
+        SN_LAUNCH("sss_tc_build_bwdm_kernel", st, sss_tc_build_bwdm_kernel<<<dim3(p->nchunks, 2, BM_SPLIT), BM_THREADS, bsmm, st>>>(p->stages, p->nb_states, p->chunks, params, dM, vg_of(p, coef), grad_params, p->reserved[0]));
+        return 0;
+    }
     const size_t bsm4 = ((size_t)BB4_FIXED + p->chunk_param_floats + B4_LPC * LMAX * 4) * sizeof(float);
     if (use_quad_build() && bsm4 <= 227 * 1024) {
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm4));
