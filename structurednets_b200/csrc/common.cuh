@@ -55,6 +55,26 @@ inline cudaStream_t as_stream(sn_stream_t s) { return reinterpret_cast<cudaStrea
         SN_CHECK_LAUNCH(name);              \
     } while (0)
 
+// A second stream for independent pieces of one call (short, partly filled grids overlap almost completely).  Fork / join with events
+// keeps the caller's stream semantics and is capturable in a CUDA graph.  One per host thread and device.
+struct SideStream {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+inline SideStream* side_stream() {
+    static thread_local SideStream sd;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    if (sd.device != dev) {
+        if (cudaStreamCreateWithFlags(&sd.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        sd.device = dev;
+    }
+    return &sd;
+}
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 

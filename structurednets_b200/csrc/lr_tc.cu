@@ -276,26 +276,9 @@ int transpose_bf16(const bf16* src, long lds, bf16* dst, long ldd, long rows, in
     return 0;
 }
 
-// A second stream for the two halves of the backward that do not depend on each other (dL and the bias gradient next to gh -> dR):
-// each of the four kernels is a short, partly filled grid, so they overlap almost completely.  Fork / join with events keeps the
-// caller's stream semantics and is capturable in a CUDA graph.
-struct SideStream {
-    int device = -1;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-};
-inline SideStream* side_stream() {
-    static thread_local SideStream sd;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-    if (sd.device != dev) {
-        if (cudaStreamCreateWithFlags(&sd.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        if (cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        sd.device = dev;
-    }
-    return &sd;
-}
+// (SideStream / side_stream(): common.cuh)  The bias gradient and dL run next to gh -> dR on a second stream.
+using snb::SideStream;
+using snb::side_stream;
 
 inline int split_for(int tiles, long K) {
     int want = snb::ceil_div(148, tiles > 0 ? tiles : 1);

@@ -3359,8 +3359,7 @@ int sn_sss_tc_build(const sn_sss_tc_plan* p, const float* params, float* coef, s
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
         SN_LAUNCH("sss_tc_build_kernel", snb::as_stream(stream), sss_tc_build_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, bsm, snb::as_stream(stream)>>>(p->stages, p->nb_states, p->chunks, params, W, SC));
     }
-    float* CW = SC + (size_t)p->nchunks * SCF;
-    SN_LAUNCH("sss_tc_pack_chain_kernel", snb::as_stream(stream), sss_tc_pack_chain_kernel<<<dim3(p->nchunks, 4), 256, 0, snb::as_stream(stream)>>>(SC, CW));
+    // the chain tiles (tensor-core chunk scans of large batches) are packed by sn_sss_tc_forward, next to its local GEMM
     return 0;
 }
 
@@ -3383,6 +3382,10 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
         const int grid = ntiles < sm_count() ? ntiles : sm_count();
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
         SN_LAUNCH("sss_tc_fwd_fused_kernel", st, sss_tc_fwd_fused_kernel<<<grid, F_THREADS, F_SMEM, st>>>(mx, mw, p->chunks, p->nchunks, (long)B, ntiles, SC, states, y, (long)ldy, bias, aligned));
+        if (use_tc_chain(B)) {     // the backward's chain kernel reads the packed tiles
+            float* CWp = const_cast<float*>(SC) + (size_t)p->nchunks * SCF;
+            SN_LAUNCH("sss_tc_pack_chain_kernel", st, sss_tc_pack_chain_kernel<<<dim3(p->nchunks, 4), 256, 0, st>>>(SC, CWp));
+        }
         return 0;
     }
     SN_CHECK_ARG(rbuf != nullptr, "sss_tc_forward: rbuf is NULL");
@@ -3395,7 +3398,26 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
         if (int rc = make_map_f32(&moy, rbuf, 32, (uint64_t)B, 32, 128, (uint64_t)p->nchunks, (uint64_t)B * 32)) return rc;
         if (int rc = make_map_f32(&mor, rbuf + NBo * 32, 16, (uint64_t)B, 16, 128, (uint64_t)2 * p->nchunks, (uint64_t)B * 16, false, 16)) return rc;
     }
+    // the chain kernels' coefficient tiles are packed on a second stream while the local GEMM runs (they are not needed before the scans)
+    snb::SideStream* sd = use_tc_chain(B) ? snb::side_stream() : nullptr;
+    if (use_tc_chain(B)) {
+        float* CWp = const_cast<float*>(SC) + (size_t)p->nchunks * SCF;
+        cudaStream_t s2 = st;
+        if (sd != nullptr) {
+            SN_CHECK_CUDA(cudaEventRecord(sd->fork, st));
+            SN_CHECK_CUDA(cudaStreamWaitEvent(sd->stream, sd->fork, 0));
+            s2 = sd->stream;
+        }
+        if (sd != nullptr) {   // no per-kernel timing events on the side stream: its span would cover the concurrent local GEMM
+            sss_tc_pack_chain_kernel<<<dim3(p->nchunks, 4), 256, 0, s2>>>(SC, CWp);
+            SN_CHECK_LAUNCH("sss_tc_pack_chain_kernel");
+            SN_CHECK_CUDA(cudaEventRecord(sd->join, sd->stream));
+        } else {
+            SN_LAUNCH("sss_tc_pack_chain_kernel", s2, sss_tc_pack_chain_kernel<<<dim3(p->nchunks, 4), 256, 0, s2>>>(SC, CWp));
+        }
+    }
     SN_LAUNCH("sss_tc_local_gemm_kernel", st, sss_tc_local_gemm_kernel<<<grid, G1_THREADS, G1_SMEM, st>>>(mx, mw, moy, mor, p->chunks, p->nchunks, (long)B, ntiles));
+    if (sd != nullptr) SN_CHECK_CUDA(cudaStreamWaitEvent(st, sd->join, 0));
     if (use_tc_chain(B)) {
         CUtensorMap mc;
         const float* CW = SC + (size_t)p->nchunks * SCF;
