@@ -3462,6 +3462,7 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     float* dM = L + (size_t)p->nchunks * B * 32;
     float* scratch = dM + (size_t)p->nchunks * 64 * DMC;
     const int aligned = p->rows_aligned ? 1 : 0;
+    snb::SideStream* bias_side = nullptr;
     if (use_tc_chain(B)) {
         CUtensorMap mc;
         const float* CW = SC + (size_t)p->nchunks * SCF;
@@ -3474,9 +3475,19 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
         if (p->nchunks == 1 && grad_bias != nullptr)
             if (int rc = snb::colsum_accumulate(grad_y, ldgy, B, p->output_dim, grad_bias, st)) return rc;
     } else if (use_mma_scans() && aligned) {
+        // the bias gradient (column sums of grad_y) is independent of the adjoint chains: second stream, joined before the function returns
+        if (grad_bias != nullptr) {
+            bias_side = snb::side_stream();
+            cudaStream_t s2 = st;
+            if (bias_side != nullptr) {
+                SN_CHECK_CUDA(cudaEventRecord(bias_side->fork, st));
+                SN_CHECK_CUDA(cudaStreamWaitEvent(bias_side->stream, bias_side->fork, 0));
+                s2 = bias_side->stream;
+            }
+            if (int rc = snb::colsum_accumulate(grad_y, ldgy, B, p->output_dim, grad_bias, s2)) return rc;
+            if (bias_side != nullptr) SN_CHECK_CUDA(cudaEventRecord(bias_side->join, bias_side->stream));
+        }
         SN_LAUNCH("sss_tc_scan_bwd_m_kernel", st, sss_tc_scan_bwd_m_kernel<<<dim3((unsigned)((B + 63) / 64), 2), SM_THREADS, 0, st>>>(p->chunks, p->nchunks, SC, grad_y, (long)ldgy, L, (long)B));
-        if (grad_bias != nullptr)
-            if (int rc = snb::colsum_accumulate(grad_y, ldgy, B, p->output_dim, grad_bias, st)) return rc;
     } else {
         const int qs_threads = B <= 16384 ? 64 : QS_THREADS;
         const unsigned ydim = use_split_scans(B) ? 2u : 1u;
@@ -3514,6 +3525,7 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     if (nsplit < 1) nsplit = 1;
     SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_grad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
     SN_LAUNCH("sss_tc_grad_gemm_kernel", st, sss_tc_grad_gemm_kernel<<<dim3(nsplit, p->nchunks), G2_THREADS, G2_SMEM, st>>>(mx, mg, ml, ms, p->chunks, (long)B, dM));
+    if (bias_side != nullptr) SN_CHECK_CUDA(cudaStreamWaitEvent(st, bias_side->join, 0));
     const size_t bsmm = ((size_t)BWM_FIXED + p->chunk_param_floats + 32) * sizeof(float);
     if (build_mode() == 2 && bsmm <= 227 * 1024) {
         // needs the states the tensor-core build kernel of THIS forward left in coef (same build mode on both sides)
