@@ -461,6 +461,13 @@ __device__ __forceinline__ int chunk_params_ranges(float* pbuf, StageP* ptrs, co
     return r_yu.sm + pad4(r_yu.n);
 }
 
+// lo part of a 3xTF32 operand of the warp-level tensor-core products (mma.sync): x - rn_tf32(x) is exact in fp32 and is handed over as
+// it is -- the tensor core drops the 13 low mantissa bits of its tf32 operands itself; because hi is rounded to NEAREST the remainder has
+// either sign, so that truncation does not bias the product (the tcgen05 paths truncate hi and therefore round lo, see lo_of_trunc).
+// cvt.rna.tf32.f32 is not an instruction on sm_100a (ptxas emits add / mask / isfinite / select): a split costs 3 instructions this way
+// instead of 9, and the splits were three quarters of the instructions of the scan kernels (ncu source view, r2n).
+__device__ __forceinline__ float mma_lo(float remainder) { return remainder; }
+
 // B fragment (M[row][col], M[row][col + 1]) of a compact row-major [nrows][ncols] matrix, zero outside; split into tf32 hi / lo
 __device__ __forceinline__ void frag_b(const float* M, int row, int nrows, int col, int ncols, float2& hi, float2& lo) {
     float2 r = make_float2(0.f, 0.f);
@@ -473,7 +480,7 @@ __device__ __forceinline__ void frag_b(const float* M, int row, int nrows, int c
         }
     }
     hi.x = tf32_hi(r.x); hi.y = tf32_hi(r.y);
-    lo.x = tf32_hi(r.x - hi.x); lo.y = tf32_hi(r.y - hi.y);
+    lo.x = mma_lo(r.x - hi.x); lo.y = mma_lo(r.y - hi.y);
 }
 
 __device__ __forceinline__ void mma_1688(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -489,7 +496,7 @@ __device__ __forceinline__ void split_frag(const float (&d)[4], Frag3& f) {
     for (int i = 0; i < 4; ++i) {
         const float hi = tf32_hi(v[i]);
         f.hi[i] = __float_as_uint(hi);
-        f.lo[i] = __float_as_uint(tf32_hi(v[i] - hi));
+        f.lo[i] = __float_as_uint(mma_lo(v[i] - hi));
     }
 }
 // d += A B with B given pre-split (hi pair, lo pair); small terms first
@@ -1601,7 +1608,7 @@ __device__ __forceinline__ void cp_async_wait_n() { asm volatile("cp.async.wait_
 __device__ __forceinline__ void frag_b16(const float* M, int row, int col, float2& hi, float2& lo) {
     const float2 r = *reinterpret_cast<const float2*>(M + row * DS + col);
     hi.x = tf32_hi(r.x); hi.y = tf32_hi(r.y);
-    lo.x = tf32_hi(r.x - hi.x); lo.y = tf32_hi(r.y - hi.y);
+    lo.x = mma_lo(r.x - hi.x); lo.y = mma_lo(r.y - hi.y);
 }
 // A fragment with the K index permuted like split_frag's (logical k = t <-> physical column 2t, k = t + 4 <-> 2t + 1 of the group of 8),
 // from two consecutive floats of rows g and g + 8
@@ -1611,7 +1618,7 @@ __device__ __forceinline__ void frag_a_from(const float2 row_a, const float2 row
     for (int i = 0; i < 4; ++i) {
         const float h = tf32_hi(v[i]);
         f.hi[i] = __float_as_uint(h);
-        f.lo[i] = __float_as_uint(tf32_hi(v[i] - h));
+        f.lo[i] = __float_as_uint(mma_lo(v[i] - h));
     }
 }
 
@@ -1698,6 +1705,7 @@ sss_tc_scan_states_m_kernel(int nchunks, const float* __restrict__ SCall, const 
 // outputs y_j = yloc_j + O_j s_j + O'_j e_{j+1} + b, parallel over (sample, chunk): grid (ceil(B / (64 * QMO_SUB)), nchunks); a warp
 // walks QMO_SUB sub-tiles of 16 samples with the chunk's 16 B fragments (K = [s | e] = 32, N = 32 outputs) split once, in registers.
 constexpr int QMO_SUB = 2;
+constexpr int SCAN_CTAB = 256;               // chunks whose (row0, nrows) the adjoint scan keeps in shared memory
 __global__ void __launch_bounds__(SM_THREADS)
 sss_tc_scan_out_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, const float* __restrict__ SCall, const float* __restrict__ rbuf,
                          const float* __restrict__ S, float* __restrict__ y, long ldy, const float* __restrict__ bias, long B) {
@@ -1773,6 +1781,9 @@ __global__ void __launch_bounds__(SM_THREADS)
 sss_tc_scan_bwd_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, const float* __restrict__ SCall, const float* __restrict__ gy,
                          long ldgy, float* __restrict__ L, long B) {
     __shared__ __align__(16) float sc[QM][DS * DS + DS * PO];
+    __shared__ int2 ctab[SCAN_CTAB];       // (row0, nrows) per chunk: the grad_y addresses must not wait on a load of the chunk table
+    for (int i = threadIdx.x; i < nchunks && i < SCAN_CTAB; i += SM_THREADS) ctab[i] = make_int2(chunks[i].row0, chunks[i].nrows);
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, mu = blockIdx.y;
     const long row0 = ((long)blockIdx.x * (SM_THREADS / 32) + warp) * 16;
     const long rowa = row0 + g, rowb = row0 + g + 8;
@@ -1792,17 +1803,18 @@ sss_tc_scan_bwd_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
     auto load_g = [&](int jj, float2 (&gv)[4][2]) {
         const float2 z = make_float2(0.f, 0.f);
         if (jj < nchunks) {
-            const sn_sss_tc_chunk c = chunks[chunk_at(jj)];
+            const int cj = chunk_at(jj);
+            const int2 c = cj < SCAN_CTAB ? ctab[cj] : make_int2(chunks[cj].row0, chunks[cj].nrows);     // (row0, nrows)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
                 const int r = 8 * ks + 2 * t;
                 float2 x0 = z, x1 = z;
-                if (r + 1 < c.nrows) {
-                    if (va) x0 = __ldg(reinterpret_cast<const float2*>(gy + rowa * ldgy + c.row0 + r));
-                    if (vb) x1 = __ldg(reinterpret_cast<const float2*>(gy + rowb * ldgy + c.row0 + r));
-                } else if (r < c.nrows) {
-                    if (va) x0.x = __ldg(gy + rowa * ldgy + c.row0 + r);
-                    if (vb) x1.x = __ldg(gy + rowb * ldgy + c.row0 + r);
+                if (r + 1 < c.y) {
+                    if (va) x0 = __ldg(reinterpret_cast<const float2*>(gy + rowa * ldgy + c.x + r));
+                    if (vb) x1 = __ldg(reinterpret_cast<const float2*>(gy + rowb * ldgy + c.x + r));
+                } else if (r < c.y) {
+                    if (va) x0.x = __ldg(gy + rowa * ldgy + c.x + r);
+                    if (vb) x1.x = __ldg(gy + rowb * ldgy + c.x + r);
                 }
                 gv[ks][0] = x0; gv[ks][1] = x1;
             }
@@ -1846,7 +1858,7 @@ sss_tc_scan_bwd_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
                 for (int ks = 0; ks < 4; ++ks) {      // O^T gy: B[k <-> r][n = a] = O[r][a] = OT[a][r]
                     const float2 r2 = *reinterpret_cast<const float2*>(OT + (8 * nt + g) * PO + 8 * ks + 2 * t);
                     float2 bh, bl;
-                    bh.x = tf32_hi(r2.x); bh.y = tf32_hi(r2.y); bl.x = tf32_hi(r2.x - bh.x); bl.y = tf32_hi(r2.y - bh.y);
+                    bh.x = tf32_hi(r2.x); bh.y = tf32_hi(r2.y); bl.x = mma_lo(r2.x - bh.x); bl.y = mma_lo(r2.y - bh.y);
                     mma3(acc, ag[ks], bh, bl);
                 }
 #pragma unroll
@@ -2502,34 +2514,44 @@ constexpr int G2_STAGE_BYTES = G2_A_BYTES + 2 * G2_BH_BYTES;   // 64 KB
 #ifndef SN_G2_PF
 #define SN_G2_PF 2
 #endif
+#ifndef SN_G2_ABL
+#define SN_G2_ABL 0      // measurements only: 1 = no reductions into dM, 2 = items ordered range-fastest
+#endif
+// item -> (sample range, chunk)
+__device__ __forceinline__ void g2_item(int item, int nchunks, int nranges, int& rg, int& ch) {
+#if SN_G2_ABL == 2
+    ch = item / nranges; rg = item - ch * nranges;
+#else
+    rg = item / nchunks; ch = item - rg * nchunks; (void)nranges;
+#endif
+}
 constexpr int G2_PF = SN_G2_PF;                   // L2 prefetch distance in 32-sample steps
-constexpr size_t G2_SMEM = (size_t)G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
+constexpr int G2_STG_OFF = 256;                   // behind the barriers: two 8 KB staging tiles of the epilogue, then the chunk table
+constexpr size_t G2_SMEM = (size_t)G2_STAGES * G2_STAGE_BYTES + 1024 + G2_STG_OFF + 2 * 8192;
 
 __global__ void __launch_bounds__(G2_THREADS, 1)
 sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_gy, const __grid_constant__ CUtensorMap map_l,
-                        const __grid_constant__ CUtensorMap map_s, const sn_sss_tc_chunk* __restrict__ chunks, long B, float* __restrict__ dM) {
+                        const __grid_constant__ CUtensorMap map_s, const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, int nranges, int per,
+                        long B, float* __restrict__ dM) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS)
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
     uint64_t* conv = full + G2_STAGES;
     uint64_t* empty = conv + G2_STAGES;
     uint64_t* acc_full = empty + G2_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    int4* ctab = reinterpret_cast<int4*>(smem + G2_STAGES * G2_STAGE_BYTES + G2_STG_OFF + 2 * 8192);   // (col0, nkb, row0, -) per chunk
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ch = blockIdx.y;
-    const sn_sss_tc_chunk c = chunks[ch];
-    const int nkb = c.nkb;
-    const int nblk = nkb + 1;                       // N blocks of 32
     const int ntk = (int)((B + G2_KS - 1) / G2_KS);
-    const int per = (ntk + gridDim.x - 1) / gridDim.x;
-    const int t0 = blockIdx.x * per;
-    const int t1 = t0 + per < ntk ? t0 + per : ntk;
-    if (t0 >= t1) return;
+    const int nitems = nranges * nchunks;           // item = (sample range, chunk), chunk fastest: neighbouring CTAs read neighbouring
+    if ((int)blockIdx.x >= nitems) return;          // 512-byte pieces of the same x rows at the same time
 
+    for (int i = threadIdx.x; i < nchunks; i += G2_THREADS) ctab[i] = make_int4(chunks[i].col0, chunks[i].nkb, chunks[i].row0, 0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < G2_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(conv + s, 128); mbar_init(empty + s, 1); }
-        mbar_init(acc_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, 128); }
         mbar_fence_init();
         tma_prefetch_desc(&map_x);
         tma_prefetch_desc(&map_gy);
@@ -2544,105 +2566,166 @@ sss_tc_grad_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 
     if (warp == 0) {
         if (elect_one()) {
-            auto prefetch_step = [&](int t) {   // into L2 only, G2_PF steps ahead of the 3-stage shared-memory pipeline
-                tma_prefetch_l2_2d(&map_gy, c.row0, t * G2_KS);
-                tma_prefetch_l2_3d(&map_l, 0, t * G2_KS, ch);
-                for (int i = 0; i < nkb; ++i) tma_prefetch_l2_2d(&map_x, c.col0 + i * KBW, t * G2_KS);
-                tma_prefetch_l2_3d(&map_s, 0, t * G2_KS, ch);
+            // L2 prefetch cursor: G2_PF 32-sample steps ahead of the 3-stage shared-memory pipeline, across item boundaries
+            int pitem = blockIdx.x, pt = 0, pt1 = 0, pch = 0, ahead = 0;
+            auto pcursor_open = [&]() {
+                if (pitem >= nitems) return;
+                int rg; g2_item(pitem, nchunks, nranges, rg, pch);
+                pt = rg * per;
+                pt1 = pt + per < ntk ? pt + per : ntk;
             };
-            for (int t = t0; t < t0 + G2_PF && t < t1; ++t) prefetch_step(t);
-            for (int t = t0, it = 0; t < t1; ++t, ++it) {
-                if (t + G2_PF < t1) prefetch_step(t + G2_PF);
-                const int s = it % G2_STAGES, round = it / G2_STAGES;
-                if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
-                uint8_t* st = smem + s * G2_STAGE_BYTES;
-                uint8_t* bh = st + G2_A_BYTES;
-                mbar_expect_tx(full + s, (2 + nblk) * G2_BLK);
-                tma_load_2d(st, &map_gy, c.row0, t * G2_KS, full + s);
-                tma_load_3d(st + G2_BLK, &map_l, 0, t * G2_KS, ch, full + s);
-                for (int i = 0; i < nkb; ++i) tma_load_2d(bh + i * G2_BLK, &map_x, c.col0 + i * KBW, t * G2_KS, full + s);
-                tma_load_3d(bh + nkb * G2_BLK, &map_s, 0, t * G2_KS, ch, full + s);
+            auto prefetch_one = [&]() {
+                if (pitem >= nitems) return;
+                const int4 c = ctab[pch];
+                tma_prefetch_l2_2d(&map_gy, c.z, pt * G2_KS);
+                tma_prefetch_l2_3d(&map_l, 0, pt * G2_KS, pch);
+                for (int i = 0; i < c.y; ++i) tma_prefetch_l2_2d(&map_x, c.x + i * KBW, pt * G2_KS);
+                tma_prefetch_l2_3d(&map_s, 0, pt * G2_KS, pch);
+                if (++pt >= pt1) { pitem += gridDim.x; pcursor_open(); }
+            };
+            pcursor_open();
+            for (; ahead < G2_PF; ++ahead) prefetch_one();
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                int rg, ch; g2_item(item, nchunks, nranges, rg, ch);
+                const int4 c = ctab[ch];
+                const int nkb = c.y, nblk = nkb + 1;
+                const int t0 = rg * per, t1 = t0 + per < ntk ? t0 + per : ntk;
+                for (int t = t0; t < t1; ++t, ++it) {
+                    prefetch_one();
+                    const uint32_t s = it % G2_STAGES, round = it / G2_STAGES;
+                    if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
+                    uint8_t* st = smem + s * G2_STAGE_BYTES;
+                    uint8_t* bh = st + G2_A_BYTES;
+                    mbar_expect_tx(full + s, (2 + nblk) * G2_BLK);
+                    tma_load_2d(st, &map_gy, c.z, t * G2_KS, full + s);
+                    tma_load_3d(st + G2_BLK, &map_l, 0, t * G2_KS, ch, full + s);
+                    for (int i = 0; i < nkb; ++i) tma_load_2d(bh + i * G2_BLK, &map_x, c.x + i * KBW, t * G2_KS, full + s);
+                    tma_load_3d(bh + nkb * G2_BLK, &map_s, 0, t * G2_KS, ch, full + s);
+                }
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            const uint32_t idesc = idesc_tf32(128, 32 * nblk, true, true);
-            // the tensor core adds into its accumulator with truncation (an error linear in the number of additions): the CTA's
-            // samples are spread over two TMEM accumulators, and the host keeps the samples per CTA small
-            const int half = (t1 - t0 + 1) / 2;
-            for (int t = t0, it = 0; t < t1; ++t, ++it) {
-                const int s = it % G2_STAGES, round = it / G2_STAGES;
-                mbar_wait(conv + s, round & 1);
+            // the tensor core adds into its accumulator with truncation (an error linear in the number of additions): an item is at
+            // most 1024 samples (the host keeps `per` <= 32), and every item has a TMEM accumulator of its own (two, alternating, so
+            // that the epilogue of one item runs under the main loop of the next)
+            uint32_t it = 0, ai = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++ai) {
+                int rg, ch; g2_item(item, nchunks, nranges, rg, ch);
+                const int nblk = ctab[ch].y + 1;
+                const int t0 = rg * per, t1 = t0 + per < ntk ? t0 + per : ntk;
+                const uint32_t idesc = idesc_tf32(128, 32 * nblk, true, true);
+                const uint32_t b = ai & 1;
+                if (ai >= 2) mbar_wait(acc_empty + b, ((ai >> 1) - 1) & 1);
                 tc_fence_after();
-                uint8_t* st = smem + s * G2_STAGE_BYTES;
-                const uint32_t acc = tmem_base + (it >= half ? 256u : 0u);
-                const int first = (it == 0 || it == half);
+                const uint32_t acc = tmem_base + b * 256u;
+                for (int t = t0; t < t1; ++t, ++it) {
+                    const uint32_t s = it % G2_STAGES, round = it / G2_STAGES;
+                    mbar_wait(conv + s, round & 1);
+                    tc_fence_after();
+                    uint8_t* st = smem + s * G2_STAGE_BYTES;
 #pragma unroll
-                for (int k = 0; k < G2_KS / 8; ++k) {   // 8 samples = 8 rows of 128 bytes = 1024 bytes per UMMA
-                    const uint64_t da = desc_mnmajor_sw128_32b(st + k * 1024, G2_BLK);
-                    const uint64_t dbh = desc_mnmajor_sw128_32b(st + G2_A_BYTES + k * 1024, G2_BLK);
-                    const uint64_t dbl = desc_mnmajor_sw128_32b(st + G2_A_BYTES + G2_BH_BYTES + k * 1024, G2_BLK);
-                    mma_tf32(acc, da, dbh, idesc, (first && k == 0) ? 0u : 1u);
-                    mma_tf32(acc, da, dbl, idesc, 1u);
+                    for (int k = 0; k < G2_KS / 8; ++k) {   // 8 samples = 8 rows of 128 bytes = 1024 bytes per UMMA
+                        const uint64_t da = desc_mnmajor_sw128_32b(st + k * 1024, G2_BLK);
+                        const uint64_t dbh = desc_mnmajor_sw128_32b(st + G2_A_BYTES + k * 1024, G2_BLK);
+                        const uint64_t dbl = desc_mnmajor_sw128_32b(st + G2_A_BYTES + G2_BH_BYTES + k * 1024, G2_BLK);
+                        mma_tf32(acc, da, dbh, idesc, (t == t0 && k == 0) ? 0u : 1u);
+                        mma_tf32(acc, da, dbl, idesc, 1u);
+                    }
+                    umma_commit(empty + s);
                 }
-                umma_commit(empty + s);
+                umma_commit(acc_full + b);
             }
-            umma_commit(acc_full);
         }
     } else if (warp < 2 + G2_CONV / 32) {
         // one group of four converter warps per stage (see the local GEMM; a group must own its stages, or it would skip phases
         // of their `full` barriers)
         const int grp = (warp - 2) >> 2, ct = (threadIdx.x - 64) & 127;
-        for (int t = t0, it = 0; t < t1; ++t, ++it) {
-            if (it % G2_STAGES != grp) continue;
-            const int s = it % G2_STAGES, round = it / G2_STAGES;
-            mbar_wait(full + s, round & 1);
-            uint8_t* st = smem + s * G2_STAGE_BYTES;
-            {   // A: gy, L (8 KB) -> lo at +8 KB
-                float4* h = reinterpret_cast<float4*>(st);
-                float4* l = h + 2 * G2_BLK / 16;
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            int rg, ch; g2_item(item, nchunks, nranges, rg, ch);
+            const int nblk = ctab[ch].y + 1;
+            const int t0 = rg * per, t1 = t0 + per < ntk ? t0 + per : ntk;
+            for (int t = t0; t < t1; ++t, ++it) {
+                if ((int)(it % G2_STAGES) != grp) continue;
+                const uint32_t s = it % G2_STAGES, round = it / G2_STAGES;
+                mbar_wait(full + s, round & 1);
+                uint8_t* st = smem + s * G2_STAGE_BYTES;
+                {   // A: gy, L (8 KB) -> lo at +8 KB
+                    float4* h = reinterpret_cast<float4*>(st);
+                    float4* l = h + 2 * G2_BLK / 16;
 #pragma unroll
-                for (int i = 0; i < 2 * G2_BLK / 16 / 128; ++i) {
-                    float4 ll;
-                    lo_of_trunc(h[ct + 128 * i], ll);   // hi = the raw tile (the tensor core truncates)
-                    l[ct + 128 * i] = ll;
+                    for (int i = 0; i < 2 * G2_BLK / 16 / 128; ++i) {
+                        float4 ll;
+                        lo_of_trunc(h[ct + 128 * i], ll);   // hi = the raw tile (the tensor core truncates)
+                        l[ct + 128 * i] = ll;
+                    }
                 }
-            }
-            {   // B: x blocks + state block -> lo at +24 KB
-                float4* h = reinterpret_cast<float4*>(st + G2_A_BYTES);
-                float4* l = h + G2_BH_BYTES / 16;
-                const int n16 = nblk * G2_BLK / 16;
+                {   // B: x blocks + state block -> lo at +24 KB
+                    float4* h = reinterpret_cast<float4*>(st + G2_A_BYTES);
+                    float4* l = h + G2_BH_BYTES / 16;
+                    const int n16 = nblk * G2_BLK / 16;
 #pragma unroll 4
-                for (int i = ct; i < n16; i += 128) {
-                    float4 ll;
-                    lo_of_trunc(h[i], ll);
-                    l[i] = ll;
+                    for (int i = ct; i < n16; i += 128) {
+                        float4 ll;
+                        lo_of_trunc(h[i], ll);
+                        l[i] = ll;
+                    }
                 }
+                fence_async_smem();
+                mbar_arrive(conv + s);
             }
-            fence_async_smem();
-            mbar_arrive(conv + s);
         }
     } else {
+        // epilogue.  Rows m and m + 64 of the accumulator are the hi and lo parts of the same dM row and sit in the TMEM lanes of
+        // different warps (q and q + 2): they are added through a small swizzled staging tile before they leave as red.global.add, which
+        // halves the atomic traffic (measured: 200 MB of reductions per step at B = 65 536 cost the kernel 50 us of its 405).
+        // Column groups of 32 alternate roles: warps 2, 3 stage and warps 0, 1 reduce on even groups, the other way round on odd ones;
+        // two staging tiles, one named barrier per group (a tile is rewritten two groups later, behind the barrier its readers passed).
         const int q = warp & 3;
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        const int m = q * 32 + lane;
-        float* drow = dM + ((size_t)ch * 64 + (m & 63)) * DMC;
-        const uint32_t acc = tmem_base + ((uint32_t)(q * 32) << 16);
-        const bool two = (t1 - t0) > 1;
-        for (int c0 = 0; c0 < 32 * nblk; c0 += 16) {
-            uint32_t v[16], w[16];
-            tmem_ld16_nowait(acc + c0, v);
-            if (two) tmem_ld16_nowait(acc + 256 + c0, w);
-            tmem_ld_wait();
-            float f[16];
+        const int r64 = (q & 1) * 32 + lane;             // dM row of the chunk
+        const uint32_t stg = smem_u32(smem + G2_STAGES * G2_STAGE_BYTES + G2_STG_OFF);
+        const uint32_t myrow = (uint32_t)r64 * 128u;
+        uint32_t ai = 0, grp = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++ai) {
+            int rg, ch; g2_item(item, nchunks, nranges, rg, ch);
+            const int nblk = ctab[ch].y + 1;
+            const uint32_t b = ai & 1;
+            mbar_wait(acc_full + b, (ai >> 1) & 1);
+            tc_fence_after();
+            float* drow = dM + ((size_t)ch * 64 + r64) * DMC;
+            const uint32_t acc = tmem_base + b * 256u + ((uint32_t)(q * 32) << 16);
+            for (int c0 = 0; c0 < 32 * nblk; c0 += 32, ++grp) {
+                uint32_t v[32];
+                tmem_ld16_nowait(acc + c0, *reinterpret_cast<uint32_t(*)[16]>(v));
+                tmem_ld16_nowait(acc + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(v + 16));
+                tmem_ld_wait();
+                const uint32_t tile = stg + (grp & 1) * 8192u + myrow;
+                const bool stager = ((q >> 1) ^ (int)(grp & 1)) != 0;      // even groups: warps 2, 3 (q >> 1 == 1)
+                if (stager) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + (two ? __uint_as_float(w[i]) : 0.f);
+                    for (int c = 0; c < 8; ++c)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile + (uint32_t)((c ^ (r64 & 7)) << 4)), "r"(v[4 * c]), "r"(v[4 * c + 1]),
+                                     "r"(v[4 * c + 2]), "r"(v[4 * c + 3]) : "memory");
+                }
+                named_bar_sync(2, 128);
+                if (!stager) {
+#if SN_G2_ABL == 1
+                    if (v[0] != 0x7fc12345u) continue;    // ablation: no reductions into dM
+#endif
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c0 + 4 * i), "f"(f[4 * i]), "f"(f[4 * i + 1]), "f"(f[4 * i + 2]),
-                             "f"(f[4 * i + 3])
-                             : "memory");
+                    for (int c = 0; c < 8; ++c) {
+                        float4 o;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w) : "r"(tile + (uint32_t)((c ^ (r64 & 7)) << 4)) : "memory");
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c0 + 4 * c), "f"(__uint_as_float(v[4 * c]) + o.x),
+                                     "f"(__uint_as_float(v[4 * c + 1]) + o.y), "f"(__uint_as_float(v[4 * c + 2]) + o.z), "f"(__uint_as_float(v[4 * c + 3]) + o.w)
+                                     : "memory");
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(acc_empty + b);
         }
     }
     tc_fence_before();
@@ -3056,7 +3139,7 @@ __device__ __forceinline__ void bwm_chain_step(float (&d)[2][4], const float* pb
                 x1 = (b0 + 1 < d_out && a < d_in) ? pbuf[m.ss + (b0 + 1) * d_in + a] : 0.f;
             }
             float2 bh, bl;
-            bh.x = tf32_hi(x0); bh.y = tf32_hi(x1); bl.x = tf32_hi(x0 - bh.x); bl.y = tf32_hi(x1 - bh.y);
+            bh.x = tf32_hi(x0); bh.y = tf32_hi(x1); bl.x = mma_lo(x0 - bh.x); bl.y = mma_lo(x1 - bh.y);
             mma3(r4, al[h], bh, bl);
         }
         for (int hr = 0; hr < ntr; ++hr) {                    // G as an A fragment (rows = columns g, g + 8; k <-> outputs r0, r0 + 1)
@@ -3069,7 +3152,7 @@ __device__ __forceinline__ void bwm_chain_step(float (&d)[2][4], const float* pb
             const float x0 = (k0 && a < d_in) ? pbuf[m.ys + r0 * d_in + a] : 0.f;
             const float x1 = (k1 && a < d_in) ? pbuf[m.ys + (r0 + 1) * d_in + a] : 0.f;
             float2 bh, bl;
-            bh.x = tf32_hi(x0); bh.y = tf32_hi(x1); bl.x = tf32_hi(x0 - bh.x); bl.y = tf32_hi(x1 - bh.y);
+            bh.x = tf32_hi(x0); bh.y = tf32_hi(x1); bl.x = mma_lo(x0 - bh.x); bl.y = mma_lo(x1 - bh.y);
             mma3(r4, ag, bh, bl);
         }
 #pragma unroll
@@ -3218,13 +3301,13 @@ sss_tc_build_bwdm_kernel(const sn_sss_stage* __restrict__ stages, int n, const s
                 for (int q4 = 0; q4 < 4; ++q4) {
                     const float h = tf32_hi(va[q4]);
                     av.hi[q4] = __float_as_uint(h);
-                    av.lo[q4] = __float_as_uint(tf32_hi(va[q4] - h));
+                    av.lo[q4] = __float_as_uint(mma_lo(va[q4] - h));
                 }
 #pragma unroll
                 for (int hn = 0; hn < 2; ++hn) {
                     const float x0 = L2[(8 * hk + t) * BWM_LLD + 8 * hn + g], x1 = L2[(8 * hk + t + 4) * BWM_LLD + 8 * hn + g];
                     float2 bh, bl;
-                    bh.x = tf32_hi(x0); bh.y = tf32_hi(x1); bl.x = tf32_hi(x0 - bh.x); bl.y = tf32_hi(x1 - bh.y);
+                    bh.x = tf32_hi(x0); bh.y = tf32_hi(x1); bl.x = mma_lo(x0 - bh.x); bl.y = mma_lo(x1 - bh.y);
                     mma3(rss[hn], av, bh, bl);
                 }
 #pragma unroll
@@ -3234,7 +3317,7 @@ sss_tc_build_bwdm_kernel(const sn_sss_stage* __restrict__ stages, int n, const s
                     const float x0 = r < st.out_dim ? dM2[(rbase + r) * BWM_DLD + 8 * hk + t] : 0.f;
                     const float x1 = r < st.out_dim ? dM2[(rbase + r) * BWM_DLD + 8 * hk + t + 4] : 0.f;
                     float2 bh, bl;
-                    bh.x = tf32_hi(x0); bh.y = tf32_hi(x1); bl.x = tf32_hi(x0 - bh.x); bl.y = tf32_hi(x1 - bh.y);
+                    bh.x = tf32_hi(x0); bh.y = tf32_hi(x1); bl.x = mma_lo(x0 - bh.x); bl.y = mma_lo(x1 - bh.y);
                     mma3(rys[hn], av, bh, bl);
                 }
             }
@@ -3289,13 +3372,13 @@ bool use_fused_forward(const sn_sss_tc_plan* p, int64_t B) {
 }
 
 // Chunk scans: the tensor-core chain kernels are bounded below by (2 x chunks) serial steps of ~1.5 us whatever the batch (forward
-// ~110 us, backward ~80 us with one CTA per SM), the SIMT four-threads-per-sample kernels scale with the batch (~18 ns / sample
-// for the three of them).  Measured (r1q): 12 288 samples 188 vs 230 us, 16 384: 192 vs 289 us, 32 768: 285 vs 534 us; about equal
-// at 8 192.  SNB200_SSS_TC_CHAIN=0/1 forces the choice (tests).
+// ~105 us, backward ~73 us with one CTA per SM), the warp-level tensor-core scans scale with the batch.  Measured (r2u, whole step):
+// 12 288 samples 0.343 ms (scans) vs 0.377 ms (chain), 16 384: 0.417 vs 0.418, 24 576: 0.577 vs ~0.55.  SNB200_SSS_TC_CHAIN=0/1 forces
+// the choice (tests).
 bool use_tc_chain(int64_t B) {
     const char* e = getenv("SNB200_SSS_TC_CHAIN");
     if (e != nullptr && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
-    return B >= 10240;
+    return B >= 16384;
 }
 
 // build / build-backward: 2 = warp-level tensor-core kernels (default), 1 = SIMT with several lanes per column
@@ -3463,6 +3546,7 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     float* scratch = dM + (size_t)p->nchunks * 64 * DMC;
     const int aligned = p->rows_aligned ? 1 : 0;
     snb::SideStream* bias_side = nullptr;
+    bool bias_later = false;
     if (use_tc_chain(B)) {
         CUtensorMap mc;
         const float* CW = SC + (size_t)p->nchunks * SCF;
@@ -3475,18 +3559,7 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
         if (p->nchunks == 1 && grad_bias != nullptr)
             if (int rc = snb::colsum_accumulate(grad_y, ldgy, B, p->output_dim, grad_bias, st)) return rc;
     } else if (use_mma_scans() && aligned) {
-        // the bias gradient (column sums of grad_y) is independent of the adjoint chains: second stream, joined before the function returns
-        if (grad_bias != nullptr) {
-            bias_side = snb::side_stream();
-            cudaStream_t s2 = st;
-            if (bias_side != nullptr) {
-                SN_CHECK_CUDA(cudaEventRecord(bias_side->fork, st));
-                SN_CHECK_CUDA(cudaStreamWaitEvent(bias_side->stream, bias_side->fork, 0));
-                s2 = bias_side->stream;
-            }
-            if (int rc = snb::colsum_accumulate(grad_y, ldgy, B, p->output_dim, grad_bias, s2)) return rc;
-            if (bias_side != nullptr) SN_CHECK_CUDA(cudaEventRecord(bias_side->join, bias_side->stream));
-        }
+        bias_later = grad_bias != nullptr;
         SN_LAUNCH("sss_tc_scan_bwd_m_kernel", st, sss_tc_scan_bwd_m_kernel<<<dim3((unsigned)((B + 63) / 64), 2), SM_THREADS, 0, st>>>(p->chunks, p->nchunks, SC, grad_y, (long)ldgy, L, (long)B));
     } else {
         const int qs_threads = B <= 16384 ? 64 : QS_THREADS;
@@ -3518,32 +3591,64 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     if (int rc = make_map_f32(&ml, L, 32, (uint64_t)B, 32, G2_KS, (uint64_t)p->nchunks, (uint64_t)B * 32, true)) return rc;
     if (int rc = make_map_f32(&ms, states, 32, (uint64_t)B, 32, G2_KS, (uint64_t)p->nchunks, (uint64_t)B * 32, true)) return rc;
     const int ntk = (int)((B + G2_KS - 1) / G2_KS);
-    int nsplit = ceil_div(2 * sm_count(), p->nchunks);
-    const int split_for_accuracy = (int)((B + 2047) / 2048);   // <= 2048 samples per CTA, 1024 per TMEM accumulator
-    if (nsplit < split_for_accuracy) nsplit = split_for_accuracy;
-    if (nsplit > ntk) nsplit = ntk;
-    if (nsplit < 1) nsplit = 1;
-    SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_grad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
-    SN_LAUNCH("sss_tc_grad_gemm_kernel", st, sss_tc_grad_gemm_kernel<<<dim3(nsplit, p->nchunks), G2_THREADS, G2_SMEM, st>>>(mx, mg, ml, ms, p->chunks, (long)B, dM));
-    if (bias_side != nullptr) SN_CHECK_CUDA(cudaStreamWaitEvent(st, bias_side->join, 0));
+    // persistent CTAs over items = (sample range of `per` 32-sample steps, chunk).  per <= 32: at most 1024 samples per TMEM accumulator
+    // (accuracy, see the kernel); among those the item size that wastes the least in the last round of items, with two steps' worth of
+    // per-item cost (accumulator switch, 48 KB of red.add) charged per item.  SNB200_SSS_G2_PER forces it (measurements).
+    int per = 0;
+    {
+        long best = -1;
+        for (int cand = 32; cand >= 1; --cand) {
+            const int nr = ceil_div(ntk, cand), pe = ceil_div(ntk, nr);
+            const long rounds = ((long)nr * p->nchunks + sm_count() - 1) / sm_count();
+            const long cost = rounds * (pe + 2);
+            if (best < 0 || cost < best) { best = cost; per = pe; }
+        }
+        const char* e = getenv("SNB200_SSS_G2_PER");
+        if (e != nullptr && atoi(e) >= 1 && atoi(e) <= 32) per = atoi(e);
+    }
+    const int nranges = ceil_div(ntk, per);
+    const long nitems = (long)nranges * p->nchunks;
+    const int g2grid = (int)(nitems < sm_count() ? nitems : sm_count());
+    const size_t g2smem = G2_SMEM + (size_t)p->nchunks * sizeof(int4);
+    SN_CHECK_ARG(g2smem <= 227 * 1024, "sss_tc_backward: too many chunks for the gradient GEMM's chunk table");
+    SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_grad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2smem));
+    SN_LAUNCH("sss_tc_grad_gemm_kernel", st, sss_tc_grad_gemm_kernel<<<g2grid, G2_THREADS, g2smem, st>>>(mx, mg, ml, ms, p->chunks, p->nchunks, nranges, per, (long)B, dM));
+    // small-batch path: the bias gradient (column sums of grad_y) runs on a second stream beside the build-backward kernel, which is
+    // one latency-bound CTA per (chunk, direction, half) and leaves most of every SM idle.  (Beside the adjoint scans it slowed them
+    // down by more than its own duration.)
+    if (bias_later) {
+        bias_side = snb::side_stream();
+        cudaStream_t s2 = st;
+        if (bias_side != nullptr) {
+            SN_CHECK_CUDA(cudaEventRecord(bias_side->fork, st));
+            SN_CHECK_CUDA(cudaStreamWaitEvent(bias_side->stream, bias_side->fork, 0));
+            s2 = bias_side->stream;
+        }
+        if (int rc = snb::colsum_accumulate(grad_y, ldgy, B, p->output_dim, grad_bias, s2)) return rc;
+        if (bias_side != nullptr) SN_CHECK_CUDA(cudaEventRecord(bias_side->join, bias_side->stream));
+    }
+    auto join_bias = [&]() -> int {
+        if (bias_side != nullptr) SN_CHECK_CUDA(cudaStreamWaitEvent(st, bias_side->join, 0));
+        return 0;
+    };
     const size_t bsmm = ((size_t)BWM_FIXED + p->chunk_param_floats + 32) * sizeof(float);
     if (build_mode() == 2 && bsmm <= 227 * 1024) {
         // needs the states the tensor-core build kernel of THIS forward left in coef (same build mode on both sides)
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_bwdm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmm));
         SN_LAUNCH("sss_tc_build_bwdm_kernel", st, sss_tc_build_bwdm_kernel<<<dim3(p->nchunks, 2, BM_SPLIT), BM_THREADS, bsmm, st>>>(p->stages, p->nb_states, p->chunks, params, dM, vg_of(p, coef), grad_params, p->reserved[0]));
-        return 0;
+        return join_bias();
     }
     const size_t bsm4 = ((size_t)BB4_FIXED + p->chunk_param_floats + B4_LPC * LMAX * 4) * sizeof(float);
     if (use_quad_build() && bsm4 <= 227 * 1024) {
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm4));
         SN_LAUNCH("sss_tc_build_bwd4_kernel", st, sss_tc_build_bwd4_kernel<<<dim3(p->nchunks, 2, B4_SPLIT), B4_THREADS, bsm4, st>>>(p->stages, p->nb_states, p->chunks, params, dM, grad_params));
-        return 0;
+        return join_bias();
     }
     const size_t bsm = ((size_t)64 * DMC + p->chunk_param_floats) * sizeof(float);
     SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
     SN_LAUNCH("sss_tc_build_bwd_kernel", st, sss_tc_build_bwd_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, bsm, st>>>(p->stages, p->nb_states, p->chunks, params, dM, scratch, grad_params));
     SN_LAUNCH("sss_tc_build_red_kernel", st, sss_tc_build_red_kernel<<<dim3(p->nchunks * LMAX, 2), BR_THREADS, 0, st>>>(p->stages, p->nb_states, p->chunks, scratch, grad_params));
-    return 0;
+    return join_bias();
 }
 
 }  // extern "C"

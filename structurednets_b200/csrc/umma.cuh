@@ -133,12 +133,10 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[1
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// fp32 -> (hi, lo) with hi = round-to-nearest tf32 and lo = x - hi (exact in fp32); the tensor core reads the top 19 bits
-__device__ __forceinline__ float tf32_hi(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+// round to nearest (ties away from zero) onto the tf32 grid.  cvt.rna.tf32.f32 has no instruction on sm_100a: ptxas emits this add + mask
+// plus an isfinite test and a select; without the test NaN payloads may change and values within half a tf32 ulp of FLT_MAX round to Inf
+// (as they should).
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
 // ---- host side: tensor maps through the driver entry point (no link-time dependency on libcuda) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
