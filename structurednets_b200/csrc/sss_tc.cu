@@ -673,11 +673,11 @@ __device__ __forceinline__ void split_tf32(const float4& v, float4& h, float4& l
     split_tf32(v.w, h.w, l.w);
 }
 
-#ifdef SN_CHAIN_PROF
+#if defined(SN_CHAIN_PROF) || defined(SN_SCAN_PROF)
 #define CHPROF_DECL(n) long long chp_acc[n]; for (int chp_i = 0; chp_i < n; ++chp_i) chp_acc[chp_i] = 0; long long chp_t = 0; (void)chp_t
 #define CHPROF_T0() chp_t = clock64()
 #define CHPROF_LAP(i) do { const long long chp_n = clock64(); chp_acc[i] += chp_n - chp_t; chp_t = chp_n; } while (0)
-#define CHPROF_PRINT(tag, n, steps) do { if (blockIdx.x == 0 || blockIdx.x == 301) for (int chp_i = 0; chp_i < n; ++chp_i) \
+#define CHPROF_PRINT(tag, n, steps) do { if (blockIdx.x == 0 || blockIdx.x == 301 || blockIdx.x == 100) for (int chp_i = 0; chp_i < n; ++chp_i) \
     printf("CHPROF %s blk %d phase %d avg %lld cyc/step\n", tag, (int)blockIdx.x, chp_i, chp_acc[chp_i] / (steps)); } while (0)
 #else
 #define CHPROF_DECL(n)
@@ -1599,7 +1599,8 @@ sss_tc_scan_bwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
 //    Requires the 16-byte aligned layouts (`aligned`); otherwise the SIMT scans run.
 // ------------------------------------------------------------------------------------------
 constexpr int QM = 4;                       // ring slots (shared memory: coefficients)
-constexpr int QPF = 4;                      // register ring depth (per-sample rows from HBM)
+constexpr int QG_S = 8;                     // cp.async ring depths (steps in flight): state scans, adjoint scans
+constexpr int QG_B = 6;
 constexpr int SM_THREADS = 128;             // 4 warps x 16 samples
 template <int N>
 __device__ __forceinline__ void cp_async_wait_n() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -1622,81 +1623,144 @@ __device__ __forceinline__ void frag_a_from(const float2 row_a, const float2 row
     }
 }
 
+// ---- warp-level tensor-core scans: layouts ----
+// The scans are bound by the L1 / shared-memory data pipe (ncu r2v: 84 % of its peak in the adjoint scan): one wavefront per 128-byte
+// line a warp instruction touches.  With the m16n8k8 fragments loaded as they are defined (lane (g, t) holds columns 2t, 2t+1 of rows
+// g, g+8) every global access is 8 bytes per lane over 8 rows: 8 wavefronts for 256 bytes.  Samples are independent and the order of the
+// state components / output rows inside a product is free as long as both operands agree, so the kernels below let lane t own FOUR
+// consecutive floats of a row (one 16-byte access: half the wavefronts per byte) and fold the resulting permutations into the packed
+// B fragments:
+//   state rows (16 floats: S, L, r):  lane t holds physical components 4t .. 4t+3 = logical (n-tile 0: 2t, 2t+1 | n-tile 1: 2t, 2t+1)
+//   32-wide rows (grad_y, [s | e], yloc, y): lane t holds 4t .. 4t+3 and 16+4t .. 16+4t+3 = (k-step or n-tile 0 | 1 | 2 | 3) x 2
+__device__ __forceinline__ int pstate(int l) { return 4 * ((l & 7) >> 1) + 2 * (l >> 3) + (l & 1); }            // logical state index -> physical
+__device__ __forceinline__ int p32(int blk, int t, int e) { return 16 * (blk >> 1) + 4 * t + 2 * (blk & 1) + e; }  // (block of 8, lane t, e) -> physical
+
+// fragment tiles FS[chunk][direction] = 16 B fragments x 32 lanes x (x0, x1), packed once per forward by sss_tc_pack_scan_kernel: a scan
+// step reads a B fragment with one conflict-free 8-byte shared-memory load.  Lane (g, t) of fragment (n-tile nt, k-step ks) holds
+// B[k = (ks, t)][n = 8 nt + g] and B[k = (ks, t + 4)][n].
+//   0..3    state scans     2 nt + ks      B[k][n] = Phi[n][k]
+//   4..7    adjoint scans   4 + 2 nt + ks  B[k][n] = Phi[k][n]           (Phi^T lambda)
+//   8..15   adjoint scans   8 + 4 nt + ks  B[k][n] = O[k][n], k < 32     (O^T gy)
+constexpr int FS_FRAGS = 16;
+constexpr int FS_TILE_FLOATS = FS_FRAGS * 32 * 2;     // 1024 floats = 4 KB per (chunk, direction)
+__global__ void __launch_bounds__(256)
+sss_tc_pack_scan_kernel(const float* __restrict__ SCall, float* __restrict__ FSall) {
+    const int ch = blockIdx.x, dir = blockIdx.y;
+    const float* Phi = SCall + (size_t)ch * SCF + dir * DS * DS;
+    const float* O = SCall + (size_t)ch * SCF + 2 * DS * DS + dir * PO * DS;
+    float2* FS = reinterpret_cast<float2*>(FSall + ((size_t)ch * 2 + dir) * FS_TILE_FLOATS);
+    for (int i = threadIdx.x; i < FS_FRAGS * 32; i += 256) {
+        const int f = i >> 5, lane = i & 31, g = lane >> 2, t = lane & 3;
+        float x0, x1;
+        if (f < 8) {
+            const int nt = (f & 3) >> 1, ks = f & 1;
+            const int n = pstate(8 * nt + g), k0 = pstate(8 * ks + 2 * t), k1 = pstate(8 * ks + 2 * t + 1);
+            if (f < 4) { x0 = Phi[n * DS + k0]; x1 = Phi[n * DS + k1]; }
+            else       { x0 = Phi[k0 * DS + n]; x1 = Phi[k1 * DS + n]; }
+        } else {
+            const int nt = (f - 8) >> 2, ks = (f - 8) & 3, n = pstate(8 * nt + g);
+            x0 = O[p32(ks, t, 0) * DS + n]; x1 = O[p32(ks, t, 1) * DS + n];
+        }
+        FS[i] = make_float2(x0, x1);
+    }
+}
+// 16-byte cp.async that reads only `bytes` (0..16) from global memory and zero-fills the rest
+__device__ __forceinline__ void cp_async16_zfill(float* dst, const float* src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes) : "memory");
+}
+// packed B fragment -> (hi.x, hi.y, lo.x, lo.y)
+__device__ __forceinline__ float4 split_b(const float2 x) {
+    const float h0 = tf32_hi(x.x), h1 = tf32_hi(x.y);
+    return make_float4(h0, h1, mma_lo(x.x - h0), mma_lo(x.y - h1));
+}
+// one of the three terms of d += A B (0: lo * hi, 1: hi * lo, 2: hi * hi; small terms first).  The scans issue the terms of several
+// INDEPENDENT accumulators round-robin: an HMMA that adds into the accumulator of its predecessor waits ~27 cycles for it.
+template <int TERM>
+__device__ __forceinline__ void mma_term(float (&d)[4], const Frag3& a, const float4 b) {
+    if (TERM == 0) mma_1688(d, a.lo, __float_as_uint(b.x), __float_as_uint(b.y));
+    else if (TERM == 1) mma_1688(d, a.hi, __float_as_uint(b.z), __float_as_uint(b.w));
+    else mma_1688(d, a.hi, __float_as_uint(b.x), __float_as_uint(b.y));
+}
+// A fragments of two k-steps from one float4 per row (rows g and g + 8): k-step 0 <- (x, y), k-step 1 <- (z, w)
+__device__ __forceinline__ void frag_a2(const float4 ra, const float4 rb, Frag3& f0, Frag3& f1) {
+    frag_a_from(make_float2(ra.x, ra.y), make_float2(rb.x, rb.y), f0);
+    frag_a_from(make_float2(ra.z, ra.w), make_float2(rb.z, rb.w), f1);
+}
+
 // forward state chains: blockIdx.y = direction (0: s_{j+1} = r_j + Phi_j s_j ascending, 1: e_j = r'_j + Phi'_j e_{j+1} descending);
 // saves the state ENTERING every chunk: S[j][row][0..15] = s_j, S[j][row][16..31] = e_{j+1}
 __global__ void __launch_bounds__(SM_THREADS)
-sss_tc_scan_states_m_kernel(int nchunks, const float* __restrict__ SCall, const float* __restrict__ rbuf, float* __restrict__ S, long B) {
-    __shared__ __align__(16) float sc[QM][DS * DS];
+sss_tc_scan_states_m_kernel(int nchunks, const float* __restrict__ FSall, const float* __restrict__ rbuf, float* __restrict__ S, long B) {
+    // rings of QG_S steps: the chunk's four B fragments (shared by the CTA) and, per warp, the step's 16 r rows.  The per-sample rows
+    // are staged by cp.async and not by loads into a register ring: a warp has six scoreboards, the compiler folds the ring's loads
+    // onto them together with everything else of the step, and an unrelated register write then waits for the youngest load of the
+    // group (ncu r2zc: a quarter of the adjoint scan's samples on one CS2R) -- the ring never had its nominal depth.
+    __shared__ __align__(16) float2 sc[QG_S][4 * 32];
+    __shared__ __align__(16) float rows[SM_THREADS / 32][QG_S][16 * 16];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, dir = blockIdx.y;
     const long row0 = ((long)blockIdx.x * (SM_THREADS / 32) + warp) * 16;
     const long rowa = row0 + g, rowb = row0 + g + 8;
     const bool va = rowa < B, vb = rowb < B;
     const size_t NB = (size_t)nchunks * B;
     const float* Rin = rbuf + NB * 32 + (dir ? NB * 16 : 0);     // r (causal) or r' (anticausal) rows, [chunk][B][16]
-    const int phi_off = dir * DS * DS;
     auto chunk_at = [&](int jj) { return dir ? nchunks - 1 - jj : jj; };
     auto issue = [&](int jj) {
         if (jj < nchunks) {
-            const float* src = SCall + (size_t)chunk_at(jj) * SCF + phi_off;
-            for (int i = threadIdx.x; i < DS * DS / 4; i += SM_THREADS) cp_async16(sc[jj % QM] + 4 * i, src + 4 * i);
+            const int ch = chunk_at(jj);
+            if (threadIdx.x < 64) cp_async16(reinterpret_cast<float*>(sc[jj % QG_S]) + 4 * threadIdx.x, FSall + ((size_t)ch * 2 + dir) * FS_TILE_FLOATS + 4 * threadIdx.x);
+            // the warp's 16 rows are 1 KB of contiguous global memory: two 512-byte pieces, same layout in shared memory
+            float* dst = rows[warp][jj % QG_S];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int fl = 4 * lane + 128 * i;             // float offset inside the 16 x 16 block; row = fl / 16
+                const bool ok = row0 + (fl >> 4) < B;
+                cp_async16_zfill(dst + fl, ok ? Rin + ((size_t)ch * B + row0) * 16 + fl : Rin, ok ? 16 : 0);
+            }
         }
         cp_async_commit();
     };
-    auto load_r = [&](int jj, float2 (&rv)[2][2]) {     // [n-tile][row a / b]: the step's r values in accumulator layout
-        const float2 z = make_float2(0.f, 0.f);
-        if (jj < nchunks) {
-            const size_t base = (size_t)chunk_at(jj) * B;
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-                rv[nt][0] = va ? __ldg(reinterpret_cast<const float2*>(Rin + (base + rowa) * 16 + 8 * nt + 2 * t)) : z;
-                rv[nt][1] = vb ? __ldg(reinterpret_cast<const float2*>(Rin + (base + rowb) * 16 + 8 * nt + 2 * t)) : z;
-            }
-        }
-    };
-#pragma unroll
-    for (int s0 = 0; s0 < QM - 1; ++s0) issue(s0);
+    for (int s0 = 0; s0 < QG_S - 1; ++s0) issue(s0);
     float d[2][4];
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
         for (int k = 0; k < 4; ++k) d[nt][k] = 0.f;
-    // the r rows come from HBM (each is read exactly once): a register ring keeps QPF steps of them in flight -- with one step of
-    // lookahead every step waited ~1 us on the accumulator's initial value (ncu: half of all samples on the first HMMA of the step)
-    float2 rq[QPF][2][2];
+#pragma unroll 2
+    for (int jj = 0; jj < nchunks; ++jj) {
+        cp_async_wait_n<QG_S - 2>();
+        __syncthreads();
+        issue(jj + QG_S - 1);
+        const int j = chunk_at(jj);
+        const float2* F = sc[jj % QG_S];
+        const float* R = rows[warp][jj % QG_S];
+        // the state entering chunk j
+        if (va) *reinterpret_cast<float4*>(S + ((size_t)j * B + rowa) * 32 + (dir ? DS : 0) + 4 * t) = make_float4(d[0][0], d[0][1], d[1][0], d[1][1]);
+        if (vb) *reinterpret_cast<float4*>(S + ((size_t)j * B + rowb) * 32 + (dir ? DS : 0) + 4 * t) = make_float4(d[0][2], d[0][3], d[1][2], d[1][3]);
+        const float4 ra = *reinterpret_cast<const float4*>(R + g * 16 + 4 * t), rb = *reinterpret_cast<const float4*>(R + (g + 8) * 16 + 4 * t);
+        Frag3 a[2];
+        split_frag(d[0], a[0]);
+        split_frag(d[1], a[1]);
+        {   // four independent chains of three products: (n-tile, k-step); k-step 1 starts from the step's r values
+            float4 f[2][2];
 #pragma unroll
-    for (int u = 0; u < QPF; ++u) load_r(u, rq[u]);
-    for (int jj0 = 0; jj0 < nchunks; jj0 += QPF) {
+            for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-        for (int u = 0; u < QPF; ++u) {
-            const int jj = jj0 + u;
-            if (jj >= nchunks) break;
-            cp_async_wait_n<QM - 2>();
-            __syncthreads();
-            issue(jj + QM - 1);
-            const int j = chunk_at(jj);
-            const float* Phi = sc[jj % QM];
-            // the state entering chunk j
+                for (int ks = 0; ks < 2; ++ks) f[nt][ks] = split_b(F[(2 * nt + ks) * 32 + lane]);
+            float acc[2][2][4];
+            acc[0][1][0] = ra.x; acc[0][1][1] = ra.y; acc[1][1][0] = ra.z; acc[1][1][1] = ra.w;
+            acc[0][1][2] = rb.x; acc[0][1][3] = rb.y; acc[1][1][2] = rb.z; acc[1][1][3] = rb.w;
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-                if (va) *reinterpret_cast<float2*>(S + ((size_t)j * B + rowa) * 32 + (dir ? DS : 0) + 8 * nt + 2 * t) = make_float2(d[nt][0], d[nt][1]);
-                if (vb) *reinterpret_cast<float2*>(S + ((size_t)j * B + rowb) * 32 + (dir ? DS : 0) + 8 * nt + 2 * t) = make_float2(d[nt][2], d[nt][3]);
-            }
-            Frag3 a[2];
-            split_frag(d[0], a[0]);
-            split_frag(d[1], a[1]);
+            for (int nt = 0; nt < 2; ++nt) acc[nt][0][0] = acc[nt][0][1] = acc[nt][0][2] = acc[nt][0][3] = 0.f;
+#define SN_ROUND(TERM)                                                                    \
+            mma_term<TERM>(acc[0][0], a[0], f[0][0]); mma_term<TERM>(acc[1][0], a[0], f[1][0]); \
+            mma_term<TERM>(acc[0][1], a[1], f[0][1]); mma_term<TERM>(acc[1][1], a[1], f[1][1]);
+            SN_ROUND(0) SN_ROUND(1) SN_ROUND(2)
+#undef SN_ROUND
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-                float acc[4] = {rq[u][nt][0].x, rq[u][nt][0].y, rq[u][nt][1].x, rq[u][nt][1].y};
+            for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                    float2 bh, bl;
-                    frag_b16(Phi, 8 * nt + g, 8 * ks + 2 * t, bh, bl);      // B[k <-> a][n = b] = Phi[b][a]
-                    mma3(acc, a[ks], bh, bl);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) d[nt][k] = acc[k];
-            }
-            load_r(jj + QPF, rq[u]);
+                for (int k = 0; k < 4; ++k) d[nt][k] = acc[nt][0][k] + acc[nt][1][k];
         }
     }
     cp_async_wait_all();
@@ -1711,26 +1775,10 @@ sss_tc_scan_out_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, const float
                          const float* __restrict__ S, float* __restrict__ y, long ldy, const float* __restrict__ bias, long B) {
     __shared__ __align__(16) float sc[2 * PO * DS];       // O (32 x 16) then O' (32 x 16)
     const int j = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const sn_sss_tc_chunk c = chunks[j];
-    for (int i = threadIdx.x; i < 2 * PO * DS / 4; i += SM_THREADS)
-        reinterpret_cast<float4*>(sc)[i] = __ldg(reinterpret_cast<const float4*>(SCall + (size_t)j * SCF + 2 * DS * DS) + i);
-    __syncthreads();
-    // B fragments: k-steps 0, 1 = s (O), 2, 3 = e (O'); n-tiles 0..3 = outputs 8 nt .. 8 nt + 7
-    float2 bh[4][4], bl[4][4];
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) frag_b16(sc + (ks >> 1) * PO * DS, 8 * nt + g, 8 * (ks & 1) + 2 * t, bh[ks][nt], bl[ks][nt]);
-    float2 bias2[4];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-        const int n = 8 * nt + 2 * t;
-        bias2[nt].x = (bias != nullptr && n < c.nrows) ? __ldg(bias + c.row0 + n) : 0.f;
-        bias2[nt].y = (bias != nullptr && n + 1 < c.nrows) ? __ldg(bias + c.row0 + n + 1) : 0.f;
-    }
-    const float2 z = make_float2(0.f, 0.f);
-    // loads of ALL the warp's sub-tiles first (they come from HBM / L2 and nothing else hides their latency), arithmetic afterwards
-    float2 av[QMO_SUB][4][2], yl[QMO_SUB][4][2];
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    // every global load of the CTA is issued before anything waits: the per-sample rows of ALL the warp's sub-tiles, the chunk's O / O'
+    // and its descriptor.  [half: columns 4t.. / 16+4t..][row a / b]
+    float4 av[QMO_SUB][2][2], yl[QMO_SUB][2][2];
 #pragma unroll
     for (int u = 0; u < QMO_SUB; ++u) {
         const long row0 = (((long)blockIdx.x * QMO_SUB + u) * (SM_THREADS / 32) + warp) * 16;
@@ -1741,33 +1789,78 @@ sss_tc_scan_out_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, const float
         const float* ya = rbuf + ((size_t)j * B + rowa) * 32;
         const float* yb = rbuf + ((size_t)j * B + rowb) * 32;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            av[u][ks][0] = va ? __ldg(reinterpret_cast<const float2*>(sa + 8 * ks + 2 * t)) : z;
-            av[u][ks][1] = vb ? __ldg(reinterpret_cast<const float2*>(sb + 8 * ks + 2 * t)) : z;
-            yl[u][ks][0] = va ? __ldg(reinterpret_cast<const float2*>(ya + 8 * ks + 2 * t)) : z;
-            yl[u][ks][1] = vb ? __ldg(reinterpret_cast<const float2*>(yb + 8 * ks + 2 * t)) : z;
+        for (int h = 0; h < 2; ++h) {
+            av[u][h][0] = va ? __ldg(reinterpret_cast<const float4*>(sa + 16 * h + 4 * t)) : z;
+            av[u][h][1] = vb ? __ldg(reinterpret_cast<const float4*>(sb + 16 * h + 4 * t)) : z;
+            yl[u][h][0] = va ? __ldg(reinterpret_cast<const float4*>(ya + 16 * h + 4 * t)) : z;
+            yl[u][h][1] = vb ? __ldg(reinterpret_cast<const float4*>(yb + 16 * h + 4 * t)) : z;
         }
     }
+    float4 scv[2 * PO * DS / 4 / SM_THREADS];
+#pragma unroll
+    for (int i = 0; i < 2 * PO * DS / 4 / SM_THREADS; ++i)
+        scv[i] = __ldg(reinterpret_cast<const float4*>(SCall + (size_t)j * SCF + 2 * DS * DS) + threadIdx.x + i * SM_THREADS);
+    const int c_row0 = __ldg(&chunks[j].row0), c_nrows = __ldg(&chunks[j].nrows);
+#pragma unroll
+    for (int i = 0; i < 2 * PO * DS / 4 / SM_THREADS; ++i) reinterpret_cast<float4*>(sc)[threadIdx.x + i * SM_THREADS] = scv[i];
+    // bias of the lane's 8 output columns: [half][4]
+    float bs[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int n = 16 * h + 4 * t + e;
+            bs[h][e] = (bias != nullptr && n < c_nrows) ? __ldg(bias + c_row0 + n) : 0.f;
+        }
+    __syncthreads();
+    // B fragments: k-steps 0, 1 = s (O), 2, 3 = e (O'); n-tile nt, lane g <-> output row p32(nt, g >> 1, g & 1); k-slot (ks, t, e) <-> state
+    // component 4t + 2 (ks & 1) + e of s (ks < 2) or e (ks >= 2)
+    float2 bh[4][4], bl[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const float2 r = *reinterpret_cast<const float2*>(sc + (ks >> 1) * PO * DS + p32(nt, g >> 1, g & 1) * DS + 4 * t + 2 * (ks & 1));
+            bh[ks][nt].x = tf32_hi(r.x); bh[ks][nt].y = tf32_hi(r.y);
+            bl[ks][nt].x = mma_lo(r.x - bh[ks][nt].x); bl[ks][nt].y = mma_lo(r.y - bh[ks][nt].y);
+        }
+    const bool vec_ok = (c_nrows & 3) == 0;
 #pragma unroll
     for (int u = 0; u < QMO_SUB; ++u) {
         const long row0 = (((long)blockIdx.x * QMO_SUB + u) * (SM_THREADS / 32) + warp) * 16;
         const long rowa = row0 + g, rowb = row0 + g + 8;
         const bool va = rowa < B, vb = rowb < B;
         Frag3 a[4];
+        frag_a2(av[u][0][0], av[u][0][1], a[0], a[1]);
+        frag_a2(av[u][1][0], av[u][1][1], a[2], a[3]);
+        float acc[4][4];
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) frag_a_from(av[u][ks][0], av[u][ks][1], a[ks]);
+        for (int h = 0; h < 2; ++h) {
+            acc[2 * h][0] = yl[u][h][0].x + bs[h][0]; acc[2 * h][1] = yl[u][h][0].y + bs[h][1];
+            acc[2 * h][2] = yl[u][h][1].x + bs[h][0]; acc[2 * h][3] = yl[u][h][1].y + bs[h][1];
+            acc[2 * h + 1][0] = yl[u][h][0].z + bs[h][2]; acc[2 * h + 1][1] = yl[u][h][0].w + bs[h][3];
+            acc[2 * h + 1][2] = yl[u][h][1].z + bs[h][2]; acc[2 * h + 1][3] = yl[u][h][1].w + bs[h][3];
+        }
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            float acc[4] = {yl[u][nt][0].x + bias2[nt].x, yl[u][nt][0].y + bias2[nt].y, yl[u][nt][1].x + bias2[nt].x, yl[u][nt][1].y + bias2[nt].y};
+        for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) mma3(acc, a[ks], bh[ks][nt], bl[ks][nt]);
-            const int n = 8 * nt + 2 * t;
-            if (n + 1 < c.nrows) {
-                if (va) *reinterpret_cast<float2*>(y + rowa * ldy + c.row0 + n) = make_float2(acc[0], acc[1]);
-                if (vb) *reinterpret_cast<float2*>(y + rowb * ldy + c.row0 + n) = make_float2(acc[2], acc[3]);
-            } else if (n < c.nrows) {
-                if (va) y[rowa * ldy + c.row0 + n] = acc[0];
-                if (vb) y[rowb * ldy + c.row0 + n] = acc[2];
+            for (int nt = 0; nt < 4; ++nt) mma3(acc[nt], a[ks], bh[ks][nt], bl[ks][nt]);      // four independent accumulators per k-step
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int n0 = 16 * h + 4 * t;
+            const float4 oa = make_float4(acc[2 * h][0], acc[2 * h][1], acc[2 * h + 1][0], acc[2 * h + 1][1]);
+            const float4 ob = make_float4(acc[2 * h][2], acc[2 * h][3], acc[2 * h + 1][2], acc[2 * h + 1][3]);
+            if (n0 + 4 <= c_nrows && vec_ok) {
+                if (va) *reinterpret_cast<float4*>(y + rowa * ldy + c_row0 + n0) = oa;
+                if (vb) *reinterpret_cast<float4*>(y + rowb * ldy + c_row0 + n0) = ob;
+            } else {
+                const float oav[4] = {oa.x, oa.y, oa.z, oa.w}, obv[4] = {ob.x, ob.y, ob.z, ob.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (n0 + e < c_nrows) {
+                        if (va) y[rowa * ldy + c_row0 + n0 + e] = oav[e];
+                        if (vb) y[rowb * ldy + c_row0 + n0 + e] = obv[e];
+                    }
             }
         }
     }
@@ -1775,12 +1868,17 @@ sss_tc_scan_out_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, const float
 
 // adjoint chains: blockIdx.y = 0: lambda_j = Phi_j^T lambda_{j+1} + O_j^T gy_j (descending), 1: mu likewise with Phi', O' (ascending).
 // L[j][row][0..15] = lambda_{j+1}, L[j][row][16..31] = mu_j: the adjoint of the state LEAVING chunk j, i.e. the value before the step.
-// Slot layout: PhiT [16][16] (PhiT[a][b] = Phi[b][a]) then OT [16][32] (OT[a][r] = O[r][a]), transposed while staging so that the B
-// fragments are 8-byte loads.
+constexpr int GROW = 48;                                  // floats per staged grad_y row: 32 + 16 of padding (conflict-free 16-byte reads)
+constexpr int SB_FRAG_FLOATS = 12 * 32 * 2;              // fragments 4..15 of a tile
+constexpr size_t SB_SMEM = (size_t)QG_B * (SB_FRAG_FLOATS + (SM_THREADS / 32) * 16 * GROW) * sizeof(float);
 __global__ void __launch_bounds__(SM_THREADS)
-sss_tc_scan_bwd_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, const float* __restrict__ SCall, const float* __restrict__ gy,
+sss_tc_scan_bwd_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, const float* __restrict__ FSall, const float* __restrict__ gy,
                          long ldgy, float* __restrict__ L, long B) {
-    __shared__ __align__(16) float sc[QM][DS * DS + DS * PO];
+    // rings of QG_B steps in dynamic shared memory: fragments 4..15 of the chunk's tile (shared by the CTA), and per warp the chunk's
+    // 32 grad_y columns of its 16 samples (see the state scans for why these are not a register ring)
+    extern __shared__ __align__(16) float sb_smem[];
+    float* frag_ring = sb_smem;                                           // [QG_B][SB_FRAG_FLOATS]
+    float* row_ring = sb_smem + (size_t)QG_B * SB_FRAG_FLOATS;            // [warp][QG_B][16][GROW]
     __shared__ int2 ctab[SCAN_CTAB];       // (row0, nrows) per chunk: the grad_y addresses must not wait on a load of the chunk table
     for (int i = threadIdx.x; i < nchunks && i < SCAN_CTAB; i += SM_THREADS) ctab[i] = make_int2(chunks[i].row0, chunks[i].nrows);
     __syncthreads();
@@ -1788,89 +1886,81 @@ sss_tc_scan_bwd_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
     const long row0 = ((long)blockIdx.x * (SM_THREADS / 32) + warp) * 16;
     const long rowa = row0 + g, rowb = row0 + g + 8;
     const bool va = rowa < B, vb = rowb < B;
-    const int phi_off = mu ? DS * DS : 0, o_off = 2 * DS * DS + (mu ? PO * DS : 0);
+    float* my_rows = row_ring + (size_t)warp * QG_B * 16 * GROW;
     auto chunk_at = [&](int jj) { return mu ? jj : nchunks - 1 - jj; };
     auto issue = [&](int jj) {
         if (jj < nchunks) {
-            const float* src = SCall + (size_t)chunk_at(jj) * SCF;
-            float* dst = sc[jj % QM];
-            for (int e = threadIdx.x; e < DS * DS; e += SM_THREADS) cp_async4(dst + (e & 15) * DS + (e >> 4), src + phi_off + e);               // Phi[b][a] -> PhiT[a][b]
-            for (int e = threadIdx.x; e < PO * DS; e += SM_THREADS) cp_async4(dst + DS * DS + (e & 15) * PO + (e >> 4), src + o_off + e);      // O[r][a] -> OT[a][r]
+            const int ch = chunk_at(jj);
+            const float* src = FSall + ((size_t)ch * 2 + mu) * FS_TILE_FLOATS + 4 * 32 * 2;
+            float* dst = frag_ring + (size_t)(jj % QG_B) * SB_FRAG_FLOATS;
+            cp_async16(dst + 4 * threadIdx.x, src + 4 * threadIdx.x);
+            if (threadIdx.x < 64) cp_async16(dst + 4 * (threadIdx.x + SM_THREADS), src + 4 * (threadIdx.x + SM_THREADS));
+            // grad_y: lane -> (row = 4 i + lane / 8, 16-byte piece = lane % 8): every instruction reads four whole 128-byte rows;
+            // bytes past the chunk's nrows and rows past B are zero-filled, never read
+            const int2 c = ch < SCAN_CTAB ? ctab[ch] : make_int2(__ldg(&chunks[ch].row0), __ldg(&chunks[ch].nrows));
+            float* rdst = my_rows + (size_t)(jj % QG_B) * 16 * GROW;
+            const int piece = lane & 7;
+            int bytes = 4 * (c.y - 4 * piece);
+            bytes = bytes < 0 ? 0 : (bytes > 16 ? 16 : bytes);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = 4 * i + (lane >> 3);
+                const bool ok = row0 + r < B && bytes > 0;
+                cp_async16_zfill(rdst + r * GROW + 4 * piece, ok ? gy + (row0 + r) * ldgy + c.x + 4 * piece : gy, ok ? bytes : 0);
+            }
         }
         cp_async_commit();
     };
-    // grad_y of the chunk as A fragments (K = the chunk's 32 output rows, permuted like split_frag): 8-byte loads, zero past nrows
-    auto load_g = [&](int jj, float2 (&gv)[4][2]) {
-        const float2 z = make_float2(0.f, 0.f);
-        if (jj < nchunks) {
-            const int cj = chunk_at(jj);
-            const int2 c = cj < SCAN_CTAB ? ctab[cj] : make_int2(chunks[cj].row0, chunks[cj].nrows);     // (row0, nrows)
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                const int r = 8 * ks + 2 * t;
-                float2 x0 = z, x1 = z;
-                if (r + 1 < c.y) {
-                    if (va) x0 = __ldg(reinterpret_cast<const float2*>(gy + rowa * ldgy + c.x + r));
-                    if (vb) x1 = __ldg(reinterpret_cast<const float2*>(gy + rowb * ldgy + c.x + r));
-                } else if (r < c.y) {
-                    if (va) x0.x = __ldg(gy + rowa * ldgy + c.x + r);
-                    if (vb) x1.x = __ldg(gy + rowb * ldgy + c.x + r);
-                }
-                gv[ks][0] = x0; gv[ks][1] = x1;
-            }
-        }
-    };
-#pragma unroll
-    for (int s0 = 0; s0 < QM - 1; ++s0) issue(s0);
+    for (int s0 = 0; s0 < QG_B - 1; ++s0) issue(s0);
     float d[2][4];
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
         for (int k = 0; k < 4; ++k) d[nt][k] = 0.f;
-    float2 gq[QPF][4][2];
+#pragma unroll 2
+    for (int jj = 0; jj < nchunks; ++jj) {
+        cp_async_wait_n<QG_B - 2>();
+        __syncthreads();
+        issue(jj + QG_B - 1);
+        const int j = chunk_at(jj);
+        const float2* F = reinterpret_cast<const float2*>(frag_ring + (size_t)(jj % QG_B) * SB_FRAG_FLOATS);
+        const float* G = my_rows + (size_t)(jj % QG_B) * 16 * GROW;
+        if (va) *reinterpret_cast<float4*>(L + ((size_t)j * B + rowa) * 32 + (mu ? DS : 0) + 4 * t) = make_float4(d[0][0], d[0][1], d[1][0], d[1][1]);
+        if (vb) *reinterpret_cast<float4*>(L + ((size_t)j * B + rowb) * 32 + (mu ? DS : 0) + 4 * t) = make_float4(d[0][2], d[0][3], d[1][2], d[1][3]);
+        Frag3 a[2], ag[4];
 #pragma unroll
-    for (int u = 0; u < QPF; ++u) load_g(u, gq[u]);
-    for (int jj0 = 0; jj0 < nchunks; jj0 += QPF) {
-#pragma unroll
-        for (int u = 0; u < QPF; ++u) {
-            const int jj = jj0 + u;
-            if (jj >= nchunks) break;
-            cp_async_wait_n<QM - 2>();
-            __syncthreads();
-            issue(jj + QM - 1);
-            const int j = chunk_at(jj);
-            const float* PhiT = sc[jj % QM];
-            const float* OT = PhiT + DS * DS;
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-                if (va) *reinterpret_cast<float2*>(L + ((size_t)j * B + rowa) * 32 + (mu ? DS : 0) + 8 * nt + 2 * t) = make_float2(d[nt][0], d[nt][1]);
-                if (vb) *reinterpret_cast<float2*>(L + ((size_t)j * B + rowb) * 32 + (mu ? DS : 0) + 8 * nt + 2 * t) = make_float2(d[nt][2], d[nt][3]);
-            }
-            Frag3 a[2], ag[4];
-            split_frag(d[0], a[0]);
-            split_frag(d[1], a[1]);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) frag_a_from(gq[u][ks][0], gq[u][ks][1], ag[ks]);
+        for (int h = 0; h < 2; ++h)
+            frag_a2(*reinterpret_cast<const float4*>(G + g * GROW + 16 * h + 4 * t), *reinterpret_cast<const float4*>(G + (g + 8) * GROW + 16 * h + 4 * t), ag[2 * h], ag[2 * h + 1]);
+        split_frag(d[0], a[0]);
+        split_frag(d[1], a[1]);
+        {   // per n-tile three independent chains of six products: O^T gy over k-steps (0, 1) and (2, 3), Phi^T over the state's two.
+            // The O^T gy chains do not depend on the previous step at all, so only the six Phi^T products sit on the recurrence.
+            float4 fo[2][4], fp[2][2];
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {      // O^T gy: B[k <-> r][n = a] = O[r][a] = OT[a][r]
-                    const float2 r2 = *reinterpret_cast<const float2*>(OT + (8 * nt + g) * PO + 8 * ks + 2 * t);
-                    float2 bh, bl;
-                    bh.x = tf32_hi(r2.x); bh.y = tf32_hi(r2.y); bl.x = mma_lo(r2.x - bh.x); bl.y = mma_lo(r2.y - bh.y);
-                    mma3(acc, ag[ks], bh, bl);
-                }
+                for (int ks = 0; ks < 4; ++ks) fo[nt][ks] = split_b(F[(4 + 4 * nt + ks) * 32 + lane]);     // O^T gy
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {      // Phi^T adjoint: B[k <-> b][n = a] = Phi[b][a] = PhiT[a][b]
-                    float2 bh, bl;
-                    frag_b16(PhiT, 8 * nt + g, 8 * ks + 2 * t, bh, bl);
-                    mma3(acc, a[ks], bh, bl);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) d[nt][k] = acc[k];
+                for (int ks = 0; ks < 2; ++ks) fp[nt][ks] = split_b(F[(2 * nt + ks) * 32 + lane]);         // Phi^T adjoint
             }
-            load_g(jj + QPF, gq[u]);
+            float acc[2][3][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[nt][c][k] = 0.f;
+#define SN_ROUND(TERM, KS)                                                                                                  \
+            mma_term<TERM>(acc[0][0], ag[KS], fo[0][KS]);         mma_term<TERM>(acc[1][0], ag[KS], fo[1][KS]);         \
+            mma_term<TERM>(acc[0][1], ag[2 + KS], fo[0][2 + KS]); mma_term<TERM>(acc[1][1], ag[2 + KS], fo[1][2 + KS]); \
+            mma_term<TERM>(acc[0][2], a[KS], fp[0][KS]);          mma_term<TERM>(acc[1][2], a[KS], fp[1][KS]);
+            SN_ROUND(0, 0) SN_ROUND(1, 0) SN_ROUND(2, 0) SN_ROUND(0, 1) SN_ROUND(1, 1) SN_ROUND(2, 1)
+#undef SN_ROUND
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) d[nt][k] = (acc[nt][0][k] + acc[nt][1][k]) + acc[nt][2][k];
         }
     }
     cp_async_wait_all();
@@ -3339,6 +3429,8 @@ sss_tc_build_bwdm_kernel(const sn_sss_stage* __restrict__ stages, int n, const s
 inline float* vg_of(const sn_sss_tc_plan* p, const float* coef) {
     return const_cast<float*>(coef) + (size_t)p->nchunks * (WROWS * WCOLS + SCF + 4 * CW_TILE_FLOATS);
 }
+// fragment tiles of the warp-level tensor-core scans, behind VG
+inline float* fs_of(const sn_sss_tc_plan* p, const float* coef) { return vg_of(p, coef) + (size_t)p->nchunks * 2 * LMAX * COLT * DS; }
 
 int check_tc_plan(const sn_sss_tc_plan* p) {
     SN_CHECK_ARG(p != nullptr, "sss_tc: NULL plan");
@@ -3410,8 +3502,10 @@ extern "C" {
 
 size_t sn_sss_tc_coef_floats(const sn_sss_tc_plan* p) {
     if (p == nullptr) return 0;
-    // W | SC | chain tiles | VG: the states entering every stage of every chunk's construction (tensor-core build -> its backward)
-    return (size_t)p->nchunks * (WROWS * WCOLS + SCF + 4 * CW_TILE_FLOATS) + (size_t)p->nchunks * 2 * LMAX * COLT * DS;
+    // W | SC | chain tiles | VG: the states entering every stage of every chunk's construction (tensor-core build -> its backward) |
+    // FS: fragment tiles of the small-batch scans
+    return (size_t)p->nchunks * (WROWS * WCOLS + SCF + 4 * CW_TILE_FLOATS) + (size_t)p->nchunks * 2 * LMAX * COLT * DS +
+           (size_t)p->nchunks * 2 * FS_TILE_FLOATS;
 }
 size_t sn_sss_tc_rbuf_floats(const sn_sss_tc_plan* p, int64_t B) {
     if (p == nullptr || B <= 0 || use_fused_forward(p, B)) return 0;
@@ -3468,6 +3562,8 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
         if (use_tc_chain(B)) {     // the backward's chain kernel reads the packed tiles
             float* CWp = const_cast<float*>(SC) + (size_t)p->nchunks * SCF;
             SN_LAUNCH("sss_tc_pack_chain_kernel", st, sss_tc_pack_chain_kernel<<<dim3(p->nchunks, 4), 256, 0, st>>>(SC, CWp));
+        } else if (use_mma_scans()) {
+            SN_LAUNCH("sss_tc_pack_scan_kernel", st, sss_tc_pack_scan_kernel<<<dim3(p->nchunks, 2), 256, 0, st>>>(SC, fs_of(p, coef)));
         }
         return 0;
     }
@@ -3481,10 +3577,14 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
         if (int rc = make_map_f32(&moy, rbuf, 32, (uint64_t)B, 32, 128, (uint64_t)p->nchunks, (uint64_t)B * 32)) return rc;
         if (int rc = make_map_f32(&mor, rbuf + NBo * 32, 16, (uint64_t)B, 16, 128, (uint64_t)2 * p->nchunks, (uint64_t)B * 16, false, 16)) return rc;
     }
-    // the chain kernels' coefficient tiles are packed on a second stream while the local GEMM runs (they are not needed before the scans)
-    snb::SideStream* sd = use_tc_chain(B) ? snb::side_stream() : nullptr;
-    if (use_tc_chain(B)) {
+    // the scans' coefficient tiles (chain tiles of the tcgen05 chain kernels, or fragment tiles of the warp-level scans) are packed on a
+    // second stream while the local GEMM runs (they are not needed before the scans)
+    const bool pack_fs = !use_tc_chain(B) && use_mma_scans();     // the backward's adjoint scan reads them whatever y's alignment is
+    const bool mma_scans = pack_fs && aligned && ((reinterpret_cast<uintptr_t>(y) & 7) == 0) && (ldy & 1) == 0;
+    snb::SideStream* sd = (use_tc_chain(B) || pack_fs) ? snb::side_stream() : nullptr;
+    if (use_tc_chain(B) || pack_fs) {
         float* CWp = const_cast<float*>(SC) + (size_t)p->nchunks * SCF;
+        float* FSp = fs_of(p, coef);
         cudaStream_t s2 = st;
         if (sd != nullptr) {
             SN_CHECK_CUDA(cudaEventRecord(sd->fork, st));
@@ -3492,9 +3592,12 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
             s2 = sd->stream;
         }
         if (sd != nullptr) {   // no per-kernel timing events on the side stream: its span would cover the concurrent local GEMM
-            sss_tc_pack_chain_kernel<<<dim3(p->nchunks, 4), 256, 0, s2>>>(SC, CWp);
+            if (pack_fs) sss_tc_pack_scan_kernel<<<dim3(p->nchunks, 2), 256, 0, s2>>>(SC, FSp);
+            else sss_tc_pack_chain_kernel<<<dim3(p->nchunks, 4), 256, 0, s2>>>(SC, CWp);
             SN_CHECK_LAUNCH("sss_tc_pack_chain_kernel");
             SN_CHECK_CUDA(cudaEventRecord(sd->join, sd->stream));
+        } else if (pack_fs) {
+            SN_LAUNCH("sss_tc_pack_scan_kernel", s2, sss_tc_pack_scan_kernel<<<dim3(p->nchunks, 2), 256, 0, s2>>>(SC, FSp));
         } else {
             SN_LAUNCH("sss_tc_pack_chain_kernel", s2, sss_tc_pack_chain_kernel<<<dim3(p->nchunks, 4), 256, 0, s2>>>(SC, CWp));
         }
@@ -3515,8 +3618,8 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
         SN_LAUNCH("sss_tc_chain_fwd_kernel", st, sss_tc_chain_fwd_kernel<<<ntiles, CH_THREADS, CHF_SMEM, st>>>(mc, mi, my, p->chunks, p->nchunks, rbuf, states, y, (long)ldy, bias, (long)B, aligned));
         return 0;
     }
-    if (use_mma_scans() && aligned && ((reinterpret_cast<uintptr_t>(y) & 7) == 0) && (ldy & 1) == 0) {
-        SN_LAUNCH("sss_tc_scan_states_m_kernel", st, sss_tc_scan_states_m_kernel<<<dim3((unsigned)((B + 63) / 64), 2), SM_THREADS, 0, st>>>(p->nchunks, SC, rbuf, states, (long)B));
+    if (mma_scans) {
+        SN_LAUNCH("sss_tc_scan_states_m_kernel", st, sss_tc_scan_states_m_kernel<<<dim3((unsigned)((B + 63) / 64), 2), SM_THREADS, 0, st>>>(p->nchunks, fs_of(p, coef), rbuf, states, (long)B));
         SN_LAUNCH("sss_tc_scan_out_m_kernel", st, sss_tc_scan_out_m_kernel<<<dim3((unsigned)((B + 64 * QMO_SUB - 1) / (64 * QMO_SUB)), p->nchunks), SM_THREADS, 0, st>>>(p->chunks, SC, rbuf, states, y, (long)ldy, bias, (long)B));
         return 0;
     }
@@ -3560,7 +3663,8 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
             if (int rc = snb::colsum_accumulate(grad_y, ldgy, B, p->output_dim, grad_bias, st)) return rc;
     } else if (use_mma_scans() && aligned) {
         bias_later = grad_bias != nullptr;
-        SN_LAUNCH("sss_tc_scan_bwd_m_kernel", st, sss_tc_scan_bwd_m_kernel<<<dim3((unsigned)((B + 63) / 64), 2), SM_THREADS, 0, st>>>(p->chunks, p->nchunks, SC, grad_y, (long)ldgy, L, (long)B));
+        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_scan_bwd_m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_SMEM));
+        SN_LAUNCH("sss_tc_scan_bwd_m_kernel", st, sss_tc_scan_bwd_m_kernel<<<dim3((unsigned)((B + 63) / 64), 2), SM_THREADS, SB_SMEM, st>>>(p->chunks, p->nchunks, fs_of(p, coef), grad_y, (long)ldgy, L, (long)B));
     } else {
         const int qs_threads = B <= 16384 ? 64 : QS_THREADS;
         const unsigned ydim = use_split_scans(B) ? 2u : 1u;
