@@ -3297,6 +3297,7 @@ sss_tc_build_bwdm_kernel(const sn_sss_stage* __restrict__ stages, int n, const s
                 const int cl = c.col0 + tcol - sdesc[i].in_off;
                 if (cl >= 0 && cl < sdesc[i].in_dim) ic = i;
             }
+#pragma unroll 8
         for (int row = lane >> 4; row < 64; row += 2) {
             float v = ok ? __ldg(src + row * DMC + cidx) : 0.f;
             if (ok && !state_tile && row < PO) {
@@ -3349,10 +3350,10 @@ sss_tc_build_bwdm_kernel(const sn_sss_stage* __restrict__ stages, int n, const s
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int b = 8 * hp + 2 * t + e;
-                        if (b < st.d_out) gparams[st.off_su + b * st.in_dim + local] += d[hp][2 * rr + e];
+                        if (b < st.d_out) atomicAdd(gparams + st.off_su + b * st.in_dim + local, d[hp][2 * rr + e]);   // RED: no load on the chain
                     }
                 if (st.off_yu >= 0)
-                    for (int r = t; r < st.out_dim; r += 4) gparams[st.off_yu + r * st.in_dim + local] += dMw[(rbase + r) * BWM_DLD + g + 8 * rr];
+                    for (int r = t; r < st.out_dim; r += 4) atomicAdd(gparams + st.off_yu + r * st.in_dim + local, dMw[(rbase + r) * BWM_DLD + g + 8 * rr]);
             }
             if (i == 0) break;                              // the adjoint entering the first stage is not needed
             if (st.d_in == DS && st.d_out == DS && st.out_dim <= 8) bwm_chain_step<true>(d, pbuf, m, st, dMw, rbase, g, t);
@@ -3371,27 +3372,37 @@ sss_tc_build_bwdm_kernel(const sn_sss_stage* __restrict__ stages, int n, const s
         for (int hn = 0; hn < 2; ++hn)
 #pragma unroll
             for (int k = 0; k < 4; ++k) { rss[hn][k] = 0.f; rys[hn][k] = 0.f; }
-        for (int w2 = 0; w2 < BM_WARPS; ++w2) {            // the tile of warp w2
+        // A = V^T: [m = component][k = column], straight from global memory (L2): ALL of the stage's fragments are requested before the
+        // first product -- loaded where they were used, each of the twelve (tile, k-step) rounds waited a full L2 round trip (ncu r2v:
+        // 47 % of the kernel's samples on the first use of va)
+        float va[BM_WARPS][2][4];
+        bool tile_on[BM_WARPS];
+#pragma unroll
+        for (int w2 = 0; w2 < BM_WARPS; ++w2) {
             const int tile2 = BM_SPLIT * w2 + blockIdx.z;
-            if (tile2 >= BM_TILES) break;
-            if (tile2 != BM_TILES - 1 && 16 * tile2 >= c.ncols) continue;
-            const float* vi = VG + (((size_t)(blockIdx.x * 2 + dir) * LMAX + i) * COLT + 16 * tile2) * DS;
+            tile_on[w2] = tile2 < BM_TILES && (tile2 == BM_TILES - 1 || 16 * tile2 < c.ncols);
+            const float* vi = VG + (((size_t)(blockIdx.x * 2 + dir) * LMAX + i) * COLT + 16 * (tile_on[w2] ? tile2 : 0)) * DS;
+#pragma unroll
+            for (int hk = 0; hk < 2; ++hk) {
+                va[w2][hk][0] = tile_on[w2] ? __ldg(vi + (8 * hk + t) * DS + g) : 0.f;
+                va[w2][hk][1] = tile_on[w2] ? __ldg(vi + (8 * hk + t) * DS + g + 8) : 0.f;
+                va[w2][hk][2] = tile_on[w2] ? __ldg(vi + (8 * hk + t + 4) * DS + g) : 0.f;
+                va[w2][hk][3] = tile_on[w2] ? __ldg(vi + (8 * hk + t + 4) * DS + g + 8) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int w2 = 0; w2 < BM_WARPS; ++w2) {            // the tile of warp w2
+            if (!tile_on[w2]) continue;
             const float* dM2 = dMs + w2 * BWM_DM;
             const float* L2 = Li + 16 * w2 * BWM_LLD;
 #pragma unroll
             for (int hk = 0; hk < 2; ++hk) {
-                // A = V^T: [m = component][k = column]
-                float va[4];
-                va[0] = __ldg(vi + (8 * hk + t) * DS + g);
-                va[1] = __ldg(vi + (8 * hk + t) * DS + g + 8);
-                va[2] = __ldg(vi + (8 * hk + t + 4) * DS + g);
-                va[3] = __ldg(vi + (8 * hk + t + 4) * DS + g + 8);
                 Frag3 av;
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
-                    const float h = tf32_hi(va[q4]);
+                    const float h = tf32_hi(va[w2][hk][q4]);
                     av.hi[q4] = __float_as_uint(h);
-                    av.lo[q4] = __float_as_uint(mma_lo(va[q4] - h));
+                    av.lo[q4] = __float_as_uint(mma_lo(va[w2][hk][q4] - h));
                 }
 #pragma unroll
                 for (int hn = 0; hn < 2; ++hn) {
