@@ -1599,8 +1599,7 @@ sss_tc_scan_bwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
 //    Requires the 16-byte aligned layouts (`aligned`); otherwise the SIMT scans run.
 // ------------------------------------------------------------------------------------------
 constexpr int QM = 4;                       // ring slots (shared memory: coefficients)
-constexpr int QG_S = 8;                     // cp.async ring depths (steps in flight): state scans, adjoint scans
-constexpr int QG_B = 6;
+constexpr int QG_S = 8;                     // cp.async ring depth (steps in flight) of the state scans
 constexpr int SM_THREADS = 128;             // 4 warps x 16 samples
 template <int N>
 __device__ __forceinline__ void cp_async_wait_n() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -1870,20 +1869,29 @@ sss_tc_scan_out_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, const float
 // L[j][row][0..15] = lambda_{j+1}, L[j][row][16..31] = mu_j: the adjoint of the state LEAVING chunk j, i.e. the value before the step.
 constexpr int GROW = 48;                                  // floats per staged grad_y row: 32 + 16 of padding (conflict-free 16-byte reads)
 constexpr int SB_FRAG_FLOATS = 12 * 32 * 2;              // fragments 4..15 of a tile
-constexpr size_t SB_SMEM = (size_t)QG_B * (SB_FRAG_FLOATS + (SM_THREADS / 32) * 16 * GROW) * sizeof(float);
+constexpr size_t sb_smem_bytes(int qg) { return (size_t)qg * (SB_FRAG_FLOATS + (SM_THREADS / 32) * 16 * GROW) * sizeof(float); }
+// QG_B = ring depth (steps in flight): 6 when the whole batch is one wave of CTAs at two per SM (the ring hides the memory latency), 3
+// above that (46 KB per CTA: four CTAs per SM hide it instead; at 65 536 samples the deep ring ran at 12 % occupancy, 47 % issue slots)
+template <int QG_B>
 __global__ void __launch_bounds__(SM_THREADS)
 sss_tc_scan_bwd_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks, const float* __restrict__ FSall, const float* __restrict__ gy,
-                         long ldgy, float* __restrict__ L, long B) {
+                         long ldgy, float* __restrict__ L, float* __restrict__ grad_bias, long B) {
     // rings of QG_B steps in dynamic shared memory: fragments 4..15 of the chunk's tile (shared by the CTA), and per warp the chunk's
     // 32 grad_y columns of its 16 samples (see the state scans for why these are not a register ring)
     extern __shared__ __align__(16) float sb_smem[];
     float* frag_ring = sb_smem;                                           // [QG_B][SB_FRAG_FLOATS]
     float* row_ring = sb_smem + (size_t)QG_B * SB_FRAG_FLOATS;            // [warp][QG_B][16][GROW]
+    // grad_bias (may be NULL): the column sums of grad_y come from the rows this kernel stages anyway -- direction mu sums the chunks
+    // of its own parity, per CTA in shared memory [chunk][32], one global reduction per (chunk, column) and CTA at the end
+    float* bsum = row_ring + (size_t)(SM_THREADS / 32) * QG_B * 16 * GROW;
+    if (grad_bias != nullptr)
+        for (int i = threadIdx.x; i < nchunks * 32; i += SM_THREADS) bsum[i] = 0.f;
     __shared__ int2 ctab[SCAN_CTAB];       // (row0, nrows) per chunk: the grad_y addresses must not wait on a load of the chunk table
     for (int i = threadIdx.x; i < nchunks && i < SCAN_CTAB; i += SM_THREADS) ctab[i] = make_int2(chunks[i].row0, chunks[i].nrows);
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, mu = blockIdx.y;
-    const long row0 = ((long)blockIdx.x * (SM_THREADS / 32) + warp) * 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, mu = blockIdx.x;   // direction fastest: the two CTAs that read the
+    // same grad_y rows (once per direction) are launched next to each other, and the second read comes from L2
+    const long row0 = ((long)blockIdx.y * (SM_THREADS / 32) + warp) * 16;
     const long rowa = row0 + g, rowb = row0 + g + 8;
     const bool va = rowa < B, vb = rowb < B;
     float* my_rows = row_ring + (size_t)warp * QG_B * 16 * GROW;
@@ -1928,6 +1936,12 @@ sss_tc_scan_bwd_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
         const float* G = my_rows + (size_t)(jj % QG_B) * 16 * GROW;
         if (va) *reinterpret_cast<float4*>(L + ((size_t)j * B + rowa) * 32 + (mu ? DS : 0) + 4 * t) = make_float4(d[0][0], d[0][1], d[1][0], d[1][1]);
         if (vb) *reinterpret_cast<float4*>(L + ((size_t)j * B + rowb) * 32 + (mu ? DS : 0) + 4 * t) = make_float4(d[0][2], d[0][3], d[1][2], d[1][3]);
+        if (grad_bias != nullptr && (j & 1) == mu) {      // lane = column of the chunk; rows past B and columns past nrows are staged as zeros
+            float cs = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) cs += G[r * GROW + lane];
+            atomicAdd(bsum + j * 32 + lane, cs);
+        }
         Frag3 a[2], ag[4];
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -1964,6 +1978,15 @@ sss_tc_scan_bwd_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
         }
     }
     cp_async_wait_all();
+    if (grad_bias != nullptr) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nchunks * 32; i += SM_THREADS) {
+            const int j = i >> 5, col = i & 31;
+            if ((j & 1) != mu) continue;
+            const int2 c = j < SCAN_CTAB ? ctab[j] : make_int2(__ldg(&chunks[j].row0), __ldg(&chunks[j].nrows));
+            if (col < c.y) atomicAdd(grad_bias + c.x + col, bsum[i]);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -3474,14 +3497,22 @@ bool use_fused_forward(const sn_sss_tc_plan* p, int64_t B) {
     return false;   // the three-kernel path with the four-threads-per-sample scans is faster at every batch size measured so far
 }
 
-// Chunk scans: the tensor-core chain kernels are bounded below by (2 x chunks) serial steps of ~1.5 us whatever the batch (forward
-// ~105 us, backward ~73 us with one CTA per SM), the warp-level tensor-core scans scale with the batch.  Measured (r2u, whole step):
-// 12 288 samples 0.343 ms (scans) vs 0.377 ms (chain), 16 384: 0.417 vs 0.418, 24 576: 0.577 vs ~0.55.  SNB200_SSS_TC_CHAIN=0/1 forces
-// the choice (tests).
-bool use_tc_chain(int64_t B) {
+// small-batch scans on the warp-level tensor cores (default) or the SIMT four-threads-per-sample kernels (SNB200_SSS_SCAN=simt)
+bool use_mma_scans() {
+    const char* e = getenv("SNB200_SSS_SCAN");
+    return !(e != nullptr && e[0] == 's');
+}
+
+// Chunk scans.  The warp-level tensor-core scans (sss_tc_scan_*_m) are the default at every batch size since round 2: they move 20 KB
+// per sample where the tcgen05 chain kernels move 24 (no ytmp round trip), are not quantised into waves of 128-sample tiles, and run
+// at the HBM roof at large batches.  Measured whole steps (r2zg/r2zh, scans vs chain): 16 384 samples 0.364 vs 0.399 ms, 32 768: 0.651
+// vs 0.656, 65 536: 1.216 vs 1.228 (before the bias sums moved into the adjoint scan).  The chain kernels remain for layers whose rows
+// are not 16-byte aligned (the SIMT scans are slower than the chain above ~10 k samples) and behind SNB200_SSS_TC_CHAIN=1 (tests).
+bool use_tc_chain(int64_t B, bool rows_aligned) {
     const char* e = getenv("SNB200_SSS_TC_CHAIN");
     if (e != nullptr && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
-    return B >= 16384;
+    if (use_mma_scans() && rows_aligned) return false;
+    return B >= 10240;
 }
 
 // build / build-backward: 2 = warp-level tensor-core kernels (default), 1 = SIMT with several lanes per column
@@ -3493,12 +3524,6 @@ int build_mode() {
     return 2;
 }
 bool use_quad_build() { return build_mode() >= 1; }
-
-// small-batch scans on the warp-level tensor cores (default) or the SIMT four-threads-per-sample kernels (SNB200_SSS_SCAN=simt)
-bool use_mma_scans() {
-    const char* e = getenv("SNB200_SSS_SCAN");
-    return !(e != nullptr && e[0] == 's');
-}
 
 // SIMT scans: split by direction (+ a parallel output kernel) by default; SNB200_SSS_SPLIT_SCANS=0 keeps the single-kernel scans
 bool use_split_scans(int64_t B) {
@@ -3570,7 +3595,7 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
         const int grid = ntiles < sm_count() ? ntiles : sm_count();
         SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
         SN_LAUNCH("sss_tc_fwd_fused_kernel", st, sss_tc_fwd_fused_kernel<<<grid, F_THREADS, F_SMEM, st>>>(mx, mw, p->chunks, p->nchunks, (long)B, ntiles, SC, states, y, (long)ldy, bias, aligned));
-        if (use_tc_chain(B)) {     // the backward's chain kernel reads the packed tiles
+        if (use_tc_chain(B, p->rows_aligned != 0)) {     // the backward's chain kernel reads the packed tiles
             float* CWp = const_cast<float*>(SC) + (size_t)p->nchunks * SCF;
             SN_LAUNCH("sss_tc_pack_chain_kernel", st, sss_tc_pack_chain_kernel<<<dim3(p->nchunks, 4), 256, 0, st>>>(SC, CWp));
         } else if (use_mma_scans()) {
@@ -3590,10 +3615,10 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
     }
     // the scans' coefficient tiles (chain tiles of the tcgen05 chain kernels, or fragment tiles of the warp-level scans) are packed on a
     // second stream while the local GEMM runs (they are not needed before the scans)
-    const bool pack_fs = !use_tc_chain(B) && use_mma_scans();     // the backward's adjoint scan reads them whatever y's alignment is
+    const bool pack_fs = !use_tc_chain(B, p->rows_aligned != 0) && use_mma_scans();     // the backward's adjoint scan reads them whatever y's alignment is
     const bool mma_scans = pack_fs && aligned && ((reinterpret_cast<uintptr_t>(y) & 7) == 0) && (ldy & 1) == 0;
-    snb::SideStream* sd = (use_tc_chain(B) || pack_fs) ? snb::side_stream() : nullptr;
-    if (use_tc_chain(B) || pack_fs) {
+    snb::SideStream* sd = (use_tc_chain(B, p->rows_aligned != 0) || pack_fs) ? snb::side_stream() : nullptr;
+    if (use_tc_chain(B, p->rows_aligned != 0) || pack_fs) {
         float* CWp = const_cast<float*>(SC) + (size_t)p->nchunks * SCF;
         float* FSp = fs_of(p, coef);
         cudaStream_t s2 = st;
@@ -3615,7 +3640,7 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
     }
     SN_LAUNCH("sss_tc_local_gemm_kernel", st, sss_tc_local_gemm_kernel<<<grid, G1_THREADS, G1_SMEM, st>>>(mx, mw, moy, mor, p->chunks, p->nchunks, (long)B, ntiles));
     if (sd != nullptr) SN_CHECK_CUDA(cudaStreamWaitEvent(st, sd->join, 0));
-    if (use_tc_chain(B)) {
+    if (use_tc_chain(B, p->rows_aligned != 0)) {
         CUtensorMap mc;
         const float* CW = SC + (size_t)p->nchunks * SCF;
         if (int rc = make_map_f32(&mc, CW, 32, (uint64_t)p->nchunks * 4 * CW_ROWS, 32, CW_ROWS)) return rc;
@@ -3661,7 +3686,7 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     const int aligned = p->rows_aligned ? 1 : 0;
     snb::SideStream* bias_side = nullptr;
     bool bias_later = false;
-    if (use_tc_chain(B)) {
+    if (use_tc_chain(B, p->rows_aligned != 0)) {
         CUtensorMap mc;
         const float* CW = SC + (size_t)p->nchunks * SCF;
         if (int rc = make_map_f32(&mc, CW, 32, (uint64_t)p->nchunks * 4 * CW_ROWS, 32, CW_ROWS)) return rc;
@@ -3673,9 +3698,21 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
         if (p->nchunks == 1 && grad_bias != nullptr)
             if (int rc = snb::colsum_accumulate(grad_y, ldgy, B, p->output_dim, grad_bias, st)) return rc;
     } else if (use_mma_scans() && aligned) {
-        bias_later = grad_bias != nullptr;
-        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_scan_bwd_m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_SMEM));
-        SN_LAUNCH("sss_tc_scan_bwd_m_kernel", st, sss_tc_scan_bwd_m_kernel<<<dim3((unsigned)((B + 63) / 64), 2), SM_THREADS, SB_SMEM, st>>>(p->chunks, p->nchunks, fs_of(p, coef), grad_y, (long)ldgy, L, (long)B));
+        // the bias gradient rides on the adjoint scan (it stages every grad_y row in shared memory); layers with so many chunks that the
+        // per-CTA sums do not fit two CTAs per SM take the separate column-sum kernel beside the build-backward kernel instead
+        SN_CHECK_ARG((B + 63) / 64 <= 65535, "sss_tc_backward: batch too large for the adjoint scan's grid (4 193 280 samples)");
+        const unsigned nblk64 = (unsigned)((B + 63) / 64);
+        const bool deep = 2 * nblk64 <= 2u * (unsigned)sm_count();
+        const size_t sb_smem = sb_smem_bytes(deep ? 6 : 3) + (size_t)p->nchunks * 32 * sizeof(float);
+        const bool bias_fused = grad_bias != nullptr && sb_smem <= (deep ? 110 : 56) * 1024;
+        bias_later = grad_bias != nullptr && !bias_fused;
+        if (deep) {
+            SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_scan_bwd_m_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb_smem));
+            SN_LAUNCH("sss_tc_scan_bwd_m_kernel", st, sss_tc_scan_bwd_m_kernel<6><<<dim3(2, nblk64), SM_THREADS, sb_smem, st>>>(p->chunks, p->nchunks, fs_of(p, coef), grad_y, (long)ldgy, L, bias_fused ? grad_bias : nullptr, (long)B));
+        } else {
+            SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_scan_bwd_m_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb_smem));
+            SN_LAUNCH("sss_tc_scan_bwd_m_kernel", st, sss_tc_scan_bwd_m_kernel<3><<<dim3(2, nblk64), SM_THREADS, sb_smem, st>>>(p->chunks, p->nchunks, fs_of(p, coef), grad_y, (long)ldgy, L, bias_fused ? grad_bias : nullptr, (long)B));
+        }
     } else {
         const int qs_threads = B <= 16384 ? 64 : QS_THREADS;
         const unsigned ydim = use_split_scans(B) ? 2u : 1u;

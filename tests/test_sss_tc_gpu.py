@@ -191,8 +191,13 @@ def test_full_batch_gradients_tc_vs_simt(built_lib, monkeypatch):
     x = torch.rand((B, 4096), device="cuda", generator=g) * 2 - 1
     gy = (torch.rand((B, 1000), device="cuda", generator=g) * 2 - 1) / B
     res = {}
-    for mode in ("tc", "simt"):
-        monkeypatch.setenv("SNB200_SSS_PATH", mode)
+    # "tc": the default scans of the tensor-core path (warp-level tensor-core scans); "tc_chain": the tcgen05 chain kernels forced
+    for mode in ("tc", "tc_chain", "simt"):
+        monkeypatch.setenv("SNB200_SSS_PATH", mode.split("_")[0])
+        if mode == "tc_chain":
+            monkeypatch.setenv("SNB200_SSS_TC_CHAIN", "1")
+        else:
+            monkeypatch.delenv("SNB200_SSS_TC_CHAIN", raising=False)
         layer.zero_flat_grad()
         for p in layer.parameters():
             p.grad = None
@@ -201,16 +206,19 @@ def test_full_batch_gradients_tc_vs_simt(built_lib, monkeypatch):
         torch.cuda.synchronize()
         res[mode] = (y.detach().double(), layer.flat_grad().detach().double().clone())
         del y
-    ey = float((res["tc"][0] - res["simt"][0]).abs().max() / res["simt"][0].abs().max())
-    eg = float((res["tc"][1] - res["simt"][1]).abs().max() / res["simt"][1].abs().max())
-    assert ey < RTOL and eg < RTOL, (ey, eg)
+    for mode in ("tc", "tc_chain"):
+        ey = float((res[mode][0] - res["simt"][0]).abs().max() / res["simt"][0].abs().max())
+        eg = float((res[mode][1] - res["simt"][1]).abs().max() / res["simt"][1].abs().max())
+        assert ey < RTOL and eg < RTOL, (mode, ey, eg)
 
 
-def test_forward_states_and_outputs_are_bitwise_reproducible(built_lib, monkeypatch):
+@pytest.mark.parametrize("chain", ["0", "1"])
+def test_forward_states_and_outputs_are_bitwise_reproducible(built_lib, monkeypatch, chain):
     """The forward has no atomics: y and the saved states S[chunk][B][32] must be bit-identical from run to run.  Guards the buffer
     hand-offs of the chain kernels (an mbarrier.arrive that released a ring slot to the next TMA load before the ld.shared of the
     writer warps had returned corrupted a few rows of S about once in eight passes at this size; scripts/stress_states.py)."""
     monkeypatch.setenv("SNB200_SSS_PATH", "tc")
+    monkeypatch.setenv("SNB200_SSS_TC_CHAIN", chain)        # 1: tcgen05 chain kernels, 0: warp-level tensor-core scans (the default)
     B = 65536
     layer = SSSLayer(4096, 1000, 0.105, nb_states=500, initial_system_approx=random_mixed_system(4096, 1000, 500, 16, seed=5000)).to("cuda")
     dev = torch.device("cuda")
@@ -222,7 +230,7 @@ def test_forward_states_and_outputs_are_bitwise_reproducible(built_lib, monkeypa
     ps = ctypes.byref(tc["struct"])
     _lib.check(L.sn_sss_tc_build(ps, _lib.ptr(layer.flat_parameters()), _lib.ptr(tc["coef"]), _lib.stream_ptr()), "build")
     ref = None
-    for rep in range(16):
+    for rep in range(10):
         y = torch.empty((B, 1000), device=dev)
         rbuf = torch.full((int(L.sn_sss_tc_rbuf_floats(ps, B)),), float("nan"), device=dev)
         states = torch.full((int(L.sn_sss_tc_states_floats(ps, B)),), float("nan"), device=dev)
