@@ -506,6 +506,15 @@ __device__ __forceinline__ void mma3(float (&d)[4], const Frag3& a, const float2
     mma_1688(d, a.hi, __float_as_uint(bh.x), __float_as_uint(bh.y));
 }
 
+// one of the three terms of d += A B (0: lo * hi, 1: hi * lo, 2: hi * hi): the kernels issue the terms of INDEPENDENT accumulators
+// round-robin -- the asm statements keep their order, and an HMMA that adds into the accumulator of its predecessor waits ~27 cycles
+template <int TERM>
+__device__ __forceinline__ void mma_t(float (&d)[4], const Frag3& a, const float2 bh, const float2 bl) {
+    if (TERM == 0) mma_1688(d, a.lo, __float_as_uint(bh.x), __float_as_uint(bh.y));
+    else if (TERM == 1) mma_1688(d, a.hi, __float_as_uint(bl.x), __float_as_uint(bl.y));
+    else mma_1688(d, a.hi, __float_as_uint(bh.x), __float_as_uint(bh.y));
+}
+
 // the two columns (fragment rows g and g + 8) a lane looks after
 struct ColPair {
     int tcol[2];      // column of the chunk (input tiles) or unit-state index (state tile)
@@ -608,17 +617,33 @@ sss_tc_buildm_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_ss
         split_frag(d[0], a[0]);
         split_frag(d[1], a[1]);
         const int rbase = st.out_off - c.row0;
-        // outputs of the stage from the state ENTERING it: Y = V ys^T (+ yu)
+        // outputs of the stage from the state ENTERING it, Y = V ys^T (+ yu), and the state leaving it, V <- V ss^T (+ su): up to four
+        // independent accumulators (two output n-tiles, two state halves), their products issued round-robin
+        const bool y0on = st.out_dim > 0, y1on = st.out_dim > 8;        // warp-uniform
+        float2 ybh[2][2], ybl[2][2], sbh[2][2], sbl[2][2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+                if (nt == 0 ? y0on : y1on) frag_b(build_smem + m.ys, 8 * nt + g, st.out_dim, 8 * h + 2 * t, st.d_in, ybh[nt][h], ybl[nt][h]);
+#pragma unroll
+            for (int hp = 0; hp < 2; ++hp) frag_b(build_smem + m.ss, 8 * hp + g, st.d_out, 8 * h + 2 * t, st.d_in, sbh[hp][h], sbl[hp][h]);
+        }
+        float y[2][4], sn[2][4];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { y[q][k] = 0.f; sn[q][k] = 0.f; }
+#define SN_ROUND(TERM, H)                                                                        \
+        if (y0on) mma_t<TERM>(y[0], a[H], ybh[0][H], ybl[0][H]);                                 \
+        mma_t<TERM>(sn[0], a[H], sbh[0][H], sbl[0][H]);                                          \
+        if (y1on) mma_t<TERM>(y[1], a[H], ybh[1][H], ybl[1][H]);                                 \
+        mma_t<TERM>(sn[1], a[H], sbh[1][H], sbl[1][H]);
+        SN_ROUND(0, 0) SN_ROUND(1, 0) SN_ROUND(2, 0) SN_ROUND(0, 1) SN_ROUND(1, 1) SN_ROUND(2, 1)
+#undef SN_ROUND
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
             if (8 * nt >= st.out_dim) break;
-            float y[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float2 bh, bl;
-                frag_b(build_smem + m.ys, 8 * nt + g, st.out_dim, 8 * h + 2 * t, st.d_in, bh, bl);
-                mma3(y, a[h], bh, bl);
-            }
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
                 if (!cp.valid[rr]) continue;
@@ -627,14 +652,29 @@ sss_tc_buildm_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_ss
                 for (int e = 0; e < 2; ++e) {
                     const int r = 8 * nt + 2 * t + e;
                     if (r >= st.out_dim) continue;
-                    float val = y[2 * rr + e];
+                    float val = y[nt][2 * rr + e];
                     if (mine[rr] && st.off_yu >= 0) val += build_smem[m.yu + r * st.in_dim + local[rr]];
                     if (state_tile) Omat[(rbase + r) * DS + cp.tcol[rr]] = val;
                     else if (wr) store_hi_lo(W, rbase + r, cp.tcol[rr], val);
                 }
             }
         }
-        mma_state_update(d, a, build_smem, m, st, mine, local, g, t);
+        // the columns whose stage this is enter the state through su
+#pragma unroll
+        for (int hp = 0; hp < 2; ++hp) {
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                if (mine[rr]) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int b = 8 * hp + 2 * t + e;
+                        if (b < st.d_out) sn[hp][2 * rr + e] += build_smem[m.su + b * st.in_dim + local[rr]];
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) d[hp][k] = sn[hp][k];
+        }
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) cp.act[rr] = cp.act[rr] || mine[rr];
     }
@@ -3235,10 +3275,12 @@ __device__ __forceinline__ void bwm_chain_step(float (&d)[2][4], const float* pb
     split_frag(d[0], al[0]);
     split_frag(d[1], al[1]);
     const int d_in = FAST ? DS : st.d_in, d_out = FAST ? DS : st.d_out;
-    const int ntr = FAST ? 1 : (st.out_dim + 7) >> 3;
+    const int ntr = FAST ? 1 : (st.out_dim + 7) >> 3;             // <= 2 (a stage has at most 16 outputs)
+    // B fragments of both halves hp of the new adjoint: ss (k <-> b, n = a = 8 hp + g) and ys (k <-> output r, n = a); G as A fragments
+    float2 sbh[2][2], sbl[2][2], ybh[2][2], ybl[2][2];
+    Frag3 ag[2];
 #pragma unroll
     for (int hp = 0; hp < 2; ++hp) {
-        float r4[4] = {0.f, 0.f, 0.f, 0.f};
         const int a = 8 * hp + g;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {                         // B[k <-> b][n = a] = ss[b][a]
@@ -3251,26 +3293,43 @@ __device__ __forceinline__ void bwm_chain_step(float (&d)[2][4], const float* pb
                 x0 = (b0 < d_out && a < d_in) ? pbuf[m.ss + b0 * d_in + a] : 0.f;
                 x1 = (b0 + 1 < d_out && a < d_in) ? pbuf[m.ss + (b0 + 1) * d_in + a] : 0.f;
             }
-            float2 bh, bl;
-            bh.x = tf32_hi(x0); bh.y = tf32_hi(x1); bl.x = mma_lo(x0 - bh.x); bl.y = mma_lo(x1 - bh.y);
-            mma3(r4, al[h], bh, bl);
-        }
-        for (int hr = 0; hr < ntr; ++hr) {                    // G as an A fragment (rows = columns g, g + 8; k <-> outputs r0, r0 + 1)
-            const int r0 = 8 * hr + 2 * t;
-            const bool k0 = r0 < st.out_dim, k1 = r0 + 1 < st.out_dim;
-            const float ga0 = k0 ? dMw[(rbase + r0) * BWM_DLD + g] : 0.f, gb0 = k0 ? dMw[(rbase + r0) * BWM_DLD + g + 8] : 0.f;
-            const float ga1 = k1 ? dMw[(rbase + r0 + 1) * BWM_DLD + g] : 0.f, gb1 = k1 ? dMw[(rbase + r0 + 1) * BWM_DLD + g + 8] : 0.f;
-            Frag3 ag;
-            frag_a_from(make_float2(ga0, ga1), make_float2(gb0, gb1), ag);
-            const float x0 = (k0 && a < d_in) ? pbuf[m.ys + r0 * d_in + a] : 0.f;
-            const float x1 = (k1 && a < d_in) ? pbuf[m.ys + (r0 + 1) * d_in + a] : 0.f;
-            float2 bh, bl;
-            bh.x = tf32_hi(x0); bh.y = tf32_hi(x1); bl.x = mma_lo(x0 - bh.x); bl.y = mma_lo(x1 - bh.y);
-            mma3(r4, ag, bh, bl);
+            sbh[hp][h].x = tf32_hi(x0); sbh[hp][h].y = tf32_hi(x1); sbl[hp][h].x = mma_lo(x0 - sbh[hp][h].x); sbl[hp][h].y = mma_lo(x1 - sbh[hp][h].y);
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) d[hp][k] = r4[k];
+        for (int hr = 0; hr < 2; ++hr) {
+            if (hr >= ntr) break;
+            const int r0 = 8 * hr + 2 * t;
+            const bool k0 = r0 < st.out_dim, k1 = r0 + 1 < st.out_dim;
+            const float x0 = (k0 && a < d_in) ? pbuf[m.ys + r0 * d_in + a] : 0.f;
+            const float x1 = (k1 && a < d_in) ? pbuf[m.ys + (r0 + 1) * d_in + a] : 0.f;
+            ybh[hp][hr].x = tf32_hi(x0); ybh[hp][hr].y = tf32_hi(x1); ybl[hp][hr].x = mma_lo(x0 - ybh[hp][hr].x); ybl[hp][hr].y = mma_lo(x1 - ybh[hp][hr].y);
+        }
     }
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {                          // G as an A fragment (rows = columns g, g + 8; k <-> outputs r0, r0 + 1)
+        if (hr >= ntr) break;
+        const int r0 = 8 * hr + 2 * t;
+        const bool k0 = r0 < st.out_dim, k1 = r0 + 1 < st.out_dim;
+        const float ga0 = k0 ? dMw[(rbase + r0) * BWM_DLD + g] : 0.f, gb0 = k0 ? dMw[(rbase + r0) * BWM_DLD + g + 8] : 0.f;
+        const float ga1 = k1 ? dMw[(rbase + r0 + 1) * BWM_DLD + g] : 0.f, gb1 = k1 ? dMw[(rbase + r0 + 1) * BWM_DLD + g + 8] : 0.f;
+        frag_a_from(make_float2(ga0, ga1), make_float2(gb0, gb1), ag[hr]);
+    }
+    // four independent accumulators (lam ss and G ys, for each half of the new adjoint), products issued round-robin
+    float rs[2][4], rg[2][4];
+#pragma unroll
+    for (int hp = 0; hp < 2; ++hp)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { rs[hp][k] = 0.f; rg[hp][k] = 0.f; }
+    const bool g0on = ntr > 0, g1on = ntr > 1;
+#define SN_ROUND(TERM, H)                                                                              \
+    mma_t<TERM>(rs[0], al[H], sbh[0][H], sbl[0][H]); mma_t<TERM>(rs[1], al[H], sbh[1][H], sbl[1][H]);  \
+    if (H == 0 ? g0on : g1on) { mma_t<TERM>(rg[0], ag[H], ybh[0][H], ybl[0][H]); mma_t<TERM>(rg[1], ag[H], ybh[1][H], ybl[1][H]); }
+    SN_ROUND(0, 0) SN_ROUND(1, 0) SN_ROUND(2, 0) SN_ROUND(0, 1) SN_ROUND(1, 1) SN_ROUND(2, 1)
+#undef SN_ROUND
+#pragma unroll
+    for (int hp = 0; hp < 2; ++hp)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d[hp][k] = rs[hp][k] + rg[hp][k];
 }
 
 __global__ void __launch_bounds__(BM_THREADS)
@@ -3427,12 +3486,12 @@ sss_tc_build_bwdm_kernel(const sn_sss_stage* __restrict__ stages, int n, const s
                     av.hi[q4] = __float_as_uint(h);
                     av.lo[q4] = __float_as_uint(mma_lo(va[w2][hk][q4] - h));
                 }
+                // four independent accumulators (two halves of d_ss, up to two of d_ys), products issued round-robin
+                float2 lbh[2], lbl[2], gbh[2], gbl[2];
 #pragma unroll
                 for (int hn = 0; hn < 2; ++hn) {
                     const float x0 = L2[(8 * hk + t) * BWM_LLD + 8 * hn + g], x1 = L2[(8 * hk + t + 4) * BWM_LLD + 8 * hn + g];
-                    float2 bh, bl;
-                    bh.x = tf32_hi(x0); bh.y = tf32_hi(x1); bl.x = mma_lo(x0 - bh.x); bl.y = mma_lo(x1 - bh.y);
-                    mma3(rss[hn], av, bh, bl);
+                    lbh[hn].x = tf32_hi(x0); lbh[hn].y = tf32_hi(x1); lbl[hn].x = mma_lo(x0 - lbh[hn].x); lbl[hn].y = mma_lo(x1 - lbh[hn].y);
                 }
 #pragma unroll
                 for (int hn = 0; hn < 2; ++hn) {
@@ -3440,10 +3499,14 @@ sss_tc_build_bwdm_kernel(const sn_sss_stage* __restrict__ stages, int n, const s
                     const int r = 8 * hn + g;
                     const float x0 = r < st.out_dim ? dM2[(rbase + r) * BWM_DLD + 8 * hk + t] : 0.f;
                     const float x1 = r < st.out_dim ? dM2[(rbase + r) * BWM_DLD + 8 * hk + t + 4] : 0.f;
-                    float2 bh, bl;
-                    bh.x = tf32_hi(x0); bh.y = tf32_hi(x1); bl.x = mma_lo(x0 - bh.x); bl.y = mma_lo(x1 - bh.y);
-                    mma3(rys[hn], av, bh, bl);
+                    gbh[hn].x = tf32_hi(x0); gbh[hn].y = tf32_hi(x1); gbl[hn].x = mma_lo(x0 - gbh[hn].x); gbl[hn].y = mma_lo(x1 - gbh[hn].y);
                 }
+#define SN_ROUND(TERM)                                                                     \
+                mma_t<TERM>(rss[0], av, lbh[0], lbl[0]); mma_t<TERM>(rss[1], av, lbh[1], lbl[1]); \
+                if (ntr > 0) mma_t<TERM>(rys[0], av, gbh[0], gbl[0]);                             \
+                if (ntr > 1) mma_t<TERM>(rys[1], av, gbh[1], gbl[1]);
+                SN_ROUND(0) SN_ROUND(1) SN_ROUND(2)
+#undef SN_ROUND
             }
         }
         // D fragments: rows a = g, g + 8; columns 8 hn + 2t, + 1 (b of d_ss, r of d_ys)
