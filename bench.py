@@ -66,13 +66,15 @@ class SSSWorkload:
     # pass, y written once; every other byte a kernel moves is scratch): 16 384 + 4 000 + 4 000 + 20 384 = 40 768
     kernel_bytes_per_sample = {"sss_tc_local_gemm_kernel": 4 * 4096, "sss_tc_chain_fwd_kernel": 4 * 1000, "sss_tc_chain_bwd_kernel": 4 * 1000,
                                "sss_tc_grad_gemm_kernel": 4 * (4096 + 1000), "sss_tc_scan_out_q_kernel": 4 * 1000,
-                               "sss_tc_scan_bwd_q_kernel": 4 * 1000}
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch at local batch 65 536 from the committed `ncu --set full` capture named in
-    # traffic_source (cold-cache replays of the same bench command); only quoted for the batch it was captured at
-    traffic_source = "profiles/r1q_sss_tc_top_kernels.md"
+                               "sss_tc_scan_bwd_q_kernel": 4 * 1000, "sss_tc_scan_out_m_kernel": 4 * 1000, "sss_tc_scan_bwd_m_kernel": 4 * 1000}
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch at local batch 65 536 from the committed `ncu --set full` captures named in
+    # traffic_source (cold-cache replays of the same bench command); only quoted for the batch they were captured at
+    traffic_source = "profiles/r2_sss_top_kernels.md, profiles/r2_sss_scans_65536.md"
     traffic_batch = 65536
-    traffic_bytes = {"sss_tc_local_gemm_kernel": 1.0775e9 + 0.5094e9, "sss_tc_chain_fwd_kernel": 0.7607e9 + 0.7648e9,
-                     "sss_tc_chain_bwd_kernel": 0.5354e9 + 0.2493e9, "sss_tc_grad_gemm_kernel": 1.9521e9 + 0.0074e9}
+    traffic_bytes = {"sss_tc_local_gemm_kernel": 1.0775e9 + 0.5096e9, "sss_tc_chain_fwd_kernel": 0.7644e9 + 0.7663e9,
+                     "sss_tc_chain_bwd_kernel": 0.5358e9 + 0.2520e9, "sss_tc_grad_gemm_kernel": 1.9522e9 + 0.0064e9,
+                     "sss_tc_scan_states_m_kernel": 0.2685e9 + 0.2421e9, "sss_tc_scan_out_m_kernel": 0.5370e9 + 0.2382e9,
+                     "sss_tc_scan_bwd_m_kernel": 0.3025e9 + 0.2379e9}
 
     def describe(self):
         return dict(workload="C5: SSS 4096->1000, 500 stages, statespace 16, fp32 fwd+bwd (param grads), global batch 65536",

@@ -466,7 +466,10 @@ __device__ __forceinline__ int chunk_params_ranges(float* pbuf, StageP* ptrs, co
 // either sign, so that truncation does not bias the product (the tcgen05 paths truncate hi and therefore round lo, see lo_of_trunc).
 // cvt.rna.tf32.f32 is not an instruction on sm_100a (ptxas emits add / mask / isfinite / select): a split costs 3 instructions this way
 // instead of 9, and the splits were three quarters of the instructions of the scan kernels (ncu source view, r2n).
-__device__ __forceinline__ float mma_lo(float remainder) { return remainder; }
+#ifndef SN_MMA_LO_ROUND
+#define SN_MMA_LO_ROUND 0
+#endif
+__device__ __forceinline__ float mma_lo(float remainder) { return SN_MMA_LO_ROUND ? tf32_hi(remainder) : remainder; }
 
 // B fragment (M[row][col], M[row][col + 1]) of a compact row-major [nrows][ncols] matrix, zero outside; split into tf32 hi / lo
 __device__ __forceinline__ void frag_b(const float* M, int row, int nrows, int col, int ncols, float2& hi, float2& lo) {

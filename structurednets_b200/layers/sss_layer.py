@@ -4,8 +4,11 @@ Drop-in for ``structurednets.layers.sss_layer.SSSLayer`` (reference layers/sss_l
 constructor, same ``ParameterList`` names ``A..G`` and shapes (so the same ``state_dict`` keys
 ``bias, A.0 .. G.{n-1}``), same ``statespace_dim`` budget rule and the same module-level helpers
 (``get_nb_parameters``, ``get_max_statespace_dim``, ``standard_dims_in_dims_out_computation``).
-``forward`` + autograd backward run in the hand-written kernels of ``csrc/sss.cu`` through the C ABI
-(``sn_sss_pack / sn_sss_forward / sn_sss_backward``, include/snb200.h); there is no CPU path.
+``forward`` + autograd backward run in hand-written sm_100a kernels through the C ABI (include/snb200.h): the tensor-core path of
+``csrc/sss_tc.cu`` (``sn_sss_tc_build / sn_sss_tc_forward / sn_sss_tc_backward``: chunked 3xTF32 formulation) for
+layers inside its limits (state dimensions <= 16, <= 16 outputs and <= 160 inputs per stage, input and output dimensions multiples of 4),
+the SIMT kernels of ``csrc/sss.cu`` (``sn_sss_pack / sn_sss_forward / sn_sss_backward``) for everything else; ``SNB200_SSS_PATH=tc|simt``
+forces one.  There is no CPU path.
 """
 import ctypes
 import os
