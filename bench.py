@@ -778,6 +778,7 @@ def run_ours(args, wl):
     if n_gpus > 1 and runner.has_flat:
         dp_ok, dp_detail = dp_check(runner, n_gpus, rank, device)
 
+    grad_transport = runner.grad_sync.transport if (n_gpus > 1 and runner.grad_sync is not None and hasattr(runner.grad_sync, "transport")) else None
     m = measure(runner, args.steps, args.warmup, peaks, local_rank, barrier, use_graph=not args.no_graph,
                 sustained_s=2.5 if (n_gpus == 1 and not args.quick) else 0.0)
     elapsed_ms = m["elapsed_ms"]
@@ -836,6 +837,9 @@ def run_ours(args, wl):
         if dp_ok is not None:
             line["dp_check"] = dp_ok
             line["dp_check_detail"] = dp_detail
+        if grad_transport is not None:
+            # "p2p": the one-shot all-reduce kernel of csrc/p2p.cu over NVLink peer memory; "nccl": torch.distributed.all_reduce
+            line["config"]["grad_allreduce"] = grad_transport
         if n_gpus == 1 and not args.no_cpu_baseline and wl.cpu_sample_batch:
             line["cpu_baseline"] = time_reference_steps(wl, steps=20, warmup=1, budget_s=12.0)[0]
             try:

@@ -286,6 +286,20 @@ int sn_flat_sgd(float* params, const float* grads, int64_t n, float lr, float gr
 int sn_flat_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
                  float eps, float grad_scale, int* step_dev /* nullable */, int step_host, sn_stream_t stream);
 
+/* ---- the path's only exchange step: one-shot all-reduce of the flat gradient buffer over NVLink peer memory.
+ * The reference has no multi-GPU code (F6); this replaces torch.distributed.all_reduce(flat_grad) in the data-parallel step.
+ * Every rank allocates one region (cudaMalloc), exports its 64-byte CUDA IPC handle, imports its peers' and then calls
+ * sn_allreduce_oneshot_f32 once per step with the same n (<= capacity): data <- scale * sum over ranks, bit-identical on every rank.
+ * regions: host array of `world` device pointers, regions[rank] = the own region.  Graph-capturable (epochs live in device memory). */
+size_t sn_p2p_region_bytes(int64_t capacity_floats, int world);
+int sn_p2p_alloc(void** region, int64_t capacity_floats, int world);
+int sn_p2p_free(void* region);
+int sn_p2p_export(const void* region, unsigned char* handle64);
+int sn_p2p_import(const unsigned char* handle64, void** region);
+int sn_p2p_close(void* region);
+int sn_allreduce_oneshot_f32(float* data, int64_t n, void* const* regions, int rank, int world, int64_t capacity_floats, float scale,
+                             sn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

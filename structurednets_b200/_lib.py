@@ -152,6 +152,20 @@ def _declare(lib):
     lib.sn_flat_sgd.argtypes = [vp, vp, i64, f32, f32, vp]
     lib.sn_flat_adam.restype = c_int
     lib.sn_flat_adam.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp, i32, vp]
+    lib.sn_p2p_region_bytes.restype = ctypes.c_size_t
+    lib.sn_p2p_region_bytes.argtypes = [i64, c_int]
+    lib.sn_p2p_alloc.restype = c_int
+    lib.sn_p2p_alloc.argtypes = [ctypes.POINTER(c_void_p), i64, c_int]
+    lib.sn_p2p_free.restype = c_int
+    lib.sn_p2p_free.argtypes = [vp]
+    lib.sn_p2p_export.restype = c_int
+    lib.sn_p2p_export.argtypes = [vp, ctypes.c_char_p]
+    lib.sn_p2p_import.restype = c_int
+    lib.sn_p2p_import.argtypes = [ctypes.c_char_p, ctypes.POINTER(c_void_p)]
+    lib.sn_p2p_close.restype = c_int
+    lib.sn_p2p_close.argtypes = [vp]
+    lib.sn_allreduce_oneshot_f32.restype = c_int
+    lib.sn_allreduce_oneshot_f32.argtypes = [vp, i64, ctypes.POINTER(c_void_p), c_int, c_int, i64, f32, vp]
     for name, fn in _EXTRA_DECLS:
         fn(lib)
 
