@@ -29,8 +29,8 @@ print("|---|---|" + "---|" * len(keys))
 rows = []
 for f, name in zip(counts, names):
     c = counts[f]
-    name = re.sub(r"\(.*", "", name).replace("(anonymous namespace)::", "").replace("snb::t3::", "").replace("snb::tc::", "").replace("snb::", "")
-    name = name.replace("void ", "")
+    name = name.replace("(anonymous namespace)::", "").replace("void ", "")
+    name = re.sub(r"\(.*", "", name).replace("snb::t3::", "").replace("snb::tc::", "").replace("snb::", "")
     rows.append((name, sum(c.values()), [sum(v for k, v in c.items() if k.startswith(key)) for key in keys]))
 for name, tot, vals in sorted(rows):
     print("| `%s` | %d | " % (name[:70], tot) + " | ".join(str(v) if v else "" for v in vals) + " |")
