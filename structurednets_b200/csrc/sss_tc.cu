@@ -525,33 +525,6 @@ struct ColPair {
     bool act[2];
 };
 
-// V <- V ss^T (+ su columns of the columns whose stage this is): d[hp] = states 8 hp .. 8 hp + 7 of the tile's 16 columns
-__device__ __forceinline__ void mma_state_update(float (&d)[2][4], const Frag3 (&a)[2], const float* pbuf, const StageP& m, const sn_sss_stage& st,
-                                                 const bool (&mine)[2], const int (&local)[2], int g, int t) {
-#pragma unroll
-    for (int hp = 0; hp < 2; ++hp) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float2 bh, bl;
-            frag_b(pbuf + m.ss, 8 * hp + g, st.d_out, 8 * h + 2 * t, st.d_in, bh, bl);
-            mma3(acc, a[h], bh, bl);
-        }
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            if (mine[rr]) {
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int b = 8 * hp + 2 * t + e;
-                    if (b < st.d_out) acc[2 * rr + e] += pbuf[m.su + b * st.in_dim + local[rr]];
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) d[hp][k] = acc[k];
-    }
-}
-
 __global__ void __launch_bounds__(BM_THREADS)
 sss_tc_buildm_kernel(const sn_sss_stage* __restrict__ stages, int n, const sn_sss_tc_chunk* __restrict__ chunks, const float* __restrict__ params,
                      float* __restrict__ Wall, float* __restrict__ SCall, float* __restrict__ VG, int lists_contiguous) {
@@ -967,9 +940,6 @@ sss_tc_local_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
 // ------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 128;
 
-__device__ __forceinline__ void load_sc(float4* dst, const float* __restrict__ src, int nfloat4) {
-    for (int i = threadIdx.x; i < nfloat4; i += SCAN_THREADS) dst[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-}
 // out[b] += sum_a M[b][a] v[a]   (M row-major DS columns in shared memory, read as broadcast float4)
 template <int ROWS>
 __device__ __forceinline__ void matvec_acc(const float4* __restrict__ M, const float (&v)[DS], float* out) {
@@ -1633,26 +1603,19 @@ sss_tc_scan_bwd_q_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
 }
 
 // ------------------------------------------------------------------------------------------
-// 3m/4m. small-batch chunk scans on the warp-level tensor cores (mma.sync m16n8k8 tf32, 3xTF32).  The four-threads-per-sample
-//    scans above are instruction-bound (ncu at 8 192 samples: 219 warp instructions per chunk step and 8 samples for 64 useful
-//    FFMA issues).  Here a warp owns 16 samples and keeps their state as the D fragment of a 16 x 16 tile; a step is
+// 3m/4m. chunk scans on the warp-level tensor cores (mma.sync m16n8k8 tf32, 3xTF32): the default scans at every batch size.  The
+//    four-threads-per-sample scans above are instruction-bound (ncu at 8 192 samples: 219 warp instructions per chunk step and 8
+//    samples for 64 useful FFMA issues).  Here a warp owns 16 samples and keeps their state as the D fragment of a 16 x 16 tile; a step is
 //        state' = r + state Phi^T      (r is the accumulator's initial value, the previous D fragment is the next A fragment --
 //                                       same register chaining as the build kernel, no shuffle, no shared-memory round trip)
-//    with Phi / O staged in shared memory through a ring of QM slots filled QM - 1 steps ahead.  ~5x fewer instructions per sample.
-//    Requires the 16-byte aligned layouts (`aligned`); otherwise the SIMT scans run.
+//    The chunk's B fragments (packed once per forward, sss_tc_pack_scan_kernel) and the warp's per-sample rows arrive through cp.async
+//    rings in shared memory.  Requires the 16-byte aligned layouts (`aligned`); otherwise the SIMT scans or the tcgen05 chain run.
 // ------------------------------------------------------------------------------------------
-constexpr int QM = 4;                       // ring slots (shared memory: coefficients)
 constexpr int QG_S = 8;                     // cp.async ring depth (steps in flight) of the state scans
 constexpr int SM_THREADS = 128;             // 4 warps x 16 samples
 template <int N>
 __device__ __forceinline__ void cp_async_wait_n() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// (hi, lo) parts of the B fragment (M[row][col], M[row][col + 1]) of a row-major matrix with 16 columns in shared memory
-__device__ __forceinline__ void frag_b16(const float* M, int row, int col, float2& hi, float2& lo) {
-    const float2 r = *reinterpret_cast<const float2*>(M + row * DS + col);
-    hi.x = tf32_hi(r.x); hi.y = tf32_hi(r.y);
-    lo.x = mma_lo(r.x - hi.x); lo.y = mma_lo(r.y - hi.y);
-}
 // A fragment with the K index permuted like split_frag's (logical k = t <-> physical column 2t, k = t + 4 <-> 2t + 1 of the group of 8),
 // from two consecutive floats of rows g and g + 8
 __device__ __forceinline__ void frag_a_from(const float2 row_a, const float2 row_b, Frag3& f) {
