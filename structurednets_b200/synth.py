@@ -31,21 +31,24 @@ class SyntheticMixedSystem:
         self.anticausal_system = _StrictSystem(anticausal_stages)
 
     def to_matrix(self) -> np.ndarray:
+        """Dense matrix of the system: one sweep per direction carrying the states of ALL earlier (later) input columns at once, so the
+        cost is n small matrix products of growing width instead of n^2 Python iterations."""
         n = len(self.dims_in)
         io = np.concatenate([[0], np.cumsum(self.dims_in)]).astype(int)
         oo = np.concatenate([[0], np.cumsum(self.dims_out)]).astype(int)
         T = np.zeros((oo[-1], io[-1]))
         cs, acs = self.causal_system.stages, self.anticausal_system.stages
-        for j in range(n):
-            T[oo[j]:oo[j + 1], io[j]:io[j + 1]] = cs[j].D_matrix
-            acc = cs[j].B_matrix
-            for i in range(j + 1, n):
-                T[oo[i]:oo[i + 1], io[j]:io[j + 1]] = cs[i].C_matrix @ acc
-                acc = cs[i].A_matrix @ acc
-            acc = acs[j].B_matrix
-            for i in range(j - 1, -1, -1):
-                T[oo[i]:oo[i + 1], io[j]:io[j + 1]] = acs[i].C_matrix @ acc
-                acc = acs[i].A_matrix @ acc
+        acc = np.zeros((cs[0].A_matrix.shape[1], 0))          # states (entering stage i) driven by the columns of stages < i
+        for i in range(n):
+            T[oo[i]:oo[i + 1], io[i]:io[i + 1]] = cs[i].D_matrix
+            if acc.shape[1]:
+                T[oo[i]:oo[i + 1], :io[i]] = cs[i].C_matrix @ acc
+            acc = np.concatenate([cs[i].A_matrix @ acc, cs[i].B_matrix], axis=1)
+        acc = np.zeros((acs[n - 1].A_matrix.shape[1], 0))     # anticausal: columns of stages > i, in column order
+        for i in range(n - 1, -1, -1):
+            if acc.shape[1]:
+                T[oo[i]:oo[i + 1], io[i + 1]:] = acs[i].C_matrix @ acc
+            acc = np.concatenate([acs[i].B_matrix, acs[i].A_matrix @ acc], axis=1)
         return T
 
 

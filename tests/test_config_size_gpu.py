@@ -91,6 +91,30 @@ def test_sss_c1_chain_kernels_vs_oracle(built_lib, monkeypatch, chain):
     assert rel_err(layer.bias.grad.cpu().numpy(), b.grad.numpy()) < RTOL
 
 
+def test_sss_layer_with_more_chunks_than_the_scan_tables_vs_oracle(built_lib, monkeypatch):
+    """4 400 stages of one input and one output = 275 chunks: more than the adjoint scan's shared-memory chunk table (256 entries, the
+    rest is read from global memory) and too many for its per-CTA bias sums (the column-sum kernel beside the build-backward kernel
+    takes over) -- the two paths the C1 / C5 layer (32 chunks) never takes."""
+    monkeypatch.setenv("SNB200_SSS_PATH", "tc")
+    B, n = 24, 4400
+    layer = SSSLayer(n, n, 0.02, nb_states=n, initial_system_approx=random_mixed_system(n, n, n, 4, seed=1005))
+    assert layer._use_tc_path()
+    rng = np.random.default_rng(1005)
+    X = rng.uniform(-1, 1, size=(B, n)).astype(np.float32); gy = rng.uniform(-1, 1, size=(B, n)).astype(np.float32) / B
+    l32 = [[p.detach().clone().requires_grad_(True) for p in getattr(layer, nm)] for nm in "ABCDEFG"]
+    b = layer.bias.detach().clone().requires_grad_(True)
+    yo = O.sss_forward(torch.tensor(X), *l32, b, layer.dims_in, layer.dims_out); (yo * torch.tensor(gy)).sum().backward()
+    layer = layer.to(DEV)
+    y = layer(torch.tensor(X, device=DEV)); (y * torch.tensor(gy, device=DEV)).sum().backward()
+    assert rel_err(y.detach().cpu().numpy(), yo.detach().numpy()) < RTOL
+    for li, name in enumerate("ABCDEFG"):
+        got = np.concatenate([p.grad.detach().cpu().numpy().reshape(-1) for p in getattr(layer, name)])
+        ref = np.concatenate([(p.grad.numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32)).reshape(-1) for p in l32[li]])
+        if ref.size:
+            assert rel_err(got, ref) < RTOL, "grad %s" % name
+    assert rel_err(layer.bias.grad.cpu().numpy(), b.grad.numpy()) < RTOL
+
+
 @pytest.mark.parametrize("path", ["leaf", "dense"])
 def test_hmat_c4h_shape_both_paths_vs_oracle(built_lib, monkeypatch, path):
     """BASELINE C4-H (2048 -> 1000, eta 0.5, min block 2: 2 560 leaves of rank <= 6) on the leaf-by-leaf kernels
