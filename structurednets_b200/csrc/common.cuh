@@ -36,6 +36,22 @@ inline cudaStream_t as_stream(sn_stream_t s) { return reinterpret_cast<cudaStrea
         }                                                                                      \
     } while (0)
 
+// cudaFuncSetAttribute(kernel, MaxDynamicSharedMemorySize, bytes) only when `bytes` exceeds what this call site has already set on the
+// current device: the attribute is sticky, and the call costs about a microsecond of host time per launch otherwise (an eager SSS step
+// is host bound at small batches).  The kernel comes last because template argument lists contain commas.
+#define SN_MAX_DEVICES 64
+#define SN_SET_MAX_SMEM(bytes, ...)                                                                              \
+    do {                                                                                                         \
+        static int sn_smem_set_[SN_MAX_DEVICES];                                                                 \
+        int sn_dev_ = -1;                                                                                        \
+        SN_CHECK_CUDA(cudaGetDevice(&sn_dev_));                                                                  \
+        const int sn_b_ = (int)(bytes);                                                                          \
+        if (sn_dev_ < 0 || sn_dev_ >= SN_MAX_DEVICES || sn_smem_set_[sn_dev_] < sn_b_) {                         \
+            SN_CHECK_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, sn_b_)); \
+            if (sn_dev_ >= 0 && sn_dev_ < SN_MAX_DEVICES) sn_smem_set_[sn_dev_] = sn_b_;                         \
+        }                                                                                                        \
+    } while (0)
+
 #define SN_CHECK_LAUNCH(name)                                                                  \
     do {                                                                                       \
         cudaError_t _e = cudaGetLastError();                                                   \

@@ -327,7 +327,7 @@ inline int gemm_bf16_tc(int M, int N, int K, const void* A, long lda, const void
     dim3 grid(ceil_div(N, BN), ceil_div(M, BM), ceil_div(K > 0 ? K : 1, args.kslice));
     SN_CHECK_ARG(EPI == ATOMIC_F32 || grid.z == 1, "split-K needs the atomic epilogue");
     constexpr size_t smem = smem_bytes<BN>();
-    SN_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, EPI, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SN_SET_MAX_SMEM((int)smem, gemm_bf16_tc_kernel<BN, EPI, MN>);
     SN_LAUNCH("gemm_bf16_tc_kernel", stream, gemm_bf16_tc_kernel<BN, EPI, MN><<<grid, THREADS, smem, stream>>>(ma, mb, args));
     return 0;
 }

@@ -241,7 +241,7 @@ inline int gemm_tf32x3_launch(int M, int N, int K, float alpha, const float* A, 
     args.kdev = kdev; args.mdev = mdev;
     dim3 grid(ceil_div(N, 128), ceil_div(M, 128), ceil_div(K > 0 ? K : 1, args.kslice));
     SN_CHECK_ARG(atomic || grid.z == 1, "gemm_tf32x3: split-K needs the accumulating epilogue");
-    SN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3_SMEM));
+    SN_SET_MAX_SMEM((int)T3_SMEM, gemm_tf32x3_kernel<A_MN, B_MN>);
     SN_LAUNCH("gemm_tf32x3_kernel", stream, gemm_tf32x3_kernel<A_MN, B_MN><<<grid, T3_THREADS, T3_SMEM, stream>>>(ma, mb, args));
     return 0;
 }

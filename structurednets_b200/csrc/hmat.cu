@@ -262,7 +262,7 @@ int sn_hmat_forward(const int32_t* leaves, int nleaves, const float* params, con
     {                                                                                                                      \
         size_t smem = hm_smem<NS>(in_dim, out_dim, false);                                                                 \
         if (smem <= 227 * 1024) {                                                                                          \
-            SN_CHECK_CUDA(cudaFuncSetAttribute(hmat_fwd_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            SN_SET_MAX_SMEM((int)smem, hmat_fwd_kernel<NS>); \
             hmat_fwd_kernel<NS><<<(unsigned)((B + NS - 1) / NS), HM_THREADS, smem, st>>>(lv, nleaves, params, x, ldx, y, ldy, bias, B, in_dim, out_dim); \
             SN_CHECK_LAUNCH("hmat_fwd_kernel");                                                                            \
             return 0;                                                                                                      \
@@ -289,7 +289,7 @@ int sn_hmat_backward(const int32_t* leaves, int nleaves, const float* params, co
     {                                                                                                                      \
         size_t smem = hm_smem<NS>(in_dim, out_dim, true);                                                                  \
         if (smem <= 227 * 1024) {                                                                                          \
-            SN_CHECK_CUDA(cudaFuncSetAttribute(hmat_bwd_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            SN_SET_MAX_SMEM((int)smem, hmat_bwd_kernel<NS>); \
             hmat_bwd_kernel<NS><<<(unsigned)((B + NS - 1) / NS), HM_THREADS, smem, st>>>(lv, nleaves, params, x, ldx, grad_y, ldgy, grad_params, B, in_dim, out_dim); \
             SN_CHECK_LAUNCH("hmat_bwd_kernel");                                                                            \
             return 0;                                                                                                      \

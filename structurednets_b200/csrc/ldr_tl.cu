@@ -329,7 +329,7 @@ int sn_ldr_build_weight(int n, int r, const double* A_vals, const int32_t* A_slo
     }
     const int C = kr_cols_fwd(n);
     const size_t smem = (size_t)2 * C * n * sizeof(double);
-    SN_CHECK_CUDA(cudaFuncSetAttribute(ldr_krylov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SN_SET_MAX_SMEM((int)smem, ldr_krylov_kernel);
     SN_LAUNCH("ldr_krylov_kernel", st, ldr_krylov_kernel<<<dim3(snb::ceil_div(r, C), 2), KR_THREADS, smem, st>>>(
         n, r, J, C, bands, G, H, reinterpret_cast<double*>(base + L.k64), K32, L.rows, reinterpret_cast<double*>(base + L.colnorm)));
     SN_LAUNCH("ldr_terms_kernel", st, ldr_terms_kernel<<<1, 1024, 0, st>>>(n, r, J, L.rows, rel_tol, reinterpret_cast<double*>(base + L.colnorm), status));
@@ -361,7 +361,7 @@ int sn_ldr_backward(int n, int r, const float* dW, const int32_t* A_slot, int A_
     SN_CHECK_CUDA(cudaMemsetAsync(gbands, 0, 2 * nb * sizeof(double), st));
     const int C = kr_cols_bwd(n);
     const size_t smem = ((size_t)2 * C * n + 3 * (size_t)n) * sizeof(double);
-    SN_CHECK_CUDA(cudaFuncSetAttribute(ldr_krylov_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SN_SET_MAX_SMEM((int)smem, ldr_krylov_bwd_kernel);
     SN_LAUNCH("ldr_krylov_bwd_kernel", st, ldr_krylov_bwd_kernel<<<dim3(snb::ceil_div(r, C), 2), KR_THREADS, smem, st>>>(
         n, r, J, C, bands, reinterpret_cast<const double*>(base + L.k64), dK32, L.rows, status, gbands, gG, gH));
     if (gA_vals && A_nnz) { band_scatter_grad_kernel<<<grid1(A_nnz), 256, 0, st>>>(gbands, A_slot, A_nnz, gA_vals); SN_CHECK_LAUNCH("band_scatter_grad"); }

@@ -319,10 +319,10 @@ int sn_lr_tc_forward(const void* x, int64_t ldx, const void* left_bf16, const vo
             if (int rc = make_map_bf16(&mr, right_bf16, (uint64_t)rank, (uint64_t)in_dim, (uint64_t)in_dim, 128)) return rc;
             if (int rc = make_map_bf16(&ml, left_bf16, (uint64_t)out_dim, (uint64_t)rank, (uint64_t)rank, 128)) return rc;
             if (bm64) {
-                SN_CHECK_CUDA(cudaFuncSetAttribute(lr_tc_fwd_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LF_SMEM));
+                SN_SET_MAX_SMEM((int)LF_SMEM, lr_tc_fwd_fused_kernel<64>);
                 SN_LAUNCH("lr_tc_fwd_fused_kernel", st, lr_tc_fwd_fused_kernel<64><<<(unsigned)((B + 63) / 64), LF_THREADS, LF_SMEM, st>>>(mx, mr, ml, bias, (bf16*)hidden, (bf16*)y, (long)ldy, (long)B, in_dim, out_dim));
             } else {
-                SN_CHECK_CUDA(cudaFuncSetAttribute(lr_tc_fwd_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LF_SMEM));
+                SN_SET_MAX_SMEM((int)LF_SMEM, lr_tc_fwd_fused_kernel<128>);
                 SN_LAUNCH("lr_tc_fwd_fused_kernel", st, lr_tc_fwd_fused_kernel<128><<<(unsigned)((B + 127) / 128), LF_THREADS, LF_SMEM, st>>>(mx, mr, ml, bias, (bf16*)hidden, (bf16*)y, (long)ldy, (long)B, in_dim, out_dim));
             }
             return 0;

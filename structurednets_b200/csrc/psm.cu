@@ -332,7 +332,7 @@ int sn_psm_forward(const sn_psm_factor* factors_host, int nf, const float* x, in
         if (int rc = pack_vals(factors_host[k].fwd, factors_host[k].vals, factors_host[k].val_fwd, st)) return rc;
     const size_t smem = (size_t)2 * ch.maxdim * NS * sizeof(float);
     SN_CHECK_ARG(smem <= 227 * 1024, "psm_forward: factor dimension %d does not fit in shared memory", ch.maxdim);
-    SN_CHECK_CUDA(cudaFuncSetAttribute(psm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SN_SET_MAX_SMEM((int)smem, psm_fwd_kernel);
     SN_LAUNCH("psm_fwd_kernel", st, psm_fwd_kernel<<<(unsigned)((B + NS - 1) / NS), PSM_THREADS, smem, st>>>(ch, x, ldx, y, ldy, bias, B, acts));
     return 0;
 }
@@ -355,12 +355,12 @@ int sn_psm_backward(const sn_psm_factor* factors_host, int nf, const float* x, i
     if (acts != nullptr) {
         const size_t smem = (size_t)2 * ch.maxdim * NS * sizeof(float);
         SN_CHECK_ARG(smem <= 227 * 1024, "psm_backward: factor dimension %d does not fit in shared memory", ch.maxdim);
-        SN_CHECK_CUDA(cudaFuncSetAttribute(psm_bwd_acts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SN_SET_MAX_SMEM((int)smem, psm_bwd_acts_kernel);
         SN_LAUNCH("psm_bwd_acts_kernel", st, psm_bwd_acts_kernel<<<(unsigned)((B + NS - 1) / NS), PSM_THREADS, smem, st>>>(ch, x, ldx, grad_y, ldgy, B, acts));
     } else {
         const size_t smem = (size_t)3 * ch.maxdim * NS * sizeof(float);
         SN_CHECK_ARG(smem <= 227 * 1024, "psm_backward: factor dimension %d does not fit in shared memory", ch.maxdim);
-        SN_CHECK_CUDA(cudaFuncSetAttribute(psm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SN_SET_MAX_SMEM((int)smem, psm_bwd_kernel);
         SN_LAUNCH("psm_bwd_kernel", st, psm_bwd_kernel<<<(unsigned)((B + NS - 1) / NS), PSM_THREADS, smem, st>>>(ch, x, ldx, grad_y, ldgy, B));
     }
     for (int k = 0; k < nf; ++k) {

@@ -897,7 +897,7 @@ static int launch_fwd(const sn_sss_plan* p, const Geom& g, const float* packed, 
     SN_CHECK_ARG(smem <= 227 * 1024, "sss_forward: stage dims need %zu bytes of shared memory (> 227 KB)", smem);
     static size_t configured = 0;
     if (smem > configured) {
-        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_fwd_kernel<PAIRS, RP4T, NSWPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SN_SET_MAX_SMEM((int)smem, sss_fwd_kernel<PAIRS, RP4T, NSWPT>);
         configured = smem;
     }
     long tile = (long)PAIRS * g.nsw;
@@ -970,8 +970,8 @@ int sn_sss_backward(const sn_sss_plan* p, const float* packed, const float* x, i
     SN_CHECK_ARG(smem <= 227 * 1024, "sss_backward: stage dims need %zu bytes of shared memory (> 227 KB)", smem);
     SN_CHECK_ARG(p->chunk_len_max <= 2 * BWD_CONS, "sss_backward: chunks of more than %d stages are not supported", 2 * BWD_CONS);
     const bool fast = p->rows_pad == 20 && p->k_pad == 28 && sm.nsp == 52 && g.nsw == 24;
-    SN_CHECK_CUDA(cudaFuncSetAttribute(sss_bwd_kernel<5, 7, 52>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SN_CHECK_CUDA(cudaFuncSetAttribute(sss_bwd_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SN_SET_MAX_SMEM(227 * 1024, sss_bwd_kernel<5, 7, 52>);
+    SN_SET_MAX_SMEM(227 * 1024, sss_bwd_kernel<0, 0, 0>);
     SN_CHECK_CUDA(cudaMemsetAsync(workspace, 0, sn_sss_backward_workspace_floats(p) * sizeof(float), st));
     long tile = (long)BWD_CONS * g.nsw;
     dim3 grid((unsigned)((B + tile - 1) / tile), 2);

@@ -3590,15 +3590,15 @@ int sn_sss_tc_build(const sn_sss_tc_plan* p, const float* params, float* coef, s
     float* SC = coef + (size_t)p->nchunks * WROWS * WCOLS;
     if (build_mode() == 2) {
         const size_t bsm = ((size_t)p->chunk_param_floats + 32) * sizeof(float);     // four contiguous list ranges, each with <= 3 floats of lead-in
-        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_buildm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+        SN_SET_MAX_SMEM((int)bsm, sss_tc_buildm_kernel);
         SN_LAUNCH("sss_tc_buildm_kernel", snb::as_stream(stream), sss_tc_buildm_kernel<<<dim3(p->nchunks, 2, BM_SPLIT), BM_THREADS, bsm, snb::as_stream(stream)>>>(p->stages, p->nb_states, p->chunks, params, W, SC, vg_of(p, coef), p->reserved[0]));
     } else if (use_quad_build()) {
         const size_t bsm = ((size_t)p->chunk_param_floats + B4_LPC * LMAX * 4) * sizeof(float);    // + the bank padding of the state matrices
-        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+        SN_SET_MAX_SMEM((int)bsm, sss_tc_build4_kernel);
         SN_LAUNCH("sss_tc_build4_kernel", snb::as_stream(stream), sss_tc_build4_kernel<<<dim3(p->nchunks, 2, B4_SPLIT), B4_THREADS, bsm, snb::as_stream(stream)>>>(p->stages, p->nb_states, p->chunks, params, W, SC));
     } else {
         const size_t bsm = (size_t)p->chunk_param_floats * sizeof(float);
-        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+        SN_SET_MAX_SMEM((int)bsm, sss_tc_build_kernel);
         SN_LAUNCH("sss_tc_build_kernel", snb::as_stream(stream), sss_tc_build_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, bsm, snb::as_stream(stream)>>>(p->stages, p->nb_states, p->chunks, params, W, SC));
     }
     // the chain tiles (tensor-core chunk scans of large batches) are packed by sn_sss_tc_forward, next to its local GEMM
@@ -3622,7 +3622,7 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
                          p->rows_aligned) ? 1 : 0;
     if (use_fused_forward(p, B)) {
         const int grid = ntiles < sm_count() ? ntiles : sm_count();
-        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_fwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F_SMEM));
+        SN_SET_MAX_SMEM((int)F_SMEM, sss_tc_fwd_fused_kernel);
         SN_LAUNCH("sss_tc_fwd_fused_kernel", st, sss_tc_fwd_fused_kernel<<<grid, F_THREADS, F_SMEM, st>>>(mx, mw, p->chunks, p->nchunks, (long)B, ntiles, SC, states, y, (long)ldy, bias, aligned));
         if (use_tc_chain(B, p->rows_aligned != 0)) {     // the backward's chain kernel reads the packed tiles
             float* CWp = const_cast<float*>(SC) + (size_t)p->nchunks * SCF;
@@ -3635,7 +3635,7 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
     SN_CHECK_ARG(rbuf != nullptr, "sss_tc_forward: rbuf is NULL");
     const long total = (long)ntiles * p->nchunks;
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_local_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G1_SMEM));
+    SN_SET_MAX_SMEM((int)G1_SMEM, sss_tc_local_gemm_kernel);
     CUtensorMap moy, mor;   // output boxes: Y [chunk][B][32], then R [chunk][B][16] and R' [chunk][B][16] back to back (chunk index nchunks + ch)
     {
         const uint64_t NBo = (uint64_t)p->nchunks * B;
@@ -3679,7 +3679,7 @@ int sn_sss_tc_forward(const sn_sss_tc_plan* p, const float* coef, const float* x
         SN_CHECK_ARG(2 * NB < 2147483647ULL, "sss_tc_forward: 2 * nchunks * B exceeds the TMA coordinate range");
         if (int rc = make_map_f32(&mi, rbuf + NB * 32, 16, 2 * NB, 16, 128, 0, 0, false, 16)) return rc;   // R rows, then R' rows
         if (int rc = make_map_f32(&my, rbuf, 32, NB, 32, 128)) return rc;                                     // yloc / ytmp rows
-        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHF_SMEM));
+        SN_SET_MAX_SMEM((int)CHF_SMEM, sss_tc_chain_fwd_kernel);
         SN_LAUNCH("sss_tc_chain_fwd_kernel", st, sss_tc_chain_fwd_kernel<<<ntiles, CH_THREADS, CHF_SMEM, st>>>(mc, mi, my, p->chunks, p->nchunks, rbuf, states, y, (long)ldy, bias, (long)B, aligned));
         return 0;
     }
@@ -3722,7 +3722,7 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
         CUtensorMap mgy;
         if (int rc = make_map_f32(&mgy, grad_y, (uint64_t)p->output_dim, (uint64_t)B, (uint64_t)ldgy, 128)) return rc;
         if (int rc = make_map_f32(&mc, CW, 32, (uint64_t)p->nchunks * 4 * CW_ROWS, 32, 64)) return rc;   // state + grad_y sub-tiles only
-        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHB_SMEM));
+        SN_SET_MAX_SMEM((int)CHB_SMEM, sss_tc_chain_bwd_kernel);
         SN_LAUNCH("sss_tc_chain_bwd_kernel", st, sss_tc_chain_bwd_kernel<<<dim3((unsigned)((B + 127) / 128), 2), CHB_THREADS, CHB_SMEM, st>>>(mc, mgy, p->chunks, p->nchunks, L, grad_bias, (long)B));
         if (p->nchunks == 1 && grad_bias != nullptr)
             if (int rc = snb::colsum_accumulate(grad_y, ldgy, B, p->output_dim, grad_bias, st)) return rc;
@@ -3736,10 +3736,10 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
         const bool bias_fused = grad_bias != nullptr && sb_smem <= (deep ? 110 : 56) * 1024;
         bias_later = grad_bias != nullptr && !bias_fused;
         if (deep) {
-            SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_scan_bwd_m_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb_smem));
+            SN_SET_MAX_SMEM((int)sb_smem, sss_tc_scan_bwd_m_kernel<6>);
             SN_LAUNCH("sss_tc_scan_bwd_m_kernel", st, sss_tc_scan_bwd_m_kernel<6><<<dim3(2, nblk64), SM_THREADS, sb_smem, st>>>(p->chunks, p->nchunks, fs_of(p, coef), grad_y, (long)ldgy, L, bias_fused ? grad_bias : nullptr, (long)B));
         } else {
-            SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_scan_bwd_m_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb_smem));
+            SN_SET_MAX_SMEM((int)sb_smem, sss_tc_scan_bwd_m_kernel<3>);
             SN_LAUNCH("sss_tc_scan_bwd_m_kernel", st, sss_tc_scan_bwd_m_kernel<3><<<dim3(2, nblk64), SM_THREADS, sb_smem, st>>>(p->chunks, p->nchunks, fs_of(p, coef), grad_y, (long)ldgy, L, bias_fused ? grad_bias : nullptr, (long)B));
         }
     } else {
@@ -3792,7 +3792,7 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     const int g2grid = (int)(nitems < sm_count() ? nitems : sm_count());
     const size_t g2smem = G2_SMEM + (size_t)p->nchunks * sizeof(int4);
     SN_CHECK_ARG(g2smem <= 227 * 1024, "sss_tc_backward: too many chunks for the gradient GEMM's chunk table");
-    SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_grad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2smem));
+    SN_SET_MAX_SMEM((int)g2smem, sss_tc_grad_gemm_kernel);
     SN_LAUNCH("sss_tc_grad_gemm_kernel", st, sss_tc_grad_gemm_kernel<<<g2grid, G2_THREADS, g2smem, st>>>(mx, mg, ml, ms, p->chunks, p->nchunks, nranges, per, (long)B, dM));
     // small-batch path: the bias gradient (column sums of grad_y) runs on a second stream beside the build-backward kernel, which is
     // one latency-bound CTA per (chunk, direction, half) and leaves most of every SM idle.  (Beside the adjoint scans it slowed them
@@ -3815,18 +3815,18 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     const size_t bsmm = ((size_t)BWM_FIXED + p->chunk_param_floats + 32) * sizeof(float);
     if (build_mode() == 2 && bsmm <= 227 * 1024) {
         // needs the states the tensor-core build kernel of THIS forward left in coef (same build mode on both sides)
-        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_bwdm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmm));
+        SN_SET_MAX_SMEM((int)bsmm, sss_tc_build_bwdm_kernel);
         SN_LAUNCH("sss_tc_build_bwdm_kernel", st, sss_tc_build_bwdm_kernel<<<dim3(p->nchunks, 2, BM_SPLIT), BM_THREADS, bsmm, st>>>(p->stages, p->nb_states, p->chunks, params, dM, vg_of(p, coef), grad_params, p->reserved[0]));
         return join_bias();
     }
     const size_t bsm4 = ((size_t)BB4_FIXED + p->chunk_param_floats + B4_LPC * LMAX * 4) * sizeof(float);
     if (use_quad_build() && bsm4 <= 227 * 1024) {
-        SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm4));
+        SN_SET_MAX_SMEM((int)bsm4, sss_tc_build_bwd4_kernel);
         SN_LAUNCH("sss_tc_build_bwd4_kernel", st, sss_tc_build_bwd4_kernel<<<dim3(p->nchunks, 2, B4_SPLIT), B4_THREADS, bsm4, st>>>(p->stages, p->nb_states, p->chunks, params, dM, grad_params));
         return join_bias();
     }
     const size_t bsm = ((size_t)64 * DMC + p->chunk_param_floats) * sizeof(float);
-    SN_CHECK_CUDA(cudaFuncSetAttribute(sss_tc_build_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsm));
+    SN_SET_MAX_SMEM((int)bsm, sss_tc_build_bwd_kernel);
     SN_LAUNCH("sss_tc_build_bwd_kernel", st, sss_tc_build_bwd_kernel<<<dim3(p->nchunks, 2), BUILD_THREADS, bsm, st>>>(p->stages, p->nb_states, p->chunks, params, dM, scratch, grad_params));
     SN_LAUNCH("sss_tc_build_red_kernel", st, sss_tc_build_red_kernel<<<dim3(p->nchunks * LMAX, 2), BR_THREADS, 0, st>>>(p->stages, p->nb_states, p->chunks, scratch, grad_params));
     return join_bias();

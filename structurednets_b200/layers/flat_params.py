@@ -172,7 +172,13 @@ class FlatParamsMixin:
         views = self.__dict__["_flat_grad_views"]
         # sentinels: the first and the last parameter that TAKE a gradient (a frozen parameter's .grad stays None for ever; using it
         # as a sentinel would clear the buffer in every backward and lose gradient accumulation)
-        live = [i for i, p in enumerate(params) if p.requires_grad]
+        # (looked up once: walking the 3 501 parameters of an SSS layer in every backward cost 150 us of host time per step; the cached
+        # pair stays valid as long as both still take gradients)
+        live = self.__dict__.get("_flat_live_sentinels")
+        if live is None or len(live) != 2 or live[1] >= len(params) or not (params[live[0]].requires_grad and params[live[1]].requires_grad):
+            idx = [i for i, p in enumerate(params) if p.requires_grad]
+            live = (idx[0], idx[-1]) if idx else ()
+            self.__dict__["_flat_live_sentinels"] = live
         if live and (params[live[0]].grad is None or params[live[-1]].grad is None
                      or params[live[0]].grad.data_ptr() != views[live[0]].data_ptr()):
             g.zero_()
