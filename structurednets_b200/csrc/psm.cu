@@ -284,13 +284,14 @@ psm_rowcomb_kernel(const int* __restrict__ ptr, const int* __restrict__ idx, con
 __global__ void __launch_bounds__(256)
 psm_masked_dot_kernel(const int* __restrict__ row, const int* __restrict__ col, int nnz, const float* __restrict__ Lt, const float* __restrict__ Ht,
                       float* __restrict__ g, int width) {
+    if (Lt == nullptr) {       // first factor (L_0 = I): one THREAD per non-zero
+        const int e = blockIdx.x * blockDim.x + threadIdx.x;
+        if (e < nnz) g[e] += __ldg(Ht + (size_t)col[e] * width + row[e]);
+        return;
+    }
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= nnz) return;
     const int m = row[warp], j = col[warp];
-    if (Lt == nullptr) {
-        if (lane == 0) g[warp] += Ht[(size_t)j * width + m];
-        return;
-    }
     const float4* a = reinterpret_cast<const float4*>(Lt + (size_t)m * width);
     const float4* b = reinterpret_cast<const float4*>(Ht + (size_t)j * width);
     float acc = 0.f;
@@ -301,6 +302,78 @@ psm_masked_dot_kernel(const int* __restrict__ row, const int* __restrict__ col, 
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (lane == 0) g[warp] += acc;
+}
+
+// Backward of factor k >= 1 in one pass over its rows (CSR): CTA = row m of S_k, warp = some of the row's non-zeros (m, j).  Every H_k^T[j]
+// row is read ONCE and used twice: for the gradient of the non-zero, g[e] += < L_k^T[m], H_k^T[j] >, and for the next adjoint,
+// H_{k-1}^T[m] = sum_j S_k[m][j] H_k^T[j].  (psm_masked_dot_kernel + psm_rowcomb_kernel read it twice: 126 + 40 us per factor at C3.)
+// width <= 1024 floats (a lane holds 8 float4 of a row).
+constexpr int PBR_WARPS = 8;
+constexpr int PBR_NI = 8;
+template <bool DOT>        // DOT = false: only the row combination Hn[m] = sum_j S[m][j] Ht[j] (the forward's prefix products)
+__global__ void __launch_bounds__(PBR_WARPS * 32)
+psm_bwd_row_kernel(const int* __restrict__ ptr, const int* __restrict__ idx, const int* __restrict__ src, const float* __restrict__ vals,
+                   const float* __restrict__ Lt, const float* __restrict__ Ht, float* __restrict__ g, float* __restrict__ Hn, int width) {
+    __shared__ float4 part[PBR_WARPS][PBR_NI * 32];
+    const int r = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e0 = ptr[r], e1 = ptr[r + 1];
+    const int w4 = width >> 2;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 lt[PBR_NI], acc[PBR_NI];
+#pragma unroll
+    for (int i = 0; i < PBR_NI; ++i) {
+        const int c = lane + 32 * i;
+        lt[i] = (DOT && c < w4) ? __ldg(reinterpret_cast<const float4*>(Lt + (size_t)r * width) + c) : z;
+        acc[i] = z;
+    }
+    // the row of the warp's NEXT non-zero is requested before the current one is used (two rows in flight per warp)
+    float4 xn[PBR_NI];
+    int se_n = 0;
+    float v_n = 0.f;
+    auto fetch = [&](int e) {
+        if (e < e1) {
+            se_n = __ldg(src + e);
+            v_n = __ldg(vals + se_n);
+            const float4* hrow = reinterpret_cast<const float4*>(Ht + (size_t)__ldg(idx + e) * width);
+#pragma unroll
+            for (int i = 0; i < PBR_NI; ++i) {
+                const int c = lane + 32 * i;
+                xn[i] = (c < w4) ? __ldg(hrow + c) : z;
+            }
+        }
+    };
+    fetch(e0 + warp);
+    for (int e = e0 + warp; e < e1; e += PBR_WARPS) {
+        const int se = se_n;
+        const float v = v_n;
+        float4 x[PBR_NI];
+#pragma unroll
+        for (int i = 0; i < PBR_NI; ++i) x[i] = xn[i];
+        fetch(e + PBR_WARPS);
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < PBR_NI; ++i) {
+            acc[i].x = fmaf(v, x[i].x, acc[i].x); acc[i].y = fmaf(v, x[i].y, acc[i].y); acc[i].z = fmaf(v, x[i].z, acc[i].z); acc[i].w = fmaf(v, x[i].w, acc[i].w);
+            if (DOT) { dot = fmaf(lt[i].x, x[i].x, dot); dot = fmaf(lt[i].y, x[i].y, dot); dot = fmaf(lt[i].z, x[i].z, dot); dot = fmaf(lt[i].w, x[i].w, dot); }
+        }
+        if (DOT) {
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+            if (lane == 0 && g != nullptr) g[se] += dot;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PBR_NI; ++i) part[warp][lane + 32 * i] = acc[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < w4; c += PBR_WARPS * 32) {
+        float4 s4 = part[0][c];
+#pragma unroll
+        for (int w = 1; w < PBR_WARPS; ++w) {
+            const float4 p4 = part[w][c];
+            s4.x += p4.x; s4.y += p4.y; s4.z += p4.z; s4.w += p4.w;
+        }
+        reinterpret_cast<float4*>(Hn + (size_t)r * width)[c] = s4;
+    }
 }
 
 int check_dense_chain(const sn_psm_dense_factor* f, int nf, int in_dim, int out_dim) {
@@ -393,6 +466,7 @@ int sn_psm_dense_forward(const sn_psm_dense_factor* f, int nf, const float* x, i
     const float* prev = nullptr;
     for (int k = 0; k < nf; ++k) {
         // L_{k+1}^T = S_k^T L_k^T: the rows of S_k^T are the columns of S_k (csc)
+        // (the pipelined row kernel of the backward, without its dot products, is slower here: 45 vs 35 us per factor at C3)
         SN_LAUNCH("psm_rowcomb_kernel", st, psm_rowcomb_kernel<<<f[k].cols, 256, 0, st>>>(f[k].csc_ptr, f[k].csc_idx, f[k].csc_src, f[k].vals, prev, cur, out_dim));
         prev = cur;
         cur += (size_t)f[k].cols * out_dim;
@@ -429,8 +503,16 @@ int sn_psm_dense_backward(const sn_psm_dense_factor* f, int nf, const float* x, 
     for (int k = 0; k < nf; ++k) off[k + 1] = off[k] + (size_t)f[k].cols * out_dim;
     for (int k = nf - 1; k >= 0; --k) {
         const float* Lt = k == 0 ? nullptr : prefix + off[k - 1];
+        if (k > 0 && out_dim <= 4 * 32 * PBR_NI) {
+            // gradient of the factor's non-zeros and the next adjoint H_{k-1}^T = S_k H_k^T [rows_k][out_dim] in one pass over H_k^T
+            float* Hn = Ht + (size_t)f[k].cols * out_dim;
+            SN_LAUNCH("psm_bwd_row_kernel", st, psm_bwd_row_kernel<true><<<f[k].rows, PBR_WARPS * 32, 0, st>>>(f[k].csr_ptr, f[k].csr_idx, f[k].csr_src, f[k].vals, Lt, Ht,
+                                                                                                       f[k].grad_vals, Hn, out_dim));
+            Ht = Hn;
+            continue;
+        }
         if (f[k].nnz > 0 && f[k].grad_vals != nullptr)
-            SN_LAUNCH("psm_masked_dot_kernel", st, psm_masked_dot_kernel<<<(unsigned)(((size_t)f[k].nnz * 32 + 255) / 256), 256, 0, st>>>(
+            SN_LAUNCH("psm_masked_dot_kernel", st, psm_masked_dot_kernel<<<(unsigned)(((size_t)f[k].nnz * (Lt == nullptr ? 1 : 32) + 255) / 256), 256, 0, st>>>(
                 f[k].coo_row, f[k].coo_col, f[k].nnz, Lt, Ht, f[k].grad_vals, out_dim));
         if (k > 0) {
             float* Hn = Ht + (size_t)f[k].cols * out_dim;   // H_{k-1}^T = S_k H_k^T: [rows_k][out_dim]
