@@ -179,8 +179,8 @@ int sn_hmat_backward(const int32_t* leaves, int nleaves, const float* params, co
 /* Dense-block path (default for layers whose dense matrix fits): W = the H-matrix as a dense (out_dim x in_dim) matrix built from
  * the leaves (max_rows = the tallest leaf), applied / differentiated with sn_dense_apply / sn_dense_weight_grad on the tensor cores,
  * and the dense gradient projected back onto the leaf factors (accumulated into grad_params). */
-int sn_hmat_build_dense(const int32_t* leaves, int nleaves, int max_rows, const float* params, float* W, int out_dim, int in_dim,
-                        sn_stream_t stream);
+int sn_hmat_build_dense(const int32_t* leaves, int nleaves, int max_rows, const int32_t* slabs /* nullable: work list, see below */, int nslabs,
+                        const float* params, float* W, int out_dim, int in_dim, sn_stream_t stream);
 int sn_hmat_project_grad(const int32_t* leaves, int nleaves, const int32_t* slabs /* (leaf, first row) per 32 rows of every leaf */, int nslabs,
                          const float* params, const float* dW, int out_dim, int in_dim, float* grad_params, sn_stream_t stream);
 

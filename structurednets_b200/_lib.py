@@ -99,7 +99,7 @@ def _declare(lib):
     lib.sn_hmat_backward.restype = c_int
     lib.sn_hmat_backward.argtypes = [vp, i32, vp, vp, i64, vp, i64, vp, vp, i64, i32, i32, vp]
     lib.sn_hmat_build_dense.restype = c_int
-    lib.sn_hmat_build_dense.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp]
+    lib.sn_hmat_build_dense.argtypes = [vp, i32, i32, vp, i32, vp, vp, i32, i32, vp]
     lib.sn_hmat_project_grad.restype = c_int
     lib.sn_hmat_project_grad.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, vp, vp]
     PF = POINTER(SnPsmFactor)

@@ -161,11 +161,15 @@ size_t hm_smem(int in_dim, int out_dim, bool bwd) {
 // ------------------------------------------------------------------------------------------
 constexpr int HD_THREADS = 256;
 constexpr int HD_ROWS = 32;   // rows of a leaf handled by one CTA of the build kernel
+constexpr int HP_SLAB = 32;   // ... and of the gradient projection (same work list)
 
 __global__ void __launch_bounds__(HD_THREADS)
-hmat_build_dense_kernel(const Leaf* __restrict__ leaves, const float* __restrict__ params, float* __restrict__ W, int ldw) {
-    const Leaf lf = leaves[blockIdx.x];
-    const int r0 = blockIdx.y * HD_ROWS;
+hmat_build_dense_kernel(const Leaf* __restrict__ leaves, const int2* __restrict__ slabs, const float* __restrict__ params, float* __restrict__ W, int ldw) {
+    // slabs (the work list of the gradient projection: (leaf, first row) per 32 rows): one CTA per slab.  Without it the grid is
+    // (leaves, slabs of the tallest leaf) and nearly all of its CTAs exit at once -- 20 480 CTAs for 2 887 slabs at C4-H, 53 us.
+    const int2 sl = slabs != nullptr ? slabs[blockIdx.x] : make_int2((int)blockIdx.x, (int)blockIdx.y * HD_ROWS);
+    const Leaf lf = leaves[sl.x];
+    const int r0 = sl.y;
     if (r0 >= lf.rows) return;
     const int nr = min(HD_ROWS, lf.rows - r0);
     const float* L = params + lf.offL;    // rows x k
@@ -183,7 +187,6 @@ hmat_build_dense_kernel(const Leaf* __restrict__ leaves, const float* __restrict
 // blockIdx.y == 0: dL[i][k] += sum_j dW[i][j] R[k][j]   warp per row i, lanes along j, eight ranks k at a time in registers
 // blockIdx.y == 1: dR[k][j] += sum_i L[i][k] dW[i][j]   thread per column j over the slab's rows (eight loads in flight), atomics
 //                                                        across the slabs of a leaf
-constexpr int HP_SLAB = 32;
 __global__ void __launch_bounds__(HD_THREADS)
 hmat_project_grad_kernel(const Leaf* __restrict__ leaves, const int2* __restrict__ slabs, const float* __restrict__ params, const float* __restrict__ dW,
                          int ldw, float* __restrict__ gparams) {
@@ -305,14 +308,18 @@ int sn_hmat_backward(const int32_t* leaves, int nleaves, const float* params, co
 }
 
 // W[out_dim x in_dim] (row-major, dense) = the H-matrix (zero where no leaf with rank > 0 lives)
-int sn_hmat_build_dense(const int32_t* leaves, int nleaves, int max_rows, const float* params, float* W, int out_dim, int in_dim, sn_stream_t stream) {
+int sn_hmat_build_dense(const int32_t* leaves, int nleaves, int max_rows, const int32_t* slabs, int nslabs, const float* params, float* W, int out_dim, int in_dim,
+                        sn_stream_t stream) {
     SN_CHECK_ARG(W != nullptr && out_dim > 0 && in_dim > 0, "hmat_build_dense: bad arguments");
     cudaStream_t st = snb::as_stream(stream);
     SN_CHECK_CUDA(cudaMemsetAsync(W, 0, (size_t)out_dim * in_dim * sizeof(float), st));
     if (nleaves <= 0) return 0;
     SN_CHECK_ARG(leaves && params && max_rows > 0, "hmat_build_dense: NULL buffer");
-    dim3 grid(nleaves, snb::ceil_div(max_rows, HD_ROWS));
-    SN_LAUNCH("hmat_build_dense_kernel", st, hmat_build_dense_kernel<<<grid, HD_THREADS, 0, st>>>(reinterpret_cast<const Leaf*>(leaves), params, W, in_dim));
+    static_assert(HD_ROWS == HP_SLAB, "the build kernel walks the projection's slab list");
+    const bool listed = slabs != nullptr && nslabs > 0;
+    dim3 grid(listed ? nslabs : nleaves, listed ? 1 : snb::ceil_div(max_rows, HD_ROWS));
+    SN_LAUNCH("hmat_build_dense_kernel", st, hmat_build_dense_kernel<<<grid, HD_THREADS, 0, st>>>(reinterpret_cast<const Leaf*>(leaves),
+                                                                                                  listed ? reinterpret_cast<const int2*>(slabs) : nullptr, params, W, in_dim));
     return 0;
 }
 // grad_params (flat, accumulated) += the dense block gradients dW projected onto the leaf factors.  slabs: device int32 pairs

@@ -63,8 +63,9 @@ class _HMatDenseFunction(torch.autograd.Function):
         table = layer._leaf_table(U.device)
         flat = layer.flat_parameters()
         W = layer._dense_buffer("_dev_W", U.device)
-        _lib.check(L.sn_hmat_build_dense(_lib.ptr(table), layer._nleaves, layer._max_leaf_rows, _lib.ptr(flat), _lib.ptr(W), layer.output_dim,
-                                         layer.input_dim, _lib.stream_ptr()), "sn_hmat_build_dense")
+        slabs = layer._slab_table(U.device)
+        _lib.check(L.sn_hmat_build_dense(_lib.ptr(table), layer._nleaves, layer._max_leaf_rows, _lib.ptr(slabs), slabs.numel() // 2, _lib.ptr(flat),
+                                         _lib.ptr(W), layer.output_dim, layer.input_dim, _lib.stream_ptr()), "sn_hmat_build_dense")
         y = torch.empty((B, layer.output_dim), dtype=torch.float32, device=U.device)
         _lib.check(L.sn_dense_apply(_lib.ptr(W), layer.output_dim, layer.input_dim, _lib.ptr(U), U.stride(0), _lib.ptr(y), y.stride(0),
                                     _lib.ptr(layer.bias if layer.use_bias else None), B, _lib.stream_ptr()), "sn_dense_apply")
