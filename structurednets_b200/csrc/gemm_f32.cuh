@@ -112,12 +112,18 @@ inline int gemm_f32(bool ta, bool tb, int M, int N, int K, float alpha, const fl
             int ksplit = 1;
             if (accumulate) {
                 const int tiles = ceil_div(N, 128) * ceil_div(M, 128);
-                ksplit = ceil_div(2 * 148, tiles);
                 const int maxsplit = ceil_div(K, 256);
-                if (ksplit > maxsplit) ksplit = maxsplit;
-                const int minsplit = ceil_div(K, 2048);   // at most 2048 of K per CTA (4 accumulators x 512): bounds the truncation error
+                int minsplit = ceil_div(K, 2048);          // at most 2048 of K per CTA (4 accumulators x 512): bounds the truncation error
+                if (minsplit < 1) minsplit = 1;
+                // among the admissible splits the one with the fewest (waves of CTAs) x (K per CTA + the cost of one accumulating epilogue,
+                // charged as 128 of K): at one CTA per SM a grid of 3.46 waves costs four (C4-H's weight gradient: 128 tiles x 4 = 512 CTAs)
+                long best = -1;
+                for (int cand = minsplit; cand <= maxsplit && cand <= minsplit + 24; ++cand) {
+                    const long waves = ceil_div(tiles * cand, 148);
+                    const long cost = waves * (round_up(ceil_div(K, cand), 32) + 128);
+                    if (best < 0 || cost < best) { best = cost; ksplit = cand; }
+                }
                 if (ksplit < minsplit) ksplit = minsplit;
-                if (ksplit < 1) ksplit = 1;
             }
             // op(A) = A^T (ta) means A is stored [K][M] (MN-major); op(B) = B (!tb) means B is stored [K][N] (MN-major)
             if (!ta && tb) return t3::gemm_tf32x3_launch<false, false>(M, N, K, alpha, A, lda, B, ldb, C, ldc, bias, ksplit, accumulate, stream, kdev, mdev);
