@@ -77,6 +77,8 @@ class P2PAllReduce:
                 _lib.check(L.sn_p2p_import(ctypes.create_string_buffer(raw, 64), ctypes.byref(peer)), "p2p_import")
                 self._regions[r] = peer.value
                 self._imported.append(peer)
+        import atexit
+        atexit.register(self.close)      # a process that exits with its peers' regions still mapped can hang in the driver's teardown
 
     def close(self):
         """Collective: unmaps the peers' regions and frees the own one (also registered with atexit: a process must not exit with its
