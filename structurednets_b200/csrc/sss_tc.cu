@@ -1774,7 +1774,8 @@ sss_tc_scan_states_m_kernel(int nchunks, const float* __restrict__ FSall, const 
 // outputs y_j = yloc_j + O_j s_j + O'_j e_{j+1} + b, parallel over (sample, chunk): grid (ceil(B / (64 * QMO_SUB)), nchunks); a warp
 // walks QMO_SUB sub-tiles of 16 samples with the chunk's 16 B fragments (K = [s | e] = 32, N = 32 outputs) split once, in registers.
 constexpr int QMO_SUB = 2;
-constexpr int SCAN_CTAB = 256;               // chunks whose (row0, nrows) the adjoint scan keeps in shared memory
+constexpr int SCAN_CTAB = 128;               // chunks whose (row0, nrows) the adjoint scan keeps in shared memory (1 KB: four CTAs of
+                                             // 53 KB + this + 1 KB reserved still fit the SM's 228 KB)
 __global__ void __launch_bounds__(SM_THREADS)
 sss_tc_scan_out_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, const float* __restrict__ SCall, const float* __restrict__ rbuf,
                          const float* __restrict__ S, float* __restrict__ y, long ldy, const float* __restrict__ bias, long B) {
@@ -1888,10 +1889,11 @@ sss_tc_scan_bwd_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
     float* frag_ring = sb_smem;                                           // [QG_B][SB_FRAG_FLOATS]
     float* row_ring = sb_smem + (size_t)QG_B * SB_FRAG_FLOATS;            // [warp][QG_B][16][GROW]
     // grad_bias (may be NULL): the column sums of grad_y come from the rows this kernel stages anyway -- direction mu sums the chunks
-    // of its own parity, per CTA in shared memory [chunk][32], one global reduction per (chunk, column) and CTA at the end
+    // of its own parity.  A warp meets every chunk exactly once, so its sums go to a slot of its own, [warp][chunk / 2][32], with a plain
+    // store (shared-memory atomics of four warps on the same 32 words held 10 % of the kernel's samples at 65 536 samples); one
+    // global reduction per (chunk, column) and CTA at the end.
     float* bsum = row_ring + (size_t)(SM_THREADS / 32) * QG_B * 16 * GROW;
-    if (grad_bias != nullptr)
-        for (int i = threadIdx.x; i < nchunks * 32; i += SM_THREADS) bsum[i] = 0.f;
+    const int nhalf = (nchunks + 1) >> 1;
     __shared__ int2 ctab[SCAN_CTAB];       // (row0, nrows) per chunk: the grad_y addresses must not wait on a load of the chunk table
     for (int i = threadIdx.x; i < nchunks && i < SCAN_CTAB; i += SM_THREADS) ctab[i] = make_int2(chunks[i].row0, chunks[i].nrows);
     __syncthreads();
@@ -1946,7 +1948,7 @@ sss_tc_scan_bwd_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
             float cs = 0.f;
 #pragma unroll
             for (int r = 0; r < 16; ++r) cs += G[r * GROW + lane];
-            atomicAdd(bsum + j * 32 + lane, cs);
+            bsum[((size_t)(threadIdx.x >> 5) * nhalf + (j >> 1)) * 32 + lane] = cs;
         }
         Frag3 a[2], ag[4];
 #pragma unroll
@@ -1986,11 +1988,14 @@ sss_tc_scan_bwd_m_kernel(const sn_sss_tc_chunk* __restrict__ chunks, int nchunks
     cp_async_wait_all();
     if (grad_bias != nullptr) {
         __syncthreads();
-        for (int i = threadIdx.x; i < nchunks * 32; i += SM_THREADS) {
-            const int j = i >> 5, col = i & 31;
-            if ((j & 1) != mu) continue;
+        for (int i = threadIdx.x; i < nhalf * 32; i += SM_THREADS) {
+            const int j = 2 * (i >> 5) + mu, col = i & 31;
+            if (j >= nchunks) continue;
             const int2 c = j < SCAN_CTAB ? ctab[j] : make_int2(__ldg(&chunks[j].row0), __ldg(&chunks[j].nrows));
-            if (col < c.y) atomicAdd(grad_bias + c.x + col, bsum[i]);
+            float sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < SM_THREADS / 32; ++w) sum += bsum[(size_t)w * nhalf * 32 + i];
+            if (col < c.y) atomicAdd(grad_bias + c.x + col, sum);
         }
     }
 }
@@ -3718,7 +3723,6 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
     if (use_tc_chain(B, p->rows_aligned != 0)) {
         CUtensorMap mc;
         const float* CW = SC + (size_t)p->nchunks * SCF;
-        if (int rc = make_map_f32(&mc, CW, 32, (uint64_t)p->nchunks * 4 * CW_ROWS, 32, CW_ROWS)) return rc;
         CUtensorMap mgy;
         if (int rc = make_map_f32(&mgy, grad_y, (uint64_t)p->output_dim, (uint64_t)B, (uint64_t)ldgy, 128)) return rc;
         if (int rc = make_map_f32(&mc, CW, 32, (uint64_t)p->nchunks * 4 * CW_ROWS, 32, 64)) return rc;   // state + grad_y sub-tiles only
@@ -3732,7 +3736,7 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
         SN_CHECK_ARG((B + 63) / 64 <= 65535, "sss_tc_backward: batch too large for the adjoint scan's grid (4 193 280 samples)");
         const unsigned nblk64 = (unsigned)((B + 63) / 64);
         const bool deep = 2 * nblk64 <= 2u * (unsigned)sm_count();
-        const size_t sb_smem = sb_smem_bytes(deep ? 6 : 3) + (size_t)p->nchunks * 32 * sizeof(float);
+        const size_t sb_smem = sb_smem_bytes(deep ? 6 : 3) + (size_t)(SM_THREADS / 32) * ((p->nchunks + 1) / 2) * 32 * sizeof(float);
         const bool bias_fused = grad_bias != nullptr && sb_smem <= (deep ? 110 : 56) * 1024;
         bias_later = grad_bias != nullptr && !bias_fused;
         if (deep) {
