@@ -79,6 +79,25 @@ def _identify_system(T_full: np.ndarray, dims_in, dims_out, statespace_dim: int,
     return MixedSystem(S)
 
 
+def _param_version(layer):
+    """Version counters that every way of updating the parameters bumps: the flat buffer's (FlatSGD / FlatAdam write it through the
+    library and bump it by hand) and those of the first and last parameter (the views do not share the buffer's counter; torch
+    optimizers update every parameter in place)."""
+    flat = layer.__dict__.get("_flat")
+    params = layer._flat_param_list()
+    return (flat._version if flat is not None else -1, params[0]._version if params else -1, params[-1]._version if params else -1)
+
+
+def _check_params_unchanged(ctx, layer):
+    """The kernels read the layer-wide coefficient / packed-parameter buffers and the CURRENT flat parameters in backward, not copies
+    saved per forward.  That is exact as long as the parameters are the ones the forward saw; an optimizer step (or any other in-place
+    write) between a forward and its backward would silently give gradients at the wrong point, so it raises like autograd does for
+    saved tensors that were modified in place."""
+    if _param_version(layer) != ctx.param_version:
+        raise RuntimeError("SSSLayer: the parameters were modified in place between this forward and its backward (an optimizer step or "
+                           "a parameter write after the forward); run backward before updating the parameters, or run the forward again")
+
+
 class _SSSFunction(torch.autograd.Function):
     """fwd: sn_sss_forward (saves chunk-entry state checkpoints); bwd: sn_sss_backward accumulating
     straight into the layer's flat gradient buffer (every ``p.grad`` is a view of it)."""
@@ -100,12 +119,14 @@ class _SSSFunction(torch.autograd.Function):
         _lib.check(rc, "sn_sss_forward")
         ctx.layer = layer
         ctx.plan = plan
+        ctx.param_version = _param_version(layer)
         ctx.save_for_backward(U, ckpt, packed)
         return y
 
     @staticmethod
     def backward(ctx, grad_y):
         layer, plan = ctx.layer, ctx.plan
+        _check_params_unchanged(ctx, layer)
         U, ckpt, packed = ctx.saved_tensors
         if ctx.needs_input_grad[0]:
             raise RuntimeError("SSSLayer: the SIMT kernels (layers outside the tensor-core path's limits) do not return the gradient "
@@ -145,6 +166,7 @@ class _SSSTCFunction(torch.autograd.Function):
         _lib.check(rc, "sn_sss_tc_forward")
         ctx.layer = layer
         ctx.tc = tc
+        ctx.param_version = _param_version(layer)
         if anchor is not None:
             ctx.save_for_backward(U, states)
         return y
@@ -152,6 +174,7 @@ class _SSSTCFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_y):
         layer, tc = ctx.layer, ctx.tc
+        _check_params_unchanged(ctx, layer)
         U, states = ctx.saved_tensors
         grad_x = torch.empty_like(U) if ctx.needs_input_grad[0] else None
         grad_y = grad_y.contiguous()

@@ -371,6 +371,7 @@ class FlatSGD:
             from structurednets_b200 import _lib
             _lib.check(_lib.lib().sn_flat_sgd(_lib.ptr(self.flat_p), _lib.ptr(self.flat_g), self.flat_p.numel(), float(self.lr), float(self.grad_scale),
                                               _lib.stream_ptr()), "sn_flat_sgd")
+            torch.autograd.graph.increment_version(self.flat_p)      # the kernel wrote the parameters behind autograd's back
         else:
             with torch.no_grad():
                 self.flat_p.add_(self.flat_g, alpha=-self.lr * self.grad_scale)
@@ -422,6 +423,7 @@ class FlatAdam(FlatSGD):
             _lib.check(_lib.lib().sn_flat_adam(_lib.ptr(self.flat_p), _lib.ptr(self.flat_g), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
                                                self.flat_p.numel(), float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
                                                float(self.grad_scale), _lib.ptr(self.step_dev), 0, _lib.stream_ptr()), "sn_flat_adam")
+            torch.autograd.graph.increment_version(self.flat_p)      # the kernel wrote the parameters behind autograd's back
         else:
             self.step_host += 1
             with torch.no_grad():

@@ -243,3 +243,23 @@ def test_forward_states_and_outputs_are_bitwise_reproducible(built_lib, monkeypa
         else:
             assert torch.equal(y, ref[0]), "y differs in repetition %d" % rep
             assert torch.equal(states, ref[1]), "saved states differ in repetition %d" % rep
+
+
+@pytest.mark.parametrize("path", ["tc", "simt"])
+def test_backward_after_a_parameter_update_raises(built_lib, monkeypatch, path):
+    """The backward reads layer-wide buffers and the current parameters: an in-place parameter write between a forward and its backward
+    must raise instead of returning gradients at the wrong point; the ordinary order (and gradient accumulation over two forwards) must not."""
+    monkeypatch.setenv("SNB200_SSS_PATH", path)
+    layer, X = make_tc(TC_CASES[2])
+    layer = layer.to("cuda")
+    x = torch.tensor(X, device="cuda")
+    y1 = layer(x)
+    y2 = layer(x)
+    y1.sum().backward()
+    y2.sum().backward()          # two forwards, two backwards, no update in between: fine
+    y3 = layer(x)
+    with torch.no_grad():
+        layer.bias.add_(1.0)     # what an optimizer step does
+    with pytest.raises(RuntimeError, match="modified in place"):
+        y3.sum().backward()
+    layer(x).sum().backward()    # a fresh forward works again
