@@ -108,7 +108,12 @@ int sn_sss_backward(const sn_sss_plan* plan_host, const float* packed, const flo
  * The stages are grouped into chunks of consecutive stages (<= 32 outputs, <= 160 inputs, <= 16 stages); the chunk
  * matrices are rebuilt from the flat parameters by sn_sss_tc_build (call once per parameter update).
  * `stages` is the same device table as sn_sss_plan.stages.  coef must be zero-initialised once by the caller
- * (padding entries are never written).
+ * (padding entries are never written).  coef is owned by the caller and shared by the three calls: sn_sss_tc_build writes the
+ * chunk matrices and the states of their construction, sn_sss_tc_forward adds the scans' coefficient tiles (packed on an auxiliary
+ * stream beside its first GEMM), sn_sss_tc_backward reads all of them -- so a backward must see the coef (and params) of its own
+ * forward: call build + forward again after a parameter update before calling backward.
+ * Kernels: chunk-matrix construction and its backward, chunk scans: warp-level tensor cores (mma.sync tf32); the two batch GEMMs and
+ * the optional chain-scan kernels: tcgen05 / TMEM / TMA.
  * ------------------------------------------------------------------------------------------ */
 #define SN_SSS_TC_DS 16
 #define SN_SSS_TC_PO 32
