@@ -3735,17 +3735,26 @@ int sn_sss_tc_backward(const sn_sss_tc_plan* p, const float* params, const float
         // per-CTA sums do not fit two CTAs per SM take the separate column-sum kernel beside the build-backward kernel instead
         SN_CHECK_ARG((B + 63) / 64 <= 65535, "sss_tc_backward: batch too large for the adjoint scan's grid (4 193 280 samples)");
         const unsigned nblk64 = (unsigned)((B + 63) / 64);
-        const bool deep = 2 * nblk64 <= 2u * (unsigned)sm_count();
-        const size_t sb_smem = sb_smem_bytes(deep ? 6 : 3) + (size_t)(SM_THREADS / 32) * ((p->nchunks + 1) / 2) * 32 * sizeof(float);
-        const bool bias_fused = grad_bias != nullptr && sb_smem <= (deep ? 110 : 56) * 1024;
-        bias_later = grad_bias != nullptr && !bias_fused;
-        if (deep) {
-            SN_SET_MAX_SMEM((int)sb_smem, sss_tc_scan_bwd_m_kernel<6>);
-            SN_LAUNCH("sss_tc_scan_bwd_m_kernel", st, sss_tc_scan_bwd_m_kernel<6><<<dim3(2, nblk64), SM_THREADS, sb_smem, st>>>(p->chunks, p->nchunks, fs_of(p, coef), grad_y, (long)ldgy, L, bias_fused ? grad_bias : nullptr, (long)B));
-        } else {
-            SN_SET_MAX_SMEM((int)sb_smem, sss_tc_scan_bwd_m_kernel<3>);
-            SN_LAUNCH("sss_tc_scan_bwd_m_kernel", st, sss_tc_scan_bwd_m_kernel<3><<<dim3(2, nblk64), SM_THREADS, sb_smem, st>>>(p->chunks, p->nchunks, fs_of(p, coef), grad_y, (long)ldgy, L, bias_fused ? grad_bias : nullptr, (long)B));
+        // ring depth: 6 while the batch is one wave of CTAs at two per SM, 3 above that (four CTAs per SM); SNB200_SSS_SCAN_RING=2|3|6 forces
+        // one (measurements: depth 2 = five CTAs per SM)
+        int ring = 2 * nblk64 <= 2u * (unsigned)sm_count() ? 6 : 3;
+        {
+            const char* e = getenv("SNB200_SSS_SCAN_RING");
+            if (e != nullptr && (e[0] == '2' || e[0] == '3' || e[0] == '6')) ring = e[0] - '0';
         }
+        const size_t sb_smem = sb_smem_bytes(ring) + (size_t)(SM_THREADS / 32) * ((p->nchunks + 1) / 2) * 32 * sizeof(float);
+        const bool bias_fused = grad_bias != nullptr && sb_smem <= (ring == 6 ? 110 : 56) * 1024;
+        bias_later = grad_bias != nullptr && !bias_fused;
+#define SN_SCAN_BWD(R)                                                                                                                  \
+        do {                                                                                                                            \
+            SN_SET_MAX_SMEM((int)sb_smem, sss_tc_scan_bwd_m_kernel<R>);                                                                 \
+            SN_LAUNCH("sss_tc_scan_bwd_m_kernel", st, sss_tc_scan_bwd_m_kernel<R><<<dim3(2, nblk64), SM_THREADS, sb_smem, st>>>(        \
+                p->chunks, p->nchunks, fs_of(p, coef), grad_y, (long)ldgy, L, bias_fused ? grad_bias : nullptr, (long)B));              \
+        } while (0)
+        if (ring == 6) SN_SCAN_BWD(6);
+        else if (ring == 3) SN_SCAN_BWD(3);
+        else SN_SCAN_BWD(2);
+#undef SN_SCAN_BWD
     } else {
         const int qs_threads = B <= 16384 ? 64 : QS_THREADS;
         const unsigned ydim = use_split_scans(B) ? 2u : 1u;
