@@ -33,7 +33,10 @@ def _worker(rank, world, port, out):
         for m in (sss, lr):
             g = m._prepare_grad_accumulation()
             g.copy_(torch.arange(g.numel(), dtype=torch.float32) * (rank + 1))
-        GradSynchronizer(model, scale=0.5)()
+        # p2p=True asks for the one-shot NVLink all-reduce; on CPU tensors / gloo it must fall back to the group's all_reduce
+        sync = GradSynchronizer(model, scale=0.5, p2p=True)
+        sync()
+        assert sync.transport == "gloo"
         total = sum(r + 1 for r in range(world))
         ok = True
         for m in (sss, lr):
